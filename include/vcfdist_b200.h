@@ -1,0 +1,188 @@
+/* vcfdist_b200 — C-ABI boundary of the B200-native precision/recall hot path.
+ *
+ * Replaces, for the reference TimD1/vcfdist v2.6.4, everything underneath
+ *
+ *     void precision_recall_threads_wrapper(
+ *             std::shared_ptr<superclusterData> clusterdata_ptr,
+ *             std::vector<std::vector<std::vector<int>>> sc_groups);
+ *                                   (decl src/dist.h:245-247, def src/dist.cpp:1656-1727,
+ *                                    called once from src/main.cpp:219)
+ *
+ * i.e. per supercluster: generate_ptrs_strs (src/dist.cpp:145-242), calc_prec_recall_aln
+ * (:251-443), calc_prec_recall_path (:486-834), get_prec_recall_path_sync (:842-999),
+ * the integer part of calc_prec_recall (:1005-1401) and wf_ed (:1406-1506).
+ *
+ * The reference has no FFI for this path; the seam is that one free function.  The
+ * host-side drop-in (vcfdist_b200/host/pr_dropin.cpp) keeps its exact signature,
+ * packs `superclusterData` into a `vd_batch_in`, calls vd_run() and scatters the
+ * integers back, evaluating the two float threshold tests (src/dist.cpp:465-467,
+ * :1293-1296, :1327-1328) on the host with the reference's own expression shapes.
+ *
+ * Conventions: plain pointers and sizes only; all buffers are caller-owned; every
+ * entry point returns 0 on success or a negative VD_E* code and never exits or
+ * throws.  There is no CPU fallback: without a CUDA device vd_create() fails.
+ */
+#ifndef VCFDIST_B200_H
+#define VCFDIST_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VD_ABI_VERSION 1
+
+/* variant types, identical to src/defs.h:31-35 */
+#define VD_TYPE_SUB 1
+#define VD_TYPE_INS 2
+#define VD_TYPE_DEL 3
+
+/* haplotype order inside a supercluster, and the four alignments (src/defs.h:101-104):
+ * alignment i aligns query hap (i>>1) against truth hap (i&1)                         */
+#define VD_HAP_Q1 0
+#define VD_HAP_Q2 1
+#define VD_HAP_T1 2
+#define VD_HAP_T2 3
+
+/* error codes */
+#define VD_OK            0
+#define VD_E_NODEVICE   -1   /* no CUDA device / wrong architecture                    */
+#define VD_E_CUDA       -2   /* a CUDA runtime call failed (see vd_last_error)         */
+#define VD_E_BADINPUT   -3   /* malformed batch (unsorted/overlapping variants, ...)   */
+#define VD_E_TOOLARGE   -4   /* a supercluster exceeds the supported matrix side       */
+#define VD_E_NOMEM      -5
+#define VD_E_ALIGN      -6   /* an alignment hit a fatal reference condition
+                                (src/dist.cpp:314, :440, :606, :644, :937)             */
+
+/* per-alignment status bits, vd_batch_out.status[4*sc + i] */
+#define VD_ST_TIE            0x0001u  /* a swap edge on a reachable optimal cell had more than one
+                                         equal-score source row: the reference's choice depends on
+                                         std::unordered_set iteration order (src/dist.cpp:347,376);
+                                         we pick the larger source row                           */
+#define VD_ST_WARN_REFED_NOTRUTH 0x0002u  /* WARN src/dist.cpp:1203-1206 */
+#define VD_ST_WARN_QED_NOQUERY   0x0004u  /* WARN src/dist.cpp:1207-1210 */
+#define VD_ST_WARN_QED_GT_REFED  0x0008u  /* WARN src/dist.cpp:1211-1214 */
+#define VD_ST_WARN_ZERO_REFED    0x0010u  /* WARN src/dist.cpp:1219-1223 (ref_ed forced to 1) */
+#define VD_ST_ERR_NO_POINTER     0x0100u  /* ERROR src/dist.cpp:937  */
+#define VD_ST_ERR_NO_SWAP_PRED   0x0200u  /* ERROR src/dist.cpp:606, :644 */
+#define VD_ST_ERR_UNFINISHED     0x0400u  /* ERROR src/dist.cpp:314, :440 */
+#define VD_ST_ERR_MASK           0xff00u
+
+/* vd_batch_out.assigned[] values */
+#define VD_ASSIGN_NONE    0   /* variant never visited: stays ERRTYPE_UN                  */
+#define VD_ASSIGN_REF_FP  1   /* passed while the path ran on the REF plane: FP, credit 0
+                                 (src/dist.cpp:1157-1168)                                 */
+#define VD_ASSIGN_SYNC    2   /* credited at a sync section (src/dist.cpp:1291-1353); the
+                                 host derives credit, TP/FP/FN from ref_ed and query_ed    */
+
+/* One batch of superclusters, in the compact form the reference's per-supercluster
+ * driver reads them (src/dist.cpp:1786-1822): the reference window plus the four
+ * haplotypes' variant lists.  Haplotype strings and the query<->ref / truth->ref
+ * pointer arrays of generate_ptrs_strs are expanded on the device.
+ *
+ * Variants of (supercluster s, hap h) are var_off[4*s+h] .. var_off[4*s+h+1]-1, h in
+ * VD_HAP_* order, sorted by position, non-overlapping, inside the window.             */
+typedef struct vd_batch_in {
+    int32_t        n_sc;
+    const int64_t *ref_off;     /* [n_sc+1] byte offsets into ref_seq; window s is
+                                   fasta[ctg][begs[s] .. ends[s]] inclusive (src/dist.cpp:163,232) */
+    const uint8_t *ref_seq;     /* FASTA bytes (upper-cased by src/fasta.h:19-20)                   */
+    const uint8_t *rplane_seq;  /* optional, may be NULL: the REF-plane string (= ref_q1 of
+                                   src/dist.cpp:1784-1792) when query-hap-1 REF alleles differ from
+                                   the FASTA; same offsets as ref_seq                                */
+    const int64_t *var_off;     /* [4*n_sc+1]                                                        */
+    const int32_t *var_pos;     /* [n_var] poss[v] - begs[s]                (src/dist.cpp:166,1076)  */
+    const int32_t *var_rlen;    /* [n_var] refs[v].size(): INS 0, SUB 1, DEL deleted length          */
+    const uint8_t *var_type;    /* [n_var] VD_TYPE_*                                                 */
+    const int64_t *alt_off;     /* [n_var+1] byte offsets into alt_seq                               */
+    const uint8_t *alt_seq;     /* alts[v] bytes (INS: inserted bases, SUB: one base, DEL: none)     */
+    const float   *var_qual;    /* [n_var] var_quals[v]; only query haps are read (:1163,:1287)      */
+    float          max_qual;    /* float(g.max_qual)                        (src/dist.cpp:1284)      */
+} vd_batch_in;
+
+/* Results.  Per-variant arrays are indexed [v] with v the batch-global variant index;
+ * each variant is written by exactly two alignments, one per phasing slot
+ * (src/dist.cpp:1037-1048): slot 0 = original phasing (Q1T1,Q2T2), slot 1 = swapped
+ * (Q1T2,Q2T1).  Element (slot, v) lives at [slot * n_var + v].                           */
+typedef struct vd_batch_out {
+    int32_t  *aln_score;       /* [4*n_sc] s[i]                         (src/dist.cpp:426)        */
+    uint8_t  *aln_end_plane;   /* [4*n_sc] 0 QUERY plane, 1 REF plane   (src/dist.cpp:436-440)    */
+    uint8_t  *aln_beg_plane;   /* [4*n_sc] plane of the path origin     (src/dist.cpp:811-814)    */
+    uint32_t *status;          /* [4*n_sc] VD_ST_* bits                                            */
+    uint8_t  *assigned;        /* [2*n_var] VD_ASSIGN_*                                            */
+    int32_t  *sync_group;      /* [2*n_var]                                                        */
+    int32_t  *ref_ed;          /* [2*n_var]                                                        */
+    int32_t  *query_ed;        /* [2*n_var]                                                        */
+    float    *callq;           /* [2*n_var] min var_qual over the section's query variants,
+                                  starting from max_qual (src/dist.cpp:1284-1288); for
+                                  VD_ASSIGN_REF_FP the variant's own quality (:1163)               */
+} vd_batch_out;
+
+/* counters of the last vd_run*/
+typedef struct vd_stats {
+    int64_t n_sc, n_var;
+    int64_t cells;            /* sum over alignments of (Lq+Lr)*Lt                  */
+    int64_t io_bytes;         /* algorithmic input+output bytes                        */
+    int64_t spill_bytes;      /* 3 B/cell for alignments whose flag matrices live in HBM           */
+    int64_t n_short, n_long;  /* alignments handled by the short / long kernels                    */
+    int64_t n_launches;       /* kernels launched                                                  */
+    int64_t h2d_bytes, d2h_bytes;
+    float   ms_total;         /* CUDA-event time of the whole call on the handle's stream          */
+    float   ms_short;         /* ... of the short-supercluster kernel                              */
+    float   ms_long_fwd, ms_long_bwd, ms_long_walk;
+    float   ms_plan;
+} vd_stats;
+
+/* Final per-variant / per-supercluster results in the reference's own terms
+ * (src/variant.h:49-60, src/cluster.h:36-42, src/defs.h:66-72, :131-134).              */
+typedef struct vd_final {
+    uint8_t *errtypes;     /* [2*n_var] ERRTYPE_TP 0 / FP 1 / FN 2 / UN 5                       */
+    float   *credit;       /* [2*n_var]                                                        */
+    float   *callq;        /* [2*n_var]                                                        */
+    int32_t *sync_group;   /* [2*n_var]                                                        */
+    int32_t *ref_ed;       /* [2*n_var]                                                        */
+    int32_t *query_ed;     /* [2*n_var]                                                        */
+    int32_t *sc_phase;     /* [n_sc] PHASE_ORIG 0 / SWAP 1 / NONE 2                            */
+    int32_t *orig_dist;    /* [n_sc] s[Q1T1]+s[Q2T2]                                           */
+    int32_t *swap_dist;    /* [n_sc] s[Q2T1]+s[Q1T2]                                           */
+} vd_final;
+
+/* Host-only float step: store_phase (src/dist.cpp:449-475) and the credit / TP-FP-FN
+ * decisions of calc_prec_recall (src/dist.cpp:1293-1352), evaluated with the reference's
+ * own expression shapes (float division, comparison against a double threshold) from the
+ * integers the device returned.  Needs no GPU.                                            */
+int  vd_finalize(const vd_batch_in *in, const vd_batch_out *out,
+                 double phase_threshold, double credit_threshold, vd_final *fin);
+
+typedef struct vd_handle vd_handle;
+
+int  vd_abi_version(void);
+
+/* One handle per GPU and per host thread; owns a stream, pinned staging buffers and HBM
+ * scratch.  `scratch_bytes` bounds the HBM used for spilled flag matrices (0 = default:
+ * 60 % of free memory), the analogue of the reference's --max-ram ladder
+ * (src/cluster.cpp:94-117, src/dist.cpp:1700-1721).                                      */
+int  vd_create(int device, int64_t scratch_bytes, vd_handle **out);
+void vd_destroy(vd_handle *h);
+
+/* Synchronous.  Host buffers in, host buffers out: H2D copy, kernels, D2H copy.          */
+int  vd_run(vd_handle *h, const vd_batch_in *in, vd_batch_out *out);
+
+/* Same computation with every pointer of `in` and `out` already resident in this GPU's
+ * HBM (n_var and the byte sizes are passed since the offsets live on the device).
+ * Asynchronous work is enqueued on the handle's stream and synchronised before return.   */
+int  vd_run_device(vd_handle *h, const vd_batch_in *in_dev, vd_batch_out *out_dev,
+                   int64_t n_var, int64_t ref_bytes, int64_t alt_bytes);
+
+int  vd_get_stats(const vd_handle *h, vd_stats *out);
+const char *vd_last_error(const vd_handle *h);
+
+/* The handle's CUDA stream (a cudaStream_t), so that a caller can order its own work,
+ * e.g. torch.cuda.ExternalStream(vd_stream(h)).                                           */
+void *vd_stream(const vd_handle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
