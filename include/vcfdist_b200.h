@@ -67,6 +67,7 @@ extern "C" {
 #define VD_ST_ERR_NO_POINTER     0x0100u  /* ERROR src/dist.cpp:937  */
 #define VD_ST_ERR_NO_SWAP_PRED   0x0200u  /* ERROR src/dist.cpp:606, :644 */
 #define VD_ST_ERR_UNFINISHED     0x0400u  /* ERROR src/dist.cpp:314, :440 */
+#define VD_ST_ERR_BADINPUT       0x0800u  /* malformed supercluster (see VD_E_BADINPUT) */
 #define VD_ST_ERR_MASK           0xff00u
 
 /* vd_batch_out.assigned[] values */

@@ -1,0 +1,60 @@
+"""The C-ABI library: builds, loads, exports every symbol include/vcfdist_b200.h declares,
+and fails loudly (no CPU fallback) when there is no GPU.  No compute calls.  CPU only."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, has_gpu
+from vcfdist_b200 import capi
+from vcfdist_b200.batch import BatchBuilder, Out, TYPE_SUB
+
+
+def declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "vcfdist_b200.h")).read()
+    return sorted(set(re.findall(r"\b(vd_[a-z_]+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = capi.load_library()
+    syms = declared_symbols()
+    assert set(capi.EXPORTS) == set(syms)
+    for s in syms:
+        assert getattr(lib, s) is not None
+    assert lib.vd_abi_version() == 1
+
+
+def test_struct_layouts_match_header():
+    # 11 pointers/ints + float, 9 pointers, 9 pointers: the ctypes mirrors must have the C sizes
+    from vcfdist_b200.batch import vd_batch_in, vd_batch_out, vd_final, vd_stats
+    assert C.sizeof(vd_batch_in) == 8 + 10 * 8 + 8
+    assert C.sizeof(vd_batch_out) == 9 * 8
+    assert C.sizeof(vd_final) == 9 * 8
+    assert C.sizeof(vd_stats) == 10 * 8 + 6 * 4
+
+
+@pytest.mark.skipif(has_gpu(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback_without_gpu():
+    with pytest.raises(capi.VdError):
+        capi.Engine(0)
+
+
+def test_finalize_host_step():
+    """store_phase and the credit thresholds (src/dist.cpp:449-475, :1293-1352) from integers."""
+    bb = BatchBuilder(max_qual=60)
+    bb.add(b"ACGT", [[(1, TYPE_SUB, 1, b"T", 10.0)], [], [(1, TYPE_SUB, 1, b"T", 20.0)], []])
+    b = bb.build()
+    out = Out(b.n_sc, b.n_var)
+    out.aln_score[:4] = [0, 1, 1, 0]              # orig = 0, swap = 2 -> PHASE_ORIG
+    out.assigned[:] = [2, 2, 1, 2]                # slot0: q sync, t sync; slot1: q ref-FP, t sync
+    out.ref_ed[:] = [1, 1, 0, 3]
+    out.query_ed[:] = [0, 0, 0, 1]                # credit 1.0, 1.0, -, 1-1/3 = 0.667 < 0.7 -> FN
+    out.callq[:] = [10, 10, 10, 60]
+    out.sync_group[:] = [0, 0, 0, 0]
+    fin = capi.finalize(b, out).trimmed()
+    assert list(fin["sc_phase"]) == [0] and list(fin["orig_dist"]) == [0] and list(fin["swap_dist"]) == [2]
+    assert list(fin["errtypes"]) == [0, 0, 1, 2]
+    assert fin["credit"][3] == np.float32(1) - np.float32(1) / np.float32(3)
+    assert fin["callq"][3] == 60.0 and fin["callq"][2] == 10.0

@@ -1,0 +1,125 @@
+"""Parity of the CUDA path (through the C-ABI, vd_run with host buffers) against the oracle
+and the committed reference outputs.  Bit-exact: integer scores, planes, status bits, credit
+integers, the exact float minima, and after the host float step every reference field."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import FINAL_KEYS, OUT_KEYS, load_golden, mismatches, non_tie_var_mask
+from vcfdist_b200 import capi, synth
+from vcfdist_b200.batch import Batch, BatchBuilder, TYPE_DEL, TYPE_INS, TYPE_SUB
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine():
+    e = capi.Engine(0)
+    yield e
+    e.close()
+
+
+def forced_engine(cls):
+    os.environ["VD_FORCE_CLASS"] = str(cls)
+    try:
+        return capi.Engine(0)
+    finally:
+        del os.environ["VD_FORCE_CLASS"]
+
+
+def check_vs_oracle(engine, b):
+    got = engine.run(b)
+    want = capi.oracle_run(b)
+    assert mismatches(got.trimmed(), want.trimmed(), OUT_KEYS) == {}
+    return got
+
+
+@pytest.mark.parametrize("name", ["demo", "adv_11", "adv_12", "sv_21"])
+def test_golden_through_c_abi(engine, name):
+    b, refA, refB = load_golden(name)
+    got = check_vs_oracle(engine, b)
+    fin = capi.finalize(b, got).trimmed()
+    assert mismatches(fin, refB, FINAL_KEYS) == {}
+    mask, _ = non_tie_var_mask(b, got.status)
+    assert mismatches(fin, refA, FINAL_KEYS, var_mask=mask) == {}
+
+
+@pytest.mark.parametrize("cls", [1, 2])
+@pytest.mark.parametrize("name", ["demo", "adv_11", "sv_21"])
+def test_every_kernel_family_on_golden(name, cls):
+    """Force all superclusters through the wavefront (1) or scalar-slab (2) kernels."""
+    b, _, refB = load_golden(name)
+    e = forced_engine(cls)
+    got = check_vs_oracle(e, b)
+    assert mismatches(capi.finalize(b, got).trimmed(), refB, FINAL_KEYS) == {}
+    e.close()
+
+
+@pytest.mark.parametrize("seed", [201, 202, 203])
+def test_adversarial_seeds(engine, seed):
+    check_vs_oracle(engine, synth.adversarial(seed, 800, max_len=20 + 15 * (seed - 200)))
+
+
+def test_wgs_like_mixture(engine):
+    b = synth.wgs_like(5, 20000, sv_frac=0.003, sv_max=1500)
+    got = check_vs_oracle(engine, b)
+    st = engine.stats()
+    assert st["cells"] == int(b.cells().sum())
+    assert st["n_short"] + st["n_long"] == 4 * b.n_sc
+
+
+@pytest.mark.parametrize("length", [70, 300, 1200])
+def test_sv_lengths(engine, length):
+    check_vs_oracle(engine, synth.sv_pairs(3, 3, length, divergence=0.03))
+
+
+def test_edge_cases(engine):
+    bb = BatchBuilder()
+    # no variants at all (window of one base and of several)
+    bb.add(b"A", [[], [], [], []])
+    bb.add(b"ACGTAC", [[], [], [], []])
+    # truth only / query only
+    bb.add(b"ACGTAC", [[], [], [(2, TYPE_SUB, 1, b"T", 30.0)], []])
+    bb.add(b"ACGTAC", [[(2, TYPE_SUB, 1, b"T", 30.0)], [], [], []])
+    # INS followed by DEL at the same position (a split CPX), deletion up to the last base but one
+    bb.add(b"ACGTACGT", [[(2, TYPE_INS, 0, b"TT", 20.0), (2, TYPE_DEL, 3, b"", 20.0)], [],
+                         [(2, TYPE_INS, 0, b"TT", 25.0), (2, TYPE_DEL, 3, b"", 25.0)], []])
+    # same allele, different representation in a homopolymer
+    bb.add(b"CAAAAAT", [[(1, TYPE_DEL, 1, b"", 12.0)], [], [(4, TYPE_DEL, 1, b"", 40.0)], []])
+    # swapped phasing
+    bb.add(b"ACGTACGTAC", [[(6, TYPE_SUB, 1, b"A", 9.0)], [(2, TYPE_SUB, 1, b"T", 8.0)],
+                           [(2, TYPE_SUB, 1, b"T", 30.0)], [(6, TYPE_SUB, 1, b"A", 30.0)]])
+    b = bb.build()
+    check_vs_oracle(engine, b)
+
+
+def test_empty_batch(engine):
+    b = BatchBuilder().build()
+    out = engine.run(b)
+    assert out.n_sc == 0
+
+
+def test_malformed_input_is_reported(engine):
+    bb = BatchBuilder()
+    bb.add(b"ACGTAC", [[(4, TYPE_SUB, 1, b"T", 30.0), (2, TYPE_SUB, 1, b"G", 30.0)], [], [], []])   # unsorted
+    with pytest.raises(capi.VdError) as ei:
+        engine.run(bb.build())
+    assert ei.value.code == -3
+
+
+def test_idempotent_and_order_independent(engine):
+    """Size-independent properties: same results on a second run, and per-supercluster results do
+    not depend on batch order (superclusters are independent units)."""
+    b = synth.wgs_like(9, 5000, sv_frac=0.002, sv_max=800)
+    a1 = engine.run(b).trimmed()
+    a2 = engine.run(b).trimmed()
+    assert mismatches(a1, a2, OUT_KEYS) == {}
+    perm = np.random.default_rng(1).permutation(b.n_sc)
+    bp = b.take(perm)
+    ap = engine.run(bp).trimmed()
+    assert (ap["aln_score"].reshape(-1, 4) == a1["aln_score"].reshape(-1, 4)[perm]).all()
+    vidx = b.var_index_of(perm)
+    for k in ("assigned", "sync_group", "ref_ed", "query_ed", "callq"):
+        x = a1[k].reshape(2, -1)[:, vidx]
+        assert (ap[k].reshape(2, -1) == x).all(), k

@@ -1,0 +1,64 @@
+// Shared definitions of the sm_100a precision/recall kernels.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "vcfdist_b200.h"
+
+namespace vd {
+
+typedef uint8_t u8;
+typedef uint16_t u16;
+typedef uint32_t u32;
+
+// move flags, src/defs.h:110-120; bits 5 and 7 are ours
+constexpr int PTR_INS = 1, PTR_DEL = 2, PTR_MAT = 4, PTR_SUB = 8, PTR_SWP = 16;
+constexpr int F_SRC1 = 32;     // the chosen swap source is the second (larger-row) of the two
+constexpr int F_TIE = 128;     // both sources had the winning score (reference order-dependent)
+// pointer flags, src/defs.h:122-129
+constexpr int P_VARIANT = 1, P_VAR_BEG = 2, P_VAR_END = 4, P_INS_LOC = 8;
+
+constexpr int INF = 1 << 29;
+
+// device view of vd_batch_in (all pointers in HBM)
+struct BatchDev {
+    int n_sc;
+    const int64_t *ref_off;
+    const u8 *ref_seq;
+    const u8 *rplane_seq;     // never null on the device: aliases ref_seq when absent
+    const int64_t *var_off;
+    const int32_t *var_pos;
+    const int32_t *var_rlen;
+    const u8 *var_type;
+    const int64_t *alt_off;
+    const u8 *alt_seq;
+    const float *var_qual;
+    float max_qual;
+    int64_t n_var;
+};
+
+struct OutDev {
+    int32_t *aln_score;
+    u8 *aln_end_plane;
+    u8 *aln_beg_plane;
+    u32 *status;
+    u8 *assigned;
+    int32_t *sync_group;
+    int32_t *ref_ed;
+    int32_t *query_ed;
+    float *callq;
+};
+
+// classes decided by the plan kernel
+enum : int { CLS_TINY = 0, CLS_WAVE = 1, CLS_SCALAR = 2, CLS_BAD = 3 };
+
+// per-supercluster plan record
+struct ScPlan {
+    int32_t lr;          // window / REF-plane length
+    int32_t len[4];      // haplotype string lengths q1,q2,t1,t2
+    int32_t cls;
+};
+
+static __host__ __device__ inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace vd
