@@ -11,10 +11,13 @@ typedef uint8_t u8;
 typedef uint16_t u16;
 typedef uint32_t u32;
 
-// move flags, src/defs.h:110-120; bits 5 and 7 are ours
+// move flags of the backward pass / walk (path_ptrs), src/defs.h:110-120
 constexpr int PTR_INS = 1, PTR_DEL = 2, PTR_MAT = 4, PTR_SUB = 8, PTR_SWP = 16;
-constexpr int F_SRC1 = 32;     // the chosen swap source is the second (larger-row) of the two
-constexpr int F_TIE = 128;     // both sources had the winning score (reference order-dependent)
+// forward flag byte (aln_ptrs).  MAT and SUB share one bit: which one it is follows from
+// comparing the two bases again.  The freed bits hold the chosen swap source.
+constexpr int F_INS = 1, F_DEL = 2, F_DIAG = 4, F_SWP = 8;
+constexpr int F_TIE = 16;      // several sources had the winning score (reference order-dependent)
+constexpr int F_K_SHIFT = 5;   // bits 5-7: index of the chosen source in the row's source list
 // pointer flags, src/defs.h:122-129
 constexpr int P_VARIANT = 1, P_VAR_BEG = 2, P_VAR_END = 4, P_INS_LOC = 8;
 

@@ -15,7 +15,8 @@ constexpr int TINY_TPB = 128;          // threads per block = 32 superclusters
 constexpr int TINY_TL = 16;            // max haplotype length
 constexpr int TINY_TR = 12;            // max window (REF plane) length
 constexpr int TINY_CAP = 320;          // private shared-memory bytes per alignment
-constexpr int TINY_SC_BYTES = 16 * TINY_TL + 14 * TINY_TR + 8;   // per-supercluster shared area
+constexpr int TINY_SW = (TINY_TL + TINY_TR + 1 + 3) & ~3;      // one CSR swap table
+constexpr int TINY_SC_BYTES = 4 * (3 * TINY_TL + TINY_TR) + 2 * (2 * TINY_TR + 2 * TINY_SW) + TINY_TR + 8;   // per-supercluster shared area
 
 constexpr u32 ST_BAD = 0x0800u;        // VD_ST_ERR_BADINPUT
 
@@ -76,23 +77,21 @@ __global__ void plan_kernel(BatchDev in, ScPlan *plan, int *list, PlanCounters *
 
 // ---- fused tiny kernel --------------------------------------------------------------------
 // per-supercluster shared area (bytes): 4 x hap {str TL, flg TL, ptr TL, ins TR},
-// 2 x qmaps {rptr TR, rflg TR, toQ 2TL, toR 2TR}, rseq TR, hlen 4 x int16
+// 2 x qmaps {rptr TR, rflg TR, toQ SW, toR SW}, rseq TR, hlen 4 x int16
 struct TinyArea {
     u8 *base;
     __device__ u8 *str(int h) const { return base + h * (3 * TINY_TL + TINY_TR); }
     __device__ u8 *flg(int h) const { return str(h) + TINY_TL; }
     __device__ int8_t *ptr(int h) const { return (int8_t *)(str(h) + 2 * TINY_TL); }
     __device__ u8 *ins(int h) const { return str(h) + 3 * TINY_TL; }
-    __device__ u8 *qm(int qh) const { return base + 4 * (3 * TINY_TL + TINY_TR) + qh * (2 * TINY_TL + 4 * TINY_TR); }
+    __device__ u8 *qm(int qh) const { return base + 4 * (3 * TINY_TL + TINY_TR) + qh * (2 * TINY_TR + 2 * TINY_SW); }
     __device__ int8_t *rptr(int qh) const { return (int8_t *)qm(qh); }
     __device__ u8 *rflg(int qh) const { return qm(qh) + TINY_TR; }
     __device__ int8_t *toQ(int qh) const { return (int8_t *)(qm(qh) + 2 * TINY_TR); }
-    __device__ int8_t *toR(int qh) const { return (int8_t *)(qm(qh) + 2 * TINY_TR + 2 * TINY_TL); }
-    __device__ u8 *rseq() const { return base + 4 * (3 * TINY_TL + TINY_TR) + 2 * (2 * TINY_TL + 4 * TINY_TR); }
+    __device__ int8_t *toR(int qh) const { return (int8_t *)(qm(qh) + 2 * TINY_TR + TINY_SW); }
+    __device__ u8 *rseq() const { return base + 4 * (3 * TINY_TL + TINY_TR) + 2 * (2 * TINY_TR + 2 * TINY_SW); }
     __device__ short *hlen() const { return (short *)(rseq() + TINY_TR); }
 };
-static_assert(4 * (3 * TINY_TL + TINY_TR) + 2 * (2 * TINY_TL + 4 * TINY_TR) + TINY_TR + 8 <= TINY_SC_BYTES,
-              "tiny shared area too small");
 static_assert((TINY_TR % 2) == 0 && (TINY_SC_BYTES % 4) == 0, "alignment of the tiny shared area");
 
 __global__ void __launch_bounds__(TINY_TPB)
@@ -142,7 +141,7 @@ tiny_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan) {
 
     int score, end_plane;
     forward_scalar<SMemIL, 2, int8_t>(mem, L, q, qm, t, A.rseq(), lr, score, end_plane);
-    const int beg_plane = backward_scalar<SMemIL, 2, int8_t>(mem, L, q, qm, lr, t.len, end_plane, status);
+    const int beg_plane = backward_scalar<SMemIL, 2, int8_t>(mem, L, q, qm, t, A.rseq(), lr, end_plane, status);
     PFScalar<SMemIL> pfr{&mem, L.oPF, q.len + lr, q.len};
     walk_credit<SMemIL, 2, int8_t>(mem, L, pfr, q, qm, t, A.rseq(), lr, beg_plane, end_plane,
                                    in, out, sc, ai, status);
@@ -156,14 +155,14 @@ tiny_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan) {
 // Expanded supercluster in HBM (32-bit pointers).  Offsets relative to the entry's slab.
 struct SlabLayout {
     int64_t hap[4];      // str L | flg L | ins Lr | pad | ptr 4L
-    int64_t qm[2];       // rflg Lr | pad | rptr 4Lr | toQ 8Lq | toR 8Lr
+    int64_t qm[2];       // rflg Lr | pad | rptr 4Lr | toQ CSR 4(Lq+Lr+1) | toR CSR 4(Lq+Lr+1)
     int64_t rseq_unused;
     int64_t aln[4];      // scalar alignment scratch (make_layout<int64,4,false>) — slab path only
     int64_t total;
 };
 
 __host__ __device__ inline int64_t slab_hap_bytes(int L, int Lr) { return align_up(2 * (int64_t)L + Lr, 16) + 4 * (int64_t)align_up(L, 4); }
-__host__ __device__ inline int64_t slab_qm_bytes(int Lq, int Lr) { return align_up(Lr, 16) + 4 * (int64_t)align_up(Lr, 4) + 8 * (int64_t)Lq + 8 * (int64_t)Lr; }
+__host__ __device__ inline int64_t slab_qm_bytes(int Lq, int Lr) { return align_up(Lr, 16) + 4 * (int64_t)align_up(Lr, 4) + 8 * ((int64_t)Lq + Lr + 1); }
 
 __host__ __device__ inline SlabLayout make_slab(const ScPlan &p, bool with_scalar_aln) {
     SlabLayout s;
@@ -193,7 +192,7 @@ struct SlabQm {
         rflg = base;
         rptr = (int *)(base + align_up(Lr, 16));
         toQ = rptr + align_up(Lr, 4);
-        toR = toQ + 2 * (int64_t)Lq;
+        toR = toQ + ((int64_t)Lq + Lr + 1);
     }
 };
 
@@ -261,7 +260,7 @@ __global__ void slab_align_kernel(BatchDev in, OutDev out, const ScPlan *plan, c
     u32 status = 0;
     int score, end_plane;
     forward_scalar<GMem, 4, int>(mem, L, q, qm, t, rseq, p.lr, score, end_plane);
-    const int beg_plane = backward_scalar<GMem, 4, int>(mem, L, q, qm, p.lr, t.len, end_plane, status);
+    const int beg_plane = backward_scalar<GMem, 4, int>(mem, L, q, qm, t, rseq, p.lr, end_plane, status);
     PFScalar<GMem> pfr{&mem, L.oPF, q.len + p.lr, q.len};
     walk_credit<GMem, 4, int>(mem, L, pfr, q, qm, t, rseq, p.lr, beg_plane, end_plane, in, out, sc, ai, status);
     out.aln_score[4 * (int64_t)sc + ai] = score;

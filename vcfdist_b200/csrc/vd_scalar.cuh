@@ -61,8 +61,8 @@ template <class PT> struct Hap {
 template <class PT> struct QMaps {     // per query hap
     const PT *rptr;    // ref -> query pointers
     const u8 *rflg;    // ref -> query flags
-    const PT *toQ;     // [2*Lq] swap sources (REF rows) of QUERY-plane destination rows, -1 = none
-    const PT *toR;     // [2*Lr] swap sources (QUERY rows) of REF-plane destination rows
+    const PT *toQ;     // CSR [Lq+1 | <=Lr]: swap sources (REF rows) of QUERY-plane destination rows
+    const PT *toR;     // CSR [Lr+1 | <=Lq]: swap sources (QUERY rows) of REF-plane destination rows
 };
 
 // byte offsets of one alignment's private scratch
@@ -160,22 +160,30 @@ __device__ int expand_hap(const BatchDev &in, int sc, int h, u8 *str, u8 *flg, P
     return Q;
 }
 
-// swap-source table of one destination plane: for destination row a, the (at most two) rows
-// b of the other plane with src(b) && ptr[b]+1 == a (:335-337, :364-366), ascending.
-// Returns false when a row has more than two sources (not producible from a parsed VCF,
-// src/variant.cpp:852-861; such superclusters are rejected as VD_E_BADINPUT).
+// swap-source table of one destination plane, CSR: tab[0..ndst] = offsets, then the source
+// rows.  Sources of destination row a are the rows b of the other plane with src(b) and
+// ptr[b]+1 == a (:335-337, :364-366); ptr is non-decreasing in b, so they are contiguous and
+// ascending.  A base before an insertion plus the insertion's last base give two sources; k
+// back-to-back deletions give k+1.  The chosen source index is kept in 3 bits of the flag
+// byte, so more than SW_MAX sources per row are rejected (VD_E_BADINPUT).
+constexpr int SW_MAX = 8;
 template <class PT>
 __device__ bool build_swsrc(const PT *ptr, const u8 *flg, int nsrc, PT *tab, int ndst) {
-    for (int a = 0; a < 2 * ndst; a++) tab[a] = (PT)-1;
-    bool ok = true;
+    PT *off = tab, *src = tab + ndst + 1;
+    for (int a = 0; a <= ndst; a++) off[a] = 0;
+    int n = 0;
     for (int b = 0; b < nsrc; b++) {
         const int f = flg[b];
         if ((f & P_VARIANT) && !(f & P_VAR_END)) continue;
         const int d = (int)ptr[b] + 1;
         if (d < 0 || d >= ndst) continue;
-        if ((int)tab[2 * d] < 0) tab[2 * d] = (PT)b;
-        else if ((int)tab[2 * d + 1] < 0) tab[2 * d + 1] = (PT)b;
-        else ok = false;
+        off[d + 1] = (PT)((int)off[d + 1] + 1);
+        src[n++] = (PT)b;
+    }
+    bool ok = true;
+    for (int a = 0; a < ndst; a++) {
+        if ((int)off[a + 1] > SW_MAX) ok = false;
+        off[a + 1] = (PT)((int)off[a + 1] + (int)off[a]);
     }
     return ok;
 }
@@ -235,7 +243,7 @@ __device__ void forward_scalar(const Mem &mem, const AlnLayout<typename Mem::off
             const int a = P ? row - Lq : row;
             const int dprev = c > 0 ? V::ld(mem, oPrev, row) : INF;
             int d, f;
-            if (a == 0 && c == 0) { d = 0; f = PTR_MAT; }                                    // :299-305
+            if (a == 0 && c == 0) { d = 0; f = F_DIAG; }                                     // :299-305
             else {
                 const bool m = (P ? rseq[a] : q.str[a]) == tch;
                 const int diag = (a > 0 && c > 0) ? up_prev + (m ? 0 : 1) : INF;             // :324-332, :415-422
@@ -244,21 +252,21 @@ __device__ void forward_scalar(const Mem &mem, const AlnLayout<typename Mem::off
                 int swp = INF, sbits = 0;
                 if (tok && m) {                                                              // :334-349, :363-378
                     const PT *tab = P ? qm.toR : qm.toQ;
+                    const PT *src = tab + (P ? Lr : Lq) + 1;
                     const int ob = P ? 0 : Lq;
-                    const int s0 = tab[2 * a], s1 = tab[2 * a + 1];
-                    if (s0 >= 0) swp = V::ld(mem, oPrev, ob + s0);
-                    if (s1 >= 0) {
-                        const int v1 = V::ld(mem, oPrev, ob + s1);
-                        if (v1 < swp) { swp = v1; sbits = F_SRC1; }
-                        else if (v1 == swp) sbits = F_SRC1 | F_TIE;     // keep the larger row
+                    const int k0 = tab[a], k1 = tab[a + 1];
+                    for (int k = k0; k < k1; k++) {
+                        const int v = V::ld(mem, oPrev, ob + (int)src[k]);
+                        if (v < swp) { swp = v; sbits = (k - k0) << F_K_SHIFT; }
+                        else if (v == swp) sbits = ((k - k0) << F_K_SHIFT) | F_TIE;   // keep the larger row
                     }
                 }
                 d = min(min(diag, ins), min(del, swp));
                 f = 0;
-                if (diag == d) f |= m ? PTR_MAT : PTR_SUB;
-                if (ins == d) f |= PTR_INS;
-                if (del == d) f |= PTR_DEL;
-                if (swp == d) f |= PTR_SWP | sbits;
+                if (diag == d) f |= F_DIAG;
+                if (ins == d) f |= F_INS;
+                if (del == d) f |= F_DEL;
+                if (swp == d) f |= F_SWP | sbits;
             }
             V::st(mem, oCur, row, d);
             mem.st8(L.oF + (off_t)c * N + row, f);
@@ -278,11 +286,11 @@ __device__ void forward_scalar(const Mem &mem, const AlnLayout<typename Mem::off
 // ---------------------------------------------------------------------------------------
 template <class Mem, int W, class PT>
 __device__ int backward_scalar(const Mem &mem, const AlnLayout<typename Mem::off_t> &L,
-                               const Hap<PT> &q, const QMaps<PT> &qm, int Lr, int Lt,
-                               int end_plane, u32 &status) {
+                               const Hap<PT> &q, const QMaps<PT> &qm, const Hap<PT> &t,
+                               const u8 *rseq, int Lr, int end_plane, u32 &status) {
     typedef Val<Mem, W> V;
     typedef typename Mem::off_t off_t;
-    const int Lq = q.len, N = Lq + Lr;
+    const int Lq = q.len, Lt = t.len, N = Lq + Lr;
     off_t oCur = L.oT0, oNext = L.oT1;          // T of column c, and of column c-1 being built
     for (int r = 0; r < N; r++) V::st(mem, oCur, r, -1);
     {
@@ -305,19 +313,22 @@ __device__ int backward_scalar(const Mem &mem, const AlnLayout<typename Mem::off
             const int f = mem.ld8(L.oF + (off_t)c * N + row);
             int tp = 0;                                                                       // :572-574
             if (!P && a > 0) tp = ((int)q.ptr[a] != (int)q.ptr[a - 1] + 1) || (q.flg[a] & P_VAR_BEG);
-            if ((f & PTR_MAT) && a > 0 && c > 0) VD_RELAX(oNext, c - 1, row - 1, tx + tp, PTR_MAT);   // :556-595
-            if ((f & PTR_SWP) && a > 0 && c > 0) {                                            // :598-679
+            if ((f & F_DIAG) && a > 0 && c > 0) {                                              // :556-595, :692-731
+                const bool m = (P ? rseq[a] : q.str[a]) == t.str[c];
+                VD_RELAX(oNext, c - 1, row - 1, tx + tp, m ? PTR_MAT : PTR_SUB);
+            }
+            if ((f & F_SWP) && a > 0 && c > 0) {                                              // :598-679
                 const int of = P ? qm.rflg[a] : q.flg[a];
                 if (!(of & P_VARIANT) || (of & P_VAR_BEG)) {
                     const PT *tab = P ? qm.toR : qm.toQ;
-                    const int zrow = (P ? 0 : Lq) + (int)tab[2 * a + ((f & F_SRC1) ? 1 : 0)];
+                    const PT *src = tab + (P ? Lr : Lq) + 1;
+                    const int zrow = (P ? 0 : Lq) + (int)src[(int)tab[a] + (f >> F_K_SHIFT)];
                     if (f & F_TIE) status |= VD_ST_TIE;
                     VD_RELAX(oNext, c - 1, zrow, tx + (P ? 0 : tp), PTR_SWP);
                 }
             }
-            if ((f & PTR_SUB) && a > 0 && c > 0) VD_RELAX(oNext, c - 1, row - 1, tx + tp, PTR_SUB);   // :692-731
-            if ((f & PTR_INS) && a > 0) VD_RELAX(oCur, c, row - 1, tx + tp, PTR_INS);          // :734-771
-            if ((f & PTR_DEL) && c > 0) VD_RELAX(oNext, c - 1, row, tx, PTR_DEL);              // :774-804
+            if ((f & F_INS) && a > 0) VD_RELAX(oCur, c, row - 1, tx + tp, PTR_INS);            // :734-771
+            if ((f & F_DEL) && c > 0) VD_RELAX(oNext, c - 1, row, tx, PTR_DEL);                // :774-804
         }
         if (c > 0) { off_t x = oCur; oCur = oNext; oNext = x; }
     }
