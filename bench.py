@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""bench.py — DP Gcells/s and superclusters/s of the precision/recall hot path.
+
+A "step" is one pass of the whole hot path (plan, fused short-supercluster kernel, wavefront
+kernels for long superclusters, credit) over one batch of synthetic superclusters:
+
+  wgs     (default) BASELINE.json configs[2]: HG002-WGS-like small variants — 3.6 M superclusters
+          drawn with replacement (seeded) from the real HG002 chr1:1-5Mb demo batch in
+          tests/golden/demo.npz, i.e. the measured WGS length distribution
+  wgs_sv  configs[3]: the same plus an SV tail (0.3 % of superclusters carry one INS/DEL of
+          log-uniform length 50..10 kb)
+  chr20   configs[1]: 75 k superclusters
+
+  python bench.py --gpus N --steps K --warmup W           (torchrun for N > 1, one rank per GPU)
+  python bench.py --impl reference ...                    the reference's own CPU code on a
+                                                          bounded sample, all host threads
+
+value   = whole-job Gcells/s with inputs resident in HBM (vd_run_device), device-timed,
+          max over ranks; cells = sum over alignments of (Lq+Lr)*Lt
+e2e     = the same metric through the reference-facing C-ABI call vd_run() with pinned HOST
+          buffers: H2D of the batch and D2H of the results inside the timed region
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from vcfdist_b200 import capi, shard, synth  # noqa: E402
+from vcfdist_b200.batch import Batch, Out, vd_batch_in, vd_batch_out  # noqa: E402
+
+WORKLOADS = {
+    "wgs": dict(n_sc=3_600_000, sv_frac=0.0, config="HG002 WGS SNP+INDEL vs GIAB v4.2.1, 1xB200 (BASELINE configs[2])"),
+    "wgs_sv": dict(n_sc=3_600_000, sv_frac=0.003, config="HG002 WGS SNP+INDEL+SV to 10 Kb (BASELINE configs[3])"),
+    "chr20": dict(n_sc=75_000, sv_frac=0.0, config="HG002 chr20 SNP+INDEL (BASELINE configs[1])"),
+}
+
+
+def load_demo() -> Batch:
+    z = np.load(os.path.join(ROOT, "tests", "golden", "demo.npz"))
+    return Batch(ref_off=z["ref_off"], ref_seq=z["ref_seq"], var_off=z["var_off"], var_pos=z["var_pos"],
+                 var_rlen=z["var_rlen"], var_type=z["var_type"], alt_off=z["alt_off"], alt_seq=z["alt_seq"],
+                 var_qual=z["var_qual"], max_qual=float(z["max_qual"]))
+
+
+def make_workload(name: str, n_sc: int, seed: int, rank: int, world: int, sv_max: int):
+    """This rank's shard of the global batch (weak scaling: n_sc superclusters per GPU, so the
+    global batch has world*n_sc), partitioned by estimated cells (LPT).  Every rank derives the
+    same global index list; only its own shard is materialised."""
+    w = WORKLOADS[name]
+    demo = load_demo()
+    rng = np.random.default_rng(seed)
+    total = n_sc * world
+    pick = rng.integers(0, demo.n_sc, total)
+    base_cells = demo.cells()
+    cells = base_cells[pick]
+    n_svs = int(round(total * w["sv_frac"]))
+    sv = None
+    if n_svs:
+        sv = synth.wgs_like(seed + 1, n_svs, sv_frac=1.0, sv_max=sv_max)
+        cells = np.concatenate([cells[: total - n_svs], sv.cells()])
+    parts = shard.lpt_partition(cells, world) if world > 1 else [np.arange(total)]
+    mine = parts[rank]
+    small = mine[mine < total - n_svs]
+    big = mine[mine >= total - n_svs] - (total - n_svs)
+    pieces = [demo.take(pick[small])]
+    if n_svs and len(big):
+        pieces.append(sv.take(big))
+    b = Batch.concat(pieces) if len(pieces) > 1 else pieces[0]
+    return b, int(cells.sum()), total
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu: int):
+        self.gpu = gpu
+        self.rows = []
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def run_reference(args):
+    """The reference's own CPU implementation (oracle/_ref/libvdref.so = unmodified sources) of
+    the same path, all host threads, on a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    if not capi.reference_available(False):
+        # the C restatement stands in when the reference objects were not built
+        kind = "port"
+    else:
+        kind = "reference"
+    sample_n = args.ref_sample
+    b, cells, total = make_workload(args.workload, sample_n, args.seed, 0, 1, args.sv_max)
+    times = []
+    for i in range(args.warmup + args.steps):
+        if kind == "reference":
+            _, sec = capi.reference_run(b, canonical=False, threads=cores)
+        else:
+            t0 = time.perf_counter(); capi.oracle_run(b); sec = time.perf_counter() - t0
+            cores = 1
+        if i >= args.warmup:
+            times.append(sec)
+    sec = float(np.mean(times))
+    val = cells / sec / 1e9
+    line = {
+        "impl": "reference", "metric": "dp_gcells_per_s", "value": val, "unit": "Gcells/s",
+        "superclusters_per_s": b.n_sc / sec, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int32", "data": "synthetic",
+        "config": {"workload": WORKLOADS[args.workload]["config"], "n_superclusters_per_step": b.n_sc,
+                   "cells_per_step": cells},
+        "cpu_baseline": {"value": val, "unit": "Gcells/s", "cores": cores, "kind": kind,
+                         "sample": f"{b.n_sc} superclusters ({cells} cells) of the {args.workload} workload per step, "
+                                   f"timed inside precision_recall_threads_wrapper (-t {cores})"},
+        "e2e": {"value": val, "unit": "Gcells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="wgs", choices=sorted(WORKLOADS))
+    ap.add_argument("--n-sc", type=int, default=0, help="superclusters per GPU (default: the workload's)")
+    ap.add_argument("--sv-max", type=int, default=10000)
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--ref-sample", type=int, default=200_000, help="superclusters in the CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    n_sc = args.n_sc or WORKLOADS[args.workload]["n_sc"]
+    b, cells_total, sc_total = make_workload(args.workload, n_sc, args.seed, rank, world, args.sv_max)
+    n_var = b.n_var
+    eng = capi.Engine(local_rank)
+    stream = torch.cuda.ExternalStream(eng.stream, device=dev)
+
+    # ---- device-resident copies of the batch and result buffers (torch owns the HBM) ----
+    def dev_t(a):
+        return torch.from_numpy(a).to(dev)
+    d_in = {k: dev_t(getattr(b, k)) for k in ("ref_off", "ref_seq", "var_off", "var_pos", "var_rlen", "var_type",
+                                              "alt_off", "alt_seq", "var_qual")}
+    din = vd_batch_in()
+    din.n_sc = b.n_sc
+    for k, t in d_in.items():
+        setattr(din, k, t.data_ptr())
+    din.rplane_seq = None
+    din.max_qual = b.max_qual
+    a4, v2 = 4 * b.n_sc, max(2 * n_var, 1)
+    d_out = {"aln_score": torch.empty(a4, dtype=torch.int32, device=dev),
+             "aln_end_plane": torch.empty(a4, dtype=torch.uint8, device=dev),
+             "aln_beg_plane": torch.empty(a4, dtype=torch.uint8, device=dev),
+             "status": torch.empty(a4, dtype=torch.int32, device=dev),
+             "assigned": torch.empty(v2, dtype=torch.uint8, device=dev),
+             "sync_group": torch.empty(v2, dtype=torch.int32, device=dev),
+             "ref_ed": torch.empty(v2, dtype=torch.int32, device=dev),
+             "query_ed": torch.empty(v2, dtype=torch.int32, device=dev),
+             "callq": torch.empty(v2, dtype=torch.float32, device=dev)}
+    dout = vd_batch_out()
+    for k, t in d_out.items():
+        setattr(dout, k, t.data_ptr())
+    torch.cuda.synchronize()
+
+    mine_sc = mine_var = None
+    if world > 1:
+        # batch-global indices of this rank's records for the final all-gather: ranks own
+        # disjoint index ranges of the (virtual) global result arrays
+        cnt = torch.tensor([b.n_sc, n_var], dtype=torch.int64, device=dev)
+        allc = [torch.zeros(2, dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(allc, cnt)
+        allc = torch.stack(allc).cpu().numpy()
+        off_sc, off_var = int(allc[:rank, 0].sum()), int(allc[:rank, 1].sum())
+        tot_sc, tot_var = int(allc[:, 0].sum()), int(allc[:, 1].sum())
+        mine_sc = np.arange(off_sc, off_sc + b.n_sc)
+        mine_var = np.arange(off_var, off_var + n_var)
+
+    def step_resident():
+        eng.run_device(din, dout, n_var, b.ref_bytes, b.alt_bytes)
+        if world > 1:
+            with torch.cuda.stream(stream):
+                shard.gather_results(d_out, mine_sc, mine_var, tot_sc, tot_var, dist, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up, then EXACTLY K timed steps; device time, max over ranks ----
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = 0
+    ms_short = ms_fwd = ms_bwd = ms_walk = ms_plan = ms_kernels = 0.0
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step_resident()
+        st = eng.stats()
+        launches += st["n_launches"]
+        ms_short += st["ms_short"]; ms_fwd += st["ms_long_fwd"]; ms_bwd += st["ms_long_bwd"]
+        ms_walk += st["ms_long_walk"]; ms_plan += st["ms_plan"]; ms_kernels += st["ms_total"]
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    st = eng.stats()
+
+    # ---- e2e: vd_run() with pinned host buffers, H2D + D2H inside the timed region ----
+    def pin(a):
+        t_ = torch.from_numpy(a).pin_memory()
+        return t_, t_.numpy()
+    keep = []
+    hb = {}
+    for k in ("ref_off", "ref_seq", "var_off", "var_pos", "var_rlen", "var_type", "alt_off", "alt_seq", "var_qual"):
+        t_, a_ = pin(getattr(b, k)); keep.append(t_); hb[k] = a_
+    bp = Batch(**hb, max_qual=b.max_qual)
+    ho = Out(b.n_sc, n_var)
+    for f in Out.FIELDS:
+        t_, a_ = pin(getattr(ho, f)); keep.append(t_); setattr(ho, f, a_)
+    for _ in range(2):
+        eng.run(bp, ho)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(2, min(args.steps, 5))
+    for _ in range(e2e_steps):
+        eng.run(bp, ho)
+        launches_e2e = eng.stats()["n_launches"]
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    st_e = eng.stats()
+    te = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_ms = float(te.item())
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        ms_step = ms_max / args.steps
+        value = cells_total / (ms_step * 1e-3) / 1e9
+        # dominant kernel of this workload and its algorithmic bytes per launch:
+        # short regime -> tiny_kernel moves the compact batch in and the result records out;
+        # long regime  -> wave_fwd writes 1 B/cell of flags (+ the same io)
+        k_short, k_fwd, k_bwd = ms_short / args.steps, ms_fwd / args.steps, ms_bwd / args.steps
+        if k_fwd > k_short:
+            dom, dom_ms = "wave_fwd_kernel", k_fwd
+            alg_bytes = st["spill_bytes"] / 3.0
+        else:
+            dom, dom_ms = "tiny_kernel", k_short
+            alg_bytes = float(b.io_bytes())
+        achieved = alg_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+        line = {
+            "metric": "dp_gcells_per_s", "value": value, "unit": "Gcells/s",
+            "superclusters_per_s": sc_total / (ms_step * 1e-3),
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32", "data": "synthetic",
+            "config": {"workload": WORKLOADS[args.workload]["config"],
+                       "source": "superclusters resampled (seeded) from the real HG002 chr1:1-5Mb demo batch"
+                                 + (" + synthetic SV tail" if WORKLOADS[args.workload]["sv_frac"] else ""),
+                       "n_superclusters_per_step": sc_total, "cells_per_step": cells_total,
+                       "per_gpu_superclusters": b.n_sc, "parallelism": f"shard{world}+allgather" if world > 1 else "single",
+                       "l2": "inputs+outputs exceed L2 (no flush needed)" if b.io_bytes() > 200e6 else "small batch: L2-resident"},
+            "clocks": clocks,
+            "e2e": {"value": cells_total / (e2e_ms * 1e-3) / 1e9, "unit": "Gcells/s",
+                    "superclusters_per_s": sc_total / (e2e_ms * 1e-3), "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int(st_e["h2d_bytes"]), "d2h_bytes_per_step": int(st_e["d2h_bytes"]),
+                    "api": "vd_run (C-ABI, pinned host buffers)"},
+            "gpu_launches": int(launches),
+            "kernel_ms_per_step": {"plan": ms_plan / args.steps, "tiny": k_short, "wave_fwd": k_fwd, "wave_bwd": k_bwd,
+                                   "wave_walk": ms_walk / args.steps, "all_kernels": ms_kernels / args.steps},
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            cores = os.cpu_count() or 1
+            sb, scells, _ = make_workload(args.workload, args.ref_sample, args.seed, 0, 1, args.sv_max)
+            if capi.reference_available(False):
+                _, sec = capi.reference_run(sb, canonical=False, threads=cores)
+                kind = "reference"
+            else:
+                t0 = time.perf_counter(); capi.oracle_run(sb); sec = time.perf_counter() - t0
+                kind, cores = "port", 1
+            line["cpu_baseline"] = {"value": scells / sec / 1e9, "unit": "Gcells/s", "cores": cores, "kind": kind,
+                                    "superclusters_per_s": sb.n_sc / sec,
+                                    "sample": f"{sb.n_sc} superclusters ({scells} cells) of the same workload, one pass, "
+                                              f"reference std::thread ladder with -t {cores}"}
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

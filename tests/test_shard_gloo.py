@@ -1,0 +1,69 @@
+"""N>1 path on CPU: LPT partition by estimated cells, per-rank compute, one all-gather of the
+result records (gloo, world_size 2).  The oracle stands in for the GPU here (tests only)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import OUT_KEYS, ROOT, mismatches
+from vcfdist_b200 import capi, shard, synth
+
+
+def test_lpt_partition_balances_and_covers():
+    rng = np.random.default_rng(0)
+    cells = np.concatenate([rng.integers(50, 400, 20000), rng.integers(10**6, 10**8, 40)])
+    parts = shard.lpt_partition(cells, 8)
+    allidx = np.sort(np.concatenate(parts))
+    assert (allidx == np.arange(len(cells))).all()
+    loads = np.array([cells[p].sum() for p in parts], np.float64)
+    assert loads.max() / loads.mean() < 1.25
+    # deterministic
+    again = shard.lpt_partition(cells, 8)
+    assert all((a == b).all() for a, b in zip(parts, again))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    b = synth.wgs_like(3, 600, sv_frac=0.01, sv_max=300)
+    parts = shard.lpt_partition(b.cells(), world)
+    mine = parts[rank]
+    sub = b.take(mine)
+    out = capi.oracle_run(sub).trimmed()
+    full = shard.gather_results(out, mine, b.var_index_of(mine), b.n_sc, b.n_var, dist)
+    want = capi.oracle_run(b).trimmed()
+    got = {k: v.numpy() for k, v in full.items()}
+    got["status"] = got["status"].view(np.uint32)
+    q.put((rank, mismatches(got, want, OUT_KEYS)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_shard_and_gather_matches_single_pass():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, bad in res:
+        assert bad == {}, (rank, bad)

@@ -1,0 +1,131 @@
+"""Multi-GPU plumbing: superclusters are independent units (src/dist.cpp:1738-1903 touches only
+sc_idx-local state), so a batch is partitioned across ranks by estimated DP-cell count with no
+data-path collective, and the fixed-width result records are exchanged once at the end with a
+single all-gather (NCCL over NVLink on the GPU box, gloo in the CPU tests).
+
+The reference's analogue of the partition is the RAM/thread ladder (src/cluster.cpp:94-117,
+src/dist.cpp:1670-1721)."""
+from __future__ import annotations
+
+from typing import List, Sequence
+
+import numpy as np
+
+
+def lpt_partition(cells: np.ndarray, n_parts: int, exact_top: int = 4096) -> List[np.ndarray]:
+    """Longest-processing-time partition of item weights `cells` into `n_parts` index lists.
+    The `exact_top` heaviest items are placed greedily on the least-loaded part (classic LPT);
+    the long tail of small items is dealt round-robin in descending order, which is LPT up to
+    one item per round.  Deterministic; every rank computes the same answer."""
+    cells = np.asarray(cells, np.int64)
+    n = len(cells)
+    order = np.argsort(-cells, kind="stable")
+    parts: List[List[np.ndarray]] = [[] for _ in range(n_parts)]
+    load = np.zeros(n_parts, np.int64)
+    top = order[: min(exact_top, n)]
+    assign = np.empty(len(top), np.int64)
+    for k, i in enumerate(top):
+        p = int(np.argmin(load))
+        assign[k] = p
+        load[p] += cells[i]
+    for p in range(n_parts):
+        parts[p].append(top[assign == p])
+    rest = order[len(top):]
+    if len(rest):
+        # continue on the currently least-loaded parts first
+        start = np.argsort(load, kind="stable")
+        for j, p in enumerate(start):
+            parts[int(p)].append(rest[j::n_parts])
+    return [np.sort(np.concatenate(p)) if p else np.zeros(0, np.int64) for p in parts]
+
+
+def gather_results(local: dict, sc_idx: np.ndarray, var_idx: np.ndarray, n_sc: int, n_var: int,
+                   dist, device=None) -> dict:
+    """All-gather the per-alignment and per-variant result arrays of every rank's shard and
+    scatter them back to batch order.  `local` holds this rank's vd_batch_out arrays (torch
+    tensors on `device`, or numpy for the CPU tests); `sc_idx` / `var_idx` are the batch-global
+    indices of the shard's superclusters / variants.  One collective per dtype width."""
+    import torch
+    world = dist.get_world_size()
+    dev = device if device is not None else "cpu"
+
+    def as_i32(x):
+        if isinstance(x, torch.Tensor):
+            t = x.to(dev)
+            return t if t.dtype == torch.int32 else t.view(torch.int32)
+        return torch.from_numpy(np.ascontiguousarray(x).view(np.int32)).to(dev)
+
+    def as_u8(x):
+        if isinstance(x, torch.Tensor):
+            return x.to(dev)
+        return torch.from_numpy(np.ascontiguousarray(x, np.uint8)).to(dev)
+
+    n_loc_sc, n_loc_var = len(sc_idx), len(var_idx)
+    counts = torch.tensor([n_loc_sc, n_loc_var], dtype=torch.int64, device=dev)
+    all_counts = [torch.zeros(2, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(all_counts, counts)
+    all_counts = torch.stack(all_counts).cpu().numpy()
+    max_sc, max_var = int(all_counts[:, 0].max()), int(all_counts[:, 1].max())
+
+    # pack everything of this rank into one int32 record buffer: [indices | per-alignment | per-variant]
+    def pad(t, n):
+        out = torch.zeros(n, dtype=t.dtype, device=dev)
+        out[: t.numel()] = t
+        return out
+
+    i32 = torch.int32
+    pieces = [
+        pad(as_i32(sc_idx.astype(np.int32)), max_sc),
+        pad(as_i32(var_idx.astype(np.int32)), max_var),
+        pad(as_i32(local["aln_score"])[: 4 * n_loc_sc], 4 * max_sc),
+        pad(as_i32(local["status"])[: 4 * n_loc_sc], 4 * max_sc),
+    ]
+    for k in ("sync_group", "ref_ed", "query_ed", "callq"):
+        t = as_i32(local[k])
+        for slot in range(2):
+            pieces.append(pad(t[slot * n_loc_var: (slot + 1) * n_loc_var], max_var))
+    u8 = torch.uint8
+    pieces8 = [pad(as_u8(local["aln_end_plane"])[: 4 * n_loc_sc], 4 * max_sc),
+               pad(as_u8(local["aln_beg_plane"])[: 4 * n_loc_sc], 4 * max_sc)]
+    a8 = as_u8(local["assigned"])
+    for slot in range(2):
+        pieces8.append(pad(a8[slot * n_loc_var: (slot + 1) * n_loc_var], max_var))
+    buf32 = torch.cat(pieces)
+    buf8 = torch.cat(pieces8)
+    # one record buffer per rank -> a single all-gather
+    rec = torch.cat([buf32.view(u8), buf8])
+    gathered = torch.empty(world * rec.numel(), dtype=u8, device=dev)
+    dist.all_gather_into_tensor(gathered, rec)
+    gathered = gathered.view(world, -1)
+
+    out = {
+        "aln_score": torch.zeros(4 * n_sc, dtype=i32, device=dev),
+        "status": torch.zeros(4 * n_sc, dtype=i32, device=dev),
+        "aln_end_plane": torch.zeros(4 * n_sc, dtype=u8, device=dev),
+        "aln_beg_plane": torch.zeros(4 * n_sc, dtype=u8, device=dev),
+        "assigned": torch.zeros(2 * n_var, dtype=u8, device=dev),
+    }
+    for k in ("sync_group", "ref_ed", "query_ed", "callq"):
+        out[k] = torch.zeros(2 * n_var, dtype=i32, device=dev)
+    n32 = buf32.numel()
+    four = torch.arange(4, device=dev)
+    for r in range(world):
+        c_sc, c_var = int(all_counts[r, 0]), int(all_counts[r, 1])
+        b32 = gathered[r, : 4 * n32].view(i32)
+        b8 = gathered[r, 4 * n32:]
+        o = 0
+        sidx = b32[o: o + c_sc].long(); o += max_sc
+        vidx = b32[o: o + c_var].long(); o += max_var
+        aidx = (sidx[:, None] * 4 + four[None, :]).reshape(-1)
+        out["aln_score"][aidx] = b32[o: o + 4 * c_sc]; o += 4 * max_sc
+        out["status"][aidx] = b32[o: o + 4 * c_sc]; o += 4 * max_sc
+        for k in ("sync_group", "ref_ed", "query_ed", "callq"):
+            for slot in range(2):
+                out[k][slot * n_var + vidx] = b32[o: o + c_var]; o += max_var
+        o = 0
+        out["aln_end_plane"][aidx] = b8[o: o + 4 * c_sc]; o += 4 * max_sc
+        out["aln_beg_plane"][aidx] = b8[o: o + 4 * c_sc]; o += 4 * max_sc
+        for slot in range(2):
+            out["assigned"][slot * n_var + vidx] = b8[o: o + c_var]; o += max_var
+    out["callq"] = out["callq"].view(torch.float32)
+    return out
