@@ -176,7 +176,7 @@ static int run_resident(vd_handle *h, const BatchDev &in, const OutDev &out) {
         CK(h->offs.ensure(8 * (size_t)(n + 1)));
         int64_t *bytes = (int64_t *)h->bytes.p, *offs = (int64_t *)h->offs.p;
         CK(cudaMemsetAsync(bytes + n, 0, 8, st));
-        slab_size_kernel<<<(n + 255) / 256, 256, 0, st>>>(plan, list, n, bytes, CLS_SCALAR);
+        wave_size_kernel<<<(n + 255) / 256, 256, 0, st>>>(plan, list, n, bytes);
         S.n_launches++;
         size_t tmp = 0;
         cub::DeviceScan::ExclusiveSum(nullptr, tmp, bytes, offs, n + 1, st);
@@ -203,10 +203,49 @@ static int run_resident(vd_handle *h, const BatchDev &in, const OutDev &out) {
             slab_align_kernel<<<(4 * m + 63) / 64, 64, 0, st>>>(in, out, plan, list, i0, i1, offs, (u8 *)h->slab.p,
                                                                 (const int *)h->hap_ok.p, CLS_SCALAR);
             S.n_launches++;
-            int rc = wave_run(h->stream, h->ev + 4, in, out, plan, list, i0, i1, offs, hoffs.data(), (u8 *)h->slab.p,
-                              (const int *)h->hap_ok.p, h->wave_desc.p ? &h->wave_desc : &h->wave_desc,
-                              h->num_sms, &S, &ms_fwd, &ms_bwd, &ms_walk);
-            if (rc != VD_OK) return fail(h, rc, "wavefront path failed: %s", cudaGetErrorString(cudaGetLastError()));
+            // ---- wavefront kernels: class-sorted items, then forward / backward / walk ----
+            wave_tables_kernel<<<(4 * m + 127) / 128, 128, 0, st>>>(plan, list, i0, i1, offs, (u8 *)h->slab.p,
+                                                                    (const int *)h->hap_ok.p);
+            CK(h->wave_desc.ensure(sizeof(WaveItems) + 4 * (size_t)(4 * m + 4)));
+            WaveItems *wi = (WaveItems *)h->wave_desc.p;
+            int *items = (int *)((u8 *)h->wave_desc.p + sizeof(WaveItems));
+            CK(cudaMemsetAsync(wi, 0, sizeof(WaveItems), st));
+            wave_count_kernel<<<(4 * m + 127) / 128, 128, 0, st>>>(plan, list, i0, i1, (const int *)h->hap_ok.p, wi);
+            S.n_launches += 2;
+            WaveItems hwi;
+            CK(cudaMemcpyAsync(&hwi, wi, sizeof(WaveItems), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            ClsBase cb;
+            int total_items = 0;
+            for (int c = 0; c < N_WCLS; c++) { cb.b[c] = total_items; total_items += hwi.count[c]; }
+            if (total_items > 0 || hwi.n_toolarge > 0) {
+                wave_fill_kernel<<<(4 * m + 127) / 128, 128, 0, st>>>(plan, list, i0, i1, (const int *)h->hap_ok.p,
+                                                                      wi, cb, items, out);
+                S.n_launches++;
+            }
+            if (total_items > 0) {
+                WaveArgs WA{in, out, plan, list, i0, offs, (u8 *)h->slab.p, items};
+                CK(cudaEventRecord(h->ev[4], st));
+                for (int c = 0; c < N_WCLS; c++)
+                    if (hwi.count[c]) { wave_launch(st, WA, c, cb.b[c], hwi.count[c], true); S.n_launches++; }
+                CK(cudaEventRecord(h->ev[5], st));
+                for (int c = 0; c < N_WCLS; c++)
+                    if (hwi.count[c]) { wave_launch(st, WA, c, cb.b[c], hwi.count[c], false); S.n_launches++; }
+                CK(cudaEventRecord(h->ev[6], st));
+                wave_walk_kernel<<<(total_items + 63) / 64, 64, 0, st>>>(WA, total_items);
+                S.n_launches++;
+                CK(cudaEventRecord(h->ev[7], st));
+                CK(cudaStreamSynchronize(st));
+                CK(cudaGetLastError());
+                float a_ = 0, b_ = 0, c_ = 0;
+                cudaEventElapsedTime(&a_, h->ev[4], h->ev[5]);
+                cudaEventElapsedTime(&b_, h->ev[5], h->ev[6]);
+                cudaEventElapsedTime(&c_, h->ev[6], h->ev[7]);
+                ms_fwd += a_; ms_bwd += b_; ms_walk += c_;
+                S.spill_bytes += 3 * (int64_t)hwi.spill_cells;
+            }
+            if (hwi.n_toolarge > 0)
+                return fail(h, VD_E_TOOLARGE, "%d alignments exceed the supported matrix side (32768 rows)", hwi.n_toolarge);
             i0 = i1;
         }
     }

@@ -1,12 +1,730 @@
-// Wavefront kernels for long superclusters (block per alignment, column sweep with a
-// min-plus prefix scan, flag matrices spilled to HBM).  -- placeholder until written --
+// Wavefront kernels for superclusters that do not fit the fused shared-memory kernel.
+//
+// One thread block per alignment.  Rows of both planes (QUERY plane, padded to a multiple of
+// K, then REF plane) are dealt K consecutive rows per thread; the kernel sweeps the truth
+// haplotype one column at a time:
+//
+//   forward   base[a] = min(diag, del, swap) from column c-1 (own rows in registers, the
+//             previous column of BOTH planes in shared memory for neighbour and swap reads),
+//             then the insertion chain D[a] = min(base[a], D[a-1]+1) as a min-plus prefix scan
+//             (thread-local, warp shuffles, one shared-memory hop across warps).  One flag
+//             byte per cell is written to HBM, K bytes per thread, vectorised and coalesced.
+//   backward  reverse sweep: T[y] = max over optimal successors (gather form), the in-column
+//             INS chain as a max-plus suffix scan; the path-flag byte overwrites the forward
+//             flag byte in place.
+//   walk      one thread per alignment: path walk, sync sections, Levenshtein, integer credit
+//             (walk_credit of vd_scalar.cuh) reading the path flags from HBM.
+//
+// HBM traffic is 3 B/cell (forward write, backward read + write); everything else is
+// O(rows + columns).  Reference: src/dist.cpp:251-443 (forward), :486-834 (backward),
+// :842-1401 (walk + credit).
 #pragma once
 #include "vd_kernels.cuh"
-struct DevBuf;
+
 namespace vd {
-constexpr int kBigClass = CLS_SCALAR;
-inline void wave_configure() {}
-inline int wave_run(cudaStream_t, cudaEvent_t *, const BatchDev &, const OutDev &, const ScPlan *, const int *,
-                    int, int, const int64_t *, const int64_t *, u8 *, const int *, DevBuf *, int, vd_stats *,
-                    float *, float *, float *) { return VD_OK; }
+
+constexpr int kBigClass = CLS_WAVE;
+constexpr int NEG = -(1 << 28);
+
+// ---- per-hap tables the wavefront kernels need, built once per supercluster --------------
+// srcinfo: bit0 valid, bits1-3 k (index in the destination's source list), bit4 tp(dest),
+//          bits 8.. destination row (plane-local)
+__device__ inline void build_srcinfo(const int *ptr, const u8 *flg, int nsrc,      // sources
+                                     const int *tab, int ndst,                    // dest CSR
+                                     const u8 *dflg, const int *dptr,             // dest plane flags / hap->ref ptrs (tp), dptr null for REF dest
+                                     int *info) {
+    const int *src = tab + ndst + 1;
+    int n = 0;      // running position in the CSR source array (ascending b)
+    for (int b = 0; b < nsrc; b++) {
+        const int f = flg[b];
+        int v = 0;
+        const bool ok = !(f & P_VARIANT) || (f & P_VAR_END);
+        const int d = ptr[b] + 1;
+        if (ok && d >= 0 && d < ndst) {
+            // src[n] == b by construction
+            const int k = n - tab[d];
+            n++;
+            const int df = dflg[d];
+            if (d > 0 && (!(df & P_VARIANT) || (df & P_VAR_BEG))) {               // :600-602, :638-640
+                int tp = 0;
+                if (dptr) tp = (dptr[d] != dptr[d - 1] + 1) || (df & P_VAR_BEG);  // :656-658
+                v = 1 | (k << 1) | (tp << 4) | (d << 8);
+            }
+        }
+        info[b] = v;
+    }
+    (void)src;
+}
+
+struct WaveHapQ {        // extra per query hap
+    int *srcQ;           // [Lq]  QUERY rows as swap sources (destinations on the REF plane)
+    int *srcR;           // [Lr]  REF rows as swap sources (destinations on the QUERY plane)
+    u8 *tpb;             // [Lq]  tp(a): entering QUERY row a counts a query variant (:572-574)
+    __device__ WaveHapQ(u8 *base, int Lq, int Lr) {
+        srcQ = (int *)base; srcR = srcQ + Lq; tpb = (u8 *)(srcR + Lr);
+    }
+};
+__host__ __device__ inline int64_t wave_hapq_bytes(int Lq, int Lr) { return 4 * ((int64_t)Lq + Lr) + align_up(Lq, 16); }
+__host__ __device__ inline int64_t wave_hapt_bytes(int Lt) { return align_up(Lt, 16); }     // tinfo: base | tok<<7
+
+// kernel shape classes: (threads per block, rows per thread)
+constexpr int N_WCLS = 8;
+__host__ __device__ inline int wave_tpb(int c) { const int v[N_WCLS] = {32, 32, 32, 128, 256, 512, 1024, 1024}; return v[c]; }
+__host__ __device__ inline int wave_k(int c) { const int v[N_WCLS] = {1, 2, 4, 4, 8, 16, 16, 32}; return v[c]; }
+__host__ __device__ inline int wave_class(int Lq, int Lr, int Lt) {
+    for (int c = 0; c < N_WCLS; c++) {
+        const int K = wave_k(c);
+        const int np = (Lq + K - 1) / K * K + (Lr + K - 1) / K * K;
+        if (np <= wave_tpb(c) * K && np + Lt < 65000) return c;
+    }
+    return -1;
+}
+
+// scratch of one alignment in the slab
+struct WaveAln {
+    int64_t oF;          // flag matrix [Lt][NP]
+    int64_t oWalk;       // walk scratch (path + Levenshtein row), AlnLayout offsets relative to it
+    int64_t total;
+    int cls, K, padQ, NP;
+};
+__host__ __device__ inline WaveAln wave_aln(int Lq, int Lr, int Lt) {
+    WaveAln w;
+    w.cls = wave_class(Lq, Lr, Lt);
+    w.K = w.cls >= 0 ? wave_k(w.cls) : 1;
+    w.padQ = (Lq + w.K - 1) / w.K * w.K;
+    w.NP = w.padQ + (Lr + w.K - 1) / w.K * w.K;      // both planes padded to whole threads
+    w.oF = 0;
+    w.oWalk = align_up((int64_t)w.NP * Lt, 16);
+    // path (int32 q, int32 t, u8 flags) + lev row
+    const int np = Lq + Lr + Lt + 4;
+    const int mn = (Lr < Lt ? Lr : Lt) + 1;
+    w.total = align_up(w.oWalk + 8 * (int64_t)np + align_up(np, 4) + 4 * (int64_t)mn, 16);
+    return w;
+}
+// walk scratch offsets in AlnLayout form (only the path / lev members are used)
+__device__ inline AlnLayout<int64_t> wave_walk_layout(int Lq, int Lr, int Lt) {
+    AlnLayout<int64_t> L;
+    const int np = Lq + Lr + Lt + 4;
+    L.oPF = L.oF = L.oD0 = L.oD1 = L.oT0 = L.oT1 = 0;
+    L.oPQ = 0;
+    L.oPT = 4 * (int64_t)np;
+    L.oPS = 8 * (int64_t)np;
+    L.oLev = L.oPS + align_up(np, 4);
+    L.total = 0;
+    return L;
+}
+
+// slab layout of a wave-class supercluster: the scalar layout's hap/qm regions, then the
+// wave tables, then per-alignment scratch
+struct WaveSlab {
+    SlabLayout base;
+    int64_t hq[2], ht[2], aln[4];
+    int64_t total;
+};
+__host__ __device__ inline WaveSlab make_wave_slab(const ScPlan &p) {
+    WaveSlab w;
+    w.base = make_slab(p, false);
+    int64_t o = w.base.total;
+    for (int k = 0; k < 2; k++) { w.hq[k] = o; o = align_up(o + wave_hapq_bytes(p.len[k], p.lr), 16); }
+    for (int k = 0; k < 2; k++) { w.ht[k] = o; o = align_up(o + wave_hapt_bytes(p.len[2 + k]), 16); }
+    for (int ai = 0; ai < 4; ai++) {
+        w.aln[ai] = o;
+        o += wave_aln(p.len[ai >> 1], p.lr, p.len[2 + (ai & 1)]).total;
+    }
+    w.total = o;
+    return w;
+}
+
+__global__ void wave_size_kernel(const ScPlan *plan, const int *list, int n, int64_t *bytes) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const ScPlan p = plan[list[i]];
+    bytes[i] = p.cls == CLS_WAVE ? make_wave_slab(p).total : make_slab(p, true).total;
+}
+
+// one thread per (entry, hap): wave tables after slab_setup_kernel's expansion
+__global__ void wave_tables_kernel(const ScPlan *plan, const int *list, int i0, int i1,
+                                   const int64_t *offs, u8 *slab, const int *hap_ok) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = i0 + (g >> 2), h = g & 3;
+    if (i >= i1) return;
+    const ScPlan p = plan[list[i]];
+    if (p.cls != CLS_WAVE) return;
+    const int *okp = hap_ok + 4 * (int64_t)(i - i0);
+    if (!(okp[0] && okp[1] && okp[2] && okp[3])) return;
+    const WaveSlab W = make_wave_slab(p);
+    u8 *base = slab + (offs[i] - offs[i0]);
+    SlabHap H(base + W.base.hap[h], p.len[h], p.lr);
+    if (h < 2) {
+        SlabQm M(base + W.base.qm[h], p.len[h], p.lr);
+        WaveHapQ X(base + W.hq[h], p.len[h], p.lr);
+        // QUERY rows as sources -> destinations on REF (CSR toR); dest flags = rflg, no tp on REF
+        build_srcinfo(H.ptr, H.flg, p.len[h], M.toR, p.lr, M.rflg, nullptr, X.srcQ);
+        // REF rows as sources -> destinations on QUERY (CSR toQ); dest flags = hap flags, tp from hap ptrs
+        build_srcinfo(M.rptr, M.rflg, p.lr, M.toQ, p.len[h], H.flg, H.ptr, X.srcR);
+        for (int a = 0; a < p.len[h]; a++)
+            X.tpb[a] = (a > 0 && ((H.ptr[a] != H.ptr[a - 1] + 1) || (H.flg[a] & P_VAR_BEG))) ? 1 : 0;
+    } else {
+        u8 *tinfo = base + W.ht[h - 2];
+        for (int c = 0; c < p.len[h]; c++) {
+            const bool tok = c > 0 && (!(H.flg[c - 1] & P_VARIANT) || (H.flg[c - 1] & P_VAR_END));   // :338-339
+            tinfo[c] = (u8)((H.str[c] & 0x7f) | (tok ? 0x80 : 0));
+        }
+    }
+}
+
+// class-sorted list of (entry, alignment) items of one chunk
+struct WaveItems {
+    int count[N_WCLS];
+    int cursor[N_WCLS];
+    int n_toolarge;
+    unsigned long long spill_cells;
+};
+struct ClsBase { int b[N_WCLS]; };
+__global__ void wave_count_kernel(const ScPlan *plan, const int *list, int i0, int i1, const int *hap_ok,
+                                  WaveItems *wi) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = i0 + (g >> 2), ai = g & 3;
+    if (i >= i1) return;
+    const ScPlan p = plan[list[i]];
+    if (p.cls != CLS_WAVE) return;
+    const int *okp = hap_ok + 4 * (int64_t)(i - i0);
+    if (!(okp[0] && okp[1] && okp[2] && okp[3])) return;
+    const int c = wave_class(p.len[ai >> 1], p.lr, p.len[2 + (ai & 1)]);
+    if (c < 0) atomicAdd(&wi->n_toolarge, 1);
+    else {
+        atomicAdd(&wi->count[c], 1);
+        atomicAdd(&wi->spill_cells, (unsigned long long)wave_aln(p.len[ai >> 1], p.lr, p.len[2 + (ai & 1)]).NP * p.len[2 + (ai & 1)]);
+    }
+}
+__global__ void wave_fill_kernel(const ScPlan *plan, const int *list, int i0, int i1, const int *hap_ok,
+                                 WaveItems *wi, ClsBase cb, int *items, OutDev out) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = i0 + (g >> 2), ai = g & 3;
+    if (i >= i1) return;
+    const int sc = list[i];
+    const ScPlan p = plan[sc];
+    if (p.cls != CLS_WAVE) return;
+    const int *okp = hap_ok + 4 * (int64_t)(i - i0);
+    if (!(okp[0] && okp[1] && okp[2] && okp[3])) {
+        out.status[4 * (int64_t)sc + ai] = ST_BAD;
+        out.aln_score[4 * (int64_t)sc + ai] = -1;
+        return;
+    }
+    const int c = wave_class(p.len[ai >> 1], p.lr, p.len[2 + (ai & 1)]);
+    if (c < 0) { out.status[4 * (int64_t)sc + ai] = ST_BAD; out.aln_score[4 * (int64_t)sc + ai] = -1; return; }
+    items[cb.b[c] + atomicAdd(&wi->cursor[c], 1)] = ((i - i0) << 2) | ai;
+}
+
+struct WaveArgs {
+    BatchDev in;
+    OutDev out;
+    const ScPlan *plan;
+    const int *list;
+    int i0;
+    const int64_t *offs;
+    u8 *slab;
+    const int *items;
+};
+
+// everything a block needs about its alignment
+struct WaveCtx {
+    int sc, ai, Lq, Lr, Lt, padQ, NP;
+    const u8 *qstr, *rseq, *tinfo, *qflg, *rflg, *tpb;
+    const int *toQ, *toR, *srcQ, *srcR;
+    u8 *F;
+};
+__device__ inline WaveCtx wave_ctx(const WaveArgs &A, int item) {
+    WaveCtx x;
+    const int e = item >> 2;
+    x.ai = item & 3;
+    const int i = A.i0 + e;
+    x.sc = A.list[i];
+    const ScPlan p = A.plan[x.sc];
+    const WaveSlab W = make_wave_slab(p);
+    u8 *base = A.slab + (A.offs[i] - A.offs[A.i0]);
+    const int qh = x.ai >> 1, th = x.ai & 1;
+    x.Lq = p.len[qh]; x.Lr = p.lr; x.Lt = p.len[2 + th];
+    const WaveAln wa = wave_aln(x.Lq, x.Lr, x.Lt);
+    x.padQ = wa.padQ; x.NP = wa.NP;
+    SlabHap HQ(base + W.base.hap[qh], x.Lq, x.Lr);
+    SlabQm M(base + W.base.qm[qh], x.Lq, x.Lr);
+    WaveHapQ X(base + W.hq[qh], x.Lq, x.Lr);
+    x.qstr = HQ.str; x.qflg = HQ.flg; x.rflg = M.rflg; x.tpb = X.tpb;
+    x.toQ = M.toQ; x.toR = M.toR; x.srcQ = X.srcQ; x.srcR = X.srcR;
+    x.rseq = A.in.rplane_seq + A.in.ref_off[x.sc];
+    x.tinfo = base + W.ht[th];
+    x.F = base + W.aln[x.ai] + wa.oF;
+    return x;
+}
+
+template <int K> __device__ __forceinline__ void store_flags(u8 *dst, const u32 *w) {
+    if constexpr (K == 1) dst[0] = (u8)w[0];
+    else if constexpr (K == 2) *(u16 *)dst = (u16)w[0];
+    else if constexpr (K == 4) *(u32 *)dst = w[0];
+    else if constexpr (K == 8) *(uint2 *)dst = make_uint2(w[0], w[1]);
+    else {
+#pragma unroll
+        for (int i = 0; i < K / 16; i++) ((uint4 *)dst)[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+    }
+}
+template <int K> __device__ __forceinline__ void load_flags(const u8 *src, u32 *w) {
+    if constexpr (K == 1) w[0] = src[0];
+    else if constexpr (K == 2) w[0] = *(const u16 *)src;
+    else if constexpr (K == 4) w[0] = *(const u32 *)src;
+    else if constexpr (K == 8) { const uint2 v = *(const uint2 *)src; w[0] = v.x; w[1] = v.y; }
+    else {
+#pragma unroll
+        for (int i = 0; i < K / 16; i++) {
+            const uint4 v = ((const uint4 *)src)[i];
+            w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+        }
+    }
+}
+__device__ __forceinline__ int byte_of(const u32 *w, int j) { return (w[j >> 2] >> ((j & 3) * 8)) & 0xff; }
+
+template <int TPB> __device__ __forceinline__ void block_sync() {
+    if constexpr (TPB == 32) __syncwarp(); else __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------
+// forward: calc_prec_recall_aln (:251-443) as a column sweep
+// ------------------------------------------------------------------------------------------
+template <int TPB, int K>
+__global__ void __launch_bounds__(TPB) wave_fwd_kernel(WaveArgs A, int item0) {
+    extern __shared__ __align__(16) u8 smem_raw[];
+    const WaveCtx X = wave_ctx(A, A.items[item0 + blockIdx.x]);
+    constexpr int NPMAX = TPB * K;
+    u16 *sD0 = (u16 *)smem_raw, *sD1 = sD0 + NPMAX;          // previous / current column, both planes
+    int *sW = (int *)(sD1 + NPMAX);                          // [2 segments][32 warps] scan totals
+    __shared__ int sEnd[2];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int tQ = X.padQ / K;                               // first thread of the REF plane
+    const bool P = t >= tQ;
+    const int row0 = t * K;
+    const int a0 = P ? row0 - X.padQ : row0;
+    const int len = P ? X.Lr : X.Lq;
+    const u8 *seq = P ? X.rseq : X.qstr;
+    const int *tab = P ? X.toR : X.toQ;                      // CSR of swap sources of my plane's rows
+    const int *src = tab + len + 1;
+    const int obase = P ? 0 : X.padQ;                        // padded row offset of the other plane
+    const int segstart = P ? tQ : 0;
+
+    u8 ch[K];
+#pragma unroll
+    for (int j = 0; j < K; j++) ch[j] = (a0 + j < len) ? (u8)(seq[a0 + j] & 0x7f) : (u8)0xff;
+    int Dp[K];
+#pragma unroll
+    for (int j = 0; j < K; j++) Dp[j] = INF;
+#pragma unroll
+    for (int j = 0; j < K; j++) sD0[row0 + j] = 0xffff;
+    block_sync<TPB>();
+
+    int tnext = X.tinfo[0];
+    for (int c = 0; c < X.Lt; c++) {
+        u16 *sPrev = (c & 1) ? sD1 : sD0, *sCur = (c & 1) ? sD0 : sD1;
+        const int tinfo = tnext;
+        if (c + 1 < X.Lt) tnext = X.tinfo[c + 1];
+        const int tch = tinfo & 0x7f;
+        const bool tok = tinfo & 0x80;
+        // ---- pass 1: thread-local chain ----
+        int up;                                             // D[a0-1][c-1]
+        {
+            const int v = (a0 > 0 && c > 0) ? sPrev[row0 - 1] : 0xffff;
+            up = v == 0xffff ? INF : v;
+        }
+        int Dc[K];
+        int run = INF;                                      // D[a-1][c] within the thread (no carry yet)
+        int upj = up;
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            const bool m = ch[j] == tch;
+            int b;
+            if (a0 + j == 0 && c == 0) b = (a0 + j < len) ? 0 : INF;       // both origins start at 0 (:299-305)
+            else {
+                b = upj + (m ? 0 : 1);                      // diag (INF-safe: INF+1 stays huge)
+                b = min(b, Dp[j] + 1);                      // del
+                if (tok && m && a0 + j < len) {             // swap (:334-349, :363-378)
+                    const int k0 = tab[a0 + j], k1 = tab[a0 + j + 1];
+                    for (int k = k0; k < k1; k++) {
+                        const int v = sPrev[obase + src[k]];
+                        b = min(b, v == 0xffff ? INF : v);
+                    }
+                }
+                if (a0 + j >= len) b = INF;
+            }
+            run = min(b, run + 1);
+            Dc[j] = run;
+            upj = Dp[j];
+        }
+        // ---- cross-thread min-plus prefix scan of G = last - lastrow ----
+        int G = Dc[K - 1] - (row0 + K - 1);
+        int incl = G;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d && t - d >= segstart) incl = min(incl, o);
+        }
+        int excl = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0 || t - 1 < segstart) excl = INF;
+        int carry = excl;
+        if constexpr (TPB > 32) {
+            // warp totals per segment: the last lane's inclusive value covers the lanes of its own
+            // segment; a warp straddling the plane boundary also publishes its QUERY-part total
+            int *sWc = sW + (c & 1) * 64;
+            const int lastQ = tQ - 1;                        // last QUERY thread
+            if (lane == 31) sWc[(P ? 32 : 0) + warp] = incl;
+            if (t == lastQ && lane != 31) sWc[warp] = incl;
+            if (lane == 31 && !P) { /* pure QUERY warp: REF total empty */ sWc[32 + warp] = INF; }
+            if (lane == 31 && P && (t - 31) >= tQ) sWc[warp] = INF;      // pure REF warp: QUERY total empty
+            __syncthreads();
+            // totals of earlier warps in my segment.  The slot choice must be warp-uniform for the
+            // butterfly: a warp that starts on the QUERY plane reads QUERY totals; its REF lanes (a
+            // straddling warp) have no earlier REF warp at all.
+            const bool warpQ = 32 * warp < tQ;
+            int wv = (lane < warp) ? sWc[(warpQ ? 0 : 32) + lane] : INF;
+#pragma unroll
+            for (int d = 16; d; d >>= 1) wv = min(wv, __shfl_xor_sync(0xffffffffu, wv, d));
+            if (warpQ && P) wv = INF;
+            carry = min(carry, wv);
+        }
+        // ---- pass 2: final values and flags ----
+        u32 fw[(K + 3) / 4];
+#pragma unroll
+        for (int i = 0; i < (K + 3) / 4; i++) fw[i] = 0;
+        // carry is min(G) = D_last - lastrow over earlier threads, so the chain value at row r is carry + r
+        int prevD = carry >= INF / 2 ? INF : carry + (row0 - 1);           // D[a0-1][c]
+        upj = up;
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            const int r = row0 + j;
+            int d = Dc[j];
+            if (carry < INF / 2) d = min(d, carry + r);
+            int f = 0;
+            if (a0 + j < len) {
+                if (a0 + j == 0 && c == 0) f = F_DIAG;
+                else {
+                    const bool m = ch[j] == tch;
+                    if (a0 + j > 0 && c > 0 && upj + (m ? 0 : 1) == d) f |= F_DIAG;
+                    if (a0 + j > 0 && prevD + 1 == d) f |= F_INS;
+                    if (c > 0 && Dp[j] + 1 == d) f |= F_DEL;
+                    if (tok && m) {
+                        const int k0 = tab[a0 + j], k1 = tab[a0 + j + 1];
+                        int best = INF, sb = 0;
+                        for (int k = k0; k < k1; k++) {
+                            int v = sPrev[obase + src[k]];
+                            v = v == 0xffff ? INF : v;
+                            if (v < best) { best = v; sb = (k - k0) << F_K_SHIFT; }
+                            else if (v == best) sb = ((k - k0) << F_K_SHIFT) | F_TIE;
+                        }
+                        if (best == d) f |= F_SWP | sb;
+                    }
+                }
+            } else d = INF;
+            fw[j >> 2] |= (u32)f << ((j & 3) * 8);
+            upj = Dp[j];
+            Dp[j] = d;
+            prevD = d;
+            sCur[r] = d >= 0xffff ? (u16)0xffff : (u16)d;
+        }
+        if (row0 < X.NP) store_flags<K>(X.F + (int64_t)c * X.NP + row0, fw);
+        block_sync<TPB>();
+    }
+    // ---- score and end plane (:390-391, :436-440) ----
+    {
+        const int rq = X.Lq - 1, rr = X.padQ + X.Lr - 1;
+        if (rq >= row0 && rq < row0 + K) {
+#pragma unroll
+            for (int j = 0; j < K; j++) if (row0 + j == rq) sEnd[0] = Dp[j];
+        }
+        if (rr >= row0 && rr < row0 + K) {
+#pragma unroll
+            for (int j = 0; j < K; j++) if (row0 + j == rr) sEnd[1] = Dp[j];
+        }
+        block_sync<TPB>();
+        if (t == 0) {
+            const int s = min(sEnd[0], sEnd[1]);
+            A.out.aln_score[4 * (int64_t)X.sc + X.ai] = s;
+            A.out.aln_end_plane[4 * (int64_t)X.sc + X.ai] = (u8)(sEnd[0] == s ? 0 : 1);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// backward: calc_prec_recall_path (:486-834) as a reverse column sweep, path flags in place
+// ------------------------------------------------------------------------------------------
+template <int TPB, int K>
+__global__ void __launch_bounds__(TPB) wave_bwd_kernel(WaveArgs A, int item0) {
+    extern __shared__ __align__(16) u8 smem_raw[];
+    const WaveCtx X = wave_ctx(A, A.items[item0 + blockIdx.x]);
+    constexpr int NPMAX = TPB * K;
+    short *sT0 = (short *)smem_raw, *sT1 = sT0 + NPMAX;      // T of column c+1 / c, all rows
+    u8 *sF0 = (u8 *)(sT1 + NPMAX), *sF1 = sF0 + NPMAX;       // forward flags of column c+1 / c
+    int *sW = (int *)(sF1 + NPMAX);                          // [32 warps][2] scan summaries
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int tQ = X.padQ / K;
+    const bool P = t >= tQ;
+    const int row0 = t * K;
+    const int a0 = P ? row0 - X.padQ : row0;
+    const int len = P ? X.Lr : X.Lq;
+    const u8 *seq = P ? X.rseq : X.qstr;
+    const int *sinfo = P ? X.srcR : X.srcQ;                  // my rows as swap SOURCES
+    const int dbase = P ? 0 : X.padQ;                        // padded row offset of the destination plane
+    const int end_plane = A.out.aln_end_plane[4 * (int64_t)X.sc + X.ai];
+    const int erow = end_plane ? X.padQ + X.Lr - 1 : X.Lq - 1;
+
+    u8 ch[K + 1];                                            // bases of rows a0 .. a0+K (one past, for the diagonal)
+#pragma unroll
+    for (int j = 0; j <= K; j++) ch[j] = (a0 + j < len) ? (u8)(seq[a0 + j] & 0x7f) : (u8)0xff;
+    unsigned long long tpw = 0;                              // bit j: tp(a0+j), j = 0..K
+    auto tpbit = [&](int j) -> int { return (int)((tpw >> j) & 1ull); };
+#pragma unroll
+    for (int j = 0; j <= K; j++) if (!P && a0 + j < len && X.tpb[a0 + j]) tpw |= 1ull << j;
+    int si[K];
+#pragma unroll
+    for (int j = 0; j < K; j++) si[j] = (a0 + j < len) ? sinfo[a0 + j] : 0;
+
+    int Tn[K];                                               // T of column c+1, my rows
+    u32 Fn[(K + 3) / 4];                                     // forward flags of column c+1, my rows
+#pragma unroll
+    for (int j = 0; j < K; j++) Tn[j] = -1;
+#pragma unroll
+    for (int i = 0; i < (K + 3) / 4; i++) Fn[i] = 0;
+    u32 status = 0;
+    u32 Fc[(K + 3) / 4];
+#pragma unroll
+    for (int i = 0; i < (K + 3) / 4; i++) Fc[i] = 0;
+    if (row0 < X.NP) load_flags<K>(X.F + (int64_t)(X.Lt - 1) * X.NP + row0, Fc);
+    int tch_next = 0;                                        // truth base of column c+1
+
+    for (int c = X.Lt - 1; c >= 0; c--) {
+        short *sTn = (c & 1) ? sT1 : sT0, *sTc = (c & 1) ? sT0 : sT1;      // column c+1 was written as "cur" last iteration
+        u8 *sFn = (c & 1) ? sF1 : sF0, *sFc = (c & 1) ? sF0 : sF1;
+        const bool last = c == X.Lt - 1;
+        // prefetch next column's forward flags
+        u32 Fp[(K + 3) / 4];
+#pragma unroll
+        for (int i = 0; i < (K + 3) / 4; i++) Fp[i] = 0;
+        if (c > 0 && row0 < X.NP) load_flags<K>(X.F + (int64_t)(c - 1) * X.NP + row0, Fp);
+        // publish my first row's flag of column c for the neighbour's INS link
+        sFc[row0] = (u8)byte_of(Fc, 0);
+        // neighbour values of column c+1 (row a0+K): T and F
+        int Tup = -1, Fup = 0;
+        if (!last && a0 + K < len) { Tup = sTn[row0 + K]; Fup = sFn[row0 + K]; }
+        // ---- pass 1: B[j] from column c+1, then local suffix chain ----
+        int B[K];
+#pragma unroll
+        for (int j = K - 1; j >= 0; j--) {
+            int b = -1;
+            if (a0 + j < len) {
+                if (last && row0 + j == erow) b = 0;                                   // :543-545
+                if (!last) {
+                    const int Tx = (j == K - 1) ? Tup : Tn[j + 1];                     // (P, a+1, c+1)
+                    const int Fx = (j == K - 1) ? Fup : byte_of(Fn, j + 1);
+                    if (a0 + j + 1 < len && Tx >= 0 && (Fx & F_DIAG)) b = max(b, Tx + tpbit(j + 1));
+                    if (Tn[j] >= 0 && (byte_of(Fn, j) & F_DEL)) b = max(b, Tn[j]);     // (P, a, c+1)
+                    const int s = si[j];
+                    if (s & 1) {                                                       // swap: I am the recorded source
+                        const int xr = dbase + (s >> 8);
+                        const int Tx2 = sTn[xr], Fx2 = sFn[xr];
+                        if (Tx2 >= 0 && (Fx2 & F_SWP) && (Fx2 >> F_K_SHIFT) == ((s >> 1) & 7)) {
+                            b = max(b, Tx2 + ((s >> 4) & 1));
+                            if (Fx2 & F_TIE) status |= VD_ST_TIE;
+                        }
+                    }
+                }
+            }
+            B[j] = b;
+        }
+        // local chain assuming no carry-in: Tl[j] = max(B[j], link(j+1) ? Tl[j+1] + w(j+1) : -1)
+        // cum[j] = weight of the unbroken INS chain from row a0+K down to row a0+j (NEG if broken)
+        int Tl0, cumtop;
+        {
+            int run = -1, cum = 0;
+            // link into row j comes from row j+1 of column c: flag F_INS of row j+1 (own Fc, or the
+            // neighbour's first row, published in sFc after the sync below -> handled via cum)
+#pragma unroll
+            for (int j = K - 1; j >= 0; j--) {
+                if (j < K - 1) {
+                    const bool link = (a0 + j + 1 < len) && (byte_of(Fc, j + 1) & F_INS);
+                    const int w = tpbit(j + 1);
+                    run = (link && run >= 0) ? run + w : -1;
+                    cum = (link && cum > NEG) ? cum + w : NEG;
+                }
+                run = max(run, B[j]);
+            }
+            Tl0 = run;
+            cumtop = cum;       // chain weight from my row K-1 ... down to row 0 (excl. the link into K-1)
+        }
+        block_sync<TPB>();                                   // sFc[row0] of every thread visible
+        // link from the neighbour's first row (a0+K) into my last row
+        const bool toplink = (a0 + K < len) && (sFc[row0 + K] & F_INS);
+        const int wtop = tpbit(K);
+        // my affine-max function of the carry-in X = T[a0+K][c]:  T[a0] = max(Tl[0], X + Aw)
+        int Aw = (toplink && cumtop > NEG) ? cumtop + wtop : NEG;
+        int Mw = Tl0;
+        // suffix composition across lanes: S_t = f_t o f_{t+1} o ... ; (A1,M1)o(A2,M2) = (A1+A2, max(M1, M2+A1))
+        int As = Aw, Ms = Mw;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int A2 = __shfl_down_sync(0xffffffffu, As, d);
+            const int M2 = __shfl_down_sync(0xffffffffu, Ms, d);
+            if (lane + d < 32) {
+                if (M2 >= 0 && As > NEG) Ms = max(Ms, M2 + As);
+                As = (As > NEG && A2 > NEG) ? As + A2 : NEG;
+            }
+        }
+        int Xw = -1;                                         // T of the first row of the next warp
+        if constexpr (TPB > 32) {
+            int *sWc = sW + (c & 1) * 64;
+            if (lane == 0) { sWc[2 * warp] = As; sWc[2 * warp + 1] = Ms; }
+            __syncthreads();
+            constexpr int NW = TPB / 32;
+            int Aq = (lane < NW) ? sWc[2 * lane] : NEG, Mq = (lane < NW) ? sWc[2 * lane + 1] : -1;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int A2 = __shfl_down_sync(0xffffffffu, Aq, d);
+                const int M2 = __shfl_down_sync(0xffffffffu, Mq, d);
+                if (lane + d < 32) {
+                    if (M2 >= 0 && Aq > NEG) Mq = max(Mq, M2 + Aq);
+                    Aq = (Aq > NEG && A2 > NEG) ? Aq + A2 : NEG;
+                }
+            }
+            Xw = __shfl_sync(0xffffffffu, Mq, (warp + 1) & 31);
+            if (warp + 1 >= NW) Xw = -1;
+        }
+        // T of my first row with the true carry, then the carry-in of each thread = T_first of t+1
+        int Tfirst = Ms;
+        if (Xw >= 0 && As > NEG) Tfirst = max(Tfirst, Xw + As);
+        int Xin = __shfl_down_sync(0xffffffffu, Tfirst, 1);
+        if (lane == 31) Xin = Xw;
+        // ---- pass 2: final T and path flags ----
+        u32 pfw[(K + 3) / 4];
+#pragma unroll
+        for (int i = 0; i < (K + 3) / 4; i++) pfw[i] = 0;
+        int Tc[K];
+        {
+            int above = (toplink && Xin >= 0) ? Xin + wtop : -1;        // INS candidate into row K-1
+#pragma unroll
+            for (int j = K - 1; j >= 0; j--) {
+                const int Tv = max(B[j], above);
+                Tc[j] = Tv;
+                int pf = 0;
+                if (Tv >= 0 && a0 + j < len) {
+                    if (last && row0 + j == erow && Tv == 0) pf |= PTR_MAT;            // :543
+                    if (!last) {
+                        const int Tx = (j == K - 1) ? Tup : Tn[j + 1];
+                        const int Fx = (j == K - 1) ? Fup : byte_of(Fn, j + 1);
+                        if (a0 + j + 1 < len && Tx >= 0 && (Fx & F_DIAG) && Tx + tpbit(j + 1) == Tv)
+                            pf |= (ch[j + 1] == tch_next) ? PTR_MAT : PTR_SUB;
+                        if (Tn[j] >= 0 && (byte_of(Fn, j) & F_DEL) && Tn[j] == Tv) pf |= PTR_DEL;
+                        const int s = si[j];
+                        if (s & 1) {
+                            const int xr = dbase + (s >> 8);
+                            const int Tx2 = sTn[xr], Fx2 = sFn[xr];
+                            if (Tx2 >= 0 && (Fx2 & F_SWP) && (Fx2 >> F_K_SHIFT) == ((s >> 1) & 7) &&
+                                Tx2 + ((s >> 4) & 1) == Tv) pf |= PTR_SWP;
+                        }
+                    }
+                    if (above >= 0 && above == Tv) pf |= PTR_INS;
+                }
+                pfw[j >> 2] |= (u32)pf << ((j & 3) * 8);
+                // INS candidate into row j-1 comes from row j
+                if (j > 0) {
+                    const bool link = (a0 + j < len) && (byte_of(Fc, j) & F_INS);
+                    above = (link && Tv >= 0) ? Tv + tpbit(j) : -1;
+                }
+            }
+        }
+        // in-place: the path flags replace the forward flags of column c
+#ifdef VD_DEBUG
+        if (blockIdx.x == 0 && row0 < X.NP)
+            printf("bwd c=%d t=%d row0=%d P=%d a0=%d len=%d Fc0=%x B0=%d Tl0=%d toplink=%d Aw=%d Ms=%d Tfirst=%d Xin=%d Tc0=%d pf0=%x Tup=%d Fup=%x erow=%d\n",
+                   c, t, row0, (int)P, a0, len, byte_of(Fc, 0), B[0], Tl0, (int)toplink, Aw, Ms, Tfirst, Xin, Tc[0], byte_of(pfw, 0), Tup, Fup, erow);
+#endif
+        if (row0 < X.NP) store_flags<K>(X.F + (int64_t)c * X.NP + row0, pfw);
+        // publish column c for the next iteration
+#pragma unroll
+        for (int j = 0; j < K; j++) { sTc[row0 + j] = (short)Tc[j]; sFc[row0 + j] = (u8)byte_of(Fc, j); Tn[j] = Tc[j]; }
+#pragma unroll
+        for (int i = 0; i < (K + 3) / 4; i++) { Fn[i] = Fc[i]; Fc[i] = Fp[i]; }
+        tch_next = X.tinfo[c] & 0x7f;
+        block_sync<TPB>();
+    }
+    // origin plane (:811-814): QUERY if its origin was reached
+    if (t == 0) A.out.aln_beg_plane[4 * (int64_t)X.sc + X.ai] = (u8)(Tn[0] >= 0 ? 0 : 1);
+    if (status) atomicOr(&A.out.status[4 * (int64_t)X.sc + X.ai], status);
+}
+
+// path flags of the wavefront layout
+struct PFWave {
+    const u8 *F; int NP, padQ;
+    __device__ __forceinline__ int get(int hi, int qri, int ti) const {
+        return F[(int64_t)ti * NP + (hi ? padQ + qri : qri)];
+    }
+};
+
+// one thread per alignment: walk + credit
+__global__ void wave_walk_kernel(WaveArgs A, int n_items) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_items) return;
+    const int item = A.items[g];
+    const int e = item >> 2, ai = item & 3;
+    const int i = A.i0 + e;
+    const int sc = A.list[i];
+    const ScPlan p = A.plan[sc];
+    const WaveSlab W = make_wave_slab(p);
+    u8 *base = A.slab + (A.offs[i] - A.offs[A.i0]);
+    const int qh = ai >> 1, th = 2 + (ai & 1);
+    SlabHap HQ(base + W.base.hap[qh], p.len[qh], p.lr), HT(base + W.base.hap[th], p.len[th], p.lr);
+    SlabQm M(base + W.base.qm[qh], p.len[qh], p.lr);
+    Hap<int> q{p.len[qh], HQ.str, HQ.flg, HQ.ptr, HQ.ins};
+    Hap<int> t{p.len[th], HT.str, HT.flg, HT.ptr, HT.ins};
+    QMaps<int> qm{M.rptr, M.rflg, M.toQ, M.toR};
+    const u8 *rseq = A.in.rplane_seq + A.in.ref_off[sc];
+    const WaveAln wa = wave_aln(q.len, p.lr, t.len);
+    u8 *ab = base + W.aln[ai];
+    GMem mem{ab + wa.oWalk};
+    const AlnLayout<int64_t> L = wave_walk_layout(q.len, p.lr, t.len);
+    PFWave pfr{ab + wa.oF, wa.NP, wa.padQ};
+    u32 status = A.out.status[4 * (int64_t)sc + ai];
+    const int beg_plane = A.out.aln_beg_plane[4 * (int64_t)sc + ai];
+    const int end_plane = A.out.aln_end_plane[4 * (int64_t)sc + ai];
+    walk_credit<GMem, 4, int>(mem, L, pfr, q, qm, t, rseq, p.lr, beg_plane, end_plane, A.in, A.out, sc, ai, status);
+    A.out.status[4 * (int64_t)sc + ai] = status;
+}
+
+// ---- host side --------------------------------------------------------------------------------
+template <int TPB, int K> constexpr int wave_fwd_smem() { return 2 * TPB * K * 2 + 2 * 64 * 4; }
+template <int TPB, int K> constexpr int wave_bwd_smem() { return 2 * TPB * K * 2 + 2 * TPB * K + 2 * 64 * 4; }
+
+template <int TPB, int K> inline void wave_configure_one() {
+    cudaFuncSetAttribute(wave_fwd_kernel<TPB, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, wave_fwd_smem<TPB, K>());
+    cudaFuncSetAttribute(wave_bwd_kernel<TPB, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, wave_bwd_smem<TPB, K>());
+}
+inline void wave_configure() {
+    wave_configure_one<32, 1>(); wave_configure_one<32, 2>(); wave_configure_one<32, 4>();
+    wave_configure_one<128, 4>(); wave_configure_one<256, 8>(); wave_configure_one<512, 16>();
+    wave_configure_one<1024, 16>(); wave_configure_one<1024, 32>();
+}
+
+template <int TPB, int K>
+inline void wave_launch_pair(cudaStream_t st, const WaveArgs &A, int item0, int n, bool fwd) {
+    if (n <= 0) return;
+    if (fwd) wave_fwd_kernel<TPB, K><<<n, TPB, wave_fwd_smem<TPB, K>(), st>>>(A, item0);
+    else wave_bwd_kernel<TPB, K><<<n, TPB, wave_bwd_smem<TPB, K>(), st>>>(A, item0);
+}
+inline void wave_launch(cudaStream_t st, const WaveArgs &A, int cls, int item0, int n, bool fwd) {
+    switch (cls) {
+        case 0: wave_launch_pair<32, 1>(st, A, item0, n, fwd); break;
+        case 1: wave_launch_pair<32, 2>(st, A, item0, n, fwd); break;
+        case 2: wave_launch_pair<32, 4>(st, A, item0, n, fwd); break;
+        case 3: wave_launch_pair<128, 4>(st, A, item0, n, fwd); break;
+        case 4: wave_launch_pair<256, 8>(st, A, item0, n, fwd); break;
+        case 5: wave_launch_pair<512, 16>(st, A, item0, n, fwd); break;
+        case 6: wave_launch_pair<1024, 16>(st, A, item0, n, fwd); break;
+        case 7: wave_launch_pair<1024, 32>(st, A, item0, n, fwd); break;
+    }
+}
+
 }  // namespace vd
