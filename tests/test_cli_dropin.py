@@ -1,0 +1,51 @@
+"""End to end through the reference's own CLI: oracle/_ref/vcfdist_ref (unmodified reference) and
+oracle/_ref/vcfdist_b200cli (same object code, hot-path call replaced by the drop-in of
+vcfdist_b200/host/pr_dropin.cpp -> vd_run on the GPU) must write byte-identical output files.
+Both binaries are prebuilt by oracle/Makefile and travel to the GPU box."""
+import filecmp
+import os
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+from vcfdist_b200 import vcfgen
+
+REF = os.path.join(ROOT, "oracle", "_ref", "vcfdist_ref")
+REFB = os.path.join(ROOT, "oracle", "_ref", "vcfdist_refB")
+CLI = os.path.join(ROOT, "oracle", "_ref", "vcfdist_b200cli")
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not (os.path.exists(REF) and os.path.exists(CLI)), reason="CLI binaries not built")]
+
+FILES = ["precision-recall.tsv", "precision-recall-summary.tsv", "query.tsv", "truth.tsv", "superclusters.tsv",
+         "phase-blocks.tsv", "phasing-summary.tsv", "switchflips.tsv"]
+
+
+def run(binary, q, t, fa, out, extra):
+    os.makedirs(out, exist_ok=True)
+    r = subprocess.run([binary, q, t, fa, "-p", out + "/", "-v", "0", *extra],
+                       capture_output=True, text=True, cwd=out, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return r
+
+
+def vcf_body(path):
+    return [l for l in open(path) if not l.startswith("##")]
+
+
+@pytest.mark.parametrize("seed,extra", [(1, ["-c", "gap", "50"]), (2, ["-c", "size", "50", "-l", "400", "-s", "2000"]),
+                                        (3, [])])
+def test_cli_outputs_identical(tmp_path, seed, extra):
+    q, t, fa = vcfgen.generate(str(tmp_path / "in"), seed=seed, contig_len=80_000 if not extra else 150_000)
+    a = str(tmp_path / "ref"); b = str(tmp_path / "gpu"); c = str(tmp_path / "refB")
+    run(REF, q, t, fa, a, extra)
+    run(CLI, q, t, fa, b, extra)
+    run(REFB, q, t, fa, c, extra)
+    # order-independent files must match the unmodified reference unconditionally
+    for f in ("superclusters.tsv", "phase-blocks.tsv", "phasing-summary.tsv", "switchflips.tsv"):
+        assert filecmp.cmp(os.path.join(a, f), os.path.join(b, f), shallow=False), f
+    # everything must match the canonical-tie-break reference byte for byte
+    for f in FILES:
+        assert filecmp.cmp(os.path.join(c, f), os.path.join(b, f), shallow=False), f
+    assert vcf_body(os.path.join(c, "summary.vcf")) == vcf_body(os.path.join(b, "summary.vcf"))
