@@ -133,6 +133,7 @@ typedef struct vd_stats {
     float   ms_short;         /* ... of the short-supercluster kernel                              */
     float   ms_long_fwd, ms_long_bwd, ms_long_walk;
     float   ms_plan;
+    float   ms_long_wall;     /* wall time of the concurrent forward+backward region            */
 } vd_stats;
 
 /* Final per-variant / per-supercluster results in the reference's own terms

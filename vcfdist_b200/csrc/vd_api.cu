@@ -38,6 +38,8 @@ struct vd_handle {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[8] = {};
+    cudaStream_t side[vd::N_WCLS] = {};     // one stream per wavefront class: classes run concurrently
+    cudaEvent_t sev[vd::N_WCLS][3] = {};
     int64_t scratch_budget = 0;
     int num_sms = 148;
     std::string err;
@@ -82,6 +84,10 @@ extern "C" int vd_create(int device, int64_t scratch_bytes, vd_handle **out) {
     h->num_sms = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return VD_E_CUDA; }
     for (auto &e : h->ev) cudaEventCreate(&e);
+    for (int c = 0; c < N_WCLS; c++) {
+        cudaStreamCreateWithFlags(&h->side[c], cudaStreamNonBlocking);
+        for (auto &e : h->sev[c]) cudaEventCreate(&e);
+    }
     cudaMallocHost((void **)&h->h_counters, sizeof(PlanCounters));
     if (scratch_bytes <= 0) {
         size_t fr = 0, tot = 0;
@@ -109,6 +115,10 @@ extern "C" void vd_destroy(vd_handle *h) {
     for (DevBuf *b : bufs) b->release();
     if (h->h_counters) cudaFreeHost(h->h_counters);
     for (auto &e : h->ev) if (e) cudaEventDestroy(e);
+    for (int c = 0; c < N_WCLS; c++) {
+        for (auto &e : h->sev[c]) if (e) cudaEventDestroy(e);
+        if (h->side[c]) cudaStreamDestroy(h->side[c]);
+    }
     cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -129,7 +139,7 @@ static int run_resident(vd_handle *h, const BatchDev &in, const OutDev &out) {
     vd_stats &S = h->stats;
     S.n_sc = n_sc; S.n_var = n_var;
     S.n_launches = 0; S.n_short = S.n_long = 0; S.spill_bytes = 0;
-    S.ms_short = S.ms_long_fwd = S.ms_long_bwd = S.ms_long_walk = S.ms_plan = 0;
+    S.ms_short = S.ms_long_fwd = S.ms_long_bwd = S.ms_long_walk = S.ms_plan = S.ms_long_wall = 0;
     if (n_sc == 0) { S.cells = 0; S.ms_total = 0; return VD_OK; }
 
     CK(cudaEventRecord(h->ev[0], st));
@@ -225,23 +235,40 @@ static int run_resident(vd_handle *h, const BatchDev &in, const OutDev &out) {
             }
             if (total_items > 0) {
                 WaveArgs WA{in, out, plan, list, i0, offs, (u8 *)h->slab.p, items};
+                // forward then backward of each class on its own stream (an alignment's backward pass
+                // only depends on its own forward pass), all classes concurrently; then join
                 CK(cudaEventRecord(h->ev[4], st));
-                for (int c = 0; c < N_WCLS; c++)
-                    if (hwi.count[c]) { wave_launch(st, WA, c, cb.b[c], hwi.count[c], true); S.n_launches++; }
-                CK(cudaEventRecord(h->ev[5], st));
-                for (int c = 0; c < N_WCLS; c++)
-                    if (hwi.count[c]) { wave_launch(st, WA, c, cb.b[c], hwi.count[c], false); S.n_launches++; }
+                for (int c = 0; c < N_WCLS; c++) {
+                    if (!hwi.count[c]) continue;
+                    cudaStream_t ss = h->side[c];
+                    CK(cudaStreamWaitEvent(ss, h->ev[4], 0));
+                    CK(cudaEventRecord(h->sev[c][0], ss));
+                    wave_launch(ss, WA, c, cb.b[c], hwi.count[c], true);
+                    CK(cudaEventRecord(h->sev[c][1], ss));
+                    wave_launch(ss, WA, c, cb.b[c], hwi.count[c], false);
+                    CK(cudaEventRecord(h->sev[c][2], ss));
+                    CK(cudaStreamWaitEvent(st, h->sev[c][2], 0));
+                    S.n_launches += 2;
+                }
                 CK(cudaEventRecord(h->ev[6], st));
                 wave_walk_kernel<<<(total_items + 63) / 64, 64, 0, st>>>(WA, total_items);
                 S.n_launches++;
                 CK(cudaEventRecord(h->ev[7], st));
                 CK(cudaStreamSynchronize(st));
                 CK(cudaGetLastError());
-                float a_ = 0, b_ = 0, c_ = 0;
-                cudaEventElapsedTime(&a_, h->ev[4], h->ev[5]);
-                cudaEventElapsedTime(&b_, h->ev[5], h->ev[6]);
+                // kernel durations: summed over classes (they overlap in wall time)
+                for (int c = 0; c < N_WCLS; c++) {
+                    if (!hwi.count[c]) continue;
+                    float a_ = 0, b_ = 0;
+                    cudaEventElapsedTime(&a_, h->sev[c][0], h->sev[c][1]);
+                    cudaEventElapsedTime(&b_, h->sev[c][1], h->sev[c][2]);
+                    ms_fwd += a_; ms_bwd += b_;
+                }
+                float c_ = 0, w_ = 0;
                 cudaEventElapsedTime(&c_, h->ev[6], h->ev[7]);
-                ms_fwd += a_; ms_bwd += b_; ms_walk += c_;
+                cudaEventElapsedTime(&w_, h->ev[4], h->ev[6]);
+                ms_walk += c_;
+                S.ms_long_wall += w_;
                 S.spill_bytes += 3 * (int64_t)hwi.spill_cells;
             }
             if (hwi.n_toolarge > 0)

@@ -33,8 +33,9 @@ __device__ __forceinline__ int tiny_need(int Lq, int Lr, int Lt) {
 
 // One thread per supercluster.
 __global__ void plan_kernel(BatchDev in, ScPlan *plan, int *list, PlanCounters *cnt, int force_class, int big_class) {
-    const int sc = blockIdx.x * blockDim.x + threadIdx.x;
-    if (sc >= in.n_sc) return;
+    const int sc0 = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = sc0 < in.n_sc;
+    const int sc = live ? sc0 : in.n_sc - 1;      // dead lanes recompute the last one and discard it
     ScPlan p;
     const int lr = (int)(in.ref_off[sc + 1] - in.ref_off[sc]);
     p.lr = lr;
@@ -66,13 +67,26 @@ __global__ void plan_kernel(BatchDev in, ScPlan *plan, int *list, PlanCounters *
         else cls = (force_class > CLS_TINY) ? force_class : big_class;
     }
     p.cls = cls;
-    plan[sc] = p;
-    if (cls == CLS_BAD) atomicAdd(&cnt->n_bad, 1);
-    else if (cls != CLS_TINY) {
-        list[atomicAdd(&cnt->n_list, 1)] = sc;
-        atomicAdd(&cnt->cells_list, cells);
+    if (live) plan[sc] = p;
+    // warp-aggregated counters: one atomic per warp and counter instead of one per thread
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const bool is_bad = live && cls == CLS_BAD, is_list = live && cls != CLS_BAD && cls != CLS_TINY;
+    unsigned long long c_all = live ? cells : 0ull, c_list = is_list ? cells : 0ull;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        c_all += __shfl_down_sync(full, c_all, d);
+        c_list += __shfl_down_sync(full, c_list, d);
     }
-    atomicAdd(&cnt->cells, cells);
+    const unsigned m_list = __ballot_sync(full, is_list), m_bad = __ballot_sync(full, is_bad);
+    int base = 0;
+    if (lane == 0) {
+        if (c_all) atomicAdd(&cnt->cells, c_all);
+        if (m_list) { base = atomicAdd(&cnt->n_list, __popc(m_list)); atomicAdd(&cnt->cells_list, c_list); }
+        if (m_bad) atomicAdd(&cnt->n_bad, __popc(m_bad));
+    }
+    base = __shfl_sync(full, base, 0);
+    if (is_list) list[base + __popc(m_list & ((1u << lane) - 1))] = sc;
 }
 
 // ---- fused tiny kernel --------------------------------------------------------------------
