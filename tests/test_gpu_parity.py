@@ -123,3 +123,20 @@ def test_idempotent_and_order_independent(engine):
     for k in ("assigned", "sync_group", "ref_ed", "query_ed", "callq"):
         x = a1[k].reshape(2, -1)[:, vidx]
         assert (ap[k].reshape(2, -1) == x).all(), k
+
+
+def test_chunked_pipeline_matches_single_pass():
+    """vd_run splits big batches into double-buffered chunks (H2D / kernels / D2H overlapped);
+    force tiny chunks so that a small batch crosses many chunk boundaries."""
+    b = synth.wgs_like(13, 7000, sv_frac=0.004, sv_max=600)
+    os.environ["VD_CHUNK_SC"] = "613"
+    try:
+        e = capi.Engine(0)
+    finally:
+        del os.environ["VD_CHUNK_SC"]
+    got = e.run(b)
+    want = capi.oracle_run(b)
+    assert mismatches(got.trimmed(), want.trimmed(), OUT_KEYS) == {}
+    st = e.stats()
+    assert st["cells"] == int(b.cells().sum()) and st["n_short"] + st["n_long"] == 4 * b.n_sc
+    e.close()

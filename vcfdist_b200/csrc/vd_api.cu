@@ -44,11 +44,18 @@ struct vd_handle {
     int num_sms = 148;
     std::string err;
     vd_stats stats = {};
+    unsigned stats_status_or = 0;   // OR of every status word of the last call
     int force_class = -1;           // VD_FORCE_CLASS env: testing hook (1 wave, 2 scalar slab)
     // staged input / output (vd_run)
-    DevBuf in_ref_off, in_ref_seq, in_rplane, in_var_off, in_var_pos, in_var_rlen, in_var_type,
-           in_alt_off, in_alt_seq, in_var_qual;
-    DevBuf o_score, o_endp, o_begp, o_status, o_assigned, o_sg, o_red, o_qed, o_callq;
+    struct Stage {                  // one of two staging sets of the host-buffer pipeline
+        DevBuf in_ref_off, in_ref_seq, in_rplane, in_var_off, in_var_pos, in_var_rlen, in_var_type,
+               in_alt_off, in_alt_seq, in_var_qual;
+        DevBuf o_score, o_endp, o_begp, o_status, o_assigned, o_sg, o_red, o_qed, o_callq;
+        cudaEvent_t in_done = nullptr, out_done = nullptr;
+        bool out_pending = false;
+    } stage[2];
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    int64_t chunk_sc = 393216;      // superclusters per pipeline chunk (VD_CHUNK_SC)
     // work
     DevBuf plan, list, counters, bytes, offs, cubtmp, slab, hap_ok, wave_desc;
     PlanCounters *h_counters = nullptr;     // pinned
@@ -96,8 +103,15 @@ extern "C" int vd_create(int device, int64_t scratch_bytes, vd_handle **out) {
     }
     h->scratch_budget = scratch_bytes;
     if (const char *fc = getenv("VD_FORCE_CLASS")) h->force_class = atoi(fc);
+    if (const char *cs = getenv("VD_CHUNK_SC")) h->chunk_sc = atoll(cs) > 0 ? atoll(cs) : h->chunk_sc;
+    cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking);
+    for (auto &sg : h->stage) {
+        cudaEventCreateWithFlags(&sg.in_done, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&sg.out_done, cudaEventDisableTiming);
+    }
     cudaFuncSetAttribute(tiny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (TINY_TPB / 4) * TINY_SC_BYTES + TINY_TPB * TINY_CAP);
+                         (TINY_TPB / 4) * TINY_SC_BYTES + TINY_TPB * TINY_STRIDE);
     wave_configure();
     *out = h;
     return VD_OK;
@@ -107,10 +121,17 @@ extern "C" void vd_destroy(vd_handle *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    DevBuf *bufs[] = {&h->in_ref_off, &h->in_ref_seq, &h->in_rplane, &h->in_var_off, &h->in_var_pos,
-                      &h->in_var_rlen, &h->in_var_type, &h->in_alt_off, &h->in_alt_seq, &h->in_var_qual,
-                      &h->o_score, &h->o_endp, &h->o_begp, &h->o_status, &h->o_assigned, &h->o_sg, &h->o_red,
-                      &h->o_qed, &h->o_callq, &h->plan, &h->list, &h->counters, &h->bytes, &h->offs,
+    for (auto &sg : h->stage) {
+        DevBuf *sb[] = {&sg.in_ref_off, &sg.in_ref_seq, &sg.in_rplane, &sg.in_var_off, &sg.in_var_pos, &sg.in_var_rlen,
+                        &sg.in_var_type, &sg.in_alt_off, &sg.in_alt_seq, &sg.in_var_qual, &sg.o_score, &sg.o_endp,
+                        &sg.o_begp, &sg.o_status, &sg.o_assigned, &sg.o_sg, &sg.o_red, &sg.o_qed, &sg.o_callq};
+        for (DevBuf *b : sb) b->release();
+        if (sg.in_done) cudaEventDestroy(sg.in_done);
+        if (sg.out_done) cudaEventDestroy(sg.out_done);
+    }
+    if (h->s_in) cudaStreamDestroy(h->s_in);
+    if (h->s_out) cudaStreamDestroy(h->s_out);
+    DevBuf *bufs[] = {&h->plan, &h->list, &h->counters, &h->bytes, &h->offs,
                       &h->cubtmp, &h->slab, &h->hap_ok, &h->wave_desc};
     for (DevBuf *b : bufs) b->release();
     if (h->h_counters) cudaFreeHost(h->h_counters);
@@ -132,23 +153,22 @@ extern "C" int vd_get_stats(const vd_handle *h, vd_stats *out) {
 }
 
 // The whole path on device-resident buffers.
-static int run_resident(vd_handle *h, const BatchDev &in, const OutDev &out) {
+// `out` may carry pointers shifted by the chunk's first variant (see vd_run); `base` has the true
+// buffer starts for the memsets.  Stats accumulate across the chunks of one call.
+static int run_resident(vd_handle *h, const BatchDev &in, const OutDev &out, const OutDev &base) {
     cudaStream_t st = h->stream;
     const int n_sc = in.n_sc;
     const int64_t n_var = in.n_var;
     vd_stats &S = h->stats;
-    S.n_sc = n_sc; S.n_var = n_var;
-    S.n_launches = 0; S.n_short = S.n_long = 0; S.spill_bytes = 0;
-    S.ms_short = S.ms_long_fwd = S.ms_long_bwd = S.ms_long_walk = S.ms_plan = S.ms_long_wall = 0;
-    if (n_sc == 0) { S.cells = 0; S.ms_total = 0; return VD_OK; }
+    if (n_sc == 0) return VD_OK;
 
     CK(cudaEventRecord(h->ev[0], st));
-    CK(cudaMemsetAsync(out.assigned, 0, 2 * n_var, st));
-    CK(cudaMemsetAsync(out.sync_group, 0, 8 * n_var, st));
-    CK(cudaMemsetAsync(out.ref_ed, 0, 8 * n_var, st));
-    CK(cudaMemsetAsync(out.query_ed, 0, 8 * n_var, st));
-    CK(cudaMemsetAsync(out.callq, 0, 8 * n_var, st));
-    CK(cudaMemsetAsync(out.status, 0, 16 * (size_t)n_sc, st));
+    CK(cudaMemsetAsync(base.assigned, 0, 2 * n_var, st));
+    CK(cudaMemsetAsync(base.sync_group, 0, 8 * n_var, st));
+    CK(cudaMemsetAsync(base.ref_ed, 0, 8 * n_var, st));
+    CK(cudaMemsetAsync(base.query_ed, 0, 8 * n_var, st));
+    CK(cudaMemsetAsync(base.callq, 0, 8 * n_var, st));
+    CK(cudaMemsetAsync(base.status, 0, 16 * (size_t)n_sc, st));
 
     CK(h->plan.ensure(sizeof(ScPlan) * (size_t)n_sc));
     CK(h->list.ensure(sizeof(int) * (size_t)n_sc));
@@ -166,7 +186,7 @@ static int run_resident(vd_handle *h, const BatchDev &in, const OutDev &out) {
     // ---- short superclusters: one fused launch over the whole batch ----
     {
         constexpr int SPB = TINY_TPB / 4;
-        const int smem = SPB * TINY_SC_BYTES + TINY_TPB * TINY_CAP;
+        const int smem = SPB * TINY_SC_BYTES + TINY_TPB * TINY_STRIDE;
         tiny_kernel<<<(n_sc + SPB - 1) / SPB, TINY_TPB, smem, st>>>(in, out, plan);
         S.n_launches++;
     }
@@ -174,9 +194,9 @@ static int run_resident(vd_handle *h, const BatchDev &in, const OutDev &out) {
     CK(cudaStreamSynchronize(st));          // counters are now on the host
     CK(cudaGetLastError());
     const PlanCounters pc = *h->h_counters;
-    S.cells = (int64_t)pc.cells;
-    S.n_long = 4 * (int64_t)pc.n_list;
-    S.n_short = 4 * (int64_t)(n_sc - pc.n_list - pc.n_bad);
+    S.cells += (int64_t)pc.cells;
+    S.n_long += 4 * (int64_t)pc.n_list;
+    S.n_short += 4 * (int64_t)(n_sc - pc.n_list - pc.n_bad);
 
     // ---- the rest: HBM slab, wavefront / scalar kernels ----
     float ms_fwd = 0, ms_bwd = 0, ms_walk = 0;
@@ -276,13 +296,18 @@ static int run_resident(vd_handle *h, const BatchDev &in, const OutDev &out) {
             i0 = i1;
         }
     }
+    status_or_kernel<<<296, 256, 0, st>>>(out.status, 4 * (int64_t)n_sc, &((PlanCounters *)h->counters.p)->status_or);
+    S.n_launches++;
+    CK(cudaMemcpyAsync(h->h_counters, h->counters.p, sizeof(PlanCounters), cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(h->ev[3], st));
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
-    cudaEventElapsedTime(&S.ms_plan, h->ev[0], h->ev[1]);
-    cudaEventElapsedTime(&S.ms_short, h->ev[1], h->ev[2]);
-    cudaEventElapsedTime(&S.ms_total, h->ev[0], h->ev[3]);
-    S.ms_long_fwd = ms_fwd; S.ms_long_bwd = ms_bwd; S.ms_long_walk = ms_walk;
+    h->stats_status_or |= h->h_counters->status_or;
+    float e_ = 0;
+    cudaEventElapsedTime(&e_, h->ev[0], h->ev[1]); S.ms_plan += e_;
+    cudaEventElapsedTime(&e_, h->ev[1], h->ev[2]); S.ms_short += e_;
+    cudaEventElapsedTime(&e_, h->ev[0], h->ev[3]); S.ms_total += e_;
+    S.ms_long_fwd += ms_fwd; S.ms_long_bwd += ms_bwd; S.ms_long_walk += ms_walk;
     if (pc.n_bad > 0) return fail(h, VD_E_BADINPUT, "%d malformed superclusters", pc.n_bad);
     return VD_OK;
 }
@@ -301,11 +326,11 @@ extern "C" int vd_run_device(vd_handle *h, const vd_batch_in *in, vd_batch_out *
                in->var_pos, in->var_rlen, in->var_type, in->alt_off, in->alt_seq, in->var_qual, in->max_qual, n_var};
     OutDev o{out->aln_score, out->aln_end_plane, out->aln_beg_plane, out->status, out->assigned,
              out->sync_group, out->ref_ed, out->query_ed, out->callq};
-    h->stats.h2d_bytes = h->stats.d2h_bytes = 0;
+    h->stats = vd_stats{};
+    h->stats_status_or = 0;
+    h->stats.n_sc = in->n_sc; h->stats.n_var = n_var;
     h->stats.io_bytes = io_bytes_of(in->n_sc, n_var, ref_bytes, alt_bytes);
-    int rc = run_resident(h, b, o);
-    if (rc != VD_OK) return rc;
-    return VD_OK;
+    return run_resident(h, b, o, o);
 }
 
 extern "C" int vd_run(vd_handle *h, const vd_batch_in *in, vd_batch_out *out) {
@@ -314,66 +339,114 @@ extern "C" int vd_run(vd_handle *h, const vd_batch_in *in, vd_batch_out *out) {
     cudaStream_t st = h->stream;
     const int64_t n_sc = in->n_sc;
     if (n_sc < 0) return fail(h, VD_E_BADINPUT, "negative n_sc");
-    if (n_sc == 0) { h->stats = vd_stats{}; return VD_OK; }
+    h->stats = vd_stats{};
+    h->stats_status_or = 0;
+    if (n_sc == 0) return VD_OK;
     const int64_t n_var = in->var_off[4 * n_sc];
     const int64_t ref_bytes = in->ref_off[n_sc];
     const int64_t alt_bytes = n_var ? in->alt_off[n_var] : 0;
     if (n_var < 0 || ref_bytes < 0 || alt_bytes < 0) return fail(h, VD_E_BADINPUT, "negative sizes");
-
-    int64_t h2d = 0;
-#define UP(buf, src, bytes) do { CK(h->buf.ensure((size_t)(bytes) + 16)); \
-        if ((bytes) > 0) CK(cudaMemcpyAsync(h->buf.p, (src), (size_t)(bytes), cudaMemcpyHostToDevice, st)); \
-        h2d += (bytes); } while (0)
-    UP(in_ref_off, in->ref_off, 8 * (n_sc + 1));
-    UP(in_ref_seq, in->ref_seq, ref_bytes);
-    if (in->rplane_seq) UP(in_rplane, in->rplane_seq, ref_bytes);
-    UP(in_var_off, in->var_off, 8 * (4 * n_sc + 1));
-    UP(in_var_pos, in->var_pos, 4 * n_var);
-    UP(in_var_rlen, in->var_rlen, 4 * n_var);
-    UP(in_var_type, in->var_type, n_var);
-    if (n_var) UP(in_alt_off, in->alt_off, 8 * (n_var + 1));
-    else { CK(h->in_alt_off.ensure(16)); CK(cudaMemsetAsync(h->in_alt_off.p, 0, 16, st)); }
-    UP(in_alt_seq, in->alt_seq, alt_bytes);
-    UP(in_var_qual, in->var_qual, 4 * n_var);
-#undef UP
-    CK(h->o_score.ensure(16 * (size_t)n_sc)); CK(h->o_endp.ensure(4 * (size_t)n_sc)); CK(h->o_begp.ensure(4 * (size_t)n_sc));
-    CK(h->o_status.ensure(16 * (size_t)n_sc)); CK(h->o_assigned.ensure(2 * (size_t)n_var + 16));
-    CK(h->o_sg.ensure(8 * (size_t)n_var + 16)); CK(h->o_red.ensure(8 * (size_t)n_var + 16));
-    CK(h->o_qed.ensure(8 * (size_t)n_var + 16)); CK(h->o_callq.ensure(8 * (size_t)n_var + 16));
-
-    BatchDev b{(int)n_sc, (const int64_t *)h->in_ref_off.p, (const u8 *)h->in_ref_seq.p,
-               (const u8 *)(in->rplane_seq ? h->in_rplane.p : h->in_ref_seq.p), (const int64_t *)h->in_var_off.p,
-               (const int32_t *)h->in_var_pos.p, (const int32_t *)h->in_var_rlen.p, (const u8 *)h->in_var_type.p,
-               (const int64_t *)h->in_alt_off.p, (const u8 *)h->in_alt_seq.p, (const float *)h->in_var_qual.p,
-               in->max_qual, n_var};
-    OutDev o{(int32_t *)h->o_score.p, (u8 *)h->o_endp.p, (u8 *)h->o_begp.p, (u32 *)h->o_status.p,
-             (u8 *)h->o_assigned.p, (int32_t *)h->o_sg.p, (int32_t *)h->o_red.p, (int32_t *)h->o_qed.p,
-             (float *)h->o_callq.p};
+    h->stats.n_sc = n_sc; h->stats.n_var = n_var;
     h->stats.io_bytes = io_bytes_of(n_sc, n_var, ref_bytes, alt_bytes);
-    int rc = run_resident(h, b, o);
-    if (rc != VD_OK && rc != VD_E_BADINPUT) return rc;
 
-    int64_t d2h = 0;
-#define DOWN(dst, buf, bytes) do { if ((bytes) > 0) CK(cudaMemcpyAsync((dst), h->buf.p, (size_t)(bytes), cudaMemcpyDeviceToHost, st)); \
-        d2h += (bytes); } while (0)
-    DOWN(out->aln_score, o_score, 16 * n_sc);
-    DOWN(out->aln_end_plane, o_endp, 4 * n_sc);
-    DOWN(out->aln_beg_plane, o_begp, 4 * n_sc);
-    DOWN(out->status, o_status, 16 * n_sc);
-    DOWN(out->assigned, o_assigned, 2 * n_var);
-    DOWN(out->sync_group, o_sg, 8 * n_var);
-    DOWN(out->ref_ed, o_red, 8 * n_var);
-    DOWN(out->query_ed, o_qed, 8 * n_var);
-    DOWN(out->callq, o_callq, 8 * n_var);
+    // Chunked, double-buffered pipeline: while chunk i computes, chunk i+1's inputs are copied
+    // in on s_in and chunk i-1's results are copied out on s_out.  Every chunk keeps the batch's
+    // ABSOLUTE offsets (ref_off / var_off / alt_off values); the data pointers handed to the
+    // kernels are shifted back by the chunk's first byte / variant instead.
+    const int64_t CH = h->chunk_sc;
+    const int n_chunks = (int)((n_sc + CH - 1) / CH);
+    int64_t h2d = 0, d2h = 0;
+    int rc_all = VD_OK;
+    struct Range { int64_t s0, s1, v0, v1, r0, r1, a0, a1; };
+    auto range_of = [&](int i) {
+        Range r;
+        r.s0 = (int64_t)i * CH; r.s1 = r.s0 + CH < n_sc ? r.s0 + CH : n_sc;
+        r.v0 = in->var_off[4 * r.s0]; r.v1 = in->var_off[4 * r.s1];
+        r.r0 = in->ref_off[r.s0]; r.r1 = in->ref_off[r.s1];
+        r.a0 = n_var ? in->alt_off[r.v0] : 0; r.a1 = n_var ? in->alt_off[r.v1] : 0;
+        return r;
+    };
+    auto upload = [&](int i) -> int {
+        vd_handle::Stage &sg = h->stage[i & 1];
+        const Range r = range_of(i);
+        const int64_t ns = r.s1 - r.s0, nv = r.v1 - r.v0;
+#define UP(buf, src, bytes) do { CK(sg.buf.ensure((size_t)(bytes) + 16)); \
+        if ((bytes) > 0) CK(cudaMemcpyAsync(sg.buf.p, (src), (size_t)(bytes), cudaMemcpyHostToDevice, h->s_in)); \
+        h2d += (bytes); } while (0)
+        UP(in_ref_off, in->ref_off + r.s0, 8 * (ns + 1));
+        UP(in_ref_seq, in->ref_seq + r.r0, r.r1 - r.r0);
+        if (in->rplane_seq) UP(in_rplane, in->rplane_seq + r.r0, r.r1 - r.r0);
+        UP(in_var_off, in->var_off + 4 * r.s0, 8 * (4 * ns + 1));
+        UP(in_var_pos, in->var_pos + r.v0, 4 * nv);
+        UP(in_var_rlen, in->var_rlen + r.v0, 4 * nv);
+        UP(in_var_type, in->var_type + r.v0, nv);
+        if (n_var) UP(in_alt_off, in->alt_off + r.v0, 8 * (nv + 1));
+        else { CK(sg.in_alt_off.ensure(16)); CK(cudaMemsetAsync(sg.in_alt_off.p, 0, 16, h->s_in)); }
+        UP(in_alt_seq, in->alt_seq + r.a0, r.a1 - r.a0);
+        UP(in_var_qual, in->var_qual + r.v0, 4 * nv);
+#undef UP
+        CK(cudaEventRecord(sg.in_done, h->s_in));
+        return VD_OK;
+    };
+
+    int rc = upload(0);
+    if (rc != VD_OK) return rc;
+    for (int i = 0; i < n_chunks; i++) {
+        vd_handle::Stage &sg = h->stage[i & 1];
+        const Range r = range_of(i);
+        const int64_t ns = r.s1 - r.s0, nv = r.v1 - r.v0;
+        if (i + 1 < n_chunks) { rc = upload(i + 1); if (rc != VD_OK) return rc; }
+        // result buffers of this stage are free once chunk i-2's copy-out has finished
+        if (sg.out_pending) { CK(cudaStreamWaitEvent(st, sg.out_done, 0)); sg.out_pending = false; }
+        CK(sg.o_score.ensure(16 * (size_t)ns)); CK(sg.o_endp.ensure(4 * (size_t)ns)); CK(sg.o_begp.ensure(4 * (size_t)ns));
+        CK(sg.o_status.ensure(16 * (size_t)ns)); CK(sg.o_assigned.ensure(2 * (size_t)nv + 16));
+        CK(sg.o_sg.ensure(8 * (size_t)nv + 16)); CK(sg.o_red.ensure(8 * (size_t)nv + 16));
+        CK(sg.o_qed.ensure(8 * (size_t)nv + 16)); CK(sg.o_callq.ensure(8 * (size_t)nv + 16));
+        CK(cudaStreamWaitEvent(st, sg.in_done, 0));
+
+        const u8 *d_ref = (const u8 *)sg.in_ref_seq.p - r.r0;
+        const u8 *d_rpl = in->rplane_seq ? (const u8 *)sg.in_rplane.p - r.r0 : d_ref;
+        BatchDev b{(int)ns, (const int64_t *)sg.in_ref_off.p, d_ref, d_rpl, (const int64_t *)sg.in_var_off.p,
+                   (const int32_t *)sg.in_var_pos.p - r.v0, (const int32_t *)sg.in_var_rlen.p - r.v0,
+                   (const u8 *)sg.in_var_type.p - r.v0, (const int64_t *)sg.in_alt_off.p - r.v0,
+                   (const u8 *)sg.in_alt_seq.p - r.a0, (const float *)sg.in_var_qual.p - r.v0, in->max_qual, nv};
+        OutDev base{(int32_t *)sg.o_score.p, (u8 *)sg.o_endp.p, (u8 *)sg.o_begp.p, (u32 *)sg.o_status.p,
+                    (u8 *)sg.o_assigned.p, (int32_t *)sg.o_sg.p, (int32_t *)sg.o_red.p, (int32_t *)sg.o_qed.p,
+                    (float *)sg.o_callq.p};
+        OutDev o = base;                       // per-variant arrays are indexed [slot*nv + (v - v0)]
+        o.assigned -= r.v0; o.sync_group -= r.v0; o.ref_ed -= r.v0; o.query_ed -= r.v0; o.callq -= r.v0;
+        rc = run_resident(h, b, o, base);      // returns with the chunk's kernels finished
+        if (rc != VD_OK && rc != VD_E_BADINPUT) return rc;
+        if (rc != VD_OK) rc_all = rc;
+
+#define DOWN(dst, buf, off, bytes) do { if ((bytes) > 0) CK(cudaMemcpyAsync((dst), (const u8 *)sg.buf.p + (off), \
+        (size_t)(bytes), cudaMemcpyDeviceToHost, h->s_out)); d2h += (bytes); } while (0)
+        DOWN(out->aln_score + 4 * r.s0, o_score, 0, 16 * ns);
+        DOWN(out->aln_end_plane + 4 * r.s0, o_endp, 0, 4 * ns);
+        DOWN(out->aln_beg_plane + 4 * r.s0, o_begp, 0, 4 * ns);
+        DOWN(out->status + 4 * r.s0, o_status, 0, 16 * ns);
+        for (int slot = 0; slot < 2; slot++) {
+            const int64_t ho = slot * n_var + r.v0, so = slot * nv;
+            DOWN(out->assigned + ho, o_assigned, so, nv);
+            DOWN(out->sync_group + ho, o_sg, 4 * so, 4 * nv);
+            DOWN(out->ref_ed + ho, o_red, 4 * so, 4 * nv);
+            DOWN(out->query_ed + ho, o_qed, 4 * so, 4 * nv);
+            DOWN(out->callq + ho, o_callq, 4 * so, 4 * nv);
+        }
 #undef DOWN
-    CK(cudaStreamSynchronize(st));
+        CK(cudaEventRecord(sg.out_done, h->s_out));
+        sg.out_pending = true;
+    }
+    CK(cudaStreamSynchronize(h->s_out));
+    h->stage[0].out_pending = h->stage[1].out_pending = false;
     h->stats.h2d_bytes = h2d;
     h->stats.d2h_bytes = d2h;
-    if (rc != VD_OK) return rc;
-    // fatal reference conditions are reported, results stay available for inspection
-    for (int64_t i = 0; i < 4 * n_sc; i++)
-        if (out->status[i] & VD_ST_ERR_MASK)
-            return fail(h, VD_E_ALIGN, "alignment %lld of supercluster %lld: status 0x%x", (long long)(i & 3),
-                        (long long)(i >> 2), out->status[i]);
+    if (rc_all != VD_OK) return rc_all;
+    // fatal reference conditions are reported; results stay available for inspection
+    if (h->stats_status_or & VD_ST_ERR_MASK)
+        for (int64_t i = 0; i < 4 * n_sc; i++)
+            if (out->status[i] & VD_ST_ERR_MASK)
+                return fail(h, VD_E_ALIGN, "alignment %lld of supercluster %lld: status 0x%x", (long long)(i & 3),
+                            (long long)(i >> 2), out->status[i]);
     return VD_OK;
 }

@@ -15,6 +15,8 @@ constexpr int TINY_TPB = 128;          // threads per block = 32 superclusters
 constexpr int TINY_TL = 16;            // max haplotype length
 constexpr int TINY_TR = 12;            // max window (REF plane) length
 constexpr int TINY_CAP = 320;          // private shared-memory bytes per alignment
+constexpr int TINY_STRIDE = TINY_CAP + 4;   // private slice stride: odd number of words -> conflict-free
+static_assert(((TINY_STRIDE / 4) & 1) == 1, "private slice stride must be an odd number of words");
 constexpr int TINY_SW = (TINY_TL + TINY_TR + 1 + 3) & ~3;      // one CSR swap table
 constexpr int TINY_SC_BYTES = 4 * (3 * TINY_TL + TINY_TR) + 2 * (2 * TINY_TR + 2 * TINY_SW) + TINY_TR + 8;   // per-supercluster shared area
 
@@ -25,7 +27,16 @@ struct PlanCounters {
     int n_bad;
     unsigned long long cells;
     unsigned long long cells_list;
+    unsigned status_or;
 };
+
+// OR of all status words (so that the host only scans them when an error bit is set)
+__global__ void status_or_kernel(const u32 *status, int64_t n, unsigned *dst) {
+    unsigned v = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) v |= status[i];
+    v = __reduce_or_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0 && v) atomicOr(dst, v);
+}
 
 __device__ __forceinline__ int tiny_need(int Lq, int Lr, int Lt) {
     return make_layout<int, 2, true>(Lq + Lr, Lt, Lr).total;
@@ -116,7 +127,7 @@ tiny_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan) {
     const int sc = blockIdx.x * SPB + quad;
     const bool active = sc < in.n_sc && plan[sc].cls == CLS_TINY;
     TinyArea A{smem + quad * TINY_SC_BYTES};
-    SMemIL mem{smem + SPB * TINY_SC_BYTES, tid, TINY_TPB};
+    SMemIL mem{smem + SPB * TINY_SC_BYTES + tid * TINY_STRIDE};
 
     int lr = 0;
     if (active) {

@@ -3,7 +3,7 @@
 //
 // The same code runs in two places, selected by the memory accessor:
 //   * the fused short-supercluster kernel (vd_tiny.cu): every matrix of the alignment lives
-//     in shared memory, word-interleaved across the block's threads (bank-conflict free
+//     in shared memory, one slice per thread with an odd word stride (bank-conflict free
 //     when lanes touch the same offset);
 //   * the scalar fallback kernel (vd_wave.cu): matrices in an HBM scratch slab, for shapes
 //     the wavefront kernels do not take (e.g. more than two swap sources per row).
@@ -28,15 +28,14 @@ struct GMem {                      // plain HBM slab
     __device__ __forceinline__ void st32(off_t o, int v) const { *(int *)(p + o) = v; }
 };
 
-struct SMemIL {                    // shared memory, 32-bit words interleaved across threads
-    typedef int off_t;
-    u8 *base;                      // block pool
-    int tid, tpb;
-    __device__ __forceinline__ u8 *at(int o) const { return base + (((o >> 2) * tpb + tid) << 2) + (o & 3); }
-    __device__ __forceinline__ int ld8(int o) const { return *at(o); }
-    __device__ __forceinline__ void st8(int o, int v) const { *at(o) = (u8)v; }
-    __device__ __forceinline__ int ld16(int o) const { return *(const short *)at(o); }
-    __device__ __forceinline__ void st16(int o, int v) const { *(short *)at(o) = (short)v; }
+struct SMemIL {                    // shared memory: one contiguous slice per thread whose stride is an
+    typedef int off_t;             // ODD number of 32-bit words, so that lanes touching the same offset
+    u8 *base;                      // hit 32 different banks (no interleaving arithmetic per access)
+    __device__ __forceinline__ u8 *at(int o) const { return base + o; }
+    __device__ __forceinline__ int ld8(int o) const { return base[o]; }
+    __device__ __forceinline__ void st8(int o, int v) const { base[o] = (u8)v; }
+    __device__ __forceinline__ int ld16(int o) const { return *(const short *)(base + o); }
+    __device__ __forceinline__ void st16(int o, int v) const { *(short *)(base + o) = (short)v; }
 };
 
 // value accessors: W = element width of the D / T / path / lev arrays (4 in HBM, 2 in smem)
