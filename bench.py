@@ -264,7 +264,7 @@ def main():
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches = 0
-    ms_short = ms_fwd = ms_bwd = ms_walk = ms_plan = ms_kernels = 0.0
+    ms_short = ms_fwd = ms_bwd = ms_walk = ms_plan = ms_kernels = ms_mid = 0.0
     barrier()
     ev0.record(stream)
     for _ in range(args.steps):
@@ -272,7 +272,7 @@ def main():
         st = eng.stats()
         launches += st["n_launches"]
         ms_short += st["ms_short"]; ms_fwd += st["ms_long_fwd"]; ms_bwd += st["ms_long_bwd"]
-        ms_walk += st["ms_long_walk"]; ms_plan += st["ms_plan"]; ms_kernels += st["ms_total"]
+        ms_walk += st["ms_long_walk"]; ms_plan += st["ms_plan"]; ms_kernels += st["ms_total"]; ms_mid += st["ms_mid"]
     ev1.record(stream)
     barrier()
     ms = ev0.elapsed_time(ev1)
@@ -344,7 +344,7 @@ def main():
                     "h2d_bytes_per_step": int(st_e["h2d_bytes"]), "d2h_bytes_per_step": int(st_e["d2h_bytes"]),
                     "api": "vd_run (C-ABI, pinned host buffers)"},
             "gpu_launches": int(launches),
-            "kernel_ms_per_step": {"plan": ms_plan / args.steps, "tiny": k_short, "wave_fwd": k_fwd, "wave_bwd": k_bwd,
+            "kernel_ms_per_step": {"plan": ms_plan / args.steps, "tiny": k_short, "mid": ms_mid / args.steps, "wave_fwd": k_fwd, "wave_bwd": k_bwd,
                                    "wave_walk": ms_walk / args.steps, "all_kernels": ms_kernels / args.steps},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,

@@ -134,6 +134,7 @@ typedef struct vd_stats {
     float   ms_long_fwd, ms_long_bwd, ms_long_walk;
     float   ms_plan;
     float   ms_long_wall;     /* wall time of the concurrent forward+backward region            */
+    float   ms_mid;           /* ... of the fused mid-size kernel (summed over its classes)       */
 } vd_stats;
 
 /* Final per-variant / per-supercluster results in the reference's own terms

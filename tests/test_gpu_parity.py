@@ -45,10 +45,11 @@ def test_golden_through_c_abi(engine, name):
     assert mismatches(fin, refA, FINAL_KEYS, var_mask=mask) == {}
 
 
-@pytest.mark.parametrize("cls", [1, 2])
-@pytest.mark.parametrize("name", ["demo", "adv_11", "sv_21"])
+@pytest.mark.parametrize("cls", [1, 2, 4])
+@pytest.mark.parametrize("name", ["demo", "adv_11", "adv_12", "sv_21"])
 def test_every_kernel_family_on_golden(name, cls):
-    """Force all superclusters through the wavefront (1) or scalar-slab (2) kernels."""
+    """Force all superclusters through the wavefront (1), scalar-slab (2) or fused mid-size (4) kernels
+    (4: whatever does not fit shared memory falls through to the wavefront kernels)."""
     b, _, refB = load_golden(name)
     e = forced_engine(cls)
     got = check_vs_oracle(e, b)

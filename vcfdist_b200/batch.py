@@ -75,7 +75,7 @@ class vd_stats(C.Structure):
         ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
         ("ms_total", C.c_float), ("ms_short", C.c_float),
         ("ms_long_fwd", C.c_float), ("ms_long_bwd", C.c_float), ("ms_long_walk", C.c_float),
-        ("ms_plan", C.c_float), ("ms_long_wall", C.c_float),
+        ("ms_plan", C.c_float), ("ms_long_wall", C.c_float), ("ms_mid", C.c_float),
     ]
 
     def as_dict(self):

@@ -16,6 +16,7 @@
 
 #include "vd_kernels.cuh"
 #include "vd_wave.cuh"
+#include "vd_mid.cuh"
 
 using namespace vd;
 
@@ -40,6 +41,7 @@ struct vd_handle {
     cudaEvent_t ev[8] = {};
     cudaStream_t side[vd::N_WCLS] = {};     // one stream per wavefront class: classes run concurrently
     cudaEvent_t sev[vd::N_WCLS][3] = {};
+    cudaEvent_t mev[vd::N_MCLS][2] = {};
     int64_t scratch_budget = 0;
     int num_sms = 148;
     std::string err;
@@ -57,7 +59,7 @@ struct vd_handle {
     cudaStream_t s_in = nullptr, s_out = nullptr;
     int64_t chunk_sc = 393216;      // superclusters per pipeline chunk (VD_CHUNK_SC)
     // work
-    DevBuf plan, list, counters, bytes, offs, cubtmp, slab, hap_ok, wave_desc;
+    DevBuf plan, list, mlist, counters, bytes, offs, cubtmp, slab, hap_ok, wave_desc;
     PlanCounters *h_counters = nullptr;     // pinned
 };
 
@@ -95,6 +97,7 @@ extern "C" int vd_create(int device, int64_t scratch_bytes, vd_handle **out) {
         cudaStreamCreateWithFlags(&h->side[c], cudaStreamNonBlocking);
         for (auto &e : h->sev[c]) cudaEventCreate(&e);
     }
+    for (int c = 0; c < N_MCLS; c++) for (auto &e : h->mev[c]) cudaEventCreate(&e);
     cudaMallocHost((void **)&h->h_counters, sizeof(PlanCounters));
     if (scratch_bytes <= 0) {
         size_t fr = 0, tot = 0;
@@ -113,6 +116,7 @@ extern "C" int vd_create(int device, int64_t scratch_bytes, vd_handle **out) {
     cudaFuncSetAttribute(tiny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (TINY_TPB / 4) * TINY_SC_BYTES + TINY_TPB * TINY_STRIDE);
     wave_configure();
+    mid_configure();
     *out = h;
     return VD_OK;
 }
@@ -131,13 +135,14 @@ extern "C" void vd_destroy(vd_handle *h) {
     }
     if (h->s_in) cudaStreamDestroy(h->s_in);
     if (h->s_out) cudaStreamDestroy(h->s_out);
-    DevBuf *bufs[] = {&h->plan, &h->list, &h->counters, &h->bytes, &h->offs,
+    DevBuf *bufs[] = {&h->plan, &h->list, &h->mlist, &h->counters, &h->bytes, &h->offs,
                       &h->cubtmp, &h->slab, &h->hap_ok, &h->wave_desc};
     for (DevBuf *b : bufs) b->release();
     if (h->h_counters) cudaFreeHost(h->h_counters);
     for (auto &e : h->ev) if (e) cudaEventDestroy(e);
     for (int c = 0; c < N_WCLS; c++) {
         for (auto &e : h->sev[c]) if (e) cudaEventDestroy(e);
+        if (c < N_MCLS) for (auto &e : h->mev[c]) if (e) cudaEventDestroy(e);
         if (h->side[c]) cudaStreamDestroy(h->side[c]);
     }
     cudaStreamDestroy(h->stream);
@@ -172,12 +177,13 @@ static int run_resident(vd_handle *h, const BatchDev &in, const OutDev &out, con
 
     CK(h->plan.ensure(sizeof(ScPlan) * (size_t)n_sc));
     CK(h->list.ensure(sizeof(int) * (size_t)n_sc));
+    CK(h->mlist.ensure(sizeof(int) * (size_t)n_sc * N_MCLS));
     CK(h->counters.ensure(sizeof(PlanCounters)));
     CK(cudaMemsetAsync(h->counters.p, 0, sizeof(PlanCounters), st));
     ScPlan *plan = (ScPlan *)h->plan.p;
     int *list = (int *)h->list.p;
 
-    plan_kernel<<<(n_sc + 255) / 256, 256, 0, st>>>(in, plan, list, (PlanCounters *)h->counters.p,
+    plan_kernel<<<(n_sc + 255) / 256, 256, 0, st>>>(in, plan, list, (int *)h->mlist.p, (PlanCounters *)h->counters.p,
                                                     h->force_class, kBigClass);
     S.n_launches++;
     CK(cudaMemcpyAsync(h->h_counters, h->counters.p, sizeof(PlanCounters), cudaMemcpyDeviceToHost, st));
@@ -197,6 +203,20 @@ static int run_resident(vd_handle *h, const BatchDev &in, const OutDev &out, con
     S.cells += (int64_t)pc.cells;
     S.n_long += 4 * (int64_t)pc.n_list;
     S.n_short += 4 * (int64_t)(n_sc - pc.n_list - pc.n_bad);
+
+    // ---- mid-size superclusters: fused shared-memory kernel, one launch per rows-per-lane class,
+    //      on the side streams so that they overlap with the slab path below ----
+    bool mid_used[N_MCLS] = {};
+    for (int kc = 0; kc < N_MCLS; kc++) {
+        if (!pc.n_mid[kc]) continue;
+        cudaStream_t ss = h->side[kc];
+        CK(cudaStreamWaitEvent(ss, h->ev[2], 0));
+        CK(cudaEventRecord(h->mev[kc][0], ss));
+        mid_launch(ss, kc, pc.n_mid[kc], pc.mid_smem[kc], in, out, plan, (const int *)h->mlist.p + (int64_t)kc * n_sc);
+        CK(cudaEventRecord(h->mev[kc][1], ss));
+        S.n_launches++;
+        mid_used[kc] = true;
+    }
 
     // ---- the rest: HBM slab, wavefront / scalar kernels ----
     float ms_fwd = 0, ms_bwd = 0, ms_walk = 0;
@@ -296,6 +316,7 @@ static int run_resident(vd_handle *h, const BatchDev &in, const OutDev &out, con
             i0 = i1;
         }
     }
+    for (int kc = 0; kc < N_MCLS; kc++) if (mid_used[kc]) CK(cudaStreamWaitEvent(st, h->mev[kc][1], 0));
     status_or_kernel<<<296, 256, 0, st>>>(out.status, 4 * (int64_t)n_sc, &((PlanCounters *)h->counters.p)->status_or);
     S.n_launches++;
     CK(cudaMemcpyAsync(h->h_counters, h->counters.p, sizeof(PlanCounters), cudaMemcpyDeviceToHost, st));
@@ -308,6 +329,8 @@ static int run_resident(vd_handle *h, const BatchDev &in, const OutDev &out, con
     cudaEventElapsedTime(&e_, h->ev[1], h->ev[2]); S.ms_short += e_;
     cudaEventElapsedTime(&e_, h->ev[0], h->ev[3]); S.ms_total += e_;
     S.ms_long_fwd += ms_fwd; S.ms_long_bwd += ms_bwd; S.ms_long_walk += ms_walk;
+    for (int kc = 0; kc < N_MCLS; kc++)
+        if (mid_used[kc]) { cudaEventElapsedTime(&e_, h->mev[kc][0], h->mev[kc][1]); S.ms_mid += e_; }
     if (pc.n_bad > 0) return fail(h, VD_E_BADINPUT, "%d malformed superclusters", pc.n_bad);
     return VD_OK;
 }

@@ -53,7 +53,7 @@ struct OutDev {
 };
 
 // classes decided by the plan kernel
-enum : int { CLS_TINY = 0, CLS_WAVE = 1, CLS_SCALAR = 2, CLS_BAD = 3 };
+enum : int { CLS_TINY = 0, CLS_WAVE = 1, CLS_SCALAR = 2, CLS_BAD = 3, CLS_MID = 4 };
 
 // per-supercluster plan record
 struct ScPlan {

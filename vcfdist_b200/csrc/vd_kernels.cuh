@@ -7,6 +7,7 @@
 // The wavefront kernels for long superclusters are in vd_wave.cuh.
 #pragma once
 #include "vd_scalar.cuh"
+#include "vd_midlayout.cuh"
 
 namespace vd {
 
@@ -28,6 +29,8 @@ struct PlanCounters {
     unsigned long long cells;
     unsigned long long cells_list;
     unsigned status_or;
+    int n_mid[N_MCLS];                 // superclusters of the fused mid-size kernel, per rows-per-lane class
+    int mid_smem[N_MCLS];              // largest shared-memory need in each class
 };
 
 // OR of all status words (so that the host only scans them when an error bit is set)
@@ -43,7 +46,7 @@ __device__ __forceinline__ int tiny_need(int Lq, int Lr, int Lt) {
 }
 
 // One thread per supercluster.
-__global__ void plan_kernel(BatchDev in, ScPlan *plan, int *list, PlanCounters *cnt, int force_class, int big_class) {
+__global__ void plan_kernel(BatchDev in, ScPlan *plan, int *list, int *mlist, PlanCounters *cnt, int force_class, int big_class) {
     const int sc0 = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = sc0 < in.n_sc;
     const int sc = live ? sc0 : in.n_sc - 1;      // dead lanes recompute the last one and discard it
@@ -75,14 +78,24 @@ __global__ void plan_kernel(BatchDev in, ScPlan *plan, int *list, PlanCounters *
             if (tiny) tiny = tiny_need(lq, lr, lt) <= TINY_CAP;
         }
         if (tiny && force_class < 0) cls = CLS_TINY;
-        else cls = (force_class > CLS_TINY) ? force_class : big_class;
+        else {
+            const int kc = mid_kclass(p);
+            const int need = kc >= 0 ? mid_layout(p, 1 << kc).total : (1 << 30);
+            if ((force_class < 0 || force_class == CLS_MID) && need <= MID_SMEM_MAX) {
+                cls = CLS_MID;
+                if (live) {
+                    mlist[(int64_t)kc * in.n_sc + atomicAdd(&cnt->n_mid[kc], 1)] = sc;
+                    atomicMax(&cnt->mid_smem[kc], need);
+                }
+            } else cls = (force_class > CLS_TINY && force_class != CLS_MID) ? force_class : big_class;
+        }
     }
     p.cls = cls;
     if (live) plan[sc] = p;
     // warp-aggregated counters: one atomic per warp and counter instead of one per thread
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const bool is_bad = live && cls == CLS_BAD, is_list = live && cls != CLS_BAD && cls != CLS_TINY;
+    const bool is_bad = live && cls == CLS_BAD, is_list = live && (cls == CLS_WAVE || cls == CLS_SCALAR);
     unsigned long long c_all = live ? cells : 0ull, c_list = is_list ? cells : 0ull;
 #pragma unroll
     for (int d = 16; d; d >>= 1) {

@@ -29,31 +29,30 @@ constexpr int NEG = -(1 << 28);
 // ---- per-hap tables the wavefront kernels need, built once per supercluster --------------
 // srcinfo: bit0 valid, bits1-3 k (index in the destination's source list), bit4 tp(dest),
 //          bits 8.. destination row (plane-local)
-__device__ inline void build_srcinfo(const int *ptr, const u8 *flg, int nsrc,      // sources
-                                     const int *tab, int ndst,                    // dest CSR
-                                     const u8 *dflg, const int *dptr,             // dest plane flags / hap->ref ptrs (tp), dptr null for REF dest
+template <class PT>
+__device__ inline void build_srcinfo(const PT *ptr, const u8 *flg, int nsrc,       // sources
+                                     const PT *tab, int ndst,                     // dest CSR
+                                     const u8 *dflg, const PT *dptr,              // dest plane flags / hap->ref ptrs (tp), dptr null for REF dest
                                      int *info) {
-    const int *src = tab + ndst + 1;
     int n = 0;      // running position in the CSR source array (ascending b)
     for (int b = 0; b < nsrc; b++) {
         const int f = flg[b];
         int v = 0;
         const bool ok = !(f & P_VARIANT) || (f & P_VAR_END);
-        const int d = ptr[b] + 1;
+        const int d = (int)ptr[b] + 1;
         if (ok && d >= 0 && d < ndst) {
-            // src[n] == b by construction
-            const int k = n - tab[d];
+            // the n-th admitted source is CSR entry n (ascending b)
+            const int k = n - (int)tab[d];
             n++;
             const int df = dflg[d];
             if (d > 0 && (!(df & P_VARIANT) || (df & P_VAR_BEG))) {               // :600-602, :638-640
                 int tp = 0;
-                if (dptr) tp = (dptr[d] != dptr[d - 1] + 1) || (df & P_VAR_BEG);  // :656-658
+                if (dptr) tp = ((int)dptr[d] != (int)dptr[d - 1] + 1) || (df & P_VAR_BEG);  // :656-658
                 v = 1 | (k << 1) | (tp << 4) | (d << 8);
             }
         }
         info[b] = v;
     }
-    (void)src;
 }
 
 struct WaveHapQ {        // extra per query hap
@@ -159,9 +158,9 @@ __global__ void wave_tables_kernel(const ScPlan *plan, const int *list, int i0, 
         SlabQm M(base + W.base.qm[h], p.len[h], p.lr);
         WaveHapQ X(base + W.hq[h], p.len[h], p.lr);
         // QUERY rows as sources -> destinations on REF (CSR toR); dest flags = rflg, no tp on REF
-        build_srcinfo(H.ptr, H.flg, p.len[h], M.toR, p.lr, M.rflg, nullptr, X.srcQ);
+        build_srcinfo<int>(H.ptr, H.flg, p.len[h], M.toR, p.lr, M.rflg, nullptr, X.srcQ);
         // REF rows as sources -> destinations on QUERY (CSR toQ); dest flags = hap flags, tp from hap ptrs
-        build_srcinfo(M.rptr, M.rflg, p.lr, M.toQ, p.len[h], H.flg, H.ptr, X.srcR);
+        build_srcinfo<int>(M.rptr, M.rflg, p.lr, M.toQ, p.len[h], H.flg, H.ptr, X.srcR);
         for (int a = 0; a < p.len[h]; a++)
             X.tpb[a] = (a > 0 && ((H.ptr[a] != H.ptr[a - 1] + 1) || (H.flg[a] & P_VAR_BEG))) ? 1 : 0;
     } else {
@@ -228,12 +227,14 @@ struct WaveArgs {
 };
 
 // everything a block needs about its alignment
-struct WaveCtx {
+template <class TT> struct WaveCtxT {      // TT: element type of the CSR swap tables (int in HBM, short in smem)
     int sc, ai, Lq, Lr, Lt, padQ, NP;
     const u8 *qstr, *rseq, *tinfo, *qflg, *rflg, *tpb;
-    const int *toQ, *toR, *srcQ, *srcR;
+    const TT *toQ, *toR;
+    const int *srcQ, *srcR;
     u8 *F;
 };
+typedef WaveCtxT<int> WaveCtx;
 __device__ inline WaveCtx wave_ctx(const WaveArgs &A, int item) {
     WaveCtx x;
     const int e = item >> 2;
@@ -290,23 +291,24 @@ template <int TPB> __device__ __forceinline__ void block_sync() {
 // ------------------------------------------------------------------------------------------
 // forward: calc_prec_recall_aln (:251-443) as a column sweep
 // ------------------------------------------------------------------------------------------
-template <int TPB, int K>
-__global__ void __launch_bounds__(TPB) wave_fwd_kernel(WaveArgs A, int item0) {
-    extern __shared__ __align__(16) u8 smem_raw[];
-    const WaveCtx X = wave_ctx(A, A.items[item0 + blockIdx.x]);
+// t = thread index within the TPB-thread group working on this alignment; smem_raw = that group's
+// scratch (wave_fwd_smem bytes); sEnd = two ints of shared scratch.  Returns score / end plane to
+// every thread of the group.
+template <int TPB, int K, class TT>
+__device__ __forceinline__ void wave_fwd_body(const WaveCtxT<TT> &X, const int t, u8 *smem_raw, int *sEnd,
+                                              int &score, int &end_plane) {
     constexpr int NPMAX = TPB * K;
     u16 *sD0 = (u16 *)smem_raw, *sD1 = sD0 + NPMAX;          // previous / current column, both planes
     int *sW = (int *)(sD1 + NPMAX);                          // [2 segments][32 warps] scan totals
-    __shared__ int sEnd[2];
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int lane = t & 31, warp = t >> 5;
     const int tQ = X.padQ / K;                               // first thread of the REF plane
     const bool P = t >= tQ;
     const int row0 = t * K;
     const int a0 = P ? row0 - X.padQ : row0;
     const int len = P ? X.Lr : X.Lq;
     const u8 *seq = P ? X.rseq : X.qstr;
-    const int *tab = P ? X.toR : X.toQ;                      // CSR of swap sources of my plane's rows
-    const int *src = tab + len + 1;
+    const TT *tab = P ? X.toR : X.toQ;                       // CSR of swap sources of my plane's rows
+    const TT *src = tab + len + 1;
     const int obase = P ? 0 : X.padQ;                        // padded row offset of the other plane
     const int segstart = P ? tQ : 0;
 
@@ -442,26 +444,36 @@ __global__ void __launch_bounds__(TPB) wave_fwd_kernel(WaveArgs A, int item0) {
             for (int j = 0; j < K; j++) if (row0 + j == rr) sEnd[1] = Dp[j];
         }
         block_sync<TPB>();
-        if (t == 0) {
-            const int s = min(sEnd[0], sEnd[1]);
-            A.out.aln_score[4 * (int64_t)X.sc + X.ai] = s;
-            A.out.aln_end_plane[4 * (int64_t)X.sc + X.ai] = (u8)(sEnd[0] == s ? 0 : 1);
-        }
+        score = min(sEnd[0], sEnd[1]);
+        end_plane = sEnd[0] == score ? 0 : 1;
+    }
+}
+
+template <int TPB, int K>
+__global__ void __launch_bounds__(TPB) wave_fwd_kernel(WaveArgs A, int item0) {
+    extern __shared__ __align__(16) u8 smem_raw[];
+    __shared__ int sEnd[2];
+    const WaveCtx X = wave_ctx(A, A.items[item0 + blockIdx.x]);
+    int score, end_plane;
+    wave_fwd_body<TPB, K, int>(X, threadIdx.x, smem_raw, sEnd, score, end_plane);
+    if (threadIdx.x == 0) {
+        A.out.aln_score[4 * (int64_t)X.sc + X.ai] = score;
+        A.out.aln_end_plane[4 * (int64_t)X.sc + X.ai] = (u8)end_plane;
     }
 }
 
 // ------------------------------------------------------------------------------------------
 // backward: calc_prec_recall_path (:486-834) as a reverse column sweep, path flags in place
 // ------------------------------------------------------------------------------------------
-template <int TPB, int K>
-__global__ void __launch_bounds__(TPB) wave_bwd_kernel(WaveArgs A, int item0) {
-    extern __shared__ __align__(16) u8 smem_raw[];
-    const WaveCtx X = wave_ctx(A, A.items[item0 + blockIdx.x]);
+// Returns the origin plane (valid on t == 0) and this thread's status bits.
+template <int TPB, int K, class TT>
+__device__ __forceinline__ void wave_bwd_body(const WaveCtxT<TT> &X, const int t, u8 *smem_raw, const int end_plane,
+                                              int &beg_plane, u32 &status_out) {
     constexpr int NPMAX = TPB * K;
     short *sT0 = (short *)smem_raw, *sT1 = sT0 + NPMAX;      // T of column c+1 / c, all rows
     u8 *sF0 = (u8 *)(sT1 + NPMAX), *sF1 = sF0 + NPMAX;       // forward flags of column c+1 / c
     int *sW = (int *)(sF1 + NPMAX);                          // [32 warps][2] scan summaries
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int lane = t & 31, warp = t >> 5;
     const int tQ = X.padQ / K;
     const bool P = t >= tQ;
     const int row0 = t * K;
@@ -470,7 +482,6 @@ __global__ void __launch_bounds__(TPB) wave_bwd_kernel(WaveArgs A, int item0) {
     const u8 *seq = P ? X.rseq : X.qstr;
     const int *sinfo = P ? X.srcR : X.srcQ;                  // my rows as swap SOURCES
     const int dbase = P ? 0 : X.padQ;                        // padded row offset of the destination plane
-    const int end_plane = A.out.aln_end_plane[4 * (int64_t)X.sc + X.ai];
     const int erow = end_plane ? X.padQ + X.Lr - 1 : X.Lq - 1;
 
     u8 ch[K + 1];                                            // bases of rows a0 .. a0+K (one past, for the diagonal)
@@ -638,7 +649,7 @@ __global__ void __launch_bounds__(TPB) wave_bwd_kernel(WaveArgs A, int item0) {
         }
         // in-place: the path flags replace the forward flags of column c
 #ifdef VD_DEBUG
-        if (blockIdx.x == 0 && row0 < X.NP)
+        if (row0 < X.NP)
             printf("bwd c=%d t=%d row0=%d P=%d a0=%d len=%d Fc0=%x B0=%d Tl0=%d toplink=%d Aw=%d Ms=%d Tfirst=%d Xin=%d Tc0=%d pf0=%x Tup=%d Fup=%x erow=%d\n",
                    c, t, row0, (int)P, a0, len, byte_of(Fc, 0), B[0], Tl0, (int)toplink, Aw, Ms, Tfirst, Xin, Tc[0], byte_of(pfw, 0), Tup, Fup, erow);
 #endif
@@ -652,7 +663,19 @@ __global__ void __launch_bounds__(TPB) wave_bwd_kernel(WaveArgs A, int item0) {
         block_sync<TPB>();
     }
     // origin plane (:811-814): QUERY if its origin was reached
-    if (t == 0) A.out.aln_beg_plane[4 * (int64_t)X.sc + X.ai] = (u8)(Tn[0] >= 0 ? 0 : 1);
+    beg_plane = Tn[0] >= 0 ? 0 : 1;
+    status_out = status;
+}
+
+template <int TPB, int K>
+__global__ void __launch_bounds__(TPB) wave_bwd_kernel(WaveArgs A, int item0) {
+    extern __shared__ __align__(16) u8 smem_raw[];
+    const WaveCtx X = wave_ctx(A, A.items[item0 + blockIdx.x]);
+    const int end_plane = A.out.aln_end_plane[4 * (int64_t)X.sc + X.ai];
+    int beg_plane;
+    u32 status;
+    wave_bwd_body<TPB, K, int>(X, threadIdx.x, smem_raw, end_plane, beg_plane, status);
+    if (threadIdx.x == 0) A.out.aln_beg_plane[4 * (int64_t)X.sc + X.ai] = (u8)beg_plane;
     if (status) atomicOr(&A.out.status[4 * (int64_t)X.sc + X.ai], status);
 }
 
