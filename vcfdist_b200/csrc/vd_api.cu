@@ -140,9 +140,9 @@ extern "C" void vd_destroy(vd_handle *h) {
     for (DevBuf *b : bufs) b->release();
     if (h->h_counters) cudaFreeHost(h->h_counters);
     for (auto &e : h->ev) if (e) cudaEventDestroy(e);
+    for (int c = 0; c < N_MCLS; c++) for (auto &e : h->mev[c]) if (e) cudaEventDestroy(e);
     for (int c = 0; c < N_WCLS; c++) {
         for (auto &e : h->sev[c]) if (e) cudaEventDestroy(e);
-        if (c < N_MCLS) for (auto &e : h->mev[c]) if (e) cudaEventDestroy(e);
         if (h->side[c]) cudaStreamDestroy(h->side[c]);
     }
     cudaStreamDestroy(h->stream);
@@ -177,7 +177,7 @@ static int run_resident(vd_handle *h, const BatchDev &in, const OutDev &out, con
 
     CK(h->plan.ensure(sizeof(ScPlan) * (size_t)n_sc));
     CK(h->list.ensure(sizeof(int) * (size_t)n_sc));
-    CK(h->mlist.ensure(sizeof(int) * (size_t)n_sc * N_MCLS));
+    CK(h->mlist.ensure(sizeof(int) * (size_t)n_sc));
     CK(h->counters.ensure(sizeof(PlanCounters)));
     CK(cudaMemsetAsync(h->counters.p, 0, sizeof(PlanCounters), st));
     ScPlan *plan = (ScPlan *)h->plan.p;
@@ -207,15 +207,25 @@ static int run_resident(vd_handle *h, const BatchDev &in, const OutDev &out, con
     // ---- mid-size superclusters: fused shared-memory kernel, one launch per rows-per-lane class,
     //      on the side streams so that they overlap with the slab path below ----
     bool mid_used[N_MCLS] = {};
-    for (int kc = 0; kc < N_MCLS; kc++) {
-        if (!pc.n_mid[kc]) continue;
-        cudaStream_t ss = h->side[kc];
-        CK(cudaStreamWaitEvent(ss, h->ev[2], 0));
-        CK(cudaEventRecord(h->mev[kc][0], ss));
-        mid_launch(ss, kc, pc.n_mid[kc], pc.mid_smem[kc], in, out, plan, (const int *)h->mlist.p + (int64_t)kc * n_sc);
-        CK(cudaEventRecord(h->mev[kc][1], ss));
-        S.n_launches++;
-        mid_used[kc] = true;
+    {
+        MidBase mb;
+        int n_mid = 0;
+        for (int mc = 0; mc < N_MCLS; mc++) { mb.b[mc] = n_mid; n_mid += pc.n_mid[mc]; }
+        if (n_mid > 0) {
+            mid_fill_kernel<<<(n_sc + 255) / 256, 256, 0, st>>>(plan, n_sc, (PlanCounters *)h->counters.p, mb, (int *)h->mlist.p);
+            S.n_launches++;
+            CK(cudaEventRecord(h->ev[5], st));
+            for (int mc = 0; mc < N_MCLS; mc++) {
+                if (!pc.n_mid[mc]) continue;
+                cudaStream_t ss = h->side[mc % N_WCLS];
+                CK(cudaStreamWaitEvent(ss, h->ev[5], 0));
+                CK(cudaEventRecord(h->mev[mc][0], ss));
+                mid_launch(ss, mc / N_MBIN, pc.n_mid[mc], mid_bin_cap(mc % N_MBIN), in, out, plan, (const int *)h->mlist.p + mb.b[mc]);
+                CK(cudaEventRecord(h->mev[mc][1], ss));
+                S.n_launches++;
+                mid_used[mc] = true;
+            }
+        }
     }
 
     // ---- the rest: HBM slab, wavefront / scalar kernels ----

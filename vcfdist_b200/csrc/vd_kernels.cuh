@@ -29,8 +29,8 @@ struct PlanCounters {
     unsigned long long cells;
     unsigned long long cells_list;
     unsigned status_or;
-    int n_mid[N_MCLS];                 // superclusters of the fused mid-size kernel, per rows-per-lane class
-    int mid_smem[N_MCLS];              // largest shared-memory need in each class
+    int n_mid[N_MCLS];                 // superclusters of the fused mid-size kernel, per (K, smem bin) class
+    int mid_cursor[N_MCLS];
 };
 
 // OR of all status words (so that the host only scans them when an error bit is set)
@@ -81,12 +81,10 @@ __global__ void plan_kernel(BatchDev in, ScPlan *plan, int *list, int *mlist, Pl
         else {
             const int kc = mid_kclass(p);
             const int need = kc >= 0 ? mid_layout(p, 1 << kc).total : (1 << 30);
-            if ((force_class < 0 || force_class == CLS_MID) && need <= MID_SMEM_MAX) {
-                cls = CLS_MID;
-                if (live) {
-                    mlist[(int64_t)kc * in.n_sc + atomicAdd(&cnt->n_mid[kc], 1)] = sc;
-                    atomicMax(&cnt->mid_smem[kc], need);
-                }
+            if (force_class == CLS_MID && need <= MID_SMEM_MAX) {      // measured slower than the slab path: opt-in only
+                const int mc = kc * N_MBIN + mid_bin(need);
+                cls = CLS_MID | (mc << 8);              // the class id rides in the upper bits
+                if (live) atomicAdd(&cnt->n_mid[mc], 1);
             } else cls = (force_class > CLS_TINY && force_class != CLS_MID) ? force_class : big_class;
         }
     }
@@ -95,6 +93,7 @@ __global__ void plan_kernel(BatchDev in, ScPlan *plan, int *list, int *mlist, Pl
     // warp-aggregated counters: one atomic per warp and counter instead of one per thread
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
+    (void)mlist;
     const bool is_bad = live && cls == CLS_BAD, is_list = live && (cls == CLS_WAVE || cls == CLS_SCALAR);
     unsigned long long c_all = live ? cells : 0ull, c_list = is_list ? cells : 0ull;
 #pragma unroll
@@ -111,6 +110,17 @@ __global__ void plan_kernel(BatchDev in, ScPlan *plan, int *list, int *mlist, Pl
     }
     base = __shfl_sync(full, base, 0);
     if (is_list) list[base + __popc(m_list & ((1u << lane) - 1))] = sc;
+}
+
+// class-sorted work list of the fused mid-size kernel
+struct MidBase { int b[N_MCLS]; };
+__global__ void mid_fill_kernel(const ScPlan *plan, int n_sc, PlanCounters *cnt, MidBase mb, int *mlist) {
+    const int sc = blockIdx.x * blockDim.x + threadIdx.x;
+    if (sc >= n_sc) return;
+    const int cls = plan[sc].cls;
+    if ((cls & 0xff) != CLS_MID) return;
+    const int mc = cls >> 8;
+    mlist[mb.b[mc] + atomicAdd(&cnt->mid_cursor[mc], 1)] = sc;
 }
 
 // ---- fused tiny kernel --------------------------------------------------------------------

@@ -7,7 +7,11 @@ namespace vd {
 
 constexpr int MID_TPB = 128;
 constexpr int MID_SMEM_MAX = 56 * 1024;      // 4 resident blocks per SM
-constexpr int N_MCLS = 4;                    // rows per lane K = 1, 2, 4, 8
+constexpr int N_MK = 4;                      // rows per lane K = 1, 2, 4, 8
+constexpr int N_MBIN = 4;                    // shared-memory bins (occupancy follows the bin, not the worst case)
+constexpr int N_MCLS = N_MK * N_MBIN;
+__host__ __device__ inline int mid_bin_cap(int b) { const int v[N_MBIN] = {6 * 1024, 12 * 1024, 24 * 1024, MID_SMEM_MAX}; return v[b]; }
+__host__ __device__ inline int mid_bin(int need) { for (int b = 0; b < N_MBIN; b++) if (need <= mid_bin_cap(b)) return b; return -1; }
 
 struct MidLayout {
     int hap[4], qm[2], wq[2], wt[2], rseq, aln[4], scr[4];
@@ -18,7 +22,7 @@ __host__ __device__ inline int mid_np(int Lq, int Lr, int K) { return (Lq + K - 
 
 // smallest K in {1,2,4,8} whose 32*K rows hold every alignment of the supercluster; -1 if none
 __host__ __device__ inline int mid_kclass(const ScPlan &p) {
-    for (int c = 0; c < N_MCLS; c++) {
+    for (int c = 0; c < N_MK; c++) {
         const int K = 1 << c;
         bool ok = true;
         for (int q = 0; q < 2; q++) ok = ok && mid_np(p.len[q], p.lr, K) <= 32 * K;
