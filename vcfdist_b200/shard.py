@@ -93,7 +93,8 @@ def gather_results(local: dict, sc_idx: np.ndarray, var_idx: np.ndarray, n_sc: i
     buf32 = torch.cat(pieces)
     buf8 = torch.cat(pieces8)
     # one record buffer per rank -> a single all-gather
-    rec = torch.cat([buf32.view(u8), buf8])
+    pad_n = (-(4 * buf32.numel() + buf8.numel())) % 16         # keep every rank's record 16-byte aligned
+    rec = torch.cat([buf32.view(u8), buf8, torch.zeros(pad_n, dtype=u8, device=dev)])
     gathered = torch.empty(world * rec.numel(), dtype=u8, device=dev)
     dist.all_gather_into_tensor(gathered, rec)
     gathered = gathered.view(world, -1)
@@ -112,7 +113,7 @@ def gather_results(local: dict, sc_idx: np.ndarray, var_idx: np.ndarray, n_sc: i
     for r in range(world):
         c_sc, c_var = int(all_counts[r, 0]), int(all_counts[r, 1])
         b32 = gathered[r, : 4 * n32].view(i32)
-        b8 = gathered[r, 4 * n32:]
+        b8 = gathered[r, 4 * n32: 4 * n32 + buf8.numel()]
         o = 0
         sidx = b32[o: o + c_sc].long(); o += max_sc
         vidx = b32[o: o + c_var].long(); o += max_var
