@@ -217,39 +217,34 @@ def main():
         setattr(din, k, t.data_ptr())
     din.rplane_seq = None
     din.max_qual = b.max_qual
-    a4, v2 = 4 * b.n_sc, max(2 * n_var, 1)
-    d_out = {"aln_score": torch.empty(a4, dtype=torch.int32, device=dev),
-             "aln_end_plane": torch.empty(a4, dtype=torch.uint8, device=dev),
-             "aln_beg_plane": torch.empty(a4, dtype=torch.uint8, device=dev),
-             "status": torch.empty(a4, dtype=torch.int32, device=dev),
-             "assigned": torch.empty(v2, dtype=torch.uint8, device=dev),
-             "sync_group": torch.empty(v2, dtype=torch.int32, device=dev),
-             "ref_ed": torch.empty(v2, dtype=torch.int32, device=dev),
-             "query_ed": torch.empty(v2, dtype=torch.int32, device=dev),
-             "callq": torch.empty(v2, dtype=torch.float32, device=dev)}
+    # results live in ONE contiguous record buffer (shard.ResultRecord): the kernels write straight
+    # into it and the end-of-step exchange is a single all-gather with no packing
+    cap = torch.tensor([b.n_sc, n_var], dtype=torch.int64, device=dev)
+    off_sc = off_var = 0
+    if world > 1:
+        allc = [torch.zeros(2, dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(allc, cap)
+        allc = torch.stack(allc).cpu().numpy()
+        off_sc, off_var = int(allc[:rank, 0].sum()), int(allc[:rank, 1].sum())
+        cap_sc, cap_var = int(allc[:, 0].max()), int(allc[:, 1].max())
+    else:
+        cap_sc, cap_var = b.n_sc, n_var
+    rec = shard.ResultRecord(cap_sc, max(cap_var, 1), dev)
+    # batch-global indices of this rank's records (ranks own disjoint ranges of the global arrays)
+    rec.set_shard(np.arange(off_sc, off_sc + b.n_sc), np.arange(off_var, off_var + n_var))
+    d_out = {k: rec.views[k] for k in ("aln_score", "aln_end_plane", "aln_beg_plane", "status", "assigned",
+                                       "sync_group", "ref_ed", "query_ed", "callq")}
     dout = vd_batch_out()
     for k, t in d_out.items():
         setattr(dout, k, t.data_ptr())
+    gathered = torch.empty(world * rec.nbytes, dtype=torch.uint8, device=dev) if world > 1 else None
     torch.cuda.synchronize()
-
-    mine_sc = mine_var = None
-    if world > 1:
-        # batch-global indices of this rank's records for the final all-gather: ranks own
-        # disjoint index ranges of the (virtual) global result arrays
-        cnt = torch.tensor([b.n_sc, n_var], dtype=torch.int64, device=dev)
-        allc = [torch.zeros(2, dtype=torch.int64, device=dev) for _ in range(world)]
-        dist.all_gather(allc, cnt)
-        allc = torch.stack(allc).cpu().numpy()
-        off_sc, off_var = int(allc[:rank, 0].sum()), int(allc[:rank, 1].sum())
-        tot_sc, tot_var = int(allc[:, 0].sum()), int(allc[:, 1].sum())
-        mine_sc = np.arange(off_sc, off_sc + b.n_sc)
-        mine_var = np.arange(off_var, off_var + n_var)
 
     def step_resident():
         eng.run_device(din, dout, n_var, b.ref_bytes, b.alt_bytes)
         if world > 1:
             with torch.cuda.stream(stream):
-                shard.gather_results(d_out, mine_sc, mine_var, tot_sc, tot_var, dist, device=dev)
+                rec.all_gather(dist, gathered)
 
     def barrier():
         if world > 1:

@@ -49,7 +49,27 @@ def _worker(rank, world, port, q):
     want = capi.oracle_run(b).trimmed()
     got = {k: v.numpy() for k, v in full.items()}
     got["status"] = got["status"].view(np.uint32)
-    q.put((rank, mismatches(got, want, OUT_KEYS)))
+    bad = mismatches(got, want, OUT_KEYS)
+    # the bench's path: results written into one contiguous record, ONE all-gather, no scatter
+    vidx = b.var_index_of(mine)
+    rec = shard.ResultRecord(max(len(p) for p in parts), b.n_var, "cpu")
+    rec.set_shard(mine, vidx)
+    for k in ("aln_score", "aln_end_plane", "aln_beg_plane", "assigned", "sync_group", "ref_ed", "query_ed", "callq"):
+        rec.views[k][: len(out[k])] = torch.from_numpy(out[k])
+    rec.views["status"][: len(out["status"])] = torch.from_numpy(out["status"].view(np.int32))
+    g = rec.all_gather(dist)
+    for r in range(world):
+        pr = rec.parse(g, r)
+        sidx = pr["sc_idx"].numpy().astype(np.int64)
+        assert (np.sort(sidx) == parts[r]).all()
+        aidx = (sidx[:, None] * 4 + np.arange(4)[None, :]).reshape(-1)
+        if not (pr["aln_score"].numpy() == want["aln_score"][aidx]).all():
+            bad["record_score"] = 1
+        vi = pr["var_idx"].numpy().astype(np.int64)
+        for k in ("assigned", "sync_group", "ref_ed", "query_ed"):
+            if not (pr[k].numpy() == want[k].reshape(2, -1)[:, vi]).all():
+                bad["record_" + k] = 1
+    q.put((rank, bad))
     dist.barrier()
     dist.destroy_process_group()
 

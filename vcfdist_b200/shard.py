@@ -130,3 +130,70 @@ def gather_results(local: dict, sc_idx: np.ndarray, var_idx: np.ndarray, n_sc: i
             out["assigned"][slot * n_var + vidx] = b8[o: o + c_var]; o += max_var
     out["callq"] = out["callq"].view(torch.float32)
     return out
+
+
+class ResultRecord:
+    """One contiguous, 16-byte-aligned device buffer holding a rank's whole result set, with the
+    `vd_batch_out` arrays as views into it, so that vd_run_device writes straight into the record
+    and the end-of-step exchange is ONE all-gather of `buf` with no packing or scatter:
+
+        [ n_sc, n_var (int64) | sc_idx i32 | var_idx i32 | aln_score i32 | status i32 |
+          sync_group i32 x2 | ref_ed i32 x2 | query_ed i32 x2 | callq f32 x2 |
+          aln_end_plane u8 | aln_beg_plane u8 | assigned u8 x2 ]
+
+    Every rank sizes the record for the largest shard (`cap_sc`, `cap_var`) so that the gathered
+    tensor is a plain [world, rec_bytes] array; `parse()` returns per-rank views."""
+
+    FIELDS32 = ("sc_idx", "var_idx", "aln_score", "status", "sync_group", "ref_ed", "query_ed", "callq")
+    FIELDS8 = ("aln_end_plane", "aln_beg_plane", "assigned")
+
+    def __init__(self, cap_sc: int, cap_var: int, device):
+        import torch
+        self.cap_sc, self.cap_var = cap_sc, cap_var
+        n32 = {"sc_idx": cap_sc, "var_idx": cap_var, "aln_score": 4 * cap_sc, "status": 4 * cap_sc,
+               "sync_group": 2 * cap_var, "ref_ed": 2 * cap_var, "query_ed": 2 * cap_var, "callq": 2 * cap_var}
+        n8 = {"aln_end_plane": 4 * cap_sc, "aln_beg_plane": 4 * cap_sc, "assigned": 2 * cap_var}
+        off, self.layout = 16, {}
+        for k in self.FIELDS32:
+            self.layout[k] = (off, n32[k], 4); off = (off + 4 * n32[k] + 15) & ~15
+        for k in self.FIELDS8:
+            self.layout[k] = (off, n8[k], 1); off = (off + n8[k] + 15) & ~15
+        self.nbytes = off
+        self.buf = torch.zeros(self.nbytes, dtype=torch.uint8, device=device)
+        self.views = self._views(self.buf)
+
+    def _views(self, buf):
+        import torch
+        v = {"counts": buf[:16].view(torch.int64)}
+        for k, (o, n, w) in self.layout.items():
+            t = buf[o: o + n * w]
+            v[k] = t.view(torch.float32) if k == "callq" else (t.view(torch.int32) if w == 4 else t)
+        return v
+
+    def set_shard(self, sc_idx: np.ndarray, var_idx: np.ndarray):
+        import torch
+        self.views["counts"][0] = len(sc_idx)
+        self.views["counts"][1] = len(var_idx)
+        self.views["sc_idx"][: len(sc_idx)] = torch.from_numpy(np.asarray(sc_idx, np.int32)).to(self.buf.device)
+        self.views["var_idx"][: len(var_idx)] = torch.from_numpy(np.asarray(var_idx, np.int32)).to(self.buf.device)
+
+    def all_gather(self, dist, out=None):
+        """The single collective of the path.  Returns the [world, nbytes] gathered tensor."""
+        import torch
+        world = dist.get_world_size()
+        if out is None:
+            out = torch.empty(world * self.nbytes, dtype=torch.uint8, device=self.buf.device)
+        dist.all_gather_into_tensor(out, self.buf)
+        return out.view(world, self.nbytes)
+
+    def parse(self, gathered, rank: int) -> dict:
+        """Views of rank `rank`'s arrays inside the gathered tensor, trimmed to its counts.
+        Per-variant arrays come back as [2, n_var_of_rank] (slot-major with the shard's own stride)."""
+        v = self._views(gathered[rank])
+        n_sc, n_var = int(v["counts"][0]), int(v["counts"][1])
+        out = {"sc_idx": v["sc_idx"][:n_sc], "var_idx": v["var_idx"][:n_var]}
+        for k in ("aln_score", "status", "aln_end_plane", "aln_beg_plane"):
+            out[k] = v[k][: 4 * n_sc]
+        for k in ("sync_group", "ref_ed", "query_ed", "callq", "assigned"):
+            out[k] = v[k][: 2 * n_var].view(2, n_var)
+        return out
