@@ -47,6 +47,7 @@ struct vd_handle {
     std::string err;
     vd_stats stats = {};
     unsigned stats_status_or = 0;   // OR of every status word of the last call
+    bool sparse_bwd = true;         // VD_DENSE_BWD=1 selects the dense backward sweep (testing)
     int force_class = -1;           // VD_FORCE_CLASS env: testing hook (1 wave, 2 scalar slab)
     // staged input / output (vd_run)
     struct Stage {                  // one of two staging sets of the host-buffer pipeline
@@ -106,6 +107,7 @@ extern "C" int vd_create(int device, int64_t scratch_bytes, vd_handle **out) {
     }
     h->scratch_budget = scratch_bytes;
     if (const char *fc = getenv("VD_FORCE_CLASS")) h->force_class = atoi(fc);
+    if (const char *db = getenv("VD_DENSE_BWD")) h->sparse_bwd = atoi(db) == 0;
     if (const char *cs = getenv("VD_CHUNK_SC")) h->chunk_sc = atoll(cs) > 0 ? atoll(cs) : h->chunk_sc;
     cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking);
@@ -295,7 +297,7 @@ static int run_resident(vd_handle *h, const BatchDev &in, const OutDev &out, con
                     CK(cudaEventRecord(h->sev[c][0], ss));
                     wave_launch(ss, WA, c, cb.b[c], hwi.count[c], true);
                     CK(cudaEventRecord(h->sev[c][1], ss));
-                    wave_launch(ss, WA, c, cb.b[c], hwi.count[c], false);
+                    wave_launch(ss, WA, c, cb.b[c], hwi.count[c], false, h->sparse_bwd);
                     CK(cudaEventRecord(h->sev[c][2], ss));
                     CK(cudaStreamWaitEvent(st, h->sev[c][2], 0));
                     S.n_launches += 2;

@@ -97,7 +97,10 @@ __host__ __device__ inline WaveAln wave_aln(int Lq, int Lr, int Lt) {
     // path (int32 q, int32 t, u8 flags) + lev row
     const int np = Lq + Lr + Lt + 4;
     const int mn = (Lr < Lt ? Lr : Lt) + 1;
-    w.total = align_up(w.oWalk + 8 * (int64_t)np + align_up(np, 4) + 4 * (int64_t)mn, 16);
+    int64_t walk = 8 * (int64_t)np + align_up(np, 4) + 4 * (int64_t)mn;
+    const int64_t lists = 16 * (int64_t)w.NP + 64;       // sparse backward: 2 frontier lists + 2 worklists (int32)
+    if (lists > walk) walk = lists;
+    w.total = align_up(w.oWalk + walk, 16);
     return w;
 }
 // walk scratch offsets in AlnLayout form (only the path / lev members are used)
@@ -679,6 +682,200 @@ __global__ void __launch_bounds__(TPB) wave_bwd_kernel(WaveArgs A, int item0) {
     if (status) atomicOr(&A.out.status[4 * (int64_t)X.sc + X.ai], status);
 }
 
+// ------------------------------------------------------------------------------------------
+// sparse backward: the same pass as wave_bwd_kernel, restricted to the cells that are actually
+// reachable from the end cell over optimal edges (what the reference's BFS visits, :549-808).
+// One warp per alignment.  Per column it keeps the list of reached rows; pushes go from the
+// reached cells of column c+1 into column c (atomic max on a dense int16 column in shared
+// memory), the in-column INS chains are closed with a worklist, then the path flags of the
+// reached cells overwrite their forward flags in HBM.  HBM traffic: ~3 bytes per REACHED cell
+// instead of 2 bytes per cell of the whole matrix.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int atomic_max16(short *addr, int v) {
+    unsigned *w = (unsigned *)((size_t)addr & ~(size_t)3);
+    const int sh = ((size_t)addr & 2) ? 16 : 0;
+    unsigned old = *w;
+    while (true) {
+        const int cur = (short)(old >> sh);
+        if (v <= cur) return cur;
+        const unsigned nw = (old & ~(0xffffu << sh)) | (((unsigned)v & 0xffffu) << sh);
+        const unsigned got = atomicCAS(w, old, nw);
+        if (got == old) return cur;
+        old = got;
+    }
+}
+__device__ __forceinline__ void atomic_or8(u8 *addr, int v) {
+    unsigned *w = (unsigned *)((size_t)addr & ~(size_t)3);
+    atomicOr(w, (unsigned)v << (((size_t)addr & 3) * 8));
+}
+
+struct SbwdPush { int n; int tgt[3]; int val[3]; int ty[3]; bool tie; };
+
+// the (at most three) pushes of reached cell x = (row, column c+1) into column c
+__device__ __forceinline__ SbwdPush sbwd_pushes(const WaveCtx &X, int row, int f, int Tx, int tch_x) {
+    SbwdPush r; r.n = 0; r.tie = false;
+    const bool P = row >= X.padQ;
+    const int a = P ? row - X.padQ : row;
+    const int tp = (!P && a > 0) ? X.tpb[a] : 0;
+    if ((f & F_DIAG) && a > 0) {                                                    // :556-595, :692-731
+        const int ch = (P ? X.rseq[a] : X.qstr[a]) & 0x7f;
+        r.tgt[r.n] = row - 1; r.val[r.n] = Tx + tp; r.ty[r.n] = (ch == tch_x) ? PTR_MAT : PTR_SUB; r.n++;
+    }
+    if (f & F_DEL) { r.tgt[r.n] = row; r.val[r.n] = Tx; r.ty[r.n] = PTR_DEL; r.n++; }   // :774-804
+    if ((f & F_SWP) && a > 0) {                                                     // :598-679
+        const int of = P ? X.rflg[a] : X.qflg[a];
+        if (!(of & P_VARIANT) || (of & P_VAR_BEG)) {
+            const int *tab = P ? X.toR : X.toQ;
+            const int *src = tab + (P ? X.Lr : X.Lq) + 1;
+            r.tgt[r.n] = (P ? 0 : X.padQ) + src[tab[a] + (f >> F_K_SHIFT)];
+            r.val[r.n] = Tx + (P ? 0 : tp); r.ty[r.n] = PTR_SWP; r.n++;
+            r.tie = f & F_TIE;
+        }
+    }
+    return r;
+}
+
+__global__ void __launch_bounds__(32) wave_sbwd_kernel(WaveArgs A, int item0, int npmax) {
+    extern __shared__ __align__(16) u8 smem_raw[];
+    const int item = A.items[item0 + blockIdx.x];
+    const WaveCtx X = wave_ctx(A, item);
+    short *T0 = (short *)smem_raw, *T1 = T0 + npmax;          // T of two columns, dense over rows
+    u8 *PF0 = (u8 *)(T1 + npmax), *PF1 = PF0 + npmax;          // path flags of two columns
+    __shared__ int cnt[2], wcnt[2];
+    const int lane = threadIdx.x;
+    // frontier lists and worklists live in the alignment's walk scratch (dead until the walk)
+    const WaveAln wa = wave_aln(X.Lq, X.Lr, X.Lt);
+    int *L0 = (int *)(X.F + wa.oWalk), *L1 = L0 + X.NP, *W0 = L1 + X.NP, *W1 = W0 + X.NP;
+    const int64_t oi = 4 * (int64_t)X.sc + X.ai;
+    const int end_plane = A.out.aln_end_plane[oi];
+    const int erow = end_plane ? X.padQ + X.Lr - 1 : X.Lq - 1;
+    u32 status = 0;
+
+    for (int r = lane; r < X.NP; r += 32) { T0[r] = -1; T1[r] = -1; PF0[r] = 0; PF1[r] = 0; }
+    if (lane == 0) { cnt[0] = cnt[1] = 0; wcnt[0] = wcnt[1] = 0; }
+    __syncwarp();
+
+    short *Tn = T0, *Tc = T1;       // column c+1 ("next", already final) and column c (being built)
+    u8 *PFn = PF0, *PFc = PF1;
+    int *Ln = L0, *Lc = L1;
+    int in = 0, ic = 1;             // indices into cnt[]
+    int tch_next = 0;
+    for (int c = X.Lt - 1; c >= 0; c--) {
+        const u8 *Fcol = X.F + (int64_t)c * X.NP;
+        // ---- phase A: seed / pushes from column c+1 ----
+        if (c == X.Lt - 1) {
+            if (lane == 0) { Tc[erow] = 0; PFc[erow] = PTR_MAT; Lc[0] = erow; cnt[ic] = 1; }      // :543-545
+        } else {
+            const int n = cnt[in];
+            for (int i = lane; i < n; i += 32) {
+                const int e = Ln[i], row = e & 0xffff, f = e >> 16;
+                const SbwdPush pu = sbwd_pushes(X, row, f, Tn[row], tch_next);
+                if (pu.tie) status |= VD_ST_TIE;
+                for (int k = 0; k < pu.n; k++) {
+                    const int old = atomic_max16(&Tc[pu.tgt[k]], pu.val[k]);
+                    if (old < 0) Lc[atomicAdd(&cnt[ic], 1)] = pu.tgt[k];
+                }
+            }
+        }
+        __syncwarp();
+        // forward flags of the rows reached so far; they also form the first worklist
+        {
+            const int n = cnt[ic];
+            for (int i = lane; i < n; i += 32) {
+                const int row = Lc[i] & 0xffff;
+                const int e = row | ((int)Fcol[row] << 16);
+                Lc[i] = e; W0[i] = e;
+            }
+            if (lane == 0) { wcnt[0] = n; wcnt[1] = 0; }
+        }
+        __syncwarp();
+        // ---- in-column INS chains (:734-771): worklist until nothing improves ----
+        {
+            int *Wa = W0, *Wb = W1;
+            int wa_i = 0;
+            while (true) {
+                const int n = wcnt[wa_i];
+                if (n == 0) break;
+                for (int i = lane; i < n; i += 32) {
+                    const int e = Wa[i], row = e & 0xffff, f = e >> 16;
+                    const bool P = row >= X.padQ;
+                    const int a = P ? row - X.padQ : row;
+                    if ((f & F_INS) && a > 0) {
+                        const int v = Tc[row] + ((!P) ? X.tpb[a] : 0);
+                        const int old = atomic_max16(&Tc[row - 1], v);
+                        if (v > old) {
+                            const int e2 = (row - 1) | ((int)Fcol[row - 1] << 16);
+                            if (old < 0) Lc[atomicAdd(&cnt[ic], 1)] = e2;
+                            Wb[atomicAdd(&wcnt[wa_i ^ 1], 1)] = e2;
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) wcnt[wa_i] = 0;
+                int *t_ = Wa; Wa = Wb; Wb = t_;
+                wa_i ^= 1;
+                __syncwarp();
+            }
+        }
+        // ---- phase B: path flags of column c ----
+        if (c < X.Lt - 1) {
+            const int n = cnt[in];
+            for (int i = lane; i < n; i += 32) {
+                const int e = Ln[i], row = e & 0xffff, f = e >> 16;
+                const SbwdPush pu = sbwd_pushes(X, row, f, Tn[row], tch_next);
+                for (int k = 0; k < pu.n; k++)
+                    if (pu.val[k] == Tc[pu.tgt[k]]) atomic_or8(&PFc[pu.tgt[k]], pu.ty[k]);
+            }
+        }
+        {
+            const int n = cnt[ic];
+            for (int i = lane; i < n; i += 32) {
+                const int e = Lc[i], row = e & 0xffff, f = e >> 16;
+                const bool P = row >= X.padQ;
+                const int a = P ? row - X.padQ : row;
+                if ((f & F_INS) && a > 0) {
+                    const int v = Tc[row] + ((!P) ? X.tpb[a] : 0);
+                    if (v == Tc[row - 1]) atomic_or8(&PFc[row - 1], PTR_INS);
+                }
+            }
+        }
+        __syncwarp();
+        // ---- column c+1 is finished: its path flags replace the forward flags in HBM ----
+        if (c < X.Lt - 1) {
+            u8 *Fnext = X.F + (int64_t)(c + 1) * X.NP;
+            const int n = cnt[in];
+            for (int i = lane; i < n; i += 32) {
+                const int row = Ln[i] & 0xffff;
+                Fnext[row] = PFn[row];
+                Tn[row] = -1; PFn[row] = 0;
+            }
+            __syncwarp();
+            if (lane == 0) cnt[in] = 0;
+        }
+        tch_next = X.tinfo[c] & 0x7f;
+        { short *t_ = Tn; Tn = Tc; Tc = t_; }
+        { u8 *t_ = PFn; PFn = PFc; PFc = t_; }
+        { int *t_ = Ln; Ln = Lc; Lc = t_; }
+        in ^= 1; ic ^= 1;
+        __syncwarp();
+    }
+    // column 0 (now "next"): origin plane (:811-814), then its path flags
+    const int beg_plane = Tn[0] >= 0 ? 0 : 1;
+    {
+        u8 *F0 = X.F;
+        const int n = cnt[in];
+        for (int i = lane; i < n; i += 32) {
+            const int row = Ln[i] & 0xffff;
+            F0[row] = PFn[row];
+        }
+    }
+    status = __reduce_or_sync(0xffffffffu, status);
+    if (lane == 0) {
+        A.out.aln_beg_plane[oi] = (u8)beg_plane;
+        if (status) atomicOr(&A.out.status[oi], status);
+    }
+}
+
 // path flags of the wavefront layout
 struct PFWave {
     const u8 *F; int NP, padQ;
@@ -729,6 +926,7 @@ inline void wave_configure() {
     wave_configure_one<32, 1>(); wave_configure_one<32, 2>(); wave_configure_one<32, 4>();
     wave_configure_one<128, 4>(); wave_configure_one<256, 8>(); wave_configure_one<512, 16>();
     wave_configure_one<1024, 16>(); wave_configure_one<1024, 32>();
+    cudaFuncSetAttribute(wave_sbwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * 32768);
 }
 
 template <int TPB, int K>
@@ -737,7 +935,12 @@ inline void wave_launch_pair(cudaStream_t st, const WaveArgs &A, int item0, int 
     if (fwd) wave_fwd_kernel<TPB, K><<<n, TPB, wave_fwd_smem<TPB, K>(), st>>>(A, item0);
     else wave_bwd_kernel<TPB, K><<<n, TPB, wave_bwd_smem<TPB, K>(), st>>>(A, item0);
 }
-inline void wave_launch(cudaStream_t st, const WaveArgs &A, int cls, int item0, int n, bool fwd) {
+inline void wave_launch(cudaStream_t st, const WaveArgs &A, int cls, int item0, int n, bool fwd, bool sparse_bwd = true) {
+    if (!fwd && sparse_bwd) {
+        const int npmax = wave_tpb(cls) * wave_k(cls);
+        wave_sbwd_kernel<<<n, 32, 6 * npmax, st>>>(A, item0, npmax);
+        return;
+    }
     switch (cls) {
         case 0: wave_launch_pair<32, 1>(st, A, item0, n, fwd); break;
         case 1: wave_launch_pair<32, 2>(st, A, item0, n, fwd); break;
