@@ -1,13 +1,8 @@
 import sys, os, numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from vcfdist_b200 import capi
-from vcfdist_b200.batch import BatchBuilder, TYPE_SUB, TYPE_INS, TYPE_DEL
-import ctypes as C
-os.environ["VD_FORCE_CLASS"] = "1"
+from vcfdist_b200 import capi, synth
 capi.LIB_PATH = os.path.join(os.path.dirname(capi.LIB_PATH), "libvcfdist_b200_dbg.so")
-bb = BatchBuilder()
-bb.add(b"ACGT", [[], [], [], []])
-b = bb.build()
+b = synth.sv_pairs(1, 1, int(sys.argv[1]) if len(sys.argv) > 1 else 1000, divergence=0.01)
 e = capi.Engine(0)
 got = e.run(b).trimmed(); want = capi.oracle_run(b).trimmed()
-for k in got: print(k, got[k], want[k])
+print("score", got["aln_score"], want["aln_score"])

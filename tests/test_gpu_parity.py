@@ -75,6 +75,28 @@ def test_sv_lengths(engine, length):
     check_vs_oracle(engine, synth.sv_pairs(3, 3, length, divergence=0.03))
 
 
+@pytest.mark.parametrize("length,div", [(1400, 0.3), (2300, 0.9), (700, 1.0)])
+def test_divergent_sv_pairs(engine, length, div):
+    """Long alignments whose score exceeds the banded sweep's bounds (96/384/1536): retries and
+    the dense fallback must give the same bits."""
+    check_vs_oracle(engine, synth.sv_pairs(5, 1, length, divergence=div))
+
+
+def test_dense_paths_match_banded_and_sparse(engine):
+    """VD_DENSE_FWD / VD_DENSE_BWD select the dense register-blocked sweeps for every alignment."""
+    b = Batch.concat([synth.sv_pairs(7, 2, 800, divergence=0.05), synth.wgs_like(8, 300, sv_frac=0.1, sv_max=900)])
+    want = capi.oracle_run(b)
+    for env in ({"VD_DENSE_FWD": "1"}, {"VD_DENSE_BWD": "1"}, {"VD_DENSE_FWD": "1", "VD_DENSE_BWD": "1"}):
+        os.environ.update(env)
+        try:
+            e = capi.Engine(0)
+        finally:
+            for k in env:
+                del os.environ[k]
+        assert mismatches(e.run(b).trimmed(), want.trimmed(), OUT_KEYS) == {}
+        e.close()
+
+
 def test_edge_cases(engine):
     bb = BatchBuilder()
     # no variants at all (window of one base and of several)

@@ -47,6 +47,7 @@ struct vd_handle {
     std::string err;
     vd_stats stats = {};
     unsigned stats_status_or = 0;   // OR of every status word of the last call
+    bool banded_fwd = true;         // VD_DENSE_FWD=1 skips the banded forward sweep (testing)
     bool sparse_bwd = true;         // VD_DENSE_BWD=1 selects the dense backward sweep (testing)
     int force_class = -1;           // VD_FORCE_CLASS env: testing hook (1 wave, 2 scalar slab)
     // staged input / output (vd_run)
@@ -60,7 +61,7 @@ struct vd_handle {
     cudaStream_t s_in = nullptr, s_out = nullptr;
     int64_t chunk_sc = 393216;      // superclusters per pipeline chunk (VD_CHUNK_SC)
     // work
-    DevBuf plan, list, mlist, counters, bytes, offs, cubtmp, slab, hap_ok, wave_desc;
+    DevBuf plan, list, mlist, need_dense, counters, bytes, offs, cubtmp, slab, hap_ok, wave_desc;
     PlanCounters *h_counters = nullptr;     // pinned
 };
 
@@ -107,6 +108,7 @@ extern "C" int vd_create(int device, int64_t scratch_bytes, vd_handle **out) {
     }
     h->scratch_budget = scratch_bytes;
     if (const char *fc = getenv("VD_FORCE_CLASS")) h->force_class = atoi(fc);
+    if (const char *df = getenv("VD_DENSE_FWD")) h->banded_fwd = atoi(df) == 0;
     if (const char *db = getenv("VD_DENSE_BWD")) h->sparse_bwd = atoi(db) == 0;
     if (const char *cs = getenv("VD_CHUNK_SC")) h->chunk_sc = atoll(cs) > 0 ? atoll(cs) : h->chunk_sc;
     cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking);
@@ -137,7 +139,7 @@ extern "C" void vd_destroy(vd_handle *h) {
     }
     if (h->s_in) cudaStreamDestroy(h->s_in);
     if (h->s_out) cudaStreamDestroy(h->s_out);
-    DevBuf *bufs[] = {&h->plan, &h->list, &h->mlist, &h->counters, &h->bytes, &h->offs,
+    DevBuf *bufs[] = {&h->plan, &h->list, &h->mlist, &h->need_dense, &h->counters, &h->bytes, &h->offs,
                       &h->cubtmp, &h->slab, &h->hap_ok, &h->wave_desc};
     for (DevBuf *b : bufs) b->release();
     if (h->h_counters) cudaFreeHost(h->h_counters);
@@ -286,6 +288,7 @@ static int run_resident(vd_handle *h, const BatchDev &in, const OutDev &out, con
                 S.n_launches++;
             }
             if (total_items > 0) {
+                CK(h->need_dense.ensure(4 * (size_t)total_items + 16));
                 WaveArgs WA{in, out, plan, list, i0, offs, (u8 *)h->slab.p, items};
                 // forward then backward of each class on its own stream (an alignment's backward pass
                 // only depends on its own forward pass), all classes concurrently; then join
@@ -295,7 +298,7 @@ static int run_resident(vd_handle *h, const BatchDev &in, const OutDev &out, con
                     cudaStream_t ss = h->side[c];
                     CK(cudaStreamWaitEvent(ss, h->ev[4], 0));
                     CK(cudaEventRecord(h->sev[c][0], ss));
-                    wave_launch(ss, WA, c, cb.b[c], hwi.count[c], true);
+                    wave_launch(ss, WA, c, cb.b[c], hwi.count[c], true, true, h->banded_fwd ? (int *)h->need_dense.p : nullptr);
                     CK(cudaEventRecord(h->sev[c][1], ss));
                     wave_launch(ss, WA, c, cb.b[c], hwi.count[c], false, h->sparse_bwd);
                     CK(cudaEventRecord(h->sev[c][2], ss));

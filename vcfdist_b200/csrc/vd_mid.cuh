@@ -84,6 +84,7 @@ __global__ void __launch_bounds__(MID_TPB) mid_kernel(BatchDev in, OutDev out, c
     X.qstr = hstr(qh); X.rseq = rseq; X.tinfo = smem + M.wt[ai & 1];
     X.qflg = hflg(qh); X.rflg = qrflg(qh); X.tpb = wtpb(qh);
     X.toQ = qtoQ(qh); X.toR = qtoR(qh); X.srcQ = wsrcQ(qh); X.srcR = wsrcR(qh);
+    X.qptr = hptr(qh); X.rptr = qrptr(qh);
     X.F = smem + M.aln[ai];
     u8 *scratch = smem + M.scr[ai];
 

@@ -25,6 +25,7 @@ namespace vd {
 
 constexpr int kBigClass = CLS_WAVE;
 constexpr int NEG = -(1 << 28);
+constexpr int FWD_TAU0 = 96;       // first score bound of the forward sweep (then x4 per retry)
 
 // ---- per-hap tables the wavefront kernels need, built once per supercluster --------------
 // srcinfo: bit0 valid, bits1-3 k (index in the destination's source list), bit4 tp(dest),
@@ -58,12 +59,14 @@ __device__ inline void build_srcinfo(const PT *ptr, const u8 *flg, int nsrc,    
 struct WaveHapQ {        // extra per query hap
     int *srcQ;           // [Lq]  QUERY rows as swap sources (destinations on the REF plane)
     int *srcR;           // [Lr]  REF rows as swap sources (destinations on the QUERY plane)
+    u32 *swiQ;           // [Lq]  QUERY rows as swap DESTINATIONS: first source (REF row) | count << 16
+    u32 *swiR;           // [Lr]  REF rows as swap DESTINATIONS: first source (QUERY row) | count << 16
     u8 *tpb;             // [Lq]  tp(a): entering QUERY row a counts a query variant (:572-574)
     __device__ WaveHapQ(u8 *base, int Lq, int Lr) {
-        srcQ = (int *)base; srcR = srcQ + Lq; tpb = (u8 *)(srcR + Lr);
+        srcQ = (int *)base; srcR = srcQ + Lq; swiQ = (u32 *)(srcR + Lr); swiR = swiQ + Lq; tpb = (u8 *)(swiR + Lr);
     }
 };
-__host__ __device__ inline int64_t wave_hapq_bytes(int Lq, int Lr) { return 4 * ((int64_t)Lq + Lr) + align_up(Lq, 16); }
+__host__ __device__ inline int64_t wave_hapq_bytes(int Lq, int Lr) { return 8 * ((int64_t)Lq + Lr) + align_up(Lq, 16); }
 __host__ __device__ inline int64_t wave_hapt_bytes(int Lt) { return align_up(Lt, 16); }     // tinfo: base | tok<<7
 
 // kernel shape classes: (threads per block, rows per thread)
@@ -166,6 +169,14 @@ __global__ void wave_tables_kernel(const ScPlan *plan, const int *list, int i0, 
         build_srcinfo<int>(M.rptr, M.rflg, p.lr, M.toQ, p.len[h], H.flg, H.ptr, X.srcR);
         for (int a = 0; a < p.len[h]; a++)
             X.tpb[a] = (a > 0 && ((H.ptr[a] != H.ptr[a - 1] + 1) || (H.flg[a] & P_VAR_BEG))) ? 1 : 0;
+        for (int a = 0; a < p.len[h]; a++) {
+            const int k0 = M.toQ[a], k1 = M.toQ[a + 1];
+            X.swiQ[a] = k1 > k0 ? ((u32)M.toQ[p.len[h] + 1 + k0] | ((u32)(k1 - k0) << 16)) : 0u;
+        }
+        for (int a = 0; a < p.lr; a++) {
+            const int k0 = M.toR[a], k1 = M.toR[a + 1];
+            X.swiR[a] = k1 > k0 ? ((u32)M.toR[p.lr + 1 + k0] | ((u32)(k1 - k0) << 16)) : 0u;
+        }
     } else {
         u8 *tinfo = base + W.ht[h - 2];
         for (int c = 0; c < p.len[h]; c++) {
@@ -234,7 +245,9 @@ template <class TT> struct WaveCtxT {      // TT: element type of the CSR swap t
     int sc, ai, Lq, Lr, Lt, padQ, NP;
     const u8 *qstr, *rseq, *tinfo, *qflg, *rflg, *tpb;
     const TT *toQ, *toR;
+    const TT *qptr, *rptr;      // query->ref and ref->query pointers (band bookkeeping of the forward sweep)
     const int *srcQ, *srcR;
+    const u32 *swiQ, *swiR;     // per destination row: first swap source | count << 16 (slab path only)
     u8 *F;
 };
 typedef WaveCtxT<int> WaveCtx;
@@ -256,6 +269,8 @@ __device__ inline WaveCtx wave_ctx(const WaveArgs &A, int item) {
     WaveHapQ X(base + W.hq[qh], x.Lq, x.Lr);
     x.qstr = HQ.str; x.qflg = HQ.flg; x.rflg = M.rflg; x.tpb = X.tpb;
     x.toQ = M.toQ; x.toR = M.toR; x.srcQ = X.srcQ; x.srcR = X.srcR;
+    x.qptr = HQ.ptr; x.rptr = M.rptr;
+    x.swiQ = X.swiQ; x.swiR = X.swiR;
     x.rseq = A.in.rplane_seq + A.in.ref_off[x.sc];
     x.tinfo = base + W.ht[th];
     x.F = base + W.aln[x.ai] + wa.oF;
@@ -299,10 +314,11 @@ template <int TPB> __device__ __forceinline__ void block_sync() {
 // every thread of the group.
 template <int TPB, int K, class TT>
 __device__ __forceinline__ void wave_fwd_body(const WaveCtxT<TT> &X, const int t, u8 *smem_raw, int *sEnd,
-                                              int &score, int &end_plane) {
+                                              int &score, int &end_plane, const int tau0 = FWD_TAU0) {
     constexpr int NPMAX = TPB * K;
     u16 *sD0 = (u16 *)smem_raw, *sD1 = sD0 + NPMAX;          // previous / current column, both planes
-    int *sW = (int *)(sD1 + NPMAX);                          // [2 segments][32 warps] scan totals
+    int *sLive = (int *)(sD1 + NPMAX);                       // [2 columns][loQ, hiQ, loR, hiR] rows with D <= tau
+    int *sW = sLive + 8;                                     // [2 segments][32 warps] scan totals
     const int lane = t & 31, warp = t >> 5;
     const int tQ = X.padQ / K;                               // first thread of the REF plane
     const bool P = t >= tQ;
@@ -318,147 +334,427 @@ __device__ __forceinline__ void wave_fwd_body(const WaveCtxT<TT> &X, const int t
     u8 ch[K];
 #pragma unroll
     for (int j = 0; j < K; j++) ch[j] = (a0 + j < len) ? (u8)(seq[a0 + j] & 0x7f) : (u8)0xff;
-    int Dp[K];
+    // swap sources of my rows, resolved once: first source as a padded row index of the other plane
+    // (bits 0-15) and the number of sources (bits 16-19).  Almost every row has exactly one, so the
+    // per-column swap candidate is a single shared-memory load instead of a chain of dependent
+    // CSR loads from global memory (which put ~100 cycles per row on the column's critical path).
+    u32 swi[K];
 #pragma unroll
-    for (int j = 0; j < K; j++) Dp[j] = INF;
-#pragma unroll
-    for (int j = 0; j < K; j++) sD0[row0 + j] = 0xffff;
-    block_sync<TPB>();
-
-    int tnext = X.tinfo[0];
-    for (int c = 0; c < X.Lt; c++) {
-        u16 *sPrev = (c & 1) ? sD1 : sD0, *sCur = (c & 1) ? sD0 : sD1;
-        const int tinfo = tnext;
-        if (c + 1 < X.Lt) tnext = X.tinfo[c + 1];
-        const int tch = tinfo & 0x7f;
-        const bool tok = tinfo & 0x80;
-        // ---- pass 1: thread-local chain ----
-        int up;                                             // D[a0-1][c-1]
-        {
-            const int v = (a0 > 0 && c > 0) ? sPrev[row0 - 1] : 0xffff;
-            up = v == 0xffff ? INF : v;
+    for (int j = 0; j < K; j++) {
+        swi[j] = 0;
+        if (a0 + j < len) {
+            const int k0 = tab[a0 + j], k1 = tab[a0 + j + 1];
+            if (k1 > k0) swi[j] = (u32)(obase + (int)src[k0]) | ((u32)(k1 - k0) << 16);
         }
-        int Dc[K];
-        int run = INF;                                      // D[a-1][c] within the thread (no carry yet)
-        int upj = up;
-#pragma unroll
-        for (int j = 0; j < K; j++) {
-            const bool m = ch[j] == tch;
-            int b;
-            if (a0 + j == 0 && c == 0) b = (a0 + j < len) ? 0 : INF;       // both origins start at 0 (:299-305)
-            else {
-                b = upj + (m ? 0 : 1);                      // diag (INF-safe: INF+1 stays huge)
-                b = min(b, Dp[j] + 1);                      // del
-                if (tok && m && a0 + j < len) {             // swap (:334-349, :363-378)
-                    const int k0 = tab[a0 + j], k1 = tab[a0 + j + 1];
-                    for (int k = k0; k < k1; k++) {
-                        const int v = sPrev[obase + src[k]];
-                        b = min(b, v == 0xffff ? INF : v);
-                    }
-                }
-                if (a0 + j >= len) b = INF;
-            }
-            run = min(b, run + 1);
-            Dc[j] = run;
-            upj = Dp[j];
-        }
-        // ---- cross-thread min-plus prefix scan of G = last - lastrow ----
-        int G = Dc[K - 1] - (row0 + K - 1);
-        int incl = G;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int o = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d && t - d >= segstart) incl = min(incl, o);
-        }
-        int excl = __shfl_up_sync(0xffffffffu, incl, 1);
-        if (lane == 0 || t - 1 < segstart) excl = INF;
-        int carry = excl;
-        if constexpr (TPB > 32) {
-            // warp totals per segment: the last lane's inclusive value covers the lanes of its own
-            // segment; a warp straddling the plane boundary also publishes its QUERY-part total
-            int *sWc = sW + (c & 1) * 64;
-            const int lastQ = tQ - 1;                        // last QUERY thread
-            if (lane == 31) sWc[(P ? 32 : 0) + warp] = incl;
-            if (t == lastQ && lane != 31) sWc[warp] = incl;
-            if (lane == 31 && !P) { /* pure QUERY warp: REF total empty */ sWc[32 + warp] = INF; }
-            if (lane == 31 && P && (t - 31) >= tQ) sWc[warp] = INF;      // pure REF warp: QUERY total empty
-            __syncthreads();
-            // totals of earlier warps in my segment.  The slot choice must be warp-uniform for the
-            // butterfly: a warp that starts on the QUERY plane reads QUERY totals; its REF lanes (a
-            // straddling warp) have no earlier REF warp at all.
-            const bool warpQ = 32 * warp < tQ;
-            int wv = (lane < warp) ? sWc[(warpQ ? 0 : 32) + lane] : INF;
-#pragma unroll
-            for (int d = 16; d; d >>= 1) wv = min(wv, __shfl_xor_sync(0xffffffffu, wv, d));
-            if (warpQ && P) wv = INF;
-            carry = min(carry, wv);
-        }
-        // ---- pass 2: final values and flags ----
-        u32 fw[(K + 3) / 4];
-#pragma unroll
-        for (int i = 0; i < (K + 3) / 4; i++) fw[i] = 0;
-        // carry is min(G) = D_last - lastrow over earlier threads, so the chain value at row r is carry + r
-        int prevD = carry >= INF / 2 ? INF : carry + (row0 - 1);           // D[a0-1][c]
-        upj = up;
-#pragma unroll
-        for (int j = 0; j < K; j++) {
-            const int r = row0 + j;
-            int d = Dc[j];
-            if (carry < INF / 2) d = min(d, carry + r);
-            int f = 0;
-            if (a0 + j < len) {
-                if (a0 + j == 0 && c == 0) f = F_DIAG;
-                else {
-                    const bool m = ch[j] == tch;
-                    if (a0 + j > 0 && c > 0 && upj + (m ? 0 : 1) == d) f |= F_DIAG;
-                    if (a0 + j > 0 && prevD + 1 == d) f |= F_INS;
-                    if (c > 0 && Dp[j] + 1 == d) f |= F_DEL;
-                    if (tok && m) {
-                        const int k0 = tab[a0 + j], k1 = tab[a0 + j + 1];
-                        int best = INF, sb = 0;
-                        for (int k = k0; k < k1; k++) {
-                            int v = sPrev[obase + src[k]];
-                            v = v == 0xffff ? INF : v;
-                            if (v < best) { best = v; sb = (k - k0) << F_K_SHIFT; }
-                            else if (v == best) sb = ((k - k0) << F_K_SHIFT) | F_TIE;
-                        }
-                        if (best == d) f |= F_SWP | sb;
-                    }
-                }
-            } else d = INF;
-            fw[j >> 2] |= (u32)f << ((j & 3) * 8);
-            upj = Dp[j];
-            Dp[j] = d;
-            prevD = d;
-            sCur[r] = d >= 0xffff ? (u16)0xffff : (u16)d;
-        }
-        if (row0 < X.NP) store_flags<K>(X.F + (int64_t)c * X.NP + row0, fw);
-        block_sync<TPB>();
     }
-    // ---- score and end plane (:390-391, :436-440) ----
-    {
-        const int rq = X.Lq - 1, rr = X.padQ + X.Lr - 1;
-        if (rq >= row0 && rq < row0 + K) {
-#pragma unroll
-            for (int j = 0; j < K; j++) if (row0 + j == rq) sEnd[0] = Dp[j];
+    auto swap_eval = [&](const int j, const u16 *sPrev, int &best, int &sb) {
+        const u32 w = swi[j];
+        const int cnt = (int)(w >> 16);
+        best = INF; sb = 0;
+        if (cnt) {
+            const int v0 = sPrev[w & 0xffffu];
+            best = v0 == 0xffff ? INF : v0;
+            if (cnt > 1) {                                     // rare: insertion / adjacent deletions
+                const int k0 = tab[a0 + j];
+                for (int k = 1; k < cnt; k++) {
+                    int v = sPrev[obase + (int)src[k0 + k]];
+                    v = v == 0xffff ? INF : v;
+                    if (v < best) { best = v; sb = k << F_K_SHIFT; }
+                    else if (v == best) sb = (k << F_K_SHIFT) | F_TIE;     // keep the larger row
+                }
+            }
         }
-        if (rr >= row0 && rr < row0 + K) {
+    };
+
+    // Score-bounded sweep (Ukkonen): cells whose distance exceeds tau cannot lie on a path of cost
+    // <= tau, so threads whose rows cannot hold such a cell skip the column.  Every cell with
+    // D <= tau keeps its exact value and flags (its optimal predecessors have D <= tau as well), so
+    // the result is exact whenever the final score is <= tau; otherwise tau is quadrupled and the
+    // sweep repeated (worst case 1/3 extra work).  The last attempt has no bound at all.
+    const int unbounded = X.NP + X.Lt + 1;
+    for (int tau = (unbounded <= 4 * tau0 || tau0 >= unbounded) ? unbounded : tau0;; tau = (4 * tau >= unbounded) ? unbounded : 4 * tau) {
+        int Dp[K];
 #pragma unroll
-            for (int j = 0; j < K; j++) if (row0 + j == rr) sEnd[1] = Dp[j];
+        for (int j = 0; j < K; j++) Dp[j] = INF;
+#pragma unroll
+        for (int j = 0; j < K; j++) sD0[row0 + j] = 0xffff;
+        if (t == 0) {
+            sLive[0] = sLive[2] = sLive[4] = sLive[6] = INF;
+            sLive[1] = sLive[3] = sLive[5] = sLive[7] = -1;
+        }
+        block_sync<TPB>();
+
+        int tnext = X.tinfo[0];
+        bool dead = false;
+        for (int c = 0; c < X.Lt; c++) {
+            u16 *sPrev = (c & 1) ? sD1 : sD0, *sCur = (c & 1) ? sD0 : sD1;
+            const int tinfo = tnext;
+            if (c + 1 < X.Lt) tnext = X.tinfo[c + 1];
+            const int tch = tinfo & 0x7f;
+            const bool tok = tinfo & 0x80;
+            // ---- rows of my plane that can hold D <= tau in this column (plane-local, inclusive) ----
+            int candLo, candHi;
+            if (c == 0) { candLo = 0; candHi = tau; }
+            else {
+                const int *lv = sLive + ((c - 1) & 1) * 4;
+                const int loQ = lv[0], hiQ = lv[1], loR = lv[2], hiR = lv[3];
+                if (hiQ < loQ && hiR < loR) { dead = true; break; }        // nothing within tau is left
+                int lo = INF, hi = -1;
+                if (!P) {
+                    if (hiQ >= loQ) { lo = loQ; hi = hiQ + 1; }                                  // del, diag
+                    if (hiR >= loR) { lo = min(lo, (int)X.rptr[loR] + 1); hi = max(hi, (int)X.rptr[hiR] + 1); }   // swap dests
+                } else {
+                    if (hiR >= loR) { lo = loR; hi = hiR + 1; }
+                    if (hiQ >= loQ) { lo = min(lo, (int)X.qptr[loQ] + 1); hi = max(hi, (int)X.qptr[hiQ] + 1); }
+                }
+                candLo = lo; candHi = hi + tau;                            // + the in-column INS chain
+            }
+            const bool act = a0 <= candHi && a0 + K - 1 >= candLo && a0 < len;
+            // ---- pass 1: thread-local chain ----
+            int up = INF;                                       // D[a0-1][c-1]
+            int Dc[K];
+            if (act) {
+                {
+                    const int v = (a0 > 0 && c > 0) ? sPrev[row0 - 1] : 0xffff;
+                    up = v == 0xffff ? INF : v;
+                }
+                int run = INF;                                  // D[a-1][c] within the thread (no carry yet)
+                int upj = up;
+#pragma unroll
+                for (int j = 0; j < K; j++) {
+                    const bool m = ch[j] == tch;
+                    int b;
+                    if (a0 + j == 0 && c == 0) b = (a0 + j < len) ? 0 : INF;   // both origins start at 0 (:299-305)
+                    else {
+                        b = upj + (m ? 0 : 1);                  // diag (INF-safe: INF+1 stays huge)
+                        b = min(b, Dp[j] + 1);                  // del
+                        if (tok && m) {                         // swap (:334-349, :363-378)
+                            int best, sb;
+                            swap_eval(j, sPrev, best, sb);
+                            b = min(b, best);
+                        }
+                        if (a0 + j >= len) b = INF;
+                    }
+                    run = min(b, run + 1);
+                    Dc[j] = run;
+                    upj = Dp[j];
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < K; j++) Dc[j] = INF;
+            }
+            // ---- cross-thread min-plus prefix scan of G = last - lastrow ----
+            int G = act ? Dc[K - 1] - (row0 + K - 1) : INF;
+            int incl = G;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int o = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d && t - d >= segstart) incl = min(incl, o);
+            }
+            int excl = __shfl_up_sync(0xffffffffu, incl, 1);
+            if (lane == 0 || t - 1 < segstart) excl = INF;
+            int carry = excl;
+            if constexpr (TPB > 32) {
+                // warp totals per segment: the last lane's inclusive value covers the lanes of its own
+                // segment; a warp straddling the plane boundary also publishes its QUERY-part total
+                int *sWc = sW + (c & 1) * 64;
+                const int lastQ = tQ - 1;                        // last QUERY thread
+                if (lane == 31) sWc[(P ? 32 : 0) + warp] = incl;
+                if (t == lastQ && lane != 31) sWc[warp] = incl;
+                if (lane == 31 && !P) { /* pure QUERY warp: REF total empty */ sWc[32 + warp] = INF; }
+                if (lane == 31 && P && (t - 31) >= tQ) sWc[warp] = INF;      // pure REF warp: QUERY total empty
+                __syncthreads();
+                // totals of earlier warps in my segment.  The slot choice must be warp-uniform for the
+                // butterfly: a warp that starts on the QUERY plane reads QUERY totals; its REF lanes (a
+                // straddling warp) have no earlier REF warp at all.
+                const bool warpQ = 32 * warp < tQ;
+                int wv = (lane < warp) ? sWc[(warpQ ? 0 : 32) + lane] : INF;
+#pragma unroll
+                for (int d = 16; d; d >>= 1) wv = min(wv, __shfl_xor_sync(0xffffffffu, wv, d));
+                if (warpQ && P) wv = INF;
+                carry = min(carry, wv);
+            } else {
+                __syncwarp();
+            }
+            // everyone has read sLive of column c-1: recycle that slot for column c+1
+            if (t == 0) {
+                int *nx = sLive + ((c + 1) & 1) * 4;
+                nx[0] = nx[2] = INF; nx[1] = nx[3] = -1;
+            }
+            // ---- pass 2: final values and flags ----
+            if (act) {
+                u32 fw[(K + 3) / 4];
+#pragma unroll
+                for (int i = 0; i < (K + 3) / 4; i++) fw[i] = 0;
+                // carry is min(G) = D_last - lastrow over earlier threads, so the chain value at row r is carry + r
+                int prevD = carry >= INF / 2 ? INF : carry + (row0 - 1);           // D[a0-1][c]
+                int upj = up;
+                int mylo = INF, myhi = -1;
+#pragma unroll
+                for (int j = 0; j < K; j++) {
+                    const int r = row0 + j;
+                    int d = Dc[j];
+                    if (carry < INF / 2) d = min(d, carry + r);
+                    int f = 0;
+                    if (a0 + j < len) {
+                        if (a0 + j == 0 && c == 0) f = F_DIAG;
+                        else {
+                            const bool m = ch[j] == tch;
+                            if (a0 + j > 0 && c > 0 && upj + (m ? 0 : 1) == d) f |= F_DIAG;
+                            if (a0 + j > 0 && prevD + 1 == d) f |= F_INS;
+                            if (c > 0 && Dp[j] + 1 == d) f |= F_DEL;
+                            if (tok && m) {
+                                int best, sb;
+                                swap_eval(j, sPrev, best, sb);
+                                if (best == d) f |= F_SWP | sb;
+                            }
+                        }
+                        if (d <= tau) { mylo = min(mylo, a0 + j); myhi = a0 + j; }
+                    } else d = INF;
+                    fw[j >> 2] |= (u32)f << ((j & 3) * 8);
+                    upj = Dp[j];
+                    Dp[j] = d;
+                    prevD = d;
+                    sCur[r] = d >= 0xffff ? (u16)0xffff : (u16)d;
+                }
+                store_flags<K>(X.F + (int64_t)c * X.NP + row0, fw);
+                if (myhi >= 0) {
+                    int *lc = sLive + (c & 1) * 4 + (P ? 2 : 0);
+                    atomicMin(&lc[0], mylo);
+                    atomicMax(&lc[1], myhi);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < K; j++) { Dp[j] = INF; sCur[row0 + j] = 0xffff; }
+            }
+            block_sync<TPB>();
+        }
+        // ---- score and end plane (:390-391, :436-440) ----
+        if (t == 0) { sEnd[0] = INF; sEnd[1] = INF; }
+        block_sync<TPB>();
+        if (!dead) {
+            const int rq = X.Lq - 1, rr = X.padQ + X.Lr - 1;
+            if (rq >= row0 && rq < row0 + K) {
+#pragma unroll
+                for (int j = 0; j < K; j++) if (row0 + j == rq) sEnd[0] = Dp[j];
+            }
+            if (rr >= row0 && rr < row0 + K) {
+#pragma unroll
+                for (int j = 0; j < K; j++) if (row0 + j == rr) sEnd[1] = Dp[j];
+            }
         }
         block_sync<TPB>();
         score = min(sEnd[0], sEnd[1]);
         end_plane = sEnd[0] == score ? 0 : 1;
+        block_sync<TPB>();
+#ifdef VD_DEBUG
+        if (t == 0) printf("fwd sc=%d ai=%d NP=%d Lt=%d tau=%d score=%d dead=%d\n", X.sc, X.ai, X.NP, X.Lt, tau, score, (int)dead);
+#endif
+        if (score <= tau || tau >= unbounded) break;
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Banded forward sweep for long alignments.  Same recurrence and flags as wave_fwd_body, but only
+// the rows that can hold a distance <= tau are visited in each column (Ukkonen's cut-off; exact
+// whenever the final score is <= tau).  The band is a few hundred rows wide while the matrix side
+// is thousands, so rows are dealt ONE per thread from the band's start in every column (D of the
+// previous column lives in shared memory for all rows, so the thread<->row mapping is free to
+// slide with the band); bands wider than the block are processed in chunks with the INS-chain
+// carry handed from chunk to chunk.  tau = 96, 384, 1536; alignments that need more are flagged
+// for the dense register-blocked kernel.
+// ------------------------------------------------------------------------------------------
+constexpr int FWDB_TPB = 512;
+constexpr int FWDB_TAU_MAX = 1536;
+__host__ __device__ inline int fwdb_smem(int npmax) { return 4 * npmax + 32 + 2 * 64 * 4 + 64; }
+
+__global__ void __launch_bounds__(FWDB_TPB) wave_fwdb_kernel(WaveArgs A, int item0, int npmax, int *need_dense) {
+    extern __shared__ __align__(16) u8 smem_raw[];
+    const WaveCtx X = wave_ctx(A, A.items[item0 + blockIdx.x]);
+    u16 *sD0 = (u16 *)smem_raw, *sD1 = sD0 + npmax;
+    int *sLive = (int *)(sD1 + npmax);
+    int *sW = sLive + 8;                                     // [2 parities][2 segments][32 warps]
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    constexpr int NW = FWDB_TPB / 32;
+    const int64_t oi = 4 * (int64_t)X.sc + X.ai;
+    const int NPr = X.padQ + X.Lr;                           // rows in use (REF plane starts at padQ)
+    bool solved = false;
+
+    for (int tau = FWD_TAU0; tau <= FWDB_TAU_MAX && !solved; tau *= 4) {
+        for (int r = t; r < NPr; r += FWDB_TPB) { sD0[r] = 0xffff; sD1[r] = 0xffff; }
+        if (t == 0) {
+            sLive[0] = sLive[2] = sLive[4] = sLive[6] = INF;
+            sLive[1] = sLive[3] = sLive[5] = sLive[7] = -1;
+        }
+        __syncthreads();
+        // candidate intervals of the two previous columns (plane-local, inclusive; empty: lo > hi)
+        int p1lo[2] = {1, 1}, p1hi[2] = {0, 0}, p2lo[2] = {1, 1}, p2hi[2] = {0, 0};
+        int tnext = X.tinfo[0];
+        bool dead = false;
+        int wpar = 0;
+        for (int c = 0; c < X.Lt; c++) {
+            u16 *sPrev = (c & 1) ? sD1 : sD0, *sCur = (c & 1) ? sD0 : sD1;
+            const int tinfo = tnext;
+            if (c + 1 < X.Lt) tnext = X.tinfo[c + 1];
+            const int tch = tinfo & 0x7f;
+            const bool tok = tinfo & 0x80;
+            // ---- candidate rows of both planes ----
+            int clo[2], chi[2];
+            if (c == 0) { clo[0] = clo[1] = 0; chi[0] = min(tau, X.Lq - 1); chi[1] = min(tau, X.Lr - 1); }
+            else {
+                const int *lv = sLive + ((c - 1) & 1) * 4;
+                const int loQ = lv[0], hiQ = lv[1], loR = lv[2], hiR = lv[3];
+                if (hiQ < loQ && hiR < loR) { dead = true; break; }
+                int lo0 = INF, hi0 = -1, lo1 = INF, hi1 = -1;
+                if (hiQ >= loQ) { lo0 = loQ; hi0 = hiQ + 1; lo1 = X.qptr[loQ] + 1; hi1 = X.qptr[hiQ] + 1; }
+                if (hiR >= loR) {
+                    lo1 = min(lo1, loR); hi1 = max(hi1, hiR + 1);
+                    lo0 = min(lo0, X.rptr[loR] + 1); hi0 = max(hi0, X.rptr[hiR] + 1);
+                }
+                clo[0] = max(lo0, 0); chi[0] = min(hi0 + tau, X.Lq - 1);
+                clo[1] = max(lo1, 0); chi[1] = min(hi1 + tau, X.Lr - 1);
+            }
+            const int nQ = max(0, chi[0] - clo[0] + 1), nR = max(0, chi[1] - clo[1] + 1);
+            const int total = nQ + nR;
+            __syncthreads();                                 // everyone has read sLive[c-1]
+            if (t == 0) { int *nx = sLive + ((c + 1) & 1) * 4; nx[0] = nx[2] = INF; nx[1] = nx[3] = -1; }
+            int cg0 = INF, cg1 = INF;                        // min(D - a) over the rows already done, per plane
+            for (int base = 0; base < total; base += FWDB_TPB) {
+                const int v = base + t;
+                const bool valid = v < total;
+                const bool P = v >= nQ;
+                const int a = P ? clo[1] + (v - nQ) : clo[0] + v;
+                const int row = P ? X.padQ + a : a;
+                int b = INF, diag = INF, del = INF, swp = INF, sb = 0;
+                bool m = false;
+                if (valid) {
+                    const int chv = (P ? X.rseq[a] : X.qstr[a]) & 0x7f;
+                    m = chv == tch;
+                    if (a == 0 && c == 0) b = 0;                                     // :299-305
+                    else {
+                        if (c > 0) {
+                            const int dv = sPrev[row];
+                            if (dv != 0xffff) del = dv + 1;                              // :406-413
+                            if (a > 0) {
+                                const int uv = sPrev[row - 1];
+                                if (uv != 0xffff) diag = uv + (m ? 0 : 1);               // :324-332, :415-422
+                            }
+                            if (tok && m) {                                              // :334-349, :363-378
+                                const u32 w = P ? X.swiR[a] : X.swiQ[a];
+                                const int cnt = (int)(w >> 16);
+                                if (cnt) {
+                                    const int ob = P ? 0 : X.padQ;
+                                    const int v0 = sPrev[ob + (int)(w & 0xffffu)];
+                                    swp = v0 == 0xffff ? INF : v0;
+                                    if (cnt > 1) {
+                                        const int *tab = P ? X.toR : X.toQ;
+                                        const int *src = tab + (P ? X.Lr : X.Lq) + 1;
+                                        const int k0 = tab[a];
+                                        for (int k = 1; k < cnt; k++) {
+                                            int v2 = sPrev[ob + src[k0 + k]];
+                                            v2 = v2 == 0xffff ? INF : v2;
+                                            if (v2 < swp) { swp = v2; sb = k << F_K_SHIFT; }
+                                            else if (v2 == swp) sb = (k << F_K_SHIFT) | F_TIE;
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                        b = min(min(diag, del), swp);
+                    }
+                }
+                // ---- min-plus scan of G = b - a over the threads of my plane in this chunk ----
+                const int segstart = P ? max(nQ - base, 0) : 0;          // first thread of my plane in this chunk
+                int incl = (valid && b < INF) ? b - a : INF;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int o = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d && t - d >= segstart) incl = min(incl, o);
+                }
+                int excl = __shfl_up_sync(0xffffffffu, incl, 1);
+                if (lane == 0 || t - 1 < segstart) excl = INF;
+                int *sWc = sW + wpar * 64;
+                wpar ^= 1;
+                // per-warp totals of each plane: lanes of plane Q are a prefix of the chunk
+                {
+                    const unsigned mq = __ballot_sync(0xffffffffu, !P);
+                    int tq = INF, tr = INF;
+                    if (mq) tq = __shfl_sync(0xffffffffu, incl, 31 - __clz(mq));   // last Q lane: inclusive over Q lanes
+                    if (~mq) tr = __shfl_sync(0xffffffffu, incl, 31);              // last lane: inclusive over R lanes
+                    if (lane == 0) { sWc[warp] = mq ? tq : INF; sWc[32 + warp] = (~mq) ? tr : INF; }
+                }
+                __syncthreads();
+                int preq = (lane < warp) ? sWc[lane] : INF, prer = (lane < warp) ? sWc[32 + lane] : INF;
+                int totq = (lane < NW) ? sWc[lane] : INF, totr = (lane < NW) ? sWc[32 + lane] : INF;
+#pragma unroll
+                for (int d = 16; d; d >>= 1) {
+                    preq = min(preq, __shfl_xor_sync(0xffffffffu, preq, d));
+                    prer = min(prer, __shfl_xor_sync(0xffffffffu, prer, d));
+                    totq = min(totq, __shfl_xor_sync(0xffffffffu, totq, d));
+                    totr = min(totr, __shfl_xor_sync(0xffffffffu, totr, d));
+                }
+                if (valid) {
+                    const int carry = min(excl, min(P ? prer : preq, P ? cg1 : cg0));
+                    const int ins = (a > 0 && carry < INF / 2) ? carry + a : INF;         // = D[a-1][c] + 1  (:397-404)
+                    const int d = min(b, ins);
+                    int f = 0;
+                    if (a == 0 && c == 0) f = F_DIAG;
+                    else if (d < INF / 2) {
+                        if (diag == d) f |= F_DIAG;
+                        if (ins == d) f |= F_INS;
+                        if (del == d) f |= F_DEL;
+                        if (swp == d) f |= F_SWP | sb;
+                    }
+                    sCur[row] = d >= 0xffff ? (u16)0xffff : (u16)d;
+                    X.F[(int64_t)c * X.NP + row] = (u8)f;
+                    if (d <= tau) {
+                        int *lc = sLive + (c & 1) * 4 + (P ? 2 : 0);
+                        atomicMin(&lc[0], a);
+                        atomicMax(&lc[1], a);
+                    }
+                }
+                cg0 = min(cg0, totq); cg1 = min(cg1, totr);
+            }
+            // ---- rows that were candidates two columns ago but not now hold stale values ----
+#pragma unroll
+            for (int P = 0; P < 2; P++) {
+                const int rb = P ? X.padQ : 0;
+                for (int a = p2lo[P] + t; a <= p2hi[P]; a += FWDB_TPB)
+                    if (a < clo[P] || a > chi[P]) sCur[rb + a] = 0xffff;
+                p2lo[P] = p1lo[P]; p2hi[P] = p1hi[P];
+                p1lo[P] = clo[P]; p1hi[P] = chi[P];
+            }
+            __syncthreads();
+        }
+        __syncthreads();
+        if (!dead) {
+            const u16 *sFin = (X.Lt & 1) ? sD1 : sD0;       // column Lt-1 was written as "cur" of its parity
+            const int vq = sFin[X.Lq - 1], vr = sFin[X.padQ + X.Lr - 1];
+            const int dq = vq == 0xffff ? INF : vq, dr = vr == 0xffff ? INF : vr;
+            const int score = min(dq, dr);
+            if (score <= tau) {
+                solved = true;
+                if (t == 0) {
+                    A.out.aln_score[oi] = score;
+                    A.out.aln_end_plane[oi] = (u8)(dq == score ? 0 : 1);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (t == 0) need_dense[item0 + blockIdx.x] = solved ? 0 : 1;
+}
+
 template <int TPB, int K>
-__global__ void __launch_bounds__(TPB) wave_fwd_kernel(WaveArgs A, int item0) {
+__global__ void __launch_bounds__(TPB) wave_fwd_kernel(WaveArgs A, int item0, const int *need_dense) {
     extern __shared__ __align__(16) u8 smem_raw[];
     __shared__ int sEnd[2];
+    if (need_dense && !need_dense[item0 + blockIdx.x]) return;       // solved by the banded sweep
     const WaveCtx X = wave_ctx(A, A.items[item0 + blockIdx.x]);
     int score, end_plane;
-    wave_fwd_body<TPB, K, int>(X, threadIdx.x, smem_raw, sEnd, score, end_plane);
+    // after a failed banded sweep (tau up to FWDB_TAU_MAX) go straight to the unbounded pass
+    wave_fwd_body<TPB, K, int>(X, threadIdx.x, smem_raw, sEnd, score, end_plane, need_dense ? (1 << 28) : FWD_TAU0);
     if (threadIdx.x == 0) {
         A.out.aln_score[4 * (int64_t)X.sc + X.ai] = score;
         A.out.aln_end_plane[4 * (int64_t)X.sc + X.ai] = (u8)end_plane;
@@ -915,7 +1211,7 @@ __global__ void wave_walk_kernel(WaveArgs A, int n_items) {
 }
 
 // ---- host side --------------------------------------------------------------------------------
-template <int TPB, int K> constexpr int wave_fwd_smem() { return 2 * TPB * K * 2 + 2 * 64 * 4; }
+template <int TPB, int K> constexpr int wave_fwd_smem() { return 2 * TPB * K * 2 + 32 + 2 * 64 * 4; }
 template <int TPB, int K> constexpr int wave_bwd_smem() { return 2 * TPB * K * 2 + 2 * TPB * K + 2 * 64 * 4; }
 
 template <int TPB, int K> inline void wave_configure_one() {
@@ -927,29 +1223,36 @@ inline void wave_configure() {
     wave_configure_one<128, 4>(); wave_configure_one<256, 8>(); wave_configure_one<512, 16>();
     wave_configure_one<1024, 16>(); wave_configure_one<1024, 32>();
     cudaFuncSetAttribute(wave_sbwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * 32768);
+    cudaFuncSetAttribute(wave_fwdb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fwdb_smem(32768));
 }
 
+constexpr int FWDB_MIN_CLASS = 4;      // classes with more than 512 rows go through the banded sweep first
 template <int TPB, int K>
-inline void wave_launch_pair(cudaStream_t st, const WaveArgs &A, int item0, int n, bool fwd) {
+inline void wave_launch_pair(cudaStream_t st, const WaveArgs &A, int item0, int n, bool fwd, int *need_dense = nullptr) {
     if (n <= 0) return;
-    if (fwd) wave_fwd_kernel<TPB, K><<<n, TPB, wave_fwd_smem<TPB, K>(), st>>>(A, item0);
+    if (fwd && need_dense) {
+        wave_fwdb_kernel<<<n, FWDB_TPB, fwdb_smem(TPB * K), st>>>(A, item0, TPB * K, need_dense);
+        wave_fwd_kernel<TPB, K><<<n, TPB, wave_fwd_smem<TPB, K>(), st>>>(A, item0, need_dense);
+    } else if (fwd) wave_fwd_kernel<TPB, K><<<n, TPB, wave_fwd_smem<TPB, K>(), st>>>(A, item0, nullptr);
     else wave_bwd_kernel<TPB, K><<<n, TPB, wave_bwd_smem<TPB, K>(), st>>>(A, item0);
 }
-inline void wave_launch(cudaStream_t st, const WaveArgs &A, int cls, int item0, int n, bool fwd, bool sparse_bwd = true) {
+inline void wave_launch(cudaStream_t st, const WaveArgs &A, int cls, int item0, int n, bool fwd, bool sparse_bwd = true,
+                        int *need_dense = nullptr) {
+    if (cls < FWDB_MIN_CLASS) need_dense = nullptr;
     if (!fwd && sparse_bwd) {
         const int npmax = wave_tpb(cls) * wave_k(cls);
         wave_sbwd_kernel<<<n, 32, 6 * npmax, st>>>(A, item0, npmax);
         return;
     }
     switch (cls) {
-        case 0: wave_launch_pair<32, 1>(st, A, item0, n, fwd); break;
-        case 1: wave_launch_pair<32, 2>(st, A, item0, n, fwd); break;
-        case 2: wave_launch_pair<32, 4>(st, A, item0, n, fwd); break;
-        case 3: wave_launch_pair<128, 4>(st, A, item0, n, fwd); break;
-        case 4: wave_launch_pair<256, 8>(st, A, item0, n, fwd); break;
-        case 5: wave_launch_pair<512, 16>(st, A, item0, n, fwd); break;
-        case 6: wave_launch_pair<1024, 16>(st, A, item0, n, fwd); break;
-        case 7: wave_launch_pair<1024, 32>(st, A, item0, n, fwd); break;
+        case 0: wave_launch_pair<32, 1>(st, A, item0, n, fwd, need_dense); break;
+        case 1: wave_launch_pair<32, 2>(st, A, item0, n, fwd, need_dense); break;
+        case 2: wave_launch_pair<32, 4>(st, A, item0, n, fwd, need_dense); break;
+        case 3: wave_launch_pair<128, 4>(st, A, item0, n, fwd, need_dense); break;
+        case 4: wave_launch_pair<256, 8>(st, A, item0, n, fwd, need_dense); break;
+        case 5: wave_launch_pair<512, 16>(st, A, item0, n, fwd, need_dense); break;
+        case 6: wave_launch_pair<1024, 16>(st, A, item0, n, fwd, need_dense); break;
+        case 7: wave_launch_pair<1024, 32>(st, A, item0, n, fwd, need_dense); break;
     }
 }
 
