@@ -168,6 +168,33 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def run_secondary(eng, args, dev, torch):
+    """BASELINE configs[3] (WGS + SV tail to 10 kb) at 1/9 scale, through vd_run with host buffers:
+    400 k superclusters of the demo mixture of which 0.3 % carry one 50 bp..10 kb INS/DEL."""
+    b, cells, n = make_workload("wgs_sv", 400_000, args.seed, 0, 1, args.sv_max)
+    for _ in range(2):
+        eng.run(b)
+    ms = []
+    kern = {"wave_fwd": 0.0, "wave_bwd": 0.0, "wave_walk": 0.0, "tiny": 0.0}
+    for _ in range(3):
+        t0 = time.perf_counter()
+        eng.run(b)
+        ms.append((time.perf_counter() - t0) * 1e3)
+        st = eng.stats()
+        kern["wave_fwd"] += st["ms_long_fwd"] / 3; kern["wave_bwd"] += st["ms_long_bwd"] / 3
+        kern["wave_walk"] += st["ms_long_walk"] / 3; kern["tiny"] += st["ms_short"] / 3
+    m = float(np.median(ms))
+    st = eng.stats()
+    peak, _ = measured_peak()
+    fwd_bytes = st["spill_bytes"] / 3.0          # forward sweep: one flag byte per cell of the spilled matrices
+    return {"workload": WORKLOADS["wgs_sv"]["config"] + " at 1/9 scale", "n_superclusters": n, "cells": cells,
+            "e2e_ms_per_step": m, "e2e_gcells_per_s": cells / (m * 1e-3) / 1e9,
+            "e2e_superclusters_per_s": n / (m * 1e-3), "kernel_ms_per_step": kern,
+            "long_alignments": int(st["n_long"]),
+            "roofline_wave_fwd": {"bound": "hbm", "achieved": fwd_bytes / (kern["wave_fwd"] * 1e-3) / 1e9 if kern["wave_fwd"] else 0.0,
+                                  "peak": peak, "unit": "GB/s", "note": "full-matrix-equivalent: 1 B/cell / summed class durations"}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -180,6 +207,8 @@ def main():
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--ref-sample", type=int, default=200_000, help="superclusters in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--secondary", action="store_true",
+                    help="also time the SV-bearing workload (BASELINE configs[3]) at 1/9 scale through vd_run")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -345,6 +374,15 @@ def main():
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes},
         }
+        # measured DRAM traffic of the dominant kernel (ncu --set full capture of this round, per launch
+        # at this workload size; profiles/README.md), null when no capture matches the workload
+        tr = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tr):
+            t_ = json.load(open(tr)).get(f"{args.workload}:{dom}")
+            if t_ and t_.get("n_sc_per_gpu") == b.n_sc:
+                line["roofline"]["traffic"] = t_["dram_bytes_per_launch"]
+        if args.secondary and world == 1 and args.workload == "wgs":
+            line["secondary"] = run_secondary(eng, args, dev, torch)
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
             sb, scells, _ = make_workload(args.workload, args.ref_sample, args.seed, 0, 1, args.sv_max)

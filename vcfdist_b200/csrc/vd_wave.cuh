@@ -617,8 +617,6 @@ __global__ void __launch_bounds__(FWDB_TPB) wave_fwdb_kernel(WaveArgs A, int ite
             }
             const int nQ = max(0, chi[0] - clo[0] + 1), nR = max(0, chi[1] - clo[1] + 1);
             const int total = nQ + nR;
-            __syncthreads();                                 // everyone has read sLive[c-1]
-            if (t == 0) { int *nx = sLive + ((c + 1) & 1) * 4; nx[0] = nx[2] = INF; nx[1] = nx[3] = -1; }
             int cg0 = INF, cg1 = INF;                        // min(D - a) over the rows already done, per plane
             for (int base = 0; base < total; base += FWDB_TPB) {
                 const int v = base + t;
@@ -685,6 +683,8 @@ __global__ void __launch_bounds__(FWDB_TPB) wave_fwdb_kernel(WaveArgs A, int ite
                     if (lane == 0) { sWc[warp] = mq ? tq : INF; sWc[32 + warp] = (~mq) ? tr : INF; }
                 }
                 __syncthreads();
+                // everyone has read sLive[c-1] by now: recycle its slot for column c+1
+                if (t == 0 && base == 0) { int *nx = sLive + ((c + 1) & 1) * 4; nx[0] = nx[2] = INF; nx[1] = nx[3] = -1; }
                 int preq = (lane < warp) ? sWc[lane] : INF, prer = (lane < warp) ? sWc[32 + lane] : INF;
                 int totq = (lane < NW) ? sWc[lane] : INF, totr = (lane < NW) ? sWc[32 + lane] : INF;
 #pragma unroll
@@ -694,6 +694,7 @@ __global__ void __launch_bounds__(FWDB_TPB) wave_fwdb_kernel(WaveArgs A, int ite
                     totq = min(totq, __shfl_xor_sync(0xffffffffu, totq, d));
                     totr = min(totr, __shfl_xor_sync(0xffffffffu, totr, d));
                 }
+                int liveA = -1;                              // my row if it is within tau
                 if (valid) {
                     const int carry = min(excl, min(P ? prer : preq, P ? cg1 : cg0));
                     const int ins = (a > 0 && carry < INF / 2) ? carry + a : INF;         // = D[a-1][c] + 1  (:397-404)
@@ -708,10 +709,22 @@ __global__ void __launch_bounds__(FWDB_TPB) wave_fwdb_kernel(WaveArgs A, int ite
                     }
                     sCur[row] = d >= 0xffff ? (u16)0xffff : (u16)d;
                     X.F[(int64_t)c * X.NP + row] = (u8)f;
-                    if (d <= tau) {
-                        int *lc = sLive + (c & 1) * 4 + (P ? 2 : 0);
-                        atomicMin(&lc[0], a);
-                        atomicMax(&lc[1], a);
+                    if (d <= tau) liveA = a;
+                }
+                {   // one shared-memory atomic per warp and bound instead of one per thread
+                    const unsigned mq2 = __ballot_sync(0xffffffffu, liveA >= 0 && !P);
+                    const unsigned mr2 = __ballot_sync(0xffffffffu, liveA >= 0 && P);
+                    int *lc = sLive + (c & 1) * 4;
+                    // rows ascend with the lane inside a plane: lowest / highest set lane give min / max
+                    if (mq2) {
+                        const int lo = __shfl_sync(0xffffffffu, liveA, __ffs(mq2) - 1);
+                        const int hi = __shfl_sync(0xffffffffu, liveA, 31 - __clz(mq2));
+                        if (lane == 0) { atomicMin(&lc[0], lo); atomicMax(&lc[1], hi); }
+                    }
+                    if (mr2) {
+                        const int lo = __shfl_sync(0xffffffffu, liveA, __ffs(mr2) - 1);
+                        const int hi = __shfl_sync(0xffffffffu, liveA, 31 - __clz(mr2));
+                        if (lane == 0) { atomicMin(&lc[2], lo); atomicMax(&lc[3], hi); }
                     }
                 }
                 cg0 = min(cg0, totq); cg1 = min(cg1, totr);
