@@ -175,14 +175,14 @@ def run_secondary(eng, args, dev, torch):
     for _ in range(2):
         eng.run(b)
     ms = []
-    kern = {"wave_fwd": 0.0, "wave_bwd": 0.0, "wave_walk": 0.0, "tiny": 0.0}
+    kern = {"wave_fwd": 0.0, "wave_bwd": 0.0, "wave_walk": 0.0, "small": 0.0}
     for _ in range(3):
         t0 = time.perf_counter()
         eng.run(b)
         ms.append((time.perf_counter() - t0) * 1e3)
         st = eng.stats()
         kern["wave_fwd"] += st["ms_long_fwd"] / 3; kern["wave_bwd"] += st["ms_long_bwd"] / 3
-        kern["wave_walk"] += st["ms_long_walk"] / 3; kern["tiny"] += st["ms_short"] / 3
+        kern["wave_walk"] += st["ms_long_walk"] / 3; kern["small"] += st["ms_short"] / 3
     m = float(np.median(ms))
     st = eng.stats()
     peak, _ = measured_peak()
@@ -288,7 +288,8 @@ def main():
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches = 0
-    ms_short = ms_fwd = ms_bwd = ms_walk = ms_plan = ms_kernels = ms_mid = 0.0
+    ms_short = ms_fwd = ms_bwd = ms_walk = ms_plan = ms_kernels = 0.0
+    ms_small = [0.0, 0.0, 0.0]
     barrier()
     ev0.record(stream)
     for _ in range(args.steps):
@@ -296,7 +297,8 @@ def main():
         st = eng.stats()
         launches += st["n_launches"]
         ms_short += st["ms_short"]; ms_fwd += st["ms_long_fwd"]; ms_bwd += st["ms_long_bwd"]
-        ms_walk += st["ms_long_walk"]; ms_plan += st["ms_plan"]; ms_kernels += st["ms_total"]; ms_mid += st["ms_mid"]
+        ms_walk += st["ms_long_walk"]; ms_plan += st["ms_plan"]; ms_kernels += st["ms_total"]
+        ms_small = [a + b_ for a, b_ in zip(ms_small, st["ms_small"])]
     ev1.record(stream)
     barrier()
     ms = ev0.elapsed_time(ev1)
@@ -340,15 +342,15 @@ def main():
         ms_step = ms_max / args.steps
         value = cells_total / (ms_step * 1e-3) / 1e9
         # dominant kernel of this workload and its algorithmic bytes per launch:
-        # short regime -> tiny_kernel moves the compact batch in and the result records out;
-        # long regime  -> wave_fwd writes 1 B/cell of flags (+ the same io)
+        # short regime -> small_kernel<k> moves the compact batch of its superclusters in and their
+        #                 result records out (vd_stats.io_small[k]);
+        # long regime  -> wave_fwd writes 1 B/cell of flags
         k_short, k_fwd, k_bwd = ms_short / args.steps, ms_fwd / args.steps, ms_bwd / args.steps
-        if k_fwd > k_short:
-            dom, dom_ms = "wave_fwd_kernel", k_fwd
-            alg_bytes = st["spill_bytes"] / 3.0
-        else:
-            dom, dom_ms = "tiny_kernel", k_short
-            alg_bytes = float(b.io_bytes())
+        k_small = [x / args.steps for x in ms_small]
+        cand = {f"small_kernel<{k}>": (k_small[k], float(st["io_small"][k])) for k in range(3)}
+        cand["wave_fwd_kernel"] = (k_fwd, st["spill_bytes"] / 3.0)
+        dom = max(cand, key=lambda k_: cand[k_][0])
+        dom_ms, alg_bytes = cand[dom]
         achieved = alg_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
         line = {
             "metric": "dp_gcells_per_s", "value": value, "unit": "Gcells/s",
@@ -368,11 +370,13 @@ def main():
                     "h2d_bytes_per_step": int(st_e["h2d_bytes"]), "d2h_bytes_per_step": int(st_e["d2h_bytes"]),
                     "api": "vd_run (C-ABI, pinned host buffers)"},
             "gpu_launches": int(launches),
-            "kernel_ms_per_step": {"plan": ms_plan / args.steps, "tiny": k_short, "mid": ms_mid / args.steps, "wave_fwd": k_fwd, "wave_bwd": k_bwd,
+            "kernel_ms_per_step": {"plan": ms_plan / args.steps, "small_all": k_short, "small_0": k_small[0], "small_1": k_small[1],
+                                   "small_2": k_small[2], "wave_fwd": k_fwd, "wave_bwd": k_bwd,
                                    "wave_walk": ms_walk / args.steps, "all_kernels": ms_kernels / args.steps},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes},
+                         "algorithmic_bytes_per_launch": alg_bytes,
+                         "superclusters_per_class": [int(x) for x in st["n_small"]] + [int(st["n_long"]) // 4]},
         }
         # measured DRAM traffic of the dominant kernel (ncu --set full capture of this round, per launch
         # at this workload size; profiles/README.md), null when no capture matches the workload

@@ -130,11 +130,14 @@ typedef struct vd_stats {
     int64_t n_launches;       /* kernels launched                                                  */
     int64_t h2d_bytes, d2h_bytes;
     float   ms_total;         /* CUDA-event time of the whole call on the handle's stream          */
-    float   ms_short;         /* ... of the short-supercluster kernel                              */
+    float   ms_short;         /* ... of the short-supercluster kernels (all classes)              */
     float   ms_long_fwd, ms_long_bwd, ms_long_walk;
     float   ms_plan;
     float   ms_long_wall;     /* wall time of the concurrent forward+backward region            */
-    float   ms_mid;           /* ... of the fused mid-size kernel (summed over its classes)       */
+    float   ms_small[3];      /* ... of the fused shared-memory kernels: thread-per-alignment class 0,
+                                 class 1, warp-per-supercluster kernel (all its launches)           */
+    int64_t n_small[3];       /* superclusters handled by each of them                             */
+    int64_t io_small[3];      /* algorithmic input+output bytes of those superclusters             */
 } vd_stats;
 
 /* Final per-variant / per-supercluster results in the reference's own terms

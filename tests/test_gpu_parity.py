@@ -45,15 +45,56 @@ def test_golden_through_c_abi(engine, name):
     assert mismatches(fin, refA, FINAL_KEYS, var_mask=mask) == {}
 
 
-@pytest.mark.parametrize("cls", [1, 2, 4])
+@pytest.mark.parametrize("cls", [1, 2])
 @pytest.mark.parametrize("name", ["demo", "adv_11", "adv_12", "sv_21"])
 def test_every_kernel_family_on_golden(name, cls):
-    """Force all superclusters through the wavefront (1), scalar-slab (2) or fused mid-size (4) kernels
-    (4: whatever does not fit shared memory falls through to the wavefront kernels)."""
+    """Force all superclusters through the wavefront (1) or scalar-slab (2) kernels."""
     b, _, refB = load_golden(name)
     e = forced_engine(cls)
     got = check_vs_oracle(e, b)
     assert mismatches(capi.finalize(b, got).trimmed(), refB, FINAL_KEYS) == {}
+    e.close()
+
+
+def engine_with(**env):
+    os.environ.update({k: str(v) for k, v in env.items()})
+    try:
+        return capi.Engine(0)
+    finally:
+        for k in env:
+            del os.environ[k]
+
+
+@pytest.mark.parametrize("lo,hi,wsc", [(0, 0, 1), (1, 1, 1), (0, 1, 0), (0, -1, 1), (0, -1, 0)])
+@pytest.mark.parametrize("name", ["demo", "adv_11", "adv_12"])
+def test_every_short_kernel_on_golden(name, lo, hi, wsc):
+    """Restrict the thread-per-alignment kernels to footprint classes lo..hi (hi < lo: none) and switch
+    the warp-per-supercluster kernel on/off, so that every kernel also sees the superclusters a cheaper
+    one would normally take; whatever is left falls through to the HBM-slab wavefront kernels."""
+    b, _, refB = load_golden(name)
+    e = engine_with(VD_SMALL_MIN=lo, VD_SMALL_MAX=hi, VD_WSC=wsc)
+    got = check_vs_oracle(e, b)
+    assert mismatches(capi.finalize(b, got).trimmed(), refB, FINAL_KEYS) == {}
+    st = e.stats()
+    assert sum(st["n_small"]) * 4 == st["n_short"] and st["n_short"] + st["n_long"] == 4 * b.n_sc
+    assert st["n_small"][0] == 0 or lo == 0
+    assert st["n_small"][1] == 0 or lo <= 1 <= hi
+    assert (st["n_small"][2] > 0) == bool(wsc)
+    if name == "demo" and hi >= lo:
+        assert sum(st["n_small"][lo:hi + 1]) > 0
+    e.close()
+
+
+def test_warp_kernel_shapes():
+    """Warp-per-supercluster kernel on its own: one to four register slots (<= 32 .. <= 128 rows),
+    several swap sources per row (insertions, adjacent deletions), every shared-memory bin."""
+    b = Batch.concat([synth.adversarial(31, 600, max_len=14), synth.adversarial(32, 600, max_len=28),
+                      synth.adversarial(33, 300, max_len=45), synth.adversarial(35, 200, max_len=60),
+                      synth.wgs_like(34, 3000)])
+    e = engine_with(VD_SMALL_MAX=-1)
+    check_vs_oracle(e, b)
+    st = e.stats()
+    assert st["n_small"][2] > 1000
     e.close()
 
 

@@ -75,11 +75,13 @@ class vd_stats(C.Structure):
         ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
         ("ms_total", C.c_float), ("ms_short", C.c_float),
         ("ms_long_fwd", C.c_float), ("ms_long_bwd", C.c_float), ("ms_long_walk", C.c_float),
-        ("ms_plan", C.c_float), ("ms_long_wall", C.c_float), ("ms_mid", C.c_float),
+        ("ms_plan", C.c_float), ("ms_long_wall", C.c_float), ("ms_small", C.c_float * 3),
+        ("n_small", C.c_int64 * 3), ("io_small", C.c_int64 * 3),
     ]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_}
+        return {k: (list(getattr(self, k)) if k in ("ms_small", "n_small", "io_small") else getattr(self, k))
+                for k, _ in self._fields_}
 
 
 def _ptr(a: Optional[np.ndarray]):

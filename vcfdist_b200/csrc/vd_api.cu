@@ -16,7 +16,6 @@
 
 #include "vd_kernels.cuh"
 #include "vd_wave.cuh"
-#include "vd_mid.cuh"
 
 using namespace vd;
 
@@ -41,7 +40,7 @@ struct vd_handle {
     cudaEvent_t ev[8] = {};
     cudaStream_t side[vd::N_WCLS] = {};     // one stream per wavefront class: classes run concurrently
     cudaEvent_t sev[vd::N_WCLS][3] = {};
-    cudaEvent_t mev[vd::N_MCLS][2] = {};
+    cudaEvent_t gev[vd::N_GROUP][2] = {};   // start / end of each short-kernel launch group
     int64_t scratch_budget = 0;
     int num_sms = 148;
     std::string err;
@@ -49,7 +48,10 @@ struct vd_handle {
     unsigned stats_status_or = 0;   // OR of every status word of the last call
     bool banded_fwd = true;         // VD_DENSE_FWD=1 skips the banded forward sweep (testing)
     bool sparse_bwd = true;         // VD_DENSE_BWD=1 selects the dense backward sweep (testing)
+    int sbwd_min_class = 4;         // VD_SBWD_MIN_CLASS: wave classes below it use the dense backward sweep
     int force_class = -1;           // VD_FORCE_CLASS env: testing hook (1 wave, 2 scalar slab)
+    int small_lo = 0, small_hi = vd::N_SMALL - 1;   // VD_SMALL_MIN / VD_SMALL_MAX: small-kernel classes in use (testing)
+    int use_wsc = 1;                // VD_WSC=0: mid-size superclusters go to the HBM-slab path instead of the warp kernel
     // staged input / output (vd_run)
     struct Stage {                  // one of two staging sets of the host-buffer pipeline
         DevBuf in_ref_off, in_ref_seq, in_rplane, in_var_off, in_var_pos, in_var_rlen, in_var_type,
@@ -99,7 +101,7 @@ extern "C" int vd_create(int device, int64_t scratch_bytes, vd_handle **out) {
         cudaStreamCreateWithFlags(&h->side[c], cudaStreamNonBlocking);
         for (auto &e : h->sev[c]) cudaEventCreate(&e);
     }
-    for (int c = 0; c < N_MCLS; c++) for (auto &e : h->mev[c]) cudaEventCreate(&e);
+    for (auto &g : h->gev) for (auto &e : g) cudaEventCreate(&e);
     cudaMallocHost((void **)&h->h_counters, sizeof(PlanCounters));
     if (scratch_bytes <= 0) {
         size_t fr = 0, tot = 0;
@@ -108,8 +110,12 @@ extern "C" int vd_create(int device, int64_t scratch_bytes, vd_handle **out) {
     }
     h->scratch_budget = scratch_bytes;
     if (const char *fc = getenv("VD_FORCE_CLASS")) h->force_class = atoi(fc);
+    if (const char *v = getenv("VD_SMALL_MIN")) h->small_lo = atoi(v);
+    if (const char *v = getenv("VD_SMALL_MAX")) h->small_hi = atoi(v);
+    if (const char *v = getenv("VD_WSC")) h->use_wsc = atoi(v);
     if (const char *df = getenv("VD_DENSE_FWD")) h->banded_fwd = atoi(df) == 0;
     if (const char *db = getenv("VD_DENSE_BWD")) h->sparse_bwd = atoi(db) == 0;
+    if (const char *sm = getenv("VD_SBWD_MIN_CLASS")) h->sbwd_min_class = atoi(sm);
     if (const char *cs = getenv("VD_CHUNK_SC")) h->chunk_sc = atoll(cs) > 0 ? atoll(cs) : h->chunk_sc;
     cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking);
@@ -117,10 +123,9 @@ extern "C" int vd_create(int device, int64_t scratch_bytes, vd_handle **out) {
         cudaEventCreateWithFlags(&sg.in_done, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&sg.out_done, cudaEventDisableTiming);
     }
-    cudaFuncSetAttribute(tiny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (TINY_TPB / 4) * TINY_SC_BYTES + TINY_TPB * TINY_STRIDE);
+    small_configure();
+    wsc_configure();
     wave_configure();
-    mid_configure();
     *out = h;
     return VD_OK;
 }
@@ -144,7 +149,7 @@ extern "C" void vd_destroy(vd_handle *h) {
     for (DevBuf *b : bufs) b->release();
     if (h->h_counters) cudaFreeHost(h->h_counters);
     for (auto &e : h->ev) if (e) cudaEventDestroy(e);
-    for (int c = 0; c < N_MCLS; c++) for (auto &e : h->mev[c]) if (e) cudaEventDestroy(e);
+    for (auto &g : h->gev) for (auto &e : g) if (e) cudaEventDestroy(e);
     for (int c = 0; c < N_WCLS; c++) {
         for (auto &e : h->sev[c]) if (e) cudaEventDestroy(e);
         if (h->side[c]) cudaStreamDestroy(h->side[c]);
@@ -186,51 +191,49 @@ static int run_resident(vd_handle *h, const BatchDev &in, const OutDev &out, con
     CK(cudaMemsetAsync(h->counters.p, 0, sizeof(PlanCounters), st));
     ScPlan *plan = (ScPlan *)h->plan.p;
     int *list = (int *)h->list.p;
+    int *order = (int *)h->mlist.p;                 // class- and cost-sorted small superclusters
+    PlanCounters *dcnt = (PlanCounters *)h->counters.p;
 
-    plan_kernel<<<(n_sc + 255) / 256, 256, 0, st>>>(in, plan, list, (int *)h->mlist.p, (PlanCounters *)h->counters.p,
-                                                    h->force_class, kBigClass);
-    S.n_launches++;
-    CK(cudaMemcpyAsync(h->h_counters, h->counters.p, sizeof(PlanCounters), cudaMemcpyDeviceToHost, st));
+    plan_kernel<<<(n_sc + 255) / 256, 256, 0, st>>>(in, plan, list, dcnt, h->force_class, kBigClass, h->small_lo, h->small_hi, h->use_wsc);
+    small_base_kernel<<<1, 32, 0, st>>>(dcnt);
+    small_fill_kernel<<<(n_sc + 255) / 256, 256, 0, st>>>(plan, n_sc, dcnt, order);
+    S.n_launches += 3;
+    CK(cudaMemcpyAsync(h->h_counters, dcnt, sizeof(PlanCounters), cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(h->ev[1], st));
-
-    // ---- short superclusters: one fused launch over the whole batch ----
-    {
-        constexpr int SPB = TINY_TPB / 4;
-        const int smem = SPB * TINY_SC_BYTES + TINY_TPB * TINY_STRIDE;
-        tiny_kernel<<<(n_sc + SPB - 1) / SPB, TINY_TPB, smem, st>>>(in, out, plan);
-        S.n_launches++;
-    }
-    CK(cudaEventRecord(h->ev[2], st));
     CK(cudaStreamSynchronize(st));          // counters are now on the host
     CK(cudaGetLastError());
     const PlanCounters pc = *h->h_counters;
+
+    // ---- short superclusters: one fused launch per group, most expensive group first: the warp
+    //      kernel's (slots, shared-memory bin) groups on the side streams (they are latency-bound and
+    //      overlap with each other and with everything else), the thread-per-alignment classes on the
+    //      main stream ----
+    int n_small = 0;
+    bool grp_used[N_GROUP] = {};
+    CK(cudaEventRecord(h->ev[5], st));
+    for (int g = N_GROUP - 1; g >= 0; g--) {
+        const int cnt = pc.grp_count[g];
+        if (cnt <= 0) continue;
+        cudaStream_t gs = g < N_SMALL ? st : h->side[(g - N_SMALL) % N_WCLS];
+        if (gs != st) CK(cudaStreamWaitEvent(gs, h->ev[5], 0));
+        CK(cudaEventRecord(h->gev[g][0], gs));
+        if (g < N_SMALL) small_launch(gs, g, in, out, plan, order + pc.grp_first[g], cnt);
+        else {
+            const int w = g - N_SMALL;                       // (slots - 1) * N_WBIN + (N_WBIN - 1 - bin)
+            wsc_launch(gs, w / N_WBIN + 1, N_WBIN - 1 - w % N_WBIN, in, out, plan, order + pc.grp_first[g], cnt);
+        }
+        CK(cudaEventRecord(h->gev[g][1], gs));
+        grp_used[g] = true;
+        S.n_launches++;
+        n_small += cnt;
+        const int k = g < N_SMALL ? g : N_SMALL;
+        S.n_small[k] += cnt;
+        S.io_small[k] += (int64_t)pc.io_grp[g];
+    }
+    CK(cudaEventRecord(h->ev[2], st));
     S.cells += (int64_t)pc.cells;
     S.n_long += 4 * (int64_t)pc.n_list;
-    S.n_short += 4 * (int64_t)(n_sc - pc.n_list - pc.n_bad);
-
-    // ---- mid-size superclusters: fused shared-memory kernel, one launch per rows-per-lane class,
-    //      on the side streams so that they overlap with the slab path below ----
-    bool mid_used[N_MCLS] = {};
-    {
-        MidBase mb;
-        int n_mid = 0;
-        for (int mc = 0; mc < N_MCLS; mc++) { mb.b[mc] = n_mid; n_mid += pc.n_mid[mc]; }
-        if (n_mid > 0) {
-            mid_fill_kernel<<<(n_sc + 255) / 256, 256, 0, st>>>(plan, n_sc, (PlanCounters *)h->counters.p, mb, (int *)h->mlist.p);
-            S.n_launches++;
-            CK(cudaEventRecord(h->ev[5], st));
-            for (int mc = 0; mc < N_MCLS; mc++) {
-                if (!pc.n_mid[mc]) continue;
-                cudaStream_t ss = h->side[mc % N_WCLS];
-                CK(cudaStreamWaitEvent(ss, h->ev[5], 0));
-                CK(cudaEventRecord(h->mev[mc][0], ss));
-                mid_launch(ss, mc / N_MBIN, pc.n_mid[mc], mid_bin_cap(mc % N_MBIN), in, out, plan, (const int *)h->mlist.p + mb.b[mc]);
-                CK(cudaEventRecord(h->mev[mc][1], ss));
-                S.n_launches++;
-                mid_used[mc] = true;
-            }
-        }
-    }
+    S.n_short += 4 * (int64_t)n_small;
 
     // ---- the rest: HBM slab, wavefront / scalar kernels ----
     float ms_fwd = 0, ms_bwd = 0, ms_walk = 0;
@@ -300,7 +303,7 @@ static int run_resident(vd_handle *h, const BatchDev &in, const OutDev &out, con
                     CK(cudaEventRecord(h->sev[c][0], ss));
                     wave_launch(ss, WA, c, cb.b[c], hwi.count[c], true, true, h->banded_fwd ? (int *)h->need_dense.p : nullptr);
                     CK(cudaEventRecord(h->sev[c][1], ss));
-                    wave_launch(ss, WA, c, cb.b[c], hwi.count[c], false, h->sparse_bwd);
+                    wave_launch(ss, WA, c, cb.b[c], hwi.count[c], false, h->sparse_bwd && c >= h->sbwd_min_class);
                     CK(cudaEventRecord(h->sev[c][2], ss));
                     CK(cudaStreamWaitEvent(st, h->sev[c][2], 0));
                     S.n_launches += 2;
@@ -331,7 +334,7 @@ static int run_resident(vd_handle *h, const BatchDev &in, const OutDev &out, con
             i0 = i1;
         }
     }
-    for (int kc = 0; kc < N_MCLS; kc++) if (mid_used[kc]) CK(cudaStreamWaitEvent(st, h->mev[kc][1], 0));
+    for (int g = N_SMALL; g < N_GROUP; g++) if (grp_used[g]) CK(cudaStreamWaitEvent(st, h->gev[g][1], 0));
     status_or_kernel<<<296, 256, 0, st>>>(out.status, 4 * (int64_t)n_sc, &((PlanCounters *)h->counters.p)->status_or);
     S.n_launches++;
     CK(cudaMemcpyAsync(h->h_counters, h->counters.p, sizeof(PlanCounters), cudaMemcpyDeviceToHost, st));
@@ -344,8 +347,11 @@ static int run_resident(vd_handle *h, const BatchDev &in, const OutDev &out, con
     cudaEventElapsedTime(&e_, h->ev[1], h->ev[2]); S.ms_short += e_;
     cudaEventElapsedTime(&e_, h->ev[0], h->ev[3]); S.ms_total += e_;
     S.ms_long_fwd += ms_fwd; S.ms_long_bwd += ms_bwd; S.ms_long_walk += ms_walk;
-    for (int kc = 0; kc < N_MCLS; kc++)
-        if (mid_used[kc]) { cudaEventElapsedTime(&e_, h->mev[kc][0], h->mev[kc][1]); S.ms_mid += e_; }
+    for (int g = 0; g < N_GROUP; g++) {       // per-group durations of the short kernels (the warp kernel's overlap)
+        if (!grp_used[g]) continue;
+        cudaEventElapsedTime(&e_, h->gev[g][0], h->gev[g][1]);
+        S.ms_small[g < N_SMALL ? g : N_SMALL] += e_;
+    }
     if (pc.n_bad > 0) return fail(h, VD_E_BADINPUT, "%d malformed superclusters", pc.n_bad);
     return VD_OK;
 }

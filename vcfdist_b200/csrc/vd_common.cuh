@@ -22,6 +22,7 @@ constexpr int F_K_SHIFT = 5;   // bits 5-7: index of the chosen source in the ro
 constexpr int P_VARIANT = 1, P_VAR_BEG = 2, P_VAR_END = 4, P_INS_LOC = 8;
 
 constexpr int INF = 1 << 29;
+constexpr int NEG = -(1 << 28);
 
 // device view of vd_batch_in (all pointers in HBM)
 struct BatchDev {
@@ -53,7 +54,9 @@ struct OutDev {
 };
 
 // classes decided by the plan kernel
-enum : int { CLS_TINY = 0, CLS_WAVE = 1, CLS_SCALAR = 2, CLS_BAD = 3, CLS_MID = 4 };
+// CLS_TINY: one of the fused shared-memory kernels (small_kernel<K>); bits 8.. of ScPlan::cls then
+// hold its (class, cost bin) slot
+enum : int { CLS_TINY = 0, CLS_WAVE = 1, CLS_SCALAR = 2, CLS_BAD = 3 };
 
 // per-supercluster plan record
 struct ScPlan {

@@ -1,36 +1,62 @@
 // Kernels of the precision/recall path (sm_100a):
 //   plan_kernel        sizes + class of every supercluster, work list of the non-tiny ones
-//   tiny_kernel        fused: one thread per alignment, one quad per supercluster, all
-//                      matrices in shared memory (the 93 % class of SURVEY.md 8d)
+//   small_kernel<K>    fused: one thread per alignment, one quad per supercluster, all
+//                      matrices in shared memory; three footprint classes, cost-sorted order
 //   slab_size_kernel / slab_setup_kernel / slab_align_kernel
 //                      thread-per-alignment path with matrices in an HBM slab
 // The wavefront kernels for long superclusters are in vd_wave.cuh.
 #pragma once
 #include "vd_scalar.cuh"
-#include "vd_midlayout.cuh"
+#include "vd_warp.cuh"
 
 namespace vd {
 
-// ---- tiny-class limits --------------------------------------------------------------------
-constexpr int TINY_TPB = 128;          // threads per block = 32 superclusters
-constexpr int TINY_TL = 16;            // max haplotype length
-constexpr int TINY_TR = 12;            // max window (REF plane) length
-constexpr int TINY_CAP = 320;          // private shared-memory bytes per alignment
-constexpr int TINY_STRIDE = TINY_CAP + 4;   // private slice stride: odd number of words -> conflict-free
-static_assert(((TINY_STRIDE / 4) & 1) == 1, "private slice stride must be an odd number of words");
-constexpr int TINY_SW = (TINY_TL + TINY_TR + 1 + 3) & ~3;      // one CSR swap table
-constexpr int TINY_SC_BYTES = 4 * (3 * TINY_TL + TINY_TR) + 2 * (2 * TINY_TR + 2 * TINY_SW) + TINY_TR + 8;   // per-supercluster shared area
+// ---- small-supercluster classes -----------------------------------------------------------
+// One thread per alignment, one quad per supercluster, every matrix in shared memory.  The class
+// fixes the static sizes of the per-supercluster shared area (haplotype strings / pointer maps,
+// TL = max haplotype length, TR = max window length) and of the per-alignment private slice
+// (CAP bytes).  Small classes have small footprints, so most of the batch (91 % of a WGS
+// small-variant batch fits class 0) runs at high occupancy; bigger classes trade occupancy for
+// keeping the alignment on chip.  Whatever fits none goes to the HBM-slab wavefront path.
+constexpr int N_SMALL = 2;
+constexpr int N_SBIN = 8;              // cost bins per class (log2 of the supercluster's cells)
+#ifndef VD_MINB0
+#define VD_MINB0 8
+#endif
+template <int K> struct SmallCfg;      // MINB: resident blocks per SM the register allocation must allow
+template <> struct SmallCfg<0> { static constexpr int TL = 8,  TR = 8,  CAP = 128,  TPB = 128, SHIFT = 3, MINB = VD_MINB0; };
+template <> struct SmallCfg<1> { static constexpr int TL = 16, TR = 20, CAP = 320,  TPB = 128, SHIFT = 5, MINB = 4; };
 
-constexpr u32 ST_BAD = 0x0800u;        // VD_ST_ERR_BADINPUT
+__host__ __device__ inline int small_tl(int k) { const int v[N_SMALL] = {SmallCfg<0>::TL, SmallCfg<1>::TL}; return v[k]; }
+__host__ __device__ inline int small_tr(int k) { const int v[N_SMALL] = {SmallCfg<0>::TR, SmallCfg<1>::TR}; return v[k]; }
+__host__ __device__ inline int small_cap(int k) { const int v[N_SMALL] = {SmallCfg<0>::CAP, SmallCfg<1>::CAP}; return v[k]; }
+__host__ __device__ inline int small_shift(int k) { const int v[N_SMALL] = {SmallCfg<0>::SHIFT, SmallCfg<1>::SHIFT}; return v[k]; }
+
+// keys of the order array: (small class, cost bin) first, then the warp kernel's (slots, smem bin);
+// launch groups: one per small class, one per (slots, smem bin)
+constexpr int N_KEY = N_SMALL * N_SBIN + WSC_MAXSLOT * N_WBIN;
+constexpr int N_GROUP = N_SMALL + WSC_MAXSLOT * N_WBIN;
+__host__ __device__ inline int group_of_key(int key) { return key < N_SMALL * N_SBIN ? key / N_SBIN : N_SMALL + (key - N_SMALL * N_SBIN); }
+
+template <int TL, int TR> struct SmallDims {
+    static constexpr int SW = (TL + TR + 1 + 3) & ~3;                 // one CSR swap table
+    static constexpr int HAP = 3 * TL + TR;                           // str TL | flg TL | ptr TL | ins TR
+    static constexpr int QM = 2 * TR + 2 * SW;                        // rptr TR | rflg TR | toQ SW | toR SW
+    static constexpr int SC_BYTES = 4 * HAP + 2 * QM + TR + 8;        // ... | rseq TR | hlen 4 x int16
+    static_assert((TR % 4) == 0 && (TL % 4) == 0 && (SC_BYTES % 4) == 0, "alignment of the shared area");
+};
 
 struct PlanCounters {
-    int n_list;                        // superclusters not handled by tiny_kernel
+    int n_list;                        // superclusters not handled by the small kernels
     int n_bad;
     unsigned long long cells;
     unsigned long long cells_list;
     unsigned status_or;
-    int n_mid[N_MCLS];                 // superclusters of the fused mid-size kernel, per (K, smem bin) class
-    int mid_cursor[N_MCLS];
+    int n_key[N_KEY];                  // superclusters per key
+    int cursor[N_KEY];
+    int base[N_KEY];                   // first slot of each key in the order array
+    int grp_first[N_GROUP], grp_count[N_GROUP];
+    unsigned long long io_grp[N_GROUP];     // algorithmic input+output bytes per launch group
 };
 
 // OR of all status words (so that the host only scans them when an error bit is set)
@@ -41,12 +67,14 @@ __global__ void status_or_kernel(const u32 *status, int64_t n, unsigned *dst) {
     if ((threadIdx.x & 31) == 0 && v) atomicOr(dst, v);
 }
 
-__device__ __forceinline__ int tiny_need(int Lq, int Lr, int Lt) {
+__device__ __forceinline__ int small_need(int Lq, int Lr, int Lt) {
     return make_layout<int, 2, true>(Lq + Lr, Lt, Lr).total;
 }
 
-// One thread per supercluster.
-__global__ void plan_kernel(BatchDev in, ScPlan *plan, int *list, int *mlist, PlanCounters *cnt, int force_class, int big_class) {
+// One thread per supercluster.  small_lo / small_hi: range of small classes in use (testing hooks
+// VD_SMALL_MIN / VD_SMALL_MAX; hi < lo disables the small kernels).
+__global__ void plan_kernel(BatchDev in, ScPlan *plan, int *list, PlanCounters *cnt, int force_class, int big_class,
+                            int small_lo, int small_hi, int use_wsc) {
     const int sc0 = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = sc0 < in.n_sc;
     const int sc = live ? sc0 : in.n_sc - 1;      // dead lanes recompute the last one and discard it
@@ -54,6 +82,7 @@ __global__ void plan_kernel(BatchDev in, ScPlan *plan, int *list, int *mlist, Pl
     const int lr = (int)(in.ref_off[sc + 1] - in.ref_off[sc]);
     p.lr = lr;
     bool bad = lr < 1;
+    int maxlen = 0;
     for (int h = 0; h < 4; h++) {
         int len = lr, prev_end = 0;
         for (int64_t v = in.var_off[4 * (int64_t)sc + h]; v < in.var_off[4 * (int64_t)sc + h + 1]; v++) {
@@ -64,36 +93,44 @@ __global__ void plan_kernel(BatchDev in, ScPlan *plan, int *list, int *mlist, Pl
             prev_end = pos + rl;
         }
         p.len[h] = len;
+        maxlen = max(maxlen, len);
         if (len < 1) bad = true;
     }
     unsigned long long cells = 0;
-    int cls = CLS_SCALAR;
+    int cls = big_class;
+    int sbin = -1;                                 // (class, cost bin) of the small kernels
     if (bad) cls = CLS_BAD;
     else {
-        bool tiny = lr <= TINY_TR;
-        for (int h = 0; h < 4; h++) tiny = tiny && p.len[h] <= TINY_TL;
+        int need = 0;
         for (int ai = 0; ai < 4; ai++) {
             const int lq = p.len[ai >> 1], lt = p.len[2 + (ai & 1)];
             cells += (unsigned long long)(lq + lr) * lt;
-            if (tiny) tiny = tiny_need(lq, lr, lt) <= TINY_CAP;
+            if (maxlen <= SmallCfg<N_SMALL - 1>::TL && lr <= SmallCfg<N_SMALL - 1>::TR) need = max(need, small_need(lq, lr, lt));
+            else need = 1 << 30;
         }
-        if (tiny && force_class < 0) cls = CLS_TINY;
+        if (force_class > CLS_TINY) cls = force_class;
         else {
-            const int kc = mid_kclass(p);
-            const int need = kc >= 0 ? mid_layout(p, 1 << kc).total : (1 << 30);
-            if (force_class == CLS_MID && need <= MID_SMEM_MAX) {      // measured slower than the slab path: opt-in only
-                const int mc = kc * N_MBIN + mid_bin(need);
-                cls = CLS_MID | (mc << 8);              // the class id rides in the upper bits
-                if (live) atomicAdd(&cnt->n_mid[mc], 1);
-            } else cls = (force_class > CLS_TINY && force_class != CLS_MID) ? force_class : big_class;
+            for (int k = max(small_lo, 0); k <= small_hi && k < N_SMALL; k++) {
+                if (maxlen <= small_tl(k) && lr <= small_tr(k) && need <= small_cap(k)) {
+                    cls = CLS_TINY;
+                    const int lg = 31 - __clz((int)cells | 1);
+                    // bins are laid out most expensive first (the tail of a launch is its cheap work)
+                    sbin = k * N_SBIN + (N_SBIN - 1 - min(max(lg - small_shift(k), 0), N_SBIN - 1));
+                    break;
+                }
+            }
+            if (sbin < 0 && use_wsc) {             // warp-per-supercluster kernel: four flag matrices in shared memory
+                const int ws = wsc_slots(p);
+                const int wb = ws > 0 ? wsc_bin(wsc_layout(p).total) : -1;
+                if (wb >= 0) { cls = CLS_TINY; sbin = N_SMALL * N_SBIN + (ws - 1) * N_WBIN + (N_WBIN - 1 - wb); }
+            }
         }
     }
-    p.cls = cls;
+    p.cls = cls | (sbin >= 0 ? (sbin << 8) : 0);
     if (live) plan[sc] = p;
     // warp-aggregated counters: one atomic per warp and counter instead of one per thread
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    (void)mlist;
     const bool is_bad = live && cls == CLS_BAD, is_list = live && (cls == CLS_WAVE || cls == CLS_SCALAR);
     unsigned long long c_all = live ? cells : 0ull, c_list = is_list ? cells : 0ull;
 #pragma unroll
@@ -110,47 +147,94 @@ __global__ void plan_kernel(BatchDev in, ScPlan *plan, int *list, int *mlist, Pl
     }
     base = __shfl_sync(full, base, 0);
     if (is_list) list[base + __popc(m_list & ((1u << lane) - 1))] = sc;
+    // per-bin counts of the small classes: one atomic per distinct bin in the warp
+    const int key = (live && sbin >= 0) ? sbin : -1;
+    const unsigned peers = __match_any_sync(full, key);
+    if (key >= 0 && lane == __ffs(peers) - 1) atomicAdd(&cnt->n_key[key], __popc(peers));
+    {   // algorithmic bytes of each launch group's superclusters (io_bytes_of in vd_api.cu): one atomic per
+        // distinct group in the warp
+        const int grp = key >= 0 ? group_of_key(key) : -1;
+        unsigned long long io = 0;
+        if (grp >= 0) {
+            const int64_t v0 = in.var_off[4 * (int64_t)sc], v1 = in.var_off[4 * (int64_t)sc + 4];
+            const int64_t nv = v1 - v0;
+            io = (unsigned long long)(lr + 8 + 32 + nv * (4 + 4 + 1 + 4 + 8) + (in.alt_off[v1] - in.alt_off[v0])
+                                      + 4 * (4 + 1 + 1 + 4) + 2 * nv * 17);
+        }
+        const unsigned gp = __match_any_sync(full, grp);
+        const int gl = __ffs(gp) - 1;
+        unsigned long long tot = 0;
+        for (unsigned m = gp; m; m &= m - 1) tot += __shfl_sync(gp, io, __ffs(m) - 1);
+        if (grp >= 0 && lane == gl) atomicAdd(&cnt->io_grp[grp], tot);
+    }
 }
 
-// class-sorted work list of the fused mid-size kernel
-struct MidBase { int b[N_MCLS]; };
-__global__ void mid_fill_kernel(const ScPlan *plan, int n_sc, PlanCounters *cnt, MidBase mb, int *mlist) {
+// exclusive scan of the per-key counts -> slots of the order array; per-group ranges
+__global__ void small_base_kernel(PlanCounters *cnt) {
+    if (threadIdx.x != 0) return;
+    int o = 0;
+    for (int g = 0; g < N_GROUP; g++) cnt->grp_count[g] = 0;
+    for (int key = 0; key < N_KEY; key++) {
+        const int g = group_of_key(key);
+        if (cnt->grp_count[g] == 0) cnt->grp_first[g] = o;
+        cnt->base[key] = o;
+        o += cnt->n_key[key];
+        cnt->grp_count[g] += cnt->n_key[key];
+    }
+}
+
+// class- and cost-sorted order of the small superclusters
+__global__ void small_fill_kernel(const ScPlan *plan, int n_sc, PlanCounters *cnt, int *order) {
     const int sc = blockIdx.x * blockDim.x + threadIdx.x;
-    if (sc >= n_sc) return;
-    const int cls = plan[sc].cls;
-    if ((cls & 0xff) != CLS_MID) return;
-    const int mc = cls >> 8;
-    mlist[mb.b[mc] + atomicAdd(&cnt->mid_cursor[mc], 1)] = sc;
+    const int cls = sc < n_sc ? plan[sc].cls : CLS_BAD;
+    const int key = (cls & 0xff) == CLS_TINY ? (cls >> 8) : -1;
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    if (key < 0) return;
+    const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+    int slot = 0;
+    if (lane == leader) slot = cnt->base[key] + atomicAdd(&cnt->cursor[key], __popc(peers));
+    slot = __shfl_sync(peers, slot, leader);
+    order[slot + __popc(peers & ((1u << lane) - 1))] = sc;
 }
 
-// ---- fused tiny kernel --------------------------------------------------------------------
+// ---- fused small kernel ---------------------------------------------------------------------
 // per-supercluster shared area (bytes): 4 x hap {str TL, flg TL, ptr TL, ins TR},
 // 2 x qmaps {rptr TR, rflg TR, toQ SW, toR SW}, rseq TR, hlen 4 x int16
-struct TinyArea {
+template <int TL, int TR> struct SmallArea {
+    typedef SmallDims<TL, TR> D;
     u8 *base;
-    __device__ u8 *str(int h) const { return base + h * (3 * TINY_TL + TINY_TR); }
-    __device__ u8 *flg(int h) const { return str(h) + TINY_TL; }
-    __device__ int8_t *ptr(int h) const { return (int8_t *)(str(h) + 2 * TINY_TL); }
-    __device__ u8 *ins(int h) const { return str(h) + 3 * TINY_TL; }
-    __device__ u8 *qm(int qh) const { return base + 4 * (3 * TINY_TL + TINY_TR) + qh * (2 * TINY_TR + 2 * TINY_SW); }
+    __device__ u8 *str(int h) const { return base + h * D::HAP; }
+    __device__ u8 *flg(int h) const { return str(h) + TL; }
+    __device__ int8_t *ptr(int h) const { return (int8_t *)(str(h) + 2 * TL); }
+    __device__ u8 *ins(int h) const { return str(h) + 3 * TL; }
+    __device__ u8 *qm(int qh) const { return base + 4 * D::HAP + qh * D::QM; }
     __device__ int8_t *rptr(int qh) const { return (int8_t *)qm(qh); }
-    __device__ u8 *rflg(int qh) const { return qm(qh) + TINY_TR; }
-    __device__ int8_t *toQ(int qh) const { return (int8_t *)(qm(qh) + 2 * TINY_TR); }
-    __device__ int8_t *toR(int qh) const { return (int8_t *)(qm(qh) + 2 * TINY_TR + TINY_SW); }
-    __device__ u8 *rseq() const { return base + 4 * (3 * TINY_TL + TINY_TR) + 2 * (2 * TINY_TR + 2 * TINY_SW); }
-    __device__ short *hlen() const { return (short *)(rseq() + TINY_TR); }
+    __device__ u8 *rflg(int qh) const { return qm(qh) + TR; }
+    __device__ int8_t *toQ(int qh) const { return (int8_t *)(qm(qh) + 2 * TR); }
+    __device__ int8_t *toR(int qh) const { return (int8_t *)(qm(qh) + 2 * TR + D::SW); }
+    __device__ u8 *rseq() const { return base + 4 * D::HAP + 2 * D::QM; }
+    __device__ short *hlen() const { return (short *)(rseq() + TR); }
 };
-static_assert((TINY_TR % 2) == 0 && (TINY_SC_BYTES % 4) == 0, "alignment of the tiny shared area");
 
-__global__ void __launch_bounds__(TINY_TPB)
-tiny_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan) {
+template <int K> struct SmallMem {
+    static constexpr int STRIDE = SmallCfg<K>::CAP + 4;               // odd number of words -> conflict-free
+    static constexpr int SMEM = (SmallCfg<K>::TPB / 4) * SmallDims<SmallCfg<K>::TL, SmallCfg<K>::TR>::SC_BYTES + SmallCfg<K>::TPB * STRIDE;
+    static_assert(((STRIDE / 4) & 1) == 1, "private slice stride must be an odd number of words");
+};
+
+template <int K>
+__global__ void __launch_bounds__(SmallCfg<K>::TPB, SmallCfg<K>::MINB)
+small_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, const int *__restrict__ order, int count) {
+    typedef SmallCfg<K> C;
+    typedef SmallDims<C::TL, C::TR> D;
     extern __shared__ __align__(16) u8 smem[];
-    constexpr int SPB = TINY_TPB / 4;
+    constexpr int SPB = C::TPB / 4;
     const int tid = threadIdx.x, quad = tid >> 2, h = tid & 3;
-    const int sc = blockIdx.x * SPB + quad;
-    const bool active = sc < in.n_sc && plan[sc].cls == CLS_TINY;
-    TinyArea A{smem + quad * TINY_SC_BYTES};
-    SMemIL mem{smem + SPB * TINY_SC_BYTES + tid * TINY_STRIDE};
+    const int slot = blockIdx.x * SPB + quad;
+    const bool active = slot < count;
+    const int sc = active ? order[slot] : 0;
+    SmallArea<C::TL, C::TR> A{smem + quad * D::SC_BYTES};
+    SMemIL mem{smem + SPB * D::SC_BYTES + tid * SmallMem<K>::STRIDE};
 
     int lr = 0;
     if (active) {
@@ -159,7 +243,7 @@ tiny_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan) {
         const bool isq = h < 2;
         const int len = expand_hap<int8_t>(in, sc, h, A.str(h), A.flg(h), A.ptr(h),
                                            isq ? A.rptr(h) : nullptr, isq ? A.rflg(h) : nullptr,
-                                           A.ins(h), TINY_TL);
+                                           A.ins(h), C::TL);
         bool ok = len == plan[sc].len[h];
         if (ok && isq) {
             ok = build_swsrc<int8_t>(A.ptr(h), A.flg(h), len, A.toR(h), lr) &&
@@ -197,6 +281,24 @@ tiny_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan) {
     out.aln_end_plane[4 * (int64_t)sc + ai] = (u8)end_plane;
     out.aln_beg_plane[4 * (int64_t)sc + ai] = (u8)beg_plane;
     out.status[4 * (int64_t)sc + ai] = status;
+}
+
+template <int K> inline void small_configure_one() {
+    cudaFuncSetAttribute(small_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmallMem<K>::SMEM);
+}
+inline void small_configure() { small_configure_one<0>(); small_configure_one<1>(); }
+template <int K> inline void small_launch_one(cudaStream_t st, const BatchDev &in, const OutDev &out, const ScPlan *plan,
+                                              const int *order, int count) {
+    constexpr int SPB = SmallCfg<K>::TPB / 4;
+    small_kernel<K><<<(count + SPB - 1) / SPB, SmallCfg<K>::TPB, SmallMem<K>::SMEM, st>>>(in, out, plan, order, count);
+}
+inline void small_launch(cudaStream_t st, int k, const BatchDev &in, const OutDev &out, const ScPlan *plan,
+                         const int *order, int count) {
+    if (count <= 0) return;
+    switch (k) {
+        case 0: small_launch_one<0>(st, in, out, plan, order, count); break;
+        case 1: small_launch_one<1>(st, in, out, plan, order, count); break;
+    }
 }
 
 // ---- HBM-slab path ---------------------------------------------------------------------------

@@ -1,0 +1,422 @@
+// Warp-per-supercluster kernel for mid-size superclusters: too big for the thread-per-alignment
+// classes of small_kernel, small enough that all four alignments' flag matrices fit in shared
+// memory (up to 128 rows over both planes).  Everything stays on chip, as in small_kernel; HBM traffic
+// is the compact batch in and the result records out.
+//
+//   phase 1  lanes 0..3 expand the four haplotypes (generate_ptrs_strs, src/dist.cpp:145-242)
+//            and build the swap-source tables; the other lanes stage the REF-plane string
+//   phase 2  the four alignments one after the other, lanes across rows (row r lives on lane
+//            r % 32, register slot r / 32; both planes back to back, QUERY rows first):
+//            forward column sweep (calc_prec_recall_aln, :251-443) with the previous column in
+//            registers — neighbour and swap-source reads are warp shuffles, the insertion chain
+//            is a plane-segmented min-plus prefix scan; one flag byte per cell to shared memory;
+//            backward sweep (calc_prec_recall_path, :486-834) in gather form, the in-column
+//            insertion chain as a link-segmented suffix max of T - S (S = suffix count of
+//            query-variant rows, which turns the weighted chain into a plain max); the path
+//            flags overwrite the forward flags in place
+//   phase 3  lanes 0..3 walk their alignment and assign credit (walk_credit of vd_scalar.cuh)
+#pragma once
+#include "vd_scalar.cuh"
+
+namespace vd {
+
+constexpr u32 ST_BAD = 0x0800u;        // VD_ST_ERR_BADINPUT
+constexpr int WSC_TPB = 128;           // 4 warps = 4 superclusters per block
+constexpr int WSC_MAXSLOT = 4;         // register slots of 32 rows: both planes of one alignment have <= 128 rows
+constexpr int WSC_MAXLEN = 120;        // haplotype / window length (int8 pointers and CSR offsets)
+constexpr int N_WBIN = 5;              // shared-memory bins: bytes per supercluster
+__host__ __device__ inline int wsc_bin_cap(int b) { const int v[N_WBIN] = {2560, 5120, 10240, 24576, 57344}; return v[b]; }
+
+__host__ __device__ inline int wa4(int x) { return (x + 3) & ~3; }
+
+struct WscLayout {
+    int hap[4];      // str L | flg L | ptr L (int8) | ins Lr
+    int qm[2];       // rptr Lr | rflg Lr | toQ (Lq+1+Lr) | toR (Lr+1+Lq)
+    int rseq;
+    int F[4];        // flag matrix [Lt][N]
+    int walk[4];     // path (int16 q, int16 t, u8 flags) + Levenshtein row
+    int total;
+};
+__host__ __device__ inline WscLayout wsc_layout(const ScPlan &p) {
+    WscLayout m;
+    int o = 0;
+    const int Lr = p.lr;
+    for (int h = 0; h < 4; h++) { m.hap[h] = o; o += wa4(3 * p.len[h] + Lr); }
+    for (int k = 0; k < 2; k++) { m.qm[k] = o; o += wa4(2 * Lr + 2 * (p.len[k] + Lr + 1)); }
+    m.rseq = o; o += wa4(Lr);
+    for (int ai = 0; ai < 4; ai++) {
+        const int N = p.len[ai >> 1] + Lr, Lt = p.len[2 + (ai & 1)];
+        m.F[ai] = o; o += wa4(N * Lt);
+        m.walk[ai] = o;
+        const int np = N + Lt + 4, mn = (Lr < Lt ? Lr : Lt) + 1;
+        o += 2 * wa4(2 * np) + wa4(np) + wa4(2 * mn);
+    }
+    m.total = o;
+    return m;
+}
+// register slots (32 rows each) the supercluster needs, 0 if it does not fit this kernel
+__host__ __device__ inline int wsc_slots(const ScPlan &p) {
+    int maxlen = p.lr;
+    for (int h = 0; h < 4; h++) maxlen = p.len[h] > maxlen ? p.len[h] : maxlen;
+    if (maxlen > WSC_MAXLEN) return 0;
+    const int N = (p.len[0] > p.len[1] ? p.len[0] : p.len[1]) + p.lr;
+    if (N > 32 * WSC_MAXSLOT) return 0;
+    return (N + 31) / 32;
+}
+__host__ __device__ inline int wsc_bin(int need) { for (int b = 0; b < N_WBIN; b++) if (need <= wsc_bin_cap(b)) return b; return -1; }
+
+struct PFWarp {      // path flags, [column][row], QUERY rows first
+    const u8 *F; int N, Lq;
+    __device__ __forceinline__ int get(int hi, int qri, int ti) const { return F[ti * N + (hi ? Lq + qri : qri)]; }
+};
+
+template <int S>
+__global__ void __launch_bounds__(WSC_TPB)
+wsc_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, const int *__restrict__ order, int count, int warp_bytes) {
+    extern __shared__ __align__(16) u8 smem[];
+    constexpr unsigned FULL = 0xffffffffu;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slot = blockIdx.x * (WSC_TPB / 32) + warp;
+    if (slot >= count) return;                      // warps are independent: no block-wide barrier anywhere
+    const int sc = order[slot];
+    const ScPlan p = plan[sc];
+    const WscLayout M = wsc_layout(p);
+    u8 *base = smem + warp * warp_bytes;
+    const int Lr = p.lr;
+    auto hstr = [&](int h) { return base + M.hap[h]; };
+    auto hflg = [&](int h) { return base + M.hap[h] + p.len[h]; };
+    auto hptr = [&](int h) { return (int8_t *)(base + M.hap[h] + 2 * p.len[h]); };
+    auto hins = [&](int h) { return base + M.hap[h] + 3 * p.len[h]; };
+    auto qrptr = [&](int k) { return (int8_t *)(base + M.qm[k]); };
+    auto qrflg = [&](int k) { return base + M.qm[k] + Lr; };
+    auto qtoQ = [&](int k) { return (int8_t *)(base + M.qm[k] + 2 * Lr); };
+    auto qtoR = [&](int k) { return (int8_t *)(base + M.qm[k] + 2 * Lr + (p.len[k] + 1 + Lr)); };
+    u8 *rseq = base + M.rseq;
+
+    // ---- phase 1: expansion ----
+    bool ok = true;
+    if (lane < 4) {
+        const int h = lane;
+        const bool isq = h < 2;
+        const int len = expand_hap<int8_t>(in, sc, h, hstr(h), hflg(h), hptr(h), isq ? qrptr(h) : nullptr,
+                                           isq ? qrflg(h) : nullptr, hins(h), p.len[h]);
+        ok = len == p.len[h];
+        if (ok && isq) ok = build_swsrc<int8_t>(hptr(h), hflg(h), len, qtoR(h), Lr) &&
+                            build_swsrc<int8_t>(qrptr(h), qrflg(h), Lr, qtoQ(h), len);
+    } else {
+        const u8 *rs = in.rplane_seq + in.ref_off[sc];
+        for (int k = lane - 4; k < Lr; k += 28) rseq[k] = rs[k];
+    }
+    if (__ballot_sync(FULL, ok) != FULL) {
+        if (lane < 4) { out.status[4 * (int64_t)sc + lane] = ST_BAD; out.aln_score[4 * (int64_t)sc + lane] = -1; }
+        return;
+    }
+    __syncwarp();
+
+    // values of an arbitrary row g / the row above / the row below, from per-slot register arrays
+    auto row_get = [&](const int (&X)[S], int g) -> int {
+        int v = __shfl_sync(FULL, X[0], g & 31);
+#pragma unroll
+        for (int s = 1; s < S; s++) { const int v1 = __shfl_sync(FULL, X[s], g & 31); if ((g >> 5) == s) v = v1; }
+        return v;
+    };
+    auto above = [&](const int (&X)[S], int s) -> int {
+        int u = __shfl_up_sync(FULL, X[s], 1);
+        if (S > 1 && s > 0) { const int w = __shfl_sync(FULL, X[s - 1], 31); if (lane == 0) u = w; }
+        return u;
+    };
+    auto below = [&](const int (&X)[S], int s) -> int {
+        int u = __shfl_down_sync(FULL, X[s], 1);
+        if (S > 1 && s < S - 1) { const int w = __shfl_sync(FULL, X[s + 1], 0); if (lane == 31) u = w; }
+        return u;
+    };
+
+    int my_score = 0, my_end = 0, my_beg = 0;
+    u32 my_status = 0;
+
+    // ---- phase 2: the four alignments ----
+    for (int ai = 0; ai < 4; ai++) {
+        const int qh = ai >> 1, th = 2 + (ai & 1);
+        const int Lq = p.len[qh], Lt = p.len[th], N = Lq + Lr;
+        const u8 *qstr = hstr(qh), *qflg = hflg(qh), *tstr = hstr(th), *tflg = hflg(th);
+        const int8_t *qptr = hptr(qh), *rptr = qrptr(qh), *toQ = qtoQ(qh), *toR = qtoR(qh);
+        const u8 *rflg = qrflg(qh);
+        u8 *F = base + M.F[ai];
+
+        // static per-row data
+        bool inrow[S], P[S], below_ok[S];
+        int a[S], ch[S], chn[S], swi[S], si[S], tpn[S], Ssum[S];
+        int maxcnt = 0;
+        int tpself[S];
+#pragma unroll
+        for (int s = 0; s < S; s++) {
+            const int r = 32 * s + lane;
+            inrow[s] = r < N;
+            P[s] = r >= Lq;
+            a[s] = P[s] ? r - Lq : r;
+            const int len = P[s] ? Lr : Lq;
+            const u8 *seq = P[s] ? rseq : qstr;
+            ch[s] = inrow[s] ? seq[a[s]] : 0x100;
+            below_ok[s] = inrow[s] && a[s] + 1 < len;
+            chn[s] = below_ok[s] ? seq[a[s] + 1] : 0x100;
+            swi[s] = 0; si[s] = 0; tpself[s] = 0;
+            if (inrow[s]) {
+                // my row as a swap DESTINATION: first source (row index over both planes) | count << 16
+                const int8_t *tab = P[s] ? toR : toQ;
+                const int k0 = tab[a[s]], k1 = tab[a[s] + 1];
+                if (k1 > k0) swi[s] = ((P[s] ? 0 : Lq) + (int)tab[len + 1 + k0]) | ((k1 - k0) << 16);
+                // my row as a swap SOURCE: valid | k << 1 | tp(dest) << 4 | dest row << 8   (:598-679)
+                const int f = P[s] ? rflg[a[s]] : qflg[a[s]];
+                const int d = (int)(P[s] ? rptr[a[s]] : qptr[a[s]]) + 1;      // plane-local row on the other plane
+                const int ndst = P[s] ? Lq : Lr;
+                if ((!(f & P_VARIANT) || (f & P_VAR_END)) && d > 0 && d < ndst) {
+                    const int df = P[s] ? qflg[d] : rflg[d];
+                    if (!(df & P_VARIANT) || (df & P_VAR_BEG)) {
+                        const int8_t *dtab = P[s] ? toQ : toR;               // CSR of the destination plane
+                        const int8_t *dsrc = dtab + ndst + 1;
+                        int k = 0;
+                        for (int j = dtab[d]; j < dtab[d + 1]; j++) if ((int)dsrc[j] == a[s]) k = j - dtab[d];
+                        int tp = 0;
+                        if (P[s]) tp = ((int)qptr[d] != (int)qptr[d - 1] + 1) || (df & P_VAR_BEG);      // dest on QUERY (:656-658)
+                        si[s] = 1 | (k << 1) | (tp << 4) | (((P[s] ? 0 : Lq) + d) << 8);
+                    }
+                }
+                if (!P[s] && a[s] > 0) tpself[s] = ((int)qptr[a[s]] != (int)qptr[a[s] - 1] + 1) || (qflg[a[s]] & P_VAR_BEG);   // :572-574
+            }
+            maxcnt = max(maxcnt, swi[s] >> 16);
+        }
+        maxcnt = __reduce_max_sync(FULL, maxcnt);
+        {   // tp of the row below, and S = number of tp rows below mine in my plane
+            unsigned tm[S];
+#pragma unroll
+            for (int s = 0; s < S; s++) tm[s] = __ballot_sync(FULL, tpself[s] != 0);
+#pragma unroll
+            for (int s = 0; s < S; s++) {
+                const int tb = below(tpself, s);
+                tpn[s] = below_ok[s] ? tb : 0;
+                int cnt = lane < 31 ? __popc(tm[s] >> (lane + 1)) : 0;
+#pragma unroll
+                for (int s2 = s + 1; s2 < S; s2++) cnt += __popc(tm[s2]);
+                Ssum[s] = cnt;           // tp is zero on REF rows, so this is already plane-local
+            }
+        }
+        const int erow_q = Lq - 1, erow_r = N - 1;
+
+        // ---------------- forward ----------------
+        int Dp[S];
+#pragma unroll
+        for (int s = 0; s < S; s++) Dp[s] = INF;
+        for (int c = 0; c < Lt; c++) {
+            const int tch = tstr[c];
+            const bool tok = c > 0 && (!(tflg[c - 1] & P_VARIANT) || (tflg[c - 1] & P_VAR_END));      // :338-339
+            int diag[S], del[S], swp[S], sbv[S], x[S];
+#pragma unroll
+            for (int s = 0; s < S; s++) {
+                const int r = 32 * s + lane;
+                const int upv = above(Dp, s);                                   // D[r-1][c-1]
+                const int cnt = swi[s] >> 16;
+                int best = row_get(Dp, swi[s] & 0xffff), sb = 0;
+                if (!cnt) best = INF;
+                if (maxcnt > 1) {                                               // rare: several sources (:347, :376)
+                    const int8_t *tab = P[s] ? toR : toQ;
+                    const int len = P[s] ? Lr : Lq;
+                    for (int k = 1; k < maxcnt; k++) {
+                        const bool has = inrow[s] && k < cnt;
+                        const int g = has ? (P[s] ? 0 : Lq) + (int)tab[len + 1 + (int)tab[a[s]] + k] : 0;
+                        const int v = row_get(Dp, g);
+                        if (has) {
+                            if (v < best) { best = v; sb = k << F_K_SHIFT; }
+                            else if (v == best) sb = (k << F_K_SHIFT) | F_TIE;   // keep the larger row
+                        }
+                    }
+                }
+                const bool m = ch[s] == tch;
+                diag[s] = (a[s] > 0 && c > 0) ? upv + (m ? 0 : 1) : INF;         // :324-332, :415-422
+                del[s] = c > 0 ? Dp[s] + 1 : INF;                               // :406-413
+                swp[s] = (tok && m) ? best : INF;                               // :334-349, :363-378
+                sbv[s] = sb;
+                int b = min(min(diag[s], del[s]), swp[s]);
+                if (a[s] == 0 && c == 0) b = 0;                                 // both origins start at 0 (:299-305)
+                if (!inrow[s]) b = INF;
+                x[s] = b < INF / 2 ? b - r : INF;
+            }
+            // insertion chain D[r] = min(b[r], D[r-1] + 1) within a plane: D[r] = r + min_{j<=r} (b[j] - j)
+            int Dn[S];
+            int carryQ = INF, carryR = INF;
+#pragma unroll
+            for (int s = 0; s < S; s++) {
+                const int r = 32 * s + lane;
+                const int seg = P[s] ? Lq : 0;
+                int incl = x[s];
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int o = __shfl_up_sync(FULL, incl, d);
+                    if (lane >= d && r - d >= seg) incl = min(incl, o);
+                }
+                incl = min(incl, P[s] ? carryR : carryQ);
+                if constexpr (S > 1) {
+                    if (s < S - 1) {                                            // totals so far, per plane
+                        const int lastq = min(31, Lq - 1 - 32 * s), lastr = min(31, N - 1 - 32 * s);
+                        const int tq = __shfl_sync(FULL, incl, max(lastq, 0)), tr = __shfl_sync(FULL, incl, max(lastr, 0));
+                        if (lastq >= 0) carryQ = tq;
+                        if (lastr >= 0 && 32 * s + lastr >= Lq) carryR = tr;
+                    }
+                }
+                Dn[s] = (inrow[s] && incl < INF / 2) ? incl + r : INF;
+            }
+#pragma unroll
+            for (int s = 0; s < S; s++) {
+                const int r = 32 * s + lane;
+                const int dabove = above(Dn, s);                                // D[r-1][c]
+                if (inrow[s]) {
+                    const int d = Dn[s];
+                    int f = 0;
+                    if (a[s] == 0 && c == 0) f = F_DIAG;
+                    else {
+                        if (diag[s] == d) f |= F_DIAG;
+                        if (a[s] > 0 && dabove + 1 == d) f |= F_INS;            // :397-404
+                        if (del[s] == d) f |= F_DEL;
+                        if (swp[s] == d) f |= F_SWP | sbv[s];
+                    }
+                    F[c * N + r] = (u8)f;
+                }
+                Dp[s] = Dn[s];
+            }
+        }
+        const int dq = row_get(Dp, erow_q), dr = row_get(Dp, erow_r);          // :390-391
+        const int score = min(dq, dr);
+        const int end_plane = (dq == score) ? 0 : 1;                            // :436-440
+        __syncwarp();
+
+        // ---------------- backward ----------------
+        u32 status = 0;
+        const int erow = end_plane ? erow_r : erow_q;
+        int TFn[S];                                  // (T << 8) | forward flags of column c+1
+#pragma unroll
+        for (int s = 0; s < S; s++) TFn[s] = (-1) << 8;
+        for (int c = Lt - 1; c >= 0; c--) {
+            const bool last = c == Lt - 1;
+            const int tch_next = last ? 0x200 : tstr[c + 1];
+            int Fc[S], B[S], U[S], T[S], swv[S];
+            bool link[S];
+#pragma unroll
+            for (int s = 0; s < S; s++) Fc[s] = inrow[s] ? F[c * N + 32 * s + lane] : 0;
+#pragma unroll
+            for (int s = 0; s < S; s++) {
+                const int r = 32 * s + lane;
+                const int tfd = below(TFn, s);                                   // (r+1, c+1)
+                const int tf2 = row_get(TFn, si[s] >> 8);                        // my swap destination at c+1
+                int b = -1;
+                swv[s] = -1;
+                if (inrow[s]) {
+                    if (last && r == erow) b = 0;                                // :543-545
+                    if (!last) {
+                        const int Td = tfd >> 8, Fd = tfd & 0xff, Tn = TFn[s] >> 8, Fn = TFn[s] & 0xff;
+                        if (below_ok[s] && Td >= 0 && (Fd & F_DIAG)) b = max(b, Td + tpn[s]);      // :556-595, :692-731
+                        if (Tn >= 0 && (Fn & F_DEL)) b = max(b, Tn);                               // :774-804
+                        if (si[s] & 1) {                                                           // :598-679
+                            const int T2 = tf2 >> 8, F2 = tf2 & 0xff;
+                            if (T2 >= 0 && (F2 & F_SWP) && (F2 >> F_K_SHIFT) == ((si[s] >> 1) & 7)) {
+                                swv[s] = T2 + ((si[s] >> 4) & 1);
+                                b = max(b, swv[s]);
+                                if (F2 & F_TIE) status |= VD_ST_TIE;
+                            }
+                        }
+                    }
+                }
+                B[s] = b;
+                const int fbelow = below(Fc, s);                                 // forward flags of (r+1, c)
+                link[s] = below_ok[s] && (fbelow & F_INS);                       // :734-771
+            }
+            // in-column chain T[r] = max(B[r], T[r+1] + tp(r+1)) over unbroken links: suffix max of T - S
+            int carryU = NEG;
+#pragma unroll
+            for (int s = S - 1; s >= 0; s--) {
+                const unsigned lm = __ballot_sync(FULL, link[s]);
+                const unsigned nm = ~(lm >> lane);
+                const int run = nm ? __ffs(nm) - 1 : 32;
+                int val = B[s] >= 0 ? B[s] - Ssum[s] : NEG;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int o = __shfl_down_sync(FULL, val, d);
+                    if (run >= d && lane + d < 32) val = max(val, o);
+                }
+                if (S > 1 && s < S - 1 && run == 32 - lane) val = max(val, carryU);
+                U[s] = val;
+                if (S > 1 && s > 0) carryU = __shfl_sync(FULL, val, 0);
+                T[s] = (inrow[s] && val > NEG / 2) ? val + Ssum[s] : -1;
+            }
+#pragma unroll
+            for (int s = 0; s < S; s++) {
+                const int r = 32 * s + lane;
+                const int tbelow = below(T, s);                                  // T[r+1][c]
+                const int tfd = below(TFn, s);
+                int pf = 0;
+                const int Tv = T[s];
+                if (inrow[s] && Tv >= 0) {
+                    if (last && r == erow && Tv == 0) pf |= PTR_MAT;             // :543
+                    if (!last) {
+                        const int Td = tfd >> 8, Fd = tfd & 0xff, Tn = TFn[s] >> 8, Fn = TFn[s] & 0xff;
+                        if (below_ok[s] && Td >= 0 && (Fd & F_DIAG) && Td + tpn[s] == Tv)
+                            pf |= (chn[s] == tch_next) ? PTR_MAT : PTR_SUB;
+                        if (Tn >= 0 && (Fn & F_DEL) && Tn == Tv) pf |= PTR_DEL;
+                        if (swv[s] >= 0 && swv[s] == Tv) pf |= PTR_SWP;
+                    }
+                    if (link[s] && tbelow >= 0 && tbelow + tpn[s] == Tv) pf |= PTR_INS;
+                }
+                if (inrow[s]) F[c * N + r] = (u8)pf;
+            }
+#pragma unroll
+            for (int s = 0; s < S; s++) TFn[s] = (T[s] << 8) | (Fc[s] & 0xff);
+        }
+        const int t00 = __shfl_sync(FULL, TFn[0], 0) >> 8;
+        const int beg_plane = t00 >= 0 ? 0 : 1;                                  // :811-814
+        status = __reduce_or_sync(FULL, status);
+        if (lane == ai) { my_score = score; my_end = end_plane; my_beg = beg_plane; my_status = status; }
+        __syncwarp();
+    }
+
+    // ---- phase 3: walk + credit, one lane per alignment ----
+    if (lane < 4) {
+        const int ai = lane, qh = ai >> 1, th = 2 + (ai & 1);
+        const int Lq = p.len[qh], Lt = p.len[th], N = Lq + Lr;
+        Hap<int8_t> q{Lq, hstr(qh), hflg(qh), hptr(qh), hins(qh)};
+        Hap<int8_t> t{Lt, hstr(th), hflg(th), hptr(th), hins(th)};
+        QMaps<int8_t> qm{qrptr(qh), qrflg(qh), qtoQ(qh), qtoR(qh)};
+        SMemIL mem{base + M.walk[ai]};
+        AlnLayout<int> L;
+        const int np = N + Lt + 4;
+        L.oPF = L.oF = L.oD0 = L.oD1 = L.oT0 = L.oT1 = 0;
+        L.oPQ = 0; L.oPT = wa4(2 * np); L.oPS = 2 * wa4(2 * np); L.oLev = L.oPS + wa4(np); L.total = 0;
+        PFWarp pfr{base + M.F[ai], N, Lq};
+        u32 status = my_status;
+        walk_credit<SMemIL, 2, int8_t>(mem, L, pfr, q, qm, t, rseq, Lr, my_beg, my_end, in, out, sc, ai, status);
+        const int64_t oi = 4 * (int64_t)sc + ai;
+        out.aln_score[oi] = my_score;
+        out.aln_end_plane[oi] = (u8)my_end;
+        out.aln_beg_plane[oi] = (u8)my_beg;
+        out.status[oi] = status;
+    }
+}
+
+inline void wsc_configure() {
+    const int mx = (WSC_TPB / 32) * wsc_bin_cap(N_WBIN - 1);
+    cudaFuncSetAttribute(wsc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    cudaFuncSetAttribute(wsc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    cudaFuncSetAttribute(wsc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    cudaFuncSetAttribute(wsc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+}
+inline void wsc_launch(cudaStream_t st, int slots, int bin, const BatchDev &in, const OutDev &out, const ScPlan *plan,
+                       const int *order, int count) {
+    if (count <= 0) return;
+    const int wb = wsc_bin_cap(bin), grid = (count + WSC_TPB / 32 - 1) / (WSC_TPB / 32);
+    const int sm = (WSC_TPB / 32) * wb;
+    switch (slots) {
+        case 1: wsc_kernel<1><<<grid, WSC_TPB, sm, st>>>(in, out, plan, order, count, wb); break;
+        case 2: wsc_kernel<2><<<grid, WSC_TPB, sm, st>>>(in, out, plan, order, count, wb); break;
+        case 3: wsc_kernel<3><<<grid, WSC_TPB, sm, st>>>(in, out, plan, order, count, wb); break;
+        case 4: wsc_kernel<4><<<grid, WSC_TPB, sm, st>>>(in, out, plan, order, count, wb); break;
+    }
+}
+
+}  // namespace vd

@@ -24,7 +24,6 @@
 namespace vd {
 
 constexpr int kBigClass = CLS_WAVE;
-constexpr int NEG = -(1 << 28);
 constexpr int FWD_TAU0 = 96;       // first score bound of the forward sweep (then x4 per retry)
 
 // ---- per-hap tables the wavefront kernels need, built once per supercluster --------------
