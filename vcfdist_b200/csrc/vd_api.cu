@@ -9,6 +9,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <ctime>
 #include <string>
 #include <vector>
 
@@ -51,6 +52,7 @@ struct vd_handle {
     int sbwd_min_class = 4;         // VD_SBWD_MIN_CLASS: wave classes below it use the dense backward sweep
     int force_class = -1;           // VD_FORCE_CLASS env: testing hook (1 wave, 2 scalar slab)
     int small_lo = 0, small_hi = vd::N_SMALL - 1;   // VD_SMALL_MIN / VD_SMALL_MAX: small-kernel classes in use (testing)
+    int serial = 0;                 // VD_SERIAL=1: every launch group on the main stream (clean per-kernel event times)
     int use_wsc = 1;                // VD_WSC=0: mid-size superclusters go to the HBM-slab path instead of the warp kernel
     // staged input / output (vd_run)
     struct Stage {                  // one of two staging sets of the host-buffer pipeline
@@ -61,10 +63,11 @@ struct vd_handle {
         bool out_pending = false;
     } stage[2];
     cudaStream_t s_in = nullptr, s_out = nullptr;
-    int64_t chunk_sc = 393216;      // superclusters per pipeline chunk (VD_CHUNK_SC)
+    int64_t chunk_sc = 1048576;      // superclusters per pipeline chunk (VD_CHUNK_SC)
     // work
     DevBuf plan, list, mlist, need_dense, counters, bytes, offs, cubtmp, slab, hap_ok, wave_desc;
-    PlanCounters *h_counters = nullptr;     // pinned
+    PlanCounters *h_counters = nullptr;     // pinned + mapped: written by publish_kernel, never by a copy engine
+    WaveItems *h_witems = nullptr;          // (a small D2H memcpy would queue behind the bulk result copies of vd_run)
 };
 
 static int fail(vd_handle *h, int code, const char *fmt, ...) {
@@ -102,7 +105,8 @@ extern "C" int vd_create(int device, int64_t scratch_bytes, vd_handle **out) {
         for (auto &e : h->sev[c]) cudaEventCreate(&e);
     }
     for (auto &g : h->gev) for (auto &e : g) cudaEventCreate(&e);
-    cudaMallocHost((void **)&h->h_counters, sizeof(PlanCounters));
+    cudaHostAlloc((void **)&h->h_counters, sizeof(PlanCounters), cudaHostAllocMapped);
+    cudaHostAlloc((void **)&h->h_witems, sizeof(WaveItems), cudaHostAllocMapped);
     if (scratch_bytes <= 0) {
         size_t fr = 0, tot = 0;
         cudaMemGetInfo(&fr, &tot);
@@ -113,6 +117,7 @@ extern "C" int vd_create(int device, int64_t scratch_bytes, vd_handle **out) {
     if (const char *v = getenv("VD_SMALL_MIN")) h->small_lo = atoi(v);
     if (const char *v = getenv("VD_SMALL_MAX")) h->small_hi = atoi(v);
     if (const char *v = getenv("VD_WSC")) h->use_wsc = atoi(v);
+    if (const char *v = getenv("VD_SERIAL")) h->serial = atoi(v);
     if (const char *df = getenv("VD_DENSE_FWD")) h->banded_fwd = atoi(df) == 0;
     if (const char *db = getenv("VD_DENSE_BWD")) h->sparse_bwd = atoi(db) == 0;
     if (const char *sm = getenv("VD_SBWD_MIN_CLASS")) h->sbwd_min_class = atoi(sm);
@@ -148,6 +153,7 @@ extern "C" void vd_destroy(vd_handle *h) {
                       &h->cubtmp, &h->slab, &h->hap_ok, &h->wave_desc};
     for (DevBuf *b : bufs) b->release();
     if (h->h_counters) cudaFreeHost(h->h_counters);
+    if (h->h_witems) cudaFreeHost(h->h_witems);
     for (auto &e : h->ev) if (e) cudaEventDestroy(e);
     for (auto &g : h->gev) for (auto &e : g) if (e) cudaEventDestroy(e);
     for (int c = 0; c < N_WCLS; c++) {
@@ -175,6 +181,10 @@ static int run_resident(vd_handle *h, const BatchDev &in, const OutDev &out, con
     const int64_t n_var = in.n_var;
     vd_stats &S = h->stats;
     if (n_sc == 0) return VD_OK;
+    const bool trace = getenv("VD_TRACE") != nullptr;
+    auto now_ms = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
+    const double t_r0 = now_ms();
+    if (trace) { cudaStreamSynchronize(st); fprintf(stderr, "[run_resident] inputs ready after %.2f ms\n", now_ms() - t_r0); }
 
     CK(cudaEventRecord(h->ev[0], st));
     CK(cudaMemsetAsync(base.assigned, 0, 2 * n_var, st));
@@ -198,11 +208,12 @@ static int run_resident(vd_handle *h, const BatchDev &in, const OutDev &out, con
     small_base_kernel<<<1, 32, 0, st>>>(dcnt);
     small_fill_kernel<<<(n_sc + 255) / 256, 256, 0, st>>>(plan, n_sc, dcnt, order);
     S.n_launches += 3;
-    CK(cudaMemcpyAsync(h->h_counters, dcnt, sizeof(PlanCounters), cudaMemcpyDeviceToHost, st));
+    publish_kernel<<<1, 64, 0, st>>>((const u32 *)dcnt, (u32 *)h->h_counters, (int)(sizeof(PlanCounters) / 4));
     CK(cudaEventRecord(h->ev[1], st));
     CK(cudaStreamSynchronize(st));          // counters are now on the host
     CK(cudaGetLastError());
     const PlanCounters pc = *h->h_counters;
+    if (trace) fprintf(stderr, "[run_resident] plan done at %.2f ms\n", now_ms() - t_r0);
 
     // ---- short superclusters: one fused launch per group, most expensive group first: the warp
     //      kernel's (slots, shared-memory bin) groups on the side streams (they are latency-bound and
@@ -214,7 +225,7 @@ static int run_resident(vd_handle *h, const BatchDev &in, const OutDev &out, con
     for (int g = N_GROUP - 1; g >= 0; g--) {
         const int cnt = pc.grp_count[g];
         if (cnt <= 0) continue;
-        cudaStream_t gs = g < N_SMALL ? st : h->side[(g - N_SMALL) % N_WCLS];
+        cudaStream_t gs = (g < N_SMALL || h->serial) ? st : h->side[(g - N_SMALL) % N_WCLS];
         if (gs != st) CK(cudaStreamWaitEvent(gs, h->ev[5], 0));
         CK(cudaEventRecord(h->gev[g][0], gs));
         if (g < N_SMALL) small_launch(gs, g, in, out, plan, order + pc.grp_first[g], cnt);
@@ -279,9 +290,9 @@ static int run_resident(vd_handle *h, const BatchDev &in, const OutDev &out, con
             CK(cudaMemsetAsync(wi, 0, sizeof(WaveItems), st));
             wave_count_kernel<<<(4 * m + 127) / 128, 128, 0, st>>>(plan, list, i0, i1, (const int *)h->hap_ok.p, wi);
             S.n_launches += 2;
-            WaveItems hwi;
-            CK(cudaMemcpyAsync(&hwi, wi, sizeof(WaveItems), cudaMemcpyDeviceToHost, st));
+            publish_kernel<<<1, 64, 0, st>>>((const u32 *)wi, (u32 *)h->h_witems, (int)(sizeof(WaveItems) / 4));
             CK(cudaStreamSynchronize(st));
+            const WaveItems hwi = *h->h_witems;
             ClsBase cb;
             int total_items = 0;
             for (int c = 0; c < N_WCLS; c++) { cb.b[c] = total_items; total_items += hwi.count[c]; }
@@ -298,14 +309,14 @@ static int run_resident(vd_handle *h, const BatchDev &in, const OutDev &out, con
                 CK(cudaEventRecord(h->ev[4], st));
                 for (int c = 0; c < N_WCLS; c++) {
                     if (!hwi.count[c]) continue;
-                    cudaStream_t ss = h->side[c];
-                    CK(cudaStreamWaitEvent(ss, h->ev[4], 0));
+                    cudaStream_t ss = h->serial ? st : h->side[c];
+                    if (ss != st) CK(cudaStreamWaitEvent(ss, h->ev[4], 0));
                     CK(cudaEventRecord(h->sev[c][0], ss));
                     wave_launch(ss, WA, c, cb.b[c], hwi.count[c], true, true, h->banded_fwd ? (int *)h->need_dense.p : nullptr);
                     CK(cudaEventRecord(h->sev[c][1], ss));
                     wave_launch(ss, WA, c, cb.b[c], hwi.count[c], false, h->sparse_bwd && c >= h->sbwd_min_class);
                     CK(cudaEventRecord(h->sev[c][2], ss));
-                    CK(cudaStreamWaitEvent(st, h->sev[c][2], 0));
+                    if (ss != st) CK(cudaStreamWaitEvent(st, h->sev[c][2], 0));
                     S.n_launches += 2;
                 }
                 CK(cudaEventRecord(h->ev[6], st));
@@ -334,13 +345,15 @@ static int run_resident(vd_handle *h, const BatchDev &in, const OutDev &out, con
             i0 = i1;
         }
     }
-    for (int g = N_SMALL; g < N_GROUP; g++) if (grp_used[g]) CK(cudaStreamWaitEvent(st, h->gev[g][1], 0));
+    if (!h->serial) for (int g = N_SMALL; g < N_GROUP; g++) if (grp_used[g]) CK(cudaStreamWaitEvent(st, h->gev[g][1], 0));
     status_or_kernel<<<296, 256, 0, st>>>(out.status, 4 * (int64_t)n_sc, &((PlanCounters *)h->counters.p)->status_or);
     S.n_launches++;
-    CK(cudaMemcpyAsync(h->h_counters, h->counters.p, sizeof(PlanCounters), cudaMemcpyDeviceToHost, st));
+    publish_kernel<<<1, 64, 0, st>>>((const u32 *)h->counters.p, (u32 *)h->h_counters, (int)(sizeof(PlanCounters) / 4));
     CK(cudaEventRecord(h->ev[3], st));
+    if (trace) fprintf(stderr, "[run_resident] all launched at %.2f ms\n", now_ms() - t_r0);
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
+    if (trace) fprintf(stderr, "[run_resident] finished at %.2f ms\n", now_ms() - t_r0);
     h->stats_status_or |= h->h_counters->status_or;
     float e_ = 0;
     cudaEventElapsedTime(&e_, h->ev[0], h->ev[1]); S.ms_plan += e_;
@@ -397,14 +410,25 @@ extern "C" int vd_run(vd_handle *h, const vd_batch_in *in, vd_batch_out *out) {
     // in on s_in and chunk i-1's results are copied out on s_out.  Every chunk keeps the batch's
     // ABSOLUTE offsets (ref_off / var_off / alt_off values); the data pointers handed to the
     // kernels are shifted back by the chunk's first byte / variant instead.
+    // chunk boundaries: small chunks first and last (the first H2D and the last D2H are not hidden
+    // behind any compute), full-size chunks in between
     const int64_t CH = h->chunk_sc;
-    const int n_chunks = (int)((n_sc + CH - 1) / CH);
+    std::vector<int64_t> cut{0};
+    {
+        int64_t s0 = 0;
+        const int64_t ramp[2] = {CH / 4, CH / 2};
+        for (int k = 0; k < 2 && n_sc - s0 > 2 * CH && ramp[k] > 0; k++) { s0 += ramp[k]; cut.push_back(s0); }
+        while (n_sc - s0 > CH + CH / 2) { s0 += CH; cut.push_back(s0); }
+        if (n_sc - s0 > CH / 2 && CH / 4 > 0) { s0 = n_sc - CH / 4; cut.push_back(s0); }
+        cut.push_back(n_sc);
+    }
+    const int n_chunks = (int)cut.size() - 1;
     int64_t h2d = 0, d2h = 0;
     int rc_all = VD_OK;
     struct Range { int64_t s0, s1, v0, v1, r0, r1, a0, a1; };
     auto range_of = [&](int i) {
         Range r;
-        r.s0 = (int64_t)i * CH; r.s1 = r.s0 + CH < n_sc ? r.s0 + CH : n_sc;
+        r.s0 = cut[i]; r.s1 = cut[i + 1];
         r.v0 = in->var_off[4 * r.s0]; r.v1 = in->var_off[4 * r.s1];
         r.r0 = in->ref_off[r.s0]; r.r1 = in->ref_off[r.s1];
         r.a0 = n_var ? in->alt_off[r.v0] : 0; r.a1 = n_var ? in->alt_off[r.v1] : 0;
@@ -433,9 +457,13 @@ extern "C" int vd_run(vd_handle *h, const vd_batch_in *in, vd_batch_out *out) {
         return VD_OK;
     };
 
+    const bool trace = getenv("VD_TRACE") != nullptr;
+    auto now_ms = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
+    const double t_start = now_ms();
     int rc = upload(0);
     if (rc != VD_OK) return rc;
     for (int i = 0; i < n_chunks; i++) {
+        const double t_c0 = now_ms();
         vd_handle::Stage &sg = h->stage[i & 1];
         const Range r = range_of(i);
         const int64_t ns = r.s1 - r.s0, nv = r.v1 - r.v0;
@@ -459,7 +487,11 @@ extern "C" int vd_run(vd_handle *h, const vd_batch_in *in, vd_batch_out *out) {
                     (float *)sg.o_callq.p};
         OutDev o = base;                       // per-variant arrays are indexed [slot*nv + (v - v0)]
         o.assigned -= r.v0; o.sync_group -= r.v0; o.ref_ed -= r.v0; o.query_ed -= r.v0; o.callq -= r.v0;
+        const double t_c1 = now_ms();
         rc = run_resident(h, b, o, base);      // returns with the chunk's kernels finished
+        const double t_c2 = now_ms();
+        if (trace) fprintf(stderr, "[vd_run] chunk %d: start %.2f ms, enqueue %.2f ms, run_resident %.2f ms (device %.2f ms so far)\n",
+                           i, t_c0 - t_start, t_c1 - t_c0, t_c2 - t_c1, h->stats.ms_total);
         if (rc != VD_OK && rc != VD_E_BADINPUT) return rc;
         if (rc != VD_OK) rc_all = rc;
 
@@ -481,7 +513,9 @@ extern "C" int vd_run(vd_handle *h, const vd_batch_in *in, vd_batch_out *out) {
         CK(cudaEventRecord(sg.out_done, h->s_out));
         sg.out_pending = true;
     }
+    const double t_e0 = now_ms();
     CK(cudaStreamSynchronize(h->s_out));
+    if (trace) fprintf(stderr, "[vd_run] drain %.2f ms, total %.2f ms\n", now_ms() - t_e0, now_ms() - t_start);
     h->stage[0].out_pending = h->stage[1].out_pending = false;
     h->stats.h2d_bytes = h2d;
     h->stats.d2h_bytes = d2h;

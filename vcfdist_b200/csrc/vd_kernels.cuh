@@ -42,8 +42,11 @@ template <int TL, int TR> struct SmallDims {
     static constexpr int SW = (TL + TR + 1 + 3) & ~3;                 // one CSR swap table
     static constexpr int HAP = 3 * TL + TR;                           // str TL | flg TL | ptr TL | ins TR
     static constexpr int QM = 2 * TR + 2 * SW;                        // rptr TR | rflg TR | toQ SW | toR SW
-    static constexpr int SC_BYTES = 4 * HAP + 2 * QM + TR + 8;        // ... | rseq TR | hlen 4 x int16
-    static_assert((TR % 4) == 0 && (TL % 4) == 0 && (SC_BYTES % 4) == 0, "alignment of the shared area");
+    static constexpr int RAW = 4 * HAP + 2 * QM + TR + 8;             // ... | rseq TR | hlen 4 x int16
+    // stride of the per-supercluster areas: an ODD number of words, so that the quads of a warp that
+    // read the same offset of their own area hit different banks
+    static constexpr int SC_BYTES = ((RAW / 4) & 1) ? RAW : RAW + 4;
+    static_assert((TR % 4) == 0 && (TL % 4) == 0 && (RAW % 4) == 0, "alignment of the shared area");
 };
 
 struct PlanCounters {
@@ -58,6 +61,13 @@ struct PlanCounters {
     int grp_first[N_GROUP], grp_count[N_GROUP];
     unsigned long long io_grp[N_GROUP];     // algorithmic input+output bytes per launch group
 };
+
+// small control blocks go to the host through mapped pinned memory (stores from the SM), not through
+// a copy engine: a D2H memcpy would wait behind the bulk result copies of the previous chunk
+__global__ void publish_kernel(const u32 *src, u32 *dst_host, int n_words) {
+    for (int i = threadIdx.x; i < n_words; i += blockDim.x) dst_host[i] = src[i];
+    __threadfence_system();
+}
 
 // OR of all status words (so that the host only scans them when an error bit is set)
 __global__ void status_or_kernel(const u32 *status, int64_t n, unsigned *dst) {
