@@ -31,7 +31,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("VD_LIB") or LIB_PATH      # VD_LIB: another build of the same library (kernel experiments)
     if not os.path.exists(p):
         raise RuntimeError(
             f"{p} is missing: the CUDA extension has not been built "

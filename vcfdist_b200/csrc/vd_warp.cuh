@@ -33,6 +33,7 @@ struct WscLayout {
     int hap[4];      // str L | flg L | ptr L (int8) | ins Lr
     int qm[2];       // rptr Lr | rflg Lr | toQ (Lq+1+Lr) | toR (Lr+1+Lq)
     int rseq;
+    int tinf[2];     // per truth hap and column: base | tok << 8 (u16)
     int F[4];        // flag matrix [Lt][N]
     int walk[4];     // path (int16 q, int16 t, u8 flags) + Levenshtein row
     int total;
@@ -44,6 +45,7 @@ __host__ __device__ inline WscLayout wsc_layout(const ScPlan &p) {
     for (int h = 0; h < 4; h++) { m.hap[h] = o; o += wa4(3 * p.len[h] + Lr); }
     for (int k = 0; k < 2; k++) { m.qm[k] = o; o += wa4(2 * Lr + 2 * (p.len[k] + Lr + 1)); }
     m.rseq = o; o += wa4(Lr);
+    for (int k = 0; k < 2; k++) { m.tinf[k] = o; o += wa4(2 * p.len[2 + k]); }
     for (int ai = 0; ai < 4; ai++) {
         const int N = p.len[ai >> 1] + Lr, Lt = p.len[2 + (ai & 1)];
         m.F[ai] = o; o += wa4(N * Lt);
@@ -70,18 +72,25 @@ struct PFWarp {      // path flags, [column][row], QUERY rows first
     __device__ __forceinline__ int get(int hi, int qri, int ti) const { return F[ti * N + (hi ? Lq + qri : qri)]; }
 };
 
-template <int S>
+// PAR = false: one warp per supercluster, its four alignments one after the other (small shared-memory
+//               bins: occupancy is register-limited and there are plenty of superclusters);
+// PAR = true:  one block per supercluster, warp w runs alignment w (big bins: few superclusters, occupancy is
+//               shared-memory-limited, so the four warps share one supercluster's footprint and its latency
+//               drops fourfold).
+template <int S, bool PAR>
 __global__ void __launch_bounds__(WSC_TPB)
 wsc_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, const int *__restrict__ order, int count, int warp_bytes) {
     extern __shared__ __align__(16) u8 smem[];
     constexpr unsigned FULL = 0xffffffffu;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int slot = blockIdx.x * (WSC_TPB / 32) + warp;
-    if (slot >= count) return;                      // warps are independent: no block-wide barrier anywhere
+    const int slot = PAR ? blockIdx.x : blockIdx.x * (WSC_TPB / 32) + warp;
+    if (slot >= count) return;                      // !PAR: warps are independent, no block-wide barrier anywhere
+    auto sync = [&]() { if constexpr (PAR) __syncthreads(); else __syncwarp(); };
+    const bool lead = !PAR || warp == 0;            // the warp that runs the single-lane phases of the supercluster
     const int sc = order[slot];
     const ScPlan p = plan[sc];
     const WscLayout M = wsc_layout(p);
-    u8 *base = smem + warp * warp_bytes;
+    u8 *base = PAR ? smem : smem + warp * warp_bytes;
     const int Lr = p.lr;
     auto hstr = [&](int h) { return base + M.hap[h]; };
     auto hflg = [&](int h) { return base + M.hap[h] + p.len[h]; };
@@ -95,7 +104,9 @@ wsc_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, const int *
 
     // ---- phase 1: expansion ----
     bool ok = true;
-    if (lane < 4) {
+    if (!lead) {
+        // PAR: the other warps wait for the expansion
+    } else if (lane < 4) {
         const int h = lane;
         const bool isq = h < 2;
         const int len = expand_hap<int8_t>(in, sc, h, hstr(h), hflg(h), hptr(h), isq ? qrptr(h) : nullptr,
@@ -107,11 +118,28 @@ wsc_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, const int *
         const u8 *rs = in.rplane_seq + in.ref_off[sc];
         for (int k = lane - 4; k < Lr; k += 28) rseq[k] = rs[k];
     }
+    if constexpr (PAR) {
+        __shared__ int s_ok;
+        if (threadIdx.x == 0) s_ok = 1;
+        __syncthreads();
+        if (!ok) s_ok = 0;
+        __syncthreads();
+        ok = s_ok != 0;
+    }
     if (__ballot_sync(FULL, ok) != FULL) {
-        if (lane < 4) { out.status[4 * (int64_t)sc + lane] = ST_BAD; out.aln_score[4 * (int64_t)sc + lane] = -1; }
+        if (lead && lane < 4) { out.status[4 * (int64_t)sc + lane] = ST_BAD; out.aln_score[4 * (int64_t)sc + lane] = -1; }
         return;
     }
     __syncwarp();
+    for (int k = 0; k < 2; k++) {                    // truth columns: base | tok << 8   (:338-339, :367-368)
+        const u8 *ts = hstr(2 + k), *tf = hflg(2 + k);
+        u16 *ti = (u16 *)(base + M.tinf[k]);
+        for (int c = PAR ? (int)threadIdx.x : lane; c < p.len[2 + k]; c += PAR ? WSC_TPB : 32) {
+            const bool tok = c > 0 && (!(tf[c - 1] & P_VARIANT) || (tf[c - 1] & P_VAR_END));
+            ti[c] = (u16)(ts[c] | (tok ? 0x100 : 0));
+        }
+    }
+    sync();
 
     // values of an arbitrary row g / the row above / the row below, from per-slot register arrays
     auto row_get = [&](const int (&X)[S], int g) -> int {
@@ -135,10 +163,11 @@ wsc_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, const int *
     u32 my_status = 0;
 
     // ---- phase 2: the four alignments ----
-    for (int ai = 0; ai < 4; ai++) {
+    for (int ai = PAR ? warp : 0; ai < (PAR ? warp + 1 : 4); ai++) {
         const int qh = ai >> 1, th = 2 + (ai & 1);
         const int Lq = p.len[qh], Lt = p.len[th], N = Lq + Lr;
-        const u8 *qstr = hstr(qh), *qflg = hflg(qh), *tstr = hstr(th), *tflg = hflg(th);
+        const u8 *qstr = hstr(qh), *qflg = hflg(qh);
+        const u16 *tinf = (const u16 *)(base + M.tinf[ai & 1]);
         const int8_t *qptr = hptr(qh), *rptr = qrptr(qh), *toQ = qtoQ(qh), *toR = qtoR(qh);
         const u8 *rflg = qrflg(qh);
         u8 *F = base + M.F[ai];
@@ -207,8 +236,9 @@ wsc_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, const int *
 #pragma unroll
         for (int s = 0; s < S; s++) Dp[s] = INF;
         for (int c = 0; c < Lt; c++) {
-            const int tch = tstr[c];
-            const bool tok = c > 0 && (!(tflg[c - 1] & P_VARIANT) || (tflg[c - 1] & P_VAR_END));      // :338-339
+            const int tic = tinf[c];
+            const int tch = tic & 0xff;
+            const bool tok = tic >> 8;                                                               // :338-339
             int diag[S], del[S], swp[S], sbv[S], x[S];
 #pragma unroll
             for (int s = 0; s < S; s++) {
@@ -296,8 +326,8 @@ wsc_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, const int *
         for (int s = 0; s < S; s++) TFn[s] = (-1) << 8;
         for (int c = Lt - 1; c >= 0; c--) {
             const bool last = c == Lt - 1;
-            const int tch_next = last ? 0x200 : tstr[c + 1];
-            int Fc[S], B[S], U[S], T[S], swv[S];
+            const int tch_next = last ? 0x200 : (tinf[c + 1] & 0xff);
+            int Fc[S], B[S], U[S], T[S], swv[S], tfdv[S];
             bool link[S];
 #pragma unroll
             for (int s = 0; s < S; s++) Fc[s] = inrow[s] ? F[c * N + 32 * s + lane] : 0;
@@ -305,6 +335,7 @@ wsc_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, const int *
             for (int s = 0; s < S; s++) {
                 const int r = 32 * s + lane;
                 const int tfd = below(TFn, s);                                   // (r+1, c+1)
+                tfdv[s] = tfd;
                 const int tf2 = row_get(TFn, si[s] >> 8);                        // my swap destination at c+1
                 int b = -1;
                 swv[s] = -1;
@@ -350,7 +381,7 @@ wsc_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, const int *
             for (int s = 0; s < S; s++) {
                 const int r = 32 * s + lane;
                 const int tbelow = below(T, s);                                  // T[r+1][c]
-                const int tfd = below(TFn, s);
+                const int tfd = tfdv[s];
                 int pf = 0;
                 const int Tv = T[s];
                 if (inrow[s] && Tv >= 0) {
@@ -372,13 +403,13 @@ wsc_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, const int *
         const int t00 = __shfl_sync(FULL, TFn[0], 0) >> 8;
         const int beg_plane = t00 >= 0 ? 0 : 1;                                  // :811-814
         status = __reduce_or_sync(FULL, status);
-        if (lane == ai) { my_score = score; my_end = end_plane; my_beg = beg_plane; my_status = status; }
+        if (lane == (PAR ? 0 : ai)) { my_score = score; my_end = end_plane; my_beg = beg_plane; my_status = status; }
         __syncwarp();
     }
 
     // ---- phase 3: walk + credit, one lane per alignment ----
-    if (lane < 4) {
-        const int ai = lane, qh = ai >> 1, th = 2 + (ai & 1);
+    if (PAR ? lane == 0 : lane < 4) {
+        const int ai = PAR ? warp : lane, qh = ai >> 1, th = 2 + (ai & 1);
         const int Lq = p.len[qh], Lt = p.len[th], N = Lq + Lr;
         Hap<int8_t> q{Lq, hstr(qh), hflg(qh), hptr(qh), hins(qh)};
         Hap<int8_t> t{Lt, hstr(th), hflg(th), hptr(th), hins(th)};
@@ -399,23 +430,26 @@ wsc_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, const int *
     }
 }
 
-inline void wsc_configure() {
-    const int mx = (WSC_TPB / 32) * wsc_bin_cap(N_WBIN - 1);
-    cudaFuncSetAttribute(wsc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-    cudaFuncSetAttribute(wsc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-    cudaFuncSetAttribute(wsc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-    cudaFuncSetAttribute(wsc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+constexpr int WSC_PAR_MINBIN = 2;      // bins >= 10 KB per supercluster: one block per supercluster, one warp per alignment
+template <int S> inline void wsc_configure_one() {
+    cudaFuncSetAttribute(wsc_kernel<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (WSC_TPB / 32) * wsc_bin_cap(WSC_PAR_MINBIN - 1));
+    cudaFuncSetAttribute(wsc_kernel<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wsc_bin_cap(N_WBIN - 1));
+}
+inline void wsc_configure() { wsc_configure_one<1>(); wsc_configure_one<2>(); wsc_configure_one<3>(); wsc_configure_one<4>(); }
+template <int S> inline void wsc_launch_one(cudaStream_t st, int bin, const BatchDev &in, const OutDev &out, const ScPlan *plan,
+                                            const int *order, int count) {
+    const int wb = wsc_bin_cap(bin), wpb = WSC_TPB / 32;
+    if (bin >= WSC_PAR_MINBIN) wsc_kernel<S, true><<<count, WSC_TPB, wb, st>>>(in, out, plan, order, count, wb);
+    else wsc_kernel<S, false><<<(count + wpb - 1) / wpb, WSC_TPB, wpb * wb, st>>>(in, out, plan, order, count, wb);
 }
 inline void wsc_launch(cudaStream_t st, int slots, int bin, const BatchDev &in, const OutDev &out, const ScPlan *plan,
                        const int *order, int count) {
     if (count <= 0) return;
-    const int wb = wsc_bin_cap(bin), grid = (count + WSC_TPB / 32 - 1) / (WSC_TPB / 32);
-    const int sm = (WSC_TPB / 32) * wb;
     switch (slots) {
-        case 1: wsc_kernel<1><<<grid, WSC_TPB, sm, st>>>(in, out, plan, order, count, wb); break;
-        case 2: wsc_kernel<2><<<grid, WSC_TPB, sm, st>>>(in, out, plan, order, count, wb); break;
-        case 3: wsc_kernel<3><<<grid, WSC_TPB, sm, st>>>(in, out, plan, order, count, wb); break;
-        case 4: wsc_kernel<4><<<grid, WSC_TPB, sm, st>>>(in, out, plan, order, count, wb); break;
+        case 1: wsc_launch_one<1>(st, bin, in, out, plan, order, count); break;
+        case 2: wsc_launch_one<2>(st, bin, in, out, plan, order, count); break;
+        case 3: wsc_launch_one<3>(st, bin, in, out, plan, order, count); break;
+        case 4: wsc_launch_one<4>(st, bin, in, out, plan, order, count); break;
     }
 }
 
