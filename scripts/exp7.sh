@@ -1,5 +1,5 @@
 mkdir -p gpurun_out/e7
 {
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-python bench.py --steps 3 --no-cpu-baseline | python scripts/benchsum.py
+VD_LIB=vcfdist_b200/libvd_par1.so python bench.py --steps 3 --no-cpu-baseline | python scripts/benchsum.py
+VD_LIB=vcfdist_b200/libvd_par0.so python bench.py --steps 3 --no-cpu-baseline | python scripts/benchsum.py
 } > gpurun_out/e7/log 2>&1; cat gpurun_out/e7/log

@@ -188,8 +188,42 @@ __device__ bool build_swsrc(const PT *ptr, const u8 *flg, int nsrc, PT *tab, int
 }
 
 // ---------------------------------------------------------------------------------------
-// plain Levenshtein, what wf_ed (:1406-1506) returns in `s`.  Row buffer in `mem` at oLev.
+// plain Levenshtein, what wf_ed (:1406-1506) returns in `s`.
 // ---------------------------------------------------------------------------------------
+// Bit-parallel unit-cost global edit distance (Myers 1999 in Hyyro's formulation for the global
+// distance: the horizontal delta shifted into row 0 is +1).  b is the pattern, n <= 64; a is the
+// text.  O(m) word operations, no memory traffic except reading the strings: the section edit
+// distances of structural variants are (thousands) x (a few) and made the one-thread row DP the
+// slowest thing in the whole long-supercluster path.
+__host__ __device__ inline int lev_myers64(const u8 *a, int m, const u8 *b, int n) {
+    typedef unsigned long long u64;
+    u64 eqA = 0, eqC = 0, eqG = 0, eqT = 0;
+    for (int j = 0; j < n; j++) {
+        const u64 bit = 1ull << j;
+        const int c = b[j];
+        if (c == 'A') eqA |= bit; else if (c == 'C') eqC |= bit; else if (c == 'G') eqG |= bit; else if (c == 'T') eqT |= bit;
+    }
+    const u64 top = 1ull << (n - 1);
+    u64 VP = ~0ull, VN = 0;
+    int score = n;
+    for (int i = 0; i < m; i++) {
+        const int c = a[i];
+        u64 Eq;
+        if (c == 'A') Eq = eqA; else if (c == 'C') Eq = eqC; else if (c == 'G') Eq = eqG; else if (c == 'T') Eq = eqT;
+        else { Eq = 0; for (int j = 0; j < n; j++) if (b[j] == c) Eq |= 1ull << j; }     // N / IUPAC: rare
+        const u64 X = Eq | VN;
+        const u64 D0 = ((VP + (X & VP)) ^ VP) | X;
+        const u64 HN = VP & D0;
+        const u64 HP = VN | ~(VP | D0);
+        if (HP & top) score++; else if (HN & top) score--;
+        const u64 Xs = (HP << 1) | 1ull;
+        VN = Xs & D0;
+        VP = (HN << 1) | ~(Xs | D0);
+    }
+    return score;
+}
+
+// Row buffer in `mem` at oLev for the general case.
 template <class Mem, int W>
 __device__ int lev_scalar(const Mem &mem, typename Mem::off_t oLev,
                           const u8 *a, int m, const u8 *b, int n) {
@@ -201,6 +235,7 @@ __device__ int lev_scalar(const Mem &mem, typename Mem::off_t oLev,
         if (k == m) return 0;
     }
     if (n > m) { const u8 *t = a; a = b; b = t; int x = m; m = n; n = x; }   // row over the shorter
+    if (n <= 64 && m * n > 64) return lev_myers64(a, m, b, n);
     typedef Val<Mem, W> V;
     for (int j = 0; j <= n; j++) V::st(mem, oLev, j, j);
     for (int i = 1; i <= m; i++) {

@@ -430,9 +430,12 @@ wsc_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, const int *
     }
 }
 
-constexpr int WSC_PAR_MINBIN = 2;      // bins >= 10 KB per supercluster: one block per supercluster, one warp per alignment
+#ifndef VD_WSC_PAR_MINBIN
+#define VD_WSC_PAR_MINBIN 2
+#endif
+constexpr int WSC_PAR_MINBIN = VD_WSC_PAR_MINBIN;      // bins >= 10 KB per supercluster: one block per supercluster, one warp per alignment
 template <int S> inline void wsc_configure_one() {
-    cudaFuncSetAttribute(wsc_kernel<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (WSC_TPB / 32) * wsc_bin_cap(WSC_PAR_MINBIN - 1));
+    cudaFuncSetAttribute(wsc_kernel<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (WSC_TPB / 32) * wsc_bin_cap(WSC_PAR_MINBIN > 0 ? WSC_PAR_MINBIN - 1 : 0));
     cudaFuncSetAttribute(wsc_kernel<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wsc_bin_cap(N_WBIN - 1));
 }
 inline void wsc_configure() { wsc_configure_one<1>(); wsc_configure_one<2>(); wsc_configure_one<3>(); wsc_configure_one<4>(); }
