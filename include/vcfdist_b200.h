@@ -138,6 +138,8 @@ typedef struct vd_stats {
                                  class 1, warp-per-supercluster kernel (all its launches)           */
     int64_t n_small[3];       /* superclusters handled by each of them                             */
     int64_t io_small[3];      /* algorithmic input+output bytes of those superclusters             */
+    int64_t n_hom;            /* homozygous superclusters among them (both query haplotypes identical and
+                                 both truth haplotypes identical: one alignment computed, records replicated) */
 } vd_stats;
 
 /* Final per-variant / per-supercluster results in the reference's own terms

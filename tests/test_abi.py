@@ -32,7 +32,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(vd_batch_in) == 8 + 10 * 8 + 8
     assert C.sizeof(vd_batch_out) == 9 * 8
     assert C.sizeof(vd_final) == 9 * 8
-    assert C.sizeof(vd_stats) == 10 * 8 + 10 * 4 + 6 * 8
+    assert C.sizeof(vd_stats) == 10 * 8 + 10 * 4 + 7 * 8
 
 
 @pytest.mark.skipif(has_gpu(), reason="checks the no-GPU failure mode")

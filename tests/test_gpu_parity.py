@@ -85,6 +85,30 @@ def test_every_short_kernel_on_golden(name, lo, hi, wsc):
     e.close()
 
 
+def test_homozygous_replication_matches_full_computation():
+    """Homozygous superclusters (both query haplotypes identical, both truth haplotypes identical) are
+    solved once and replicated; VD_HOM=0 runs all four alignments.  Both must equal the oracle; the
+    batch mixes real demo superclusters (43 % homozygous) with synthetic homozygous ones of every size."""
+    demo, _, _ = load_golden("demo")
+    rng = np.random.default_rng(7)
+    bb = BatchBuilder()
+    for i in range(400):
+        L = int(rng.integers(3, 70))
+        ref = bytes(rng.choice(list(b"ACGT"), L).tolist())
+        qv = synth.random_hap(rng, ref, 0.15, 4, b"ACGT")
+        tv = synth.random_hap(rng, ref, 0.15, 4, b"ACGT") if i % 3 else qv
+        bb.add(ref, [qv, qv, tv, tv])
+    b = Batch.concat([demo, bb.build()])
+    want = capi.oracle_run(b).trimmed()
+    for hom in (1, 0):
+        e = engine_with(VD_HOM=hom)
+        got = e.run(b).trimmed()
+        assert mismatches(got, want, OUT_KEYS) == {}
+        st = e.stats()
+        assert (st["n_hom"] > 2000) == bool(hom)
+        e.close()
+
+
 def test_warp_kernel_shapes():
     """Warp-per-supercluster kernel on its own: one to four register slots (<= 32 .. <= 128 rows),
     several swap sources per row (insertions, adjacent deletions), every shared-memory bin."""

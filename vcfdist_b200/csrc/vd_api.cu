@@ -53,6 +53,7 @@ struct vd_handle {
     int force_class = -1;           // VD_FORCE_CLASS env: testing hook (1 wave, 2 scalar slab)
     int small_lo = 0, small_hi = vd::N_SMALL - 1;   // VD_SMALL_MIN / VD_SMALL_MAX: small-kernel classes in use (testing)
     int serial = 0;                 // VD_SERIAL=1: every launch group on the main stream (clean per-kernel event times)
+    int use_hom = 1;                // VD_HOM=0: homozygous superclusters run all four alignments (testing)
     int use_wsc = 1;                // VD_WSC=0: mid-size superclusters go to the HBM-slab path instead of the warp kernel
     // staged input / output (vd_run)
     struct Stage {                  // one of two staging sets of the host-buffer pipeline
@@ -118,6 +119,7 @@ extern "C" int vd_create(int device, int64_t scratch_bytes, vd_handle **out) {
     if (const char *v = getenv("VD_SMALL_MAX")) h->small_hi = atoi(v);
     if (const char *v = getenv("VD_WSC")) h->use_wsc = atoi(v);
     if (const char *v = getenv("VD_SERIAL")) h->serial = atoi(v);
+    if (const char *v = getenv("VD_HOM")) h->use_hom = atoi(v);
     if (const char *df = getenv("VD_DENSE_FWD")) h->banded_fwd = atoi(df) == 0;
     if (const char *db = getenv("VD_DENSE_BWD")) h->sparse_bwd = atoi(db) == 0;
     if (const char *sm = getenv("VD_SBWD_MIN_CLASS")) h->sbwd_min_class = atoi(sm);
@@ -204,7 +206,7 @@ static int run_resident(vd_handle *h, const BatchDev &in, const OutDev &out, con
     int *order = (int *)h->mlist.p;                 // class- and cost-sorted small superclusters
     PlanCounters *dcnt = (PlanCounters *)h->counters.p;
 
-    plan_kernel<<<(n_sc + 255) / 256, 256, 0, st>>>(in, plan, list, dcnt, h->force_class, kBigClass, h->small_lo, h->small_hi, h->use_wsc);
+    plan_kernel<<<(n_sc + 255) / 256, 256, 0, st>>>(in, plan, list, dcnt, h->force_class, kBigClass, h->small_lo, h->small_hi, h->use_wsc, h->use_hom);
     small_base_kernel<<<1, 32, 0, st>>>(dcnt);
     small_fill_kernel<<<(n_sc + 255) / 256, 256, 0, st>>>(plan, n_sc, dcnt, order);
     S.n_launches += 3;
@@ -225,21 +227,24 @@ static int run_resident(vd_handle *h, const BatchDev &in, const OutDev &out, con
     for (int g = N_GROUP - 1; g >= 0; g--) {
         const int cnt = pc.grp_count[g];
         if (cnt <= 0) continue;
-        cudaStream_t gs = (g < N_SMALL || h->serial) ? st : h->side[(g - N_SMALL) % N_WCLS];
+        const int g0 = g >> 1;                               // group without the homozygous bit
+        const bool hom = g & 1;
+        cudaStream_t gs = (g0 < N_SMALL || h->serial) ? st : h->side[(g - 2 * N_SMALL) % N_WCLS];
         if (gs != st) CK(cudaStreamWaitEvent(gs, h->ev[5], 0));
         CK(cudaEventRecord(h->gev[g][0], gs));
-        if (g < N_SMALL) small_launch(gs, g, in, out, plan, order + pc.grp_first[g], cnt);
+        if (g0 < N_SMALL) small_launch(gs, g0, hom, in, out, plan, order + pc.grp_first[g], cnt);
         else {
-            const int w = g - N_SMALL;                       // (slots - 1) * N_WBIN + (N_WBIN - 1 - bin)
-            wsc_launch(gs, w / N_WBIN + 1, N_WBIN - 1 - w % N_WBIN, in, out, plan, order + pc.grp_first[g], cnt);
+            const int w = g0 - N_SMALL;                      // (slots - 1) * N_WBIN + (N_WBIN - 1 - bin)
+            wsc_launch(gs, w / N_WBIN + 1, N_WBIN - 1 - w % N_WBIN, hom, in, out, plan, order + pc.grp_first[g], cnt);
         }
         CK(cudaEventRecord(h->gev[g][1], gs));
         grp_used[g] = true;
         S.n_launches++;
         n_small += cnt;
-        const int k = g < N_SMALL ? g : N_SMALL;
+        const int k = g0 < N_SMALL ? g0 : N_SMALL;
         S.n_small[k] += cnt;
         S.io_small[k] += (int64_t)pc.io_grp[g];
+        if (hom) S.n_hom += cnt;
     }
     CK(cudaEventRecord(h->ev[2], st));
     S.cells += (int64_t)pc.cells;
@@ -345,7 +350,7 @@ static int run_resident(vd_handle *h, const BatchDev &in, const OutDev &out, con
             i0 = i1;
         }
     }
-    if (!h->serial) for (int g = N_SMALL; g < N_GROUP; g++) if (grp_used[g]) CK(cudaStreamWaitEvent(st, h->gev[g][1], 0));
+    if (!h->serial) for (int g = 2 * N_SMALL; g < N_GROUP; g++) if (grp_used[g]) CK(cudaStreamWaitEvent(st, h->gev[g][1], 0));
     status_or_kernel<<<296, 256, 0, st>>>(out.status, 4 * (int64_t)n_sc, &((PlanCounters *)h->counters.p)->status_or);
     S.n_launches++;
     publish_kernel<<<1, 64, 0, st>>>((const u32 *)h->counters.p, (u32 *)h->h_counters, (int)(sizeof(PlanCounters) / 4));
@@ -363,7 +368,7 @@ static int run_resident(vd_handle *h, const BatchDev &in, const OutDev &out, con
     for (int g = 0; g < N_GROUP; g++) {       // per-group durations of the short kernels (the warp kernel's overlap)
         if (!grp_used[g]) continue;
         cudaEventElapsedTime(&e_, h->gev[g][0], h->gev[g][1]);
-        S.ms_small[g < N_SMALL ? g : N_SMALL] += e_;
+        S.ms_small[(g >> 1) < N_SMALL ? (g >> 1) : N_SMALL] += e_;
     }
     if (pc.n_bad > 0) return fail(h, VD_E_BADINPUT, "%d malformed superclusters", pc.n_bad);
     return VD_OK;

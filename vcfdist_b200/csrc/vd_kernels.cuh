@@ -34,9 +34,14 @@ __host__ __device__ inline int small_shift(int k) { const int v[N_SMALL] = {Smal
 
 // keys of the order array: (small class, cost bin) first, then the warp kernel's (slots, smem bin);
 // launch groups: one per small class, one per (slots, smem bin)
-constexpr int N_KEY = N_SMALL * N_SBIN + WSC_MAXSLOT * N_WBIN;
-constexpr int N_GROUP = N_SMALL + WSC_MAXSLOT * N_WBIN;
-__host__ __device__ inline int group_of_key(int key) { return key < N_SMALL * N_SBIN ? key / N_SBIN : N_SMALL + (key - N_SMALL * N_SBIN); }
+// Every key / group exists twice: bit 0 = homozygous supercluster (replicate_hom: one alignment instead of four).
+constexpr int N_KEY0 = N_SMALL * N_SBIN + WSC_MAXSLOT * N_WBIN;
+constexpr int N_GROUP0 = N_SMALL + WSC_MAXSLOT * N_WBIN;
+constexpr int N_KEY = 2 * N_KEY0, N_GROUP = 2 * N_GROUP0;
+__host__ __device__ inline int group_of_key(int key) {
+    const int k0 = key >> 1;
+    return 2 * (k0 < N_SMALL * N_SBIN ? k0 / N_SBIN : N_SMALL + (k0 - N_SMALL * N_SBIN)) + (key & 1);
+}
 
 template <int TL, int TR> struct SmallDims {
     static constexpr int SW = (TL + TR + 1 + 3) & ~3;                 // one CSR swap table
@@ -84,7 +89,7 @@ __device__ __forceinline__ int small_need(int Lq, int Lr, int Lt) {
 // One thread per supercluster.  small_lo / small_hi: range of small classes in use (testing hooks
 // VD_SMALL_MIN / VD_SMALL_MAX; hi < lo disables the small kernels).
 __global__ void plan_kernel(BatchDev in, ScPlan *plan, int *list, PlanCounters *cnt, int force_class, int big_class,
-                            int small_lo, int small_hi, int use_wsc) {
+                            int small_lo, int small_hi, int use_wsc, int use_hom) {
     const int sc0 = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = sc0 < in.n_sc;
     const int sc = live ? sc0 : in.n_sc - 1;      // dead lanes recompute the last one and discard it
@@ -106,9 +111,25 @@ __global__ void plan_kernel(BatchDev in, ScPlan *plan, int *list, PlanCounters *
         maxlen = max(maxlen, len);
         if (len < 1) bad = true;
     }
+    // homozygous: query haps 0/1 carry the same variants with the same qualities, truth haps 2/3 the same variants
+    bool hom = use_hom && !bad;
+    for (int side = 0; side < 2 && hom; side++) {
+        const int64_t b1 = in.var_off[4 * (int64_t)sc + 2 * side], b2 = in.var_off[4 * (int64_t)sc + 2 * side + 1];
+        const int64_t e2 = in.var_off[4 * (int64_t)sc + 2 * side + 2];
+        if (b2 - b1 != e2 - b2) { hom = false; break; }
+        for (int64_t j = 0; j < b2 - b1 && hom; j++) {
+            const int64_t x = b1 + j, y = b2 + j;
+            const int64_t ax = in.alt_off[x], ay = in.alt_off[y];
+            const int al = (int)(in.alt_off[x + 1] - ax);
+            hom = in.var_pos[x] == in.var_pos[y] && in.var_type[x] == in.var_type[y] && in.var_rlen[x] == in.var_rlen[y] &&
+                  al == (int)(in.alt_off[y + 1] - ay) &&
+                  (side == 1 || __float_as_uint(in.var_qual[x]) == __float_as_uint(in.var_qual[y]));
+            for (int k = 0; k < al && hom; k++) hom = in.alt_seq[ax + k] == in.alt_seq[ay + k];
+        }
+    }
     unsigned long long cells = 0;
     int cls = big_class;
-    int sbin = -1;                                 // (class, cost bin) of the small kernels
+    int sbin = -1;                                 // key of the short kernels (without the homozygous bit)
     if (bad) cls = CLS_BAD;
     else {
         int need = 0;
@@ -131,11 +152,12 @@ __global__ void plan_kernel(BatchDev in, ScPlan *plan, int *list, PlanCounters *
             }
             if (sbin < 0 && use_wsc) {             // warp-per-supercluster kernel: four flag matrices in shared memory
                 const int ws = wsc_slots(p);
-                const int wb = ws > 0 ? wsc_bin(wsc_layout(p).total) : -1;
+                const int wb = ws > 0 ? wsc_bin(wsc_layout(p, hom).total) : -1;
                 if (wb >= 0) { cls = CLS_TINY; sbin = N_SMALL * N_SBIN + (ws - 1) * N_WBIN + (N_WBIN - 1 - wb); }
             }
         }
     }
+    if (sbin >= 0) sbin = 2 * sbin + (hom ? 1 : 0);
     p.cls = cls | (sbin >= 0 ? (sbin << 8) : 0);
     if (live) plan[sc] = p;
     // warp-aggregated counters: one atomic per warp and counter instead of one per thread
@@ -179,17 +201,18 @@ __global__ void plan_kernel(BatchDev in, ScPlan *plan, int *list, PlanCounters *
     }
 }
 
-// exclusive scan of the per-key counts -> slots of the order array; per-group ranges
+// exclusive scan of the per-key counts -> slots of the order array, group by group (the keys of a
+// launch group are contiguous in the order array)
 __global__ void small_base_kernel(PlanCounters *cnt) {
     if (threadIdx.x != 0) return;
     int o = 0;
-    for (int g = 0; g < N_GROUP; g++) cnt->grp_count[g] = 0;
-    for (int key = 0; key < N_KEY; key++) {
-        const int g = group_of_key(key);
-        if (cnt->grp_count[g] == 0) cnt->grp_first[g] = o;
-        cnt->base[key] = o;
-        o += cnt->n_key[key];
-        cnt->grp_count[g] += cnt->n_key[key];
+    for (int g = 0; g < N_GROUP; g++) {
+        const int g0 = g >> 1, hom = g & 1;
+        const int k0 = g0 < N_SMALL ? g0 * N_SBIN : N_SMALL * N_SBIN + (g0 - N_SMALL);
+        const int nk = g0 < N_SMALL ? N_SBIN : 1;
+        cnt->grp_first[g] = o;
+        for (int k = k0; k < k0 + nk; k++) { cnt->base[2 * k + hom] = o; o += cnt->n_key[2 * k + hom]; }
+        cnt->grp_count[g] = o - cnt->grp_first[g];
     }
 }
 
@@ -293,21 +316,90 @@ small_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, const int
     out.status[4 * (int64_t)sc + ai] = status;
 }
 
+
+// Homozygous superclusters (replicate_hom): one THREAD per supercluster runs Q1T1 and copies the
+// records; shared memory holds two haplotypes and one query map per supercluster.
+template <int TL, int TR> struct SmallHomDims {
+    static constexpr int SW = SmallDims<TL, TR>::SW;
+    static constexpr int RAW = 2 * (3 * TL + TR) + (2 * TR + 2 * SW) + TR;
+    static constexpr int SC_BYTES = ((RAW / 4) & 1) ? RAW : RAW + 4;      // odd number of words
+};
+template <int K> struct SmallHomMem {
+    static constexpr int SMEM = SmallCfg<K>::TPB * (SmallHomDims<SmallCfg<K>::TL, SmallCfg<K>::TR>::SC_BYTES + SmallMem<K>::STRIDE);
+};
+template <int K>
+__global__ void __launch_bounds__(SmallCfg<K>::TPB)
+small_hom_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, const int *__restrict__ order, int count) {
+    typedef SmallCfg<K> C;
+    typedef SmallHomDims<C::TL, C::TR> D;
+    extern __shared__ __align__(16) u8 smem[];
+    const int tid = threadIdx.x;
+    const int slot = blockIdx.x * C::TPB + tid;
+    if (slot >= count) return;
+    const int sc = order[slot];
+    u8 *A = smem + tid * D::SC_BYTES;
+    u8 *qstr = A, *qflg = A + C::TL, *qins = A + 3 * C::TL;
+    int8_t *qptr = (int8_t *)(A + 2 * C::TL);
+    u8 *T = A + 3 * C::TL + C::TR;
+    u8 *tstr = T, *tflg = T + C::TL, *tins = T + 3 * C::TL;
+    int8_t *tptr = (int8_t *)(T + 2 * C::TL);
+    u8 *Q = T + 3 * C::TL + C::TR;
+    int8_t *rptr = (int8_t *)Q, *toQ = (int8_t *)(Q + 2 * C::TR), *toR = (int8_t *)(Q + 2 * C::TR + D::SW);
+    u8 *rflg = Q + C::TR;
+    u8 *rseq = Q + 2 * C::TR + 2 * D::SW;
+    SMemIL mem{smem + C::TPB * D::SC_BYTES + tid * SmallMem<K>::STRIDE};
+
+    const int lr = plan[sc].lr;
+    const int lq = expand_hap<int8_t>(in, sc, 0, qstr, qflg, qptr, rptr, rflg, qins, C::TL);
+    bool ok = lq == plan[sc].len[0];
+    if (ok) ok = build_swsrc<int8_t>(qptr, qflg, lq, toR, lr) && build_swsrc<int8_t>(rptr, rflg, lr, toQ, lq);
+    const int lt = expand_hap<int8_t>(in, sc, 2, tstr, tflg, tptr, nullptr, nullptr, tins, C::TL);
+    ok = ok && lt == plan[sc].len[2];
+    {
+        const u8 *rs = in.rplane_seq + in.ref_off[sc];
+        for (int k = 0; k < lr; k++) rseq[k] = rs[k];
+    }
+    const int64_t oi = 4 * (int64_t)sc;
+    if (!ok) {
+        for (int k = 0; k < 4; k++) { out.status[oi + k] = ST_BAD; out.aln_score[oi + k] = -1; }
+        return;
+    }
+    Hap<int8_t> q{lq, qstr, qflg, qptr, qins};
+    Hap<int8_t> t{lt, tstr, tflg, tptr, tins};
+    QMaps<int8_t> qm{rptr, rflg, toQ, toR};
+    const AlnLayout<int> L = make_layout<int, 2, true>(lq + lr, lt, lr);
+    u32 status = 0;
+    int score, end_plane;
+    forward_scalar<SMemIL, 2, int8_t>(mem, L, q, qm, t, rseq, lr, score, end_plane);
+    const int beg_plane = backward_scalar<SMemIL, 2, int8_t>(mem, L, q, qm, t, rseq, lr, end_plane, status);
+    PFScalar<SMemIL> pfr{&mem, L.oPF, lq + lr, lq};
+    walk_credit<SMemIL, 2, int8_t>(mem, L, pfr, q, qm, t, rseq, lr, beg_plane, end_plane, in, out, sc, 0, status);
+    for (int k = 0; k < 4; k++) {
+        out.aln_score[oi + k] = score;
+        out.aln_end_plane[oi + k] = (u8)end_plane;
+        out.aln_beg_plane[oi + k] = (u8)beg_plane;
+        out.status[oi + k] = status;
+    }
+    replicate_hom(in, out, sc);
+}
+
 template <int K> inline void small_configure_one() {
     cudaFuncSetAttribute(small_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmallMem<K>::SMEM);
+    cudaFuncSetAttribute(small_hom_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmallHomMem<K>::SMEM);
 }
 inline void small_configure() { small_configure_one<0>(); small_configure_one<1>(); }
-template <int K> inline void small_launch_one(cudaStream_t st, const BatchDev &in, const OutDev &out, const ScPlan *plan,
+template <int K> inline void small_launch_one(cudaStream_t st, bool hom, const BatchDev &in, const OutDev &out, const ScPlan *plan,
                                               const int *order, int count) {
-    constexpr int SPB = SmallCfg<K>::TPB / 4;
-    small_kernel<K><<<(count + SPB - 1) / SPB, SmallCfg<K>::TPB, SmallMem<K>::SMEM, st>>>(in, out, plan, order, count);
+    constexpr int TPB = SmallCfg<K>::TPB, SPB = TPB / 4;
+    if (hom) small_hom_kernel<K><<<(count + TPB - 1) / TPB, TPB, SmallHomMem<K>::SMEM, st>>>(in, out, plan, order, count);
+    else small_kernel<K><<<(count + SPB - 1) / SPB, TPB, SmallMem<K>::SMEM, st>>>(in, out, plan, order, count);
 }
-inline void small_launch(cudaStream_t st, int k, const BatchDev &in, const OutDev &out, const ScPlan *plan,
+inline void small_launch(cudaStream_t st, int k, bool hom, const BatchDev &in, const OutDev &out, const ScPlan *plan,
                          const int *order, int count) {
     if (count <= 0) return;
     switch (k) {
-        case 0: small_launch_one<0>(st, in, out, plan, order, count); break;
-        case 1: small_launch_one<1>(st, in, out, plan, order, count); break;
+        case 0: small_launch_one<0>(st, hom, in, out, plan, order, count); break;
+        case 1: small_launch_one<1>(st, hom, in, out, plan, order, count); break;
     }
 }
 

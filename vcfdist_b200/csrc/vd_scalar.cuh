@@ -519,4 +519,30 @@ __device__ void walk_credit(const Mem &mem, const AlnLayout<typename Mem::off_t>
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Homozygous superclusters: when the two query haplotypes carry the same variants (same
+// qualities) and the two truth haplotypes too, the four alignments Q1T1, Q1T2, Q2T1, Q2T2 are
+// the same problem.  It is solved once (as Q1T1: query-hap-1 / truth-hap-1 records of phasing
+// slot 0) and the records are replicated to the other haplotype and the other slot — every
+// (haplotype, slot) pair is written by exactly one of the four alignments (:1037-1048), all
+// with these values.
+// ---------------------------------------------------------------------------------------
+__device__ inline void replicate_hom(const BatchDev &in, const OutDev &out, int sc) {
+    const int64_t nv = in.n_var;
+#pragma unroll 1
+    for (int side = 0; side < 2; side++) {                // query haps 0,1 then truth haps 2,3
+        const int64_t b1 = in.var_off[4 * (int64_t)sc + 2 * side], b2 = in.var_off[4 * (int64_t)sc + 2 * side + 1];
+        const int n = (int)(b2 - b1);
+        for (int j = 0; j < n; j++) {
+            const int64_t s = b1 + j, d = b2 + j;
+            const u8 a = out.assigned[s];
+            const int32_t g = out.sync_group[s], r = out.ref_ed[s], q = out.query_ed[s];
+            const float c = out.callq[s];
+            out.assigned[d] = a; out.sync_group[d] = g; out.ref_ed[d] = r; out.query_ed[d] = q; out.callq[d] = c;
+            out.assigned[nv + s] = a; out.sync_group[nv + s] = g; out.ref_ed[nv + s] = r; out.query_ed[nv + s] = q; out.callq[nv + s] = c;
+            out.assigned[nv + d] = a; out.sync_group[nv + d] = g; out.ref_ed[nv + d] = r; out.query_ed[nv + d] = q; out.callq[nv + d] = c;
+        }
+    }
+}
+
 }  // namespace vd

@@ -38,15 +38,18 @@ struct WscLayout {
     int walk[4];     // path (int16 q, int16 t, u8 flags) + Levenshtein row
     int total;
 };
-__host__ __device__ inline WscLayout wsc_layout(const ScPlan &p) {
+// hom: homozygous supercluster (replicate_hom) - only query hap 0, truth hap 2 and alignment 0 are laid out
+__host__ __device__ inline WscLayout wsc_layout(const ScPlan &p, bool hom = false) {
     WscLayout m;
     int o = 0;
     const int Lr = p.lr;
-    for (int h = 0; h < 4; h++) { m.hap[h] = o; o += wa4(3 * p.len[h] + Lr); }
-    for (int k = 0; k < 2; k++) { m.qm[k] = o; o += wa4(2 * Lr + 2 * (p.len[k] + Lr + 1)); }
+    for (int h = 0; h < 4; h++) { m.hap[h] = o; if (!hom || !(h & 1)) o += wa4(3 * p.len[h] + Lr); }
+    for (int k = 0; k < 2; k++) { m.qm[k] = o; if (!hom || k == 0) o += wa4(2 * Lr + 2 * (p.len[k] + Lr + 1)); }
     m.rseq = o; o += wa4(Lr);
-    for (int k = 0; k < 2; k++) { m.tinf[k] = o; o += wa4(2 * p.len[2 + k]); }
+    for (int k = 0; k < 2; k++) { m.tinf[k] = o; if (!hom || k == 0) o += wa4(2 * p.len[2 + k]); }
     for (int ai = 0; ai < 4; ai++) {
+        m.F[ai] = m.walk[ai] = o;
+        if (hom && ai > 0) continue;
         const int N = p.len[ai >> 1] + Lr, Lt = p.len[2 + (ai & 1)];
         m.F[ai] = o; o += wa4(N * Lt);
         m.walk[ai] = o;
@@ -77,7 +80,8 @@ struct PFWarp {      // path flags, [column][row], QUERY rows first
 // PAR = true:  one block per supercluster, warp w runs alignment w (big bins: few superclusters, occupancy is
 //               shared-memory-limited, so the four warps share one supercluster's footprint and its latency
 //               drops fourfold).
-template <int S, bool PAR>
+// HOM: homozygous superclusters (always !PAR): alignment Q1T1 only, then replicate_hom.
+template <int S, bool PAR, bool HOM>
 __global__ void __launch_bounds__(WSC_TPB)
 wsc_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, const int *__restrict__ order, int count, int warp_bytes) {
     extern __shared__ __align__(16) u8 smem[];
@@ -89,7 +93,8 @@ wsc_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, const int *
     const bool lead = !PAR || warp == 0;            // the warp that runs the single-lane phases of the supercluster
     const int sc = order[slot];
     const ScPlan p = plan[sc];
-    const WscLayout M = wsc_layout(p);
+    static_assert(!(PAR && HOM), "homozygous superclusters run one warp per supercluster");
+    const WscLayout M = wsc_layout(p, HOM);
     u8 *base = PAR ? smem : smem + warp * warp_bytes;
     const int Lr = p.lr;
     auto hstr = [&](int h) { return base + M.hap[h]; };
@@ -109,11 +114,13 @@ wsc_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, const int *
     } else if (lane < 4) {
         const int h = lane;
         const bool isq = h < 2;
+        if (HOM && (h & 1)) { /* same as haplotype h-1 */ } else {
         const int len = expand_hap<int8_t>(in, sc, h, hstr(h), hflg(h), hptr(h), isq ? qrptr(h) : nullptr,
                                            isq ? qrflg(h) : nullptr, hins(h), p.len[h]);
         ok = len == p.len[h];
         if (ok && isq) ok = build_swsrc<int8_t>(hptr(h), hflg(h), len, qtoR(h), Lr) &&
                             build_swsrc<int8_t>(qrptr(h), qrflg(h), Lr, qtoQ(h), len);
+        }
     } else {
         const u8 *rs = in.rplane_seq + in.ref_off[sc];
         for (int k = lane - 4; k < Lr; k += 28) rseq[k] = rs[k];
@@ -131,7 +138,7 @@ wsc_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, const int *
         return;
     }
     __syncwarp();
-    for (int k = 0; k < 2; k++) {                    // truth columns: base | tok << 8   (:338-339, :367-368)
+    for (int k = 0; k < (HOM ? 1 : 2); k++) {        // truth columns: base | tok << 8   (:338-339, :367-368)
         const u8 *ts = hstr(2 + k), *tf = hflg(2 + k);
         u16 *ti = (u16 *)(base + M.tinf[k]);
         for (int c = PAR ? (int)threadIdx.x : lane; c < p.len[2 + k]; c += PAR ? WSC_TPB : 32) {
@@ -163,7 +170,7 @@ wsc_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, const int *
     u32 my_status = 0;
 
     // ---- phase 2: the four alignments ----
-    for (int ai = PAR ? warp : 0; ai < (PAR ? warp + 1 : 4); ai++) {
+    for (int ai = PAR ? warp : 0; ai < (PAR ? warp + 1 : (HOM ? 1 : 4)); ai++) {
         const int qh = ai >> 1, th = 2 + (ai & 1);
         const int Lq = p.len[qh], Lt = p.len[th], N = Lq + Lr;
         const u8 *qstr = hstr(qh), *qflg = hflg(qh);
@@ -408,7 +415,7 @@ wsc_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, const int *
     }
 
     // ---- phase 3: walk + credit, one lane per alignment ----
-    if (PAR ? lane == 0 : lane < 4) {
+    if (PAR ? lane == 0 : lane < (HOM ? 1 : 4)) {
         const int ai = PAR ? warp : lane, qh = ai >> 1, th = 2 + (ai & 1);
         const int Lq = p.len[qh], Lt = p.len[th], N = Lq + Lr;
         Hap<int8_t> q{Lq, hstr(qh), hflg(qh), hptr(qh), hins(qh)};
@@ -423,10 +430,13 @@ wsc_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, const int *
         u32 status = my_status;
         walk_credit<SMemIL, 2, int8_t>(mem, L, pfr, q, qm, t, rseq, Lr, my_beg, my_end, in, out, sc, ai, status);
         const int64_t oi = 4 * (int64_t)sc + ai;
-        out.aln_score[oi] = my_score;
-        out.aln_end_plane[oi] = (u8)my_end;
-        out.aln_beg_plane[oi] = (u8)my_beg;
-        out.status[oi] = status;
+        for (int k = 0; k < (HOM ? 4 : 1); k++) {
+            out.aln_score[oi + k] = my_score;
+            out.aln_end_plane[oi + k] = (u8)my_end;
+            out.aln_beg_plane[oi + k] = (u8)my_beg;
+            out.status[oi + k] = status;
+        }
+        if constexpr (HOM) replicate_hom(in, out, sc);
     }
 }
 
@@ -435,24 +445,26 @@ wsc_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, const int *
 #endif
 constexpr int WSC_PAR_MINBIN = VD_WSC_PAR_MINBIN;      // bins >= 10 KB per supercluster: one block per supercluster, one warp per alignment
 template <int S> inline void wsc_configure_one() {
-    cudaFuncSetAttribute(wsc_kernel<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (WSC_TPB / 32) * wsc_bin_cap(WSC_PAR_MINBIN > 0 ? WSC_PAR_MINBIN - 1 : 0));
-    cudaFuncSetAttribute(wsc_kernel<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wsc_bin_cap(N_WBIN - 1));
+    cudaFuncSetAttribute(wsc_kernel<S, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (WSC_TPB / 32) * wsc_bin_cap(WSC_PAR_MINBIN > 0 ? WSC_PAR_MINBIN - 1 : 0));
+    cudaFuncSetAttribute(wsc_kernel<S, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wsc_bin_cap(N_WBIN - 1));
+    cudaFuncSetAttribute(wsc_kernel<S, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (WSC_TPB / 32) * wsc_bin_cap(N_WBIN - 1));
 }
 inline void wsc_configure() { wsc_configure_one<1>(); wsc_configure_one<2>(); wsc_configure_one<3>(); wsc_configure_one<4>(); }
-template <int S> inline void wsc_launch_one(cudaStream_t st, int bin, const BatchDev &in, const OutDev &out, const ScPlan *plan,
+template <int S> inline void wsc_launch_one(cudaStream_t st, int bin, bool hom, const BatchDev &in, const OutDev &out, const ScPlan *plan,
                                             const int *order, int count) {
     const int wb = wsc_bin_cap(bin), wpb = WSC_TPB / 32;
-    if (bin >= WSC_PAR_MINBIN) wsc_kernel<S, true><<<count, WSC_TPB, wb, st>>>(in, out, plan, order, count, wb);
-    else wsc_kernel<S, false><<<(count + wpb - 1) / wpb, WSC_TPB, wpb * wb, st>>>(in, out, plan, order, count, wb);
+    if (hom) wsc_kernel<S, false, true><<<(count + wpb - 1) / wpb, WSC_TPB, wpb * wb, st>>>(in, out, plan, order, count, wb);
+    else if (bin >= WSC_PAR_MINBIN) wsc_kernel<S, true, false><<<count, WSC_TPB, wb, st>>>(in, out, plan, order, count, wb);
+    else wsc_kernel<S, false, false><<<(count + wpb - 1) / wpb, WSC_TPB, wpb * wb, st>>>(in, out, plan, order, count, wb);
 }
-inline void wsc_launch(cudaStream_t st, int slots, int bin, const BatchDev &in, const OutDev &out, const ScPlan *plan,
+inline void wsc_launch(cudaStream_t st, int slots, int bin, bool hom, const BatchDev &in, const OutDev &out, const ScPlan *plan,
                        const int *order, int count) {
     if (count <= 0) return;
     switch (slots) {
-        case 1: wsc_launch_one<1>(st, bin, in, out, plan, order, count); break;
-        case 2: wsc_launch_one<2>(st, bin, in, out, plan, order, count); break;
-        case 3: wsc_launch_one<3>(st, bin, in, out, plan, order, count); break;
-        case 4: wsc_launch_one<4>(st, bin, in, out, plan, order, count); break;
+        case 1: wsc_launch_one<1>(st, bin, hom, in, out, plan, order, count); break;
+        case 2: wsc_launch_one<2>(st, bin, hom, in, out, plan, order, count); break;
+        case 3: wsc_launch_one<3>(st, bin, hom, in, out, plan, order, count); break;
+        case 4: wsc_launch_one<4>(st, bin, hom, in, out, plan, order, count); break;
     }
 }
 
