@@ -16,5 +16,10 @@ for f in Out.FIELDS:
     t_, a_ = pin(getattr(ho,f)); keep.append(t_); setattr(ho,f,a_)
 e = capi.Engine(0)
 for i in range(3): e.run(bp, ho)
-os.environ["VD_TRACE"]="1"
-t=time.perf_counter(); e.run(bp, ho); print("e2e ms", (time.perf_counter()-t)*1e3)
+ts=[]
+for i in range(7):
+    t=time.perf_counter(); e.run(bp, ho); ts.append((time.perf_counter()-t)*1e3)
+tag = " ".join(f"{k}={v}" for k, v in os.environ.items() if k.startswith("VD_"))
+print(f"[{tag}] e2e ms median {sorted(ts)[3]:.2f} min {min(ts):.2f} dev {e.stats()['ms_total']:.2f}")
+if os.environ.get("TRACE"):
+    os.environ["VD_TRACE"]="1"; e.run(bp, ho)

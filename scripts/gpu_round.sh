@@ -19,15 +19,14 @@ for w in $what; do
                timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv \
                  --log-file "$out/launches_wgs_sv.csv" python bench.py --workload wgs_sv --n-sc 400000 --steps 1 --warmup 3 --no-cpu-baseline > "$out/launches_wgs_sv.log" 2>&1
                echo "launches rc=$?" ;;
-    full_small) timeout 900 ncu --set full --clock-control none --import-source on -k regex:small_kernel -s 6 -c 2 \
+    full_small) timeout 900 ncu --set full --clock-control none --import-source on -k regex:'small_kernel|small_hom_kernel' -s 12 -c 4 \
                  -f -o "$out/prof_small" python bench.py --steps 1 --warmup 3 --no-cpu-baseline > "$out/prof_small.log" 2>&1; echo "full_small rc=$?"
                ncu -i "$out/prof_small.ncu-rep" --page raw --csv > "$out/prof_small_raw.csv" 2>/dev/null
                ncu -i "$out/prof_small.ncu-rep" --page details > "$out/prof_small_details.txt" 2>/dev/null ;;
-    full_wsc)  timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:'wsc_kernel<\(int\)1>' -s 9 -c 2 \
+    full_wsc)  timeout 1200 ncu --set full --clock-control none -k regex:wsc_kernel -c 64 \
                  -f -o "$out/prof_wsc" python bench.py --steps 1 --warmup 3 --no-cpu-baseline > "$out/prof_wsc.log" 2>&1; echo "full_wsc rc=$?"
                ncu -i "$out/prof_wsc.ncu-rep" --page raw --csv > "$out/prof_wsc_raw.csv" 2>/dev/null
-               ncu -i "$out/prof_wsc.ncu-rep" --page details > "$out/prof_wsc_details.txt" 2>/dev/null
-               ncu -i "$out/prof_wsc.ncu-rep" --page source --csv > "$out/prof_wsc_source.csv" 2>/dev/null ;;
+               rm -f "$out/prof_wsc.ncu-rep" ;;
     full_wave) timeout 900 ncu --set full --clock-control none --import-source on -k regex:'wave_fwdb_kernel|wave_fwd_kernel|wave_sbwd_kernel|wave_bwd_kernel|wave_walk_kernel' -s 40 -c 12 \
                  -f -o "$out/prof_wave" python bench.py --workload wgs_sv --n-sc 400000 --steps 1 --warmup 3 --no-cpu-baseline > "$out/prof_wave.log" 2>&1; echo "full_wave rc=$?"
                ncu -i "$out/prof_wave.ncu-rep" --page raw --csv > "$out/prof_wave_raw.csv" 2>/dev/null

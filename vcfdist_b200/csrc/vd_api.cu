@@ -13,6 +13,7 @@
 #include <string>
 #include <vector>
 
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include "vd_kernels.cuh"
@@ -64,9 +65,10 @@ struct vd_handle {
         bool out_pending = false;
     } stage[2];
     cudaStream_t s_in = nullptr, s_out = nullptr;
+    int ramp = 1;                   // VD_RAMP=0: uniform chunks
     int64_t chunk_sc = 1048576;      // superclusters per pipeline chunk (VD_CHUNK_SC)
     // work
-    DevBuf plan, list, mlist, need_dense, counters, bytes, offs, cubtmp, slab, hap_ok, wave_desc;
+    DevBuf ranks, ranks_out, iota, plan, list, mlist, need_dense, counters, bytes, offs, cubtmp, slab, hap_ok, wave_desc;
     PlanCounters *h_counters = nullptr;     // pinned + mapped: written by publish_kernel, never by a copy engine
     WaveItems *h_witems = nullptr;          // (a small D2H memcpy would queue behind the bulk result copies of vd_run)
 };
@@ -120,6 +122,7 @@ extern "C" int vd_create(int device, int64_t scratch_bytes, vd_handle **out) {
     if (const char *v = getenv("VD_WSC")) h->use_wsc = atoi(v);
     if (const char *v = getenv("VD_SERIAL")) h->serial = atoi(v);
     if (const char *v = getenv("VD_HOM")) h->use_hom = atoi(v);
+    if (const char *v = getenv("VD_RAMP")) h->ramp = atoi(v);
     if (const char *df = getenv("VD_DENSE_FWD")) h->banded_fwd = atoi(df) == 0;
     if (const char *db = getenv("VD_DENSE_BWD")) h->sparse_bwd = atoi(db) == 0;
     if (const char *sm = getenv("VD_SBWD_MIN_CLASS")) h->sbwd_min_class = atoi(sm);
@@ -151,7 +154,7 @@ extern "C" void vd_destroy(vd_handle *h) {
     }
     if (h->s_in) cudaStreamDestroy(h->s_in);
     if (h->s_out) cudaStreamDestroy(h->s_out);
-    DevBuf *bufs[] = {&h->plan, &h->list, &h->mlist, &h->need_dense, &h->counters, &h->bytes, &h->offs,
+    DevBuf *bufs[] = {&h->ranks, &h->ranks_out, &h->iota, &h->plan, &h->list, &h->mlist, &h->need_dense, &h->counters, &h->bytes, &h->offs,
                       &h->cubtmp, &h->slab, &h->hap_ok, &h->wave_desc};
     for (DevBuf *b : bufs) b->release();
     if (h->h_counters) cudaFreeHost(h->h_counters);
@@ -206,10 +209,19 @@ static int run_resident(vd_handle *h, const BatchDev &in, const OutDev &out, con
     int *order = (int *)h->mlist.p;                 // class- and cost-sorted small superclusters
     PlanCounters *dcnt = (PlanCounters *)h->counters.p;
 
-    plan_kernel<<<(n_sc + 255) / 256, 256, 0, st>>>(in, plan, list, dcnt, h->force_class, kBigClass, h->small_lo, h->small_hi, h->use_wsc, h->use_hom);
+    CK(h->ranks.ensure((size_t)n_sc)); CK(h->ranks_out.ensure((size_t)n_sc)); CK(h->iota.ensure(4 * (size_t)n_sc));
+    plan_kernel<<<(n_sc + 255) / 256, 256, 0, st>>>(in, plan, list, (u8 *)h->ranks.p, (int *)h->iota.p, dcnt, h->force_class, kBigClass,
+                                                    h->small_lo, h->small_hi, h->use_wsc, h->use_hom);
     small_base_kernel<<<1, 32, 0, st>>>(dcnt);
-    small_fill_kernel<<<(n_sc + 255) / 256, 256, 0, st>>>(plan, n_sc, dcnt, order);
-    S.n_launches += 3;
+    {   // order[] = supercluster indices stably sorted by rank (non-short superclusters sort to the end)
+        size_t tmp = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp, (const u8 *)h->ranks.p, (u8 *)h->ranks_out.p, (const int *)h->iota.p, order,
+                                        n_sc, 0, 8, st);
+        CK(h->cubtmp.ensure(tmp));
+        cub::DeviceRadixSort::SortPairs(h->cubtmp.p, tmp, (const u8 *)h->ranks.p, (u8 *)h->ranks_out.p, (const int *)h->iota.p, order,
+                                        n_sc, 0, 8, st);
+    }
+    S.n_launches += 5;
     publish_kernel<<<1, 64, 0, st>>>((const u32 *)dcnt, (u32 *)h->h_counters, (int)(sizeof(PlanCounters) / 4));
     CK(cudaEventRecord(h->ev[1], st));
     CK(cudaStreamSynchronize(st));          // counters are now on the host
@@ -422,9 +434,9 @@ extern "C" int vd_run(vd_handle *h, const vd_batch_in *in, vd_batch_out *out) {
     {
         int64_t s0 = 0;
         const int64_t ramp[2] = {CH / 4, CH / 2};
-        for (int k = 0; k < 2 && n_sc - s0 > 2 * CH && ramp[k] > 0; k++) { s0 += ramp[k]; cut.push_back(s0); }
+        for (int k = 0; k < 2 && h->ramp && n_sc - s0 > 2 * CH && ramp[k] > 0; k++) { s0 += ramp[k]; cut.push_back(s0); }
         while (n_sc - s0 > CH + CH / 2) { s0 += CH; cut.push_back(s0); }
-        if (n_sc - s0 > CH / 2 && CH / 4 > 0) { s0 = n_sc - CH / 4; cut.push_back(s0); }
+        if (h->ramp && n_sc - s0 > CH / 2 && CH / 4 > 0) { s0 = n_sc - CH / 4; cut.push_back(s0); }
         cut.push_back(n_sc);
     }
     const int n_chunks = (int)cut.size() - 1;

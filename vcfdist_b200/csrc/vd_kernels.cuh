@@ -34,13 +34,23 @@ __host__ __device__ inline int small_shift(int k) { const int v[N_SMALL] = {Smal
 
 // keys of the order array: (small class, cost bin) first, then the warp kernel's (slots, smem bin);
 // launch groups: one per small class, one per (slots, smem bin)
-// Every key / group exists twice: bit 0 = homozygous supercluster (replicate_hom: one alignment instead of four).
-constexpr int N_KEY0 = N_SMALL * N_SBIN + WSC_MAXSLOT * N_WBIN;
+// Launch groups and ranks.  A group is one kernel launch: (small class k, homozygous bit) for the
+// thread-per-alignment kernels, (slots, shared-memory bin, homozygous bit) for the warp kernel.
+// The order array is the batch STABLY sorted by rank (cub radix sort), rank = the group's position
+// with the cost bin of the small classes as minor key, so that a group is a contiguous range, the
+// lanes of a warp get similar costs, and superclusters keep their batch order inside a rank (their
+// inputs stay neighbours in HBM).
 constexpr int N_GROUP0 = N_SMALL + WSC_MAXSLOT * N_WBIN;
-constexpr int N_KEY = 2 * N_KEY0, N_GROUP = 2 * N_GROUP0;
-__host__ __device__ inline int group_of_key(int key) {
-    const int k0 = key >> 1;
-    return 2 * (k0 < N_SMALL * N_SBIN ? k0 / N_SBIN : N_SMALL + (k0 - N_SMALL * N_SBIN)) + (key & 1);
+constexpr int N_GROUP = 2 * N_GROUP0;
+constexpr int N_KEY = 2 * N_SMALL * N_SBIN + 2 * WSC_MAXSLOT * N_WBIN;      // ranks
+constexpr int RANK_NONE = 255;                                              // not a short supercluster
+static_assert(N_KEY < RANK_NONE, "ranks are sorted as 8-bit keys");
+// g0: group without the homozygous bit (small class k, or N_SMALL + (slots-1)*N_WBIN + reversed bin)
+__host__ __device__ inline int rank_of(int g0, int hom, int sbin) {
+    return g0 < N_SMALL ? (2 * g0 + hom) * N_SBIN + sbin : 2 * N_SMALL * N_SBIN + 2 * (g0 - N_SMALL) + hom;
+}
+__host__ __device__ inline int group_of_key(int rank) {
+    return rank < 2 * N_SMALL * N_SBIN ? rank / N_SBIN : 2 * N_SMALL + (rank - 2 * N_SMALL * N_SBIN);
 }
 
 template <int TL, int TR> struct SmallDims {
@@ -60,9 +70,7 @@ struct PlanCounters {
     unsigned long long cells;
     unsigned long long cells_list;
     unsigned status_or;
-    int n_key[N_KEY];                  // superclusters per key
-    int cursor[N_KEY];
-    int base[N_KEY];                   // first slot of each key in the order array
+    int n_key[N_KEY];                  // superclusters per rank
     int grp_first[N_GROUP], grp_count[N_GROUP];
     unsigned long long io_grp[N_GROUP];     // algorithmic input+output bytes per launch group
 };
@@ -88,8 +96,8 @@ __device__ __forceinline__ int small_need(int Lq, int Lr, int Lt) {
 
 // One thread per supercluster.  small_lo / small_hi: range of small classes in use (testing hooks
 // VD_SMALL_MIN / VD_SMALL_MAX; hi < lo disables the small kernels).
-__global__ void plan_kernel(BatchDev in, ScPlan *plan, int *list, PlanCounters *cnt, int force_class, int big_class,
-                            int small_lo, int small_hi, int use_wsc, int use_hom) {
+__global__ void plan_kernel(BatchDev in, ScPlan *plan, int *list, u8 *ranks, int *iota, PlanCounters *cnt, int force_class,
+                            int big_class, int small_lo, int small_hi, int use_wsc, int use_hom) {
     const int sc0 = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = sc0 < in.n_sc;
     const int sc = live ? sc0 : in.n_sc - 1;      // dead lanes recompute the last one and discard it
@@ -129,7 +137,7 @@ __global__ void plan_kernel(BatchDev in, ScPlan *plan, int *list, PlanCounters *
     }
     unsigned long long cells = 0;
     int cls = big_class;
-    int sbin = -1;                                 // key of the short kernels (without the homozygous bit)
+    int sbin = -1;                                 // rank of the short kernels
     if (bad) cls = CLS_BAD;
     else {
         int need = 0;
@@ -146,20 +154,19 @@ __global__ void plan_kernel(BatchDev in, ScPlan *plan, int *list, PlanCounters *
                     cls = CLS_TINY;
                     const int lg = 31 - __clz((int)cells | 1);
                     // bins are laid out most expensive first (the tail of a launch is its cheap work)
-                    sbin = k * N_SBIN + (N_SBIN - 1 - min(max(lg - small_shift(k), 0), N_SBIN - 1));
+                    sbin = rank_of(k, hom, N_SBIN - 1 - min(max(lg - small_shift(k), 0), N_SBIN - 1));
                     break;
                 }
             }
             if (sbin < 0 && use_wsc) {             // warp-per-supercluster kernel: four flag matrices in shared memory
                 const int ws = wsc_slots(p);
                 const int wb = ws > 0 ? wsc_bin(wsc_layout(p, hom).total) : -1;
-                if (wb >= 0) { cls = CLS_TINY; sbin = N_SMALL * N_SBIN + (ws - 1) * N_WBIN + (N_WBIN - 1 - wb); }
+                if (wb >= 0) { cls = CLS_TINY; sbin = rank_of(N_SMALL + (ws - 1) * N_WBIN + (N_WBIN - 1 - wb), hom, 0); }
             }
         }
     }
-    if (sbin >= 0) sbin = 2 * sbin + (hom ? 1 : 0);
     p.cls = cls | (sbin >= 0 ? (sbin << 8) : 0);
-    if (live) plan[sc] = p;
+    if (live) { plan[sc] = p; ranks[sc] = (u8)(sbin >= 0 ? sbin : RANK_NONE); iota[sc] = sc; }
     // warp-aggregated counters: one atomic per warp and counter instead of one per thread
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -201,33 +208,17 @@ __global__ void plan_kernel(BatchDev in, ScPlan *plan, int *list, PlanCounters *
     }
 }
 
-// exclusive scan of the per-key counts -> slots of the order array, group by group (the keys of a
-// launch group are contiguous in the order array)
+// group ranges in the rank-sorted order array
 __global__ void small_base_kernel(PlanCounters *cnt) {
     if (threadIdx.x != 0) return;
     int o = 0;
-    for (int g = 0; g < N_GROUP; g++) {
-        const int g0 = g >> 1, hom = g & 1;
-        const int k0 = g0 < N_SMALL ? g0 * N_SBIN : N_SMALL * N_SBIN + (g0 - N_SMALL);
-        const int nk = g0 < N_SMALL ? N_SBIN : 1;
-        cnt->grp_first[g] = o;
-        for (int k = k0; k < k0 + nk; k++) { cnt->base[2 * k + hom] = o; o += cnt->n_key[2 * k + hom]; }
-        cnt->grp_count[g] = o - cnt->grp_first[g];
+    for (int g = 0; g < N_GROUP; g++) cnt->grp_count[g] = 0;
+    for (int r = 0; r < N_KEY; r++) {
+        const int g = group_of_key(r);
+        if (cnt->grp_count[g] == 0) cnt->grp_first[g] = o;
+        o += cnt->n_key[r];
+        cnt->grp_count[g] += cnt->n_key[r];
     }
-}
-
-// class- and cost-sorted order of the small superclusters
-__global__ void small_fill_kernel(const ScPlan *plan, int n_sc, PlanCounters *cnt, int *order) {
-    const int sc = blockIdx.x * blockDim.x + threadIdx.x;
-    const int cls = sc < n_sc ? plan[sc].cls : CLS_BAD;
-    const int key = (cls & 0xff) == CLS_TINY ? (cls >> 8) : -1;
-    const unsigned peers = __match_any_sync(0xffffffffu, key);
-    if (key < 0) return;
-    const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
-    int slot = 0;
-    if (lane == leader) slot = cnt->base[key] + atomicAdd(&cnt->cursor[key], __popc(peers));
-    slot = __shfl_sync(peers, slot, leader);
-    order[slot + __popc(peers & ((1u << lane) - 1))] = sc;
 }
 
 // ---- fused small kernel ---------------------------------------------------------------------
