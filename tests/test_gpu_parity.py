@@ -109,6 +109,24 @@ def test_homozygous_replication_matches_full_computation():
         e.close()
 
 
+def test_rplane_string_differs_from_fasta(engine):
+    """REF-plane string given separately (query-hap-1 REF alleles that differ from the FASTA,
+    src/dist.cpp:1784-1792): every kernel family must read it, and the no-variant shortcut of the
+    warp kernel must not be taken."""
+    b = synth.adversarial(41, 1500, max_len=40)
+    rng = np.random.default_rng(3)
+    rp = b.ref_seq.copy()
+    idx = rng.integers(0, len(rp), len(rp) // 15)
+    rp[idx] = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, len(idx))]
+    b2 = Batch(ref_off=b.ref_off, ref_seq=b.ref_seq, var_off=b.var_off, var_pos=b.var_pos, var_rlen=b.var_rlen,
+               var_type=b.var_type, alt_off=b.alt_off, alt_seq=b.alt_seq, var_qual=b.var_qual, max_qual=b.max_qual,
+               rplane_seq=rp)
+    check_vs_oracle(engine, b2)
+    e = engine_with(VD_SMALL_MAX=-1)
+    check_vs_oracle(e, b2)
+    e.close()
+
+
 def test_warp_kernel_shapes():
     """Warp-per-supercluster kernel on its own: one to four register slots (<= 32 .. <= 128 rows),
     several swap sources per row (insertions, adjacent deletions), every shared-memory bin."""

@@ -169,8 +169,21 @@ wsc_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, const int *
     int my_score = 0, my_end = 0, my_beg = 0;
     u32 my_status = 0;
 
+    // An alignment whose query and truth haplotypes both carry no variant compares the window with
+    // itself: score 0, both path ends on the QUERY plane, no status bit, no variant to credit (the
+    // Q1T1 alignment of every heterozygous site).  trivial: bit ai.  Not used when the REF plane has its
+    // own string (rplane_seq): its sections could then differ from the truth and raise WARN status bits.
+    unsigned trivial = 0;
+    if (in.rplane_seq == in.ref_seq) {
+        const int64_t *vo = in.var_off + 4 * (int64_t)sc;
+        const int64_t o0 = vo[0], o1 = vo[1], o2 = vo[2], o3 = vo[3], o4 = vo[4];
+        const bool eq0 = o1 == o0, eq1 = o2 == o1, et0 = o3 == o2, et1 = o4 == o3;
+        trivial = (eq0 && et0 ? 1u : 0u) | (eq0 && et1 ? 2u : 0u) | (eq1 && et0 ? 4u : 0u) | (eq1 && et1 ? 8u : 0u);
+    }
+
     // ---- phase 2: the four alignments ----
     for (int ai = PAR ? warp : 0; ai < (PAR ? warp + 1 : (HOM ? 1 : 4)); ai++) {
+        if ((trivial >> ai) & 1) continue;          // my_score = my_end = my_beg = my_status = 0
         const int qh = ai >> 1, th = 2 + (ai & 1);
         const int Lq = p.len[qh], Lt = p.len[th], N = Lq + Lr;
         const u8 *qstr = hstr(qh), *qflg = hflg(qh);
@@ -428,7 +441,8 @@ wsc_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, const int *
         L.oPQ = 0; L.oPT = wa4(2 * np); L.oPS = 2 * wa4(2 * np); L.oLev = L.oPS + wa4(np); L.total = 0;
         PFWarp pfr{base + M.F[ai], N, Lq};
         u32 status = my_status;
-        walk_credit<SMemIL, 2, int8_t>(mem, L, pfr, q, qm, t, rseq, Lr, my_beg, my_end, in, out, sc, ai, status);
+        if (!((trivial >> ai) & 1))
+            walk_credit<SMemIL, 2, int8_t>(mem, L, pfr, q, qm, t, rseq, Lr, my_beg, my_end, in, out, sc, ai, status);
         const int64_t oi = 4 * (int64_t)sc + ai;
         for (int k = 0; k < (HOM ? 4 : 1); k++) {
             out.aln_score[oi + k] = my_score;
