@@ -16,6 +16,7 @@ if os.environ.get("VD_LIB"):
 e = capi.Engine(0)
 tag = " ".join(f"{k}={v}" for k, v in os.environ.items() if k.startswith("VD_"))
 for i in range(reps):
+    if i == reps - 1 and os.environ.get("TRACE"): os.environ["VD_TRACE"] = "1"
     t = time.time(); e.run(b); dt = time.time() - t
     st = e.stats()
     if i == reps - 1:

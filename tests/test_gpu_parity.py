@@ -166,10 +166,13 @@ def test_divergent_sv_pairs(engine, length, div):
 
 
 def test_dense_paths_match_banded_and_sparse(engine):
-    """VD_DENSE_FWD / VD_DENSE_BWD select the dense register-blocked sweeps for every alignment."""
-    b = Batch.concat([synth.sv_pairs(7, 2, 800, divergence=0.05), synth.wgs_like(8, 300, sv_frac=0.1, sv_max=900)])
+    """VD_DENSE_FWD / VD_DENSE_BWD select the dense register-blocked sweeps for every alignment,
+    VD_SPARSE_BWD the frontier backward kernel instead of the banded one."""
+    b = Batch.concat([synth.sv_pairs(7, 2, 800, divergence=0.05), synth.wgs_like(8, 300, sv_frac=0.1, sv_max=900),
+                      synth.sv_pairs(9, 2, 2600, divergence=0.02)])
     want = capi.oracle_run(b)
-    for env in ({"VD_DENSE_FWD": "1"}, {"VD_DENSE_BWD": "1"}, {"VD_DENSE_FWD": "1", "VD_DENSE_BWD": "1"}):
+    for env in ({"VD_DENSE_FWD": "1"}, {"VD_DENSE_BWD": "1"}, {"VD_DENSE_FWD": "1", "VD_DENSE_BWD": "1"},
+                {"VD_SPARSE_BWD": "1"}):
         os.environ.update(env)
         try:
             e = capi.Engine(0)

@@ -49,6 +49,7 @@ struct vd_handle {
     vd_stats stats = {};
     unsigned stats_status_or = 0;   // OR of every status word of the last call
     bool banded_fwd = true;         // VD_DENSE_FWD=1 skips the banded forward sweep (testing)
+    bool banded_bwd = true;         // VD_SPARSE_BWD=1: frontier kernel instead of the banded backward sweep (testing)
     bool sparse_bwd = true;         // VD_DENSE_BWD=1 selects the dense backward sweep (testing)
     int sbwd_min_class = 4;         // VD_SBWD_MIN_CLASS: wave classes below it use the dense backward sweep
     int force_class = -1;           // VD_FORCE_CLASS env: testing hook (1 wave, 2 scalar slab)
@@ -125,6 +126,7 @@ extern "C" int vd_create(int device, int64_t scratch_bytes, vd_handle **out) {
     if (const char *v = getenv("VD_RAMP")) h->ramp = atoi(v);
     if (const char *df = getenv("VD_DENSE_FWD")) h->banded_fwd = atoi(df) == 0;
     if (const char *db = getenv("VD_DENSE_BWD")) h->sparse_bwd = atoi(db) == 0;
+    if (const char *v = getenv("VD_SPARSE_BWD")) h->banded_bwd = atoi(v) == 0;
     if (const char *sm = getenv("VD_SBWD_MIN_CLASS")) h->sbwd_min_class = atoi(sm);
     if (const char *cs = getenv("VD_CHUNK_SC")) h->chunk_sc = atoll(cs) > 0 ? atoll(cs) : h->chunk_sc;
     cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking);
@@ -331,7 +333,8 @@ static int run_resident(vd_handle *h, const BatchDev &in, const OutDev &out, con
                     CK(cudaEventRecord(h->sev[c][0], ss));
                     wave_launch(ss, WA, c, cb.b[c], hwi.count[c], true, true, h->banded_fwd ? (int *)h->need_dense.p : nullptr);
                     CK(cudaEventRecord(h->sev[c][1], ss));
-                    wave_launch(ss, WA, c, cb.b[c], hwi.count[c], false, h->sparse_bwd && c >= h->sbwd_min_class);
+                    wave_launch(ss, WA, c, cb.b[c], hwi.count[c], false, h->sparse_bwd && c >= h->sbwd_min_class,
+                                h->banded_fwd ? (int *)h->need_dense.p : nullptr, h->banded_bwd);
                     CK(cudaEventRecord(h->sev[c][2], ss));
                     if (ss != st) CK(cudaStreamWaitEvent(st, h->sev[c][2], 0));
                     S.n_launches += 2;
@@ -349,6 +352,15 @@ static int run_resident(vd_handle *h, const BatchDev &in, const OutDev &out, con
                     cudaEventElapsedTime(&a_, h->sev[c][0], h->sev[c][1]);
                     cudaEventElapsedTime(&b_, h->sev[c][1], h->sev[c][2]);
                     ms_fwd += a_; ms_bwd += b_;
+                    if (trace) {
+                        int nd = 0;
+                        if (h->banded_fwd && c >= 4) {
+                            std::vector<int> v(hwi.count[c]);
+                            cudaMemcpy(v.data(), (int *)h->need_dense.p + cb.b[c], 4 * (size_t)hwi.count[c], cudaMemcpyDeviceToHost);
+                            for (int x : v) nd += x;
+                        }
+                        fprintf(stderr, "[run_resident] wave class %d: %d alignments (%d full-matrix), fwd %.2f ms, bwd %.2f ms\n", c, hwi.count[c], nd, a_, b_);
+                    }
                 }
                 float c_ = 0, w_ = 0;
                 cudaEventElapsedTime(&c_, h->ev[6], h->ev[7]);

@@ -61,11 +61,13 @@ struct WaveHapQ {        // extra per query hap
     u32 *swiQ;           // [Lq]  QUERY rows as swap DESTINATIONS: first source (REF row) | count << 16
     u32 *swiR;           // [Lr]  REF rows as swap DESTINATIONS: first source (QUERY row) | count << 16
     u8 *tpb;             // [Lq]  tp(a): entering QUERY row a counts a query variant (:572-574)
+    u16 *tps;            // [Lq]  number of rows a' > a with tp(a') (potential of the backward insertion chain)
     __device__ WaveHapQ(u8 *base, int Lq, int Lr) {
         srcQ = (int *)base; srcR = srcQ + Lq; swiQ = (u32 *)(srcR + Lr); swiR = swiQ + Lq; tpb = (u8 *)(swiR + Lr);
+        tps = (u16 *)(tpb + align_up(Lq, 16));
     }
 };
-__host__ __device__ inline int64_t wave_hapq_bytes(int Lq, int Lr) { return 8 * ((int64_t)Lq + Lr) + align_up(Lq, 16); }
+__host__ __device__ inline int64_t wave_hapq_bytes(int Lq, int Lr) { return 8 * ((int64_t)Lq + Lr) + align_up(Lq, 16) + align_up(2 * (int64_t)Lq, 16); }
 __host__ __device__ inline int64_t wave_hapt_bytes(int Lt) { return align_up(Lt, 16); }     // tinfo: base | tok<<7
 
 // kernel shape classes: (threads per block, rows per thread)
@@ -168,6 +170,10 @@ __global__ void wave_tables_kernel(const ScPlan *plan, const int *list, int i0, 
         build_srcinfo<int>(M.rptr, M.rflg, p.lr, M.toQ, p.len[h], H.flg, H.ptr, X.srcR);
         for (int a = 0; a < p.len[h]; a++)
             X.tpb[a] = (a > 0 && ((H.ptr[a] != H.ptr[a - 1] + 1) || (H.flg[a] & P_VAR_BEG))) ? 1 : 0;
+        {
+            int cnt = 0;
+            for (int a = p.len[h] - 1; a >= 0; a--) { X.tps[a] = (u16)cnt; cnt += X.tpb[a]; }
+        }
         for (int a = 0; a < p.len[h]; a++) {
             const int k0 = M.toQ[a], k1 = M.toQ[a + 1];
             X.swiQ[a] = k1 > k0 ? ((u32)M.toQ[p.len[h] + 1 + k0] | ((u32)(k1 - k0) << 16)) : 0u;
@@ -243,6 +249,8 @@ struct WaveArgs {
 template <class TT> struct WaveCtxT {      // TT: element type of the CSR swap tables (int in HBM, short in smem)
     int sc, ai, Lq, Lr, Lt, padQ, NP;
     const u8 *qstr, *rseq, *tinfo, *qflg, *rflg, *tpb;
+    const u16 *tps;
+    short *band;                // [Lt][4] rows visited by the banded forward sweep (walk scratch, dead until the walk)
     const TT *toQ, *toR;
     const TT *qptr, *rptr;      // query->ref and ref->query pointers (band bookkeeping of the forward sweep)
     const int *srcQ, *srcR;
@@ -266,13 +274,14 @@ __device__ inline WaveCtx wave_ctx(const WaveArgs &A, int item) {
     SlabHap HQ(base + W.base.hap[qh], x.Lq, x.Lr);
     SlabQm M(base + W.base.qm[qh], x.Lq, x.Lr);
     WaveHapQ X(base + W.hq[qh], x.Lq, x.Lr);
-    x.qstr = HQ.str; x.qflg = HQ.flg; x.rflg = M.rflg; x.tpb = X.tpb;
+    x.qstr = HQ.str; x.qflg = HQ.flg; x.rflg = M.rflg; x.tpb = X.tpb; x.tps = X.tps;
     x.toQ = M.toQ; x.toR = M.toR; x.srcQ = X.srcQ; x.srcR = X.srcR;
     x.qptr = HQ.ptr; x.rptr = M.rptr;
     x.swiQ = X.swiQ; x.swiR = X.swiR;
     x.rseq = A.in.rplane_seq + A.in.ref_off[x.sc];
     x.tinfo = base + W.ht[th];
     x.F = base + W.aln[x.ai] + wa.oF;
+    x.band = (short *)(base + W.aln[x.ai] + wa.oWalk);
     return x;
 }
 
@@ -616,6 +625,8 @@ __global__ void __launch_bounds__(FWDB_TPB) wave_fwdb_kernel(WaveArgs A, int ite
             }
             const int nQ = max(0, chi[0] - clo[0] + 1), nR = max(0, chi[1] - clo[1] + 1);
             const int total = nQ + nR;
+            if (t == 0) *(short4 *)(X.band + 4 * (int64_t)c) = make_short4((short)(nQ ? clo[0] : 1), (short)(nQ ? chi[0] : 0),
+                                                                             (short)(nR ? clo[1] : 1), (short)(nR ? chi[1] : 0));
             int cg0 = INF, cg1 = INF;                        // min(D - a) over the rows already done, per plane
             for (int base = 0; base < total; base += FWDB_TPB) {
                 const int v = base + t;
@@ -979,8 +990,9 @@ __device__ __forceinline__ void wave_bwd_body(const WaveCtxT<TT> &X, const int t
 }
 
 template <int TPB, int K>
-__global__ void __launch_bounds__(TPB) wave_bwd_kernel(WaveArgs A, int item0) {
+__global__ void __launch_bounds__(TPB) wave_bwd_kernel(WaveArgs A, int item0, const int *only_dense) {
     extern __shared__ __align__(16) u8 smem_raw[];
+    if (only_dense && !only_dense[item0 + blockIdx.x]) return;       // solved by the banded sweeps
     const WaveCtx X = wave_ctx(A, A.items[item0 + blockIdx.x]);
     const int end_plane = A.out.aln_end_plane[4 * (int64_t)X.sc + X.ai];
     int beg_plane;
@@ -1043,8 +1055,9 @@ __device__ __forceinline__ SbwdPush sbwd_pushes(const WaveCtx &X, int row, int f
     return r;
 }
 
-__global__ void __launch_bounds__(32) wave_sbwd_kernel(WaveArgs A, int item0, int npmax) {
+__global__ void __launch_bounds__(32) wave_sbwd_kernel(WaveArgs A, int item0, int npmax, const int *only_dense) {
     extern __shared__ __align__(16) u8 smem_raw[];
+    if (only_dense && !only_dense[item0 + blockIdx.x]) return;       // done by the banded backward sweep
     const int item = A.items[item0 + blockIdx.x];
     const WaveCtx X = wave_ctx(A, item);
     short *T0 = (short *)smem_raw, *T1 = T0 + npmax;          // T of two columns, dense over rows
@@ -1184,6 +1197,221 @@ __global__ void __launch_bounds__(32) wave_sbwd_kernel(WaveArgs A, int item0, in
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Windowed backward sweep: calc_prec_recall_path (:486-834) in gather form over a window of rows
+// that follows the reached cells.  Reached cells of column c come from reached cells x of column
+// c+1 — (row-1) by a diagonal edge, (row) by a deletion edge, the recorded source row by a swap
+// edge — and from the in-column insertion chain, which only runs towards lower rows.  So the rows
+// to look at in column c are [lowest target - E, highest target] per plane, cut to the rows the
+// banded forward sweep visited (X.band: cells outside hold no valid flags); if the chain is still
+// alive at the lowest row of the window, one thread follows it further down (rare).  One row per
+// thread; T and the forward flags of two columns live in shared memory (dense over rows, only
+// entries of the processed windows are ever read).  The insertion chain
+// T[r] = max(B[r], T[r+1] + tp(r+1)) is a link-segmented suffix max of T - S (S = X.tps), as in
+// wsc_kernel.  Replaces the one-warp-per-alignment frontier kernel wherever the banded forward
+// sweep succeeded: a column step is four block barriers on a few dozen rows instead of ~8
+// dependent HBM/L2 round trips.
+// ------------------------------------------------------------------------------------------
+constexpr int BWDB_TPB = 256;
+constexpr int BWDB_E = 24;             // rows below the lowest target that are looked at without the chain follower
+__host__ __device__ inline int bwdb_smem(int npmax) { return 6 * npmax + 128 * 4; }
+
+__global__ void __launch_bounds__(BWDB_TPB) wave_bwdb_kernel(WaveArgs A, int item0, int npmax, const int *need_dense) {
+    extern __shared__ __align__(16) u8 smem_raw[];
+    if (need_dense[item0 + blockIdx.x]) return;              // full-matrix forward sweep: frontier kernel instead
+    const WaveCtx X = wave_ctx(A, A.items[item0 + blockIdx.x]);
+    short *sT0 = (short *)smem_raw, *sT1 = sT0 + npmax;      // T of column c+1 / c
+    u8 *sF0 = (u8 *)(sT1 + npmax), *sF1 = sF0 + npmax;       // forward flags of column c+1 / c
+    int *sW = (int *)(sF1 + npmax);                          // [NW] warp heads, [NW] all-linked flags, chunk carry
+    constexpr int NW = BWDB_TPB / 32;
+    int *sWin = sW + 2 * NW + 8;                             // [2 parities][lo0, hi0, lo1, hi1] targets of the next column
+    int *sExt = sWin + 8;                                    // [2] new lowest processed row per plane after the chain follower
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int64_t oi = 4 * (int64_t)X.sc + X.ai;
+    const int end_plane = A.out.aln_end_plane[oi];
+    u32 status = 0;
+
+    if (t == 0) {
+        // targets of the last column: the end cell
+        int *w = sWin + ((X.Lt - 1) & 1) * 4;
+        w[0] = w[2] = INF; w[1] = w[3] = -1;
+        const int ea = end_plane ? X.Lr - 1 : X.Lq - 1;
+        w[2 * end_plane] = ea; w[2 * end_plane + 1] = ea;
+    }
+    __syncthreads();
+
+    int nlo[2] = {1, 1}, nhi[2] = {0, 0};                    // processed rows of column c+1 (plane-local, inclusive)
+    int tch_next = 0;
+    for (int c = X.Lt - 1; c >= 0; c--) {
+        short *sTn = (c & 1) ? sT1 : sT0, *sTc = (c & 1) ? sT0 : sT1;
+        u8 *sFn = (c & 1) ? sF1 : sF0, *sFc = (c & 1) ? sF0 : sF1;
+        const bool last = c == X.Lt - 1;
+        const short4 bd = *(const short4 *)(X.band + 4 * (int64_t)c);
+        const int blo[2] = {bd.x, bd.z}, bhi[2] = {bd.y, bd.w};                        // rows with valid forward flags
+        int *wcur = sWin + (c & 1) * 4, *wnext = sWin + ((c + 1) & 1) * 4;
+        int clo[2], chi[2];
+#pragma unroll
+        for (int P = 0; P < 2; P++) {
+            clo[P] = max(max(wcur[2 * P] - BWDB_E, 0), blo[P]);
+            chi[P] = min(wcur[2 * P + 1], bhi[P]);
+        }
+        const int nQ = max(0, chi[0] - clo[0] + 1), nR = max(0, chi[1] - clo[1] + 1);
+        const int total = nQ + nR;
+        const int erow = end_plane ? X.padQ + X.Lr - 1 : X.Lq - 1;
+        u8 *Fcol = X.F + (int64_t)c * X.NP;
+        auto Tnext = [&](int P, int a) -> int { return (a >= nlo[P] && a <= nhi[P]) ? (int)sTn[(P ? X.padQ : 0) + a] : -1; };
+        auto Fnext = [&](int P, int a) -> int { return (a >= nlo[P] && a <= nhi[P]) ? (int)sFn[(P ? X.padQ : 0) + a] : 0; };
+        __syncthreads();                                     // everyone has read wcur
+        if (t == 0) { wnext[0] = wnext[2] = INF; wnext[1] = wnext[3] = -1; }            // becomes the target set of column c-1
+        // my contribution to the targets of column c-1: reached cell (P, a) with forward flags f
+        auto contribute = [&](int P, int a, int f) {
+            if (a > 0 && (f & F_DIAG)) atomicMin(&wnext[2 * P], a - 1), atomicMax(&wnext[2 * P + 1], a - 1);
+            if (f & F_DEL) atomicMin(&wnext[2 * P], a), atomicMax(&wnext[2 * P + 1], a);
+            if ((f & F_SWP) && a > 0) {                                                // :598-679
+                const int of = P ? X.rflg[a] : X.qflg[a];
+                if (!(of & P_VARIANT) || (of & P_VAR_BEG)) {
+                    const int *tab = P ? X.toR : X.toQ;
+                    const int *src = tab + (P ? X.Lr : X.Lq) + 1;
+                    const int z = src[tab[a] + (f >> F_K_SHIFT)];
+                    atomicMin(&wnext[2 * (1 - P)], z), atomicMax(&wnext[2 * (1 - P) + 1], z);
+                }
+            }
+        };
+        int chunk_carry = NEG;                               // U of the lowest row of the chunk above (processed before)
+        bool chunk_first = true;
+        for (int base = ((total - 1) / BWDB_TPB) * BWDB_TPB; base >= 0; base -= BWDB_TPB) {
+            const int v = base + t;
+            const bool valid = v < total;
+            const bool P = v >= nQ;
+            const int a = P ? clo[1] + (v - nQ) : clo[0] + v;
+            const int len = P ? X.Lr : X.Lq;
+            const int row = P ? X.padQ + a : a;
+            // ---- stage A: forward flags of my cell, candidates from column c+1 ----
+            int fc = 0, B = -1, swv = -1, tpn = 0, S = 0, Td = -1, Fd = 0, Tn = -1, Fn = 0;
+            bool below_ok = false;
+            if (valid) {
+                fc = Fcol[row];
+                sFc[row] = (u8)fc;
+                below_ok = a + 1 < len;
+                if (!P) { S = X.tps[a]; if (below_ok) tpn = X.tpb[a + 1]; }
+                if (last && row == erow) B = 0;                                        // :543-545
+                if (!last) {
+                    if (below_ok) { Td = Tnext(P, a + 1); Fd = Fnext(P, a + 1); }
+                    Tn = Tnext(P, a); Fn = Fnext(P, a);
+                    if (Td >= 0 && (Fd & F_DIAG)) B = max(B, Td + tpn);                // :556-595, :692-731
+                    if (Tn >= 0 && (Fn & F_DEL)) B = max(B, Tn);                       // :774-804
+                    const int si = P ? X.srcR[a] : X.srcQ[a];                          // my row as the recorded swap source
+                    if (si & 1) {                                                      // :598-679
+                        const int d = si >> 8;
+                        const int T2 = Tnext(P ? 0 : 1, d), F2 = Fnext(P ? 0 : 1, d);
+                        if (T2 >= 0 && (F2 & F_SWP) && (F2 >> F_K_SHIFT) == ((si >> 1) & 7)) {
+                            swv = T2 + ((si >> 4) & 1);
+                            B = max(B, swv);
+                            if (F2 & F_TIE) status |= VD_ST_TIE;
+                        }
+                    }
+                }
+            }
+            __syncthreads();                                                           // sFc of this chunk (and the one above) visible
+            // ---- stage B: insertion chain (:734-771): link-segmented suffix max of T - S ----
+            bool link = false;                               // (row+1, c) is in my plane, was processed and has F_INS
+            if (valid && below_ok && a + 1 <= chi[P]) link = sFc[row + 1] & F_INS;
+            const unsigned lm = __ballot_sync(0xffffffffu, link);
+            const unsigned nm = ~(lm >> lane);
+            const int run = nm ? __ffs(nm) - 1 : 32;
+            int val = (valid && B >= 0) ? B - S : NEG;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int o = __shfl_down_sync(0xffffffffu, val, d);
+                if (run >= d && lane + d < 32) val = max(val, o);
+            }
+            if (lane == 0) { sW[warp] = val; sW[NW + warp] = (lm == 0xffffffffu) ? 1 : 0; }
+            __syncthreads();
+            {   // carry into my warp: what arrives at its lane 31 from above
+                int acc = chunk_first ? NEG : chunk_carry;
+                for (int w = NW - 1; w > warp; w--) acc = max(sW[w], sW[NW + w] ? acc : NEG);
+                if (run == 32 - lane) val = max(val, acc);
+            }
+            const int T = (valid && val > NEG / 2) ? val + S : -1;
+            if (valid) sTc[row] = (short)T;
+            const int head_all = __shfl_sync(0xffffffffu, val, 0);
+            __syncthreads();                                                           // sTc visible; sW free again
+            if (t == 0) sW[2 * NW] = head_all;                                         // U of the chunk's lowest row
+            // ---- stage C: path flags (in place), targets of the next column ----
+            if (valid) {
+                int pf = 0;
+                if (T >= 0) {
+                    if (last && row == erow && T == 0) pf |= PTR_MAT;                  // :543
+                    if (!last) {
+                        if (Td >= 0 && (Fd & F_DIAG) && Td + tpn == T) {
+                            const int chn = (P ? X.rseq[a + 1] : X.qstr[a + 1]) & 0x7f;
+                            pf |= (chn == tch_next) ? PTR_MAT : PTR_SUB;
+                        }
+                        if (Tn >= 0 && (Fn & F_DEL) && Tn == T) pf |= PTR_DEL;
+                        if (swv >= 0 && swv == T) pf |= PTR_SWP;
+                    }
+                    if (link) {
+                        const int tb = sTc[row + 1];
+                        if (tb >= 0 && tb + tpn == T) pf |= PTR_INS;
+                    }
+                    contribute(P, a, fc);
+                }
+                Fcol[row] = (u8)pf;
+            }
+            __syncthreads();
+            chunk_carry = sW[2 * NW];
+            chunk_first = false;
+        }
+        // ---- chain follower: the insertion chain is still alive at the lowest row of a window ----
+        int plo[2] = {clo[0], clo[1]};
+        {
+            bool need[2];
+#pragma unroll
+            for (int P = 0; P < 2; P++) {
+                const int r0 = (P ? X.padQ : 0) + clo[P];
+                need[P] = (P ? nR : nQ) > 0 && clo[P] > max(blo[P], 0) && sTc[r0] >= 0 && (sFc[r0] & F_INS);
+            }
+            if (need[0] || need[1]) {                        // block-uniform
+                if (t == 0) {
+                    for (int P = 0; P < 2; P++) {
+                        int a = clo[P];
+                        if (need[P]) {
+                            const int rb = P ? X.padQ : 0;
+                            // cell (a-1) is reached from (a) when F[a] has F_INS (:734-771); nothing else targets it
+                            while (a > max(blo[P], 0) && sTc[rb + a] >= 0 && (sFc[rb + a] & F_INS)) {
+                                const int tv = sTc[rb + a] + ((!P) ? (int)X.tpb[a] : 0);
+                                a--;
+                                const int f = Fcol[rb + a];
+                                sFc[rb + a] = (u8)f;
+                                sTc[rb + a] = (short)tv;
+                                Fcol[rb + a] = (u8)PTR_INS;
+                                contribute(P, a, f);
+                            }
+                        }
+                        sExt[P] = a;
+                    }
+                }
+                __syncthreads();
+                plo[0] = sExt[0]; plo[1] = sExt[1];
+            }
+        }
+        nlo[0] = plo[0]; nhi[0] = chi[0]; nlo[1] = plo[1]; nhi[1] = chi[1];
+        if (nQ == 0) { nlo[0] = 1; nhi[0] = 0; }
+        if (nR == 0) { nlo[1] = 1; nhi[1] = 0; }
+        tch_next = X.tinfo[c] & 0x7f;
+        __syncthreads();                                     // wnext complete before the next column reads it
+    }
+    // origin plane (:811-814): QUERY if its origin was reached
+    status = __reduce_or_sync(0xffffffffu, status);
+    if (lane == 0 && status) atomicOr(&A.out.status[oi], status);
+    if (t == 0) {
+        const short *sTl = sT1;                              // column 0 was written as "cur" of c = 0
+        const int t00 = (0 >= nlo[0] && 0 <= nhi[0]) ? (int)sTl[0] : -1;
+        A.out.aln_beg_plane[oi] = (u8)(t00 >= 0 ? 0 : 1);
+    }
+}
+
 // path flags of the wavefront layout
 struct PFWave {
     const u8 *F; int NP, padQ;
@@ -1236,6 +1464,7 @@ inline void wave_configure() {
     wave_configure_one<1024, 16>(); wave_configure_one<1024, 32>();
     cudaFuncSetAttribute(wave_sbwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * 32768);
     cudaFuncSetAttribute(wave_fwdb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fwdb_smem(32768));
+    cudaFuncSetAttribute(wave_bwdb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bwdb_smem(32768));
 }
 
 constexpr int FWDB_MIN_CLASS = 4;      // classes with more than 512 rows go through the banded sweep first
@@ -1246,16 +1475,24 @@ inline void wave_launch_pair(cudaStream_t st, const WaveArgs &A, int item0, int 
         wave_fwdb_kernel<<<n, FWDB_TPB, fwdb_smem(TPB * K), st>>>(A, item0, TPB * K, need_dense);
         wave_fwd_kernel<TPB, K><<<n, TPB, wave_fwd_smem<TPB, K>(), st>>>(A, item0, need_dense);
     } else if (fwd) wave_fwd_kernel<TPB, K><<<n, TPB, wave_fwd_smem<TPB, K>(), st>>>(A, item0, nullptr);
-    else wave_bwd_kernel<TPB, K><<<n, TPB, wave_bwd_smem<TPB, K>(), st>>>(A, item0);
+    else wave_bwd_kernel<TPB, K><<<n, TPB, wave_bwd_smem<TPB, K>(), st>>>(A, item0, need_dense);
 }
+// backward of a class that went through the banded forward sweep: the windowed sweep for the alignments
+// it solved; the DENSE sweep for the rest (score above the last bound: a structural variant that only one
+// side carries - nearly every cell of such a matrix lies on some optimal path, so the frontier kernel
+// would crawl over the whole matrix with one warp).  banded_bwd = false: frontier kernel for all of them
+// (VD_SPARSE_BWD=1, testing).  Classes without the banded forward sweep: dense or frontier kernel.
 inline void wave_launch(cudaStream_t st, const WaveArgs &A, int cls, int item0, int n, bool fwd, bool sparse_bwd = true,
-                        int *need_dense = nullptr) {
+                        int *need_dense = nullptr, bool banded_bwd = true) {
     if (cls < FWDB_MIN_CLASS) need_dense = nullptr;
-    if (!fwd && sparse_bwd) {
-        const int npmax = wave_tpb(cls) * wave_k(cls);
-        wave_sbwd_kernel<<<n, 32, 6 * npmax, st>>>(A, item0, npmax);
+    const int npmax = wave_tpb(cls) * wave_k(cls);
+    if (!fwd && sparse_bwd && need_dense && banded_bwd)
+        wave_bwdb_kernel<<<n, BWDB_TPB, bwdb_smem(npmax), st>>>(A, item0, npmax, need_dense);   // then the dense kernel below
+    else if (!fwd && sparse_bwd) {
+        wave_sbwd_kernel<<<n, 32, 6 * npmax, st>>>(A, item0, npmax, nullptr);
         return;
     }
+    if (!fwd && !(sparse_bwd && banded_bwd)) need_dense = nullptr;                               // dense sweep for everything
     switch (cls) {
         case 0: wave_launch_pair<32, 1>(st, A, item0, n, fwd, need_dense); break;
         case 1: wave_launch_pair<32, 2>(st, A, item0, n, fwd, need_dense); break;
