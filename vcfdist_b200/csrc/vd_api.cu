@@ -41,7 +41,7 @@ struct vd_handle {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[8] = {};
     cudaStream_t side[vd::N_WCLS] = {};     // one stream per wavefront class: classes run concurrently
-    cudaEvent_t sev[vd::N_WCLS][3] = {};
+    cudaEvent_t sev[vd::N_WCLS][4] = {};
     cudaEvent_t gev[vd::N_GROUP][2] = {};   // start / end of each short-kernel launch group
     int64_t scratch_budget = 0;
     int num_sms = 148;
@@ -326,7 +326,7 @@ static int run_resident(vd_handle *h, const BatchDev &in, const OutDev &out, con
                 // forward then backward of each class on its own stream (an alignment's backward pass
                 // only depends on its own forward pass), all classes concurrently; then join
                 CK(cudaEventRecord(h->ev[4], st));
-                for (int c = 0; c < N_WCLS; c++) {
+                for (int c = N_WCLS - 1; c >= 0; c--) {            // biggest shapes first: they are the critical path
                     if (!hwi.count[c]) continue;
                     cudaStream_t ss = h->serial ? st : h->side[c];
                     if (ss != st) CK(cudaStreamWaitEvent(ss, h->ev[4], 0));
@@ -336,12 +336,13 @@ static int run_resident(vd_handle *h, const BatchDev &in, const OutDev &out, con
                     wave_launch(ss, WA, c, cb.b[c], hwi.count[c], false, h->sparse_bwd && c >= h->sbwd_min_class,
                                 h->banded_fwd ? (int *)h->need_dense.p : nullptr, h->banded_bwd);
                     CK(cudaEventRecord(h->sev[c][2], ss));
-                    if (ss != st) CK(cudaStreamWaitEvent(st, h->sev[c][2], 0));
-                    S.n_launches += 2;
+                    // walk + credit of this class right behind its backward sweep, on the same stream
+                    wave_walk_kernel<<<(hwi.count[c] + 31) / 32, 32, 0, ss>>>(WA, cb.b[c], hwi.count[c]);
+                    CK(cudaEventRecord(h->sev[c][3], ss));
+                    if (ss != st) CK(cudaStreamWaitEvent(st, h->sev[c][3], 0));
+                    S.n_launches += 3;
                 }
                 CK(cudaEventRecord(h->ev[6], st));
-                wave_walk_kernel<<<(total_items + 63) / 64, 64, 0, st>>>(WA, total_items);
-                S.n_launches++;
                 CK(cudaEventRecord(h->ev[7], st));
                 CK(cudaStreamSynchronize(st));
                 CK(cudaGetLastError());
@@ -351,7 +352,9 @@ static int run_resident(vd_handle *h, const BatchDev &in, const OutDev &out, con
                     float a_ = 0, b_ = 0;
                     cudaEventElapsedTime(&a_, h->sev[c][0], h->sev[c][1]);
                     cudaEventElapsedTime(&b_, h->sev[c][1], h->sev[c][2]);
-                    ms_fwd += a_; ms_bwd += b_;
+                    float w2 = 0;
+                    cudaEventElapsedTime(&w2, h->sev[c][2], h->sev[c][3]);
+                    ms_fwd += a_; ms_bwd += b_; ms_walk += w2;
                     if (trace) {
                         int nd = 0;
                         if (h->banded_fwd && c >= 4) {
@@ -359,13 +362,12 @@ static int run_resident(vd_handle *h, const BatchDev &in, const OutDev &out, con
                             cudaMemcpy(v.data(), (int *)h->need_dense.p + cb.b[c], 4 * (size_t)hwi.count[c], cudaMemcpyDeviceToHost);
                             for (int x : v) nd += x;
                         }
-                        fprintf(stderr, "[run_resident] wave class %d: %d alignments (%d full-matrix), fwd %.2f ms, bwd %.2f ms\n", c, hwi.count[c], nd, a_, b_);
+                        fprintf(stderr, "[run_resident] wave class %d: %d alignments (%d full-matrix), fwd %.2f ms, bwd %.2f ms, walk %.2f ms\n", c, hwi.count[c], nd, a_, b_, w2);
                     }
                 }
                 float c_ = 0, w_ = 0;
                 cudaEventElapsedTime(&c_, h->ev[6], h->ev[7]);
                 cudaEventElapsedTime(&w_, h->ev[4], h->ev[6]);
-                ms_walk += c_;
                 S.ms_long_wall += w_;
                 S.spill_bytes += 3 * (int64_t)hwi.spill_cells;
             }

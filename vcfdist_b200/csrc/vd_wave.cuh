@@ -589,7 +589,30 @@ __global__ void __launch_bounds__(FWDB_TPB) wave_fwdb_kernel(WaveArgs A, int ite
     const int NPr = X.padQ + X.Lr;                           // rows in use (REF plane starts at padQ)
     bool solved = false;
 
+    // Lower bound of the score: every path spells the reference with a SUBSET of the query haplotype's
+    // variants applied (planes are only left / entered at variant boundaries, :335-337, :364-366), and
+    // aligning a string of length Lm to the truth costs at least |Lm - Lt|.  Bounds below it are skipped -
+    // an SV that only one side carries goes straight to the full-matrix kernel instead of failing three
+    // ever wider banded sweeps first.
+    __shared__ int s_lb;
+    {
+        const int qh = X.ai >> 1;
+        const int64_t v0 = A.in.var_off[4 * (int64_t)X.sc + qh], v1 = A.in.var_off[4 * (int64_t)X.sc + qh + 1];
+        const int nv = (int)(v1 - v0);
+        if (t == 0) s_lb = nv <= 9 ? INF : 0;
+        __syncthreads();
+        if (nv <= 9 && t < (1 << nv)) {
+            int lm = X.Lr;
+            for (int j = 0; j < nv; j++)
+                if ((t >> j) & 1) lm += (int)(A.in.alt_off[v0 + j + 1] - A.in.alt_off[v0 + j]) - A.in.var_rlen[v0 + j];
+            atomicMin(&s_lb, abs(lm - X.Lt));
+        }
+        __syncthreads();
+    }
+    const int score_lb = s_lb;
+
     for (int tau = FWD_TAU0; tau <= FWDB_TAU_MAX && !solved; tau *= 4) {
+        if (tau < score_lb) continue;
         for (int r = t; r < NPr; r += FWDB_TPB) { sD0[r] = 0xffff; sD1[r] = 0xffff; }
         if (t == 0) {
             sLive[0] = sLive[2] = sLive[4] = sLive[6] = INF;
@@ -1421,10 +1444,10 @@ struct PFWave {
 };
 
 // one thread per alignment: walk + credit
-__global__ void wave_walk_kernel(WaveArgs A, int n_items) {
+__global__ void wave_walk_kernel(WaveArgs A, int item0, int n_items) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n_items) return;
-    const int item = A.items[g];
+    const int item = A.items[item0 + g];
     const int e = item >> 2, ai = item & 3;
     const int i = A.i0 + e;
     const int sc = A.list[i];
