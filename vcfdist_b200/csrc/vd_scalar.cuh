@@ -378,6 +378,7 @@ template <class Mem> struct PFScalar {          // [column][row], rows = Lq + Lr
     __device__ __forceinline__ int get(int hi, int qri, int ti) const {
         return mem->ld8(oPF + (typename Mem::off_t)ti * N + (hi ? Lq + qri : qri));
     }
+    __device__ __forceinline__ void prefetch(int, int, int) const {}
 };
 
 // ---------------------------------------------------------------------------------------
@@ -410,6 +411,7 @@ __device__ void walk_credit(const Mem &mem, const AlnLayout<typename Mem::off_t>
             else if (hi == 0 && (pf & PTR_SWP)) { ty = PTR_SWP; hi = 1; qri = (int)q.ptr[qri] + 1; ti++; ed = 0; }  // :930-934
             else { status |= VD_ST_ERR_NO_POINTER; return; }                                    // :936-939
             if ((hi == 0 && qri >= Lq) || (hi == 1 && qri >= Lr) || ti >= Lt) { last_edit = ed; ns++; break; }  // :941
+            pfr.prefetch(hi, qri, ti);                  // flag bytes a few steps ahead (HBM-resident matrices only)
             if (np >= maxpath) { status |= VD_ST_ERR_NO_POINTER; return; }
             const int tf = t.flg[ti];
             bool in_truth_var = tf & P_VARIANT;                                                 // :949-951

@@ -73,6 +73,7 @@ __host__ __device__ inline int wsc_bin(int need) { for (int b = 0; b < N_WBIN; b
 struct PFWarp {      // path flags, [column][row], QUERY rows first
     const u8 *F; int N, Lq;
     __device__ __forceinline__ int get(int hi, int qri, int ti) const { return F[ti * N + (hi ? Lq + qri : qri)]; }
+    __device__ __forceinline__ void prefetch(int, int, int) const {}
 };
 
 // PAR = false: one warp per supercluster, its four alignments one after the other (small shared-memory

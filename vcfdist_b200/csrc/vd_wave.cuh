@@ -1437,9 +1437,20 @@ __global__ void __launch_bounds__(BWDB_TPB) wave_bwdb_kernel(WaveArgs A, int ite
 
 // path flags of the wavefront layout
 struct PFWave {
-    const u8 *F; int NP, padQ;
+    const u8 *F; int NP, padQ; int Lt;
     __device__ __forceinline__ int get(int hi, int qri, int ti) const {
         return F[(int64_t)ti * NP + (hi ? padQ + qri : qri)];
+    }
+    // The walk is one dependent flag load per step, each in a new 128-byte line (a diagonal step moves one
+    // column = NP bytes): pull the lines of the cells AHEAD steps further along the diagonal and along the
+    // row (deletion runs) towards L1 while the current step is still being decided.
+    static constexpr int AHEAD = 8;
+    __device__ __forceinline__ void prefetch(int hi, int qri, int ti) const {
+        if (ti + AHEAD < Lt) {
+            const u8 *p = F + (int64_t)(ti + AHEAD) * NP + (hi ? padQ + qri : qri);
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(p + AHEAD));
+        }
     }
 };
 
@@ -1465,7 +1476,7 @@ __global__ void wave_walk_kernel(WaveArgs A, int item0, int n_items) {
     u8 *ab = base + W.aln[ai];
     GMem mem{ab + wa.oWalk};
     const AlnLayout<int64_t> L = wave_walk_layout(q.len, p.lr, t.len);
-    PFWave pfr{ab + wa.oF, wa.NP, wa.padQ};
+    PFWave pfr{ab + wa.oF, wa.NP, wa.padQ, t.len};
     u32 status = A.out.status[4 * (int64_t)sc + ai];
     const int beg_plane = A.out.aln_beg_plane[4 * (int64_t)sc + ai];
     const int end_plane = A.out.aln_end_plane[4 * (int64_t)sc + ai];
