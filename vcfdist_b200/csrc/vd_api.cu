@@ -337,7 +337,7 @@ static int run_resident(vd_handle *h, const BatchDev &in, const OutDev &out, con
                                 h->banded_fwd ? (int *)h->need_dense.p : nullptr, h->banded_bwd);
                     CK(cudaEventRecord(h->sev[c][2], ss));
                     // walk + credit of this class right behind its backward sweep, on the same stream
-                    wave_walk_kernel<<<(hwi.count[c] + 31) / 32, 32, 0, ss>>>(WA, cb.b[c], hwi.count[c]);
+                    wave_walk_kernel<<<(hwi.count[c] + 3) / 4, 128, 0, ss>>>(WA, cb.b[c], hwi.count[c]);
                     CK(cudaEventRecord(h->sev[c][3], ss));
                     if (ss != st) CK(cudaStreamWaitEvent(st, h->sev[c][3], 0));
                     S.n_launches += 3;

@@ -1455,9 +1455,11 @@ struct PFWave {
 };
 
 // one thread per alignment: walk + credit
+// One alignment per WARP (lane 0 walks): walks of very different lengths and move mixes in one warp
+// serialise each other's branches, and there are only a few thousand long alignments in a batch.
 __global__ void wave_walk_kernel(WaveArgs A, int item0, int n_items) {
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= n_items) return;
+    const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (g >= n_items || (threadIdx.x & 31)) return;
     const int item = A.items[item0 + g];
     const int e = item >> 2, ai = item & 3;
     const int i = A.i0 + e;
