@@ -36,7 +36,26 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+// Per-chunk state of the scheduler: plan, order array, counters and the events of one chunk.  Two sets,
+// so that the plan pass of chunk i+1 runs while the kernels of chunk i are still executing.
+struct Work {
+    DevBuf plan, list, order, ranks, ranks_out, iota, counters, cubtmp;
+    PlanCounters *h_counters = nullptr;     // pinned + mapped: written by publish_kernel, never by a copy engine
+    cudaEvent_t ev[4] = {};                 // plan start, plan end, short kernels issued, chunk end
+    cudaEvent_t ev5 = nullptr;              // fork point of the short-kernel launch groups
+    cudaEvent_t evL = nullptr;              // everything issued on the main stream for this chunk
+    cudaEvent_t gev[vd::N_GROUP][2] = {};   // start / end of each short-kernel launch group
+    bool grp_used[vd::N_GROUP] = {};
+    bool busy = false;                      // launched, not yet harvested
+    BatchDev in; OutDev out;
+    float ms_fwd = 0, ms_bwd = 0, ms_walk = 0;
+    int n_bad = 0;
+};
+
 struct vd_handle {
+    Work work[2];
+    cudaStream_t s_plan = nullptr;          // plan pass of the next chunk
+    cudaStream_t s_epi = nullptr;           // join of a chunk's launch groups + status reduction (the main stream moves on)
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[8] = {};
@@ -69,9 +88,8 @@ struct vd_handle {
     int ramp = 1;                   // VD_RAMP=0: uniform chunks
     int64_t chunk_sc = 1048576;      // superclusters per pipeline chunk (VD_CHUNK_SC)
     // work
-    DevBuf ranks, ranks_out, iota, plan, list, mlist, need_dense, counters, bytes, offs, cubtmp, slab, hap_ok, wave_desc;
-    PlanCounters *h_counters = nullptr;     // pinned + mapped: written by publish_kernel, never by a copy engine
-    WaveItems *h_witems = nullptr;          // (a small D2H memcpy would queue behind the bulk result copies of vd_run)
+    DevBuf need_dense, bytes, offs, cubtmp, slab, hap_ok, wave_desc;
+    WaveItems *h_witems = nullptr;          // pinned + mapped (a small D2H memcpy would queue behind the bulk result copies of vd_run)
 };
 
 static int fail(vd_handle *h, int code, const char *fmt, ...) {
@@ -108,8 +126,15 @@ extern "C" int vd_create(int device, int64_t scratch_bytes, vd_handle **out) {
         cudaStreamCreateWithFlags(&h->side[c], cudaStreamNonBlocking);
         for (auto &e : h->sev[c]) cudaEventCreate(&e);
     }
-    for (auto &g : h->gev) for (auto &e : g) cudaEventCreate(&e);
-    cudaHostAlloc((void **)&h->h_counters, sizeof(PlanCounters), cudaHostAllocMapped);
+    for (auto &w : h->work) {
+        for (auto &e : w.ev) cudaEventCreate(&e);
+        cudaEventCreate(&w.ev5);
+        cudaEventCreate(&w.evL);
+        for (auto &g : w.gev) for (auto &e : g) cudaEventCreate(&e);
+        cudaHostAlloc((void **)&w.h_counters, sizeof(PlanCounters), cudaHostAllocMapped);
+    }
+    cudaStreamCreateWithFlags(&h->s_plan, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&h->s_epi, cudaStreamNonBlocking);
     cudaHostAlloc((void **)&h->h_witems, sizeof(WaveItems), cudaHostAllocMapped);
     if (scratch_bytes <= 0) {
         size_t fr = 0, tot = 0;
@@ -156,13 +181,21 @@ extern "C" void vd_destroy(vd_handle *h) {
     }
     if (h->s_in) cudaStreamDestroy(h->s_in);
     if (h->s_out) cudaStreamDestroy(h->s_out);
-    DevBuf *bufs[] = {&h->ranks, &h->ranks_out, &h->iota, &h->plan, &h->list, &h->mlist, &h->need_dense, &h->counters, &h->bytes, &h->offs,
-                      &h->cubtmp, &h->slab, &h->hap_ok, &h->wave_desc};
+    DevBuf *bufs[] = {&h->need_dense, &h->bytes, &h->offs, &h->cubtmp, &h->slab, &h->hap_ok, &h->wave_desc};
     for (DevBuf *b : bufs) b->release();
-    if (h->h_counters) cudaFreeHost(h->h_counters);
+    for (auto &w : h->work) {
+        DevBuf *wb[] = {&w.plan, &w.list, &w.order, &w.ranks, &w.ranks_out, &w.iota, &w.counters, &w.cubtmp};
+        for (DevBuf *b : wb) b->release();
+        if (w.h_counters) cudaFreeHost(w.h_counters);
+        for (auto &e : w.ev) if (e) cudaEventDestroy(e);
+        if (w.ev5) cudaEventDestroy(w.ev5);
+        if (w.evL) cudaEventDestroy(w.evL);
+        for (auto &g : w.gev) for (auto &e : g) if (e) cudaEventDestroy(e);
+    }
+    if (h->s_plan) cudaStreamDestroy(h->s_plan);
+    if (h->s_epi) cudaStreamDestroy(h->s_epi);
     if (h->h_witems) cudaFreeHost(h->h_witems);
     for (auto &e : h->ev) if (e) cudaEventDestroy(e);
-    for (auto &g : h->gev) for (auto &e : g) if (e) cudaEventDestroy(e);
     for (int c = 0; c < N_WCLS; c++) {
         for (auto &e : h->sev[c]) if (e) cudaEventDestroy(e);
         if (h->side[c]) cudaStreamDestroy(h->side[c]);
@@ -179,80 +212,90 @@ extern "C" int vd_get_stats(const vd_handle *h, vd_stats *out) {
     return VD_OK;
 }
 
-// The whole path on device-resident buffers.
+// The whole path on device-resident buffers, in three steps per chunk so that chunks overlap:
+//   chunk_plan     (stream sp)   memsets of the result buffers, plan pass, order sort, counters to the host
+//   chunk_exec     (stream st)   reads the counters, issues every launch group (+ the long path, which still
+//                                synchronises internally) and records the chunk's end event; no host sync
+//   chunk_harvest                waits for the end event, folds event times and counters into the stats
 // `out` may carry pointers shifted by the chunk's first variant (see vd_run); `base` has the true
 // buffer starts for the memsets.  Stats accumulate across the chunks of one call.
-static int run_resident(vd_handle *h, const BatchDev &in, const OutDev &out, const OutDev &base) {
-    cudaStream_t st = h->stream;
+static int chunk_plan(vd_handle *h, Work &W, cudaStream_t sp, const BatchDev &in, const OutDev &out, const OutDev &base) {
     const int n_sc = in.n_sc;
     const int64_t n_var = in.n_var;
-    vd_stats &S = h->stats;
-    if (n_sc == 0) return VD_OK;
-    const bool trace = getenv("VD_TRACE") != nullptr;
-    auto now_ms = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
-    const double t_r0 = now_ms();
-    if (trace) { cudaStreamSynchronize(st); fprintf(stderr, "[run_resident] inputs ready after %.2f ms\n", now_ms() - t_r0); }
+    W.in = in; W.out = out;
+    W.busy = true;
+    W.ms_fwd = W.ms_bwd = W.ms_walk = 0;
+    for (auto &u : W.grp_used) u = false;
+    CK(cudaEventRecord(W.ev[0], sp));
+    CK(cudaMemsetAsync(base.assigned, 0, 2 * n_var, sp));
+    CK(cudaMemsetAsync(base.sync_group, 0, 8 * n_var, sp));
+    CK(cudaMemsetAsync(base.ref_ed, 0, 8 * n_var, sp));
+    CK(cudaMemsetAsync(base.query_ed, 0, 8 * n_var, sp));
+    CK(cudaMemsetAsync(base.callq, 0, 8 * n_var, sp));
+    CK(cudaMemsetAsync(base.status, 0, 16 * (size_t)n_sc, sp));
 
-    CK(cudaEventRecord(h->ev[0], st));
-    CK(cudaMemsetAsync(base.assigned, 0, 2 * n_var, st));
-    CK(cudaMemsetAsync(base.sync_group, 0, 8 * n_var, st));
-    CK(cudaMemsetAsync(base.ref_ed, 0, 8 * n_var, st));
-    CK(cudaMemsetAsync(base.query_ed, 0, 8 * n_var, st));
-    CK(cudaMemsetAsync(base.callq, 0, 8 * n_var, st));
-    CK(cudaMemsetAsync(base.status, 0, 16 * (size_t)n_sc, st));
-
-    CK(h->plan.ensure(sizeof(ScPlan) * (size_t)n_sc));
-    CK(h->list.ensure(sizeof(int) * (size_t)n_sc));
-    CK(h->mlist.ensure(sizeof(int) * (size_t)n_sc));
-    CK(h->counters.ensure(sizeof(PlanCounters)));
-    CK(cudaMemsetAsync(h->counters.p, 0, sizeof(PlanCounters), st));
-    ScPlan *plan = (ScPlan *)h->plan.p;
-    int *list = (int *)h->list.p;
-    int *order = (int *)h->mlist.p;                 // class- and cost-sorted small superclusters
-    PlanCounters *dcnt = (PlanCounters *)h->counters.p;
-
-    CK(h->ranks.ensure((size_t)n_sc)); CK(h->ranks_out.ensure((size_t)n_sc)); CK(h->iota.ensure(4 * (size_t)n_sc));
-    plan_kernel<<<(n_sc + 255) / 256, 256, 0, st>>>(in, plan, list, (u8 *)h->ranks.p, (int *)h->iota.p, dcnt, h->force_class, kBigClass,
-                                                    h->small_lo, h->small_hi, h->use_wsc, h->use_hom);
-    small_base_kernel<<<1, 32, 0, st>>>(dcnt);
+    CK(W.plan.ensure(sizeof(ScPlan) * (size_t)n_sc));
+    CK(W.list.ensure(sizeof(int) * (size_t)n_sc));
+    CK(W.order.ensure(sizeof(int) * (size_t)n_sc));
+    CK(W.counters.ensure(sizeof(PlanCounters)));
+    CK(W.ranks.ensure((size_t)n_sc)); CK(W.ranks_out.ensure((size_t)n_sc)); CK(W.iota.ensure(4 * (size_t)n_sc));
+    CK(cudaMemsetAsync(W.counters.p, 0, sizeof(PlanCounters), sp));
+    PlanCounters *dcnt = (PlanCounters *)W.counters.p;
+    int *order = (int *)W.order.p;                   // class- and cost-sorted short superclusters
+    plan_kernel<<<(n_sc + 255) / 256, 256, 0, sp>>>(in, (ScPlan *)W.plan.p, (int *)W.list.p, (u8 *)W.ranks.p, (int *)W.iota.p, dcnt,
+                                                    h->force_class, kBigClass, h->small_lo, h->small_hi, h->use_wsc, h->use_hom);
+    small_base_kernel<<<1, 32, 0, sp>>>(dcnt);
     {   // order[] = supercluster indices stably sorted by rank (non-short superclusters sort to the end)
         size_t tmp = 0;
-        cub::DeviceRadixSort::SortPairs(nullptr, tmp, (const u8 *)h->ranks.p, (u8 *)h->ranks_out.p, (const int *)h->iota.p, order,
-                                        n_sc, 0, 8, st);
-        CK(h->cubtmp.ensure(tmp));
-        cub::DeviceRadixSort::SortPairs(h->cubtmp.p, tmp, (const u8 *)h->ranks.p, (u8 *)h->ranks_out.p, (const int *)h->iota.p, order,
-                                        n_sc, 0, 8, st);
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp, (const u8 *)W.ranks.p, (u8 *)W.ranks_out.p, (const int *)W.iota.p, order,
+                                        n_sc, 0, 8, sp);
+        CK(W.cubtmp.ensure(tmp));
+        cub::DeviceRadixSort::SortPairs(W.cubtmp.p, tmp, (const u8 *)W.ranks.p, (u8 *)W.ranks_out.p, (const int *)W.iota.p, order,
+                                        n_sc, 0, 8, sp);
     }
-    S.n_launches += 5;
-    publish_kernel<<<1, 64, 0, st>>>((const u32 *)dcnt, (u32 *)h->h_counters, (int)(sizeof(PlanCounters) / 4));
-    CK(cudaEventRecord(h->ev[1], st));
-    CK(cudaStreamSynchronize(st));          // counters are now on the host
+    h->stats.n_launches += 6;
+    publish_kernel<<<1, 64, 0, sp>>>((const u32 *)dcnt, (u32 *)W.h_counters, (int)(sizeof(PlanCounters) / 4));
+    CK(cudaEventRecord(W.ev[1], sp));
+    return VD_OK;
+}
+
+static int chunk_exec(vd_handle *h, Work &W) {
+    cudaStream_t st = h->stream;
+    const BatchDev &in = W.in;
+    const OutDev &out = W.out;
+    const int n_sc = in.n_sc;
+    vd_stats &S = h->stats;
+    const bool trace = getenv("VD_TRACE") != nullptr;
+    ScPlan *plan = (ScPlan *)W.plan.p;
+    int *list = (int *)W.list.p;
+    int *order = (int *)W.order.p;
+    CK(cudaEventSynchronize(W.ev[1]));       // counters are now on the host
     CK(cudaGetLastError());
-    const PlanCounters pc = *h->h_counters;
-    if (trace) fprintf(stderr, "[run_resident] plan done at %.2f ms\n", now_ms() - t_r0);
+    const PlanCounters pc = *W.h_counters;
+    W.n_bad = pc.n_bad;
+    CK(cudaStreamWaitEvent(st, W.ev[1], 0));
 
     // ---- short superclusters: one fused launch per group, most expensive group first: the warp
     //      kernel's (slots, shared-memory bin) groups on the side streams (they are latency-bound and
     //      overlap with each other and with everything else), the thread-per-alignment classes on the
     //      main stream ----
     int n_small = 0;
-    bool grp_used[N_GROUP] = {};
-    CK(cudaEventRecord(h->ev[5], st));
+    CK(cudaEventRecord(W.ev5, st));
     for (int g = N_GROUP - 1; g >= 0; g--) {
         const int cnt = pc.grp_count[g];
         if (cnt <= 0) continue;
         const int g0 = g >> 1;                               // group without the homozygous bit
         const bool hom = g & 1;
         cudaStream_t gs = (g0 < N_SMALL || h->serial) ? st : h->side[(g - 2 * N_SMALL) % N_WCLS];
-        if (gs != st) CK(cudaStreamWaitEvent(gs, h->ev[5], 0));
-        CK(cudaEventRecord(h->gev[g][0], gs));
+        if (gs != st) CK(cudaStreamWaitEvent(gs, W.ev5, 0));
+        CK(cudaEventRecord(W.gev[g][0], gs));
         if (g0 < N_SMALL) small_launch(gs, g0, hom, in, out, plan, order + pc.grp_first[g], cnt);
         else {
             const int w = g0 - N_SMALL;                      // (slots - 1) * N_WBIN + (N_WBIN - 1 - bin)
             wsc_launch(gs, w / N_WBIN + 1, N_WBIN - 1 - w % N_WBIN, hom, in, out, plan, order + pc.grp_first[g], cnt);
         }
-        CK(cudaEventRecord(h->gev[g][1], gs));
-        grp_used[g] = true;
+        CK(cudaEventRecord(W.gev[g][1], gs));
+        W.grp_used[g] = true;
         S.n_launches++;
         n_small += cnt;
         const int k = g0 < N_SMALL ? g0 : N_SMALL;
@@ -260,7 +303,7 @@ static int run_resident(vd_handle *h, const BatchDev &in, const OutDev &out, con
         S.io_small[k] += (int64_t)pc.io_grp[g];
         if (hom) S.n_hom += cnt;
     }
-    CK(cudaEventRecord(h->ev[2], st));
+    CK(cudaEventRecord(W.ev[2], st));
     S.cells += (int64_t)pc.cells;
     S.n_long += 4 * (int64_t)pc.n_list;
     S.n_short += 4 * (int64_t)n_small;
@@ -376,27 +419,40 @@ static int run_resident(vd_handle *h, const BatchDev &in, const OutDev &out, con
             i0 = i1;
         }
     }
-    if (!h->serial) for (int g = 2 * N_SMALL; g < N_GROUP; g++) if (grp_used[g]) CK(cudaStreamWaitEvent(st, h->gev[g][1], 0));
-    status_or_kernel<<<296, 256, 0, st>>>(out.status, 4 * (int64_t)n_sc, &((PlanCounters *)h->counters.p)->status_or);
+    // join on the epilogue stream: the main stream is free for the next chunk while this chunk's
+    // side-stream groups drain
+    cudaStream_t se = h->serial ? st : h->s_epi;
+    if (se != st) {
+        CK(cudaEventRecord(W.evL, st));
+        CK(cudaStreamWaitEvent(se, W.evL, 0));
+        for (int g = 2 * N_SMALL; g < N_GROUP; g++) if (W.grp_used[g]) CK(cudaStreamWaitEvent(se, W.gev[g][1], 0));
+    }
+    status_or_kernel<<<296, 256, 0, se>>>(out.status, 4 * (int64_t)n_sc, &((PlanCounters *)W.counters.p)->status_or);
     S.n_launches++;
-    publish_kernel<<<1, 64, 0, st>>>((const u32 *)h->counters.p, (u32 *)h->h_counters, (int)(sizeof(PlanCounters) / 4));
-    CK(cudaEventRecord(h->ev[3], st));
-    if (trace) fprintf(stderr, "[run_resident] all launched at %.2f ms\n", now_ms() - t_r0);
-    CK(cudaStreamSynchronize(st));
+    publish_kernel<<<1, 64, 0, se>>>((const u32 *)W.counters.p, (u32 *)W.h_counters, (int)(sizeof(PlanCounters) / 4));
+    CK(cudaEventRecord(W.ev[3], se));
+    W.ms_fwd = ms_fwd; W.ms_bwd = ms_bwd; W.ms_walk = ms_walk;
+    return VD_OK;
+}
+
+static int chunk_harvest(vd_handle *h, Work &W) {
+    if (!W.busy) return VD_OK;
+    W.busy = false;
+    vd_stats &S = h->stats;
+    CK(cudaEventSynchronize(W.ev[3]));
     CK(cudaGetLastError());
-    if (trace) fprintf(stderr, "[run_resident] finished at %.2f ms\n", now_ms() - t_r0);
-    h->stats_status_or |= h->h_counters->status_or;
+    h->stats_status_or |= W.h_counters->status_or;
     float e_ = 0;
-    cudaEventElapsedTime(&e_, h->ev[0], h->ev[1]); S.ms_plan += e_;
-    cudaEventElapsedTime(&e_, h->ev[1], h->ev[2]); S.ms_short += e_;
-    cudaEventElapsedTime(&e_, h->ev[0], h->ev[3]); S.ms_total += e_;
-    S.ms_long_fwd += ms_fwd; S.ms_long_bwd += ms_bwd; S.ms_long_walk += ms_walk;
+    cudaEventElapsedTime(&e_, W.ev[0], W.ev[1]); S.ms_plan += e_;
+    cudaEventElapsedTime(&e_, W.ev5, W.ev[2]); S.ms_short += e_;
+    cudaEventElapsedTime(&e_, W.ev[0], W.ev[3]); S.ms_total += e_;      // chunk spans overlap in vd_run
+    S.ms_long_fwd += W.ms_fwd; S.ms_long_bwd += W.ms_bwd; S.ms_long_walk += W.ms_walk;
     for (int g = 0; g < N_GROUP; g++) {       // per-group durations of the short kernels (the warp kernel's overlap)
-        if (!grp_used[g]) continue;
-        cudaEventElapsedTime(&e_, h->gev[g][0], h->gev[g][1]);
+        if (!W.grp_used[g]) continue;
+        cudaEventElapsedTime(&e_, W.gev[g][0], W.gev[g][1]);
         S.ms_small[(g >> 1) < N_SMALL ? (g >> 1) : N_SMALL] += e_;
     }
-    if (pc.n_bad > 0) return fail(h, VD_E_BADINPUT, "%d malformed superclusters", pc.n_bad);
+    if (W.n_bad > 0) return fail(h, VD_E_BADINPUT, "%d malformed superclusters", W.n_bad);
     return VD_OK;
 }
 
@@ -418,7 +474,11 @@ extern "C" int vd_run_device(vd_handle *h, const vd_batch_in *in, vd_batch_out *
     h->stats_status_or = 0;
     h->stats.n_sc = in->n_sc; h->stats.n_var = n_var;
     h->stats.io_bytes = io_bytes_of(in->n_sc, n_var, ref_bytes, alt_bytes);
-    return run_resident(h, b, o, o);
+    Work &W = h->work[0];
+    int rc = chunk_plan(h, W, h->stream, b, o, o);
+    if (rc == VD_OK) rc = chunk_exec(h, W);
+    const int rc2 = chunk_harvest(h, W);
+    return rc != VD_OK ? rc : rc2;
 }
 
 extern "C" int vd_run(vd_handle *h, const vd_batch_in *in, vd_batch_out *out) {
@@ -467,6 +527,8 @@ extern "C" int vd_run(vd_handle *h, const vd_batch_in *in, vd_batch_out *out) {
     };
     auto upload = [&](int i) -> int {
         vd_handle::Stage &sg = h->stage[i & 1];
+        // the input buffers of this stage were read by chunk i-2: copy in only behind its last kernel
+        if (h->work[i & 1].busy) CK(cudaStreamWaitEvent(h->s_in, h->work[i & 1].ev[3], 0));
         const Range r = range_of(i);
         const int64_t ns = r.s1 - r.s0, nv = r.v1 - r.v0;
 #define UP(buf, src, bytes) do { CK(sg.buf.ensure((size_t)(bytes) + 16)); \
@@ -491,22 +553,24 @@ extern "C" int vd_run(vd_handle *h, const vd_batch_in *in, vd_batch_out *out) {
     const bool trace = getenv("VD_TRACE") != nullptr;
     auto now_ms = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
     const double t_start = now_ms();
-    int rc = upload(0);
-    if (rc != VD_OK) return rc;
-    for (int i = 0; i < n_chunks; i++) {
-        const double t_c0 = now_ms();
+    // chunk i: [H2D on s_in] -> [plan pass on s_plan] -> [kernels on st + side streams] -> [D2H on s_out];
+    // the host never waits for a chunk's kernels, only for its plan counters (and, two chunks later, for
+    // its end event when the work set is reused)
+    auto plan_chunk = [&](int i) -> int {
         vd_handle::Stage &sg = h->stage[i & 1];
+        Work &W = h->work[i & 1];
+        int rcp = chunk_harvest(h, W);                       // chunk i-2 used this work set
+        if (rcp != VD_OK && rcp != VD_E_BADINPUT) return rcp;
+        if (rcp != VD_OK) rc_all = rcp;
         const Range r = range_of(i);
         const int64_t ns = r.s1 - r.s0, nv = r.v1 - r.v0;
-        if (i + 1 < n_chunks) { rc = upload(i + 1); if (rc != VD_OK) return rc; }
         // result buffers of this stage are free once chunk i-2's copy-out has finished
-        if (sg.out_pending) { CK(cudaStreamWaitEvent(st, sg.out_done, 0)); sg.out_pending = false; }
+        if (sg.out_pending) { CK(cudaStreamWaitEvent(h->s_plan, sg.out_done, 0)); sg.out_pending = false; }
         CK(sg.o_score.ensure(16 * (size_t)ns)); CK(sg.o_endp.ensure(4 * (size_t)ns)); CK(sg.o_begp.ensure(4 * (size_t)ns));
         CK(sg.o_status.ensure(16 * (size_t)ns)); CK(sg.o_assigned.ensure(2 * (size_t)nv + 16));
         CK(sg.o_sg.ensure(8 * (size_t)nv + 16)); CK(sg.o_red.ensure(8 * (size_t)nv + 16));
         CK(sg.o_qed.ensure(8 * (size_t)nv + 16)); CK(sg.o_callq.ensure(8 * (size_t)nv + 16));
-        CK(cudaStreamWaitEvent(st, sg.in_done, 0));
-
+        CK(cudaStreamWaitEvent(h->s_plan, sg.in_done, 0));
         const u8 *d_ref = (const u8 *)sg.in_ref_seq.p - r.r0;
         const u8 *d_rpl = in->rplane_seq ? (const u8 *)sg.in_rplane.p - r.r0 : d_ref;
         BatchDev b{(int)ns, (const int64_t *)sg.in_ref_off.p, d_ref, d_rpl, (const int64_t *)sg.in_var_off.p,
@@ -518,14 +582,30 @@ extern "C" int vd_run(vd_handle *h, const vd_batch_in *in, vd_batch_out *out) {
                     (float *)sg.o_callq.p};
         OutDev o = base;                       // per-variant arrays are indexed [slot*nv + (v - v0)]
         o.assigned -= r.v0; o.sync_group -= r.v0; o.ref_ed -= r.v0; o.query_ed -= r.v0; o.callq -= r.v0;
-        const double t_c1 = now_ms();
-        rc = run_resident(h, b, o, base);      // returns with the chunk's kernels finished
-        const double t_c2 = now_ms();
-        if (trace) fprintf(stderr, "[vd_run] chunk %d: start %.2f ms, enqueue %.2f ms, run_resident %.2f ms (device %.2f ms so far)\n",
-                           i, t_c0 - t_start, t_c1 - t_c0, t_c2 - t_c1, h->stats.ms_total);
-        if (rc != VD_OK && rc != VD_E_BADINPUT) return rc;
-        if (rc != VD_OK) rc_all = rc;
+        return chunk_plan(h, W, h->s_plan, b, o, base);
+    };
 
+    int rc = upload(0);
+    if (rc != VD_OK) return rc;
+    rc = plan_chunk(0);
+    if (rc != VD_OK) return rc;
+    for (int i = 0; i < n_chunks; i++) {
+        const double t_c0 = now_ms();
+        vd_handle::Stage &sg = h->stage[i & 1];
+        Work &W = h->work[i & 1];
+        const Range r = range_of(i);
+        const int64_t ns = r.s1 - r.s0, nv = r.v1 - r.v0;
+        if (i + 1 < n_chunks) { rc = upload(i + 1); if (rc != VD_OK) return rc; }
+        const double t_c1 = now_ms();
+        rc = chunk_exec(h, W);                 // returns with the chunk's kernels issued
+        if (rc != VD_OK) return rc;
+        const double t_c2 = now_ms();
+        // the plan pass of the next chunk runs beside this chunk's kernels
+        if (i + 1 < n_chunks) { rc = plan_chunk(i + 1); if (rc != VD_OK) return rc; }
+        if (trace) fprintf(stderr, "[vd_run] chunk %d: start %.2f ms, upload %.2f ms, exec %.2f ms, plan next %.2f ms\n",
+                           i, t_c0 - t_start, t_c1 - t_c0, t_c2 - t_c1, now_ms() - t_c2);
+
+        CK(cudaStreamWaitEvent(h->s_out, W.ev[3], 0));      // copy-out behind the chunk's last kernel
 #define DOWN(dst, buf, off, bytes) do { if ((bytes) > 0) CK(cudaMemcpyAsync((dst), (const u8 *)sg.buf.p + (off), \
         (size_t)(bytes), cudaMemcpyDeviceToHost, h->s_out)); d2h += (bytes); } while (0)
         DOWN(out->aln_score + 4 * r.s0, o_score, 0, 16 * ns);
@@ -543,6 +623,11 @@ extern "C" int vd_run(vd_handle *h, const vd_batch_in *in, vd_batch_out *out) {
 #undef DOWN
         CK(cudaEventRecord(sg.out_done, h->s_out));
         sg.out_pending = true;
+    }
+    for (auto &W : h->work) {
+        const int rch = chunk_harvest(h, W);
+        if (rch != VD_OK && rch != VD_E_BADINPUT) return rch;
+        if (rch != VD_OK) rc_all = rch;
     }
     const double t_e0 = now_ms();
     CK(cudaStreamSynchronize(h->s_out));
