@@ -53,7 +53,8 @@ struct Work {
 };
 
 struct vd_handle {
-    Work work[2];
+    static constexpr int NST = 3;           // chunks in flight in vd_run (staging + work sets)
+    Work work[NST];
     cudaStream_t s_plan = nullptr;          // plan pass of the next chunk
     cudaStream_t s_epi = nullptr;           // join of a chunk's launch groups + status reduction (the main stream moves on)
     int device = 0;
@@ -77,13 +78,13 @@ struct vd_handle {
     int use_hom = 1;                // VD_HOM=0: homozygous superclusters run all four alignments (testing)
     int use_wsc = 1;                // VD_WSC=0: mid-size superclusters go to the HBM-slab path instead of the warp kernel
     // staged input / output (vd_run)
-    struct Stage {                  // one of two staging sets of the host-buffer pipeline
+    struct Stage {                  // one of the staging sets of the host-buffer pipeline
         DevBuf in_ref_off, in_ref_seq, in_rplane, in_var_off, in_var_pos, in_var_rlen, in_var_type,
                in_alt_off, in_alt_seq, in_var_qual;
         DevBuf o_score, o_endp, o_begp, o_status, o_assigned, o_sg, o_red, o_qed, o_callq;
         cudaEvent_t in_done = nullptr, out_done = nullptr;
         bool out_pending = false;
-    } stage[2];
+    } stage[NST];
     cudaStream_t s_in = nullptr, s_out = nullptr;
     int ramp = 1;                   // VD_RAMP=0: uniform chunks
     int64_t chunk_sc = 1048576;      // superclusters per pipeline chunk (VD_CHUNK_SC)
@@ -526,9 +527,9 @@ extern "C" int vd_run(vd_handle *h, const vd_batch_in *in, vd_batch_out *out) {
         return r;
     };
     auto upload = [&](int i) -> int {
-        vd_handle::Stage &sg = h->stage[i & 1];
-        // the input buffers of this stage were read by chunk i-2: copy in only behind its last kernel
-        if (h->work[i & 1].busy) CK(cudaStreamWaitEvent(h->s_in, h->work[i & 1].ev[3], 0));
+        vd_handle::Stage &sg = h->stage[i % vd_handle::NST];
+        // the input buffers of this stage were read by chunk i-NST: copy in only behind its last kernel
+        if (h->work[i % vd_handle::NST].busy) CK(cudaStreamWaitEvent(h->s_in, h->work[i % vd_handle::NST].ev[3], 0));
         const Range r = range_of(i);
         const int64_t ns = r.s1 - r.s0, nv = r.v1 - r.v0;
 #define UP(buf, src, bytes) do { CK(sg.buf.ensure((size_t)(bytes) + 16)); \
@@ -554,17 +555,17 @@ extern "C" int vd_run(vd_handle *h, const vd_batch_in *in, vd_batch_out *out) {
     auto now_ms = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
     const double t_start = now_ms();
     // chunk i: [H2D on s_in] -> [plan pass on s_plan] -> [kernels on st + side streams] -> [D2H on s_out];
-    // the host never waits for a chunk's kernels, only for its plan counters (and, two chunks later, for
+    // the host never waits for a chunk's kernels, only for its plan counters (and, NST chunks later, for
     // its end event when the work set is reused)
     auto plan_chunk = [&](int i) -> int {
-        vd_handle::Stage &sg = h->stage[i & 1];
-        Work &W = h->work[i & 1];
-        int rcp = chunk_harvest(h, W);                       // chunk i-2 used this work set
+        vd_handle::Stage &sg = h->stage[i % vd_handle::NST];
+        Work &W = h->work[i % vd_handle::NST];
+        int rcp = chunk_harvest(h, W);                       // chunk i-NST used this work set
         if (rcp != VD_OK && rcp != VD_E_BADINPUT) return rcp;
         if (rcp != VD_OK) rc_all = rcp;
         const Range r = range_of(i);
         const int64_t ns = r.s1 - r.s0, nv = r.v1 - r.v0;
-        // result buffers of this stage are free once chunk i-2's copy-out has finished
+        // result buffers of this stage are free once chunk i-NST's copy-out has finished
         if (sg.out_pending) { CK(cudaStreamWaitEvent(h->s_plan, sg.out_done, 0)); sg.out_pending = false; }
         CK(sg.o_score.ensure(16 * (size_t)ns)); CK(sg.o_endp.ensure(4 * (size_t)ns)); CK(sg.o_begp.ensure(4 * (size_t)ns));
         CK(sg.o_status.ensure(16 * (size_t)ns)); CK(sg.o_assigned.ensure(2 * (size_t)nv + 16));
@@ -591,8 +592,8 @@ extern "C" int vd_run(vd_handle *h, const vd_batch_in *in, vd_batch_out *out) {
     if (rc != VD_OK) return rc;
     for (int i = 0; i < n_chunks; i++) {
         const double t_c0 = now_ms();
-        vd_handle::Stage &sg = h->stage[i & 1];
-        Work &W = h->work[i & 1];
+        vd_handle::Stage &sg = h->stage[i % vd_handle::NST];
+        Work &W = h->work[i % vd_handle::NST];
         const Range r = range_of(i);
         const int64_t ns = r.s1 - r.s0, nv = r.v1 - r.v0;
         if (i + 1 < n_chunks) { rc = upload(i + 1); if (rc != VD_OK) return rc; }
@@ -632,7 +633,7 @@ extern "C" int vd_run(vd_handle *h, const vd_batch_in *in, vd_batch_out *out) {
     const double t_e0 = now_ms();
     CK(cudaStreamSynchronize(h->s_out));
     if (trace) fprintf(stderr, "[vd_run] drain %.2f ms, total %.2f ms\n", now_ms() - t_e0, now_ms() - t_start);
-    h->stage[0].out_pending = h->stage[1].out_pending = false;
+    for (auto &sg : h->stage) sg.out_pending = false;
     h->stats.h2d_bytes = h2d;
     h->stats.d2h_bytes = d2h;
     if (rc_all != VD_OK) return rc_all;
