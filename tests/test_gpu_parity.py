@@ -145,6 +145,13 @@ def test_adversarial_seeds(engine, seed):
     check_vs_oracle(engine, synth.adversarial(seed, 800, max_len=20 + 15 * (seed - 200)))
 
 
+@pytest.mark.parametrize("seed,max_len", [(301, 8), (302, 12), (303, 18), (304, 26), (305, 40), (306, 58)])
+def test_adversarial_sweep_over_kernel_boundaries(engine, seed, max_len):
+    """Window lengths straddling every kernel boundary (thread-per-alignment classes 0/1, warp kernel with
+    1-4 register slots and every shared-memory bin, HBM-slab path), 1500 superclusters each."""
+    check_vs_oracle(engine, synth.adversarial(seed, 1500, max_len=max_len))
+
+
 def test_wgs_like_mixture(engine):
     b = synth.wgs_like(5, 20000, sv_frac=0.003, sv_max=1500)
     got = check_vs_oracle(engine, b)
@@ -163,6 +170,50 @@ def test_divergent_sv_pairs(engine, length, div):
     """Long alignments whose score exceeds the banded sweep's bounds (96/384/1536): retries and
     the dense fallback must give the same bits."""
     check_vs_oracle(engine, synth.sv_pairs(5, 1, length, divergence=div))
+
+
+def _long_mixed_batch(seed, n_sc):
+    """Long alignments (hundreds to thousands of rows) in which the banded forward sweep succeeds but the
+    optimal paths carry long runs: a big insertion shared by truth and query (large matrices), plus an
+    insertion only the query has (a run of insertion moves longer than the windowed backward sweep's
+    margin, so its chain follower has to continue below the window), a deletion only the truth has, and
+    scattered substitutions.  Mixed zygosity, so that all four alignments differ."""
+    rng = np.random.default_rng(seed)
+    A = b"ACGT"
+    bb = BatchBuilder()
+    for i in range(n_sc):
+        W = int(rng.integers(260, 420))
+        ref = bytes(rng.choice(list(A), W).tolist())
+        big = bytes(rng.choice(list(A), int(rng.integers(300, 1500))).tolist())
+        shared = (40, TYPE_INS, 0, big, 30.0)
+        q_only = (120, TYPE_INS, 0, bytes(rng.choice(list(A), int(rng.integers(30, 260))).tolist()), 22.0)
+        t_only = (180, TYPE_DEL, int(rng.integers(30, 70)), b"", 40.0)
+        def subs(lo, hi, n, qual):
+            out, used = [], set()
+            for p_ in sorted(set(int(x) for x in rng.integers(lo, hi, n))):
+                alt = A[(A.index(ref[p_]) + 1 + int(rng.integers(0, 3))) % 4]
+                out.append((p_, TYPE_SUB, 1, bytes([alt]), qual))
+            return out
+        q1 = [shared, q_only] + subs(W - 60, W - 2, 3, 15.0)
+        q2 = [shared] if i % 2 else []
+        t1 = [shared, t_only] + subs(W - 60, W - 2, 2, 33.0)
+        t2 = [shared] if i % 3 else [t_only]
+        for lst in (q1, q2, t1, t2):
+            lst.sort(key=lambda v: (v[0], v[1] != TYPE_INS))
+        bb.add(ref, [q1, q2, t1, t2])
+    return bb.build()
+
+
+def test_long_alignments_with_one_sided_runs(engine):
+    """Windowed backward sweep (chain follower, swap targets across planes), dense backward sweep for the
+    alignments above the last score bound, walk over long insertion / deletion runs."""
+    b = _long_mixed_batch(17, 24)
+    check_vs_oracle(engine, b)
+    st = engine.stats()
+    assert st["n_long"] == 4 * b.n_sc
+    e = engine_with(VD_SPARSE_BWD=1)          # the frontier kernel must agree as well
+    check_vs_oracle(e, b)
+    e.close()
 
 
 def test_dense_paths_match_banded_and_sparse(engine):
