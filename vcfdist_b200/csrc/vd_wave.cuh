@@ -1237,7 +1237,10 @@ __global__ void __launch_bounds__(32) wave_sbwd_kernel(WaveArgs A, int item0, in
 // dependent HBM/L2 round trips.
 // ------------------------------------------------------------------------------------------
 constexpr int BWDB_TPB = 256;
-constexpr int BWDB_E = 24;             // rows below the lowest target that are looked at without the chain follower
+#ifndef VD_BWDB_E
+#define VD_BWDB_E 24
+#endif
+constexpr int BWDB_E = VD_BWDB_E;             // rows below the lowest target that are looked at without the chain follower
 __host__ __device__ inline int bwdb_smem(int npmax) { return 6 * npmax + 128 * 4; }
 
 __global__ void __launch_bounds__(BWDB_TPB) wave_bwdb_kernel(WaveArgs A, int item0, int npmax, const int *need_dense) {
