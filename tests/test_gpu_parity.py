@@ -167,7 +167,7 @@ def test_sv_lengths(engine, length):
 
 @pytest.mark.parametrize("length,div", [(1400, 0.3), (2300, 0.9), (700, 1.0)])
 def test_divergent_sv_pairs(engine, length, div):
-    """Long alignments whose score exceeds the banded sweep's bounds (96/384/1536): retries and
+    """Long alignments whose score exceeds the banded sweep's bounds (80 ... 1280): retries and
     the dense fallback must give the same bits."""
     check_vs_oracle(engine, synth.sv_pairs(5, 1, length, divergence=div))
 

@@ -24,7 +24,7 @@
 namespace vd {
 
 constexpr int kBigClass = CLS_WAVE;
-constexpr int FWD_TAU0 = 96;       // first score bound of the forward sweep (then x4 per retry)
+constexpr int FWD_TAU0 = 96;       // first score bound of the register-blocked forward sweep (then x4 per retry)
 
 // ---- per-hap tables the wavefront kernels need, built once per supercluster --------------
 // srcinfo: bit0 valid, bits1-3 k (index in the destination's source list), bit4 tp(dest),
@@ -570,11 +570,13 @@ __device__ __forceinline__ void wave_fwd_body(const WaveCtxT<TT> &X, const int t
 // is thousands, so rows are dealt ONE per thread from the band's start in every column (D of the
 // previous column lives in shared memory for all rows, so the thread<->row mapping is free to
 // slide with the band); bands wider than the block are processed in chunks with the INS-chain
-// carry handed from chunk to chunk.  tau = 96, 384, 1536; alignments that need more are flagged
+// carry handed from chunk to chunk.  tau = 80, 160, ... 1280 (with tau = 80 the candidate rows of both planes,
+// 2 x (2 tau + 1 + tau), fit one 512-thread chunk); alignments that need more are flagged
 // for the dense register-blocked kernel.
 // ------------------------------------------------------------------------------------------
 constexpr int FWDB_TPB = 512;
-constexpr int FWDB_TAU_MAX = 1536;
+constexpr int FWDB_TAU0 = 80;
+constexpr int FWDB_TAU_MAX = 1280;
 __host__ __device__ inline int fwdb_smem(int npmax) { return 4 * npmax + 32 + 2 * 64 * 4 + 64; }
 
 __global__ void __launch_bounds__(FWDB_TPB) wave_fwdb_kernel(WaveArgs A, int item0, int npmax, int *need_dense) {
@@ -611,7 +613,7 @@ __global__ void __launch_bounds__(FWDB_TPB) wave_fwdb_kernel(WaveArgs A, int ite
     }
     const int score_lb = s_lb;
 
-    for (int tau = FWD_TAU0; tau <= FWDB_TAU_MAX && !solved; tau *= 4) {
+    for (int tau = FWDB_TAU0; tau <= FWDB_TAU_MAX && !solved; tau *= 2) {
         if (tau < score_lb) continue;
         for (int r = t; r < NPr; r += FWDB_TPB) { sD0[r] = 0xffff; sD1[r] = 0xffff; }
         if (t == 0) {
