@@ -208,6 +208,9 @@ def main():
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--ref-sample", type=int, default=600_000, help="superclusters in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather-slices", type=int, default=0,
+                    help="N > 1: slices of a rank's shard whose result all-gather overlaps the next slice's kernels "
+                         "(0 = by world size: 1 up to 2 GPUs, 2 up to 4, 3 beyond - the exchange grows with the number of ranks)")
     ap.add_argument("--secondary", action="store_true", default=True,
                     help="also time the SV-bearing workload (BASELINE configs[3]) at 1/9 scale through vd_run (default at N=1)")
     ap.add_argument("--no-secondary", dest="secondary", action="store_false")
@@ -248,34 +251,71 @@ def main():
         setattr(din, k, t.data_ptr())
     din.rplane_seq = None
     din.max_qual = b.max_qual
-    # results live in ONE contiguous record buffer (shard.ResultRecord): the kernels write straight
-    # into it and the end-of-step exchange is a single all-gather with no packing
-    cap = torch.tensor([b.n_sc, n_var], dtype=torch.int64, device=dev)
+    # Results live in contiguous record buffers (shard.ResultRecord): the kernels write straight into
+    # them and the end-of-step exchange is an all-gather with no packing.  With several GPUs the shard
+    # is run in `--gather-slices` slices (vd_run_device_slice), each with its own record, so that the
+    # all-gather of slice k (on a side stream) overlaps the kernels of slice k+1; one GPU: one slice.
+    K = (args.gather_slices or (1 if world <= 2 else 2 if world <= 4 else 3)) if world > 1 else 1
+    s_cut = [b.n_sc * k // K for k in range(K + 1)]
+    v_cut = [int(b.var_off[4 * c]) for c in s_cut]
+    counts = torch.tensor([[s_cut[k + 1] - s_cut[k], v_cut[k + 1] - v_cut[k]] for k in range(K)], dtype=torch.int64, device=dev)
     off_sc = off_var = 0
     if world > 1:
-        allc = [torch.zeros(2, dtype=torch.int64, device=dev) for _ in range(world)]
-        dist.all_gather(allc, cap)
-        allc = torch.stack(allc).cpu().numpy()
-        off_sc, off_var = int(allc[:rank, 0].sum()), int(allc[:rank, 1].sum())
-        cap_sc, cap_var = int(allc[:, 0].max()), int(allc[:, 1].max())
+        allc = [torch.zeros_like(counts) for _ in range(world)]
+        dist.all_gather(allc, counts)
+        allc = torch.stack(allc).cpu().numpy()                      # [world, K, 2]
+        off_sc, off_var = int(allc[:rank, :, 0].sum()), int(allc[:rank, :, 1].sum())
+        caps = allc.max(axis=0)                                     # [K, 2]
     else:
-        cap_sc, cap_var = b.n_sc, n_var
-    rec = shard.ResultRecord(cap_sc, max(cap_var, 1), dev)
-    # batch-global indices of this rank's records (ranks own disjoint ranges of the global arrays)
-    rec.set_shard(np.arange(off_sc, off_sc + b.n_sc), np.arange(off_var, off_var + n_var))
-    d_out = {k: rec.views[k] for k in ("aln_score", "aln_end_plane", "aln_beg_plane", "status", "assigned",
-                                       "sync_group", "ref_ed", "query_ed", "callq")}
-    dout = vd_batch_out()
-    for k, t in d_out.items():
-        setattr(dout, k, t.data_ptr())
-    gathered = torch.empty(world * rec.nbytes, dtype=torch.uint8, device=dev) if world > 1 else None
+        caps = counts.cpu().numpy()
+    recs, slices, gathered = [], [], []
+    for k in range(K):
+        s0, s1, v0, v1 = s_cut[k], s_cut[k + 1], v_cut[k], v_cut[k + 1]
+        rec = shard.ResultRecord(int(caps[k, 0]), max(int(caps[k, 1]), 1), dev)
+        # batch-global indices of this slice's records (ranks own disjoint ranges of the global arrays)
+        rec.set_shard(np.arange(off_sc + s0, off_sc + s1), np.arange(off_var + v0, off_var + v1))
+        din_k = vd_batch_in()
+        din_k.n_sc = s1 - s0
+        for name, t in d_in.items():
+            setattr(din_k, name, t.data_ptr())
+        din_k.ref_off = d_in["ref_off"].data_ptr() + 8 * s0
+        din_k.var_off = d_in["var_off"].data_ptr() + 8 * 4 * s0
+        din_k.rplane_seq = None
+        din_k.max_qual = b.max_qual
+        dout_k = vd_batch_out()
+        for name in ("aln_score", "aln_end_plane", "aln_beg_plane", "status", "assigned", "sync_group", "ref_ed", "query_ed", "callq"):
+            setattr(dout_k, name, rec.views[name].data_ptr())
+        recs.append(rec)
+        slices.append((din_k, dout_k, v0, v1 - v0))
+        gathered.append(torch.empty(world * rec.nbytes, dtype=torch.uint8, device=dev) if world > 1 else None)
+    rec, dout = recs[0], slices[0][1]          # one GPU: the whole shard is slice 0
+    comm = torch.cuda.Stream(device=dev) if world > 1 else None
     torch.cuda.synchronize()
+    step_stats = {}
+
+    def run_pass(engine, acc, exchange):
+        """One pass of the hot path over this rank's shard, slice by slice (+ the exchange)."""
+        acc.clear()
+        for k in range(K):
+            din_k, dout_k, v0, nv = slices[k]
+            if K == 1:
+                engine.run_device(din, dout, n_var, b.ref_bytes, b.alt_bytes)
+            else:
+                engine.run_device_slice(din_k, dout_k, v0, nv, b.ref_bytes // K, b.alt_bytes // K)
+            st_ = engine.stats()               # returns with the slice's kernels finished
+            for key, val in st_.items():
+                if isinstance(val, list):
+                    acc[key] = [x + y for x, y in zip(acc.get(key, [0] * len(val)), val)]
+                else:
+                    acc[key] = acc.get(key, 0) + val
+            if exchange and world > 1:
+                with torch.cuda.stream(comm):
+                    recs[k].all_gather(dist, gathered[k])
+        if exchange and world > 1:
+            stream.wait_stream(comm)           # the step ends when the last slice has been exchanged
 
     def step_resident():
-        eng.run_device(din, dout, n_var, b.ref_bytes, b.alt_bytes)
-        if world > 1:
-            with torch.cuda.stream(stream):
-                rec.all_gather(dist, gathered)
+        run_pass(eng, step_stats, True)
 
     def barrier():
         if world > 1:
@@ -296,7 +336,7 @@ def main():
     ev0.record(stream)
     for _ in range(args.steps):
         step_resident()
-        st = eng.stats()
+        st = dict(step_stats)
         launches += st["n_launches"]
         ms_short += st["ms_short"]; ms_fwd += st["ms_long_fwd"]; ms_bwd += st["ms_long_bwd"]
         ms_walk += st["ms_long_walk"]; ms_plan += st["ms_plan"]; ms_kernels += st["ms_total"]
@@ -309,7 +349,7 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
-    st = eng.stats()
+    st = dict(step_stats)
 
     # ---- e2e: vd_run() with pinned host buffers, H2D + D2H inside the timed region ----
     def pin(a):
@@ -323,16 +363,17 @@ def main():
     ho = Out(b.n_sc, n_var)
     for f in Out.FIELDS:
         t_, a_ = pin(getattr(ho, f)); keep.append(t_); setattr(ho, f, a_)
-    for _ in range(2):
+    for _ in range(3):
         eng.run(bp, ho)
     barrier()
-    t0 = time.perf_counter()
-    e2e_steps = max(2, min(args.steps, 5))
-    for _ in range(e2e_steps):
+    e2e_steps = max(3, min(args.steps, 7))
+    e2e_times = []
+    for _ in range(e2e_steps):                 # vd_run is synchronous: results are in host memory on return
+        t0 = time.perf_counter()
         eng.run(bp, ho)
-        launches_e2e = eng.stats()["n_launches"]
+        e2e_times.append((time.perf_counter() - t0) * 1e3)
     torch.cuda.synchronize()
-    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    e2e_ms = float(np.mean(e2e_times))
     st_e = eng.stats()
     te = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -358,9 +399,9 @@ def main():
         ser = {"small_kernel<0>": [0.0, 0.0], "small_kernel<1>": [0.0, 0.0], "wsc_kernel<S>": [0.0, 0.0], "wave_fwd_kernel": [0.0, 0.0]}
         SER_STEPS = 3
         for i in range(2 + SER_STEPS):
-            eng_s.run_device(din, dout, n_var, b.ref_bytes, b.alt_bytes)
+            ss = {}
+            run_pass(eng_s, ss, False)
             if i >= 2:
-                ss = eng_s.stats()
                 for k_, nm in enumerate(("small_kernel<0>", "small_kernel<1>", "wsc_kernel<S>")):
                     ser[nm][0] += ss["ms_small"][k_] / SER_STEPS; ser[nm][1] += float(ss["io_small"][k_]) / SER_STEPS
                 ser["wave_fwd_kernel"][0] += ss["ms_long_fwd"] / SER_STEPS; ser["wave_fwd_kernel"][1] += ss["spill_bytes"] / 3.0 / SER_STEPS
@@ -381,13 +422,14 @@ def main():
                        "source": "superclusters resampled (seeded) from the real HG002 chr1:1-5Mb demo batch"
                                  + (" + synthetic SV tail" if WORKLOADS[args.workload]["sv_frac"] else ""),
                        "n_superclusters_per_step": sc_total, "cells_per_step": cells_total,
-                       "per_gpu_superclusters": b.n_sc, "parallelism": f"shard{world}+allgather" if world > 1 else "single",
+                       "per_gpu_superclusters": b.n_sc, "parallelism": f"shard{world}+allgather({K} overlapped slices)" if world > 1 else "single",
                        "l2": "inputs+outputs exceed L2 (no flush needed)" if b.io_bytes() > 200e6 else "small batch: L2-resident"},
             "clocks": clocks,
             "e2e": {"value": cells_total / (e2e_ms * 1e-3) / 1e9, "unit": "Gcells/s",
                     "superclusters_per_s": sc_total / (e2e_ms * 1e-3), "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(st_e["h2d_bytes"]), "d2h_bytes_per_step": int(st_e["d2h_bytes"]),
-                    "api": "vd_run (C-ABI, pinned host buffers)"},
+                    "api": "vd_run (C-ABI, pinned host buffers)", "steps": e2e_steps,
+                    "ms_min": float(min(e2e_times)), "ms_max": float(max(e2e_times))},
             "gpu_launches": int(launches),
             "kernel_ms_per_step": {"plan": ms_plan / args.steps, "short_region": k_short, "small_kernel<0>": k_small[0],
                                    "small_kernel<1>": k_small[1], "wsc_kernel<S>(sum, overlapping)": k_small[2],

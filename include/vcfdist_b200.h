@@ -183,6 +183,15 @@ int  vd_run(vd_handle *h, const vd_batch_in *in, vd_batch_out *out);
 int  vd_run_device(vd_handle *h, const vd_batch_in *in_dev, vd_batch_out *out_dev,
                    int64_t n_var, int64_t ref_bytes, int64_t alt_bytes);
 
+/* A slice of a resident batch: superclusters [first_sc, first_sc + in_dev->n_sc) of the batch whose
+ * arrays in_dev points at - ref_off and var_off are passed already advanced to the slice (ref_off +
+ * first_sc, var_off + 4*first_sc), every other array whole, since the offsets stay batch-absolute.
+ * first_var = var_off[4*first_sc] and n_var = the slice's variant count.  out_dev holds the SLICE's
+ * own result arrays ([4*n_sc] and [2*n_var], slot stride n_var).  Lets a caller overlap the exchange
+ * of one slice's results (all-gather, copy-out) with the kernels of the next.                       */
+int  vd_run_device_slice(vd_handle *h, const vd_batch_in *in_dev, vd_batch_out *out_dev,
+                         int64_t first_var, int64_t n_var, int64_t ref_bytes, int64_t alt_bytes);
+
 int  vd_get_stats(const vd_handle *h, vd_stats *out);
 const char *vd_last_error(const vd_handle *h);
 

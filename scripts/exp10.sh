@@ -1,6 +1,5 @@
 mkdir -p gpurun_out/e10
 {
-nvidia-smi -L
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 3 --warmup 3
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 1 --warmup 1
-} > gpurun_out/e10/log 2>&1; tail -c 6000 gpurun_out/e10/log
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 4 --steps 3 --warmup 3 --gather-slices 1 2>&1 | grep '^{' | python scripts/benchsum.py
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 4 --steps 3 --warmup 3 2>&1 | grep '^{' | python scripts/benchsum.py
+} > gpurun_out/e10/log4 2>&1; tail -c 3000 gpurun_out/e10/log4

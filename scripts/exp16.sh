@@ -1,0 +1,5 @@
+mkdir -p gpurun_out/e16
+{
+timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
+python bench.py --steps 3 --no-cpu-baseline --no-secondary | python scripts/benchsum.py
+} > gpurun_out/e16/log 2>&1; cat gpurun_out/e16/log

@@ -285,6 +285,51 @@ def test_idempotent_and_order_independent(engine):
         assert (ap[k].reshape(2, -1) == x).all(), k
 
 
+def test_device_slices_match_whole_batch(engine):
+    """vd_run_device_slice on four slices of a device-resident batch writes the same records as one
+    vd_run_device over the whole batch (and as the oracle)."""
+    import torch
+    from vcfdist_b200.batch import vd_batch_in, vd_batch_out
+    b = synth.wgs_like(21, 6000, sv_frac=0.003, sv_max=500)
+    want = capi.oracle_run(b).trimmed()
+    dev = torch.device("cuda", 0)
+    names = ("ref_off", "ref_seq", "var_off", "var_pos", "var_rlen", "var_type", "alt_off", "alt_seq", "var_qual")
+    d_in = {k: torch.from_numpy(getattr(b, k)).to(dev) for k in names}
+    fields = {"aln_score": (torch.int32, 4, "sc"), "aln_end_plane": (torch.uint8, 4, "sc"), "aln_beg_plane": (torch.uint8, 4, "sc"),
+              "status": (torch.int32, 4, "sc"), "assigned": (torch.uint8, 2, "var"), "sync_group": (torch.int32, 2, "var"),
+              "ref_ed": (torch.int32, 2, "var"), "query_ed": (torch.int32, 2, "var"), "callq": (torch.float32, 2, "var")}
+    K = 4
+    cut = [b.n_sc * k // K for k in range(K + 1)]
+    vcut = [int(b.var_off[4 * c]) for c in cut]
+    got = {k: [] for k in fields}
+    for k in range(K):
+        ns, nv = cut[k + 1] - cut[k], vcut[k + 1] - vcut[k]
+        din = vd_batch_in()
+        din.n_sc = ns
+        for name, t in d_in.items():
+            setattr(din, name, t.data_ptr())
+        din.ref_off = d_in["ref_off"].data_ptr() + 8 * cut[k]
+        din.var_off = d_in["var_off"].data_ptr() + 32 * cut[k]
+        din.rplane_seq = None
+        din.max_qual = b.max_qual
+        outs = {name: torch.full((mult * (ns if kind == "sc" else max(nv, 1)),), 77, dtype=dt, device=dev)
+                for name, (dt, mult, kind) in fields.items()}
+        dout = vd_batch_out()
+        for name, t in outs.items():
+            setattr(dout, name, t.data_ptr())
+        engine.run_device_slice(din, dout, vcut[k], nv, 0, 0)
+        for name, (dt, mult, kind) in fields.items():
+            a = outs[name].cpu().numpy()
+            got[name].append(a if kind == "sc" else a[: 2 * nv].reshape(2, nv))
+    for name, (dt, mult, kind) in fields.items():
+        full = np.concatenate(got[name]) if kind == "sc" else np.concatenate(got[name], axis=1).reshape(-1)
+        w = want[name]
+        if w.dtype.kind == "f":
+            assert (full.view(np.uint32) == w.view(np.uint32)).all(), name
+        else:
+            assert (full.astype(np.int64) == w.astype(np.int64)).all(), name
+
+
 def test_chunked_pipeline_matches_single_pass():
     """vd_run splits big batches into double-buffered chunks (H2D / kernels / D2H overlapped);
     force tiny chunks so that a small batch crosses many chunk boundaries."""

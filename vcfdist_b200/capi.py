@@ -20,7 +20,7 @@ _ROOT = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_ROOT, "libvcfdist_b200.so")
 ORACLE_DIR = os.path.join(os.path.dirname(_ROOT), "oracle", "_ref")
 
-EXPORTS = ("vd_abi_version", "vd_create", "vd_destroy", "vd_run", "vd_run_device",
+EXPORTS = ("vd_abi_version", "vd_create", "vd_destroy", "vd_run", "vd_run_device", "vd_run_device_slice",
            "vd_finalize", "vd_get_stats", "vd_last_error", "vd_stream")
 
 _lib = None
@@ -48,6 +48,9 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.vd_run_device.argtypes = [C.c_void_p, C.POINTER(vd_batch_in), C.POINTER(vd_batch_out),
                                   C.c_int64, C.c_int64, C.c_int64]
     lib.vd_run_device.restype = C.c_int
+    lib.vd_run_device_slice.argtypes = [C.c_void_p, C.POINTER(vd_batch_in), C.POINTER(vd_batch_out),
+                                        C.c_int64, C.c_int64, C.c_int64, C.c_int64]
+    lib.vd_run_device_slice.restype = C.c_int
     lib.vd_finalize.argtypes = [C.POINTER(vd_batch_in), C.POINTER(vd_batch_out), C.c_double, C.c_double,
                                 C.POINTER(vd_final)]
     lib.vd_finalize.restype = C.c_int
@@ -116,6 +119,12 @@ class Engine:
     def run_device(self, din: vd_batch_in, dout: vd_batch_out, n_var: int, ref_bytes: int, alt_bytes: int):
         """All pointers already resident in this GPU's HBM."""
         self._check(self.lib.vd_run_device(self.h, C.byref(din), C.byref(dout), n_var, ref_bytes, alt_bytes))
+
+    def run_device_slice(self, din: vd_batch_in, dout: vd_batch_out, first_var: int, n_var: int,
+                         ref_bytes: int, alt_bytes: int):
+        """A slice of a resident batch (vd_run_device_slice): ref_off / var_off advanced to the slice."""
+        self._check(self.lib.vd_run_device_slice(self.h, C.byref(din), C.byref(dout), first_var, n_var,
+                                                 ref_bytes, alt_bytes))
 
     def stats(self) -> dict:
         st = vd_stats()

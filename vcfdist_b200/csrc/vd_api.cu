@@ -463,8 +463,16 @@ static int64_t io_bytes_of(int64_t n_sc, int64_t n_var, int64_t ref_bytes, int64
     return inp + outb;
 }
 
+extern "C" int vd_run_device_slice(vd_handle *h, const vd_batch_in *in, vd_batch_out *out,
+                                   int64_t first_var, int64_t n_var, int64_t ref_bytes, int64_t alt_bytes);
+
 extern "C" int vd_run_device(vd_handle *h, const vd_batch_in *in, vd_batch_out *out,
                              int64_t n_var, int64_t ref_bytes, int64_t alt_bytes) {
+    return vd_run_device_slice(h, in, out, 0, n_var, ref_bytes, alt_bytes);
+}
+
+extern "C" int vd_run_device_slice(vd_handle *h, const vd_batch_in *in, vd_batch_out *out,
+                                   int64_t first_var, int64_t n_var, int64_t ref_bytes, int64_t alt_bytes) {
     if (!h || !in || !out) return VD_E_BADINPUT;
     CK(cudaSetDevice(h->device));
     BatchDev b{in->n_sc, in->ref_off, in->ref_seq, in->rplane_seq ? in->rplane_seq : in->ref_seq, in->var_off,
@@ -476,7 +484,9 @@ extern "C" int vd_run_device(vd_handle *h, const vd_batch_in *in, vd_batch_out *
     h->stats.n_sc = in->n_sc; h->stats.n_var = n_var;
     h->stats.io_bytes = io_bytes_of(in->n_sc, n_var, ref_bytes, alt_bytes);
     Work &W = h->work[0];
-    int rc = chunk_plan(h, W, h->stream, b, o, o);
+    const OutDev base = o;                 // per-variant arrays are indexed [slot*n_var + (v - first_var)]
+    o.assigned -= first_var; o.sync_group -= first_var; o.ref_ed -= first_var; o.query_ed -= first_var; o.callq -= first_var;
+    int rc = chunk_plan(h, W, h->stream, b, o, base);
     if (rc == VD_OK) rc = chunk_exec(h, W);
     const int rc2 = chunk_harvest(h, W);
     return rc != VD_OK ? rc : rc2;
