@@ -35,6 +35,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 from vcfdist_b200 import capi, shard, synth  # noqa: E402
+from oracle import checkers  # noqa: E402  (CPU-baseline legs only: the reference arm and cpu_baseline)
 from vcfdist_b200.batch import Batch, Out, vd_batch_in, vd_batch_out  # noqa: E402
 
 WORKLOADS = {
@@ -135,7 +136,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    if not capi.reference_available(False):
+    if not checkers.reference_available(False):
         # the C restatement stands in when the reference objects were not built
         kind = "port"
     else:
@@ -145,9 +146,9 @@ def run_reference(args):
     times = []
     for i in range(args.warmup + args.steps):
         if kind == "reference":
-            _, sec = capi.reference_run(b, canonical=False, threads=cores)
+            _, sec = checkers.reference_run(b, canonical=False, threads=cores)
         else:
-            t0 = time.perf_counter(); capi.oracle_run(b); sec = time.perf_counter() - t0
+            t0 = time.perf_counter(); checkers.oracle_run(b); sec = time.perf_counter() - t0
             cores = 1
         if i >= args.warmup:
             times.append(sec)
@@ -455,11 +456,11 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
             sb, scells, _ = make_workload(args.workload, args.ref_sample, args.seed, 0, 1, args.sv_max)
-            if capi.reference_available(False):
-                _, sec = capi.reference_run(sb, canonical=False, threads=cores)
+            if checkers.reference_available(False):
+                _, sec = checkers.reference_run(sb, canonical=False, threads=cores)
                 kind = "reference"
             else:
-                t0 = time.perf_counter(); capi.oracle_run(sb); sec = time.perf_counter() - t0
+                t0 = time.perf_counter(); checkers.oracle_run(sb); sec = time.perf_counter() - t0
                 kind, cores = "port", 1
             line["cpu_baseline"] = {"value": scells / sec / 1e9, "unit": "Gcells/s", "cores": cores, "kind": kind,
                                     "superclusters_per_s": sb.n_sc / sec,

@@ -1,0 +1,93 @@
+"""TEST INFRASTRUCTURE - loaders of the checker libraries under oracle/_ref/.
+
+  liboracle.so          the plain-C restatement of the path (oracle/vd_oracle.c)
+  libvdref.so / B       the reference's own object code behind a function-level harness
+                        (oracle/ref_harness.cpp; B = with the canonical tie-break patch)
+
+Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may import this module;
+it is the checker, never the thing measured or shipped.  The product path
+(vcfdist_b200.capi.Engine) does not know it exists.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import sys
+from typing import Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(_HERE))
+
+from vcfdist_b200.batch import Batch, Out, vd_batch_in, vd_batch_out  # noqa: E402
+from vcfdist_b200.capi import VdError  # noqa: E402
+
+ORACLE_DIR = os.path.join(_HERE, "_ref")
+
+
+def load_oracle() -> C.CDLL:
+    p = os.path.join(ORACLE_DIR, "liboracle.so")
+    if not os.path.exists(p):
+        raise RuntimeError(f"{p} missing: run `make -C oracle port`")
+    lib = C.CDLL(p)
+    lib.vdo_run.argtypes = [C.POINTER(vd_batch_in), C.POINTER(vd_batch_out)]
+    lib.vdo_run.restype = C.c_int
+    return lib
+
+
+def oracle_run(batch: Batch) -> Out:
+    lib = load_oracle()
+    out = Out(batch.n_sc, batch.n_var)
+    cin, cout = batch.as_c(), out.as_c()
+    rc = lib.vdo_run(C.byref(cin), C.byref(cout))
+    if rc != 0:
+        raise VdError(rc, "oracle rejected the batch")
+    return out
+
+
+class vdref_out(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in
+                ("errtypes", "sync_group", "ref_ed", "query_ed", "callq", "credit",
+                 "sc_phase", "orig_dist", "swap_dist")]
+
+
+def reference_available(canonical: bool = False) -> bool:
+    return os.path.exists(os.path.join(ORACLE_DIR, "libvdrefB.so" if canonical else "libvdref.so"))
+
+
+_ref_libs = {}
+
+
+def reference_run(batch: Batch, canonical: bool = False, threads: int = 1, max_ram: float = 64.0,
+                  phase_threshold: float = 0.6, credit_threshold: float = 0.7,
+                  max_qual: int = 60) -> Tuple[dict, float]:
+    """Run the REFERENCE's own object code (oracle/_ref/libvdref[B].so) on the batch.
+    Returns (results dict like Final.trimmed(), seconds inside precision_recall_threads_wrapper)."""
+    name = "libvdrefB.so" if canonical else "libvdref.so"
+    if name not in _ref_libs:
+        lib = C.CDLL(os.path.join(ORACLE_DIR, name))
+        lib.vdref_run.argtypes = [C.POINTER(vd_batch_in), C.POINTER(vdref_out), C.c_int, C.c_double,
+                                  C.c_double, C.c_double, C.c_int, C.POINTER(C.c_double)]
+        lib.vdref_run.restype = C.c_int
+        _ref_libs[name] = lib
+    lib = _ref_libs[name]
+    v, s = max(2 * batch.n_var, 1), max(batch.n_sc, 1)
+    arrs = dict(errtypes=np.zeros(v, np.uint8), sync_group=np.zeros(v, np.int32),
+                ref_ed=np.zeros(v, np.int32), query_ed=np.zeros(v, np.int32),
+                callq=np.zeros(v, np.float32), credit=np.zeros(v, np.float32),
+                sc_phase=np.zeros(s, np.int32), orig_dist=np.zeros(s, np.int32),
+                swap_dist=np.zeros(s, np.int32))
+    ro = vdref_out()
+    for k, a in arrs.items():
+        setattr(ro, k, a.ctypes.data)
+    sec = C.c_double(0)
+    cin = batch.as_c()
+    rc = lib.vdref_run(C.byref(cin), C.byref(ro), threads, max_ram, phase_threshold, credit_threshold,
+                       max_qual, C.byref(sec))
+    if rc != 0:
+        raise VdError(rc, "reference harness")
+    nv2 = 2 * batch.n_var
+    res = {k: (a[:nv2] if k not in ("sc_phase", "orig_dist", "swap_dist") else a[: batch.n_sc])
+           for k, a in arrs.items()}
+    return res, sec.value

@@ -2,13 +2,14 @@ import sys, os, numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 from conftest import load_golden, OUT_KEYS
+from oracle import checkers
 from vcfdist_b200 import capi, synth
 name = sys.argv[1] if len(sys.argv) > 1 else "adv_11"
 b, _, _ = load_golden(name)
 for fc in (os.environ.get("DBG_CLASSES", "1").split(",")):
     if fc: os.environ["VD_FORCE_CLASS"] = fc
     e = capi.Engine(0)
-    got = e.run(b).trimmed(); want = capi.oracle_run(b).trimmed()
+    got = e.run(b).trimmed(); want = checkers.oracle_run(b).trimmed()
     L = b.hap_len(); lr = b.window_len()
     bad_aln = np.flatnonzero((got["aln_score"] != want["aln_score"]) | (got["status"] != want["status"]) | (got["aln_end_plane"] != want["aln_end_plane"])| (got["aln_beg_plane"] != want["aln_beg_plane"]))
     print("force", fc, "stats", e.stats())

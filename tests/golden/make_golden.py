@@ -20,6 +20,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from vcfdist_b200 import capi, synth  # noqa: E402
+from oracle import checkers  # noqa: E402
 from vcfdist_b200.batch import Batch  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -55,21 +56,21 @@ def main():
                        check=True, env=env, cwd=tmp, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
         b = synth.batch_from_vdarr(f"{tmp}/batch.vdarr")
         refA = synth.read_vdarr(f"{tmp}/final.vdarr")
-    refB, _ = capi.reference_run(b, canonical=True, threads=8)
+    refB, _ = checkers.reference_run(b, canonical=True, threads=8)
     save("demo.npz", b, refA=refA, refB=refB)
 
     # ---- adversarial ----
     for seed, n, mx in ((11, 1200, 28), (12, 600, 60)):
         b = synth.adversarial(seed, n, max_len=mx)
-        rA, _ = capi.reference_run(b, canonical=False, threads=8)
-        rB, _ = capi.reference_run(b, canonical=True, threads=8)
+        rA, _ = checkers.reference_run(b, canonical=False, threads=8)
+        rB, _ = checkers.reference_run(b, canonical=True, threads=8)
         save(f"adv_{seed}.npz", b, refA=rA, refB=rB)
 
     # ---- long shapes ----
     b = Batch.concat([synth.wgs_like(21, 60, sv_frac=0.5, sv_min=50, sv_max=600),
                       synth.sv_pairs(22, 2, 900, divergence=0.02)])
-    rA, _ = capi.reference_run(b, canonical=False, threads=8)
-    rB, _ = capi.reference_run(b, canonical=True, threads=8)
+    rA, _ = checkers.reference_run(b, canonical=False, threads=8)
+    rB, _ = checkers.reference_run(b, canonical=True, threads=8)
     save("sv_21.npz", b, refA=rA, refB=rB)
 
 

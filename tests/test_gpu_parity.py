@@ -8,6 +8,7 @@ import pytest
 
 from conftest import FINAL_KEYS, OUT_KEYS, load_golden, mismatches, non_tie_var_mask
 from vcfdist_b200 import capi, synth
+from oracle import checkers
 from vcfdist_b200.batch import Batch, BatchBuilder, TYPE_DEL, TYPE_INS, TYPE_SUB
 
 pytestmark = pytest.mark.gpu
@@ -30,7 +31,7 @@ def forced_engine(cls):
 
 def check_vs_oracle(engine, b):
     got = engine.run(b)
-    want = capi.oracle_run(b)
+    want = checkers.oracle_run(b)
     assert mismatches(got.trimmed(), want.trimmed(), OUT_KEYS) == {}
     return got
 
@@ -99,7 +100,7 @@ def test_homozygous_replication_matches_full_computation():
         tv = synth.random_hap(rng, ref, 0.15, 4, b"ACGT") if i % 3 else qv
         bb.add(ref, [qv, qv, tv, tv])
     b = Batch.concat([demo, bb.build()])
-    want = capi.oracle_run(b).trimmed()
+    want = checkers.oracle_run(b).trimmed()
     for hom in (1, 0):
         e = engine_with(VD_HOM=hom)
         got = e.run(b).trimmed()
@@ -221,7 +222,7 @@ def test_dense_paths_match_banded_and_sparse(engine):
     VD_SPARSE_BWD the frontier backward kernel instead of the banded one."""
     b = Batch.concat([synth.sv_pairs(7, 2, 800, divergence=0.05), synth.wgs_like(8, 300, sv_frac=0.1, sv_max=900),
                       synth.sv_pairs(9, 2, 2600, divergence=0.02)])
-    want = capi.oracle_run(b)
+    want = checkers.oracle_run(b)
     for env in ({"VD_DENSE_FWD": "1"}, {"VD_DENSE_BWD": "1"}, {"VD_DENSE_FWD": "1", "VD_DENSE_BWD": "1"},
                 {"VD_SPARSE_BWD": "1"}):
         os.environ.update(env)
@@ -291,7 +292,7 @@ def test_device_slices_match_whole_batch(engine):
     import torch
     from vcfdist_b200.batch import vd_batch_in, vd_batch_out
     b = synth.wgs_like(21, 6000, sv_frac=0.003, sv_max=500)
-    want = capi.oracle_run(b).trimmed()
+    want = checkers.oracle_run(b).trimmed()
     dev = torch.device("cuda", 0)
     names = ("ref_off", "ref_seq", "var_off", "var_pos", "var_rlen", "var_type", "alt_off", "alt_seq", "var_qual")
     d_in = {k: torch.from_numpy(getattr(b, k)).to(dev) for k in names}
@@ -340,7 +341,7 @@ def test_chunked_pipeline_matches_single_pass():
     finally:
         del os.environ["VD_CHUNK_SC"]
     got = e.run(b)
-    want = capi.oracle_run(b)
+    want = checkers.oracle_run(b)
     assert mismatches(got.trimmed(), want.trimmed(), OUT_KEYS) == {}
     st = e.stats()
     assert st["cells"] == int(b.cells().sum()) and st["n_short"] + st["n_long"] == 4 * b.n_sc

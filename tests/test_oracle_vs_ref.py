@@ -6,18 +6,19 @@ import pytest
 
 from conftest import FINAL_KEYS, mismatches, non_tie_var_mask
 from vcfdist_b200 import capi, synth
+from oracle import checkers
 
-pytestmark = pytest.mark.skipif(not (capi.reference_available(False) and capi.reference_available(True)),
+pytestmark = pytest.mark.skipif(not (checkers.reference_available(False) and checkers.reference_available(True)),
                                 reason="oracle/_ref/libvdref*.so not built")
 
 
 @pytest.mark.parametrize("seed,n,mx", [(101, 400, 24), (102, 300, 48), (103, 150, 80)])
 def test_adversarial_vs_reference(seed, n, mx, capfd):
     b = synth.adversarial(seed, n, max_len=mx)
-    out = capi.oracle_run(b)
+    out = checkers.oracle_run(b)
     fin = capi.finalize(b, out).trimmed()
-    refB, _ = capi.reference_run(b, canonical=True, threads=4)
-    refA, _ = capi.reference_run(b, canonical=False, threads=4)
+    refB, _ = checkers.reference_run(b, canonical=True, threads=4)
+    refA, _ = checkers.reference_run(b, canonical=False, threads=4)
     capfd.readouterr()          # the reference prints its data WARNs
     assert mismatches(fin, refB, FINAL_KEYS) == {}
     mask, _ = non_tie_var_mask(b, out.status)
@@ -26,9 +27,9 @@ def test_adversarial_vs_reference(seed, n, mx, capfd):
 
 def test_wgs_like_vs_reference(capfd):
     b = synth.wgs_like(7, 3000, sv_frac=0.01, sv_max=400)
-    out = capi.oracle_run(b)
+    out = checkers.oracle_run(b)
     fin = capi.finalize(b, out).trimmed()
-    refB, _ = capi.reference_run(b, canonical=True, threads=4)
+    refB, _ = checkers.reference_run(b, canonical=True, threads=4)
     capfd.readouterr()
     assert mismatches(fin, refB, FINAL_KEYS) == {}
 
@@ -44,8 +45,8 @@ def test_rplane_override(capfd):
     t1 = [(3, TYPE_SUB, 1, b"C", 30.0), (6, TYPE_DEL, 2, b"", 30.0)]
     bb.add(ref, [q1, [], t1, []], rplane=rplane)
     b = bb.build()
-    out = capi.oracle_run(b)
+    out = checkers.oracle_run(b)
     fin = capi.finalize(b, out).trimmed()
-    refB, _ = capi.reference_run(b, canonical=True, threads=1)
+    refB, _ = checkers.reference_run(b, canonical=True, threads=1)
     capfd.readouterr()
     assert mismatches(fin, refB, FINAL_KEYS) == {}

@@ -12,6 +12,7 @@ import torch.multiprocessing as mp
 
 from conftest import OUT_KEYS, ROOT, mismatches
 from vcfdist_b200 import capi, shard, synth
+from oracle import checkers
 
 
 def test_lpt_partition_balances_and_covers():
@@ -44,9 +45,9 @@ def _worker(rank, world, port, q):
     parts = shard.lpt_partition(b.cells(), world)
     mine = parts[rank]
     sub = b.take(mine)
-    out = capi.oracle_run(sub).trimmed()
+    out = checkers.oracle_run(sub).trimmed()
     full = shard.gather_results(out, mine, b.var_index_of(mine), b.n_sc, b.n_var, dist)
-    want = capi.oracle_run(b).trimmed()
+    want = checkers.oracle_run(b).trimmed()
     got = {k: v.numpy() for k, v in full.items()}
     got["status"] = got["status"].view(np.uint32)
     bad = mismatches(got, want, OUT_KEYS)

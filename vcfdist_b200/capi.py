@@ -2,9 +2,9 @@
 
 `Engine` is the product path: it loads vcfdist_b200/libvcfdist_b200.so (hand-written
 sm_100a CUDA behind `extern "C"`) and fails loudly when the library or a GPU is missing —
-there is no CPU fallback.  The checker libraries under oracle/_ref/ are loaded by
-`load_oracle()` / `load_reference()`, which only tests/, __graft_entry__.smoke() and
-bench.py's CPU-baseline legs may call.
+there is no CPU fallback.  The checker libraries under oracle/_ref/ have their own
+loader, `oracle/checkers.py` (test infrastructure: tests/, __graft_entry__.smoke() and
+bench.py's CPU-baseline legs only); nothing in this package touches them.
 """
 from __future__ import annotations
 
@@ -18,7 +18,6 @@ from .batch import Batch, Final, Out, vd_batch_in, vd_batch_out, vd_final, vd_st
 
 _ROOT = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_ROOT, "libvcfdist_b200.so")
-ORACLE_DIR = os.path.join(os.path.dirname(_ROOT), "oracle", "_ref")
 
 EXPORTS = ("vd_abi_version", "vd_create", "vd_destroy", "vd_run", "vd_run_device", "vd_run_device_slice",
            "vd_finalize", "vd_get_stats", "vd_last_error", "vd_stream")
@@ -134,74 +133,3 @@ class Engine:
     @property
     def stream(self) -> int:
         return int(self.lib.vd_stream(self.h) or 0)
-
-
-# --------------------------------------------------------------------------------------
-# checkers (oracle/): tests, smoke() and bench.py's CPU-baseline legs only
-# --------------------------------------------------------------------------------------
-
-def load_oracle() -> C.CDLL:
-    p = os.path.join(ORACLE_DIR, "liboracle.so")
-    if not os.path.exists(p):
-        raise RuntimeError(f"{p} missing: run `make -C oracle port`")
-    lib = C.CDLL(p)
-    lib.vdo_run.argtypes = [C.POINTER(vd_batch_in), C.POINTER(vd_batch_out)]
-    lib.vdo_run.restype = C.c_int
-    return lib
-
-
-def oracle_run(batch: Batch) -> Out:
-    lib = load_oracle()
-    out = Out(batch.n_sc, batch.n_var)
-    cin, cout = batch.as_c(), out.as_c()
-    rc = lib.vdo_run(C.byref(cin), C.byref(cout))
-    if rc != 0:
-        raise VdError(rc, "oracle rejected the batch")
-    return out
-
-
-class vdref_out(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in
-                ("errtypes", "sync_group", "ref_ed", "query_ed", "callq", "credit",
-                 "sc_phase", "orig_dist", "swap_dist")]
-
-
-def reference_available(canonical: bool = False) -> bool:
-    return os.path.exists(os.path.join(ORACLE_DIR, "libvdrefB.so" if canonical else "libvdref.so"))
-
-
-_ref_libs = {}
-
-
-def reference_run(batch: Batch, canonical: bool = False, threads: int = 1, max_ram: float = 64.0,
-                  phase_threshold: float = 0.6, credit_threshold: float = 0.7,
-                  max_qual: int = 60) -> Tuple[dict, float]:
-    """Run the REFERENCE's own object code (oracle/_ref/libvdref[B].so) on the batch.
-    Returns (results dict like Final.trimmed(), seconds inside precision_recall_threads_wrapper)."""
-    name = "libvdrefB.so" if canonical else "libvdref.so"
-    if name not in _ref_libs:
-        lib = C.CDLL(os.path.join(ORACLE_DIR, name))
-        lib.vdref_run.argtypes = [C.POINTER(vd_batch_in), C.POINTER(vdref_out), C.c_int, C.c_double,
-                                  C.c_double, C.c_double, C.c_int, C.POINTER(C.c_double)]
-        lib.vdref_run.restype = C.c_int
-        _ref_libs[name] = lib
-    lib = _ref_libs[name]
-    v, s = max(2 * batch.n_var, 1), max(batch.n_sc, 1)
-    arrs = dict(errtypes=np.zeros(v, np.uint8), sync_group=np.zeros(v, np.int32),
-                ref_ed=np.zeros(v, np.int32), query_ed=np.zeros(v, np.int32),
-                callq=np.zeros(v, np.float32), credit=np.zeros(v, np.float32),
-                sc_phase=np.zeros(s, np.int32), orig_dist=np.zeros(s, np.int32),
-                swap_dist=np.zeros(s, np.int32))
-    ro = vdref_out()
-    for k, a in arrs.items():
-        setattr(ro, k, a.ctypes.data)
-    sec = C.c_double(0)
-    cin = batch.as_c()
-    rc = lib.vdref_run(C.byref(cin), C.byref(ro), threads, max_ram, phase_threshold, credit_threshold,
-                       max_qual, C.byref(sec))
-    if rc != 0:
-        raise VdError(rc, "reference harness")
-    nv2 = 2 * batch.n_var
-    res = {k: (a[:nv2] if k not in ("sc_phase", "orig_dist", "swap_dist") else a[: batch.n_sc])
-           for k, a in arrs.items()}
-    return res, sec.value
