@@ -451,6 +451,9 @@ def main():
             t_ = json.load(open(tr)).get(f"{args.workload}:{dom}")
             if t_ and t_.get("n_sc_per_gpu") == b.n_sc:
                 line["roofline"]["traffic"] = t_["dram_bytes_per_launch"]
+                # the kernel is issue-bound, not HBM-bound: what the same capture says about the issue slots
+                line["roofline"]["ncu"] = {k_: t_[k_] for k_ in ("issue_slots_busy_pct", "warps_active_pct",
+                                                                  "active_lanes_per_instruction") if k_ in t_}
         if args.secondary and world == 1 and args.workload == "wgs":
             line["secondary"] = run_secondary(eng, args, dev, torch)
         if not args.no_cpu_baseline and world == 1:

@@ -58,3 +58,26 @@ def test_finalize_host_step():
     assert list(fin["errtypes"]) == [0, 0, 1, 2]
     assert fin["credit"][3] == np.float32(1) - np.float32(1) / np.float32(3)
     assert fin["callq"][3] == 60.0 and fin["callq"][2] == 10.0
+
+
+def test_product_package_never_touches_the_oracle():
+    """The checkers under oracle/ are test infrastructure: no module of the product package may import,
+    load or name them (docstrings that say so excepted), and importing the package must not pull
+    oracle.checkers in."""
+    import ast
+    import subprocess
+    import sys
+    pkg = os.path.join(ROOT, "vcfdist_b200")
+    for fn in sorted(os.listdir(pkg)):
+        if not fn.endswith(".py"):
+            continue
+        tree = ast.parse(open(os.path.join(pkg, fn)).read())
+        for node in ast.walk(tree):
+            if isinstance(node, (ast.Import, ast.ImportFrom)):
+                names = [a.name for a in node.names] + [getattr(node, "module", "") or ""]
+                assert not any(n.split(".")[0] == "oracle" for n in names), (fn, names)
+            if isinstance(node, ast.Constant) and isinstance(node.value, str) and node.value is not ast.get_docstring(tree, clean=False):
+                assert "liboracle" not in node.value and "libvdref" not in node.value, (fn, node.value[:60])
+    code = "import sys; import vcfdist_b200, vcfdist_b200.capi, vcfdist_b200.shard, vcfdist_b200.synth; " \
+           "sys.exit(1 if any(m.startswith('oracle') for m in sys.modules) else 0)"
+    assert subprocess.run([sys.executable, "-c", code], cwd=ROOT).returncode == 0

@@ -458,6 +458,10 @@ wsc_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, const int *
 #ifndef VD_WSC_PAR_MINBIN
 #define VD_WSC_PAR_MINBIN 2
 #endif
+#ifndef VD_WSC_PAR_MINBIN_S2
+#define VD_WSC_PAR_MINBIN_S2 VD_WSC_PAR_MINBIN
+#endif
+constexpr int WSC_PAR_MINBIN_S2 = VD_WSC_PAR_MINBIN_S2;   // the same threshold for two or more register slots
 constexpr int WSC_PAR_MINBIN = VD_WSC_PAR_MINBIN;      // bins >= 10 KB per supercluster: one block per supercluster, one warp per alignment
 template <int S> inline void wsc_configure_one() {
     cudaFuncSetAttribute(wsc_kernel<S, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (WSC_TPB / 32) * wsc_bin_cap(WSC_PAR_MINBIN > 0 ? WSC_PAR_MINBIN - 1 : 0));
@@ -469,7 +473,7 @@ template <int S> inline void wsc_launch_one(cudaStream_t st, int bin, bool hom, 
                                             const int *order, int count) {
     const int wb = wsc_bin_cap(bin), wpb = WSC_TPB / 32;
     if (hom) wsc_kernel<S, false, true><<<(count + wpb - 1) / wpb, WSC_TPB, wpb * wb, st>>>(in, out, plan, order, count, wb);
-    else if (bin >= WSC_PAR_MINBIN) wsc_kernel<S, true, false><<<count, WSC_TPB, wb, st>>>(in, out, plan, order, count, wb);
+    else if (bin >= (S >= 2 ? WSC_PAR_MINBIN_S2 : WSC_PAR_MINBIN)) wsc_kernel<S, true, false><<<count, WSC_TPB, wb, st>>>(in, out, plan, order, count, wb);
     else wsc_kernel<S, false, false><<<(count + wpb - 1) / wpb, WSC_TPB, wpb * wb, st>>>(in, out, plan, order, count, wb);
 }
 inline void wsc_launch(cudaStream_t st, int slots, int bin, bool hom, const BatchDev &in, const OutDev &out, const ScPlan *plan,
