@@ -76,6 +76,276 @@ struct PFWarp {      // path flags, [column][row], QUERY rows first
     __device__ __forceinline__ void prefetch(int, int, int) const {}
 };
 
+// one alignment as the sweeps see it (all pointers into the supercluster's shared-memory region)
+struct WscAln {
+    const u8 *qstr, *qflg, *rseq, *rflg;
+    const int8_t *qptr, *rptr, *toQ, *toR;
+    const u16 *tinf;
+    u8 *F;
+    int Lq, Lr, Lt;
+};
+
+// Forward and backward sweep of one alignment by one warp (phase 2 of the header comment); on return F
+// holds the path flags and every lane the score, the end plane, the origin plane and the status bits.
+template <int S>
+__device__ __forceinline__ void wsc_sweep(const int lane, const WscAln &X, int &score, int &end_plane, int &beg_plane, u32 &status) {
+    constexpr unsigned FULL = 0xffffffffu;
+    const u8 *qstr = X.qstr, *qflg = X.qflg, *rseq = X.rseq, *rflg = X.rflg;
+    const int8_t *qptr = X.qptr, *rptr = X.rptr, *toQ = X.toQ, *toR = X.toR;
+    const u16 *tinf = X.tinf;
+    u8 *F = X.F;
+    const int Lq = X.Lq, Lr = X.Lr, Lt = X.Lt, N = Lq + Lr;
+    // values of an arbitrary row g / the row above / the row below, from per-slot register arrays
+    auto row_get = [&](const int (&X)[S], int g) -> int {
+        int v = __shfl_sync(FULL, X[0], g & 31);
+#pragma unroll
+        for (int s = 1; s < S; s++) { const int v1 = __shfl_sync(FULL, X[s], g & 31); if ((g >> 5) == s) v = v1; }
+        return v;
+    };
+    auto above = [&](const int (&X)[S], int s) -> int {
+        int u = __shfl_up_sync(FULL, X[s], 1);
+        if (S > 1 && s > 0) { const int w = __shfl_sync(FULL, X[s - 1], 31); if (lane == 0) u = w; }
+        return u;
+    };
+    auto below = [&](const int (&X)[S], int s) -> int {
+        int u = __shfl_down_sync(FULL, X[s], 1);
+        if (S > 1 && s < S - 1) { const int w = __shfl_sync(FULL, X[s + 1], 0); if (lane == 31) u = w; }
+        return u;
+    };
+
+    // static per-row data
+    bool inrow[S], P[S], below_ok[S];
+    int a[S], ch[S], chn[S], swi[S], si[S], tpn[S], Ssum[S];
+    int maxcnt = 0;
+    int tpself[S];
+#pragma unroll
+    for (int s = 0; s < S; s++) {
+        const int r = 32 * s + lane;
+        inrow[s] = r < N;
+        P[s] = r >= Lq;
+        a[s] = P[s] ? r - Lq : r;
+        const int len = P[s] ? Lr : Lq;
+        const u8 *seq = P[s] ? rseq : qstr;
+        ch[s] = inrow[s] ? seq[a[s]] : 0x100;
+        below_ok[s] = inrow[s] && a[s] + 1 < len;
+        chn[s] = below_ok[s] ? seq[a[s] + 1] : 0x100;
+        swi[s] = 0; si[s] = 0; tpself[s] = 0;
+        if (inrow[s]) {
+            // my row as a swap DESTINATION: first source (row index over both planes) | count << 16
+            const int8_t *tab = P[s] ? toR : toQ;
+            const int k0 = tab[a[s]], k1 = tab[a[s] + 1];
+            if (k1 > k0) swi[s] = ((P[s] ? 0 : Lq) + (int)tab[len + 1 + k0]) | ((k1 - k0) << 16);
+            // my row as a swap SOURCE: valid | k << 1 | tp(dest) << 4 | dest row << 8   (:598-679)
+            const int f = P[s] ? rflg[a[s]] : qflg[a[s]];
+            const int d = (int)(P[s] ? rptr[a[s]] : qptr[a[s]]) + 1;      // plane-local row on the other plane
+            const int ndst = P[s] ? Lq : Lr;
+            if ((!(f & P_VARIANT) || (f & P_VAR_END)) && d > 0 && d < ndst) {
+                const int df = P[s] ? qflg[d] : rflg[d];
+                if (!(df & P_VARIANT) || (df & P_VAR_BEG)) {
+                    const int8_t *dtab = P[s] ? toQ : toR;               // CSR of the destination plane
+                    const int8_t *dsrc = dtab + ndst + 1;
+                    int k = 0;
+                    for (int j = dtab[d]; j < dtab[d + 1]; j++) if ((int)dsrc[j] == a[s]) k = j - dtab[d];
+                    int tp = 0;
+                    if (P[s]) tp = ((int)qptr[d] != (int)qptr[d - 1] + 1) || (df & P_VAR_BEG);      // dest on QUERY (:656-658)
+                    si[s] = 1 | (k << 1) | (tp << 4) | (((P[s] ? 0 : Lq) + d) << 8);
+                }
+            }
+            if (!P[s] && a[s] > 0) tpself[s] = ((int)qptr[a[s]] != (int)qptr[a[s] - 1] + 1) || (qflg[a[s]] & P_VAR_BEG);   // :572-574
+        }
+        maxcnt = max(maxcnt, swi[s] >> 16);
+    }
+    maxcnt = __reduce_max_sync(FULL, maxcnt);
+    {   // tp of the row below, and S = number of tp rows below mine in my plane
+        unsigned tm[S];
+#pragma unroll
+        for (int s = 0; s < S; s++) tm[s] = __ballot_sync(FULL, tpself[s] != 0);
+#pragma unroll
+        for (int s = 0; s < S; s++) {
+            const int tb = below(tpself, s);
+            tpn[s] = below_ok[s] ? tb : 0;
+            int cnt = lane < 31 ? __popc(tm[s] >> (lane + 1)) : 0;
+#pragma unroll
+            for (int s2 = s + 1; s2 < S; s2++) cnt += __popc(tm[s2]);
+            Ssum[s] = cnt;           // tp is zero on REF rows, so this is already plane-local
+        }
+    }
+    const int erow_q = Lq - 1, erow_r = N - 1;
+
+    // ---------------- forward ----------------
+    int Dp[S];
+#pragma unroll
+    for (int s = 0; s < S; s++) Dp[s] = INF;
+    for (int c = 0; c < Lt; c++) {
+        const int tic = tinf[c];
+        const int tch = tic & 0xff;
+        const bool tok = tic >> 8;                                                               // :338-339
+        int diag[S], del[S], swp[S], sbv[S], x[S];
+#pragma unroll
+        for (int s = 0; s < S; s++) {
+            const int r = 32 * s + lane;
+            const int upv = above(Dp, s);                                   // D[r-1][c-1]
+            const int cnt = swi[s] >> 16;
+            int best = row_get(Dp, swi[s] & 0xffff), sb = 0;
+            if (!cnt) best = INF;
+            if (maxcnt > 1) {                                               // rare: several sources (:347, :376)
+                const int8_t *tab = P[s] ? toR : toQ;
+                const int len = P[s] ? Lr : Lq;
+                for (int k = 1; k < maxcnt; k++) {
+                    const bool has = inrow[s] && k < cnt;
+                    const int g = has ? (P[s] ? 0 : Lq) + (int)tab[len + 1 + (int)tab[a[s]] + k] : 0;
+                    const int v = row_get(Dp, g);
+                    if (has) {
+                        if (v < best) { best = v; sb = k << F_K_SHIFT; }
+                        else if (v == best) sb = (k << F_K_SHIFT) | F_TIE;   // keep the larger row
+                    }
+                }
+            }
+            const bool m = ch[s] == tch;
+            diag[s] = (a[s] > 0 && c > 0) ? upv + (m ? 0 : 1) : INF;         // :324-332, :415-422
+            del[s] = c > 0 ? Dp[s] + 1 : INF;                               // :406-413
+            swp[s] = (tok && m) ? best : INF;                               // :334-349, :363-378
+            sbv[s] = sb;
+            int b = min(min(diag[s], del[s]), swp[s]);
+            if (a[s] == 0 && c == 0) b = 0;                                 // both origins start at 0 (:299-305)
+            if (!inrow[s]) b = INF;
+            x[s] = b < INF / 2 ? b - r : INF;
+        }
+        // insertion chain D[r] = min(b[r], D[r-1] + 1) within a plane: D[r] = r + min_{j<=r} (b[j] - j)
+        int Dn[S];
+        int carryQ = INF, carryR = INF;
+#pragma unroll
+        for (int s = 0; s < S; s++) {
+            const int r = 32 * s + lane;
+            const int seg = P[s] ? Lq : 0;
+            int incl = x[s];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int o = __shfl_up_sync(FULL, incl, d);
+                if (lane >= d && r - d >= seg) incl = min(incl, o);
+            }
+            incl = min(incl, P[s] ? carryR : carryQ);
+            if constexpr (S > 1) {
+                if (s < S - 1) {                                            // totals so far, per plane
+                    const int lastq = min(31, Lq - 1 - 32 * s), lastr = min(31, N - 1 - 32 * s);
+                    const int tq = __shfl_sync(FULL, incl, max(lastq, 0)), tr = __shfl_sync(FULL, incl, max(lastr, 0));
+                    if (lastq >= 0) carryQ = tq;
+                    if (lastr >= 0 && 32 * s + lastr >= Lq) carryR = tr;
+                }
+            }
+            Dn[s] = (inrow[s] && incl < INF / 2) ? incl + r : INF;
+        }
+#pragma unroll
+        for (int s = 0; s < S; s++) {
+            const int r = 32 * s + lane;
+            const int dabove = above(Dn, s);                                // D[r-1][c]
+            if (inrow[s]) {
+                const int d = Dn[s];
+                int f = 0;
+                if (a[s] == 0 && c == 0) f = F_DIAG;
+                else {
+                    if (diag[s] == d) f |= F_DIAG;
+                    if (a[s] > 0 && dabove + 1 == d) f |= F_INS;            // :397-404
+                    if (del[s] == d) f |= F_DEL;
+                    if (swp[s] == d) f |= F_SWP | sbv[s];
+                }
+                F[c * N + r] = (u8)f;
+            }
+            Dp[s] = Dn[s];
+        }
+    }
+    const int dq = row_get(Dp, erow_q), dr = row_get(Dp, erow_r);          // :390-391
+    score = min(dq, dr);
+    end_plane = (dq == score) ? 0 : 1;                            // :436-440
+    __syncwarp();
+
+    // ---------------- backward ----------------
+    status = 0;
+    const int erow = end_plane ? erow_r : erow_q;
+    int TFn[S];                                  // (T << 8) | forward flags of column c+1
+#pragma unroll
+    for (int s = 0; s < S; s++) TFn[s] = (-1) << 8;
+    for (int c = Lt - 1; c >= 0; c--) {
+        const bool last = c == Lt - 1;
+        const int tch_next = last ? 0x200 : (tinf[c + 1] & 0xff);
+        int Fc[S], B[S], U[S], T[S], swv[S], tfdv[S];
+        bool link[S];
+#pragma unroll
+        for (int s = 0; s < S; s++) Fc[s] = inrow[s] ? F[c * N + 32 * s + lane] : 0;
+#pragma unroll
+        for (int s = 0; s < S; s++) {
+            const int r = 32 * s + lane;
+            const int tfd = below(TFn, s);                                   // (r+1, c+1)
+            tfdv[s] = tfd;
+            const int tf2 = row_get(TFn, si[s] >> 8);                        // my swap destination at c+1
+            int b = -1;
+            swv[s] = -1;
+            if (inrow[s]) {
+                if (last && r == erow) b = 0;                                // :543-545
+                if (!last) {
+                    const int Td = tfd >> 8, Fd = tfd & 0xff, Tn = TFn[s] >> 8, Fn = TFn[s] & 0xff;
+                    if (below_ok[s] && Td >= 0 && (Fd & F_DIAG)) b = max(b, Td + tpn[s]);      // :556-595, :692-731
+                    if (Tn >= 0 && (Fn & F_DEL)) b = max(b, Tn);                               // :774-804
+                    if (si[s] & 1) {                                                           // :598-679
+                        const int T2 = tf2 >> 8, F2 = tf2 & 0xff;
+                        if (T2 >= 0 && (F2 & F_SWP) && (F2 >> F_K_SHIFT) == ((si[s] >> 1) & 7)) {
+                            swv[s] = T2 + ((si[s] >> 4) & 1);
+                            b = max(b, swv[s]);
+                            if (F2 & F_TIE) status |= VD_ST_TIE;
+                        }
+                    }
+                }
+            }
+            B[s] = b;
+            const int fbelow = below(Fc, s);                                 // forward flags of (r+1, c)
+            link[s] = below_ok[s] && (fbelow & F_INS);                       // :734-771
+        }
+        // in-column chain T[r] = max(B[r], T[r+1] + tp(r+1)) over unbroken links: suffix max of T - S
+        int carryU = NEG;
+#pragma unroll
+        for (int s = S - 1; s >= 0; s--) {
+            const unsigned lm = __ballot_sync(FULL, link[s]);
+            const unsigned nm = ~(lm >> lane);
+            const int run = nm ? __ffs(nm) - 1 : 32;
+            int val = B[s] >= 0 ? B[s] - Ssum[s] : NEG;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int o = __shfl_down_sync(FULL, val, d);
+                if (run >= d && lane + d < 32) val = max(val, o);
+            }
+            if (S > 1 && s < S - 1 && run == 32 - lane) val = max(val, carryU);
+            U[s] = val;
+            if (S > 1 && s > 0) carryU = __shfl_sync(FULL, val, 0);
+            T[s] = (inrow[s] && val > NEG / 2) ? val + Ssum[s] : -1;
+        }
+#pragma unroll
+        for (int s = 0; s < S; s++) {
+            const int r = 32 * s + lane;
+            const int tbelow = below(T, s);                                  // T[r+1][c]
+            const int tfd = tfdv[s];
+            int pf = 0;
+            const int Tv = T[s];
+            if (inrow[s] && Tv >= 0) {
+                if (last && r == erow && Tv == 0) pf |= PTR_MAT;             // :543
+                if (!last) {
+                    const int Td = tfd >> 8, Fd = tfd & 0xff, Tn = TFn[s] >> 8, Fn = TFn[s] & 0xff;
+                    if (below_ok[s] && Td >= 0 && (Fd & F_DIAG) && Td + tpn[s] == Tv)
+                        pf |= (chn[s] == tch_next) ? PTR_MAT : PTR_SUB;
+                    if (Tn >= 0 && (Fn & F_DEL) && Tn == Tv) pf |= PTR_DEL;
+                    if (swv[s] >= 0 && swv[s] == Tv) pf |= PTR_SWP;
+                }
+                if (link[s] && tbelow >= 0 && tbelow + tpn[s] == Tv) pf |= PTR_INS;
+            }
+            if (inrow[s]) F[c * N + r] = (u8)pf;
+        }
+#pragma unroll
+        for (int s = 0; s < S; s++) TFn[s] = (T[s] << 8) | (Fc[s] & 0xff);
+    }
+    const int t00 = __shfl_sync(FULL, TFn[0], 0) >> 8;
+    beg_plane = t00 >= 0 ? 0 : 1;                                  // :811-814
+    status = __reduce_or_sync(FULL, status);
+}
+
 // PAR = false: one warp per supercluster, its four alignments one after the other (small shared-memory
 //               bins: occupancy is register-limited and there are plenty of superclusters);
 // PAR = true:  one block per supercluster, warp w runs alignment w (big bins: few superclusters, occupancy is
@@ -149,24 +419,6 @@ wsc_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, const int *
     }
     sync();
 
-    // values of an arbitrary row g / the row above / the row below, from per-slot register arrays
-    auto row_get = [&](const int (&X)[S], int g) -> int {
-        int v = __shfl_sync(FULL, X[0], g & 31);
-#pragma unroll
-        for (int s = 1; s < S; s++) { const int v1 = __shfl_sync(FULL, X[s], g & 31); if ((g >> 5) == s) v = v1; }
-        return v;
-    };
-    auto above = [&](const int (&X)[S], int s) -> int {
-        int u = __shfl_up_sync(FULL, X[s], 1);
-        if (S > 1 && s > 0) { const int w = __shfl_sync(FULL, X[s - 1], 31); if (lane == 0) u = w; }
-        return u;
-    };
-    auto below = [&](const int (&X)[S], int s) -> int {
-        int u = __shfl_down_sync(FULL, X[s], 1);
-        if (S > 1 && s < S - 1) { const int w = __shfl_sync(FULL, X[s + 1], 0); if (lane == 31) u = w; }
-        return u;
-    };
-
     int my_score = 0, my_end = 0, my_beg = 0;
     u32 my_status = 0;
 
@@ -193,237 +445,10 @@ wsc_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, const int *
         const u8 *rflg = qrflg(qh);
         u8 *F = base + M.F[ai];
 
-        // static per-row data
-        bool inrow[S], P[S], below_ok[S];
-        int a[S], ch[S], chn[S], swi[S], si[S], tpn[S], Ssum[S];
-        int maxcnt = 0;
-        int tpself[S];
-#pragma unroll
-        for (int s = 0; s < S; s++) {
-            const int r = 32 * s + lane;
-            inrow[s] = r < N;
-            P[s] = r >= Lq;
-            a[s] = P[s] ? r - Lq : r;
-            const int len = P[s] ? Lr : Lq;
-            const u8 *seq = P[s] ? rseq : qstr;
-            ch[s] = inrow[s] ? seq[a[s]] : 0x100;
-            below_ok[s] = inrow[s] && a[s] + 1 < len;
-            chn[s] = below_ok[s] ? seq[a[s] + 1] : 0x100;
-            swi[s] = 0; si[s] = 0; tpself[s] = 0;
-            if (inrow[s]) {
-                // my row as a swap DESTINATION: first source (row index over both planes) | count << 16
-                const int8_t *tab = P[s] ? toR : toQ;
-                const int k0 = tab[a[s]], k1 = tab[a[s] + 1];
-                if (k1 > k0) swi[s] = ((P[s] ? 0 : Lq) + (int)tab[len + 1 + k0]) | ((k1 - k0) << 16);
-                // my row as a swap SOURCE: valid | k << 1 | tp(dest) << 4 | dest row << 8   (:598-679)
-                const int f = P[s] ? rflg[a[s]] : qflg[a[s]];
-                const int d = (int)(P[s] ? rptr[a[s]] : qptr[a[s]]) + 1;      // plane-local row on the other plane
-                const int ndst = P[s] ? Lq : Lr;
-                if ((!(f & P_VARIANT) || (f & P_VAR_END)) && d > 0 && d < ndst) {
-                    const int df = P[s] ? qflg[d] : rflg[d];
-                    if (!(df & P_VARIANT) || (df & P_VAR_BEG)) {
-                        const int8_t *dtab = P[s] ? toQ : toR;               // CSR of the destination plane
-                        const int8_t *dsrc = dtab + ndst + 1;
-                        int k = 0;
-                        for (int j = dtab[d]; j < dtab[d + 1]; j++) if ((int)dsrc[j] == a[s]) k = j - dtab[d];
-                        int tp = 0;
-                        if (P[s]) tp = ((int)qptr[d] != (int)qptr[d - 1] + 1) || (df & P_VAR_BEG);      // dest on QUERY (:656-658)
-                        si[s] = 1 | (k << 1) | (tp << 4) | (((P[s] ? 0 : Lq) + d) << 8);
-                    }
-                }
-                if (!P[s] && a[s] > 0) tpself[s] = ((int)qptr[a[s]] != (int)qptr[a[s] - 1] + 1) || (qflg[a[s]] & P_VAR_BEG);   // :572-574
-            }
-            maxcnt = max(maxcnt, swi[s] >> 16);
-        }
-        maxcnt = __reduce_max_sync(FULL, maxcnt);
-        {   // tp of the row below, and S = number of tp rows below mine in my plane
-            unsigned tm[S];
-#pragma unroll
-            for (int s = 0; s < S; s++) tm[s] = __ballot_sync(FULL, tpself[s] != 0);
-#pragma unroll
-            for (int s = 0; s < S; s++) {
-                const int tb = below(tpself, s);
-                tpn[s] = below_ok[s] ? tb : 0;
-                int cnt = lane < 31 ? __popc(tm[s] >> (lane + 1)) : 0;
-#pragma unroll
-                for (int s2 = s + 1; s2 < S; s2++) cnt += __popc(tm[s2]);
-                Ssum[s] = cnt;           // tp is zero on REF rows, so this is already plane-local
-            }
-        }
-        const int erow_q = Lq - 1, erow_r = N - 1;
-
-        // ---------------- forward ----------------
-        int Dp[S];
-#pragma unroll
-        for (int s = 0; s < S; s++) Dp[s] = INF;
-        for (int c = 0; c < Lt; c++) {
-            const int tic = tinf[c];
-            const int tch = tic & 0xff;
-            const bool tok = tic >> 8;                                                               // :338-339
-            int diag[S], del[S], swp[S], sbv[S], x[S];
-#pragma unroll
-            for (int s = 0; s < S; s++) {
-                const int r = 32 * s + lane;
-                const int upv = above(Dp, s);                                   // D[r-1][c-1]
-                const int cnt = swi[s] >> 16;
-                int best = row_get(Dp, swi[s] & 0xffff), sb = 0;
-                if (!cnt) best = INF;
-                if (maxcnt > 1) {                                               // rare: several sources (:347, :376)
-                    const int8_t *tab = P[s] ? toR : toQ;
-                    const int len = P[s] ? Lr : Lq;
-                    for (int k = 1; k < maxcnt; k++) {
-                        const bool has = inrow[s] && k < cnt;
-                        const int g = has ? (P[s] ? 0 : Lq) + (int)tab[len + 1 + (int)tab[a[s]] + k] : 0;
-                        const int v = row_get(Dp, g);
-                        if (has) {
-                            if (v < best) { best = v; sb = k << F_K_SHIFT; }
-                            else if (v == best) sb = (k << F_K_SHIFT) | F_TIE;   // keep the larger row
-                        }
-                    }
-                }
-                const bool m = ch[s] == tch;
-                diag[s] = (a[s] > 0 && c > 0) ? upv + (m ? 0 : 1) : INF;         // :324-332, :415-422
-                del[s] = c > 0 ? Dp[s] + 1 : INF;                               // :406-413
-                swp[s] = (tok && m) ? best : INF;                               // :334-349, :363-378
-                sbv[s] = sb;
-                int b = min(min(diag[s], del[s]), swp[s]);
-                if (a[s] == 0 && c == 0) b = 0;                                 // both origins start at 0 (:299-305)
-                if (!inrow[s]) b = INF;
-                x[s] = b < INF / 2 ? b - r : INF;
-            }
-            // insertion chain D[r] = min(b[r], D[r-1] + 1) within a plane: D[r] = r + min_{j<=r} (b[j] - j)
-            int Dn[S];
-            int carryQ = INF, carryR = INF;
-#pragma unroll
-            for (int s = 0; s < S; s++) {
-                const int r = 32 * s + lane;
-                const int seg = P[s] ? Lq : 0;
-                int incl = x[s];
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const int o = __shfl_up_sync(FULL, incl, d);
-                    if (lane >= d && r - d >= seg) incl = min(incl, o);
-                }
-                incl = min(incl, P[s] ? carryR : carryQ);
-                if constexpr (S > 1) {
-                    if (s < S - 1) {                                            // totals so far, per plane
-                        const int lastq = min(31, Lq - 1 - 32 * s), lastr = min(31, N - 1 - 32 * s);
-                        const int tq = __shfl_sync(FULL, incl, max(lastq, 0)), tr = __shfl_sync(FULL, incl, max(lastr, 0));
-                        if (lastq >= 0) carryQ = tq;
-                        if (lastr >= 0 && 32 * s + lastr >= Lq) carryR = tr;
-                    }
-                }
-                Dn[s] = (inrow[s] && incl < INF / 2) ? incl + r : INF;
-            }
-#pragma unroll
-            for (int s = 0; s < S; s++) {
-                const int r = 32 * s + lane;
-                const int dabove = above(Dn, s);                                // D[r-1][c]
-                if (inrow[s]) {
-                    const int d = Dn[s];
-                    int f = 0;
-                    if (a[s] == 0 && c == 0) f = F_DIAG;
-                    else {
-                        if (diag[s] == d) f |= F_DIAG;
-                        if (a[s] > 0 && dabove + 1 == d) f |= F_INS;            // :397-404
-                        if (del[s] == d) f |= F_DEL;
-                        if (swp[s] == d) f |= F_SWP | sbv[s];
-                    }
-                    F[c * N + r] = (u8)f;
-                }
-                Dp[s] = Dn[s];
-            }
-        }
-        const int dq = row_get(Dp, erow_q), dr = row_get(Dp, erow_r);          // :390-391
-        const int score = min(dq, dr);
-        const int end_plane = (dq == score) ? 0 : 1;                            // :436-440
-        __syncwarp();
-
-        // ---------------- backward ----------------
-        u32 status = 0;
-        const int erow = end_plane ? erow_r : erow_q;
-        int TFn[S];                                  // (T << 8) | forward flags of column c+1
-#pragma unroll
-        for (int s = 0; s < S; s++) TFn[s] = (-1) << 8;
-        for (int c = Lt - 1; c >= 0; c--) {
-            const bool last = c == Lt - 1;
-            const int tch_next = last ? 0x200 : (tinf[c + 1] & 0xff);
-            int Fc[S], B[S], U[S], T[S], swv[S], tfdv[S];
-            bool link[S];
-#pragma unroll
-            for (int s = 0; s < S; s++) Fc[s] = inrow[s] ? F[c * N + 32 * s + lane] : 0;
-#pragma unroll
-            for (int s = 0; s < S; s++) {
-                const int r = 32 * s + lane;
-                const int tfd = below(TFn, s);                                   // (r+1, c+1)
-                tfdv[s] = tfd;
-                const int tf2 = row_get(TFn, si[s] >> 8);                        // my swap destination at c+1
-                int b = -1;
-                swv[s] = -1;
-                if (inrow[s]) {
-                    if (last && r == erow) b = 0;                                // :543-545
-                    if (!last) {
-                        const int Td = tfd >> 8, Fd = tfd & 0xff, Tn = TFn[s] >> 8, Fn = TFn[s] & 0xff;
-                        if (below_ok[s] && Td >= 0 && (Fd & F_DIAG)) b = max(b, Td + tpn[s]);      // :556-595, :692-731
-                        if (Tn >= 0 && (Fn & F_DEL)) b = max(b, Tn);                               // :774-804
-                        if (si[s] & 1) {                                                           // :598-679
-                            const int T2 = tf2 >> 8, F2 = tf2 & 0xff;
-                            if (T2 >= 0 && (F2 & F_SWP) && (F2 >> F_K_SHIFT) == ((si[s] >> 1) & 7)) {
-                                swv[s] = T2 + ((si[s] >> 4) & 1);
-                                b = max(b, swv[s]);
-                                if (F2 & F_TIE) status |= VD_ST_TIE;
-                            }
-                        }
-                    }
-                }
-                B[s] = b;
-                const int fbelow = below(Fc, s);                                 // forward flags of (r+1, c)
-                link[s] = below_ok[s] && (fbelow & F_INS);                       // :734-771
-            }
-            // in-column chain T[r] = max(B[r], T[r+1] + tp(r+1)) over unbroken links: suffix max of T - S
-            int carryU = NEG;
-#pragma unroll
-            for (int s = S - 1; s >= 0; s--) {
-                const unsigned lm = __ballot_sync(FULL, link[s]);
-                const unsigned nm = ~(lm >> lane);
-                const int run = nm ? __ffs(nm) - 1 : 32;
-                int val = B[s] >= 0 ? B[s] - Ssum[s] : NEG;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const int o = __shfl_down_sync(FULL, val, d);
-                    if (run >= d && lane + d < 32) val = max(val, o);
-                }
-                if (S > 1 && s < S - 1 && run == 32 - lane) val = max(val, carryU);
-                U[s] = val;
-                if (S > 1 && s > 0) carryU = __shfl_sync(FULL, val, 0);
-                T[s] = (inrow[s] && val > NEG / 2) ? val + Ssum[s] : -1;
-            }
-#pragma unroll
-            for (int s = 0; s < S; s++) {
-                const int r = 32 * s + lane;
-                const int tbelow = below(T, s);                                  // T[r+1][c]
-                const int tfd = tfdv[s];
-                int pf = 0;
-                const int Tv = T[s];
-                if (inrow[s] && Tv >= 0) {
-                    if (last && r == erow && Tv == 0) pf |= PTR_MAT;             // :543
-                    if (!last) {
-                        const int Td = tfd >> 8, Fd = tfd & 0xff, Tn = TFn[s] >> 8, Fn = TFn[s] & 0xff;
-                        if (below_ok[s] && Td >= 0 && (Fd & F_DIAG) && Td + tpn[s] == Tv)
-                            pf |= (chn[s] == tch_next) ? PTR_MAT : PTR_SUB;
-                        if (Tn >= 0 && (Fn & F_DEL) && Tn == Tv) pf |= PTR_DEL;
-                        if (swv[s] >= 0 && swv[s] == Tv) pf |= PTR_SWP;
-                    }
-                    if (link[s] && tbelow >= 0 && tbelow + tpn[s] == Tv) pf |= PTR_INS;
-                }
-                if (inrow[s]) F[c * N + r] = (u8)pf;
-            }
-#pragma unroll
-            for (int s = 0; s < S; s++) TFn[s] = (T[s] << 8) | (Fc[s] & 0xff);
-        }
-        const int t00 = __shfl_sync(FULL, TFn[0], 0) >> 8;
-        const int beg_plane = t00 >= 0 ? 0 : 1;                                  // :811-814
-        status = __reduce_or_sync(FULL, status);
+        WscAln X{qstr, qflg, rseq, rflg, qptr, rptr, toQ, toR, tinf, F, Lq, Lr, Lt};
+        int score, end_plane, beg_plane;
+        u32 status;
+        wsc_sweep<S>(lane, X, score, end_plane, beg_plane, status);
         if (lane == (PAR ? 0 : ai)) { my_score = score; my_end = end_plane; my_beg = beg_plane; my_status = status; }
         __syncwarp();
     }
@@ -455,6 +480,151 @@ wsc_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, const int *
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Block-shared variant of the warp-per-supercluster kernel (small shared-memory bins): the four
+// warps of a block still run the sweeps of their own supercluster, but the single-lane phases
+// (expansion + swap tables before, walk + credit after) of all four superclusters are done by
+// warp 0, one lane per haplotype / alignment: 16 busy lanes in one warp instead of 4 busy lanes in
+// each of four warps, i.e. a quarter of the issue slots for the part that cannot use more lanes.
+// ------------------------------------------------------------------------------------------
+struct WscDesc {
+    ScPlan p; WscLayout M;
+    int sc;            // -1: no supercluster for this warp (tail of the launch)
+    int ok;            // expansion succeeded
+    unsigned trivial;  // alignments without variants on either side
+    int res[4][4];     // per alignment: score, end plane, origin plane, status
+};
+
+template <int S, bool HOM>
+__global__ void __launch_bounds__(WSC_TPB)
+wsc_block_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, const int *__restrict__ order, int count, int warp_bytes) {
+    extern __shared__ __align__(16) u8 smem[];
+    __shared__ WscDesc desc[WSC_TPB / 32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slot = blockIdx.x * (WSC_TPB / 32) + warp;
+    const bool live = slot < count;
+    if (lane == 0) {
+        WscDesc &d = desc[warp];
+        d.sc = live ? order[slot] : -1;
+        d.ok = 1;
+        d.trivial = 0;
+        if (live) {
+            d.p = plan[d.sc];
+            d.M = wsc_layout(d.p, HOM);
+            if (in.rplane_seq == in.ref_seq) {       // see wsc_kernel
+                const int64_t *vo = in.var_off + 4 * (int64_t)d.sc;
+                const int64_t o0 = vo[0], o1 = vo[1], o2 = vo[2], o3 = vo[3], o4 = vo[4];
+                const bool eq0 = o1 == o0, eq1 = o2 == o1, et0 = o3 == o2, et1 = o4 == o3;
+                d.trivial = (eq0 && et0 ? 1u : 0u) | (eq0 && et1 ? 2u : 0u) | (eq1 && et0 ? 4u : 0u) | (eq1 && et1 ? 8u : 0u);
+            }
+        }
+    }
+    __syncthreads();
+    // shared-memory views of supercluster w
+    auto hbase = [&](int w, int h) { return smem + w * warp_bytes + desc[w].M.hap[h]; };
+    auto qbase = [&](int w, int k) { return smem + w * warp_bytes + desc[w].M.qm[k]; };
+
+    // ---- phase 1: warp 0, lane 4w+h expands haplotype h of supercluster w ----
+    if (warp == 0 && lane < 4 * (WSC_TPB / 32)) {
+        const int w = lane >> 2, h = lane & 3;
+        const WscDesc &d = desc[w];
+        if (d.sc >= 0 && !(HOM && (h & 1))) {
+            const int L = d.p.len[h], Lr = d.p.lr;
+            u8 *str = hbase(w, h), *flg = str + L, *ins = str + 3 * L;
+            int8_t *ptr = (int8_t *)(str + 2 * L);
+            const bool isq = h < 2;
+            int8_t *rptr = isq ? (int8_t *)qbase(w, h) : nullptr;
+            u8 *rflg = isq ? qbase(w, h) + Lr : nullptr;
+            const int len = expand_hap<int8_t>(in, d.sc, h, str, flg, ptr, rptr, rflg, ins, L);
+            bool ok = len == L;
+            if (ok && isq) {
+                int8_t *toQ = (int8_t *)(qbase(w, h) + 2 * Lr), *toR = toQ + (L + 1 + Lr);
+                ok = build_swsrc<int8_t>(ptr, flg, len, toR, Lr) && build_swsrc<int8_t>(rptr, rflg, Lr, toQ, len);
+            }
+            if (!ok) desc[w].ok = 0;
+        }
+    }
+    if (live) {                                      // every warp stages its own REF-plane string meanwhile
+        const WscDesc &d = desc[warp];
+        const u8 *rs = in.rplane_seq + in.ref_off[d.sc];
+        u8 *rseq = smem + warp * warp_bytes + d.M.rseq;
+        for (int k = lane; k < d.p.lr; k += 32) rseq[k] = rs[k];
+    }
+    __syncthreads();
+
+    // ---- phase 2: every warp sweeps the alignments of its own supercluster ----
+    if (live && desc[warp].ok) {
+        const WscDesc &d = desc[warp];
+        u8 *base = smem + warp * warp_bytes;
+        const int Lr = d.p.lr;
+        for (int k = 0; k < (HOM ? 1 : 2); k++) {    // truth columns: base | tok << 8   (:338-339, :367-368)
+            const int Ltk = d.p.len[2 + k];
+            const u8 *ts = hbase(warp, 2 + k), *tf = ts + Ltk;
+            u16 *ti = (u16 *)(base + d.M.tinf[k]);
+            for (int c = lane; c < Ltk; c += 32) {
+                const bool tok = c > 0 && (!(tf[c - 1] & P_VARIANT) || (tf[c - 1] & P_VAR_END));
+                ti[c] = (u16)(ts[c] | (tok ? 0x100 : 0));
+            }
+        }
+        __syncwarp();
+        for (int ai = 0; ai < (HOM ? 1 : 4); ai++) {
+            int score = 0, end_plane = 0, beg_plane = 0;
+            u32 status = 0;
+            if (!((d.trivial >> ai) & 1)) {
+                const int qh = ai >> 1, th = 2 + (ai & 1);
+                const int Lq = d.p.len[qh], Lt = d.p.len[th];
+                const u8 *qs = hbase(warp, qh);
+                const u8 *qb = qbase(warp, qh);
+                WscAln X{qs, qs + Lq, base + d.M.rseq, qb + Lr, (const int8_t *)(qs + 2 * Lq), (const int8_t *)qb,
+                         (const int8_t *)(qb + 2 * Lr), (const int8_t *)(qb + 2 * Lr + (Lq + 1 + Lr)),
+                         (const u16 *)(base + d.M.tinf[ai & 1]), base + d.M.F[ai], Lq, Lr, Lt};
+                wsc_sweep<S>(lane, X, score, end_plane, beg_plane, status);
+            }
+            if (lane == 0) { int *r = desc[warp].res[ai]; r[0] = score; r[1] = end_plane; r[2] = beg_plane; r[3] = (int)status; }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 3: warp 0, lane 4w+ai walks alignment ai of supercluster w ----
+    if (warp == 0 && lane < 4 * (WSC_TPB / 32)) {
+        const int w = lane >> 2, ai = lane & 3;
+        const WscDesc &d = desc[w];
+        if (d.sc < 0 || (HOM && ai)) return;
+        const int sc = d.sc;
+        const int64_t oi = 4 * (int64_t)sc + ai;
+        if (!d.ok) {
+            for (int k = 0; k < (HOM ? 4 : 1); k++) { out.status[oi + k] = ST_BAD; out.aln_score[oi + k] = -1; }
+            return;
+        }
+        const int qh = ai >> 1, th = 2 + (ai & 1);
+        const int Lr = d.p.lr, Lq = d.p.len[qh], Lt = d.p.len[th], N = Lq + Lr;
+        u8 *base = smem + w * warp_bytes;
+        const u8 *qs = hbase(w, qh), *ts = hbase(w, th), *qb = qbase(w, qh);
+        Hap<int8_t> q{Lq, qs, qs + Lq, (const int8_t *)(qs + 2 * Lq), qs + 3 * Lq};
+        Hap<int8_t> t{Lt, ts, ts + Lt, (const int8_t *)(ts + 2 * Lt), ts + 3 * Lt};
+        QMaps<int8_t> qm{(const int8_t *)qb, qb + Lr, (const int8_t *)(qb + 2 * Lr), (const int8_t *)(qb + 2 * Lr + (Lq + 1 + Lr))};
+        SMemIL mem{base + d.M.walk[ai]};
+        AlnLayout<int> L;
+        const int np = N + Lt + 4;
+        L.oPF = L.oF = L.oD0 = L.oD1 = L.oT0 = L.oT1 = 0;
+        L.oPQ = 0; L.oPT = wa4(2 * np); L.oPS = 2 * wa4(2 * np); L.oLev = L.oPS + wa4(np); L.total = 0;
+        PFWarp pfr{base + d.M.F[ai], N, Lq};
+        const int *r = d.res[ai];
+        u32 status = (u32)r[3];
+        if (!((d.trivial >> ai) & 1))
+            walk_credit<SMemIL, 2, int8_t>(mem, L, pfr, q, qm, t, base + d.M.rseq, Lr, r[2], r[1], in, out, sc, ai, status);
+        for (int k = 0; k < (HOM ? 4 : 1); k++) {
+            out.aln_score[oi + k] = r[0];
+            out.aln_end_plane[oi + k] = (u8)r[1];
+            out.aln_beg_plane[oi + k] = (u8)r[2];
+            out.status[oi + k] = status;
+        }
+        if constexpr (HOM) replicate_hom(in, out, sc);
+    }
+}
+
 #ifndef VD_WSC_PAR_MINBIN
 #define VD_WSC_PAR_MINBIN 2
 #endif
@@ -463,7 +633,12 @@ wsc_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, const int *
 #endif
 constexpr int WSC_PAR_MINBIN_S2 = VD_WSC_PAR_MINBIN_S2;   // the same threshold for two or more register slots
 constexpr int WSC_PAR_MINBIN = VD_WSC_PAR_MINBIN;      // bins >= 10 KB per supercluster: one block per supercluster, one warp per alignment
+#ifndef VD_WSC_SHARED
+#define VD_WSC_SHARED 1
+#endif
 template <int S> inline void wsc_configure_one() {
+    cudaFuncSetAttribute(wsc_block_kernel<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (WSC_TPB / 32) * wsc_bin_cap(N_WBIN - 1));
+    cudaFuncSetAttribute(wsc_block_kernel<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (WSC_TPB / 32) * wsc_bin_cap(N_WBIN - 1));
     cudaFuncSetAttribute(wsc_kernel<S, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (WSC_TPB / 32) * wsc_bin_cap(WSC_PAR_MINBIN > 0 ? WSC_PAR_MINBIN - 1 : 0));
     cudaFuncSetAttribute(wsc_kernel<S, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wsc_bin_cap(N_WBIN - 1));
     cudaFuncSetAttribute(wsc_kernel<S, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (WSC_TPB / 32) * wsc_bin_cap(N_WBIN - 1));
@@ -472,7 +647,11 @@ inline void wsc_configure() { wsc_configure_one<1>(); wsc_configure_one<2>(); ws
 template <int S> inline void wsc_launch_one(cudaStream_t st, int bin, bool hom, const BatchDev &in, const OutDev &out, const ScPlan *plan,
                                             const int *order, int count) {
     const int wb = wsc_bin_cap(bin), wpb = WSC_TPB / 32;
-    if (hom) wsc_kernel<S, false, true><<<(count + wpb - 1) / wpb, WSC_TPB, wpb * wb, st>>>(in, out, plan, order, count, wb);
+    const bool par = bin >= (S >= 2 ? WSC_PAR_MINBIN_S2 : WSC_PAR_MINBIN);
+    if (VD_WSC_SHARED && (hom || !par)) {
+        if (hom) wsc_block_kernel<S, true><<<(count + wpb - 1) / wpb, WSC_TPB, wpb * wb, st>>>(in, out, plan, order, count, wb);
+        else wsc_block_kernel<S, false><<<(count + wpb - 1) / wpb, WSC_TPB, wpb * wb, st>>>(in, out, plan, order, count, wb);
+    } else if (hom) wsc_kernel<S, false, true><<<(count + wpb - 1) / wpb, WSC_TPB, wpb * wb, st>>>(in, out, plan, order, count, wb);
     else if (bin >= (S >= 2 ? WSC_PAR_MINBIN_S2 : WSC_PAR_MINBIN)) wsc_kernel<S, true, false><<<count, WSC_TPB, wb, st>>>(in, out, plan, order, count, wb);
     else wsc_kernel<S, false, false><<<(count + wpb - 1) / wpb, WSC_TPB, wpb * wb, st>>>(in, out, plan, order, count, wb);
 }
