@@ -496,13 +496,13 @@ struct WscDesc {
     int res[4][4];     // per alignment: score, end plane, origin plane, status
 };
 
-template <int S, bool HOM>
-__global__ void __launch_bounds__(WSC_TPB)
+template <int S, bool HOM, int NW>
+__global__ void __launch_bounds__(32 * NW)
 wsc_block_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, const int *__restrict__ order, int count, int warp_bytes) {
     extern __shared__ __align__(16) u8 smem[];
-    __shared__ WscDesc desc[WSC_TPB / 32];
+    __shared__ WscDesc desc[NW];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int slot = blockIdx.x * (WSC_TPB / 32) + warp;
+    const int slot = blockIdx.x * (NW) + warp;
     const bool live = slot < count;
     if (lane == 0) {
         WscDesc &d = desc[warp];
@@ -526,7 +526,7 @@ wsc_block_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, const
     auto qbase = [&](int w, int k) { return smem + w * warp_bytes + desc[w].M.qm[k]; };
 
     // ---- phase 1: warp 0, lane 4w+h expands haplotype h of supercluster w ----
-    if (warp == 0 && lane < 4 * (WSC_TPB / 32)) {
+    if (warp == 0 && lane < 4 * (NW)) {
         const int w = lane >> 2, h = lane & 3;
         const WscDesc &d = desc[w];
         if (d.sc >= 0 && !(HOM && (h & 1))) {
@@ -588,7 +588,7 @@ wsc_block_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, const
     __syncthreads();
 
     // ---- phase 3: warp 0, lane 4w+ai walks alignment ai of supercluster w ----
-    if (warp == 0 && lane < 4 * (WSC_TPB / 32)) {
+    if (warp == 0 && lane < 4 * (NW)) {
         const int w = lane >> 2, ai = lane & 3;
         const WscDesc &d = desc[w];
         if (d.sc < 0 || (HOM && ai)) return;
@@ -636,9 +636,15 @@ constexpr int WSC_PAR_MINBIN = VD_WSC_PAR_MINBIN;      // bins >= 10 KB per supe
 #ifndef VD_WSC_SHARED
 #define VD_WSC_SHARED 1
 #endif
+#ifndef VD_WSC_NW
+#define VD_WSC_NW 4
+#endif
+constexpr int WSC_NW = VD_WSC_NW;      // superclusters (warps) per block of wsc_block_kernel
+constexpr int WSC_SMEM_MAX = 227 * 1024;
 template <int S> inline void wsc_configure_one() {
-    cudaFuncSetAttribute(wsc_block_kernel<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (WSC_TPB / 32) * wsc_bin_cap(N_WBIN - 1));
-    cudaFuncSetAttribute(wsc_block_kernel<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (WSC_TPB / 32) * wsc_bin_cap(N_WBIN - 1));
+    const int shmax = WSC_NW * wsc_bin_cap(N_WBIN - 1) < WSC_SMEM_MAX ? WSC_NW * wsc_bin_cap(N_WBIN - 1) : WSC_SMEM_MAX;
+    cudaFuncSetAttribute(wsc_block_kernel<S, false, WSC_NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, shmax);
+    cudaFuncSetAttribute(wsc_block_kernel<S, true, WSC_NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, shmax);
     cudaFuncSetAttribute(wsc_kernel<S, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (WSC_TPB / 32) * wsc_bin_cap(WSC_PAR_MINBIN > 0 ? WSC_PAR_MINBIN - 1 : 0));
     cudaFuncSetAttribute(wsc_kernel<S, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wsc_bin_cap(N_WBIN - 1));
     cudaFuncSetAttribute(wsc_kernel<S, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (WSC_TPB / 32) * wsc_bin_cap(N_WBIN - 1));
@@ -648,9 +654,9 @@ template <int S> inline void wsc_launch_one(cudaStream_t st, int bin, bool hom, 
                                             const int *order, int count) {
     const int wb = wsc_bin_cap(bin), wpb = WSC_TPB / 32;
     const bool par = bin >= (S >= 2 ? WSC_PAR_MINBIN_S2 : WSC_PAR_MINBIN);
-    if (VD_WSC_SHARED && (hom || !par)) {
-        if (hom) wsc_block_kernel<S, true><<<(count + wpb - 1) / wpb, WSC_TPB, wpb * wb, st>>>(in, out, plan, order, count, wb);
-        else wsc_block_kernel<S, false><<<(count + wpb - 1) / wpb, WSC_TPB, wpb * wb, st>>>(in, out, plan, order, count, wb);
+    if (VD_WSC_SHARED && (hom || !par) && WSC_NW * wb <= WSC_SMEM_MAX) {
+        if (hom) wsc_block_kernel<S, true, WSC_NW><<<(count + WSC_NW - 1) / WSC_NW, 32 * WSC_NW, WSC_NW * wb, st>>>(in, out, plan, order, count, wb);
+        else wsc_block_kernel<S, false, WSC_NW><<<(count + WSC_NW - 1) / WSC_NW, 32 * WSC_NW, WSC_NW * wb, st>>>(in, out, plan, order, count, wb);
     } else if (hom) wsc_kernel<S, false, true><<<(count + wpb - 1) / wpb, WSC_TPB, wpb * wb, st>>>(in, out, plan, order, count, wb);
     else if (bin >= (S >= 2 ? WSC_PAR_MINBIN_S2 : WSC_PAR_MINBIN)) wsc_kernel<S, true, false><<<count, WSC_TPB, wb, st>>>(in, out, plan, order, count, wb);
     else wsc_kernel<S, false, false><<<(count + wpb - 1) / wpb, WSC_TPB, wpb * wb, st>>>(in, out, plan, order, count, wb);
