@@ -23,7 +23,7 @@ for w in $what; do
                  -f -o "$out/prof_small" python bench.py --steps 1 --warmup 3 --no-cpu-baseline > "$out/prof_small.log" 2>&1; echo "full_small rc=$?"
                ncu -i "$out/prof_small.ncu-rep" --page raw --csv > "$out/prof_small_raw.csv" 2>/dev/null
                ncu -i "$out/prof_small.ncu-rep" --page details > "$out/prof_small_details.txt" 2>/dev/null ;;
-    full_wsc)  timeout 1200 ncu --set full --clock-control none -k regex:wsc_kernel -c 24 \
+    full_wsc)  timeout 1200 ncu --set full --clock-control none -k regex:'wsc_kernel|wsc_block_kernel' -c 22 \
                  -f -o "$out/prof_wsc" python bench.py --steps 1 --warmup 3 --no-cpu-baseline > "$out/prof_wsc.log" 2>&1; echo "full_wsc rc=$?"
                ncu -i "$out/prof_wsc.ncu-rep" --page raw --csv > "$out/prof_wsc_raw.csv" 2>/dev/null
                rm -f "$out/prof_wsc.ncu-rep" ;;
