@@ -70,6 +70,38 @@ def _worker(rank, world, port, q):
         for k in ("assigned", "sync_group", "ref_ed", "query_ed"):
             if not (pr[k].numpy() == want[k].reshape(2, -1)[:, vi]).all():
                 bad["record_" + k] = 1
+    # the bench's path beyond two GPUs: the shard in K slices, one record and one all-gather per slice
+    K = 3
+    cut = [len(mine) * k // K for k in range(K + 1)]
+    counts = torch.tensor([[cut[k + 1] - cut[k], int(np.diff(sub.var_off[[4 * cut[k], 4 * cut[k + 1]]])[0])] for k in range(K)])
+    allc = [torch.zeros_like(counts) for _ in range(world)]
+    dist.all_gather(allc, counts)
+    caps = torch.stack(allc).numpy().max(axis=0)
+    seen_sc = []
+    for k in range(K):
+        sl = np.arange(cut[k], cut[k + 1])
+        part = sub.take(sl)
+        o = checkers.oracle_run(part).trimmed()
+        rk = shard.ResultRecord(int(caps[k, 0]), max(int(caps[k, 1]), 1), "cpu")
+        rk.set_shard(mine[sl], vidx[int(sub.var_off[4 * cut[k]]): int(sub.var_off[4 * cut[k + 1]])])
+        for name in ("aln_score", "aln_end_plane", "aln_beg_plane", "assigned", "sync_group", "ref_ed", "query_ed", "callq"):
+            rk.views[name][: len(o[name])] = torch.from_numpy(o[name])
+        rk.views["status"][: len(o["status"])] = torch.from_numpy(o["status"].view(np.int32))
+        gk = rk.all_gather(dist)
+        for r in range(world):
+            pr = rk.parse(gk, r)
+            sidx = pr["sc_idx"].numpy().astype(np.int64)
+            if r == rank:
+                seen_sc.append(sidx)
+            aidx = (sidx[:, None] * 4 + np.arange(4)[None, :]).reshape(-1)
+            if not (pr["aln_score"].numpy() == want["aln_score"][aidx]).all():
+                bad["slice_score"] = 1
+            vi = pr["var_idx"].numpy().astype(np.int64)
+            for name in ("assigned", "sync_group", "ref_ed", "query_ed"):
+                if not (pr[name].numpy() == want[name].reshape(2, -1)[:, vi]).all():
+                    bad["slice_" + name] = 1
+    if not (np.concatenate(seen_sc) == mine).all():
+        bad["slice_cover"] = 1
     q.put((rank, bad))
     dist.barrier()
     dist.destroy_process_group()
