@@ -76,6 +76,15 @@ struct PFWarp {      // path flags, [column][row], QUERY rows first
     __device__ __forceinline__ void prefetch(int, int, int) const {}
 };
 
+// resident blocks per SM the register allocation must allow, by register-slot count (build-time knobs)
+#ifndef VD_WSC_MINB_S1
+#define VD_WSC_MINB_S1 1
+#endif
+#ifndef VD_WSC_MINB_S3
+#define VD_WSC_MINB_S3 1
+#endif
+constexpr int wsc_minb(int S) { return S == 1 ? VD_WSC_MINB_S1 : (S >= 3 ? VD_WSC_MINB_S3 : 1); }
+
 // one alignment as the sweeps see it (all pointers into the supercluster's shared-memory region)
 struct WscAln {
     const u8 *qstr, *qflg, *rseq, *rflg;
@@ -353,7 +362,7 @@ __device__ __forceinline__ void wsc_sweep(const int lane, const WscAln &X, int &
 //               drops fourfold).
 // HOM: homozygous superclusters (always !PAR): alignment Q1T1 only, then replicate_hom.
 template <int S, bool PAR, bool HOM>
-__global__ void __launch_bounds__(WSC_TPB)
+__global__ void __launch_bounds__(WSC_TPB, wsc_minb(S))
 wsc_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, const int *__restrict__ order, int count, int warp_bytes) {
     extern __shared__ __align__(16) u8 smem[];
     constexpr unsigned FULL = 0xffffffffu;
@@ -497,7 +506,7 @@ struct WscDesc {
 };
 
 template <int S, bool HOM, int NW>
-__global__ void __launch_bounds__(32 * NW)
+__global__ void __launch_bounds__(32 * NW, wsc_minb(S))
 wsc_block_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, const int *__restrict__ order, int count, int warp_bytes) {
     extern __shared__ __align__(16) u8 smem[];
     __shared__ WscDesc desc[NW];
