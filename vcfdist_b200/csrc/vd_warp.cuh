@@ -77,13 +77,17 @@ struct PFWarp {      // path flags, [column][row], QUERY rows first
 };
 
 // resident blocks per SM the register allocation must allow, by register-slot count (build-time knobs)
+// (S=1: 8 blocks = 64 registers, measured best; more slots need more registers per thread)
 #ifndef VD_WSC_MINB_S1
-#define VD_WSC_MINB_S1 1
+#define VD_WSC_MINB_S1 8
+#endif
+#ifndef VD_WSC_MINB_S2
+#define VD_WSC_MINB_S2 6
 #endif
 #ifndef VD_WSC_MINB_S3
-#define VD_WSC_MINB_S3 1
+#define VD_WSC_MINB_S3 4
 #endif
-constexpr int wsc_minb(int S) { return S == 1 ? VD_WSC_MINB_S1 : (S >= 3 ? VD_WSC_MINB_S3 : 1); }
+constexpr int wsc_minb(int S) { return S == 1 ? VD_WSC_MINB_S1 : (S == 2 ? VD_WSC_MINB_S2 : VD_WSC_MINB_S3); }
 
 // one alignment as the sweeps see it (all pointers into the supercluster's shared-memory region)
 struct WscAln {
