@@ -495,7 +495,6 @@ extern "C" int vd_run_device_slice(vd_handle *h, const vd_batch_in *in, vd_batch
 extern "C" int vd_run(vd_handle *h, const vd_batch_in *in, vd_batch_out *out) {
     if (!h || !in || !out) return VD_E_BADINPUT;
     CK(cudaSetDevice(h->device));
-    cudaStream_t st = h->stream;
     const int64_t n_sc = in->n_sc;
     if (n_sc < 0) return fail(h, VD_E_BADINPUT, "negative n_sc");
     h->stats = vd_stats{};

@@ -451,7 +451,7 @@ wsc_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, const int *
     for (int ai = PAR ? warp : 0; ai < (PAR ? warp + 1 : (HOM ? 1 : 4)); ai++) {
         if ((trivial >> ai) & 1) continue;          // my_score = my_end = my_beg = my_status = 0
         const int qh = ai >> 1, th = 2 + (ai & 1);
-        const int Lq = p.len[qh], Lt = p.len[th], N = Lq + Lr;
+        const int Lq = p.len[qh], Lt = p.len[th];
         const u8 *qstr = hstr(qh), *qflg = hflg(qh);
         const u16 *tinf = (const u16 *)(base + M.tinf[ai & 1]);
         const int8_t *qptr = hptr(qh), *rptr = qrptr(qh), *toQ = qtoQ(qh), *toR = qtoR(qh);
