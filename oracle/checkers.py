@@ -91,3 +91,32 @@ def reference_run(batch: Batch, canonical: bool = False, threads: int = 1, max_r
     res = {k: (a[:nv2] if k not in ("sc_phase", "orig_dist", "swap_dist") else a[: batch.n_sc])
            for k, a in arrs.items()}
     return res, sec.value
+
+
+# --------------------------------------------------------------------------------------
+# SURVEY 8f-1 groundwork: wf_swg_max_reach (src/dist.cpp:2150-2333)
+# --------------------------------------------------------------------------------------
+_REACH_ARGS = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+
+
+def reach_oracle(query: bytes, truth: bytes, main_diag: int, main_diag_start: int, max_score: int,
+                 sub: int, open_: int, extend: int, reverse: bool) -> int:
+    """The C restatement (oracle/vd_reach.c)."""
+    lib = load_oracle()
+    lib.vdo_max_reach.argtypes = _REACH_ARGS
+    lib.vdo_max_reach.restype = C.c_int
+    return lib.vdo_max_reach(query, len(query), truth, len(truth), main_diag, main_diag_start, max_score,
+                             sub, open_, extend, int(reverse))
+
+
+def reach_reference(query: bytes, truth: bytes, main_diag: int, main_diag_start: int, max_score: int,
+                    sub: int, open_: int, extend: int, reverse: bool) -> int:
+    """The reference's own object code (oracle/ref_harness.cpp: vdref_max_reach)."""
+    key = "reach:libvdref.so"
+    if key not in _ref_libs:
+        _ref_libs[key] = C.CDLL(os.path.join(ORACLE_DIR, "libvdref.so"))
+    lib = _ref_libs[key]
+    lib.vdref_max_reach.argtypes = _REACH_ARGS
+    lib.vdref_max_reach.restype = C.c_int
+    return lib.vdref_max_reach(query, len(query), truth, len(truth), main_diag, main_diag_start, max_score,
+                               sub, open_, extend, int(reverse))

@@ -156,4 +156,16 @@ int vdref_run(const vd_batch_in *in, vdref_out *out, int threads, double max_ram
     return 0;
 }
 
+/* SURVEY 8f-1 groundwork: the reference's own wf_swg_max_reach (src/dist.cpp:2150-2333) on plain
+ * strings, with the offsets buffer prepared as its callers do (src/cluster.cpp:1080-1091, :1141-1152:
+ * MATS * (max(open+extend, sub)+1) * (|query|+|truth|-1) entries, all -2).                          */
+int vdref_max_reach(const char *query, int query_len, const char *truth, int truth_len,
+                    int main_diag, int main_diag_start, int max_score, int sub, int open, int extend,
+                    int reverse) {
+    const std::string q(query, query + query_len), t(truth, truth + truth_len);
+    std::vector<int> offs((size_t)MATS * (std::max(open + extend, sub) + 1) * (q.size() + t.size() - 1), -2);
+    return wf_swg_max_reach(q, t, offs, main_diag, main_diag_start, max_score, sub, open, extend,
+                            false /* print */, reverse != 0);
+}
+
 }  /* extern "C" */

@@ -1,0 +1,136 @@
+/* TEST INFRASTRUCTURE - plain-C restatement of the reference's wf_swg_max_reach
+ * (/root/reference/src/dist.cpp:2150-2333): affine-gap (Gotoh) wavefront search that returns the
+ * farthest truth (reference) index reachable with a score <= max_score when every variant of the
+ * cluster must be taken; the cluster-growing step of SURVEY.md 8f-1 (src/cluster.cpp:954-1263 calls
+ * it with iterative doubling).  Groundwork for the next row of the scope table: only the oracle
+ * exists so far, pinned against the reference's object code by tests/test_reach_oracle.py.
+ *
+ * Wavefront layout.  Diagonal index d in [0, nd), nd = |query| + |truth| - 1, stands for
+ * k = d + 1 - |query| (truth index minus query index).  Three wavefront kinds (M: match/substitution,
+ * I: insertion = query base consumed, D: deletion = truth base consumed), each holding for every
+ * diagonal the furthest QUERY index reached, NONE (-2) when the diagonal is not reached; the M
+ * wavefront of score 0 starts at query index -1 on the main diagonal k = 0.  Only the last
+ * max(x, o+e) + 1 scores are kept (ring buffer).
+ *
+ * forward  (reverse = 0): opening a gap costs o+e, extending e, leaving a gap is free and happens
+ *          at the start of the same score (I/D wavefronts are merged into M before extension);
+ * reverse  (reverse = 1): entering a gap costs e, leaving it costs o (the string pair is reversed
+ *          by the caller, so the gap-open penalty is paid on the other side).
+ * main_diag / main_diag_start: on the diagonal k = main_diag the free extension stops one before
+ * query index (main_diag_start - main_diag) - matching reference bases beyond the cluster is not a
+ * "reach" (src/dist.cpp:2144-2147).                                                               */
+#include <stdlib.h>
+
+#define NONE (-2)
+enum { WM = 0, WI = 1, WD = 2, NW = 3 };
+
+typedef struct {
+    int *v;              /* [NW][ring][nd] */
+    int nd, ring;
+} wf_t;
+
+static inline int *wf(const wf_t *w, int kind, int slot, int d) {
+    return w->v + ((size_t)kind * w->ring + slot) * w->nd + d;
+}
+static inline int slot_of(int slot, int back, int ring) {
+    int s = slot - back;
+    return s < 0 ? s + ring : s;
+}
+
+int vdo_max_reach(const char *query, int qlen, const char *truth, int tlen,
+                  int main_diag, int main_diag_start, int max_score, int x, int o, int e, int reverse) {
+    wf_t w;
+    w.nd = qlen + tlen - 1;
+    w.ring = (x > o + e ? x : o + e) + 1;
+    const size_t total = (size_t)NW * w.ring * w.nd;
+    w.v = (int *)malloc(sizeof(int) * (total ? total : 1));
+    for (size_t i = 0; i < total; i++) w.v[i] = NONE;
+    const int stop_q = main_diag_start - main_diag;      /* :2160 */
+    int score = 0, slot = 0, result = -1;
+    *wf(&w, WM, slot, qlen - 1) = -1;                    /* :2166: diagonal k = 0, before the first base */
+
+    for (;;) {
+        /* forward: gaps are left for free at the score they were reached with   (:2171-2184) */
+        if (!reverse)
+            for (int kind = WI; kind <= WD; kind++)
+                for (int d = 0; d < w.nd; d++) {
+                    const int q = *wf(&w, kind, slot, d), k = d + 1 - qlen;
+                    if (q >= 0 && q < qlen && k + q >= 0 && k + q < tlen && q >= *wf(&w, WM, slot, d))
+                        *wf(&w, WM, slot, d) = q;
+                }
+        /* free extension along matches, then the two exits   (:2187-2212) */
+        for (int d = 0; d < w.nd; d++) {
+            int q = *wf(&w, WM, slot, d);
+            const int k = d + 1 - qlen;
+            while ((k != main_diag || q + 1 < stop_q) && q != NONE && k + q >= -1 &&
+                   q < qlen - 1 && k + q < tlen - 1 && query[q + 1] == truth[k + q + 1])
+                q++;
+            *wf(&w, WM, slot, d) = q;
+            if (q + k == tlen - 1) { result = tlen - 1; goto done; }                     /* :2205-2207 */
+            if (q == qlen - 1 && q + k >= 0 && q + k < tlen - 1) { result = q + k; goto done; }   /* :2208-2210 */
+        }
+        if (score == max_score) break;                   /* :2213 */
+
+        /* next score   (:2225-2311) */
+        score++;
+        slot = slot + 1 == w.ring ? 0 : slot + 1;
+        for (int kind = WM; kind < NW; kind++)           /* :2228-2232 clears I and D; M of this slot is */
+            for (int d = 0; d < w.nd; d++)               /* overwritten below only through >= tests      */
+                if (kind != WM) *wf(&w, kind, slot, d) = NONE;
+        for (int d = 0; d < w.nd; d++) {
+            const int k = d + 1 - qlen;
+            int *m_cur = wf(&w, WM, slot, d), *i_cur = wf(&w, WI, slot, d), *d_cur = wf(&w, WD, slot, d);
+            /* substitution   (:2239-2250) */
+            if (score - x >= 0) {
+                const int p = *wf(&w, WM, slot_of(slot, x, w.ring), d);
+                if (p != NONE && p + 1 < qlen && k + p + 1 < tlen && p + 1 >= *m_cur) *m_cur = p + 1;
+            }
+            /* gap opening: o+e forwards, e in the reversed problem   (:2252-2275) */
+            {
+                const int cost = reverse ? e : o + e;
+                if (score - cost >= 0) {
+                    const int ps = slot_of(slot, cost, w.ring);
+                    if (d > 0) {
+                        const int p = *wf(&w, WM, ps, d - 1);
+                        if (p != NONE && k + p < tlen && p >= *d_cur) *d_cur = p;
+                    }
+                    if (d < w.nd - 1) {
+                        const int p = *wf(&w, WM, ps, d + 1);
+                        if (p != NONE && p + 1 < qlen && k + p + 1 < tlen && k + p + 1 >= 0 && p + 1 >= *i_cur) *i_cur = p + 1;
+                    }
+                }
+            }
+            /* reversed problem: leaving a gap costs o   (:2277-2294) */
+            if (reverse && score - o >= 0) {
+                const int ps = slot_of(slot, o, w.ring);
+                for (int kind = WI; kind <= WD; kind++) {
+                    const int p = *wf(&w, kind, ps, d);
+                    if (p >= 0 && p < qlen && k + p >= 0 && k + p < tlen && p > *m_cur) *m_cur = p;
+                }
+            }
+            /* gap extension   (:2296-2311) */
+            if (score - e >= 0) {
+                const int ps = slot_of(slot, e, w.ring);
+                if (d > 0) {
+                    const int p = *wf(&w, WD, ps, d - 1);
+                    if (p != NONE && k + p < tlen && p >= *d_cur) *d_cur = p;
+                }
+                if (d < w.nd - 1) {
+                    const int p = *wf(&w, WI, ps, d + 1);
+                    if (p != NONE && p + 1 < qlen && k + p + 1 < tlen && k + p + 1 >= 0 && p + 1 >= *i_cur) *i_cur = p + 1;
+                }
+            }
+        }
+    }
+    /* the score budget is spent: furthest truth index over everything still in the ring   (:2316-2331) */
+    result = 0;
+    for (int kind = WM; kind < NW; kind++)
+        for (int s = 0; s < w.ring; s++)
+            for (int d = 0; d < w.nd; d++) {
+                const int q = *wf(&w, kind, s, d), k = d + 1 - qlen;
+                if (q >= 0 && q < qlen && k + q >= 0 && k + q < tlen && k + q > result) result = k + q;
+            }
+done:
+    free(w.v);
+    return result;
+}

@@ -1,0 +1,26 @@
+"""Known answers of the reference's wf_swg_max_reach (src/dist.cpp:2150-2333) on seeded random cases,
+recorded through oracle/_ref/libvdref.so (needs /root/reference to have been built by oracle/Makefile).
+usage: python tests/golden/make_reach_kat.py   ->  tests/golden/reach_kat.npz"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from oracle import checkers  # noqa: E402
+from test_reach_oracle import random_case  # noqa: E402
+
+rng = np.random.default_rng(20261017)
+qs, ts, q_off, t_off, params, answer = [], [], [0], [0], [], []
+for _ in range(3000):
+    q, t, md, mds, ms, x, o, e, rev = random_case(rng)
+    qs.append(np.frombuffer(q, np.uint8)); ts.append(np.frombuffer(t, np.uint8))
+    q_off.append(q_off[-1] + len(q)); t_off.append(t_off[-1] + len(t))
+    params.append([md, mds, ms, x, o, e, int(rev)])
+    answer.append(checkers.reach_reference(q, t, md, mds, ms, x, o, e, rev))
+np.savez_compressed(os.path.join(ROOT, "tests", "golden", "reach_kat.npz"), query=np.concatenate(qs), truth=np.concatenate(ts),
+                    q_off=np.array(q_off, np.int64), t_off=np.array(t_off, np.int64), params=np.array(params, np.int32),
+                    answer=np.array(answer, np.int32))
+print("wrote", len(answer), "cases; distinct answers:", len(set(answer)))

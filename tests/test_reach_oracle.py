@@ -1,0 +1,65 @@
+"""SURVEY 8f-1 groundwork: the C restatement of wf_swg_max_reach (oracle/vd_reach.c) against the
+reference's own object code (src/dist.cpp:2150-2333 behind oracle/ref_harness.cpp) on fresh random
+cases, and against known answers recorded from the reference (tests/golden/reach_kat.npz) where the
+reference objects are not available.  CPU only; no CUDA path exists for this row yet."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from oracle import checkers
+
+KAT = os.path.join(ROOT, "tests", "golden", "reach_kat.npz")
+
+
+def random_case(rng):
+    """A cluster-like pair: truth = reference window, query = the window with a few variants applied
+    (so that main_diag = net length change, as src/cluster.cpp:1059-1064 computes it), optionally
+    reversed as the leftward search does (src/cluster.cpp:1077-1078)."""
+    alphabet = b"ACGT"[: int(rng.integers(2, 5))]
+    tlen = int(rng.integers(2, 90))
+    truth = bytes(rng.choice(list(alphabet), tlen).tolist())
+    q = bytearray()
+    main_diag = 0
+    pos = 0
+    last_var_end = 0
+    while pos < tlen:
+        r = rng.random()
+        if r < 0.06:                                   # substitution
+            q.append(alphabet[(alphabet.index(truth[pos]) + 1) % len(alphabet)]); pos += 1; last_var_end = pos
+        elif r < 0.10:                                 # insertion
+            n = int(rng.integers(1, 6)); q.extend(rng.choice(list(alphabet), n).tolist()); main_diag -= n; last_var_end = pos
+        elif r < 0.14:                                 # deletion
+            n = int(rng.integers(1, 6)); pos += n; main_diag += min(n, tlen - (pos - n)); last_var_end = min(pos, tlen)
+        else:
+            q.append(truth[pos]); pos += 1
+    if not q:
+        q.append(alphabet[0])
+    query = bytes(q)
+    reverse = bool(rng.integers(0, 2))
+    if reverse:
+        query, truth = query[::-1], truth[::-1]
+    sub, open_, extend = int(rng.integers(0, 6)), int(rng.integers(0, 7)), int(rng.integers(1, 4))
+    max_score = int(rng.integers(0, 40))
+    main_diag_start = int(rng.integers(0, tlen + 3)) if rng.random() < 0.5 else last_var_end
+    return query, truth, main_diag, main_diag_start, max_score, sub, open_, extend, reverse
+
+
+@pytest.mark.skipif(not checkers.reference_available(False), reason="reference objects not built (no /root/reference)")
+def test_restatement_matches_reference_object_code():
+    rng = np.random.default_rng()          # fresh cases every run
+    for _ in range(4000):
+        case = random_case(rng)
+        assert checkers.reach_oracle(*case) == checkers.reach_reference(*case), case
+
+
+def test_restatement_matches_recorded_reference_answers():
+    z = np.load(KAT, allow_pickle=False)
+    n = len(z["answer"])
+    assert n >= 1000
+    for i in range(n):
+        q = z["query"][z["q_off"][i]: z["q_off"][i + 1]].tobytes()
+        t = z["truth"][z["t_off"][i]: z["t_off"][i + 1]].tobytes()
+        p = [int(x) for x in z["params"][i]]
+        assert checkers.reach_oracle(q, t, p[0], p[1], p[2], p[3], p[4], p[5], bool(p[6])) == int(z["answer"][i]), i
