@@ -5,7 +5,7 @@ for f in sys.argv[1:]:
     agg=collections.OrderedDict()
     for r in rows:
         name=re.sub(r"\(.*","",r[4])
-        m=re.search(r"(wave_fwd_kernel|wave_bwd_kernel|mid_kernel|small_kernel)<([\d, ]+)>", r[4])
+        m=re.search(r"(wave_fwd_kernel|wave_bwd_kernel|small_kernel|small_hom_kernel|wsc_kernel|wsc_block_kernel)<([\d, ]+)>", r[4])
         if m: name=f"{m.group(1)}<{m.group(2)}>"
         key=(name,r[7],)
         a=agg.setdefault(key,[0,0.0,0])

@@ -1,5 +1,6 @@
 // Kernels of the precision/recall path (sm_100a):
-//   plan_kernel        sizes + class of every supercluster, work list of the non-tiny ones
+//   plan_kernel        sizes, kernel choice (launch rank) and homozygosity of every supercluster, work list
+//                      of the long ones
 //   small_kernel<K>    fused: one thread per alignment, one quad per supercluster, all
 //                      matrices in shared memory; three footprint classes, cost-sorted order
 //   slab_size_kernel / slab_setup_kernel / slab_align_kernel

@@ -2,10 +2,10 @@
 // two-plane DP, backward max-TP pass, path walk, sync sections and integer credit.
 //
 // The same code runs in two places, selected by the memory accessor:
-//   * the fused short-supercluster kernel (vd_tiny.cu): every matrix of the alignment lives
+//   * the fused short-supercluster kernels (small_kernel / small_hom_kernel, vd_kernels.cuh): every matrix of the alignment lives
 //     in shared memory, one slice per thread with an odd word stride (bank-conflict free
 //     when lanes touch the same offset);
-//   * the scalar fallback kernel (vd_wave.cu): matrices in an HBM scratch slab, for shapes
+//   * the scalar fallback kernel (slab_align_kernel, vd_kernels.cuh): matrices in an HBM scratch slab, for shapes
 //     the wavefront kernels do not take (e.g. more than two swap sources per row).
 // The walk / credit / Levenshtein tail is also what the long-supercluster path runs after
 // its wavefront forward and backward kernels.
