@@ -120,3 +120,25 @@ def reach_reference(query: bytes, truth: bytes, main_diag: int, main_diag_start:
     lib.vdref_max_reach.restype = C.c_int
     return lib.vdref_max_reach(query, len(query), truth, len(truth), main_diag, main_diag_start, max_score,
                                sub, open_, extend, int(reverse))
+
+
+_SWG_ARGS = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int]
+
+
+def swg_score_oracle(query: bytes, truth: bytes, sub: int, open_: int, extend: int) -> int:
+    """Affine-gap alignment score, C restatement of wf_swg_align's score (oracle/vd_reach.c)."""
+    lib = load_oracle()
+    lib.vdo_swg_score.argtypes = _SWG_ARGS
+    lib.vdo_swg_score.restype = C.c_int
+    return lib.vdo_swg_score(query, len(query), truth, len(truth), sub, open_, extend)
+
+
+def swg_score_reference(query: bytes, truth: bytes, sub: int, open_: int, extend: int) -> int:
+    """The reference's own wf_swg_align (oracle/ref_harness.cpp: vdref_swg_score)."""
+    key = "reach:libvdref.so"
+    if key not in _ref_libs:
+        _ref_libs[key] = C.CDLL(os.path.join(ORACLE_DIR, "libvdref.so"))
+    lib = _ref_libs[key]
+    lib.vdref_swg_score.argtypes = _SWG_ARGS
+    lib.vdref_swg_score.restype = C.c_int
+    return lib.vdref_swg_score(query, len(query), truth, len(truth), sub, open_, extend)

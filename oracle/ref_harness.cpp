@@ -168,4 +168,14 @@ int vdref_max_reach(const char *query, int query_len, const char *truth, int tru
                             false /* print */, reverse != 0);
 }
 
+/* the reference's wf_swg_align (src/dist.cpp:1510-1652): its score */
+int vdref_swg_score(const char *query, int query_len, const char *truth, int truth_len, int sub, int open, int extend) {
+    const std::string q(query, query + query_len), t(truth, truth + truth_len);
+    std::vector<std::vector<std::vector<uint8_t>>> ptrs(MATS);
+    std::vector<std::vector<std::vector<int>>> offs(MATS);
+    int s = 0;
+    wf_swg_align(q, t, ptrs, offs, s, sub, open, extend, false);
+    return s;
+}
+
 }  /* extern "C" */

@@ -134,3 +134,80 @@ done:
     free(w.v);
     return result;
 }
+
+
+/* Restatement of the reference's wf_swg_align (/root/reference/src/dist.cpp:1510-1652) as far as its
+ * score goes: global affine-gap (Gotoh) wavefront alignment, mismatch x, gap open o, gap extension e;
+ * returns the first score at which some wavefront reaches the last base of both strings.  The
+ * cluster-growing step uses only this score (src/cluster.cpp:1040-1046: the budget of the reach
+ * searches); the backtrack pointers the reference also records are what `--distance` consumes
+ *  and are not restated here.  Same diagonal / wavefront conventions as above; every
+ * wavefront of a new score starts empty (:1583-1587).
+ *
+ * Not the textbook Gotoh distance: the search starts BEFORE the first base on the main diagonal and a
+ * gap cannot be opened there (the insertion test needs a truth index >= 0, :1613-1617, and the
+ * deletion moves to a diagonal whose query index -1 can never be extended into query[0] with truth[0]),
+ * so the first bases of the two strings are always paired: "CA" vs "A" scores x + (o+e), not o+e.
+ * The reference's callers always pass strings that start with the same flanking reference base
+ * (src/cluster.cpp:1037-1041), where the two coincide; measured against a textbook implementation the
+ * two differ in about one of six random pairs.  Anything that replaces this function must reproduce it
+ * or keep that precondition.                                                                         */
+int vdo_swg_score(const char *query, int qlen, const char *truth, int tlen, int x, int o, int e) {
+    wf_t w;
+    w.nd = qlen + tlen - 1;
+    w.ring = (x > o + e ? x : o + e) + 1;
+    const size_t total = (size_t)NW * w.ring * w.nd;
+    w.v = (int *)malloc(sizeof(int) * (total ? total : 1));
+    for (size_t i = 0; i < total; i++) w.v[i] = NONE;
+    int score = 0, slot = 0;
+    *wf(&w, WM, slot, qlen - 1) = -1;                                   /* :1528 */
+    for (;;) {
+        for (int kind = WI; kind <= WD; kind++)                           /* gaps are left for free (:1533-1547) */
+            for (int d = 0; d < w.nd; d++) {
+                const int q = *wf(&w, kind, slot, d), k = d + 1 - qlen;
+                if (q >= 0 && q < qlen && k + q >= 0 && k + q < tlen && q >= *wf(&w, WM, slot, d))
+                    *wf(&w, WM, slot, d) = q;
+            }
+        for (int d = 0; d < w.nd; d++) {                                  /* extension (:1550-1568) */
+            int q = *wf(&w, WM, slot, d);
+            const int k = d + 1 - qlen;
+            while (q != NONE && k + q >= -1 && q < qlen - 1 && k + q < tlen - 1 && query[q + 1] == truth[k + q + 1]) q++;
+            *wf(&w, WM, slot, d) = q;
+            if (q == qlen - 1 && q + k == tlen - 1) { free(w.v); return score; }
+        }
+        score++;
+        slot = slot + 1 == w.ring ? 0 : slot + 1;
+        for (int kind = WM; kind < NW; kind++)
+            for (int d = 0; d < w.nd; d++) *wf(&w, kind, slot, d) = NONE;
+        for (int d = 0; d < w.nd; d++) {
+            const int k = d + 1 - qlen;
+            int *m_cur = wf(&w, WM, slot, d), *i_cur = wf(&w, WI, slot, d), *d_cur = wf(&w, WD, slot, d);
+            if (score - x >= 0) {                                         /* :1592-1600 */
+                const int p = *wf(&w, WM, slot_of(slot, x, w.ring), d);
+                if (p != NONE && p + 1 < qlen && k + p + 1 < tlen && p + 1 >= *m_cur) *m_cur = p + 1;
+            }
+            if (score - (o + e) >= 0) {                                   /* :1602-1625 */
+                const int ps = slot_of(slot, o + e, w.ring);
+                if (d > 0) {
+                    const int p = *wf(&w, WM, ps, d - 1);
+                    if (p != NONE && k + p < tlen && p >= *d_cur) *d_cur = p;
+                }
+                if (d < w.nd - 1) {
+                    const int p = *wf(&w, WM, ps, d + 1);
+                    if (p != NONE && p + 1 < qlen && k + p + 1 < tlen && k + p + 1 >= 0 && p + 1 >= *i_cur) *i_cur = p + 1;
+                }
+            }
+            if (score - e >= 0) {                                         /* :1627-1650 */
+                const int ps = slot_of(slot, e, w.ring);
+                if (d > 0) {
+                    const int p = *wf(&w, WD, ps, d - 1);
+                    if (p != NONE && k + p < tlen && p >= *d_cur) *d_cur = p;
+                }
+                if (d < w.nd - 1) {
+                    const int p = *wf(&w, WI, ps, d + 1);
+                    if (p != NONE && p + 1 < qlen && k + p + 1 < tlen && k + p + 1 >= 0 && p + 1 >= *i_cur) *i_cur = p + 1;
+                }
+            }
+        }
+    }
+}

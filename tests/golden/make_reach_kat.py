@@ -20,7 +20,14 @@ for _ in range(3000):
     q_off.append(q_off[-1] + len(q)); t_off.append(t_off[-1] + len(t))
     params.append([md, mds, ms, x, o, e, int(rev)])
     answer.append(checkers.reach_reference(q, t, md, mds, ms, x, o, e, rev))
+# affine scores (wf_swg_align) of the same string pairs with their own penalties
+swg_params, swg_answer = [], []
+for i in range(len(answer)):
+    x, o, e = int(rng.integers(1, 7)), int(rng.integers(0, 8)), int(rng.integers(1, 4))
+    swg_params.append([x, o, e])
+    swg_answer.append(checkers.swg_score_reference(qs[i].tobytes(), ts[i].tobytes(), x, o, e))
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "reach_kat.npz"), query=np.concatenate(qs), truth=np.concatenate(ts),
                     q_off=np.array(q_off, np.int64), t_off=np.array(t_off, np.int64), params=np.array(params, np.int32),
-                    answer=np.array(answer, np.int32))
+                    answer=np.array(answer, np.int32), swg_params=np.array(swg_params, np.int32),
+                    swg_answer=np.array(swg_answer, np.int32))
 print("wrote", len(answer), "cases; distinct answers:", len(set(answer)))

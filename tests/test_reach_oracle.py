@@ -63,3 +63,47 @@ def test_restatement_matches_recorded_reference_answers():
         t = z["truth"][z["t_off"][i]: z["t_off"][i + 1]].tobytes()
         p = [int(x) for x in z["params"][i]]
         assert checkers.reach_oracle(q, t, p[0], p[1], p[2], p[3], p[4], p[5], bool(p[6])) == int(z["answer"][i]), i
+
+
+def random_pair(rng):
+    alphabet = b"ACGT"[: int(rng.integers(2, 5))]
+    q = bytes(rng.choice(list(alphabet), int(rng.integers(1, 60))).tolist())
+    if rng.random() < 0.6:                      # truth = query with a few edits (the clustering use case)
+        t = bytearray(q)
+        for _ in range(int(rng.integers(0, 5))):
+            p = int(rng.integers(0, len(t) + 1))
+            r = rng.random()
+            if r < 0.4 and len(t) > 1:
+                del t[p: p + int(rng.integers(1, 5))]
+            elif r < 0.8:
+                t[p:p] = bytes(rng.choice(list(alphabet), int(rng.integers(1, 5))).tolist())
+            elif p < len(t):
+                t[p] = alphabet[(alphabet.index(t[p]) + 1) % len(alphabet)]
+        t = bytes(t) if len(t) else alphabet[:1]
+    else:
+        t = bytes(rng.choice(list(alphabet), int(rng.integers(1, 60))).tolist())
+    return q, t, int(rng.integers(1, 7)), int(rng.integers(0, 8)), int(rng.integers(1, 4))
+
+
+@pytest.mark.skipif(not checkers.reference_available(False), reason="reference objects not built (no /root/reference)")
+def test_affine_score_matches_reference_object_code():
+    """wf_swg_align's score (src/dist.cpp:1510-1652): the budget of the reach searches."""
+    rng = np.random.default_rng()
+    for _ in range(4000):
+        case = random_pair(rng)
+        assert checkers.swg_score_oracle(*case) == checkers.swg_score_reference(*case), case
+
+
+def test_affine_score_known_answers():
+    """Recorded from the reference (first bases are always paired: no leading gap)."""
+    for q, t, x, o, e, want in [(b"CA", b"A", 1, 1, 1, 3), (b"CA", b"A", 3, 1, 1, 5), (b"A", b"CA", 1, 1, 1, 3),
+                               (b"AC", b"A", 3, 1, 1, 2), (b"A", b"AC", 1, 1, 1, 2), (b"GCA", b"A", 3, 1, 1, 6),
+                               (b"CCCA", b"A", 1, 1, 1, 5), (b"ACCC", b"A", 3, 1, 1, 4)]:
+        assert checkers.swg_score_oracle(q, t, x, o, e) == want
+    z = np.load(KAT, allow_pickle=False)
+    if "swg_answer" in z.files:
+        for i in range(len(z["swg_answer"])):
+            q = z["query"][z["q_off"][i]: z["q_off"][i + 1]].tobytes()
+            t = z["truth"][z["t_off"][i]: z["t_off"][i + 1]].tobytes()
+            p = [int(v) for v in z["swg_params"][i]]
+            assert checkers.swg_score_oracle(q, t, p[0], p[1], p[2]) == int(z["swg_answer"][i]), i
