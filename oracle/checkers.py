@@ -142,3 +142,26 @@ def swg_score_reference(query: bytes, truth: bytes, sub: int, open_: int, extend
     lib.vdref_swg_score.argtypes = _SWG_ARGS
     lib.vdref_swg_score.restype = C.c_int
     return lib.vdref_swg_score(query, len(query), truth, len(truth), sub, open_, extend)
+
+
+def cluster_reference(fasta: bytes, var, sub: int, open_: int, extend: int, max_iters: int = 4, reach_min_gap: int = 10):
+    """The reference's own wf_swg_cluster (oracle/ref_harness.cpp: vdref_cluster) on one haplotype.
+    var[i] = (pos, rlen, type, alt bytes), sorted.  -> (clusters, left_reaches, right_reaches)."""
+    key = "reach:libvdref.so"
+    if key not in _ref_libs:
+        _ref_libs[key] = C.CDLL(os.path.join(ORACLE_DIR, "libvdref.so"))
+    lib = _ref_libs[key]
+    n = len(var)
+    pos = np.array([v[0] for v in var], np.int32)
+    rlen = np.array([v[1] for v in var], np.int32)
+    typ = np.array([v[2] for v in var], np.uint8)
+    alt_off = np.zeros(n + 1, np.int64)
+    alt_off[1:] = np.cumsum([len(v[3]) for v in var])
+    alt = b"".join(v[3] for v in var) or b"\0"
+    out = [np.zeros(n + 1, np.int32) for _ in range(3)]
+    lib.vdref_cluster.restype = C.c_int
+    lib.vdref_cluster.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p,
+                                  C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    nc = lib.vdref_cluster(fasta, len(fasta), n, pos.ctypes.data, rlen.ctypes.data, typ.ctypes.data, alt_off.ctypes.data, alt,
+                           sub, open_, extend, max_iters, reach_min_gap, out[0].ctypes.data, out[1].ctypes.data, out[2].ctypes.data)
+    return [list(map(int, o[:nc])) for o in out]

@@ -178,4 +178,40 @@ int vdref_swg_score(const char *query, int query_len, const char *truth, int tru
     return s;
 }
 
+/* the reference's wf_swg_cluster (src/cluster.cpp:954-1263) on one haplotype of one contig: variants
+ * (sorted, 0-based positions, REF/ALT texts) in, cluster boundaries and reaches out.  `clusters` has
+ * room for n+1 entries (variant index of each cluster start + the sentinel n); returns their number. */
+int vdref_cluster(const char *fasta, int fasta_len, int n, const int *pos, const int *rlen, const uint8_t *type,
+                  const int64_t *alt_off, const char *alt_seq, int sub, int open, int extend,
+                  int max_iters, int reach_min_gap, int *clusters, int *left_reach, int *right_reach) {
+    g.max_cluster_itrs = max_iters;
+    g.reach_min_gap = reach_min_gap;
+    FILE *devnull = fopen("/dev/null", "r");
+    std::shared_ptr<fastaData> ref(new fastaData(devnull));
+    const std::string ctg = "vdref";
+    ref->fasta[ctg] = std::string(fasta, (size_t)fasta_len);
+    ref->lengths[ctg] = fasta_len;
+    variantData vd;
+    vd.ref = ref;
+    vd.contigs.push_back(ctg);
+    vd.lengths.push_back(fasta_len);
+    vd.ploidy.push_back(2);
+    vd.variants.resize(HAPS);
+    std::shared_ptr<ctgVariants> cv(new ctgVariants());
+    for (int h = 0; h < HAPS; h++) vd.variants[h][ctg] = (h == 0) ? cv : std::shared_ptr<ctgVariants>(new ctgVariants());
+    for (int v = 0; v < n; v++) {
+        std::string refa(fasta + pos[v], (size_t)rlen[v]);
+        std::string alta(alt_seq + alt_off[v], (size_t)(alt_off[v + 1] - alt_off[v]));
+        cv->add_var(pos[v], rlen[v], 0, type[v], BED_INSIDE, refa, alta, GT_ALT1_REF, 0, 30, 0);
+    }
+    wf_swg_cluster(&vd, 0, 0, sub, open, extend);
+    const int nc = (int)cv->clusters.size();
+    for (int i = 0; i < nc; i++) {
+        clusters[i] = cv->clusters[i];
+        left_reach[i] = i < (int)cv->left_reaches.size() ? cv->left_reaches[i] : 0;
+        right_reach[i] = i < (int)cv->right_reaches.size() ? cv->right_reaches[i] : 0;
+    }
+    return nc;
+}
+
 }  /* extern "C" */

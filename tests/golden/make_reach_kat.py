@@ -10,7 +10,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from oracle import checkers  # noqa: E402
-from test_reach_oracle import random_case  # noqa: E402
+import json  # noqa: E402
+
+from test_reach_oracle import random_case, random_cluster_case  # noqa: E402
 
 rng = np.random.default_rng(20261017)
 qs, ts, q_off, t_off, params, answer = [], [], [0], [0], [], []
@@ -31,3 +33,15 @@ np.savez_compressed(os.path.join(ROOT, "tests", "golden", "reach_kat.npz"), quer
                     answer=np.array(answer, np.int32), swg_params=np.array(swg_params, np.int32),
                     swg_answer=np.array(swg_answer, np.int32))
 print("wrote", len(answer), "cases; distinct answers:", len(set(answer)))
+
+# known answers of the reference's wf_swg_cluster (src/cluster.cpp:954-1263)
+rng = np.random.default_rng(20261018)
+kat = []
+while len(kat) < 200:
+    fasta, var, x, o, e = random_cluster_case(rng)
+    if not var:
+        continue
+    kat.append({"fasta": fasta.decode(), "var": [[v[0], v[1], v[2], v[3].decode()] for v in var], "penalties": [x, o, e],
+                "answer": checkers.cluster_reference(fasta, var, x, o, e)})
+json.dump(kat, open(os.path.join(ROOT, "tests", "golden", "cluster_kat.json"), "w"))
+print("wrote", len(kat), "clustering cases")

@@ -7,8 +7,10 @@ import os
 import numpy as np
 import pytest
 
+import json
+
 from conftest import ROOT
-from oracle import checkers
+from oracle import checkers, vd_cluster
 
 KAT = os.path.join(ROOT, "tests", "golden", "reach_kat.npz")
 
@@ -107,3 +109,55 @@ def test_affine_score_known_answers():
             t = z["truth"][z["t_off"][i]: z["t_off"][i + 1]].tobytes()
             p = [int(v) for v in z["swg_params"][i]]
             assert checkers.swg_score_oracle(q, t, p[0], p[1], p[2]) == int(z["swg_answer"][i]), i
+
+
+CLUSTER_KAT = os.path.join(ROOT, "tests", "golden", "cluster_kat.json")
+
+
+def random_cluster_case(rng):
+    """One haplotype of one contig: random reference with short tandem repeats (so that reaches wander),
+    sorted non-overlapping SUB / INS / DEL variants away from the contig ends, random penalties."""
+    A = b"ACGT"[: int(rng.integers(2, 5))]
+    L = int(rng.integers(60, 400))
+    unit = bytes(rng.choice(list(A), int(rng.integers(1, 4))).tolist())
+    fasta = bytearray(rng.choice(list(A), L).tolist())
+    for _ in range(int(rng.integers(0, 4))):
+        p = int(rng.integers(0, L - 20)); k = int(rng.integers(5, 20))
+        fasta[p: p + k] = (unit * k)[:k]
+    fasta = bytes(fasta)
+    var, pos = [], int(rng.integers(3, 15))
+    while pos < L - 12:
+        r = rng.random()
+        if r < 0.4:
+            var.append((pos, 1, vd_cluster.TYPE_SUB, bytes([A[(A.index(fasta[pos]) + 1) % len(A)]]))); pos += 1
+        elif r < 0.7:
+            var.append((pos, 0, vd_cluster.TYPE_INS, bytes(rng.choice(list(A), int(rng.integers(1, 6))).tolist()))); pos += 1
+        else:
+            n = int(rng.integers(1, 6)); var.append((pos, n, vd_cluster.TYPE_DEL, b"")); pos += n
+        pos += int(rng.integers(1, 40))
+    return fasta, var, int(rng.integers(1, 6)), int(rng.integers(0, 7)), int(rng.integers(1, 4))
+
+
+@pytest.mark.skipif(not checkers.reference_available(False), reason="reference objects not built (no /root/reference)")
+def test_cluster_growth_matches_reference_object_code():
+    """wf_swg_cluster (src/cluster.cpp:954-1263): cluster boundaries and reaches."""
+    rng = np.random.default_rng()
+    merged = 0
+    for _ in range(600):
+        fasta, var, x, o, e = random_cluster_case(rng)
+        if not var:
+            continue
+        got = vd_cluster.wf_swg_cluster(fasta, var, x, o, e)
+        want = checkers.cluster_reference(fasta, var, x, o, e)
+        assert [list(v) for v in got] == want, (fasta, var, x, o, e)
+        merged += len(got[0]) - 1 < len(var)
+    assert merged > 100
+
+
+def test_cluster_growth_known_answers():
+    kat = json.load(open(CLUSTER_KAT))
+    assert len(kat) >= 150
+    for c in kat:
+        var = [(v[0], v[1], v[2], v[3].encode()) for v in c["var"]]
+        got = vd_cluster.wf_swg_cluster(c["fasta"].encode(), var, *c["penalties"])
+        assert [list(v) for v in got] == c["answer"]
