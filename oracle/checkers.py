@@ -165,3 +165,26 @@ def cluster_reference(fasta: bytes, var, sub: int, open_: int, extend: int, max_
     nc = lib.vdref_cluster(fasta, len(fasta), n, pos.ctypes.data, rlen.ctypes.data, typ.ctypes.data, alt_off.ctypes.data, alt,
                            sub, open_, extend, max_iters, reach_min_gap, out[0].ctypes.data, out[1].ctypes.data, out[2].ctypes.data)
     return [list(map(int, o[:nc])) for o in out]
+
+
+def swg_cigar_oracle(query: bytes, truth: bytes, sub: int, open_: int, extend: int):
+    """Affine-gap alignment + walk back, C restatement (oracle/vd_reach.c: vdo_swg_cigar) -> (score, cigar)."""
+    lib = load_oracle()
+    lib.vdo_swg_cigar.argtypes = _SWG_ARGS + [C.c_void_p]
+    lib.vdo_swg_cigar.restype = C.c_int
+    cig = np.zeros(len(query) + len(truth), np.int32)
+    s = lib.vdo_swg_cigar(query, len(query), truth, len(truth), sub, open_, extend, cig.ctypes.data)
+    return s, cig
+
+
+def swg_cigar_reference(query: bytes, truth: bytes, sub: int, open_: int, extend: int):
+    """The reference's wf_swg_align + wf_swg_backtrack (oracle/ref_harness.cpp: vdref_swg_cigar)."""
+    key = "reach:libvdref.so"
+    if key not in _ref_libs:
+        _ref_libs[key] = C.CDLL(os.path.join(ORACLE_DIR, "libvdref.so"))
+    lib = _ref_libs[key]
+    lib.vdref_swg_cigar.argtypes = _SWG_ARGS + [C.c_void_p]
+    lib.vdref_swg_cigar.restype = C.c_int
+    cig = np.zeros(len(query) + len(truth), np.int32)
+    s = lib.vdref_swg_cigar(query, len(query), truth, len(truth), sub, open_, extend, cig.ctypes.data)
+    return s, cig

@@ -214,4 +214,18 @@ int vdref_cluster(const char *fasta, int fasta_len, int n, const int *pos, const
     return nc;
 }
 
+/* the reference's wf_swg_align + wf_swg_backtrack (src/dist.cpp:1510-1652, :2625-2757): score and CIGAR
+ * (|query|+|truth| entries) */
+int vdref_swg_cigar(const char *query, int query_len, const char *truth, int truth_len, int sub, int open, int extend,
+                    int *cigar) {
+    const std::string q(query, query + query_len), t(truth, truth + truth_len);
+    std::vector<std::vector<std::vector<uint8_t>>> ptrs(MATS);
+    std::vector<std::vector<std::vector<int>>> offs(MATS);
+    int s = 0;
+    wf_swg_align(q, t, ptrs, offs, s, sub, open, extend, false);
+    const std::vector<int> c = wf_swg_backtrack(q, t, ptrs, offs, s, sub, open, extend, false);
+    for (size_t i = 0; i < c.size(); i++) cigar[i] = c[i];
+    return s;
+}
+
 }  /* extern "C" */

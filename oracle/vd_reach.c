@@ -211,3 +211,126 @@ int vdo_swg_score(const char *query, int qlen, const char *truth, int tlen, int 
         }
     }
 }
+
+
+/* Restatement of the reference's wf_swg_align WITH its predecessor flags and of wf_swg_backtrack
+ * (/root/reference/src/dist.cpp:1510-1652, :2625-2757): the affine-gap alignment the optional
+ * `--distance` pass runs per supercluster and haplotype (edits_wrapper, :1908-2077).
+ * Every score keeps its three wavefronts and one flag byte per diagonal: how the cell was entered
+ * (F_INS / F_DEL: by leaving or extending that gap, F_SUB: by a substitution or by opening a gap,
+ * F_MAT: the origin).  The walk back from the last cell prefers, on the M wavefront, leaving an
+ * insertion over leaving a deletion over a substitution (:2662-2700) and, inside a gap, extending over
+ * opening (:2716-2745).  cigar[] has |query|+|truth| entries, filled from the back as the reference
+ * does: two entries per match / substitution, one per inserted / deleted base, zeros in front.
+ * Returns the score.                                                                                */
+enum { F_INS = 1, F_DEL = 2, F_MAT = 4, F_SUB = 8 };
+
+typedef struct { int *off[NW]; unsigned char *flag[NW]; } wave_t;
+
+int vdo_swg_cigar(const char *query, int qlen, const char *truth, int tlen, int x, int o, int e, int *cigar) {
+    const int nd = qlen + tlen - 1;
+    int cap = 16, score = 0;
+    wave_t *W = (wave_t *)malloc(sizeof(wave_t) * cap);
+#define NEW_WAVE(sidx) do { for (int k_ = 0; k_ < NW; k_++) { \
+        W[sidx].off[k_] = (int *)malloc(sizeof(int) * nd); W[sidx].flag[k_] = (unsigned char *)calloc(nd, 1); \
+        for (int d_ = 0; d_ < nd; d_++) W[sidx].off[k_][d_] = NONE; } } while (0)
+    NEW_WAVE(0);
+    W[0].off[WM][qlen - 1] = -1;                                        /* :1528-1529 */
+    W[0].flag[WM][qlen - 1] = F_MAT;
+    for (;;) {
+        wave_t *c = &W[score];
+        for (int kind = WI; kind <= WD; kind++)                           /* :1533-1547 */
+            for (int d = 0; d < nd; d++) {
+                const int q = c->off[kind][d], k = d + 1 - qlen;
+                if (q >= 0 && q < qlen && k + q >= 0 && k + q < tlen && q >= c->off[WM][d]) {
+                    c->off[WM][d] = q;
+                    c->flag[WM][d] |= (kind == WI) ? F_INS : F_DEL;
+                }
+            }
+        int done = 0;
+        for (int d = 0; d < nd && !done; d++) {                           /* :1550-1568 */
+            int q = c->off[WM][d];
+            const int k = d + 1 - qlen;
+            while (q != NONE && k + q >= -1 && q < qlen - 1 && k + q < tlen - 1 && query[q + 1] == truth[k + q + 1]) q++;
+            c->off[WM][d] = q;
+            if (q == qlen - 1 && q + k == tlen - 1) done = 1;
+        }
+        if (done) break;
+        score++;
+        if (score == cap) { cap *= 2; W = (wave_t *)realloc(W, sizeof(wave_t) * cap); }
+        NEW_WAVE(score);
+        c = &W[score];
+        for (int d = 0; d < nd; d++) {
+            const int k = d + 1 - qlen;
+            if (score - x >= 0) {                                         /* :1592-1600 */
+                const int p = W[score - x].off[WM][d];
+                if (p != NONE && p + 1 < qlen && k + p + 1 < tlen && p + 1 >= c->off[WM][d]) { c->off[WM][d] = p + 1; c->flag[WM][d] |= F_SUB; }
+            }
+            if (score - (o + e) >= 0) {                                   /* :1602-1625 */
+                const wave_t *pw = &W[score - (o + e)];
+                if (d > 0) {
+                    const int p = pw->off[WM][d - 1];
+                    if (p != NONE && k + p < tlen && p >= c->off[WD][d]) { c->off[WD][d] = p; c->flag[WD][d] |= F_SUB; }
+                }
+                if (d < nd - 1) {
+                    const int p = pw->off[WM][d + 1];
+                    if (p != NONE && p + 1 < qlen && k + p + 1 < tlen && k + p + 1 >= 0 && p + 1 >= c->off[WI][d]) { c->off[WI][d] = p + 1; c->flag[WI][d] |= F_SUB; }
+                }
+            }
+            if (score - e >= 0) {                                         /* :1627-1650 */
+                const wave_t *pw = &W[score - e];
+                if (d > 0) {
+                    const int p = pw->off[WD][d - 1];
+                    if (p != NONE && k + p < tlen && p >= c->off[WD][d]) { c->off[WD][d] = p; c->flag[WD][d] |= F_DEL; }
+                }
+                if (d < nd - 1) {
+                    const int p = pw->off[WI][d + 1];
+                    if (p != NONE && p + 1 < qlen && k + p + 1 < tlen && k + p + 1 >= 0 && p + 1 >= c->off[WI][d]) { c->off[WI][d] = p + 1; c->flag[WI][d] |= F_INS; }
+                }
+            }
+        }
+    }
+    /* ---- walk back (:2648-2755) ---- */
+    const int final_score = score;
+    for (int i = 0; i < qlen + tlen; i++) cigar[i] = 0;
+    int cp = qlen + tlen - 1, kind = WM, qi = qlen - 1, ti = tlen - 1, s = score, failed = 0;
+    while ((qi >= 0 || ti >= 0) && !failed) {
+        if (s < 0) { failed = 1; break; }
+        const int d = qlen - 1 + (ti - qi);
+        if (kind == WM) {
+            const int f = W[s].flag[WM][d];
+            if (f & (F_INS | F_DEL)) {                                    /* a gap was left here for free */
+                const int g = (f & F_INS) ? WI : WD;
+                const int stop = W[s].off[g][d];
+                while (qi > stop) { cigar[cp--] = F_MAT; cigar[cp--] = F_MAT; qi--; ti--; if (qi < 0 || ti < 0) { failed = 1; break; } }
+                kind = g;
+            } else if (f & F_SUB) {
+                if (s - x < 0) { failed = 1; break; }
+                const int stop = W[s - x].off[WM][d] + 1;
+                while (qi > stop) { cigar[cp--] = F_MAT; cigar[cp--] = F_MAT; qi--; ti--; if (qi < 0 || ti < 0) { failed = 1; break; } }
+                if (failed) break;
+                cigar[cp--] = F_SUB; cigar[cp--] = F_SUB; qi--; ti--;
+                s -= x;
+            } else if (f & F_MAT) {
+                while (qi >= 0 && ti >= 0) { cigar[cp--] = F_MAT; cigar[cp--] = F_MAT; qi--; ti--; }
+                if (qi >= 0 || ti >= 0) failed = 1;
+            } else failed = 1;
+        } else if (kind == WI) {
+            const int f = W[s].flag[WI][d];
+            if (f & F_INS) { cigar[cp--] = F_INS; qi--; s -= e; }
+            else if (f & F_SUB) { cigar[cp--] = F_INS; qi--; kind = WM; s -= o + e; }
+            else failed = 1;
+        } else {
+            const int f = W[s].flag[WD][d];
+            if (f & F_DEL) { cigar[cp--] = F_DEL; ti--; s -= e; }
+            else if (f & F_SUB) { cigar[cp--] = F_DEL; ti--; kind = WM; s -= o + e; }
+            else failed = 1;
+        }
+        if (!(qi == -1 && ti == -1) && (qi < 0 || ti < 0)) failed = 1;
+    }
+    for (int i = 0; i <= final_score; i++)
+        for (int k_ = 0; k_ < NW; k_++) { free(W[i].off[k_]); free(W[i].flag[k_]); }
+    free(W);
+#undef NEW_WAVE
+    return failed ? -1 : final_score;                                    /* -1: the reference would ERROR() and exit */
+}

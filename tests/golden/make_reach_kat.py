@@ -28,10 +28,17 @@ for i in range(len(answer)):
     x, o, e = int(rng.integers(1, 7)), int(rng.integers(0, 8)), int(rng.integers(1, 4))
     swg_params.append([x, o, e])
     swg_answer.append(checkers.swg_score_reference(qs[i].tobytes(), ts[i].tobytes(), x, o, e))
+# score + CIGAR (wf_swg_align + wf_swg_backtrack) of the first 600 pairs
+cig_score, cigs, cig_off = [], [], [0]
+for i in range(600):
+    x, o, e = swg_params[i]
+    s_, c_ = checkers.swg_cigar_reference(qs[i].tobytes(), ts[i].tobytes(), x, o, e)
+    cig_score.append(s_); cigs.append(c_); cig_off.append(cig_off[-1] + len(c_))
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "reach_kat.npz"), query=np.concatenate(qs), truth=np.concatenate(ts),
                     q_off=np.array(q_off, np.int64), t_off=np.array(t_off, np.int64), params=np.array(params, np.int32),
                     answer=np.array(answer, np.int32), swg_params=np.array(swg_params, np.int32),
-                    swg_answer=np.array(swg_answer, np.int32))
+                    swg_answer=np.array(swg_answer, np.int32), cig_score=np.array(cig_score, np.int32),
+                    cigar=np.concatenate(cigs).astype(np.int8), cig_off=np.array(cig_off, np.int64))
 print("wrote", len(answer), "cases; distinct answers:", len(set(answer)))
 
 # known answers of the reference's wf_swg_cluster (src/cluster.cpp:954-1263)

@@ -161,3 +161,35 @@ def test_cluster_growth_known_answers():
         var = [(v[0], v[1], v[2], v[3].encode()) for v in c["var"]]
         got = vd_cluster.wf_swg_cluster(c["fasta"].encode(), var, *c["penalties"])
         assert [list(v) for v in got] == c["answer"]
+
+
+@pytest.mark.skipif(not checkers.reference_available(False), reason="reference objects not built (no /root/reference)")
+def test_affine_alignment_cigar_matches_reference_object_code():
+    """wf_swg_align + wf_swg_backtrack (src/dist.cpp:1510-1652, :2625-2757), the `--distance` kernel pair
+    (SURVEY 8f-2): score and CIGAR.  The reference is only called where the restatement walks back cleanly
+    (its own failure mode is ERROR() + exit, which would take the test process with it)."""
+    rng = np.random.default_rng()
+    n = 0
+    for _ in range(3000):
+        case = random_pair(rng)
+        so, co = checkers.swg_cigar_oracle(*case)
+        assert so == checkers.swg_score_oracle(*case)
+        if so < 0:
+            continue
+        sr, cr = checkers.swg_cigar_reference(*case)
+        assert so == sr and (co == cr).all(), case
+        n += 1
+    assert n > 2900
+
+
+def test_affine_alignment_cigar_known_answers():
+    z = np.load(KAT, allow_pickle=False)
+    m = len(z["cig_score"])
+    assert m >= 500
+    for i in range(m):
+        q = z["query"][z["q_off"][i]: z["q_off"][i + 1]].tobytes()
+        t = z["truth"][z["t_off"][i]: z["t_off"][i + 1]].tobytes()
+        p = [int(v) for v in z["swg_params"][i]]
+        s, cig = checkers.swg_cigar_oracle(q, t, p[0], p[1], p[2])
+        assert s == int(z["cig_score"][i]) == int(z["swg_answer"][i])
+        assert (cig == z["cigar"][z["cig_off"][i]: z["cig_off"][i + 1]]).all(), i
