@@ -34,7 +34,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-from vcfdist_b200 import capi, shard, synth  # noqa: E402
+from vcfdist_b200 import capi, shard
+from workloads import synth  # noqa: E402
 from oracle import checkers  # noqa: E402  (CPU-baseline legs only: the reference arm and cpu_baseline)
 from vcfdist_b200.batch import Batch, Out, vd_batch_in, vd_batch_out  # noqa: E402
 

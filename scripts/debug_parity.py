@@ -3,7 +3,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 from conftest import load_golden, OUT_KEYS
 from oracle import checkers
-from vcfdist_b200 import capi, synth
+from vcfdist_b200 import capi
+from workloads import synth
 name = sys.argv[1] if len(sys.argv) > 1 else "adv_11"
 b, _, _ = load_golden(name)
 for fc in (os.environ.get("DBG_CLASSES", "1").split(",")):

@@ -2,7 +2,8 @@ import sys, os, time, numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 from conftest import load_golden
-from vcfdist_b200 import capi, synth
+from vcfdist_b200 import capi
+from workloads import synth
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 400000
 demo, _, _ = load_golden("demo")
 t=time.time(); b = synth.bootstrap(1, demo, n); print("bootstrap", time.time()-t, "s; n_sc", b.n_sc, "cells", int(b.cells().sum()))

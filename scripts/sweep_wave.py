@@ -1,6 +1,7 @@
 import sys, os, time, numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from vcfdist_b200 import capi, synth
+from vcfdist_b200 import capi
+from workloads import synth
 e = capi.Engine(0)
 for L, n in ((60, 20000), (250, 4000), (1000, 600), (3000, 150), (7000, 150), (12000, 148)):
     b = synth.sv_pairs(1, n, L, divergence=0.01)

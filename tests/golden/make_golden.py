@@ -5,7 +5,7 @@ where /root/reference exists and `make -C oracle` has built oracle/_ref/).
                   GRCh38_chr1_5Mb.fa, BED) taken through the reference's own parser, clustering
                   and superclustering by oracle/_ref/vcfdist_dump: the packed hot-path input of
                   all 6037 superclusters and the unmodified reference's results for it
-  adv_*.npz       seeded adversarial batches (vcfdist_b200.synth.adversarial) with the results
+  adv_*.npz       seeded adversarial batches (workloads.synth.adversarial) with the results
                   of the unmodified reference (refA_*) and of the canonical-tie-break reference
                   (refB_*), both run through oracle/_ref/libvdref[B].so
   sv_*.npz        a few superclusters with long insertions/deletions (long-kernel shapes)
@@ -19,7 +19,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
-from vcfdist_b200 import capi, synth  # noqa: E402
+from vcfdist_b200 import capi
+from workloads import synth  # noqa: E402
 from oracle import checkers  # noqa: E402
 from vcfdist_b200.batch import Batch  # noqa: E402
 
@@ -72,7 +73,22 @@ def main():
     rA, _ = checkers.reference_run(b, canonical=False, threads=8)
     rB, _ = checkers.reference_run(b, canonical=True, threads=8)
     save("sv_21.npz", b, refA=rA, refB=rB)
+    make_sv_10k()
+
+
+def make_sv_10k():
+    """10 kb structural variants (BASELINE configs[3]) through the reference's own object code."""
+    cases = [("ins", "het", 0.01), ("ins", "mixed", 0.0), ("del", "hom", 0.01), ("ins_truth_only", "het", 0.0),
+             ("ins_query_only", "cross", 0.0), ("del_truth_only", "het", 0.0), ("del_query_only", "het", 0.0)]
+    b = Batch.concat([synth.sv_case(500 + i, 10000, k, z, d) for i, (k, z, d) in enumerate(cases)])
+    rA, sa = checkers.reference_run(b, canonical=False, threads=8)
+    rB, sb = checkers.reference_run(b, canonical=True, threads=8)
+    print("reference seconds", sa, sb)
+    save("sv_10k.npz", b, refA=rA, refB=rB)
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "sv_10k":
+        make_sv_10k()
+    else:
+        main()

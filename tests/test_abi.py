@@ -78,6 +78,6 @@ def test_product_package_never_touches_the_oracle():
                 assert not any(n.split(".")[0] == "oracle" for n in names), (fn, names)
             if isinstance(node, ast.Constant) and isinstance(node.value, str) and node.value is not ast.get_docstring(tree, clean=False):
                 assert "liboracle" not in node.value and "libvdref" not in node.value, (fn, node.value[:60])
-    code = "import sys; import vcfdist_b200, vcfdist_b200.capi, vcfdist_b200.shard, vcfdist_b200.synth; " \
+    code = "import sys; import vcfdist_b200, vcfdist_b200.capi, vcfdist_b200.shard, vcfdist_b200.batch; " \
            "sys.exit(1 if any(m.startswith('oracle') for m in sys.modules) else 0)"
     assert subprocess.run([sys.executable, "-c", code], cwd=ROOT).returncode == 0

@@ -9,7 +9,7 @@ import subprocess
 import pytest
 
 from conftest import ROOT
-from vcfdist_b200 import vcfgen
+from workloads import vcfgen
 
 REF = os.path.join(ROOT, "oracle", "_ref", "vcfdist_ref")
 REFB = os.path.join(ROOT, "oracle", "_ref", "vcfdist_refB")

@@ -7,7 +7,8 @@ import numpy as np
 import pytest
 
 from conftest import FINAL_KEYS, OUT_KEYS, load_golden, mismatches, non_tie_var_mask
-from vcfdist_b200 import capi, synth
+from vcfdist_b200 import capi
+from workloads import synth
 from oracle import checkers
 from vcfdist_b200.batch import Batch, BatchBuilder, TYPE_DEL, TYPE_INS, TYPE_SUB
 

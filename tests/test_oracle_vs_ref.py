@@ -5,7 +5,8 @@ import numpy as np
 import pytest
 
 from conftest import FINAL_KEYS, mismatches, non_tie_var_mask
-from vcfdist_b200 import capi, synth
+from vcfdist_b200 import capi
+from workloads import synth
 from oracle import checkers
 
 pytestmark = pytest.mark.skipif(not (checkers.reference_available(False) and checkers.reference_available(True)),

@@ -11,7 +11,8 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from conftest import OUT_KEYS, ROOT, mismatches
-from vcfdist_b200 import capi, shard, synth
+from vcfdist_b200 import capi, shard
+from workloads import synth
 from oracle import checkers
 
 

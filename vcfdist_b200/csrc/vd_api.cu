@@ -13,8 +13,10 @@
 #include <string>
 #include <vector>
 
+#ifndef VD_EMU
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#endif
 
 #include "vd_kernels.cuh"
 #include "vd_wave.cuh"
@@ -243,9 +245,9 @@ static int chunk_plan(vd_handle *h, Work &W, cudaStream_t sp, const BatchDev &in
     CK(cudaMemsetAsync(W.counters.p, 0, sizeof(PlanCounters), sp));
     PlanCounters *dcnt = (PlanCounters *)W.counters.p;
     int *order = (int *)W.order.p;                   // class- and cost-sorted short superclusters
-    plan_kernel<<<(n_sc + 255) / 256, 256, 0, sp>>>(in, (ScPlan *)W.plan.p, (int *)W.list.p, (u8 *)W.ranks.p, (int *)W.iota.p, dcnt,
+    VD_LAUNCH(plan_kernel, (n_sc + 255) / 256, 256, 0, sp, in, (ScPlan *)W.plan.p, (int *)W.list.p, (u8 *)W.ranks.p, (int *)W.iota.p, dcnt,
                                                     h->force_class, kBigClass, h->small_lo, h->small_hi, h->use_wsc, h->use_hom);
-    small_base_kernel<<<1, 32, 0, sp>>>(dcnt);
+    VD_LAUNCH(small_base_kernel, 1, 32, 0, sp, dcnt);
     {   // order[] = supercluster indices stably sorted by rank (non-short superclusters sort to the end)
         size_t tmp = 0;
         cub::DeviceRadixSort::SortPairs(nullptr, tmp, (const u8 *)W.ranks.p, (u8 *)W.ranks_out.p, (const int *)W.iota.p, order,
@@ -255,7 +257,7 @@ static int chunk_plan(vd_handle *h, Work &W, cudaStream_t sp, const BatchDev &in
                                         n_sc, 0, 8, sp);
     }
     h->stats.n_launches += 6;
-    publish_kernel<<<1, 64, 0, sp>>>((const u32 *)dcnt, (u32 *)W.h_counters, (int)(sizeof(PlanCounters) / 4));
+    VD_LAUNCH(publish_kernel, 1, 64, 0, sp, (const u32 *)dcnt, (u32 *)W.h_counters, (int)(sizeof(PlanCounters) / 4));
     CK(cudaEventRecord(W.ev[1], sp));
     return VD_OK;
 }
@@ -317,7 +319,7 @@ static int chunk_exec(vd_handle *h, Work &W) {
         CK(h->offs.ensure(8 * (size_t)(n + 1)));
         int64_t *bytes = (int64_t *)h->bytes.p, *offs = (int64_t *)h->offs.p;
         CK(cudaMemsetAsync(bytes + n, 0, 8, st));
-        wave_size_kernel<<<(n + 255) / 256, 256, 0, st>>>(plan, list, n, bytes);
+        VD_LAUNCH(wave_size_kernel, (n + 255) / 256, 256, 0, st, plan, list, n, bytes);
         S.n_launches++;
         size_t tmp = 0;
         cub::DeviceScan::ExclusiveSum(nullptr, tmp, bytes, offs, n + 1, st);
@@ -338,29 +340,29 @@ static int chunk_exec(vd_handle *h, Work &W) {
             CK(h->slab.ensure((size_t)need));
             const int m = i1 - i0;
             CK(h->hap_ok.ensure(16 * (size_t)m));
-            slab_setup_kernel<<<(4 * m + 127) / 128, 128, 0, st>>>(in, plan, list, i0, i1, offs, (u8 *)h->slab.p,
+            VD_LAUNCH(slab_setup_kernel, (4 * m + 127) / 128, 128, 0, st, in, plan, list, i0, i1, offs, (u8 *)h->slab.p,
                                                                    (int *)h->hap_ok.p);
             S.n_launches++;
-            slab_align_kernel<<<(4 * m + 63) / 64, 64, 0, st>>>(in, out, plan, list, i0, i1, offs, (u8 *)h->slab.p,
+            VD_LAUNCH(slab_align_kernel, (4 * m + 63) / 64, 64, 0, st, in, out, plan, list, i0, i1, offs, (u8 *)h->slab.p,
                                                                 (const int *)h->hap_ok.p, CLS_SCALAR);
             S.n_launches++;
             // ---- wavefront kernels: class-sorted items, then forward / backward / walk ----
-            wave_tables_kernel<<<(4 * m + 127) / 128, 128, 0, st>>>(plan, list, i0, i1, offs, (u8 *)h->slab.p,
+            VD_LAUNCH(wave_tables_kernel, (4 * m + 127) / 128, 128, 0, st, plan, list, i0, i1, offs, (u8 *)h->slab.p,
                                                                     (const int *)h->hap_ok.p);
             CK(h->wave_desc.ensure(sizeof(WaveItems) + 4 * (size_t)(4 * m + 4)));
             WaveItems *wi = (WaveItems *)h->wave_desc.p;
             int *items = (int *)((u8 *)h->wave_desc.p + sizeof(WaveItems));
             CK(cudaMemsetAsync(wi, 0, sizeof(WaveItems), st));
-            wave_count_kernel<<<(4 * m + 127) / 128, 128, 0, st>>>(plan, list, i0, i1, (const int *)h->hap_ok.p, wi);
+            VD_LAUNCH(wave_count_kernel, (4 * m + 127) / 128, 128, 0, st, plan, list, i0, i1, (const int *)h->hap_ok.p, wi);
             S.n_launches += 2;
-            publish_kernel<<<1, 64, 0, st>>>((const u32 *)wi, (u32 *)h->h_witems, (int)(sizeof(WaveItems) / 4));
+            VD_LAUNCH(publish_kernel, 1, 64, 0, st, (const u32 *)wi, (u32 *)h->h_witems, (int)(sizeof(WaveItems) / 4));
             CK(cudaStreamSynchronize(st));
             const WaveItems hwi = *h->h_witems;
             ClsBase cb;
             int total_items = 0;
             for (int c = 0; c < N_WCLS; c++) { cb.b[c] = total_items; total_items += hwi.count[c]; }
             if (total_items > 0 || hwi.n_toolarge > 0) {
-                wave_fill_kernel<<<(4 * m + 127) / 128, 128, 0, st>>>(plan, list, i0, i1, (const int *)h->hap_ok.p,
+                VD_LAUNCH(wave_fill_kernel, (4 * m + 127) / 128, 128, 0, st, plan, list, i0, i1, (const int *)h->hap_ok.p,
                                                                       wi, cb, items, out);
                 S.n_launches++;
             }
@@ -381,7 +383,7 @@ static int chunk_exec(vd_handle *h, Work &W) {
                                 h->banded_fwd ? (int *)h->need_dense.p : nullptr, h->banded_bwd);
                     CK(cudaEventRecord(h->sev[c][2], ss));
                     // walk + credit of this class right behind its backward sweep, on the same stream
-                    wave_walk_kernel<<<(hwi.count[c] + 3) / 4, 128, 0, ss>>>(WA, cb.b[c], hwi.count[c]);
+                    VD_LAUNCH(wave_walk_kernel, (hwi.count[c] + 3) / 4, 128, 0, ss, WA, cb.b[c], hwi.count[c]);
                     CK(cudaEventRecord(h->sev[c][3], ss));
                     if (ss != st) CK(cudaStreamWaitEvent(st, h->sev[c][3], 0));
                     S.n_launches += 3;
@@ -428,9 +430,9 @@ static int chunk_exec(vd_handle *h, Work &W) {
         CK(cudaStreamWaitEvent(se, W.evL, 0));
         for (int g = 2 * N_SMALL; g < N_GROUP; g++) if (W.grp_used[g]) CK(cudaStreamWaitEvent(se, W.gev[g][1], 0));
     }
-    status_or_kernel<<<296, 256, 0, se>>>(out.status, 4 * (int64_t)n_sc, &((PlanCounters *)W.counters.p)->status_or);
+    VD_LAUNCH(status_or_kernel, 296, 256, 0, se, out.status, 4 * (int64_t)n_sc, &((PlanCounters *)W.counters.p)->status_or);
     S.n_launches++;
-    publish_kernel<<<1, 64, 0, se>>>((const u32 *)W.counters.p, (u32 *)W.h_counters, (int)(sizeof(PlanCounters) / 4));
+    VD_LAUNCH(publish_kernel, 1, 64, 0, se, (const u32 *)W.counters.p, (u32 *)W.h_counters, (int)(sizeof(PlanCounters) / 4));
     CK(cudaEventRecord(W.ev[3], se));
     W.ms_fwd = ms_fwd; W.ms_bwd = ms_bwd; W.ms_walk = ms_walk;
     return VD_OK;

@@ -1,7 +1,14 @@
 // Shared definitions of the sm_100a precision/recall kernels.
 #pragma once
 #include <cstdint>
+#ifdef VD_EMU
+// kernel-logic debugging on the CPU: tests/simt/simt_emu.h (force-included by tests/simt/Makefile)
+// provides the CUDA subset these sources use; never part of the product build
+#else
 #include <cuda_runtime.h>
+#define VD_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define VD_DYN_SHARED(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
 
 #include "vcfdist_b200.h"
 

@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(SmallCfg<K>::TPB, SmallCfg<K>::MINB)
 small_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, const int *__restrict__ order, int count) {
     typedef SmallCfg<K> C;
     typedef SmallDims<C::TL, C::TR> D;
-    extern __shared__ __align__(16) u8 smem[];
+    VD_DYN_SHARED(smem);
     constexpr int SPB = C::TPB / 4;
     const int tid = threadIdx.x, quad = tid >> 2, h = tid & 3;
     const int slot = blockIdx.x * SPB + quad;
@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(SmallCfg<K>::TPB)
 small_hom_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, const int *__restrict__ order, int count) {
     typedef SmallCfg<K> C;
     typedef SmallHomDims<C::TL, C::TR> D;
-    extern __shared__ __align__(16) u8 smem[];
+    VD_DYN_SHARED(smem);
     const int tid = threadIdx.x;
     const int slot = blockIdx.x * C::TPB + tid;
     if (slot >= count) return;
@@ -383,8 +383,8 @@ inline void small_configure() { small_configure_one<0>(); small_configure_one<1>
 template <int K> inline void small_launch_one(cudaStream_t st, bool hom, const BatchDev &in, const OutDev &out, const ScPlan *plan,
                                               const int *order, int count) {
     constexpr int TPB = SmallCfg<K>::TPB, SPB = TPB / 4;
-    if (hom) small_hom_kernel<K><<<(count + TPB - 1) / TPB, TPB, SmallHomMem<K>::SMEM, st>>>(in, out, plan, order, count);
-    else small_kernel<K><<<(count + SPB - 1) / SPB, TPB, SmallMem<K>::SMEM, st>>>(in, out, plan, order, count);
+    if (hom) VD_LAUNCH(small_hom_kernel<K>, (count + TPB - 1) / TPB, TPB, SmallHomMem<K>::SMEM, st, in, out, plan, order, count);
+    else VD_LAUNCH(small_kernel<K>, (count + SPB - 1) / SPB, TPB, SmallMem<K>::SMEM, st, in, out, plan, order, count);
 }
 inline void small_launch(cudaStream_t st, int k, bool hom, const BatchDev &in, const OutDev &out, const ScPlan *plan,
                          const int *order, int count) {

@@ -368,7 +368,7 @@ __device__ __forceinline__ void wsc_sweep(const int lane, const WscAln &X, int &
 template <int S, bool PAR, bool HOM>
 __global__ void __launch_bounds__(WSC_TPB, wsc_minb(S))
 wsc_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, const int *__restrict__ order, int count, int warp_bytes) {
-    extern __shared__ __align__(16) u8 smem[];
+    VD_DYN_SHARED(smem);
     constexpr unsigned FULL = 0xffffffffu;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int slot = PAR ? blockIdx.x : blockIdx.x * (WSC_TPB / 32) + warp;
@@ -512,7 +512,7 @@ struct WscDesc {
 template <int S, bool HOM, int NW>
 __global__ void __launch_bounds__(32 * NW, wsc_minb(S))
 wsc_block_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, const int *__restrict__ order, int count, int warp_bytes) {
-    extern __shared__ __align__(16) u8 smem[];
+    VD_DYN_SHARED(smem);
     __shared__ WscDesc desc[NW];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int slot = blockIdx.x * (NW) + warp;
@@ -668,11 +668,18 @@ template <int S> inline void wsc_launch_one(cudaStream_t st, int bin, bool hom, 
     const int wb = wsc_bin_cap(bin), wpb = WSC_TPB / 32;
     const bool par = bin >= (S >= 2 ? WSC_PAR_MINBIN_S2 : WSC_PAR_MINBIN);
     if (VD_WSC_SHARED && (hom || !par) && WSC_NW * wb <= WSC_SMEM_MAX) {
-        if (hom) wsc_block_kernel<S, true, WSC_NW><<<(count + WSC_NW - 1) / WSC_NW, 32 * WSC_NW, WSC_NW * wb, st>>>(in, out, plan, order, count, wb);
-        else wsc_block_kernel<S, false, WSC_NW><<<(count + WSC_NW - 1) / WSC_NW, 32 * WSC_NW, WSC_NW * wb, st>>>(in, out, plan, order, count, wb);
-    } else if (hom) wsc_kernel<S, false, true><<<(count + wpb - 1) / wpb, WSC_TPB, wpb * wb, st>>>(in, out, plan, order, count, wb);
-    else if (bin >= (S >= 2 ? WSC_PAR_MINBIN_S2 : WSC_PAR_MINBIN)) wsc_kernel<S, true, false><<<count, WSC_TPB, wb, st>>>(in, out, plan, order, count, wb);
-    else wsc_kernel<S, false, false><<<(count + wpb - 1) / wpb, WSC_TPB, wpb * wb, st>>>(in, out, plan, order, count, wb);
+        auto kb = hom ? wsc_block_kernel<S, true, WSC_NW> : wsc_block_kernel<S, false, WSC_NW>;
+        VD_LAUNCH(kb, (count + WSC_NW - 1) / WSC_NW, 32 * WSC_NW, WSC_NW * wb, st, in, out, plan, order, count, wb);
+    } else if (hom) {
+        auto kh = wsc_kernel<S, false, true>;
+        VD_LAUNCH(kh, (count + wpb - 1) / wpb, WSC_TPB, wpb * wb, st, in, out, plan, order, count, wb);
+    } else if (par) {
+        auto kp = wsc_kernel<S, true, false>;
+        VD_LAUNCH(kp, count, WSC_TPB, wb, st, in, out, plan, order, count, wb);
+    } else {
+        auto kw = wsc_kernel<S, false, false>;
+        VD_LAUNCH(kw, (count + wpb - 1) / wpb, WSC_TPB, wpb * wb, st, in, out, plan, order, count, wb);
+    }
 }
 inline void wsc_launch(cudaStream_t st, int slots, int bin, bool hom, const BatchDev &in, const OutDev &out, const ScPlan *plan,
                        const int *order, int count) {

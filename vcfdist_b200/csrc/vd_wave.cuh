@@ -580,7 +580,7 @@ constexpr int FWDB_TAU_MAX = 1280;
 __host__ __device__ inline int fwdb_smem(int npmax) { return 4 * npmax + 32 + 2 * 64 * 4 + 64; }
 
 __global__ void __launch_bounds__(FWDB_TPB) wave_fwdb_kernel(WaveArgs A, int item0, int npmax, int *need_dense) {
-    extern __shared__ __align__(16) u8 smem_raw[];
+    VD_DYN_SHARED(smem_raw);
     const WaveCtx X = wave_ctx(A, A.items[item0 + blockIdx.x]);
     u16 *sD0 = (u16 *)smem_raw, *sD1 = sD0 + npmax;
     int *sLive = (int *)(sD1 + npmax);
@@ -796,7 +796,7 @@ __global__ void __launch_bounds__(FWDB_TPB) wave_fwdb_kernel(WaveArgs A, int ite
 
 template <int TPB, int K>
 __global__ void __launch_bounds__(TPB) wave_fwd_kernel(WaveArgs A, int item0, const int *need_dense) {
-    extern __shared__ __align__(16) u8 smem_raw[];
+    VD_DYN_SHARED(smem_raw);
     __shared__ int sEnd[2];
     if (need_dense && !need_dense[item0 + blockIdx.x]) return;       // solved by the banded sweep
     const WaveCtx X = wave_ctx(A, A.items[item0 + blockIdx.x]);
@@ -1003,7 +1003,10 @@ __device__ __forceinline__ void wave_bwd_body(const WaveCtxT<TT> &X, const int t
         if (row0 < X.NP) store_flags<K>(X.F + (int64_t)c * X.NP + row0, pfw);
         // publish column c for the next iteration
 #pragma unroll
-        for (int j = 0; j < K; j++) { sTc[row0 + j] = (short)Tc[j]; sFc[row0 + j] = (u8)byte_of(Fc, j); Tn[j] = Tc[j]; }
+        for (int j = 0; j < K; j++) {          // sFc[row0] was published above and is being read by the neighbour
+            sTc[row0 + j] = (short)Tc[j]; Tn[j] = Tc[j];
+            if (j > 0) sFc[row0 + j] = (u8)byte_of(Fc, j);
+        }
 #pragma unroll
         for (int i = 0; i < (K + 3) / 4; i++) { Fn[i] = Fc[i]; Fc[i] = Fp[i]; }
         tch_next = X.tinfo[c] & 0x7f;
@@ -1016,7 +1019,7 @@ __device__ __forceinline__ void wave_bwd_body(const WaveCtxT<TT> &X, const int t
 
 template <int TPB, int K>
 __global__ void __launch_bounds__(TPB) wave_bwd_kernel(WaveArgs A, int item0, const int *only_dense) {
-    extern __shared__ __align__(16) u8 smem_raw[];
+    VD_DYN_SHARED(smem_raw);
     if (only_dense && !only_dense[item0 + blockIdx.x]) return;       // solved by the banded sweeps
     const WaveCtx X = wave_ctx(A, A.items[item0 + blockIdx.x]);
     const int end_plane = A.out.aln_end_plane[4 * (int64_t)X.sc + X.ai];
@@ -1081,7 +1084,7 @@ __device__ __forceinline__ SbwdPush sbwd_pushes(const WaveCtx &X, int row, int f
 }
 
 __global__ void __launch_bounds__(32) wave_sbwd_kernel(WaveArgs A, int item0, int npmax, const int *only_dense) {
-    extern __shared__ __align__(16) u8 smem_raw[];
+    VD_DYN_SHARED(smem_raw);
     if (only_dense && !only_dense[item0 + blockIdx.x]) return;       // done by the banded backward sweep
     const int item = A.items[item0 + blockIdx.x];
     const WaveCtx X = wave_ctx(A, item);
@@ -1246,7 +1249,7 @@ constexpr int BWDB_E = VD_BWDB_E;             // rows below the lowest target th
 __host__ __device__ inline int bwdb_smem(int npmax) { return 6 * npmax + 128 * 4; }
 
 __global__ void __launch_bounds__(BWDB_TPB) wave_bwdb_kernel(WaveArgs A, int item0, int npmax, const int *need_dense) {
-    extern __shared__ __align__(16) u8 smem_raw[];
+    VD_DYN_SHARED(smem_raw);
     if (need_dense[item0 + blockIdx.x]) return;              // full-matrix forward sweep: frontier kernel instead
     const WaveCtx X = wave_ctx(A, A.items[item0 + blockIdx.x]);
     short *sT0 = (short *)smem_raw, *sT1 = sT0 + npmax;      // T of column c+1 / c
@@ -1453,8 +1456,12 @@ struct PFWave {
     __device__ __forceinline__ void prefetch(int hi, int qri, int ti) const {
         if (ti + AHEAD < Lt) {
             const u8 *p = F + (int64_t)(ti + AHEAD) * NP + (hi ? padQ + qri : qri);
+#ifndef VD_EMU
             asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
             asm volatile("prefetch.global.L1 [%0];" ::"l"(p + AHEAD));
+#else
+            (void)p;
+#endif
         }
     }
 };
@@ -1512,11 +1519,14 @@ constexpr int FWDB_MIN_CLASS = 4;      // classes with more than 512 rows go thr
 template <int TPB, int K>
 inline void wave_launch_pair(cudaStream_t st, const WaveArgs &A, int item0, int n, bool fwd, int *need_dense = nullptr) {
     if (n <= 0) return;
+    auto kf = wave_fwd_kernel<TPB, K>;
+    auto kb = wave_bwd_kernel<TPB, K>;
+    const int smf = wave_fwd_smem<TPB, K>(), smb = wave_bwd_smem<TPB, K>();
     if (fwd && need_dense) {
-        wave_fwdb_kernel<<<n, FWDB_TPB, fwdb_smem(TPB * K), st>>>(A, item0, TPB * K, need_dense);
-        wave_fwd_kernel<TPB, K><<<n, TPB, wave_fwd_smem<TPB, K>(), st>>>(A, item0, need_dense);
-    } else if (fwd) wave_fwd_kernel<TPB, K><<<n, TPB, wave_fwd_smem<TPB, K>(), st>>>(A, item0, nullptr);
-    else wave_bwd_kernel<TPB, K><<<n, TPB, wave_bwd_smem<TPB, K>(), st>>>(A, item0, need_dense);
+        VD_LAUNCH(wave_fwdb_kernel, n, FWDB_TPB, fwdb_smem(TPB * K), st, A, item0, TPB * K, need_dense);
+        VD_LAUNCH(kf, n, TPB, smf, st, A, item0, (const int *)need_dense);
+    } else if (fwd) VD_LAUNCH(kf, n, TPB, smf, st, A, item0, (const int *)nullptr);
+    else VD_LAUNCH(kb, n, TPB, smb, st, A, item0, (const int *)need_dense);
 }
 // backward of a class that went through the banded forward sweep: the windowed sweep for the alignments
 // it solved; the DENSE sweep for the rest (score above the last bound: a structural variant that only one
@@ -1528,9 +1538,9 @@ inline void wave_launch(cudaStream_t st, const WaveArgs &A, int cls, int item0, 
     if (cls < FWDB_MIN_CLASS) need_dense = nullptr;
     const int npmax = wave_tpb(cls) * wave_k(cls);
     if (!fwd && sparse_bwd && need_dense && banded_bwd)
-        wave_bwdb_kernel<<<n, BWDB_TPB, bwdb_smem(npmax), st>>>(A, item0, npmax, need_dense);   // then the dense kernel below
+        VD_LAUNCH(wave_bwdb_kernel, n, BWDB_TPB, bwdb_smem(npmax), st, A, item0, npmax, (const int *)need_dense);   // then the dense kernel below
     else if (!fwd && sparse_bwd) {
-        wave_sbwd_kernel<<<n, 32, 6 * npmax, st>>>(A, item0, npmax, nullptr);
+        VD_LAUNCH(wave_sbwd_kernel, n, 32, 6 * npmax, st, A, item0, npmax, (const int *)nullptr);
         return;
     }
     if (!fwd && !(sparse_bwd && banded_bwd)) need_dense = nullptr;                               // dense sweep for everything

@@ -16,7 +16,7 @@ from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 
-from .batch import Batch, BatchBuilder, TYPE_DEL, TYPE_INS, TYPE_SUB, Variant
+from vcfdist_b200.batch import Batch, BatchBuilder, TYPE_DEL, TYPE_INS, TYPE_SUB, Variant
 
 _DT = {"q": np.int64, "i": np.int32, "B": np.uint8, "f": np.float32}
 
@@ -222,3 +222,64 @@ def bootstrap(seed: int, base: Batch, n_sc: int) -> Batch:
     """`n_sc` superclusters drawn with replacement from `base` (vectorised)."""
     rng = np.random.default_rng(seed)
     return base.take(rng.integers(0, base.n_sc, n_sc))
+
+
+SV_KINDS = ("ins", "del", "ins_truth_only", "ins_query_only", "del_truth_only", "del_query_only")
+SV_ZYG = ("hom", "het", "cross", "mixed")
+
+
+def sv_case(seed: int, length: int, kind: str = "ins", zyg: str = "hom", divergence: float = 0.0,
+            flank: int = 25, flank_snps: bool = True, max_qual: float = 60.0) -> Batch:
+    """One supercluster around one structural variant of `length` bases (BASELINE configs[3]: SV to 10 kb).
+
+    kind  ins / del            both sides carry it; the query's copy is `divergence`-mutated (INS) or deletes a
+                               span shifted and shortened by length*divergence bases (DEL)
+          *_truth_only / *_query_only   only one side carries it (a false negative / false positive SV)
+    zyg   hom    both haplotypes of a side carry the side's variants (four identical alignments)
+          het    haplotype 1 only
+          cross  query on haplotype 2, truth on haplotype 1 (swapped phasing)
+          mixed  query homozygous, truth heterozygous
+    flank_snps: one SNP in each flank (shared by truth and query, different qualities) so that the path also has
+    small-variant sync points around the SV."""
+    rng = np.random.default_rng(seed)
+    A = b"ACGT"
+    d = int(round(length * divergence))
+    q = lambda: float(np.float32(rng.uniform(3, 50)))
+    is_del = kind.startswith("del")
+    W = 2 * flank + 1 + (length if is_del else 0)
+    ref = bytearray(_rand_seq(rng, W, A))
+    tv: List[Variant] = []
+    qv: List[Variant] = []
+    if is_del:
+        t_sv = (flank, TYPE_DEL, length, b"", q())
+        q_sv = (flank + d, TYPE_DEL, max(length - d, 1), b"", q()) if d else (flank, TYPE_DEL, length, b"", q())
+    else:
+        ins = bytearray(_rand_seq(rng, length, A))
+        t_sv = (flank, TYPE_INS, 0, bytes(ins), q())
+        for p in rng.integers(0, length, d):
+            ins[p] = A[(A.index(ins[p]) + 1) % 4]
+        q_sv = (flank, TYPE_INS, 0, bytes(ins), q())
+    if not kind.endswith("query_only"):
+        tv.append(t_sv)
+    if not kind.endswith("truth_only"):
+        qv.append(q_sv)
+    if flank_snps and flank >= 8:
+        for pos in (3, W - 4):
+            alt = bytes([A[(A.index(ref[pos]) + 1 + int(rng.integers(0, 3))) % 4]])
+            tv.append((pos, TYPE_SUB, 1, alt, q()))
+            qv.append((pos, TYPE_SUB, 1, alt, q()))
+    tv.sort(key=lambda v: (v[0], v[1] != TYPE_INS))
+    qv.sort(key=lambda v: (v[0], v[1] != TYPE_INS))
+    if zyg == "hom":
+        haps = [qv, list(qv), tv, list(tv)]
+    elif zyg == "het":
+        haps = [qv, [], tv, []]
+    elif zyg == "cross":
+        haps = [[], qv, tv, []]
+    elif zyg == "mixed":
+        haps = [qv, list(qv), tv, []]
+    else:
+        raise ValueError(zyg)
+    bb = BatchBuilder(max_qual)
+    bb.add(bytes(ref), haps)
+    return bb.build()
