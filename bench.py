@@ -142,7 +142,8 @@ def run_reference(args):
         kind = "port"
     else:
         kind = "reference"
-    sample_n = args.ref_sample
+    # the SAME batch the GPU arm runs (--ref-sample 0, the default); a smaller sample only on request
+    sample_n = args.ref_sample or args.n_sc or WORKLOADS[args.workload]["n_sc"]
     b, cells, total = make_workload(args.workload, sample_n, args.seed, 0, 1, args.sv_max)
     times = []
     for i in range(args.warmup + args.steps):
@@ -208,7 +209,9 @@ def main():
     ap.add_argument("--n-sc", type=int, default=0, help="superclusters per GPU (default: the workload's)")
     ap.add_argument("--sv-max", type=int, default=10000)
     ap.add_argument("--seed", type=int, default=1)
-    ap.add_argument("--ref-sample", type=int, default=600_000, help="superclusters in the CPU-baseline sample")
+    ap.add_argument("--ref-sample", type=int, default=0,
+                    help="--impl reference: superclusters per step (0 = the workload's full batch, i.e. the GPU arm's config)")
+    ap.add_argument("--cpu-sample", type=int, default=600_000, help="superclusters in the cpu_baseline sample of the GPU arm's line")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gather-slices", type=int, default=0,
                     help="N > 1: slices of a rank's shard whose result all-gather overlaps the next slice's kernels "
@@ -217,10 +220,11 @@ def main():
                     help="also time the SV-bearing workload (BASELINE configs[3]) at 1/9 scale through vd_run (default at N=1)")
     ap.add_argument("--no-secondary", dest="secondary", action="store_false")
     args = ap.parse_args()
+    if args.impl == "reference":
+        args.warmup = max(args.warmup, 1)
+        return run_reference(args)
     if args.warmup < 3:
         args.warmup = 3
-    if args.impl == "reference":
-        return run_reference(args)
 
     import torch
     import torch.distributed as dist
@@ -459,17 +463,18 @@ def main():
             line["secondary"] = run_secondary(eng, args, dev, torch)
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
-            sb, scells, _ = make_workload(args.workload, args.ref_sample, args.seed, 0, 1, args.sv_max)
+            sb, scells, _ = make_workload(args.workload, args.cpu_sample, args.seed, 0, 1, args.sv_max)
             if checkers.reference_available(False):
-                _, sec = checkers.reference_run(sb, canonical=False, threads=cores)
+                secs = [checkers.reference_run(sb, canonical=False, threads=cores)[1] for _ in range(4)]
+                sec = float(np.median(secs[1:]))          # one warm-up pass, median of three
                 kind = "reference"
             else:
                 t0 = time.perf_counter(); checkers.oracle_run(sb); sec = time.perf_counter() - t0
                 kind, cores = "port", 1
             line["cpu_baseline"] = {"value": scells / sec / 1e9, "unit": "Gcells/s", "cores": cores, "kind": kind,
                                     "superclusters_per_s": sb.n_sc / sec,
-                                    "sample": f"{sb.n_sc} superclusters ({scells} cells) of the same workload, one pass, "
-                                              f"reference std::thread ladder with -t {cores}"}
+                                    "sample": f"{sb.n_sc} superclusters ({scells} cells) of the same workload, one warm-up pass then "
+                                              f"the median of three, reference std::thread ladder with -t {cores}"}
         print(json.dumps(line), flush=True)
     eng.close()
     if world > 1:

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define VD_ABI_VERSION 1
+#define VD_ABI_VERSION 2
 
 /* variant types, identical to src/defs.h:31-35 */
 #define VD_TYPE_SUB 1
@@ -50,7 +50,7 @@ extern "C" {
 #define VD_E_NODEVICE   -1   /* no CUDA device / wrong architecture                    */
 #define VD_E_CUDA       -2   /* a CUDA runtime call failed (see vd_last_error)         */
 #define VD_E_BADINPUT   -3   /* malformed batch (unsorted/overlapping variants, ...)   */
-#define VD_E_TOOLARGE   -4   /* a supercluster exceeds the supported matrix side       */
+#define VD_E_TOOLARGE   -4   /* one supercluster alone exceeds the HBM scratch budget  */
 #define VD_E_NOMEM      -5
 #define VD_E_ALIGN      -6   /* an alignment hit a fatal reference condition
                                 (src/dist.cpp:314, :440, :606, :644, :937)             */
@@ -140,6 +140,9 @@ typedef struct vd_stats {
     int64_t io_small[3];      /* algorithmic input+output bytes of those superclusters             */
     int64_t n_hom;            /* homozygous superclusters among them (both query haplotypes identical and
                                  both truth haplotypes identical: one alignment computed, records replicated) */
+    int64_t n_dense;          /* long alignments the banded warp kernels left to the dense block kernels        */
+    float   ms_band;          /* wall time of the banded warp kernels (all rungs, forward + backward + walk)    */
+    float   pad_;
 } vd_stats;
 
 /* Final per-variant / per-supercluster results in the reference's own terms

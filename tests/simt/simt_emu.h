@@ -177,7 +177,7 @@ inline void launch(dim3 grid, dim3 block, size_t smem, std::function<void()> bod
 }
 
 // two-phase rendezvous of the lanes in `mask`; returns the values of all lanes in out[32]
-inline void collect(unsigned mask, uint64_t v, uint64_t *out) {
+inline unsigned collect(unsigned mask, uint64_t v, uint64_t *out) {
     Ctx &c = ctx();
     Fiber *f = c.cur;
     WarpState &w = c.warp[f->lin >> 5];
@@ -188,6 +188,7 @@ inline void collect(unsigned mask, uint64_t v, uint64_t *out) {
     c.progress++;
     while (((w.arrived | w.exited) & mask) != mask) yield();
     memcpy(out, w.val, sizeof(w.val));
+    const unsigned participants = w.arrived & mask;         // lanes that took part (exited lanes did not)
     w.left |= bit;
     if (((w.left | w.exited) & mask) == mask) {
         w.arrived &= ~mask; w.left &= ~mask;
@@ -198,6 +199,7 @@ inline void collect(unsigned mask, uint64_t v, uint64_t *out) {
         w.released &= ~bit;
         c.progress++;
     }
+    return participants;
 }
 
 template <class T> inline uint64_t pack(T v) { uint64_t u = 0; static_assert(sizeof(T) <= 8, "shuffle type"); memcpy(&u, &v, sizeof(T)); return u; }
@@ -237,45 +239,43 @@ inline unsigned simt_active(unsigned mask) {      // lanes of the mask that stil
     return mask & ~simt::ctx().warp[simt::ctx().cur->lin >> 5].exited;
 }
 inline unsigned __ballot_sync(unsigned mask, int pred) {
-    uint64_t a[32]; simt::collect(mask, (uint64_t)(pred != 0), a);
+    uint64_t a[32]; const unsigned act = simt::collect(mask, (uint64_t)(pred != 0), a);
     unsigned r = 0;
-    const unsigned act = simt_active(mask);
     for (int i = 0; i < 32; i++) if (((act >> i) & 1) && a[i]) r |= 1u << i;
     return r;
 }
 inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }
-inline int __all_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) == simt_active(mask); }
+inline int __all_sync(unsigned mask, int pred) {
+    uint64_t a[32]; const unsigned act = simt::collect(mask, (uint64_t)(pred != 0), a);
+    for (int i = 0; i < 32; i++) if (((act >> i) & 1) && !a[i]) return 0;
+    return 1;
+}
 inline int __reduce_max_sync(unsigned mask, int v) {
-    uint64_t a[32]; simt::collect(mask, simt::pack(v), a);
-    const unsigned act = simt_active(mask);
+    uint64_t a[32]; const unsigned act = simt::collect(mask, simt::pack(v), a);
     int r = INT32_MIN;
     for (int i = 0; i < 32; i++) if ((act >> i) & 1) r = std::max(r, simt::unpack<int>(a[i]));
     return r;
 }
 inline int __reduce_min_sync(unsigned mask, int v) {
-    uint64_t a[32]; simt::collect(mask, simt::pack(v), a);
-    const unsigned act = simt_active(mask);
+    uint64_t a[32]; const unsigned act = simt::collect(mask, simt::pack(v), a);
     int r = INT32_MAX;
     for (int i = 0; i < 32; i++) if ((act >> i) & 1) r = std::min(r, simt::unpack<int>(a[i]));
     return r;
 }
 inline unsigned __reduce_or_sync(unsigned mask, unsigned v) {
-    uint64_t a[32]; simt::collect(mask, simt::pack(v), a);
-    const unsigned act = simt_active(mask);
+    uint64_t a[32]; const unsigned act = simt::collect(mask, simt::pack(v), a);
     unsigned r = 0;
     for (int i = 0; i < 32; i++) if ((act >> i) & 1) r |= simt::unpack<unsigned>(a[i]);
     return r;
 }
 inline unsigned __reduce_add_sync(unsigned mask, unsigned v) {
-    uint64_t a[32]; simt::collect(mask, simt::pack(v), a);
-    const unsigned act = simt_active(mask);
+    uint64_t a[32]; const unsigned act = simt::collect(mask, simt::pack(v), a);
     unsigned r = 0;
     for (int i = 0; i < 32; i++) if ((act >> i) & 1) r += simt::unpack<unsigned>(a[i]);
     return r;
 }
 template <class T> inline unsigned __match_any_sync(unsigned mask, T v) {
-    uint64_t a[32]; simt::collect(mask, simt::pack(v), a);
-    const unsigned act = simt_active(mask);
+    uint64_t a[32]; const unsigned act = simt::collect(mask, simt::pack(v), a);
     unsigned r = 0;
     const uint64_t mine = simt::pack(v);
     for (int i = 0; i < 32; i++) if (((act >> i) & 1) && a[i] == mine) r |= 1u << i;

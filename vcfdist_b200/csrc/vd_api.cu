@@ -20,6 +20,7 @@
 
 #include "vd_kernels.cuh"
 #include "vd_wave.cuh"
+#include "vd_band.cuh"
 
 using namespace vd;
 
@@ -78,6 +79,7 @@ struct vd_handle {
     int small_lo = 0, small_hi = vd::N_SMALL - 1;   // VD_SMALL_MIN / VD_SMALL_MAX: small-kernel classes in use (testing)
     int serial = 0;                 // VD_SERIAL=1: every launch group on the main stream (clean per-kernel event times)
     int use_hom = 1;                // VD_HOM=0: homozygous superclusters run all four alignments (testing)
+    int use_band = 1;               // VD_BAND=0: no banded warp kernels, every long alignment goes to the dense block kernels (testing)
     int use_wsc = 1;                // VD_WSC=0: mid-size superclusters go to the HBM-slab path instead of the warp kernel
     // staged input / output (vd_run)
     struct Stage {                  // one of the staging sets of the host-buffer pipeline
@@ -91,7 +93,7 @@ struct vd_handle {
     int ramp = 1;                   // VD_RAMP=0: uniform chunks
     int64_t chunk_sc = 1048576;      // superclusters per pipeline chunk (VD_CHUNK_SC)
     // work
-    DevBuf need_dense, bytes, offs, cubtmp, slab, hap_ok, wave_desc;
+    DevBuf need_dense, bytes, offs, cubtmp, slab, hap_ok, wave_desc, band_state, band_lb, dense_bytes, dense_off, dense;
     WaveItems *h_witems = nullptr;          // pinned + mapped (a small D2H memcpy would queue behind the bulk result copies of vd_run)
 };
 
@@ -149,6 +151,7 @@ extern "C" int vd_create(int device, int64_t scratch_bytes, vd_handle **out) {
     if (const char *v = getenv("VD_SMALL_MIN")) h->small_lo = atoi(v);
     if (const char *v = getenv("VD_SMALL_MAX")) h->small_hi = atoi(v);
     if (const char *v = getenv("VD_WSC")) h->use_wsc = atoi(v);
+    if (const char *v = getenv("VD_BAND")) h->use_band = atoi(v);
     if (const char *v = getenv("VD_SERIAL")) h->serial = atoi(v);
     if (const char *v = getenv("VD_HOM")) h->use_hom = atoi(v);
     if (const char *v = getenv("VD_RAMP")) h->ramp = atoi(v);
@@ -166,6 +169,7 @@ extern "C" int vd_create(int device, int64_t scratch_bytes, vd_handle **out) {
     small_configure();
     wsc_configure();
     wave_configure();
+    band_configure();
     *out = h;
     return VD_OK;
 }
@@ -184,7 +188,8 @@ extern "C" void vd_destroy(vd_handle *h) {
     }
     if (h->s_in) cudaStreamDestroy(h->s_in);
     if (h->s_out) cudaStreamDestroy(h->s_out);
-    DevBuf *bufs[] = {&h->need_dense, &h->bytes, &h->offs, &h->cubtmp, &h->slab, &h->hap_ok, &h->wave_desc};
+    DevBuf *bufs[] = {&h->need_dense, &h->bytes, &h->offs, &h->cubtmp, &h->slab, &h->hap_ok, &h->wave_desc, &h->band_state,
+                      &h->band_lb, &h->dense_bytes, &h->dense_off, &h->dense};
     for (DevBuf *b : bufs) b->release();
     for (auto &w : h->work) {
         DevBuf *wb[] = {&w.plan, &w.list, &w.order, &w.ranks, &w.ranks_out, &w.iota, &w.counters, &w.cubtmp};
@@ -346,9 +351,9 @@ static int chunk_exec(vd_handle *h, Work &W) {
             VD_LAUNCH(slab_align_kernel, (4 * m + 63) / 64, 64, 0, st, in, out, plan, list, i0, i1, offs, (u8 *)h->slab.p,
                                                                 (const int *)h->hap_ok.p, CLS_SCALAR);
             S.n_launches++;
-            // ---- wavefront kernels: class-sorted items, then forward / backward / walk ----
-            VD_LAUNCH(wave_tables_kernel, (4 * m + 127) / 128, 128, 0, st, plan, list, i0, i1, offs, (u8 *)h->slab.p,
-                                                                    (const int *)h->hap_ok.p);
+            // ---- long path: class-sorted items; banded warp kernels first, dense block kernels for the rest ----
+            VD_LAUNCH(wave_tables_kernel, (4 * m + 127) / 128, 128, 0, st, in, plan, list, i0, i1, offs, (u8 *)h->slab.p,
+                      (const int *)h->hap_ok.p);
             CK(h->wave_desc.ensure(sizeof(WaveItems) + 4 * (size_t)(4 * m + 4)));
             WaveItems *wi = (WaveItems *)h->wave_desc.p;
             int *items = (int *)((u8 *)h->wave_desc.p + sizeof(WaveItems));
@@ -357,68 +362,130 @@ static int chunk_exec(vd_handle *h, Work &W) {
             S.n_launches += 2;
             VD_LAUNCH(publish_kernel, 1, 64, 0, st, (const u32 *)wi, (u32 *)h->h_witems, (int)(sizeof(WaveItems) / 4));
             CK(cudaStreamSynchronize(st));
-            const WaveItems hwi = *h->h_witems;
+            WaveItems hwi = *h->h_witems;
             ClsBase cb;
             int total_items = 0;
-            for (int c = 0; c < N_WCLS; c++) { cb.b[c] = total_items; total_items += hwi.count[c]; }
-            if (total_items > 0 || hwi.n_toolarge > 0) {
-                VD_LAUNCH(wave_fill_kernel, (4 * m + 127) / 128, 128, 0, st, plan, list, i0, i1, (const int *)h->hap_ok.p,
-                                                                      wi, cb, items, out);
-                S.n_launches++;
-            }
+            for (int c = 0; c < N_WLIST; c++) { cb.b[c] = total_items; total_items += hwi.count[c]; }
+            CK(h->band_state.ensure(4 * (size_t)total_items + 16));
+            CK(h->band_lb.ensure(4 * (size_t)total_items + 16));
+            int *bstate = (int *)h->band_state.p, *blb = (int *)h->band_lb.p;
+            VD_LAUNCH(wave_fill_kernel, (4 * m + 127) / 128, 128, 0, st, in, plan, list, i0, i1, (const int *)h->hap_ok.p,
+                      wi, cb, items, out, bstate, blb, h->use_band);
+            S.n_launches++;
             if (total_items > 0) {
                 CK(h->need_dense.ensure(4 * (size_t)total_items + 16));
-                WaveArgs WA{in, out, plan, list, i0, offs, (u8 *)h->slab.p, items};
-                // forward then backward of each class on its own stream (an alignment's backward pass
-                // only depends on its own forward pass), all classes concurrently; then join
+                CK(h->dense_bytes.ensure(8 * (size_t)(total_items + 1)));
+                CK(h->dense_off.ensure(8 * (size_t)(total_items + 1)));
+                WaveArgs WA{in, out, plan, list, i0, offs, (u8 *)h->slab.p, items, bstate, nullptr, nullptr};
                 CK(cudaEventRecord(h->ev[4], st));
-                for (int c = N_WCLS - 1; c >= 0; c--) {            // biggest shapes first: they are the critical path
-                    if (!hwi.count[c]) continue;
-                    cudaStream_t ss = h->serial ? st : h->side[c];
-                    if (ss != st) CK(cudaStreamWaitEvent(ss, h->ev[4], 0));
-                    CK(cudaEventRecord(h->sev[c][0], ss));
-                    wave_launch(ss, WA, c, cb.b[c], hwi.count[c], true, true, h->banded_fwd ? (int *)h->need_dense.p : nullptr);
-                    CK(cudaEventRecord(h->sev[c][1], ss));
-                    wave_launch(ss, WA, c, cb.b[c], hwi.count[c], false, h->sparse_bwd && c >= h->sbwd_min_class,
-                                h->banded_fwd ? (int *)h->need_dense.p : nullptr, h->banded_bwd);
-                    CK(cudaEventRecord(h->sev[c][2], ss));
-                    // walk + credit of this class right behind its backward sweep, on the same stream
-                    VD_LAUNCH(wave_walk_kernel, (hwi.count[c] + 3) / 4, 128, 0, ss, WA, cb.b[c], hwi.count[c]);
-                    CK(cudaEventRecord(h->sev[c][3], ss));
-                    if (ss != st) CK(cudaStreamWaitEvent(st, h->sev[c][3], 0));
-                    S.n_launches += 3;
+                // ---- banded warp kernels (vd_band.cuh): rung K = 4, 8, 16; the backward sweep and the walk of a rung
+                //      run beside the forward sweep of the next one ----
+                if (h->use_band) {
+                    cudaStream_t bs[3] = {h->serial ? st : h->side[0], h->serial ? st : h->side[1], h->serial ? st : h->side[2]};
+                    for (int r = 0; r < 3; r++) {
+                        if (bs[r] != st) CK(cudaStreamWaitEvent(bs[r], r ? h->sev[r - 1][1] : h->ev[4], 0));
+                        CK(cudaEventRecord(h->sev[r][0], bs[r]));
+                        if (r == 0) band_launch<4>(bs[r], WA, total_items, bstate, blb, true);
+                        else if (r == 1) band_launch<8>(bs[r], WA, total_items, bstate, blb, true);
+                        else band_launch<16>(bs[r], WA, total_items, bstate, blb, true);
+                        CK(cudaEventRecord(h->sev[r][1], bs[r]));
+                        if (r == 0) band_launch<4>(bs[r], WA, total_items, bstate, blb, false);
+                        else if (r == 1) band_launch<8>(bs[r], WA, total_items, bstate, blb, false);
+                        else band_launch<16>(bs[r], WA, total_items, bstate, blb, false);
+                        CK(cudaEventRecord(h->sev[r][2], bs[r]));
+                        VD_LAUNCH(band_walk_kernel, (total_items + 3) / 4, 128, 0, bs[r], WA, total_items, (const int *)bstate, 4 << r);
+                        CK(cudaEventRecord(h->sev[r][3], bs[r]));
+                        S.n_launches += 3;
+                    }
+                    for (int r = 0; r < 3; r++) if (bs[r] != st) CK(cudaStreamWaitEvent(st, h->sev[r][3], 0));
                 }
-                CK(cudaEventRecord(h->ev[6], st));
-                CK(cudaEventRecord(h->ev[7], st));
+                // ---- what is left: dense-phase scratch sized on the device, then the block kernels per shape class ----
+                int64_t *dbytes = (int64_t *)h->dense_bytes.p, *doff = (int64_t *)h->dense_off.p;
+                CK(cudaMemsetAsync(dbytes + total_items, 0, 8, st));
+                VD_LAUNCH(wave_dense_size_kernel, (total_items + 255) / 256, 256, 0, st, plan, list, i0, (const int *)items, (const int *)bstate,
+                          total_items, dbytes, wi);
+                VD_LAUNCH(publish_kernel, 1, 64, 0, st, (const u32 *)wi, (u32 *)h->h_witems, (int)(sizeof(WaveItems) / 4));
+                S.n_launches += 2;
+                CK(cudaEventRecord(h->ev[5], st));
                 CK(cudaStreamSynchronize(st));
                 CK(cudaGetLastError());
-                // kernel durations: summed over classes (they overlap in wall time)
-                for (int c = 0; c < N_WCLS; c++) {
-                    if (!hwi.count[c]) continue;
-                    float a_ = 0, b_ = 0;
-                    cudaEventElapsedTime(&a_, h->sev[c][0], h->sev[c][1]);
-                    cudaEventElapsedTime(&b_, h->sev[c][1], h->sev[c][2]);
-                    float w2 = 0;
-                    cudaEventElapsedTime(&w2, h->sev[c][2], h->sev[c][3]);
-                    ms_fwd += a_; ms_bwd += b_; ms_walk += w2;
-                    if (trace) {
-                        int nd = 0;
-                        if (h->banded_fwd && c >= 4) {
-                            std::vector<int> v(hwi.count[c]);
-                            cudaMemcpy(v.data(), (int *)h->need_dense.p + cb.b[c], 4 * (size_t)hwi.count[c], cudaMemcpyDeviceToHost);
-                            for (int x : v) nd += x;
-                        }
-                        fprintf(stderr, "[run_resident] wave class %d: %d alignments (%d full-matrix), fwd %.2f ms, bwd %.2f ms, walk %.2f ms\n", c, hwi.count[c], nd, a_, b_, w2);
+                hwi = *h->h_witems;
+                S.n_dense += hwi.n_dense;
+                if (h->use_band) {
+                    for (int r = 0; r < 3; r++) {
+                        float a_ = 0, b_ = 0, w_ = 0;
+                        cudaEventElapsedTime(&a_, h->sev[r][0], h->sev[r][1]);
+                        cudaEventElapsedTime(&b_, h->sev[r][1], h->sev[r][2]);
+                        cudaEventElapsedTime(&w_, h->sev[r][2], h->sev[r][3]);
+                        ms_fwd += a_; ms_bwd += b_; ms_walk += w_;
+                        if (trace) fprintf(stderr, "[run_resident] band rung K=%d: fwd %.2f ms, bwd %.2f ms, walk %.2f ms\n", 4 << r, a_, b_, w_);
                     }
+                    float e_ = 0;
+                    cudaEventElapsedTime(&e_, h->ev[4], h->ev[5]);
+                    S.ms_band += e_;
+                    if (trace) fprintf(stderr, "[run_resident] %d long alignments, banded phase %.2f ms, %d left to the dense kernels (%.1f MB)\n",
+                                       total_items, e_, hwi.n_dense, hwi.dense_bytes / 1e6);
                 }
-                float c_ = 0, w_ = 0;
-                cudaEventElapsedTime(&c_, h->ev[6], h->ev[7]);
-                cudaEventElapsedTime(&w_, h->ev[4], h->ev[6]);
+                if (hwi.n_dense > 0) {
+                    if ((int64_t)hwi.dense_bytes > h->scratch_budget)
+                        return fail(h, VD_E_NOMEM, "dense phase needs %lld bytes of scratch (budget %lld)", (long long)hwi.dense_bytes,
+                                    (long long)h->scratch_budget);
+                    size_t tmp2 = 0;
+                    cub::DeviceScan::ExclusiveSum(nullptr, tmp2, dbytes, doff, total_items + 1, st);
+                    CK(h->cubtmp.ensure(tmp2));
+                    cub::DeviceScan::ExclusiveSum(h->cubtmp.p, tmp2, dbytes, doff, total_items + 1, st);
+                    CK(h->dense.ensure((size_t)hwi.dense_bytes + 256));
+                    WA.dense = (u8 *)h->dense.p; WA.dense_off = doff;
+                    S.n_launches++;
+                    // forward then backward of each class on its own stream (an alignment's backward pass
+                    // only depends on its own forward pass), all classes concurrently; then join
+                    CK(cudaEventRecord(h->ev[6], st));
+                    for (int c = N_WLIST - 1; c >= 0; c--) {            // biggest shapes first: they are the critical path
+                        if (!hwi.count[c]) continue;
+                        cudaStream_t ss = h->serial ? st : h->side[c % N_WCLS];
+                        if (ss != st) CK(cudaStreamWaitEvent(ss, h->ev[6], 0));
+                        CK(cudaEventRecord(h->sev[c % N_WCLS][0], ss));
+                        if (c == N_WCLS) {                              // no block kernel takes the shape: thread per alignment
+                            VD_LAUNCH(wave_oversize_kernel, (hwi.count[c] + 31) / 32, 32, 0, ss, WA, cb.b[c], hwi.count[c]);
+                            CK(cudaEventRecord(h->sev[c % N_WCLS][3], ss));
+                            if (ss != st) CK(cudaStreamWaitEvent(st, h->sev[c % N_WCLS][3], 0));
+                            S.n_launches++;
+                            continue;
+                        }
+                        wave_launch(ss, WA, c, cb.b[c], hwi.count[c], true, true, h->banded_fwd ? (int *)h->need_dense.p : nullptr);
+                        CK(cudaEventRecord(h->sev[c][1], ss));
+                        wave_launch(ss, WA, c, cb.b[c], hwi.count[c], false, h->sparse_bwd && c >= h->sbwd_min_class,
+                                    h->banded_fwd ? (int *)h->need_dense.p : nullptr, h->banded_bwd);
+                        CK(cudaEventRecord(h->sev[c][2], ss));
+                        // walk + credit of this class right behind its backward sweep, on the same stream
+                        VD_LAUNCH(wave_walk_kernel, (hwi.count[c] + 3) / 4, 128, 0, ss, WA, cb.b[c], hwi.count[c]);
+                        CK(cudaEventRecord(h->sev[c][3], ss));
+                        if (ss != st) CK(cudaStreamWaitEvent(st, h->sev[c][3], 0));
+                        S.n_launches += 3;
+                    }
+                    CK(cudaEventRecord(h->ev[7], st));
+                    CK(cudaStreamSynchronize(st));
+                    CK(cudaGetLastError());
+                    // kernel durations: summed over classes (they overlap in wall time)
+                    for (int c = 0; c < N_WCLS; c++) {
+                        if (!hwi.count[c]) continue;
+                        float a_ = 0, b_ = 0, w2 = 0;
+                        cudaEventElapsedTime(&a_, h->sev[c][0], h->sev[c][1]);
+                        cudaEventElapsedTime(&b_, h->sev[c][1], h->sev[c][2]);
+                        cudaEventElapsedTime(&w2, h->sev[c][2], h->sev[c][3]);
+                        ms_fwd += a_; ms_bwd += b_; ms_walk += w2;
+                        if (trace) fprintf(stderr, "[run_resident] dense phase, wave class %d: %d alignments in the class, fwd %.2f ms, bwd %.2f ms, walk %.2f ms\n", c, hwi.count[c], a_, b_, w2);
+                    }
+                    S.spill_bytes += 3 * (int64_t)hwi.spill_cells;
+                }
+                VD_LAUNCH(wave_hom_replicate_kernel, (m + 127) / 128, 128, 0, st, in, out, plan, list, i0, i1, (const int *)h->hap_ok.p);
+                S.n_launches++;
+                CK(cudaEventRecord(h->ev[7], st));
+                CK(cudaStreamSynchronize(st));
+                float w_ = 0;
+                cudaEventElapsedTime(&w_, h->ev[4], h->ev[7]);
                 S.ms_long_wall += w_;
-                S.spill_bytes += 3 * (int64_t)hwi.spill_cells;
             }
-            if (hwi.n_toolarge > 0)
-                return fail(h, VD_E_TOOLARGE, "%d alignments exceed the supported matrix side (32768 rows)", hwi.n_toolarge);
             i0 = i1;
         }
     }

@@ -70,6 +70,7 @@ struct ScPlan {
     int32_t lr;          // window / REF-plane length
     int32_t len[4];      // haplotype string lengths q1,q2,t1,t2
     int32_t cls;
+    int32_t hom;         // query haplotypes identical and truth haplotypes identical: one alignment, records replicated
 };
 
 static __host__ __device__ inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }

@@ -167,6 +167,7 @@ __global__ void plan_kernel(BatchDev in, ScPlan *plan, int *list, u8 *ranks, int
         }
     }
     p.cls = cls | (sbin >= 0 ? (sbin << 8) : 0);
+    p.hom = hom ? 1 : 0;
     if (live) { plan[sc] = p; ranks[sc] = (u8)(sbin >= 0 ? sbin : RANK_NONE); iota[sc] = sc; }
     // warp-aggregated counters: one atomic per warp and counter instead of one per thread
     const unsigned full = 0xffffffffu;
@@ -456,6 +457,7 @@ __global__ void slab_setup_kernel(BatchDev in, ScPlan *plan, const int *list, in
     if (i >= i1) return;
     const int sc = list[i];
     const ScPlan p = plan[sc];
+    if (p.hom && (h & 1) && p.cls == CLS_WAVE) { hap_ok[4 * (int64_t)(i - i0) + h] = 1; return; }   // same as haplotype h-1, never read
     const SlabLayout S = make_slab(p, p.cls == CLS_SCALAR);
     u8 *base = slab + (offs[i] - offs[i0]);
     SlabHap H(base + S.hap[h], p.len[h], p.lr);

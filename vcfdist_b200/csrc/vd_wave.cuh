@@ -55,6 +55,15 @@ __device__ inline void build_srcinfo(const PT *ptr, const u8 *flg, int nsrc,    
     }
 }
 
+// Packed per-row record of the banded warp kernels (vd_band.cuh): everything a lane needs about a row of
+// the QUERY or REF plane in one 16-byte load.
+struct RowRec {
+    u32 swi;             // my row as a swap DESTINATION: first source row of the other plane (bits 0-23) | count << 24
+    u32 si;              // my row as a swap SOURCE: srcinfo (bit 0 valid, bits 1-3 k, bit 4 tp(dest), bits 8.. destination row)
+    u32 tps;             // rows a' > a of my plane with tp(a') (bits 0-23) | tp(a) << 24 | tp(a+1) << 25
+    u32 chw;             // base of the row (bits 0-7) | base of row a+1 (bits 8-15, 0xff: none)
+};
+
 struct WaveHapQ {        // extra per query hap
     int *srcQ;           // [Lq]  QUERY rows as swap sources (destinations on the REF plane)
     int *srcR;           // [Lr]  REF rows as swap sources (destinations on the QUERY plane)
@@ -62,12 +71,16 @@ struct WaveHapQ {        // extra per query hap
     u32 *swiR;           // [Lr]  REF rows as swap DESTINATIONS: first source (QUERY row) | count << 16
     u8 *tpb;             // [Lq]  tp(a): entering QUERY row a counts a query variant (:572-574)
     u16 *tps;            // [Lq]  number of rows a' > a with tp(a') (potential of the backward insertion chain)
+    RowRec *rowQ, *rowR; // [Lq], [Lr] packed records of the banded warp kernels
+    int2 *hullQ, *hullR; // [Lq], [Lr] fewest / most row steps from the row to the end of either plane (see wave_row_hulls)
     __device__ WaveHapQ(u8 *base, int Lq, int Lr) {
-        srcQ = (int *)base; srcR = srcQ + Lq; swiQ = (u32 *)(srcR + Lr); swiR = swiQ + Lq; tpb = (u8 *)(swiR + Lr);
+        rowQ = (RowRec *)base; rowR = rowQ + Lq;
+        hullQ = (int2 *)(rowR + Lr); hullR = hullQ + Lq;
+        srcQ = (int *)(hullR + Lr); srcR = srcQ + Lq; swiQ = (u32 *)(srcR + Lr); swiR = swiQ + Lq; tpb = (u8 *)(swiR + Lr);
         tps = (u16 *)(tpb + align_up(Lq, 16));
     }
 };
-__host__ __device__ inline int64_t wave_hapq_bytes(int Lq, int Lr) { return 8 * ((int64_t)Lq + Lr) + align_up(Lq, 16) + align_up(2 * (int64_t)Lq, 16); }
+__host__ __device__ inline int64_t wave_hapq_bytes(int Lq, int Lr) { return 32 * ((int64_t)Lq + Lr) + align_up(Lq, 16) + align_up(2 * (int64_t)Lq, 16); }
 __host__ __device__ inline int64_t wave_hapt_bytes(int Lt) { return align_up(Lt, 16); }     // tinfo: base | tok<<7
 
 // kernel shape classes: (threads per block, rows per thread)
@@ -82,13 +95,26 @@ __host__ __device__ inline int wave_class(int Lq, int Lr, int Lt) {
     }
     return -1;
 }
+// item lists: one per shape class, plus one for the alignments no block kernel takes (more than 32768 rows over
+// both planes, or a score that could overflow 16 bits): banded warp kernels first, thread-per-alignment kernel else
+constexpr int N_WLIST = N_WCLS + 1;
+__host__ __device__ inline int wave_list_of(int Lq, int Lr, int Lt) { const int c = wave_class(Lq, Lr, Lt); return c < 0 ? N_WCLS : c; }
+// banded flag storage (vd_band.cuh): smallest rung (rows per lane) whose window of 32*K rows holds both planes
+// entirely (0: none), and the widest rung an alignment can reach - its storage is sized for that one
+__host__ __device__ inline int band_fit_k(int Lq, int Lr) {
+    const int m = Lq > Lr ? Lq : Lr;
+    return m <= 128 ? 4 : (m <= 256 ? 8 : (m <= 512 ? 16 : 0));
+}
+__host__ __device__ inline int band_kmax(int Lq, int Lr) { const int k = band_fit_k(Lq, Lr); return k ? k : 16; }
 
 // scratch of one alignment in the slab
 struct WaveAln {
-    int64_t oF;          // flag matrix [Lt][NP]
+    int64_t oF;          // BANDED flags [Lt][2][32*kmax] (vd_band.cuh); the dense matrix [Lt][NP] of the block kernels
+                         // lives in a separate buffer that only the alignments the banded kernels give up on get
+    int64_t oBand;       // int4[Lt]: candidate rows of every column (banded kernels)
     int64_t oWalk;       // walk scratch (path + Levenshtein row), AlnLayout offsets relative to it
     int64_t total;
-    int cls, K, padQ, NP;
+    int cls, K, padQ, NP, kmax;
 };
 __host__ __device__ inline WaveAln wave_aln(int Lq, int Lr, int Lt) {
     WaveAln w;
@@ -96,16 +122,25 @@ __host__ __device__ inline WaveAln wave_aln(int Lq, int Lr, int Lt) {
     w.K = w.cls >= 0 ? wave_k(w.cls) : 1;
     w.padQ = (Lq + w.K - 1) / w.K * w.K;
     w.NP = w.padQ + (Lr + w.K - 1) / w.K * w.K;      // both planes padded to whole threads
+    w.kmax = band_kmax(Lq, Lr);
     w.oF = 0;
-    w.oWalk = align_up((int64_t)w.NP * Lt, 16);
+    w.oBand = align_up((int64_t)Lt * 64 * w.kmax, 16);
+    w.oWalk = w.oBand + 16 * (int64_t)Lt;
     // path (int32 q, int32 t, u8 flags) + lev row
     const int np = Lq + Lr + Lt + 4;
     const int mn = (Lr < Lt ? Lr : Lt) + 1;
     int64_t walk = 8 * (int64_t)np + align_up(np, 4) + 4 * (int64_t)mn;
     const int64_t lists = 16 * (int64_t)w.NP + 64;       // sparse backward: 2 frontier lists + 2 worklists (int32)
-    if (lists > walk) walk = lists;
+    if (lists > walk && w.cls >= 0) walk = lists;
     w.total = align_up(w.oWalk + walk, 16);
     return w;
+}
+// bytes of the dense-phase scratch of one alignment: the flag matrix of the block kernels, or everything the
+// thread-per-alignment kernel needs when no block kernel takes the shape
+__host__ __device__ inline int64_t wave_dense_bytes(int Lq, int Lr, int Lt) {
+    const WaveAln w = wave_aln(Lq, Lr, Lt);
+    if (w.cls < 0) return align_up(make_layout<int64_t, 4, false>(Lq + Lr, Lt, Lr).total, 256);
+    return align_up((int64_t)w.NP * Lt, 256);
 }
 // walk scratch offsets in AlnLayout form (only the path / lev members are used)
 __device__ inline AlnLayout<int64_t> wave_walk_layout(int Lq, int Lr, int Lt) {
@@ -148,14 +183,68 @@ __global__ void wave_size_kernel(const ScPlan *plan, const int *list, int n, int
     bytes[i] = p.cls == CLS_WAVE ? make_wave_slab(p).total : make_slab(p, true).total;
 }
 
+// Row-step hulls for the score-bounded sweeps.  Forget the truth for a moment and look at the ROW graph of a
+// query haplotype: QUERY row a -> a+1, REF row r -> r+1, and the swap edges (source row -> ptr+1 on the other
+// plane, :335-337, :364-366).  A path from a cell to the end of either plane takes k row steps for some k in
+// [lo, hi] = the shortest / longest path in that graph; every row step that is not an insertion consumes a
+// truth base and every deletion consumes a truth base without a row step, so with rc truth bases left the
+// remaining cost is at least max(0, rc - hi, lo - rc).  The bound is consistent along every edge of the
+// two-plane graph (an edge taking dr row steps and dc truth bases costs at least |dr - dc|, except diagonal
+// and swap edges with dr = dc), so a sweep that only keeps cells with D + bound <= tau still gives every kept
+// cell its exact distance and its complete set of optimal predecessors - and it drops, for instance, the cells
+// that reach the far side of a 10 kb insertion through the REF plane at no cost but can never finish.
+// Computed backwards by merging the two planes so that every swap destination is done before its source.
+__device__ inline void wave_row_hulls(const int *qptr, const u8 *qflg, int Lq, const int *rptr, const u8 *rflg, int Lr,
+                                      int2 *hullQ, int2 *hullR) {
+    int a = Lq - 1, r = Lr - 1;
+    while (a >= 0 || r >= 0) {
+        bool okQ = false, okR = false, swQ = false, swR = false;
+        int dQ = -1, dR = -1;
+        if (a >= 0) {
+            const int f = qflg[a];
+            dQ = qptr[a] + 1;
+            swQ = (!(f & P_VARIANT) || (f & P_VAR_END)) && dQ >= 0 && dQ < Lr;
+            okQ = !swQ || dQ > r;
+        }
+        if (r >= 0) {
+            const int f = rflg[r];
+            dR = rptr[r] + 1;
+            swR = (!(f & P_VARIANT) || (f & P_VAR_END)) && dR >= 0 && dR < Lq;
+            okR = !swR || dR > a;
+        }
+        const bool takeQ = okQ || (!okR && a >= 0);
+        if (takeQ) {
+            int lo, hi;
+            if (a == Lq - 1) lo = hi = 0; else { lo = hullQ[a + 1].x + 1; hi = hullQ[a + 1].y + 1; }
+            if (swQ) {
+                if (dQ > r) { lo = min(lo, hullR[dQ].x + 1); hi = max(hi, hullR[dQ].y + 1); }
+                else { lo = 0; hi = INF; }                     // cannot happen in a DAG; no bound rather than a wrong one
+            }
+            hullQ[a] = make_int2(lo, hi);
+            a--;
+        } else {
+            int lo, hi;
+            if (r == Lr - 1) lo = hi = 0; else { lo = hullR[r + 1].x + 1; hi = hullR[r + 1].y + 1; }
+            if (swR) {
+                if (dR > a) { lo = min(lo, hullQ[dR].x + 1); hi = max(hi, hullQ[dR].y + 1); }
+                else { lo = 0; hi = INF; }
+            }
+            hullR[r] = make_int2(lo, hi);
+            r--;
+        }
+    }
+}
+
 // one thread per (entry, hap): wave tables after slab_setup_kernel's expansion
-__global__ void wave_tables_kernel(const ScPlan *plan, const int *list, int i0, int i1,
+__global__ void wave_tables_kernel(BatchDev in, const ScPlan *plan, const int *list, int i0, int i1,
                                    const int64_t *offs, u8 *slab, const int *hap_ok) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = i0 + (g >> 2), h = g & 3;
     if (i >= i1) return;
+    const u8 *rseq = in.rplane_seq + in.ref_off[list[i]];
     const ScPlan p = plan[list[i]];
     if (p.cls != CLS_WAVE) return;
+    if (p.hom && (h & 1)) return;                       // homozygous: haplotypes 1 / 3 equal 0 / 2 and are never used
     const int *okp = hap_ok + 4 * (int64_t)(i - i0);
     if (!(okp[0] && okp[1] && okp[2] && okp[3])) return;
     const WaveSlab W = make_wave_slab(p);
@@ -182,6 +271,32 @@ __global__ void wave_tables_kernel(const ScPlan *plan, const int *list, int i0, 
             const int k0 = M.toR[a], k1 = M.toR[a + 1];
             X.swiR[a] = k1 > k0 ? ((u32)M.toR[p.lr + 1 + k0] | ((u32)(k1 - k0) << 16)) : 0u;
         }
+        // packed row records of the banded warp kernels
+        const int Lq = p.len[h];
+        wave_row_hulls(H.ptr, H.flg, Lq, M.rptr, M.rflg, p.lr, X.hullQ, X.hullR);
+        {
+            int cnt = 0;
+            for (int a = Lq - 1; a >= 0; a--) {
+                RowRec r;
+                const int k0 = M.toQ[a], k1 = M.toQ[a + 1];
+                r.swi = k1 > k0 ? (((u32)M.toQ[Lq + 1 + k0] & 0xffffffu) | ((u32)(k1 - k0) << 24)) : 0u;
+                r.si = (u32)X.srcQ[a];
+                const u32 tpa = X.tpb[a], tpn = a + 1 < Lq ? X.tpb[a + 1] : 0;
+                r.tps = (u32)cnt | (tpa << 24) | (tpn << 25);
+                r.chw = (u32)(H.str[a] & 0x7f) | ((a + 1 < Lq ? (u32)(H.str[a + 1] & 0x7f) : 0xffu) << 8);
+                X.rowQ[a] = r;
+                cnt += (int)tpa;
+            }
+        }
+        for (int a = 0; a < p.lr; a++) {
+            RowRec r;
+            const int k0 = M.toR[a], k1 = M.toR[a + 1];
+            r.swi = k1 > k0 ? (((u32)M.toR[p.lr + 1 + k0] & 0xffffffu) | ((u32)(k1 - k0) << 24)) : 0u;
+            r.si = (u32)X.srcR[a];
+            r.tps = 0;                                   // tp is zero on the REF plane
+            r.chw = (u32)(rseq[a] & 0x7f) | ((a + 1 < p.lr ? (u32)(rseq[a + 1] & 0x7f) : 0xffu) << 8);
+            X.rowR[a] = r;
+        }
     } else {
         u8 *tinfo = base + W.ht[h - 2];
         for (int c = 0; c < p.len[h]; c++) {
@@ -193,12 +308,14 @@ __global__ void wave_tables_kernel(const ScPlan *plan, const int *list, int i0, 
 
 // class-sorted list of (entry, alignment) items of one chunk
 struct WaveItems {
-    int count[N_WCLS];
-    int cursor[N_WCLS];
-    int n_toolarge;
+    int count[N_WLIST];
+    int cursor[N_WLIST];
+    int n_dense;                 // items left to the dense phase once the banded kernels are through
+    int pad_;
     unsigned long long spill_cells;
+    unsigned long long dense_bytes;
 };
-struct ClsBase { int b[N_WCLS]; };
+struct ClsBase { int b[N_WLIST]; };
 __global__ void wave_count_kernel(const ScPlan *plan, const int *list, int i0, int i1, const int *hap_ok,
                                   WaveItems *wi) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
@@ -206,17 +323,15 @@ __global__ void wave_count_kernel(const ScPlan *plan, const int *list, int i0, i
     if (i >= i1) return;
     const ScPlan p = plan[list[i]];
     if (p.cls != CLS_WAVE) return;
+    if (p.hom && ai) return;                             // homozygous: alignment 0 only, records replicated afterwards
     const int *okp = hap_ok + 4 * (int64_t)(i - i0);
     if (!(okp[0] && okp[1] && okp[2] && okp[3])) return;
-    const int c = wave_class(p.len[ai >> 1], p.lr, p.len[2 + (ai & 1)]);
-    if (c < 0) atomicAdd(&wi->n_toolarge, 1);
-    else {
-        atomicAdd(&wi->count[c], 1);
-        atomicAdd(&wi->spill_cells, (unsigned long long)wave_aln(p.len[ai >> 1], p.lr, p.len[2 + (ai & 1)]).NP * p.len[2 + (ai & 1)]);
-    }
+    atomicAdd(&wi->count[wave_list_of(p.len[ai >> 1], p.lr, p.len[2 + (ai & 1)])], 1);
 }
-__global__ void wave_fill_kernel(const ScPlan *plan, const int *list, int i0, int i1, const int *hap_ok,
-                                 WaveItems *wi, ClsBase cb, int *items, OutDev out) {
+__device__ inline int band_score_lb(const BatchDev &in, int sc, int ai, int Lr, int Lt);
+// state[]: 0 = pending for the banded kernels (band_on) or -1 = dense phase; lbound[]: lower bound of the score
+__global__ void wave_fill_kernel(BatchDev in, const ScPlan *plan, const int *list, int i0, int i1, const int *hap_ok,
+                                 WaveItems *wi, ClsBase cb, int *items, OutDev out, int *state, int *lbound, int band_on) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = i0 + (g >> 2), ai = g & 3;
     if (i >= i1) return;
@@ -229,9 +344,31 @@ __global__ void wave_fill_kernel(const ScPlan *plan, const int *list, int i0, in
         out.aln_score[4 * (int64_t)sc + ai] = -1;
         return;
     }
-    const int c = wave_class(p.len[ai >> 1], p.lr, p.len[2 + (ai & 1)]);
-    if (c < 0) { out.status[4 * (int64_t)sc + ai] = ST_BAD; out.aln_score[4 * (int64_t)sc + ai] = -1; return; }
-    items[cb.b[c] + atomicAdd(&wi->cursor[c], 1)] = ((i - i0) << 2) | ai;
+    if (p.hom && ai) return;
+    const int Lq = p.len[ai >> 1], Lt = p.len[2 + (ai & 1)];
+    const int pos = cb.b[wave_list_of(Lq, p.lr, Lt)] + atomicAdd(&wi->cursor[wave_list_of(Lq, p.lr, Lt)], 1);
+    items[pos] = ((i - i0) << 2) | ai;
+    state[pos] = band_on ? 0 : -1;
+    lbound[pos] = band_score_lb(in, sc, ai, p.lr, Lt);
+}
+
+// dense phase: scratch bytes of every item the banded kernels did not solve (0 for the others)
+__global__ void wave_dense_size_kernel(const ScPlan *plan, const int *list, int i0, const int *items, const int *state, int n_items,
+                                       int64_t *bytes, WaveItems *wi) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_items) return;
+    int64_t b = 0;
+    if (state[idx] <= 0) {
+        const int item = items[idx];
+        const ScPlan p = plan[list[i0 + (item >> 2)]];
+        const int ai = item & 3;
+        b = wave_dense_bytes(p.len[ai >> 1], p.lr, p.len[2 + (ai & 1)]);
+        atomicAdd(&wi->n_dense, 1);
+        atomicAdd(&wi->dense_bytes, (unsigned long long)b);
+        const WaveAln wa = wave_aln(p.len[ai >> 1], p.lr, p.len[2 + (ai & 1)]);
+        if (wa.cls >= 0) atomicAdd(&wi->spill_cells, (unsigned long long)wa.NP * p.len[2 + (ai & 1)]);
+    }
+    bytes[idx] = b;
 }
 
 struct WaveArgs {
@@ -243,6 +380,9 @@ struct WaveArgs {
     const int64_t *offs;
     u8 *slab;
     const int *items;
+    const int *bstate;           // per item: > 0 solved by the banded kernels (vd_band.cuh): the dense kernels skip it
+    u8 *dense;                   // dense-phase scratch: flag matrices of the block kernels
+    const int64_t *dense_off;    // per item, byte offset into dense
 };
 
 // everything a block needs about its alignment
@@ -255,11 +395,15 @@ template <class TT> struct WaveCtxT {      // TT: element type of the CSR swap t
     const TT *qptr, *rptr;      // query->ref and ref->query pointers (band bookkeeping of the forward sweep)
     const int *srcQ, *srcR;
     const u32 *swiQ, *swiR;     // per destination row: first swap source | count << 16 (slab path only)
-    u8 *F;
+    u8 *F;                      // dense flag matrix [Lt][NP] (dense-phase scratch)
+    u8 *walk;                   // the alignment's walk scratch in the slab
+    bool skip;                  // solved by the banded kernels
 };
 typedef WaveCtxT<int> WaveCtx;
-__device__ inline WaveCtx wave_ctx(const WaveArgs &A, int item) {
+__device__ inline WaveCtx wave_ctx(const WaveArgs &A, int idx) {
     WaveCtx x;
+    const int item = A.items[idx];
+    x.skip = A.bstate && A.bstate[idx] > 0;
     const int e = item >> 2;
     x.ai = item & 3;
     const int i = A.i0 + e;
@@ -280,8 +424,9 @@ __device__ inline WaveCtx wave_ctx(const WaveArgs &A, int item) {
     x.swiQ = X.swiQ; x.swiR = X.swiR;
     x.rseq = A.in.rplane_seq + A.in.ref_off[x.sc];
     x.tinfo = base + W.ht[th];
-    x.F = base + W.aln[x.ai] + wa.oF;
-    x.band = (short *)(base + W.aln[x.ai] + wa.oWalk);
+    x.F = (A.dense && !x.skip) ? A.dense + A.dense_off[idx] : nullptr;
+    x.walk = base + W.aln[x.ai] + wa.oWalk;
+    x.band = (short *)x.walk;
     return x;
 }
 
@@ -581,7 +726,8 @@ __host__ __device__ inline int fwdb_smem(int npmax) { return 4 * npmax + 32 + 2 
 
 __global__ void __launch_bounds__(FWDB_TPB) wave_fwdb_kernel(WaveArgs A, int item0, int npmax, int *need_dense) {
     VD_DYN_SHARED(smem_raw);
-    const WaveCtx X = wave_ctx(A, A.items[item0 + blockIdx.x]);
+    const WaveCtx X = wave_ctx(A, item0 + blockIdx.x);
+    if (X.skip) return;
     u16 *sD0 = (u16 *)smem_raw, *sD1 = sD0 + npmax;
     int *sLive = (int *)(sD1 + npmax);
     int *sW = sLive + 8;                                     // [2 parities][2 segments][32 warps]
@@ -799,7 +945,8 @@ __global__ void __launch_bounds__(TPB) wave_fwd_kernel(WaveArgs A, int item0, co
     VD_DYN_SHARED(smem_raw);
     __shared__ int sEnd[2];
     if (need_dense && !need_dense[item0 + blockIdx.x]) return;       // solved by the banded sweep
-    const WaveCtx X = wave_ctx(A, A.items[item0 + blockIdx.x]);
+    const WaveCtx X = wave_ctx(A, item0 + blockIdx.x);
+    if (X.skip) return;
     int score, end_plane;
     // after a failed banded sweep (tau up to FWDB_TAU_MAX) go straight to the unbounded pass
     wave_fwd_body<TPB, K, int>(X, threadIdx.x, smem_raw, sEnd, score, end_plane, need_dense ? (1 << 28) : FWD_TAU0);
@@ -1021,7 +1168,8 @@ template <int TPB, int K>
 __global__ void __launch_bounds__(TPB) wave_bwd_kernel(WaveArgs A, int item0, const int *only_dense) {
     VD_DYN_SHARED(smem_raw);
     if (only_dense && !only_dense[item0 + blockIdx.x]) return;       // solved by the banded sweeps
-    const WaveCtx X = wave_ctx(A, A.items[item0 + blockIdx.x]);
+    const WaveCtx X = wave_ctx(A, item0 + blockIdx.x);
+    if (X.skip) return;
     const int end_plane = A.out.aln_end_plane[4 * (int64_t)X.sc + X.ai];
     int beg_plane;
     u32 status;
@@ -1086,15 +1234,14 @@ __device__ __forceinline__ SbwdPush sbwd_pushes(const WaveCtx &X, int row, int f
 __global__ void __launch_bounds__(32) wave_sbwd_kernel(WaveArgs A, int item0, int npmax, const int *only_dense) {
     VD_DYN_SHARED(smem_raw);
     if (only_dense && !only_dense[item0 + blockIdx.x]) return;       // done by the banded backward sweep
-    const int item = A.items[item0 + blockIdx.x];
-    const WaveCtx X = wave_ctx(A, item);
+    const WaveCtx X = wave_ctx(A, item0 + blockIdx.x);
+    if (X.skip) return;
     short *T0 = (short *)smem_raw, *T1 = T0 + npmax;          // T of two columns, dense over rows
     u8 *PF0 = (u8 *)(T1 + npmax), *PF1 = PF0 + npmax;          // path flags of two columns
     __shared__ int cnt[2], wcnt[2];
     const int lane = threadIdx.x;
     // frontier lists and worklists live in the alignment's walk scratch (dead until the walk)
-    const WaveAln wa = wave_aln(X.Lq, X.Lr, X.Lt);
-    int *L0 = (int *)(X.F + wa.oWalk), *L1 = L0 + X.NP, *W0 = L1 + X.NP, *W1 = W0 + X.NP;
+    int *L0 = (int *)X.walk, *L1 = L0 + X.NP, *W0 = L1 + X.NP, *W1 = W0 + X.NP;
     const int64_t oi = 4 * (int64_t)X.sc + X.ai;
     const int end_plane = A.out.aln_end_plane[oi];
     const int erow = end_plane ? X.padQ + X.Lr - 1 : X.Lq - 1;
@@ -1251,7 +1398,8 @@ __host__ __device__ inline int bwdb_smem(int npmax) { return 6 * npmax + 128 * 4
 __global__ void __launch_bounds__(BWDB_TPB) wave_bwdb_kernel(WaveArgs A, int item0, int npmax, const int *need_dense) {
     VD_DYN_SHARED(smem_raw);
     if (need_dense[item0 + blockIdx.x]) return;              // full-matrix forward sweep: frontier kernel instead
-    const WaveCtx X = wave_ctx(A, A.items[item0 + blockIdx.x]);
+    const WaveCtx X = wave_ctx(A, item0 + blockIdx.x);
+    if (X.skip) return;
     short *sT0 = (short *)smem_raw, *sT1 = sT0 + npmax;      // T of column c+1 / c
     u8 *sF0 = (u8 *)(sT1 + npmax), *sF1 = sF0 + npmax;       // forward flags of column c+1 / c
     int *sW = (int *)(sF1 + npmax);                          // [NW] warp heads, [NW] all-linked flags, chunk carry
@@ -1472,6 +1620,7 @@ struct PFWave {
 __global__ void wave_walk_kernel(WaveArgs A, int item0, int n_items) {
     const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (g >= n_items || (threadIdx.x & 31)) return;
+    if (A.bstate && A.bstate[item0 + g] > 0) return;         // walked by band_walk_kernel
     const int item = A.items[item0 + g];
     const int e = item >> 2, ai = item & 3;
     const int i = A.i0 + e;
@@ -1490,12 +1639,67 @@ __global__ void wave_walk_kernel(WaveArgs A, int item0, int n_items) {
     u8 *ab = base + W.aln[ai];
     GMem mem{ab + wa.oWalk};
     const AlnLayout<int64_t> L = wave_walk_layout(q.len, p.lr, t.len);
-    PFWave pfr{ab + wa.oF, wa.NP, wa.padQ, t.len};
+    PFWave pfr{A.dense + A.dense_off[item0 + g], wa.NP, wa.padQ, t.len};
     u32 status = A.out.status[4 * (int64_t)sc + ai];
     const int beg_plane = A.out.aln_beg_plane[4 * (int64_t)sc + ai];
     const int end_plane = A.out.aln_end_plane[4 * (int64_t)sc + ai];
     walk_credit<GMem, 4, int>(mem, L, pfr, q, qm, t, rseq, p.lr, beg_plane, end_plane, A.in, A.out, sc, ai, status);
     A.out.status[4 * (int64_t)sc + ai] = status;
+}
+
+// Alignments no block kernel takes (more than 32768 rows over both planes, or a score that could overflow the
+// 16-bit columns) and the banded kernels did not solve either: one thread per alignment with every matrix in
+// the dense-phase scratch (the reference only WARNs about the RAM and computes such a supercluster,
+// src/cluster.cpp:102-107).  Slow, but it never refuses.
+__global__ void wave_oversize_kernel(WaveArgs A, int item0, int n_items) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_items) return;
+    if (A.bstate && A.bstate[item0 + g] > 0) return;
+    const int item = A.items[item0 + g];
+    const int e = item >> 2, ai = item & 3;
+    const int i = A.i0 + e;
+    const int sc = A.list[i];
+    const ScPlan p = A.plan[sc];
+    const WaveSlab W = make_wave_slab(p);
+    u8 *base = A.slab + (A.offs[i] - A.offs[A.i0]);
+    const int qh = ai >> 1, th = 2 + (ai & 1);
+    SlabHap HQ(base + W.base.hap[qh], p.len[qh], p.lr), HT(base + W.base.hap[th], p.len[th], p.lr);
+    SlabQm M(base + W.base.qm[qh], p.len[qh], p.lr);
+    Hap<int> q{p.len[qh], HQ.str, HQ.flg, HQ.ptr, HQ.ins};
+    Hap<int> t{p.len[th], HT.str, HT.flg, HT.ptr, HT.ins};
+    QMaps<int> qm{M.rptr, M.rflg, M.toQ, M.toR};
+    const u8 *rseq = A.in.rplane_seq + A.in.ref_off[sc];
+    GMem mem{A.dense + A.dense_off[item0 + g]};
+    const AlnLayout<int64_t> L = make_layout<int64_t, 4, false>(q.len + p.lr, t.len, p.lr);
+    u32 status = 0;
+    int score, end_plane;
+    forward_scalar<GMem, 4, int>(mem, L, q, qm, t, rseq, p.lr, score, end_plane);
+    const int beg_plane = backward_scalar<GMem, 4, int>(mem, L, q, qm, t, rseq, p.lr, end_plane, status);
+    PFScalar<GMem> pfr{&mem, L.oPF, q.len + p.lr, q.len};
+    walk_credit<GMem, 4, int>(mem, L, pfr, q, qm, t, rseq, p.lr, beg_plane, end_plane, A.in, A.out, sc, ai, status);
+    A.out.aln_score[4 * (int64_t)sc + ai] = score;
+    A.out.aln_end_plane[4 * (int64_t)sc + ai] = (u8)end_plane;
+    A.out.aln_beg_plane[4 * (int64_t)sc + ai] = (u8)beg_plane;
+    A.out.status[4 * (int64_t)sc + ai] = status;
+}
+
+// homozygous long superclusters: alignment 0 was computed, its records go to the other haplotype and slot
+__global__ void wave_hom_replicate_kernel(BatchDev in, OutDev out, const ScPlan *plan, const int *list, int i0, int i1, const int *hap_ok) {
+    const int i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= i1) return;
+    const int sc = list[i];
+    const ScPlan p = plan[sc];
+    if (p.cls != CLS_WAVE || !p.hom) return;
+    const int *okp = hap_ok + 4 * (int64_t)(i - i0);
+    if (!(okp[0] && okp[1] && okp[2] && okp[3])) return;
+    const int64_t oi = 4 * (int64_t)sc;
+    for (int k = 1; k < 4; k++) {
+        out.aln_score[oi + k] = out.aln_score[oi];
+        out.aln_end_plane[oi + k] = out.aln_end_plane[oi];
+        out.aln_beg_plane[oi + k] = out.aln_beg_plane[oi];
+        out.status[oi + k] = out.status[oi];
+    }
+    replicate_hom(in, out, sc);
 }
 
 // ---- host side --------------------------------------------------------------------------------
