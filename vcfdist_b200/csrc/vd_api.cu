@@ -381,23 +381,19 @@ static int chunk_exec(vd_handle *h, Work &W) {
                 // ---- banded warp kernels (vd_band.cuh): rung K = 4, 8, 16; the backward sweep and the walk of a rung
                 //      run beside the forward sweep of the next one ----
                 if (h->use_band) {
-                    cudaStream_t bs[3] = {h->serial ? st : h->side[0], h->serial ? st : h->side[1], h->serial ? st : h->side[2]};
-                    for (int r = 0; r < 3; r++) {
-                        if (bs[r] != st) CK(cudaStreamWaitEvent(bs[r], r ? h->sev[r - 1][1] : h->ev[4], 0));
-                        CK(cudaEventRecord(h->sev[r][0], bs[r]));
-                        if (r == 0) band_launch<4>(bs[r], WA, total_items, bstate, blb, true);
-                        else if (r == 1) band_launch<8>(bs[r], WA, total_items, bstate, blb, true);
-                        else band_launch<16>(bs[r], WA, total_items, bstate, blb, true);
-                        CK(cudaEventRecord(h->sev[r][1], bs[r]));
-                        if (r == 0) band_launch<4>(bs[r], WA, total_items, bstate, blb, false);
-                        else if (r == 1) band_launch<8>(bs[r], WA, total_items, bstate, blb, false);
-                        else band_launch<16>(bs[r], WA, total_items, bstate, blb, false);
-                        CK(cudaEventRecord(h->sev[r][2], bs[r]));
-                        VD_LAUNCH(band_walk_kernel, (total_items + 3) / 4, 128, 0, bs[r], WA, total_items, (const int *)bstate, 4 << r);
-                        CK(cudaEventRecord(h->sev[r][3], bs[r]));
+                    for (int r = 0; r < N_RUNG; r++) {
+                        cudaStream_t bs = h->serial ? st : h->side[r];
+                        if (bs != st) CK(cudaStreamWaitEvent(bs, r ? h->sev[r - 1][1] : h->ev[4], 0));
+                        CK(cudaEventRecord(h->sev[r][0], bs));
+                        band_launch_rung(bs, r, WA, total_items, bstate, blb, true);
+                        CK(cudaEventRecord(h->sev[r][1], bs));
+                        band_launch_rung(bs, r, WA, total_items, bstate, blb, false);
+                        CK(cudaEventRecord(h->sev[r][2], bs));
+                        VD_LAUNCH(band_walk_kernel, (total_items + 3) / 4, 128, 0, bs, WA, total_items, (const int *)bstate, band_rung_k(r));
+                        CK(cudaEventRecord(h->sev[r][3], bs));
                         S.n_launches += 3;
                     }
-                    for (int r = 0; r < 3; r++) if (bs[r] != st) CK(cudaStreamWaitEvent(st, h->sev[r][3], 0));
+                    for (int r = 0; r < N_RUNG; r++) if (!h->serial) CK(cudaStreamWaitEvent(st, h->sev[r][3], 0));
                 }
                 // ---- what is left: dense-phase scratch sized on the device, then the block kernels per shape class ----
                 int64_t *dbytes = (int64_t *)h->dense_bytes.p, *doff = (int64_t *)h->dense_off.p;
@@ -412,13 +408,13 @@ static int chunk_exec(vd_handle *h, Work &W) {
                 hwi = *h->h_witems;
                 S.n_dense += hwi.n_dense;
                 if (h->use_band) {
-                    for (int r = 0; r < 3; r++) {
+                    for (int r = 0; r < N_RUNG; r++) {
                         float a_ = 0, b_ = 0, w_ = 0;
                         cudaEventElapsedTime(&a_, h->sev[r][0], h->sev[r][1]);
                         cudaEventElapsedTime(&b_, h->sev[r][1], h->sev[r][2]);
                         cudaEventElapsedTime(&w_, h->sev[r][2], h->sev[r][3]);
                         ms_fwd += a_; ms_bwd += b_; ms_walk += w_;
-                        if (trace) fprintf(stderr, "[run_resident] band rung K=%d: fwd %.2f ms, bwd %.2f ms, walk %.2f ms\n", 4 << r, a_, b_, w_);
+                        if (trace) fprintf(stderr, "[run_resident] band rung K=%d tau=%d: fwd %.2f ms, bwd %.2f ms, walk %.2f ms\n", band_rung_k(r), band_rung_tau(r), a_, b_, w_);
                     }
                     float e_ = 0;
                     cudaEventElapsedTime(&e_, h->ev[4], h->ev[5]);

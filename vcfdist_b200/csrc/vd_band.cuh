@@ -6,35 +6,39 @@
 // (:309-443), so it only ever touches cells whose distance is at most the final score.  A structural
 // variant that truth and query both carry gives matrices of thousands x thousands with a score of a few
 // dozen: the cells that matter are a narrow band around one diagonal per plane.  These kernels keep, per
-// plane, a WINDOW of 32*K consecutive rows that slides with the band (Ukkonen's cut-off at a score bound
-// tau; exact whenever the final score is <= tau):
+// plane, a WINDOW of 32*K consecutive rows that slides with the band:
 //
+//   * score bound tau (Ukkonen's cut-off) sharpened by an exact lower bound of the remaining cost
+//     (wave_row_hulls in vd_wave.cuh): a cell is kept while D + bound <= tau.  Every kept cell has its exact
+//     distance and its complete set of optimal predecessors, so the result is exact whenever the final score
+//     is <= tau; otherwise the next rung (wider window, larger tau) tries again;
 //   * rows are dealt in blocks of K consecutive rows, block b always to lane b % 32; the window of a column
-//     is the 32 blocks starting at the block of the lowest candidate row.  A lane whose block leaves the
-//     window picks up the block 32 further on and reloads the K packed row records (RowRec, 16 bytes a
-//     row: swap source, swap destination, query-variant counts, bases) - once every K columns in a
-//     diagonal region;
+//     is the 32 blocks starting at the block of the lowest candidate row;
 //   * the column step of a lane is a serial chain over its K rows in registers (diagonal, deletion, swap
 //     candidate, the in-column insertion chain), then ONE warp scan hands the chain across lanes
 //     (min-plus prefix scan forward, link-segmented suffix max of T - S backward), then a second pass over
-//     the K rows finalises values and flags.  Swap edges read the other plane's previous column from a
-//     ring in shared memory (32*K entries per plane and column parity);
-//   * flags are stored BANDED: F[column][plane][row mod 32K], one byte per cell of the window - 64*K bytes
-//     per column instead of (Lq+Lr) bytes, so an alignment of 10 k x 10 k needs 2.5-10 MB instead of 200 MB
-//     and the walk's dependent flag loads stay within a few cache lines per column.
+//     the K rows finalises values and flags;
+//   * nothing on the per-column dependency chain touches HBM: the packed per-row records (FwdRow / BwdRow,
+//     16 bytes a row) stream through a shared-memory ring in 512-byte chunks pulled by the TMA copy engine
+//     (cp.async.bulk + mbarrier) a window ahead of the sweep; the truth bases and the band records arrive in
+//     32-column chunks; swap edges read the other plane's previous column from a ring in shared memory;
+//     the next columns' candidate rows come from warp reductions over the kept cells;
+//   * flags are stored BANDED: F[column][plane][row mod 32K], one byte per cell of the window.
 //
-// Rungs: K = 4 (tau 40), K = 8 (tau 80), K = 16 (tau 160).  A rung whose planes both fit the window
-// entirely (<= 32*K rows each) runs unbounded: that is the dense sweep of the thin-but-wide matrices (no
-// variant on the query side against a long insertion on the truth side).  An alignment is tried rung by
-// rung, skipping rungs below a lower bound of its score; what no rung solves (score > 160, or a band wider
-// than the window) goes to the dense block-per-alignment kernels of vd_wave.cuh.
+// Rungs (rows per lane / score bound): 1/10, 2/20, 4/40, 8/80, 16/160 (a window holds 3 tau + 2 rows).  A rung whose window holds both
+// planes entirely (<= 32*K rows each) runs unbounded: the dense sweep of thin-but-wide matrices.  What no
+// rung solves (score above the last bound, or kept cells further apart than a window) goes to the dense
+// block-per-alignment kernels of vd_wave.cuh.
 #pragma once
 #include "vd_wave.cuh"
 
 namespace vd {
 
 constexpr int BAND_WARPS = 4;                                  // alignments per block (one warp each)
-__host__ __device__ inline int band_tau(int K) { return 10 * K; }
+constexpr int N_RUNG = 5;
+inline int band_rung_k(int r) { const int v[N_RUNG] = {1, 2, 4, 8, 16}; return v[r]; }
+inline int band_rung_tau(int r) { const int v[N_RUNG] = {10, 20, 40, 80, 160}; return v[r]; }
+
 // per-item state shared by the rungs
 constexpr int BAND_PENDING = 0;       // not solved yet
 constexpr int BAND_DENSE = -1;        // given up: dense kernels
@@ -43,9 +47,8 @@ constexpr int BAND_DENSE = -1;        // given up: dense kernels
 struct BandCtx {
     int sc, ai, Lq, Lr, Lt;
     const u8 *tinfo;
-    const RowRec *row[2];             // QUERY plane rows, REF plane rows
-    const int2 *hull[2];              // row-step hulls (wave_row_hulls)
-    const int *optr[2];               // row -> row of the other plane (qptr, rptr)
+    const FwdRow *frow[2];            // QUERY plane rows, REF plane rows
+    const BwdRow *brow[2];
     const int *tab[2];                // CSR swap-source tables of destination rows (toQ, toR)
     u8 *F;                            // banded flags, [Lt][2][32*kmax]
     int4 *band;                       // [Lt] candidate rows (loQ, hiQ, loR, hiR), empty: lo > hi
@@ -64,13 +67,11 @@ __device__ inline BandCtx band_ctx(const WaveArgs &A, int item) {
     const int qh = x.ai >> 1, th = x.ai & 1;
     x.Lq = p.len[qh]; x.Lr = p.lr; x.Lt = p.len[2 + th];
     const WaveAln wa = wave_aln(x.Lq, x.Lr, x.Lt);
-    SlabHap HQ(base + W.base.hap[qh], x.Lq, x.Lr);
     SlabQm M(base + W.base.qm[qh], x.Lq, x.Lr);
     WaveHapQ T(base + W.hq[qh], x.Lq, x.Lr);
     x.tinfo = base + W.ht[th];
-    x.row[0] = T.rowQ; x.row[1] = T.rowR;
-    x.hull[0] = T.hullQ; x.hull[1] = T.hullR;
-    x.optr[0] = HQ.ptr; x.optr[1] = M.rptr;
+    x.frow[0] = T.fwdQ; x.frow[1] = T.fwdR;
+    x.brow[0] = T.bwdQ; x.brow[1] = T.bwdR;
     x.tab[0] = M.toQ; x.tab[1] = M.toR;
     x.F = base + W.aln[x.ai] + wa.oF;
     x.band = (int4 *)(base + W.aln[x.ai] + wa.oBand);
@@ -95,115 +96,168 @@ __device__ inline int band_score_lb(const BatchDev &in, int sc, int ai, int Lr, 
     return best;
 }
 
-// static data of the K rows of block blk for the forward sweep: swap sources (RowRec::swi) and bases
-// and, into the warp's shared-memory cache, their row-step hulls turned into the first / last column in which
-// the row can still finish within the bound at distance 0: cmin = Lt-1-hi, cmax = Lt-1-lo
-template <int K> __device__ __forceinline__ void band_load_rows(const RowRec *rows, const int2 *hull, int len, int blk, int Lt,
-                                                                u32 (&swi)[K], u32 (&chw)[K], int2 *hcache) {
-#pragma unroll
-    for (int j = 0; j < K; j++) {
-        const int a = blk * K + j;
-        if (a < len) {
-            const uint4 r = *(const uint4 *)(rows + a);
-            swi[j] = r.x; chw[j] = r.w;
-            const int2 hb = hull[a];
-            hcache[j] = make_int2(hb.y >= INF / 2 ? -INF : Lt - 1 - hb.y, Lt - 1 - hb.x);
-        } else { swi[j] = 0; chw[j] = 0xffffu; }
+// several swap sources for one destination row (an insertion's first base, adjacent deletions): the smallest
+// value wins, the larger row on equal values, and the tie is recorded (src/dist.cpp:347, :376 keep the last
+// writer, whose identity depends on hash-set order).  src: the row's source list, src[0] already looked at.
+__device__ VD_NOINLINE int2 band_swap_multi(const int *src, int cnt, const int *rprev_o, int pblo_o, int K, int best) {
+    int sb = 0;
+    const int W = 32 * K;
+    for (int k = 1; k < cnt; k++) {
+        const int s = src[k];
+        int v = INF;
+        if ((unsigned)(s / K - pblo_o) < 32u) v = rprev_o[s & (W - 1)];
+        if (v < best) { best = v; sb = k << F_K_SHIFT; }
+        else if (v == best && v < INF / 2) sb = (k << F_K_SHIFT) | F_TIE;   // keep the larger row
     }
+    return make_int2(best, sb);
 }
+
+// ------------------------------------------------------------------------------------------
+// One plane's per-row records streaming through a shared-memory ring of NS 32-row chunks (512 bytes each):
+// the chunk is the unit of the TMA bulk copy, slot = chunk % NS, one mbarrier per slot.  All members are
+// warp-uniform; lane 0 issues the copies, every lane waits on the barrier of a chunk before its first use.
+// DESC: the sweep moves towards lower rows (backward kernel).
+// ------------------------------------------------------------------------------------------
+template <int NS, bool DESC>
+struct RowStream {
+    const uint4 *src;                 // global array, 16 bytes a row, padded to whole chunks
+    uint4 *ring;                      // shared: NS * 32 rows
+    unsigned long long *bar;          // shared: NS mbarriers
+    int nchunk;
+    int vlo, vhi;                     // chunks issued and not overwritten since: [vlo, vhi], empty when vlo > vhi
+    int wlo, whi;                     // of those, the chunks already waited for: [wlo, whi]
+    unsigned phase;                   // per slot: parity of its next completion
+
+    __device__ __forceinline__ void init(const void *s, uint4 *r, unsigned long long *b, int rows) {
+        src = (const uint4 *)s; ring = r; bar = b; nchunk = (rows + 31) >> 5;
+        vlo = wlo = 0; vhi = whi = -1; phase = 0;
+    }
+    __device__ __forceinline__ void issue(int ch, int lane) {
+        if (lane == 0) VD_BULK_G2S(ring + (ch & (NS - 1)) * 32, src + (int64_t)ch * 32, 512u, bar + (ch & (NS - 1)));
+    }
+    __device__ __forceinline__ void wait(int ch) {
+        const int slot = ch & (NS - 1);
+        VD_MBAR_WAIT(bar + slot, (phase >> slot) & 1u);
+        phase ^= 1u << slot;
+    }
+    // rows [lo, hi] must be readable on return; up to `pref` further chunks are requested ahead of the sweep
+    __device__ __forceinline__ void need(int lo, int hi, int lane, int pref) {
+        const int cl = lo >> 5, ch = hi >> 5;
+        const bool restart = vlo > vhi || (DESC ? (ch > vhi || ch < vlo - 1) : (cl < vlo || cl > vhi + 1));
+        if (restart) {
+            if (!DESC) { while (whi < vhi) wait(++whi); } else { while (wlo > vlo) wait(--wlo); }   // drain: keep the parities in step
+            if (!DESC) { vlo = wlo = cl; vhi = whi = cl - 1; } else { vhi = whi = ch; vlo = wlo = ch + 1; }
+        }
+        if (!DESC) {
+            if (cl > vlo) { vlo = cl; if (wlo < vlo) wlo = vlo; }                                   // chunks below the window may be overwritten
+            const int target = min(nchunk - 1, ch + pref);
+            while (vhi < target && vhi + 1 - vlo < NS) issue(++vhi, lane);
+            while (whi < ch) wait(++whi);
+        } else {
+            if (ch < vhi) { vhi = ch; if (whi > vhi) whi = vhi; }
+            const int target = max(0, cl - pref);
+            while (vlo > target && vhi - (vlo - 1) < NS) issue(--vlo, lane);
+            while (wlo > cl) wait(--wlo);
+        }
+    }
+};
+
+template <int K> struct BandCfg {
+    static constexpr int W = 32 * K;                               // rows of a window
+    static constexpr int R = 2 * W > 128 ? 2 * W : 128;            // rows of the record ring
+    static constexpr int NS = R / 32;
+    static constexpr int PREF = NS - (K + 1) < K ? NS - (K + 1) : K;   // chunks requested ahead of the window
+    // per warp: value ring [2 parities][2 planes][W] ints, record ring [2 planes][R] x 16 B, band chunks [2][32] x 16 B, barriers
+    static constexpr int SMEM = 16 * W + 32 * R + 1024 + 16 * NS;
+};
 
 // ------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------
 template <int K>
-__global__ void __launch_bounds__(32 * BAND_WARPS) band_fwd_kernel(WaveArgs A, int n_items, int *state, const int *lbound) {
+__global__ void __launch_bounds__(32 * BAND_WARPS) band_fwd_kernel(WaveArgs A, int n_items, int *state, const int *lbound, int tau_rung, int last_rung) {
     VD_DYN_SHARED(smem_raw);
+    typedef BandCfg<K> C;
     constexpr unsigned FULL = 0xffffffffu;
-    constexpr int W = 32 * K;
+    constexpr int W = C::W, R = C::R, NS = C::NS;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int idx = n_items - 1 - (blockIdx.x * BAND_WARPS + warp);          // biggest shape classes first
     if (idx < 0) return;
     if (state[idx] != BAND_PENDING) return;
     const BandCtx X = band_ctx(A, A.items[idx]);
-    if (K > X.kmax) { if (lane == 0) state[idx] = BAND_DENSE; return; }
     const int len[2] = {X.Lq, X.Lr};
     const bool unbounded = (X.Lq + K - 1) / K <= 32 && (X.Lr + K - 1) / K <= 32;
-    const int tau = unbounded ? INF : band_tau(K);
-    if (!unbounded && lbound[idx] > tau) {                                    // this rung cannot succeed
-        if (K == 16 && lane == 0) state[idx] = BAND_DENSE;
+    const int tau = unbounded ? INF : tau_rung;
+    if (K > X.kmax || max(X.Lq, X.Lr) >= BAND_ROW_LIMIT || (!unbounded && lbound[idx] > tau)) {   // this rung cannot take it
+        if (last_rung && lane == 0) state[idx] = BAND_DENSE;
         return;
     }
-    int *ring = (int *)smem_raw + warp * (8 * W);                             // [column parity][plane][W]: D of the previous column
-    int2 *hcache = (int2 *)(ring + 4 * W);                                    // [plane][W]: column range in which a row can still finish
+    u8 *sm = smem_raw + warp * C::SMEM;
+    int *ring = (int *)sm;                                                    // [column parity][plane][W]: D of the previous column
+    uint4 *srow = (uint4 *)(sm + 16 * W);                                     // [plane][R]: FwdRow records
+    unsigned long long *bars = (unsigned long long *)(sm + 16 * W + 32 * R + 1024);
+    if (lane == 0) for (int i = 0; i < 2 * NS; i++) VD_MBAR_INIT(bars + i, 1);
+    VD_MBAR_INIT_FENCE();
+    __syncwarp();
+    RowStream<NS, false> strm[2];
+    strm[0].init(X.frow[0], srow, bars, X.Lq);
+    strm[1].init(X.frow[1], srow + R, bars + NS, X.Lr);
     u8 *F = X.F;
     const int WS = 32 * X.kmax;                                               // row stride of the flag storage (sized for kmax)
 
     int blk[2] = {lane, lane};                                                // the window starts at block 0
     int Dp[2][K];
-    u32 swi[2][K], chw[2][K];
 #pragma unroll
-    for (int P = 0; P < 2; P++) {
-        band_load_rows<K>(X.row[P], X.hull[P], len[P], blk[P], X.Lt, swi[P], chw[P], hcache + P * W + lane * K);
+    for (int P = 0; P < 2; P++)
 #pragma unroll
         for (int j = 0; j < K; j++) Dp[P][j] = INF;
-    }
-    int liveLo[2] = {INF, INF}, liveHi[2] = {-1, -1}, dmin = 0;
+    int nextLo[2] = {0, 0}, nextHi[2] = {0, 0}, dmin = 0;                     // rows reached from the kept cells of the previous column
     int pblo[2] = {0, 0};                                                     // first block of the previous column's window
     bool pvalid[2] = {false, false};                                          // the ring holds the plane's previous column
     bool failed = false;
-    int tnext = X.tinfo[0];
+    // truth bases in 32-column chunks: one coalesced load per chunk, a chunk ahead
+    int tchunk = lane < X.Lt ? X.tinfo[lane] : 0, tchunk_next = 32 + lane < X.Lt ? X.tinfo[32 + lane] : 0;
     for (int c = 0; c < X.Lt; c++) {
-        const int tin = tnext;
-        if (c + 1 < X.Lt) tnext = X.tinfo[c + 1];
+        if ((c & 31) == 0 && c) { tchunk = tchunk_next; tchunk_next = c + 32 + lane < X.Lt ? X.tinfo[c + 32 + lane] : 0; }
+        const int tin = __shfl_sync(FULL, tchunk, c & 31);
         const int tch = tin & 0x7f;
         const bool tok = tin & 0x80;
         // ---- candidate rows of both planes (plane-local, inclusive) ----
         int cLo[2], cHi[2];
-        if (c == 0 || unbounded) {
-            cLo[0] = cLo[1] = 0;
-            cHi[0] = unbounded ? X.Lq - 1 : min(tau, X.Lq - 1);
-            cHi[1] = unbounded ? X.Lr - 1 : min(tau, X.Lr - 1);
-        } else {
-            const bool hq = liveHi[0] >= liveLo[0], hr = liveHi[1] >= liveLo[1];
-            if (!hq && !hr) { failed = true; break; }                         // nothing within tau is left
-            int lo0 = INF, hi0 = -1, lo1 = INF, hi1 = -1;
-            if (hq) { lo0 = liveLo[0]; hi0 = liveHi[0] + 1; lo1 = X.optr[0][liveLo[0]] + 1; hi1 = X.optr[0][liveHi[0]] + 1; }
-            if (hr) {
-                lo1 = min(lo1, liveLo[1]); hi1 = max(hi1, liveHi[1] + 1);
-                lo0 = min(lo0, X.optr[1][liveLo[1]] + 1); hi0 = max(hi0, X.optr[1][liveHi[1]] + 1);
-            }
-            const int ext = tau - dmin;                                       // the in-column insertion chain reaches this far
-            cLo[0] = max(lo0, 0); cHi[0] = min(hi0 + ext, X.Lq - 1);
-            cLo[1] = max(lo1, 0); cHi[1] = min(hi1 + ext, X.Lr - 1);
-        }
         bool has[2];
         int blo[2];
 #pragma unroll
         for (int P = 0; P < 2; P++) {
+            if (c == 0 || unbounded) { cLo[P] = 0; cHi[P] = unbounded ? len[P] - 1 : min(tau, len[P] - 1); }
+            else { cLo[P] = max(nextLo[P], 0); cHi[P] = min(nextHi[P] + (tau - dmin), len[P] - 1); }   // + the in-column insertion chain
             has[P] = cHi[P] >= cLo[P];
             blo[P] = has[P] ? cLo[P] / K : pblo[P];
-            if (has[P] && cHi[P] / K - blo[P] > 31) failed = true;            // band wider than the window
+            if (has[P] && cHi[P] / K - blo[P] > 31) failed = true;            // kept cells further apart than the window
         }
+        if (!unbounded && c > 0 && !has[0] && !has[1]) failed = true;         // nothing within the bound is left
+#ifdef VD_BAND_DEBUG
+        if (failed && lane == 0) printf("  fail at c=%d cand Q[%d,%d] R[%d,%d]\n", c, cLo[0], cHi[0], cLo[1], cHi[1]);
+#endif
         if (failed) break;
         if (lane == 0) X.band[c] = make_int4(has[0] ? cLo[0] : 1, has[0] ? cHi[0] : 0, has[1] ? cLo[1] : 1, has[1] ? cHi[1] : 0);
-        const int *rprev = ring + ((c + 1) & 1) * 2 * W, *rcur_c = ring + (c & 1) * 2 * W;
+        const int *rprev = ring + ((c + 1) & 1) * 2 * W;
         int *rcur = ring + (c & 1) * 2 * W;
-        (void)rcur_c;
         int nlo[2] = {INF, INF}, nhi[2] = {-1, -1}, ndmin = INF;
 #pragma unroll
         for (int P = 0; P < 2; P++) {
-            if (!has[P]) {                                                    // plane without candidates: nothing live in this column
+            if (!has[P]) {                                                    // plane without candidates: nothing kept in this column
                 if (pvalid[P] || c == 0) {
 #pragma unroll
                     for (int j = 0; j < K; j++) Dp[P][j] = INF;
                 }
                 continue;
             }
+            strm[P].need(cLo[P], cHi[P], lane, C::PREF);
+            const uint4 *rows = srow + P * R;
             // ---- my block in this column's window ----
             const int nb = blo[P] + ((lane - blo[P]) & 31);
             if (nb != blk[P]) {
                 blk[P] = nb;
-                band_load_rows<K>(X.row[P], X.hull[P], len[P], nb, X.Lt, swi[P], chw[P], hcache + P * W + lane * K);
 #pragma unroll
                 for (int j = 0; j < K; j++) Dp[P][j] = INF;
             }
@@ -214,24 +268,17 @@ __global__ void __launch_bounds__(32 * BAND_WARPS) band_fwd_kernel(WaveArgs A, i
             // D[a0-1][c-1] from the lane holding the block below mine
             int up = __shfl_sync(FULL, Dp[P][K - 1], (lane - 1) & 31);
             if (li == 0) up = INF;
+            u32 w0[K];                                                        // swap source | count << 20 | base << 24 of my candidate rows
             auto swap_eval = [&](const int j, int &best, int &sb) {
-                const u32 w = swi[P][j];
-                const int cnt = (int)(w >> 24);
+                const u32 w = w0[j];
+                const int cnt = (int)((w >> 20) & 15u);
                 best = INF; sb = 0;
                 if (cnt && pvalid[o]) {
-                    const int s0 = (int)(w & 0xffffffu);
-                    const unsigned bo = (unsigned)(s0 / K - pblo[o]);
-                    if (bo < 32u) best = rprev[o * W + (s0 & (W - 1))];
+                    const int s0 = (int)(w & 0xfffffu);
+                    if ((unsigned)(s0 / K - pblo[o]) < 32u) best = rprev[o * W + (s0 & (W - 1))];
                     if (cnt > 1) {                                            // rare: insertion / adjacent deletions (:347, :376)
-                        const int *tab = X.tab[P];
-                        const int k0 = tab[a0 + j];
-                        for (int k = 1; k < cnt; k++) {
-                            const int s = tab[len[P] + 1 + k0 + k];
-                            int v = INF;
-                            if ((unsigned)(s / K - pblo[o]) < 32u) v = rprev[o * W + (s & (W - 1))];
-                            if (v < best) { best = v; sb = k << F_K_SHIFT; }
-                            else if (v == best && v < INF / 2) sb = (k << F_K_SHIFT) | F_TIE;   // keep the larger row
-                        }
+                        const int2 r = band_swap_multi(X.tab[P] + len[P] + 1 + X.tab[P][a0 + j], cnt, rprev + o * W, pblo[o], K, best);
+                        best = r.x; sb = r.y;
                     }
                 }
             };
@@ -242,7 +289,9 @@ __global__ void __launch_bounds__(32 * BAND_WARPS) band_fwd_kernel(WaveArgs A, i
 #pragma unroll
                 for (int j = 0; j < K; j++) {
                     const int a = a0 + j;
-                    const bool m = (int)(chw[P][j] & 0xff) == tch;
+                    const bool cand = a >= cLo[P] && a <= cHi[P];
+                    w0[j] = cand ? rows[a & (R - 1)].x : 0xff000000u;
+                    const bool m = (int)(w0[j] >> 24) == tch;
                     int b;
                     if (a == 0 && c == 0) b = 0;                              // both origins start at 0 (:299-305)
                     else {
@@ -254,7 +303,7 @@ __global__ void __launch_bounds__(32 * BAND_WARPS) band_fwd_kernel(WaveArgs A, i
                             b = min(b, best);
                         }
                     }
-                    if (a < cLo[P] || a > cHi[P]) b = INF;
+                    if (!cand) b = INF;
                     run = min(b, run + 1);                                    // insertion chain (:397-404)
                     if (run > INF) run = INF;
                     Dc[j] = run;
@@ -262,7 +311,7 @@ __global__ void __launch_bounds__(32 * BAND_WARPS) band_fwd_kernel(WaveArgs A, i
                 }
             } else {
 #pragma unroll
-                for (int j = 0; j < K; j++) Dc[j] = INF;
+                for (int j = 0; j < K; j++) { Dc[j] = INF; w0[j] = 0xff000000u; }
             }
             // ---- min-plus prefix scan of G = D(last row) - (last row) over the blocks of the window ----
             int incl = (act && Dc[K - 1] < INF / 2) ? Dc[K - 1] - (a0 + K - 1) : INF;
@@ -274,10 +323,10 @@ __global__ void __launch_bounds__(32 * BAND_WARPS) band_fwd_kernel(WaveArgs A, i
             int carry = __shfl_sync(FULL, incl, (lane - 1) & 31);
             if (li == 0) carry = INF;
             // ---- pass 2: final values and flags ----
-            u32 fw[(K + 3) / 4];
-#pragma unroll
-            for (int i = 0; i < (K + 3) / 4; i++) fw[i] = 0;
             if (act) {
+                u32 fw[(K + 3) / 4];
+#pragma unroll
+                for (int i = 0; i < (K + 3) / 4; i++) fw[i] = 0;
                 int prevD = carry >= INF / 2 ? INF : carry + (a0 - 1);        // D[a0-1][c]
                 int upj = up;
 #pragma unroll
@@ -289,7 +338,7 @@ __global__ void __launch_bounds__(32 * BAND_WARPS) band_fwd_kernel(WaveArgs A, i
                     if (a >= cLo[P] && a <= cHi[P] && d < INF / 2) {
                         if (a == 0 && c == 0) f = F_DIAG;
                         else {
-                            const bool m = (int)(chw[P][j] & 0xff) == tch;
+                            const bool m = (int)(w0[j] >> 24) == tch;
                             if (a > 0 && c > 0 && upj + (m ? 0 : 1) == d) f |= F_DIAG;
                             if (a > 0 && prevD + 1 == d) f |= F_INS;
                             if (c > 0 && Dp[P][j] + 1 == d) f |= F_DEL;
@@ -299,11 +348,16 @@ __global__ void __launch_bounds__(32 * BAND_WARPS) band_fwd_kernel(WaveArgs A, i
                                 if (best == d) f |= F_SWP | sb;
                             }
                         }
-                        if (d <= tau) {
-                            // within the bound AND able to finish within it (remaining cost >= distance of c to the
-                            // row's column range, see wave_row_hulls)
-                            const int2 cr = hcache[P * W + lane * K + j];
-                            if (unbounded || (c >= cr.x - (tau - d) && c <= cr.y + (tau - d))) { nlo[P] = min(nlo[P], a); nhi[P] = a; ndmin = min(ndmin, d); }
+                        if (!unbounded && d <= tau) {
+                            // kept: within the bound AND able to finish within it (wave_row_hulls: with rc truth bases
+                            // left the remaining cost is at least max(0, rc - hhi, hlo - rc))
+                            const uint4 rec = rows[a & (R - 1)];
+                            const int rc = X.Lt - 1 - c, slack = tau - d;
+                            if (rc - (int)rec.w <= slack && (int)rec.z - rc <= slack) {
+                                nlo[P] = min(nlo[P], a); nhi[P] = max(nhi[P], a + 1); ndmin = min(ndmin, d);
+                                const int fd = (int)rec.y;                    // my row as a swap source: candidate on the other plane
+                                if (fd >= 0) { nlo[o] = min(nlo[o], fd); nhi[o] = max(nhi[o], fd); }
+                            }
                         }
                     } else d = INF;
                     fw[j >> 2] |= (u32)f << ((j & 3) * 8);
@@ -319,25 +373,23 @@ __global__ void __launch_bounds__(32 * BAND_WARPS) band_fwd_kernel(WaveArgs A, i
 #pragma unroll
             for (int j = 0; j < K; j++) rcur[P * W + lane * K + j] = Dp[P][j];
         }
-        // ---- rows within tau: the next column's candidates come from them ----
+        // ---- the next column's candidates: successors of the kept cells (same row, row + 1, swap destinations) ----
 #pragma unroll
-        for (int P = 0; P < 2; P++) {
-            pvalid[P] = has[P];
-            pblo[P] = blo[P];
-            if (!unbounded) {
-                liveLo[P] = has[P] ? __reduce_min_sync(FULL, nlo[P]) : INF;
-                liveHi[P] = has[P] ? __reduce_max_sync(FULL, nhi[P]) : -1;
-            }
+        for (int P = 0; P < 2; P++) { pvalid[P] = has[P]; pblo[P] = blo[P]; }
+        if (!unbounded) {
+            nextLo[0] = __reduce_min_sync(FULL, nlo[0]); nextHi[0] = __reduce_max_sync(FULL, nhi[0]);
+            nextLo[1] = __reduce_min_sync(FULL, nlo[1]); nextHi[1] = __reduce_max_sync(FULL, nhi[1]);
+            dmin = K >= 4 ? __reduce_min_sync(FULL, ndmin) : 0;
+            if (dmin > tau) dmin = tau;
         }
-        if (!unbounded) dmin = __reduce_min_sync(FULL, ndmin);
         __syncwarp();                                                         // ring of this column visible to all lanes
     }
 #ifdef VD_BAND_DEBUG
-    if (lane == 0) printf("band_fwd K=%d idx=%d sc=%d ai=%d Lq=%d Lr=%d Lt=%d tau=%d failed=%d live Q[%d,%d] R[%d,%d] dmin=%d\n", K, idx, X.sc, X.ai, X.Lq, X.Lr, X.Lt, tau,
-                          (int)failed, liveLo[0], liveHi[0], liveLo[1], liveHi[1], dmin);
+    if (lane == 0) printf("band_fwd K=%d idx=%d sc=%d ai=%d Lq=%d Lr=%d Lt=%d tau=%d failed=%d next Q[%d,%d] R[%d,%d] dmin=%d\n", K, idx, X.sc, X.ai, X.Lq, X.Lr, X.Lt, tau,
+                          (int)failed, nextLo[0], nextHi[0], nextLo[1], nextHi[1], dmin);
 #endif
     if (failed) {
-        if (K == 16 && lane == 0) state[idx] = BAND_DENSE;
+        if (last_rung && lane == 0) state[idx] = BAND_DENSE;
         return;
     }
     // ---- score and end plane (:390-391, :436-440): the last rows of the last column, through the ring ----
@@ -346,9 +398,6 @@ __global__ void __launch_bounds__(32 * BAND_WARPS) band_fwd_kernel(WaveArgs A, i
     if (pvalid[0] && (unsigned)((X.Lq - 1) / K - pblo[0]) < 32u) dq = rl[(X.Lq - 1) & (W - 1)];
     if (pvalid[1] && (unsigned)((X.Lr - 1) / K - pblo[1]) < 32u) dr = rl[W + ((X.Lr - 1) & (W - 1))];
     const int score = min(dq, dr);
-#ifdef VD_BAND_DEBUG
-    if (lane == 0) printf("band_fwd K=%d idx=%d score=%d (dq %d dr %d)\n", K, idx, score, dq, dr);
-#endif
     if (score <= tau && score < INF / 2) {
         if (lane == 0) {
             const int64_t oi = 4 * (int64_t)X.sc + X.ai;
@@ -356,7 +405,7 @@ __global__ void __launch_bounds__(32 * BAND_WARPS) band_fwd_kernel(WaveArgs A, i
             A.out.aln_end_plane[oi] = (u8)(dq == score ? 0 : 1);
             state[idx] = K;
         }
-    } else if (K == 16 && lane == 0) state[idx] = BAND_DENSE;
+    } else if (last_rung && lane == 0) state[idx] = BAND_DENSE;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -365,8 +414,10 @@ __global__ void __launch_bounds__(32 * BAND_WARPS) band_fwd_kernel(WaveArgs A, i
 template <int K>
 __global__ void __launch_bounds__(32 * BAND_WARPS) band_bwd_kernel(WaveArgs A, int n_items, const int *state) {
     VD_DYN_SHARED(smem_raw);
+    typedef BandCfg<K> C;
     constexpr unsigned FULL = 0xffffffffu;
-    constexpr int W = 32 * K;
+    constexpr int W = C::W, R = C::R, NS = C::NS;
+    constexpr int PFD = 6;                                                    // columns the flag prefetch runs ahead
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int idx = n_items - 1 - (blockIdx.x * BAND_WARPS + warp);
     if (idx < 0) return;
@@ -375,7 +426,17 @@ __global__ void __launch_bounds__(32 * BAND_WARPS) band_bwd_kernel(WaveArgs A, i
     const int len[2] = {X.Lq, X.Lr};
     const int64_t oi = 4 * (int64_t)X.sc + X.ai;
     const int end_plane = A.out.aln_end_plane[oi];
-    int *ring = (int *)smem_raw + warp * (4 * W);                             // [column parity][plane][W]: (T << 8) | forward flags
+    u8 *sm = smem_raw + warp * C::SMEM;
+    int *ring = (int *)sm;                                                    // [column parity][plane][W]: T * 256 + forward flags
+    uint4 *srow = (uint4 *)(sm + 16 * W);                                     // [plane][R]: BwdRow records
+    int4 *bandbuf = (int4 *)(sm + 16 * W + 32 * R);                           // [chunk parity][32]: band records of 32 columns
+    unsigned long long *bars = (unsigned long long *)(sm + 16 * W + 32 * R + 1024);
+    if (lane == 0) for (int i = 0; i < 2 * NS; i++) VD_MBAR_INIT(bars + i, 1);
+    VD_MBAR_INIT_FENCE();
+    __syncwarp();
+    RowStream<NS, true> strm[2];
+    strm[0].init(X.brow[0], srow, bars, X.Lq);
+    strm[1].init(X.brow[1], srow + R, bars + NS, X.Lr);
     u8 *F = X.F;
     const int WS = 32 * X.kmax;
     u32 status = 0;
@@ -383,29 +444,49 @@ __global__ void __launch_bounds__(32 * BAND_WARPS) band_bwd_kernel(WaveArgs A, i
     int blk[2] = {-1, -1};
     int Tn[2][K];                                                             // T of column c+1, my rows
     u32 Fn[2][(K + 3) / 4];                                                   // forward flags of column c+1, my rows
-    u32 si[2][K], tw[2][K];                                                   // my rows as swap sources; tps | tp(a) << 24 | tp(a+1) << 25
-    u32 chn[2][(K + 3) / 4];                                                  // bases of rows a+1
 #pragma unroll
     for (int P = 0; P < 2; P++) {
 #pragma unroll
-        for (int j = 0; j < K; j++) { Tn[P][j] = -1; si[P][j] = 0; tw[P][j] = 0; }
+        for (int j = 0; j < K; j++) Tn[P][j] = -1;
 #pragma unroll
-        for (int i = 0; i < (K + 3) / 4; i++) { Fn[P][i] = 0; chn[P][i] = 0xffffffffu; }
+        for (int i = 0; i < (K + 3) / 4; i++) Fn[P][i] = 0;
     }
     int nblo[2] = {0, 0};                                                     // first block of column c+1's window
     bool nvalid[2] = {false, false};
-    int4 bd = X.band[X.Lt - 1];
+    // band records and truth bases in 32-column chunks, a chunk ahead
+    const int cc0 = (X.Lt - 1) >> 5;
+    {
+        const int col = cc0 * 32 + lane;
+        bandbuf[(cc0 & 1) * 32 + lane] = col < X.Lt ? X.band[col] : make_int4(1, 0, 1, 0);
+    }
+    int4 bnext = cc0 > 0 ? X.band[(cc0 - 1) * 32 + lane] : make_int4(1, 0, 1, 0);
+    int tchunk = cc0 * 32 + lane < X.Lt ? X.tinfo[cc0 * 32 + lane] : 0, tchunk_next = cc0 > 0 ? X.tinfo[(cc0 - 1) * 32 + lane] : 0;
+    __syncwarp();
     int tch_next = 0;
     for (int c = X.Lt - 1; c >= 0; c--) {
         const bool last = c == X.Lt - 1;
+        const int cc = c >> 5;
+        if ((c & 31) == 31 && !last) {                                        // entering chunk cc: its records were requested a chunk ago
+            bandbuf[(cc & 1) * 32 + lane] = bnext;
+            tchunk = tchunk_next;
+            if (cc > 0) { bnext = X.band[(cc - 1) * 32 + lane]; tchunk_next = X.tinfo[(cc - 1) * 32 + lane]; }
+            __syncwarp();
+        }
+        const int4 bd = bandbuf[(cc & 1) * 32 + (c & 31)];
         const int cLo[2] = {bd.x, bd.z}, cHi[2] = {bd.y, bd.w};
-        if (c > 0) bd = X.band[c - 1];
         const int *rnext = ring + ((c + 1) & 1) * 2 * W;
         int *rcur = ring + (c & 1) * 2 * W;
         bool has[2];
         int blo[2];
 #pragma unroll
         for (int P = 0; P < 2; P++) { has[P] = cHi[P] >= cLo[P]; blo[P] = has[P] ? cLo[P] / K : nblo[P]; }
+#ifndef VD_EMU
+        if (c >= PFD) {                                                       // the flag bytes of my slots PFD columns ahead (the slot does not depend on the window)
+            const u8 *pf = F + ((int64_t)(c - PFD) * 2) * WS + lane * K;
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(pf));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(pf + WS));
+        }
+#endif
 #pragma unroll
         for (int P = 0; P < 2; P++) {
             if (!has[P]) {                                                    // nothing of this plane is on any path through column c
@@ -415,6 +496,8 @@ __global__ void __launch_bounds__(32 * BAND_WARPS) band_bwd_kernel(WaveArgs A, i
                 for (int i = 0; i < (K + 3) / 4; i++) Fn[P][i] = 0;
                 continue;
             }
+            strm[P].need(cLo[P], cHi[P], lane, C::PREF);
+            const uint4 *rows = srow + P * R;
             const int o = 1 - P;
             const int nb = blo[P] + ((lane - blo[P]) & 31);
             // (row a0+K, column c+1) lives on the next lane if it held block nb+1 in column c+1
@@ -425,36 +508,34 @@ __global__ void __launch_bounds__(32 * BAND_WARPS) band_bwd_kernel(WaveArgs A, i
             if (nb != blk[P]) {
                 blk[P] = nb;
 #pragma unroll
-                for (int j = 0; j < K; j++) {
-                    const int a = nb * K + j;
-                    u32 cw = 0xff;
-                    if (a < len[P]) {
-                        const uint4 r = *(const uint4 *)(X.row[P] + a);
-                        si[P][j] = r.y; tw[P][j] = r.z; cw = (r.w >> 8) & 0xff;
-                    } else { si[P][j] = 0; tw[P][j] = 0; }
-                    chn[P][j >> 2] = (chn[P][j >> 2] & ~(0xffu << ((j & 3) * 8))) | (cw << ((j & 3) * 8));
-                    Tn[P][j] = -1;
-                }
+                for (int j = 0; j < K; j++) Tn[P][j] = -1;
 #pragma unroll
                 for (int i = 0; i < (K + 3) / 4; i++) Fn[P][i] = 0;
             }
             const int li = nb - blo[P];
             const int a0 = nb * K;
             const bool act = a0 <= cHi[P] && a0 + K - 1 >= cLo[P];
-            // forward flags of my rows in column c (only rows of the band hold valid flags)
+            // forward flags of my rows in column c (only rows of the band hold valid flags) and their records
             u32 Fc[(K + 3) / 4];
 #pragma unroll
             for (int i = 0; i < (K + 3) / 4; i++) Fc[i] = 0;
+            u32 si[K], tw[K], chn[K];
             if (act) {
                 load_flags<K>(F + ((int64_t)c * 2 + P) * WS + (a0 & (W - 1)), Fc);
 #pragma unroll
-                for (int j = 0; j < K; j++)
-                    if (a0 + j < cLo[P] || a0 + j > cHi[P]) Fc[j >> 2] &= ~(0xffu << ((j & 3) * 8));
+                for (int j = 0; j < K; j++) {
+                    const int a = a0 + j;
+                    if (a < cLo[P] || a > cHi[P]) { Fc[j >> 2] &= ~(0xffu << ((j & 3) * 8)); si[j] = 0; tw[j] = 0; chn[j] = 0xff; }
+                    else { const uint4 rec = rows[a & (R - 1)]; si[j] = rec.x; tw[j] = rec.y; chn[j] = rec.z; }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < K; j++) { si[j] = 0; tw[j] = 0; chn[j] = 0xff; }
             }
             // flag of row a0+K in column c (the link into my last row): the next lane's first row
             int FcUp = __shfl_sync(FULL, (int)(Fc[0] & 0xff), (lane + 1) & 31);
             if (li == 31) FcUp = 0;
-            // ---- pass 1: candidates from column c+1, local chain in potential form U = T - S ----
+            // ---- pass 1: candidates from column c+1 ----
             int B[K];
             int swv[K];
 #pragma unroll
@@ -467,10 +548,10 @@ __global__ void __launch_bounds__(32 * BAND_WARPS) band_bwd_kernel(WaveArgs A, i
                     if (!last) {
                         const int Tx = (j == K - 1) ? Tup : Tn[P][j == K - 1 ? j : j + 1];
                         const int Fx = (j == K - 1) ? Fup : byte_of(Fn[P], j == K - 1 ? j : j + 1);
-                        const int tpn = (int)((tw[P][j] >> 25) & 1);
+                        const int tpn = (int)((tw[j] >> 25) & 1);
                         if (a + 1 < len[P] && Tx >= 0 && (Fx & F_DIAG)) b = max(b, Tx + tpn);      // :556-595, :692-731
                         if (Tn[P][j] >= 0 && (byte_of(Fn[P], j) & F_DEL)) b = max(b, Tn[P][j]);  // :774-804
-                        const u32 s = si[P][j];
+                        const u32 s = si[j];
                         if ((s & 1) && nvalid[o]) {                                               // :598-679
                             const int d = (int)(s >> 8);
                             if ((unsigned)(d / K - nblo[o]) < 32u) {
@@ -494,10 +575,10 @@ __global__ void __launch_bounds__(32 * BAND_WARPS) band_bwd_kernel(WaveArgs A, i
                 const int fb = (j == K - 1) ? FcUp : byte_of(Fc, j == K - 1 ? j : j + 1);
                 if ((fb & F_INS) && a0 + j + 1 < len[P]) links |= 1u << j;
             }
-            int head = NEG;                                                   // U of row a0 without anything arriving from above
+            int head = NEG;                                                   // U = T - S of row a0 without anything arriving from above
 #pragma unroll
             for (int j = K - 1; j >= 0; j--) {
-                const int bu = B[j] >= 0 ? B[j] - (int)(tw[P][j] & 0xffffffu) : NEG;
+                const int bu = B[j] >= 0 ? B[j] - (int)(tw[j] & 0xffffffu) : NEG;
                 head = (j < K - 1 && ((links >> j) & 1)) ? max(bu, head) : bu;
             }
             // ---- link-segmented suffix max of the block heads over the window ----
@@ -526,8 +607,8 @@ __global__ void __launch_bounds__(32 * BAND_WARPS) band_bwd_kernel(WaveArgs A, i
                 for (int j = K - 1; j >= 0; j--) {
                     const int a = a0 + j;
                     const bool lk = (links >> j) & 1;
-                    const int S = (int)(tw[P][j] & 0xffffffu);
-                    const int tpn = (int)((tw[P][j] >> 25) & 1);
+                    const int S = (int)(tw[j] & 0xffffffu);
+                    const int tpn = (int)((tw[j] >> 25) & 1);
                     const int bu = B[j] >= 0 ? B[j] - S : NEG;
                     const int u = (lk && uin > NEG / 2) ? max(bu, uin) : bu;
                     const int Tv = u > NEG / 2 ? u + S : -1;
@@ -539,7 +620,7 @@ __global__ void __launch_bounds__(32 * BAND_WARPS) band_bwd_kernel(WaveArgs A, i
                             const int Tx = (j == K - 1) ? Tup : Tn[P][j == K - 1 ? j : j + 1];
                             const int Fx = (j == K - 1) ? Fup : byte_of(Fn[P], j == K - 1 ? j : j + 1);
                             if (a + 1 < len[P] && Tx >= 0 && (Fx & F_DIAG) && Tx + tpn == Tv)
-                                pf |= (byte_of(chn[P], j) == tch_next) ? PTR_MAT : PTR_SUB;
+                                pf |= ((int)chn[j] == tch_next) ? PTR_MAT : PTR_SUB;
                             if (Tn[P][j] >= 0 && (byte_of(Fn[P], j) & F_DEL) && Tn[P][j] == Tv) pf |= PTR_DEL;
                             if (swv[j] >= 0 && swv[j] == Tv) pf |= PTR_SWP;
                         }
@@ -562,7 +643,7 @@ __global__ void __launch_bounds__(32 * BAND_WARPS) band_bwd_kernel(WaveArgs A, i
         }
 #pragma unroll
         for (int P = 0; P < 2; P++) { nvalid[P] = has[P]; nblo[P] = blo[P]; }
-        tch_next = X.tinfo[c] & 0x7f;
+        tch_next = __shfl_sync(FULL, tchunk, c & 31) & 0x7f;
         __syncwarp();
     }
     // origin plane (:811-814): QUERY if its origin was reached
@@ -626,23 +707,28 @@ __global__ void band_walk_kernel(WaveArgs A, int n_items, const int *state, int 
     A.out.status[4 * (int64_t)sc + ai] = status;
 }
 
-// items the band kernels gave up on (or never tried): input of the dense phase
-__global__ void band_count_dense_kernel(const int *state, int n_items, int *n_dense) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool d = i < n_items && state[i] <= 0;
-    const unsigned m = __ballot_sync(0xffffffffu, d);
-    if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_dense, __popc(m));
-}
-
-template <int K> inline void band_launch(cudaStream_t st, const WaveArgs &A, int n_items, int *state, const int *lbound, bool fwd) {
+template <int K> inline void band_launch(cudaStream_t st, const WaveArgs &A, int n_items, int *state, const int *lbound, bool fwd, int tau, int last) {
     if (n_items <= 0) return;
-    const int nb = (n_items + BAND_WARPS - 1) / BAND_WARPS, sm = BAND_WARPS * 4 * 32 * K * 4;
-    if (fwd) VD_LAUNCH(band_fwd_kernel<K>, nb, 32 * BAND_WARPS, 2 * sm, st, A, n_items, state, lbound);
+    const int nb = (n_items + BAND_WARPS - 1) / BAND_WARPS, sm = BAND_WARPS * BandCfg<K>::SMEM;
+    if (fwd) VD_LAUNCH(band_fwd_kernel<K>, nb, 32 * BAND_WARPS, sm, st, A, n_items, state, lbound, tau, last);
     else VD_LAUNCH(band_bwd_kernel<K>, nb, 32 * BAND_WARPS, sm, st, A, n_items, (const int *)state);
 }
+inline void band_launch_rung(cudaStream_t st, int rung, const WaveArgs &A, int n_items, int *state, const int *lbound, bool fwd) {
+    const int tau = band_rung_tau(rung), last = rung == N_RUNG - 1;
+    switch (band_rung_k(rung)) {
+        case 1: band_launch<1>(st, A, n_items, state, lbound, fwd, tau, last); break;
+        case 2: band_launch<2>(st, A, n_items, state, lbound, fwd, tau, last); break;
+        case 4: band_launch<4>(st, A, n_items, state, lbound, fwd, tau, last); break;
+        case 8: band_launch<8>(st, A, n_items, state, lbound, fwd, tau, last); break;
+        case 16: band_launch<16>(st, A, n_items, state, lbound, fwd, tau, last); break;
+    }
+}
+template <int K> inline void band_configure_one() {
+    cudaFuncSetAttribute(band_fwd_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, BAND_WARPS * BandCfg<K>::SMEM);
+    cudaFuncSetAttribute(band_bwd_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, BAND_WARPS * BandCfg<K>::SMEM);
+}
 inline void band_configure() {
-    cudaFuncSetAttribute(band_fwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * BAND_WARPS * 4 * 32 * 16 * 4);
-    cudaFuncSetAttribute(band_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, BAND_WARPS * 4 * 32 * 16 * 4);
+    band_configure_one<1>(); band_configure_one<2>(); band_configure_one<4>(); band_configure_one<8>(); band_configure_one<16>();
 }
 
 }  // namespace vd

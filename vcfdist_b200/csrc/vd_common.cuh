@@ -2,12 +2,45 @@
 #pragma once
 #include <cstdint>
 #ifdef VD_EMU
+#define VD_NOINLINE __attribute__((noinline))
 // kernel-logic debugging on the CPU: tests/simt/simt_emu.h (force-included by tests/simt/Makefile)
 // provides the CUDA subset these sources use; never part of the product build
 #else
 #include <cuda_runtime.h>
+#define VD_NOINLINE __noinline__
 #define VD_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #define VD_DYN_SHARED(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
+
+// ---- TMA bulk copies (cp.async.bulk, the 1-D form of the tensor memory accelerator) + mbarrier ----------
+// Contiguous, 16-byte aligned ranges of HBM are pulled into shared memory by the copy engine: one lane
+// arms an mbarrier with the byte count and issues the copy, the consumers wait on the barrier's phase.
+#ifdef VD_EMU
+#define VD_MBAR_INIT(bar, count) ((void)0)
+#define VD_MBAR_INIT_FENCE() ((void)0)
+#define VD_BULK_G2S(dst, src, bytes, bar) memcpy((void *)(dst), (const void *)(src), (size_t)(bytes))
+#define VD_MBAR_WAIT(bar, parity) __syncwarp()
+#else
+namespace vd {
+__device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, void *bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void *bar, unsigned parity) {
+    asm volatile("{\n.reg .pred P1;\nVD_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n@P1 bra VD_DONE;\nbra VD_WAIT;\nVD_DONE:\n}"
+                 ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+}  // namespace vd
+#define VD_MBAR_INIT(bar, count) vd::mbar_init((bar), (count))
+#define VD_MBAR_INIT_FENCE() vd::mbar_init_fence()
+#define VD_BULK_G2S(dst, src, bytes, bar) vd::bulk_g2s((dst), (src), (bytes), (bar))
+#define VD_MBAR_WAIT(bar, parity) vd::mbar_wait((bar), (parity))
 #endif
 
 #include "vcfdist_b200.h"

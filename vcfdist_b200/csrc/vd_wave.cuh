@@ -55,14 +55,21 @@ __device__ inline void build_srcinfo(const PT *ptr, const u8 *flg, int nsrc,    
     }
 }
 
-// Packed per-row record of the banded warp kernels (vd_band.cuh): everything a lane needs about a row of
-// the QUERY or REF plane in one 16-byte load.
-struct RowRec {
-    u32 swi;             // my row as a swap DESTINATION: first source row of the other plane (bits 0-23) | count << 24
-    u32 si;              // my row as a swap SOURCE: srcinfo (bit 0 valid, bits 1-3 k, bit 4 tp(dest), bits 8.. destination row)
-    u32 tps;             // rows a' > a of my plane with tp(a') (bits 0-23) | tp(a) << 24 | tp(a+1) << 25
-    u32 chw;             // base of the row (bits 0-7) | base of row a+1 (bits 8-15, 0xff: none)
+// Packed per-row records of the banded warp kernels (vd_band.cuh), 16 bytes each so that 32 rows are one
+// 512-byte bulk copy into a warp's shared-memory ring.
+struct FwdRow {          // forward sweep
+    u32 w0;              // my row as a swap DESTINATION: first source row of the other plane (bits 0-19) | number of
+                         // sources (bits 20-23) | base of the row (bits 24-31)
+    int fdest;           // my row as a swap SOURCE of the forward sweep: ptr+1 on the other plane, -1: none (:335-337, :364-366)
+    int hlo, hhi;        // fewest / most row steps from the row to the end of either plane (wave_row_hulls)
 };
+struct BwdRow {          // backward sweep
+    u32 si;              // my row as the recorded swap source: srcinfo (bit 0 valid, bits 1-3 k, bit 4 tp(dest), bits 8.. destination row)
+    u32 tw;              // rows a' > a of my plane with tp(a') (bits 0-23) | tp(a) << 24 | tp(a+1) << 25
+    u32 chn;             // base of row a+1 (0xff: none)
+    u32 pad;
+};
+constexpr int BAND_ROW_LIMIT = 1 << 20;      // rows per plane the packed records can address
 
 struct WaveHapQ {        // extra per query hap
     int *srcQ;           // [Lq]  QUERY rows as swap sources (destinations on the REF plane)
@@ -71,16 +78,17 @@ struct WaveHapQ {        // extra per query hap
     u32 *swiR;           // [Lr]  REF rows as swap DESTINATIONS: first source (QUERY row) | count << 16
     u8 *tpb;             // [Lq]  tp(a): entering QUERY row a counts a query variant (:572-574)
     u16 *tps;            // [Lq]  number of rows a' > a with tp(a') (potential of the backward insertion chain)
-    RowRec *rowQ, *rowR; // [Lq], [Lr] packed records of the banded warp kernels
-    int2 *hullQ, *hullR; // [Lq], [Lr] fewest / most row steps from the row to the end of either plane (see wave_row_hulls)
+    FwdRow *fwdQ, *fwdR; // [Lq], [Lr] packed records of the banded warp kernels; every array is padded to whole
+    BwdRow *bwdQ, *bwdR; //            32-row chunks (the unit of the bulk copies)
     __device__ WaveHapQ(u8 *base, int Lq, int Lr) {
-        rowQ = (RowRec *)base; rowR = rowQ + Lq;
-        hullQ = (int2 *)(rowR + Lr); hullR = hullQ + Lq;
-        srcQ = (int *)(hullR + Lr); srcR = srcQ + Lq; swiQ = (u32 *)(srcR + Lr); swiR = swiQ + Lq; tpb = (u8 *)(swiR + Lr);
+        const int64_t pq = align_up(Lq, 32), pr = align_up(Lr, 32);
+        fwdQ = (FwdRow *)base; fwdR = fwdQ + pq;
+        bwdQ = (BwdRow *)(fwdR + pr); bwdR = bwdQ + pq;
+        srcQ = (int *)(bwdR + pr); srcR = srcQ + Lq; swiQ = (u32 *)(srcR + Lr); swiR = swiQ + Lq; tpb = (u8 *)(swiR + Lr);
         tps = (u16 *)(tpb + align_up(Lq, 16));
     }
 };
-__host__ __device__ inline int64_t wave_hapq_bytes(int Lq, int Lr) { return 32 * ((int64_t)Lq + Lr) + align_up(Lq, 16) + align_up(2 * (int64_t)Lq, 16); }
+__host__ __device__ inline int64_t wave_hapq_bytes(int Lq, int Lr) { return 32 * (align_up(Lq, 32) + align_up(Lr, 32)) + 8 * ((int64_t)Lq + Lr) + align_up(Lq, 16) + align_up(2 * (int64_t)Lq, 16); }
 __host__ __device__ inline int64_t wave_hapt_bytes(int Lt) { return align_up(Lt, 16); }     // tinfo: base | tok<<7
 
 // kernel shape classes: (threads per block, rows per thread)
@@ -195,7 +203,7 @@ __global__ void wave_size_kernel(const ScPlan *plan, const int *list, int n, int
 // that reach the far side of a 10 kb insertion through the REF plane at no cost but can never finish.
 // Computed backwards by merging the two planes so that every swap destination is done before its source.
 __device__ inline void wave_row_hulls(const int *qptr, const u8 *qflg, int Lq, const int *rptr, const u8 *rflg, int Lr,
-                                      int2 *hullQ, int2 *hullR) {
+                                      FwdRow *hullQ, FwdRow *hullR) {
     int a = Lq - 1, r = Lr - 1;
     while (a >= 0 || r >= 0) {
         bool okQ = false, okR = false, swQ = false, swR = false;
@@ -215,21 +223,21 @@ __device__ inline void wave_row_hulls(const int *qptr, const u8 *qflg, int Lq, c
         const bool takeQ = okQ || (!okR && a >= 0);
         if (takeQ) {
             int lo, hi;
-            if (a == Lq - 1) lo = hi = 0; else { lo = hullQ[a + 1].x + 1; hi = hullQ[a + 1].y + 1; }
+            if (a == Lq - 1) lo = hi = 0; else { lo = hullQ[a + 1].hlo + 1; hi = hullQ[a + 1].hhi + 1; }
             if (swQ) {
-                if (dQ > r) { lo = min(lo, hullR[dQ].x + 1); hi = max(hi, hullR[dQ].y + 1); }
+                if (dQ > r) { lo = min(lo, hullR[dQ].hlo + 1); hi = max(hi, hullR[dQ].hhi + 1); }
                 else { lo = 0; hi = INF; }                     // cannot happen in a DAG; no bound rather than a wrong one
             }
-            hullQ[a] = make_int2(lo, hi);
+            hullQ[a].hlo = lo; hullQ[a].hhi = hi; hullQ[a].fdest = swQ ? dQ : -1;
             a--;
         } else {
             int lo, hi;
-            if (r == Lr - 1) lo = hi = 0; else { lo = hullR[r + 1].x + 1; hi = hullR[r + 1].y + 1; }
+            if (r == Lr - 1) lo = hi = 0; else { lo = hullR[r + 1].hlo + 1; hi = hullR[r + 1].hhi + 1; }
             if (swR) {
-                if (dR > a) { lo = min(lo, hullQ[dR].x + 1); hi = max(hi, hullQ[dR].y + 1); }
+                if (dR > a) { lo = min(lo, hullQ[dR].hlo + 1); hi = max(hi, hullQ[dR].hhi + 1); }
                 else { lo = 0; hi = INF; }
             }
-            hullR[r] = make_int2(lo, hi);
+            hullR[r].hlo = lo; hullR[r].hhi = hi; hullR[r].fdest = swR ? dR : -1;
             r--;
         }
     }
@@ -273,29 +281,31 @@ __global__ void wave_tables_kernel(BatchDev in, const ScPlan *plan, const int *l
         }
         // packed row records of the banded warp kernels
         const int Lq = p.len[h];
-        wave_row_hulls(H.ptr, H.flg, Lq, M.rptr, M.rflg, p.lr, X.hullQ, X.hullR);
+        wave_row_hulls(H.ptr, H.flg, Lq, M.rptr, M.rflg, p.lr, X.fwdQ, X.fwdR);
         {
             int cnt = 0;
             for (int a = Lq - 1; a >= 0; a--) {
-                RowRec r;
                 const int k0 = M.toQ[a], k1 = M.toQ[a + 1];
-                r.swi = k1 > k0 ? (((u32)M.toQ[Lq + 1 + k0] & 0xffffffu) | ((u32)(k1 - k0) << 24)) : 0u;
+                X.fwdQ[a].w0 = (k1 > k0 ? (((u32)M.toQ[Lq + 1 + k0] & 0xfffffu) | ((u32)(k1 - k0) << 20)) : 0u) | ((u32)(H.str[a] & 0x7f) << 24);
+                BwdRow r;
                 r.si = (u32)X.srcQ[a];
                 const u32 tpa = X.tpb[a], tpn = a + 1 < Lq ? X.tpb[a + 1] : 0;
-                r.tps = (u32)cnt | (tpa << 24) | (tpn << 25);
-                r.chw = (u32)(H.str[a] & 0x7f) | ((a + 1 < Lq ? (u32)(H.str[a + 1] & 0x7f) : 0xffu) << 8);
-                X.rowQ[a] = r;
+                r.tw = (u32)cnt | (tpa << 24) | (tpn << 25);
+                r.chn = a + 1 < Lq ? (u32)(H.str[a + 1] & 0x7f) : 0xffu;
+                r.pad = 0;
+                X.bwdQ[a] = r;
                 cnt += (int)tpa;
             }
         }
         for (int a = 0; a < p.lr; a++) {
-            RowRec r;
             const int k0 = M.toR[a], k1 = M.toR[a + 1];
-            r.swi = k1 > k0 ? (((u32)M.toR[p.lr + 1 + k0] & 0xffffffu) | ((u32)(k1 - k0) << 24)) : 0u;
+            X.fwdR[a].w0 = (k1 > k0 ? (((u32)M.toR[p.lr + 1 + k0] & 0xfffffu) | ((u32)(k1 - k0) << 20)) : 0u) | ((u32)(rseq[a] & 0x7f) << 24);
+            BwdRow r;
             r.si = (u32)X.srcR[a];
-            r.tps = 0;                                   // tp is zero on the REF plane
-            r.chw = (u32)(rseq[a] & 0x7f) | ((a + 1 < p.lr ? (u32)(rseq[a + 1] & 0x7f) : 0xffu) << 8);
-            X.rowR[a] = r;
+            r.tw = 0;                                    // tp is zero on the REF plane
+            r.chn = a + 1 < p.lr ? (u32)(rseq[a + 1] & 0x7f) : 0xffu;
+            r.pad = 0;
+            X.bwdR[a] = r;
         }
     } else {
         u8 *tinfo = base + W.ht[h - 2];
