@@ -171,32 +171,59 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def tie_count(status, n_sc):
+    """Superclusters in which an alignment followed an ambiguous swap edge (VD_ST_TIE): the reference's choice there
+    depends on hash-set iteration order, ours is canonical."""
+    return int((status[: 4 * n_sc].reshape(-1, 4) & 1).any(axis=1).sum())
+
+
 def run_secondary(eng, args, dev, torch):
-    """BASELINE configs[3] (WGS + SV tail to 10 kb) at 1/9 scale, through vd_run with host buffers:
-    400 k superclusters of the demo mixture of which 0.3 % carry one 50 bp..10 kb INS/DEL."""
-    b, cells, n = make_workload("wgs_sv", 400_000, args.seed, 0, 1, args.sv_max)
+    """BASELINE configs[3] (WGS + SV tail to 10 kb) at FULL scale through vd_run with host buffers: 3.6 M
+    superclusters of the demo mixture of which 0.3 % carry one 50 bp..10 kb INS/DEL, with its own CPU baseline
+    (the reference's object code on a bounded sample of the same workload) and tie count."""
+    b, cells, n = make_workload("wgs_sv", args.sv_n_sc, args.seed, 0, 1, args.sv_max)
+    out = None
     for _ in range(2):
-        eng.run(b)
-    ms = []
-    kern = {"wave_fwd": 0.0, "wave_bwd": 0.0, "wave_walk": 0.0, "small": 0.0}
-    for _ in range(3):
+        out = eng.run(b, out)
+    ms, dev_ms = [], []
+    kern = {"long_fwd": 0.0, "long_bwd": 0.0, "long_walk": 0.0, "short": 0.0, "band_phase_wall": 0.0, "long_wall": 0.0}
+    R = 3
+    for _ in range(R):
         t0 = time.perf_counter()
-        eng.run(b)
+        out = eng.run(b, out)
         ms.append((time.perf_counter() - t0) * 1e3)
         st = eng.stats()
-        kern["wave_fwd"] += st["ms_long_fwd"] / 3; kern["wave_bwd"] += st["ms_long_bwd"] / 3
-        kern["wave_walk"] += st["ms_long_walk"] / 3; kern["small"] += st["ms_short"] / 3
+        dev_ms.append(float(st["ms_total"]))
+        kern["long_fwd"] += st["ms_long_fwd"] / R; kern["long_bwd"] += st["ms_long_bwd"] / R
+        kern["long_walk"] += st["ms_long_walk"] / R; kern["short"] += st["ms_short"] / R
+        kern["band_phase_wall"] += st["ms_band"] / R; kern["long_wall"] += st["ms_long_wall"] / R
     m = float(np.median(ms))
     st = eng.stats()
     peak, _ = measured_peak()
-    fwd_bytes = st["spill_bytes"] / 3.0          # forward sweep: one flag byte per cell of the spilled matrices
-    return {"workload": WORKLOADS["wgs_sv"]["config"] + " at 1/9 scale", "n_superclusters": n, "cells": cells,
-            "e2e_ms_per_step": m, "e2e_gcells_per_s": cells / (m * 1e-3) / 1e9,
-            "e2e_superclusters_per_s": n / (m * 1e-3), "device_ms_per_step": float(st["ms_total"]),
-            "kernel_ms_per_step": kern, "kernel_ms_note": "summed over the shape classes, which run concurrently on their own streams",
-            "long_alignments": int(st["n_long"]), "long_region_wall_ms": float(st["ms_long_wall"]),
-            "roofline_wave_fwd": {"bound": "hbm", "achieved": fwd_bytes / (kern["wave_fwd"] * 1e-3) / 1e9 if kern["wave_fwd"] else 0.0,
-                                  "peak": peak, "unit": "GB/s", "note": "full-matrix-equivalent: 1 B/cell / summed class durations"}}
+    res = {"workload": WORKLOADS["wgs_sv"]["config"], "n_superclusters": n, "cells": cells,
+           "e2e_ms_per_step": m, "e2e_gcells_per_s": cells / (m * 1e-3) / 1e9,
+           "e2e_superclusters_per_s": n / (m * 1e-3), "device_ms_per_step": float(np.median(dev_ms)),
+           "kernel_ms_per_step": kern,
+           "kernel_ms_note": "long_fwd/bwd/walk are summed over rungs and shape classes, which run concurrently on their own streams; "
+                             "band_phase_wall / long_wall are wall times of the banded phase and of the whole long path",
+           "long_alignments": int(st["n_long"]), "long_alignments_left_to_dense_kernels": int(st["n_dense"]),
+           "tie_superclusters": tie_count(out.status, b.n_sc)}
+    # the banded forward sweep against the HBM roof, on the bytes it actually visits: one flag byte per kept cell
+    # written, the 16-byte row records and the band records read (DESIGN.md)
+    if st.get("band_cells", 0) and kern["long_fwd"] > 0:
+        vis = float(st["band_cells"]) + 16.0 * float(st.get("band_rows", 0)) + 16.0 * float(st.get("band_cols", 0))
+        res["roofline_band_fwd"] = {"bound": "hbm", "achieved": vis / (kern["long_fwd"] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                    "frac": vis / (kern["long_fwd"] * 1e-3) / 1e9 / peak, "visited_cells": int(st["band_cells"]),
+                                    "note": "visited bytes / summed forward-kernel durations of all rungs; the sweep is latency-bound "
+                                            "(one warp per alignment, a dependent column step), not bandwidth-bound"}
+    if not args.no_cpu_baseline and checkers.reference_available(False):
+        cores = os.cpu_count() or 1
+        sb, scells, _ = make_workload("wgs_sv", args.sv_cpu_sample, args.seed, 0, 1, args.sv_max)
+        _, sec = checkers.reference_run(sb, canonical=False, threads=cores)
+        res["cpu_baseline"] = {"value": scells / sec / 1e9, "unit": "Gcells/s", "cores": cores, "kind": "reference",
+                               "superclusters_per_s": sb.n_sc / sec,
+                               "sample": f"{sb.n_sc} superclusters ({scells} cells) of the same workload, one pass, -t {cores}"}
+    return res
 
 
 def main():
@@ -216,8 +243,10 @@ def main():
     ap.add_argument("--gather-slices", type=int, default=0,
                     help="N > 1: slices of a rank's shard whose result all-gather overlaps the next slice's kernels "
                          "(0 = by world size: 1 up to 2 GPUs, 2 up to 4, 3 beyond - the exchange grows with the number of ranks)")
+    ap.add_argument("--sv-n-sc", type=int, default=3_600_000, help="superclusters of the secondary (configs[3]) workload")
+    ap.add_argument("--sv-cpu-sample", type=int, default=40_000, help="superclusters in the secondary workload's cpu_baseline sample")
     ap.add_argument("--secondary", action="store_true", default=True,
-                    help="also time the SV-bearing workload (BASELINE configs[3]) at 1/9 scale through vd_run (default at N=1)")
+                    help="also time the SV-bearing workload (BASELINE configs[3]) at full scale through vd_run (default at N=1)")
     ap.add_argument("--no-secondary", dest="secondary", action="store_false")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -437,6 +466,9 @@ def main():
                     "api": "vd_run (C-ABI, pinned host buffers)", "steps": e2e_steps,
                     "ms_min": float(min(e2e_times)), "ms_max": float(max(e2e_times))},
             "gpu_launches": int(launches),
+            "tie_superclusters": {"count": tie_count(ho.status, b.n_sc) if world == 1 else None, "of": b.n_sc,
+                                  "note": "superclusters with VD_ST_TIE on this rank: an ambiguous swap edge on an optimal path, where the "
+                                          "reference's pick depends on unordered_set iteration order (SURVEY.md 8a); parity there is against oracle-B"},
             "kernel_ms_per_step": {"plan": ms_plan / args.steps, "short_region": k_short, "small_kernel<0>": k_small[0],
                                    "small_kernel<1>": k_small[1], "wsc_kernel<S>(sum, overlapping)": k_small[2],
                                    "wave_fwd": k_fwd, "wave_bwd": k_bwd,

@@ -143,6 +143,9 @@ typedef struct vd_stats {
     int64_t n_dense;          /* long alignments the banded warp kernels left to the dense block kernels        */
     float   ms_band;          /* wall time of the banded warp kernels (all rungs, forward + backward + walk)    */
     float   pad_;
+    int64_t band_cells;       /* cells the banded forward sweeps visited in the alignments they solved           */
+    int64_t band_rows;        /* ... rows (both planes) and truth columns of those alignments                    */
+    int64_t band_cols;
 } vd_stats;
 
 /* Final per-variant / per-supercluster results in the reference's own terms

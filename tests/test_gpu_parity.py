@@ -274,6 +274,29 @@ def test_malformed_input_is_reported(engine):
     assert ei.value.code == -3
 
 
+def test_input_the_kernels_cannot_process_is_reported(engine):
+    """More than 8 swap sources for one row (9 adjacent deletions): the kernels flag the supercluster
+    (VD_ST_ERR_BADINPUT on its alignments) and vd_run returns VD_E_BADINPUT, for a short and for a long
+    supercluster; the rest of the batch is computed and a second call on the same handle is clean."""
+    rng = np.random.default_rng(4)
+    for W in (40, 700):
+        ref = bytes(rng.choice(list(b"ACGT"), W).tolist())
+        dels = [(5 + k, TYPE_DEL, 1, b"", 30.0) for k in range(9)]
+        bb = BatchBuilder()
+        bb.add(b"ACGTACGT", [[(2, TYPE_SUB, 1, b"T", 30.0)], [], [(2, TYPE_SUB, 1, b"T", 30.0)], []])
+        bb.add(ref, [dels, [], dels, []])
+        b = bb.build()
+        out = capi.Out(b.n_sc, b.n_var) if hasattr(capi, "Out") else None
+        from vcfdist_b200.batch import Out
+        out = Out(b.n_sc, b.n_var)
+        with pytest.raises(capi.VdError) as ei:
+            engine.run(b, out)
+        assert ei.value.code == -3
+        assert (out.status[4:8] & 0x0800).all() and not (out.status[0:4] & 0xff00).any()
+        assert out.aln_score[0] == 0
+    check_vs_oracle(engine, synth.adversarial(77, 200, max_len=30))
+
+
 def test_idempotent_and_order_independent(engine):
     """Size-independent properties: same results on a second run, and per-supercluster results do
     not depend on batch order (superclusters are independent units)."""

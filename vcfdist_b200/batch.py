@@ -78,6 +78,7 @@ class vd_stats(C.Structure):
         ("ms_plan", C.c_float), ("ms_long_wall", C.c_float), ("ms_small", C.c_float * 3),
         ("n_small", C.c_int64 * 3), ("io_small", C.c_int64 * 3), ("n_hom", C.c_int64),
         ("n_dense", C.c_int64), ("ms_band", C.c_float), ("pad_", C.c_float),
+        ("band_cells", C.c_int64), ("band_rows", C.c_int64), ("band_cols", C.c_int64),
     ]
 
     def as_dict(self):

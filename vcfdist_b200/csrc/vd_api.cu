@@ -21,6 +21,7 @@
 #include "vd_kernels.cuh"
 #include "vd_wave.cuh"
 #include "vd_band.cuh"
+#include "vd_setup.cuh"
 
 using namespace vd;
 
@@ -126,21 +127,22 @@ extern "C" int vd_create(int device, int64_t scratch_bytes, vd_handle **out) {
     h->device = device;
     h->num_sms = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return VD_E_CUDA; }
-    for (auto &e : h->ev) cudaEventCreate(&e);
+    bool cok = true;
+    for (auto &e : h->ev) cok &= cudaEventCreate(&e) == cudaSuccess;
     for (int c = 0; c < N_WCLS; c++) {
-        cudaStreamCreateWithFlags(&h->side[c], cudaStreamNonBlocking);
-        for (auto &e : h->sev[c]) cudaEventCreate(&e);
+        cok &= cudaStreamCreateWithFlags(&h->side[c], cudaStreamNonBlocking) == cudaSuccess;
+        for (auto &e : h->sev[c]) cok &= cudaEventCreate(&e) == cudaSuccess;
     }
     for (auto &w : h->work) {
-        for (auto &e : w.ev) cudaEventCreate(&e);
-        cudaEventCreate(&w.ev5);
-        cudaEventCreate(&w.evL);
-        for (auto &g : w.gev) for (auto &e : g) cudaEventCreate(&e);
-        cudaHostAlloc((void **)&w.h_counters, sizeof(PlanCounters), cudaHostAllocMapped);
+        for (auto &e : w.ev) cok &= cudaEventCreate(&e) == cudaSuccess;
+        cok &= cudaEventCreate(&w.ev5) == cudaSuccess;
+        cok &= cudaEventCreate(&w.evL) == cudaSuccess;
+        for (auto &g : w.gev) for (auto &e : g) cok &= cudaEventCreate(&e) == cudaSuccess;
+        cok &= cudaHostAlloc((void **)&w.h_counters, sizeof(PlanCounters), cudaHostAllocMapped) == cudaSuccess;
     }
-    cudaStreamCreateWithFlags(&h->s_plan, cudaStreamNonBlocking);
-    cudaStreamCreateWithFlags(&h->s_epi, cudaStreamNonBlocking);
-    cudaHostAlloc((void **)&h->h_witems, sizeof(WaveItems), cudaHostAllocMapped);
+    cok &= cudaStreamCreateWithFlags(&h->s_plan, cudaStreamNonBlocking) == cudaSuccess;
+    cok &= cudaStreamCreateWithFlags(&h->s_epi, cudaStreamNonBlocking) == cudaSuccess;
+    cok &= cudaHostAlloc((void **)&h->h_witems, sizeof(WaveItems), cudaHostAllocMapped) == cudaSuccess;
     if (scratch_bytes <= 0) {
         size_t fr = 0, tot = 0;
         cudaMemGetInfo(&fr, &tot);
@@ -160,12 +162,13 @@ extern "C" int vd_create(int device, int64_t scratch_bytes, vd_handle **out) {
     if (const char *v = getenv("VD_SPARSE_BWD")) h->banded_bwd = atoi(v) == 0;
     if (const char *sm = getenv("VD_SBWD_MIN_CLASS")) h->sbwd_min_class = atoi(sm);
     if (const char *cs = getenv("VD_CHUNK_SC")) h->chunk_sc = atoll(cs) > 0 ? atoll(cs) : h->chunk_sc;
-    cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking);
-    cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking);
+    cok &= cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking) == cudaSuccess;
+    cok &= cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking) == cudaSuccess;
     for (auto &sg : h->stage) {
-        cudaEventCreateWithFlags(&sg.in_done, cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&sg.out_done, cudaEventDisableTiming);
+        cok &= cudaEventCreateWithFlags(&sg.in_done, cudaEventDisableTiming) == cudaSuccess;
+        cok &= cudaEventCreateWithFlags(&sg.out_done, cudaEventDisableTiming) == cudaSuccess;
     }
+    if (!cok) { vd_destroy(h); return VD_E_CUDA; }          // a stream, event or pinned block could not be created
     small_configure();
     wsc_configure();
     wave_configure();
@@ -250,7 +253,7 @@ static int chunk_plan(vd_handle *h, Work &W, cudaStream_t sp, const BatchDev &in
     CK(cudaMemsetAsync(W.counters.p, 0, sizeof(PlanCounters), sp));
     PlanCounters *dcnt = (PlanCounters *)W.counters.p;
     int *order = (int *)W.order.p;                   // class- and cost-sorted short superclusters
-    VD_LAUNCH(plan_kernel, (n_sc + 255) / 256, 256, 0, sp, in, (ScPlan *)W.plan.p, (int *)W.list.p, (u8 *)W.ranks.p, (int *)W.iota.p, dcnt,
+    VD_LAUNCH(plan_kernel, (n_sc + 255) / 256, 256, 0, sp, in, out, (ScPlan *)W.plan.p, (int *)W.list.p, (u8 *)W.ranks.p, (int *)W.iota.p, dcnt,
                                                     h->force_class, kBigClass, h->small_lo, h->small_hi, h->use_wsc, h->use_hom);
     VD_LAUNCH(small_base_kernel, 1, 32, 0, sp, dcnt);
     {   // order[] = supercluster indices stably sorted by rank (non-short superclusters sort to the end)
@@ -345,15 +348,18 @@ static int chunk_exec(vd_handle *h, Work &W) {
             CK(h->slab.ensure((size_t)need));
             const int m = i1 - i0;
             CK(h->hap_ok.ensure(16 * (size_t)m));
-            VD_LAUNCH(slab_setup_kernel, (4 * m + 127) / 128, 128, 0, st, in, plan, list, i0, i1, offs, (u8 *)h->slab.p,
-                                                                   (int *)h->hap_ok.p);
+            // expansion + tables: a warp per haplotype for the long path, a thread per haplotype for the scalar-slab class
+            VD_LAUNCH(long_setup_kernel, m, 128, 0, st, in, (const ScPlan *)plan, (const int *)list, i0, i1, (const int64_t *)offs, (u8 *)h->slab.p,
+                      (int *)h->hap_ok.p);
             S.n_launches++;
-            VD_LAUNCH(slab_align_kernel, (4 * m + 63) / 64, 64, 0, st, in, out, plan, list, i0, i1, offs, (u8 *)h->slab.p,
-                                                                (const int *)h->hap_ok.p, CLS_SCALAR);
-            S.n_launches++;
+            if (h->force_class == CLS_SCALAR) {
+                VD_LAUNCH(slab_setup_kernel, (4 * m + 127) / 128, 128, 0, st, in, plan, list, i0, i1, offs, (u8 *)h->slab.p,
+                          (int *)h->hap_ok.p);
+                VD_LAUNCH(slab_align_kernel, (4 * m + 63) / 64, 64, 0, st, in, out, plan, list, i0, i1, offs, (u8 *)h->slab.p,
+                          (const int *)h->hap_ok.p, CLS_SCALAR);
+                S.n_launches += 2;
+            }
             // ---- long path: class-sorted items; banded warp kernels first, dense block kernels for the rest ----
-            VD_LAUNCH(wave_tables_kernel, (4 * m + 127) / 128, 128, 0, st, in, plan, list, i0, i1, offs, (u8 *)h->slab.p,
-                      (const int *)h->hap_ok.p);
             CK(h->wave_desc.ensure(sizeof(WaveItems) + 4 * (size_t)(4 * m + 4)));
             WaveItems *wi = (WaveItems *)h->wave_desc.p;
             int *items = (int *)((u8 *)h->wave_desc.p + sizeof(WaveItems));
@@ -367,10 +373,10 @@ static int chunk_exec(vd_handle *h, Work &W) {
             int total_items = 0;
             for (int c = 0; c < N_WLIST; c++) { cb.b[c] = total_items; total_items += hwi.count[c]; }
             CK(h->band_state.ensure(4 * (size_t)total_items + 16));
-            CK(h->band_lb.ensure(4 * (size_t)total_items + 16));
+            CK(h->band_lb.ensure(8 * (size_t)total_items + 16));
             int *bstate = (int *)h->band_state.p, *blb = (int *)h->band_lb.p;
             VD_LAUNCH(wave_fill_kernel, (4 * m + 127) / 128, 128, 0, st, in, plan, list, i0, i1, (const int *)h->hap_ok.p,
-                      wi, cb, items, out, bstate, blb, h->use_band);
+                      wi, cb, items, out, bstate, blb, blb + total_items, h->use_band);
             S.n_launches++;
             if (total_items > 0) {
                 CK(h->need_dense.ensure(4 * (size_t)total_items + 16));
@@ -381,19 +387,29 @@ static int chunk_exec(vd_handle *h, Work &W) {
                 // ---- banded warp kernels (vd_band.cuh): rung K = 4, 8, 16; the backward sweep and the walk of a rung
                 //      run beside the forward sweep of the next one ----
                 if (h->use_band) {
+                    // round 1: rung 0 takes every item; what it cannot solve leaves with a guess of the rung it needs,
+                    // and rungs 1.. then run side by side, each on the items guessed for it.  round 2: rung after rung
+                    // over whatever a guess was too low for (normally nothing)
+                    int *bhint = blb + total_items;
                     for (int r = 0; r < N_RUNG; r++) {
                         cudaStream_t bs = h->serial ? st : h->side[r];
-                        if (bs != st) CK(cudaStreamWaitEvent(bs, r ? h->sev[r - 1][1] : h->ev[4], 0));
+                        if (bs != st) CK(cudaStreamWaitEvent(bs, r ? h->sev[0][1] : h->ev[4], 0));
                         CK(cudaEventRecord(h->sev[r][0], bs));
-                        band_launch_rung(bs, r, WA, total_items, bstate, blb, true);
+                        band_launch_rung(bs, r, WA, total_items, bstate, blb, bhint, true, r > 0, wi);
                         CK(cudaEventRecord(h->sev[r][1], bs));
-                        band_launch_rung(bs, r, WA, total_items, bstate, blb, false);
+                        band_launch_rung(bs, r, WA, total_items, bstate, blb, bhint, false, 0, wi);
                         CK(cudaEventRecord(h->sev[r][2], bs));
-                        VD_LAUNCH(band_walk_kernel, (total_items + 3) / 4, 128, 0, bs, WA, total_items, (const int *)bstate, band_rung_k(r));
+                        VD_LAUNCH(band_walk_kernel, (total_items + 3) / 4, 128, 0, bs, WA, total_items, bstate, band_rung_k(r));
                         CK(cudaEventRecord(h->sev[r][3], bs));
                         S.n_launches += 3;
                     }
                     for (int r = 0; r < N_RUNG; r++) if (!h->serial) CK(cudaStreamWaitEvent(st, h->sev[r][3], 0));
+                    for (int r = 2; r < N_RUNG; r++) {
+                        band_launch_rung(st, r, WA, total_items, bstate, blb, bhint, true, 0, wi);
+                        band_launch_rung(st, r, WA, total_items, bstate, blb, bhint, false, 0, wi);
+                        VD_LAUNCH(band_walk_kernel, (total_items + 3) / 4, 128, 0, st, WA, total_items, bstate, band_rung_k(r));
+                        S.n_launches += 3;
+                    }
                 }
                 // ---- what is left: dense-phase scratch sized on the device, then the block kernels per shape class ----
                 int64_t *dbytes = (int64_t *)h->dense_bytes.p, *doff = (int64_t *)h->dense_off.p;
@@ -407,6 +423,7 @@ static int chunk_exec(vd_handle *h, Work &W) {
                 CK(cudaGetLastError());
                 hwi = *h->h_witems;
                 S.n_dense += hwi.n_dense;
+                S.band_cells += (int64_t)hwi.band_cells; S.band_rows += (int64_t)hwi.band_rows; S.band_cols += (int64_t)hwi.band_cols;
                 if (h->use_band) {
                     for (int r = 0; r < N_RUNG; r++) {
                         float a_ = 0, b_ = 0, w_ = 0;
@@ -557,6 +574,18 @@ extern "C" int vd_run_device_slice(vd_handle *h, const vd_batch_in *in, vd_batch
     return rc != VD_OK ? rc : rc2;
 }
 
+// error path of vd_run: nothing of this call may still be in flight when the caller gets its buffers back, and
+// the handle must be reusable (no stale chunk state, no stale malformed-input count)
+static int quiesce(vd_handle *h, int rc) {
+    cudaStream_t ss[] = {h->s_in, h->s_plan, h->stream, h->s_epi, h->s_out};
+    for (cudaStream_t s_ : ss) if (s_) cudaStreamSynchronize(s_);
+    for (int c = 0; c < N_WCLS; c++) if (h->side[c]) cudaStreamSynchronize(h->side[c]);
+    for (auto &W : h->work) { W.busy = false; W.n_bad = 0; }
+    for (auto &sg : h->stage) sg.out_pending = false;
+    cudaGetLastError();
+    return rc;
+}
+
 extern "C" int vd_run(vd_handle *h, const vd_batch_in *in, vd_batch_out *out) {
     if (!h || !in || !out) return VD_E_BADINPUT;
     CK(cudaSetDevice(h->device));
@@ -661,22 +690,22 @@ extern "C" int vd_run(vd_handle *h, const vd_batch_in *in, vd_batch_out *out) {
     };
 
     int rc = upload(0);
-    if (rc != VD_OK) return rc;
+    if (rc != VD_OK) return quiesce(h, rc);
     rc = plan_chunk(0);
-    if (rc != VD_OK) return rc;
+    if (rc != VD_OK) return quiesce(h, rc);
     for (int i = 0; i < n_chunks; i++) {
         const double t_c0 = now_ms();
         vd_handle::Stage &sg = h->stage[i % vd_handle::NST];
         Work &W = h->work[i % vd_handle::NST];
         const Range r = range_of(i);
         const int64_t ns = r.s1 - r.s0, nv = r.v1 - r.v0;
-        if (i + 1 < n_chunks) { rc = upload(i + 1); if (rc != VD_OK) return rc; }
+        if (i + 1 < n_chunks) { rc = upload(i + 1); if (rc != VD_OK) return quiesce(h, rc); }
         const double t_c1 = now_ms();
         rc = chunk_exec(h, W);                 // returns with the chunk's kernels issued
-        if (rc != VD_OK) return rc;
+        if (rc != VD_OK) return quiesce(h, rc);
         const double t_c2 = now_ms();
         // the plan pass of the next chunk runs beside this chunk's kernels
-        if (i + 1 < n_chunks) { rc = plan_chunk(i + 1); if (rc != VD_OK) return rc; }
+        if (i + 1 < n_chunks) { rc = plan_chunk(i + 1); if (rc != VD_OK) return quiesce(h, rc); }
         if (trace) fprintf(stderr, "[vd_run] chunk %d: start %.2f ms, upload %.2f ms, exec %.2f ms, plan next %.2f ms\n",
                            i, t_c0 - t_start, t_c1 - t_c0, t_c2 - t_c1, now_ms() - t_c2);
 
@@ -701,7 +730,7 @@ extern "C" int vd_run(vd_handle *h, const vd_batch_in *in, vd_batch_out *out) {
     }
     for (auto &W : h->work) {
         const int rch = chunk_harvest(h, W);
-        if (rch != VD_OK && rch != VD_E_BADINPUT) return rch;
+        if (rch != VD_OK && rch != VD_E_BADINPUT) return quiesce(h, rch);
         if (rch != VD_OK) rc_all = rch;
     }
     const double t_e0 = now_ms();
@@ -715,7 +744,8 @@ extern "C" int vd_run(vd_handle *h, const vd_batch_in *in, vd_batch_out *out) {
     if (h->stats_status_or & VD_ST_ERR_MASK)
         for (int64_t i = 0; i < 4 * n_sc; i++)
             if (out->status[i] & VD_ST_ERR_MASK)
-                return fail(h, VD_E_ALIGN, "alignment %lld of supercluster %lld: status 0x%x", (long long)(i & 3),
-                            (long long)(i >> 2), out->status[i]);
+                return fail(h, (out->status[i] & VD_ST_ERR_BADINPUT) ? VD_E_BADINPUT : VD_E_ALIGN,
+                            "alignment %lld of supercluster %lld: status 0x%x%s", (long long)(i & 3), (long long)(i >> 2), out->status[i],
+                            (out->status[i] & VD_ST_ERR_BADINPUT) ? " (input the kernels cannot process, e.g. more than 8 swap sources for one row)" : "");
     return VD_OK;
 }

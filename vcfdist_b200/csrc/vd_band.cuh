@@ -25,7 +25,7 @@
 //     the next columns' candidate rows come from warp reductions over the kept cells;
 //   * flags are stored BANDED: F[column][plane][row mod 32K], one byte per cell of the window.
 //
-// Rungs (rows per lane / score bound): 1/10, 2/20, 4/40, 8/80, 16/160 (a window holds 3 tau + 2 rows).  A rung whose window holds both
+// Rungs (rows per lane / score bound): 1/14, 2/30, 4/60, 8/120, 16/240 (a window holds 2 tau + 2 rows).  A rung whose window holds both
 // planes entirely (<= 32*K rows each) runs unbounded: the dense sweep of thin-but-wide matrices.  What no
 // rung solves (score above the last bound, or kept cells further apart than a window) goes to the dense
 // block-per-alignment kernels of vd_wave.cuh.
@@ -37,7 +37,8 @@ namespace vd {
 constexpr int BAND_WARPS = 4;                                  // alignments per block (one warp each)
 constexpr int N_RUNG = 5;
 inline int band_rung_k(int r) { const int v[N_RUNG] = {1, 2, 4, 8, 16}; return v[r]; }
-inline int band_rung_tau(int r) { const int v[N_RUNG] = {10, 20, 40, 80, 160}; return v[r]; }
+__host__ __device__ inline int band_rung_tau(int r) { const int v[N_RUNG] = {14, 30, 60, 120, 240}; return v[r]; }
+constexpr int BAND_DONE = 0x100;      // state bit: walked (the rungs run in two rounds, see vd_api.cu)
 
 // per-item state shared by the rungs
 constexpr int BAND_PENDING = 0;       // not solved yet
@@ -174,8 +175,14 @@ template <int K> struct BandCfg {
 // ------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------
+// hint[]: first rung worth trying for an item.  A sweep that runs out of budget at column c has seen about
+// tau + 1 edits in c columns: the rung whose bound covers that rate over the whole truth haplotype is tried next
+// instead of every rung in between (a guess about speed only - whatever rung solves an item solves it exactly).
+// exact_hint: take only the items whose hint IS this rung (first round, all rungs side by side); otherwise
+// every pending item whose hint is not above it (second round, rung after rung).
 template <int K>
-__global__ void __launch_bounds__(32 * BAND_WARPS) band_fwd_kernel(WaveArgs A, int n_items, int *state, const int *lbound, int tau_rung, int last_rung) {
+__global__ void __launch_bounds__(32 * BAND_WARPS) band_fwd_kernel(WaveArgs A, int n_items, int *state, const int *lbound, int *hint,
+                                                                   int rung, int exact_hint, WaveItems *wi) {
     VD_DYN_SHARED(smem_raw);
     typedef BandCfg<K> C;
     constexpr unsigned FULL = 0xffffffffu;
@@ -184,12 +191,14 @@ __global__ void __launch_bounds__(32 * BAND_WARPS) band_fwd_kernel(WaveArgs A, i
     const int idx = n_items - 1 - (blockIdx.x * BAND_WARPS + warp);          // biggest shape classes first
     if (idx < 0) return;
     if (state[idx] != BAND_PENDING) return;
+    if (exact_hint ? hint[idx] != rung : hint[idx] > rung) return;
+    const bool last_rung = rung == N_RUNG - 1;
     const BandCtx X = band_ctx(A, A.items[idx]);
     const int len[2] = {X.Lq, X.Lr};
     const bool unbounded = (X.Lq + K - 1) / K <= 32 && (X.Lr + K - 1) / K <= 32;
-    const int tau = unbounded ? INF : tau_rung;
+    const int tau = unbounded ? INF : band_rung_tau(rung);
     if (K > X.kmax || max(X.Lq, X.Lr) >= BAND_ROW_LIMIT || (!unbounded && lbound[idx] > tau)) {   // this rung cannot take it
-        if (last_rung && lane == 0) state[idx] = BAND_DENSE;
+        if (lane == 0) { if (last_rung) state[idx] = BAND_DENSE; else hint[idx] = rung + 1; }
         return;
     }
     u8 *sm = smem_raw + warp * C::SMEM;
@@ -211,10 +220,12 @@ __global__ void __launch_bounds__(32 * BAND_WARPS) band_fwd_kernel(WaveArgs A, i
     for (int P = 0; P < 2; P++)
 #pragma unroll
         for (int j = 0; j < K; j++) Dp[P][j] = INF;
-    int nextLo[2] = {0, 0}, nextHi[2] = {0, 0}, dmin = 0;                     // rows reached from the kept cells of the previous column
+    int nextLo[2] = {0, 0}, nextHi[2] = {0, 0};                               // candidate rows of the next column (from the kept cells of this one)
     int pblo[2] = {0, 0};                                                     // first block of the previous column's window
     bool pvalid[2] = {false, false};                                          // the ring holds the plane's previous column
     bool failed = false;
+    int c_fail = -1;                                                          // column at which the budget ran out
+    long long visited = 0;                                                    // candidate cells of the sweep (statistics)
     // truth bases in 32-column chunks: one coalesced load per chunk, a chunk ahead
     int tchunk = lane < X.Lt ? X.tinfo[lane] : 0, tchunk_next = 32 + lane < X.Lt ? X.tinfo[32 + lane] : 0;
     for (int c = 0; c < X.Lt; c++) {
@@ -229,20 +240,21 @@ __global__ void __launch_bounds__(32 * BAND_WARPS) band_fwd_kernel(WaveArgs A, i
 #pragma unroll
         for (int P = 0; P < 2; P++) {
             if (c == 0 || unbounded) { cLo[P] = 0; cHi[P] = unbounded ? len[P] - 1 : min(tau, len[P] - 1); }
-            else { cLo[P] = max(nextLo[P], 0); cHi[P] = min(nextHi[P] + (tau - dmin), len[P] - 1); }   // + the in-column insertion chain
+            else { cLo[P] = max(nextLo[P], 0); cHi[P] = min(nextHi[P], len[P] - 1); }
             has[P] = cHi[P] >= cLo[P];
             blo[P] = has[P] ? cLo[P] / K : pblo[P];
             if (has[P] && cHi[P] / K - blo[P] > 31) failed = true;            // kept cells further apart than the window
         }
-        if (!unbounded && c > 0 && !has[0] && !has[1]) failed = true;         // nothing within the bound is left
+        if (!unbounded && c > 0 && !has[0] && !has[1]) { failed = true; c_fail = c; }   // nothing within the bound is left
 #ifdef VD_BAND_DEBUG
         if (failed && lane == 0) printf("  fail at c=%d cand Q[%d,%d] R[%d,%d]\n", c, cLo[0], cHi[0], cLo[1], cHi[1]);
 #endif
         if (failed) break;
+        visited += (has[0] ? cHi[0] - cLo[0] + 1 : 0) + (has[1] ? cHi[1] - cLo[1] + 1 : 0);
         if (lane == 0) X.band[c] = make_int4(has[0] ? cLo[0] : 1, has[0] ? cHi[0] : 0, has[1] ? cLo[1] : 1, has[1] ? cHi[1] : 0);
         const int *rprev = ring + ((c + 1) & 1) * 2 * W;
         int *rcur = ring + (c & 1) * 2 * W;
-        int nlo[2] = {INF, INF}, nhi[2] = {-1, -1}, ndmin = INF;
+        int nlo[2] = {INF, INF}, nhi[2] = {-1, -1};
 #pragma unroll
         for (int P = 0; P < 2; P++) {
             if (!has[P]) {                                                    // plane without candidates: nothing kept in this column
@@ -354,9 +366,11 @@ __global__ void __launch_bounds__(32 * BAND_WARPS) band_fwd_kernel(WaveArgs A, i
                             const uint4 rec = rows[a & (R - 1)];
                             const int rc = X.Lt - 1 - c, slack = tau - d;
                             if (rc - (int)rec.w <= slack && (int)rec.z - rc <= slack) {
-                                nlo[P] = min(nlo[P], a); nhi[P] = max(nhi[P], a + 1); ndmin = min(ndmin, d);
-                                const int fd = (int)rec.y;                    // my row as a swap source: candidate on the other plane
-                                if (fd >= 0) { nlo[o] = min(nlo[o], fd); nhi[o] = max(nhi[o], fd); }
+                                // successors in the next column: the same row (deletion), the row above (diagonal) and my swap
+                                // destination; from each of them the insertion chain climbs while the bound allows: + slack rows
+                                nlo[P] = min(nlo[P], a); nhi[P] = max(nhi[P], a + 1 + slack);
+                                const int fd = (int)rec.y;
+                                if (fd >= 0) { nlo[o] = min(nlo[o], fd); nhi[o] = max(nhi[o], fd + slack); }
                             }
                         }
                     } else d = INF;
@@ -379,17 +393,22 @@ __global__ void __launch_bounds__(32 * BAND_WARPS) band_fwd_kernel(WaveArgs A, i
         if (!unbounded) {
             nextLo[0] = __reduce_min_sync(FULL, nlo[0]); nextHi[0] = __reduce_max_sync(FULL, nhi[0]);
             nextLo[1] = __reduce_min_sync(FULL, nlo[1]); nextHi[1] = __reduce_max_sync(FULL, nhi[1]);
-            dmin = K >= 4 ? __reduce_min_sync(FULL, ndmin) : 0;
-            if (dmin > tau) dmin = tau;
         }
         __syncwarp();                                                         // ring of this column visible to all lanes
     }
 #ifdef VD_BAND_DEBUG
-    if (lane == 0) printf("band_fwd K=%d idx=%d sc=%d ai=%d Lq=%d Lr=%d Lt=%d tau=%d failed=%d next Q[%d,%d] R[%d,%d] dmin=%d\n", K, idx, X.sc, X.ai, X.Lq, X.Lr, X.Lt, tau,
-                          (int)failed, nextLo[0], nextHi[0], nextLo[1], nextHi[1], dmin);
+    if (lane == 0) printf("band_fwd K=%d idx=%d sc=%d ai=%d Lq=%d Lr=%d Lt=%d tau=%d failed=%d next Q[%d,%d] R[%d,%d]\n", K, idx, X.sc, X.ai, X.Lq, X.Lr, X.Lt, tau,
+                          (int)failed, nextLo[0], nextHi[0], nextLo[1], nextHi[1]);
 #endif
     if (failed) {
-        if (last_rung && lane == 0) state[idx] = BAND_DENSE;
+        if (lane == 0) {
+            int nh = rung + 1;
+            if (c_fail > 0) {                                                 // extrapolate the edit rate seen so far
+                const long long est = (long long)(tau + 1) * X.Lt / c_fail * 9 / 8;      // + 1/8: a guess too low costs a whole extra sweep
+                while (nh < N_RUNG - 1 && band_rung_tau(nh) < est) nh++;
+            }
+            if (last_rung) state[idx] = BAND_DENSE; else hint[idx] = nh;
+        }
         return;
     }
     // ---- score and end plane (:390-391, :436-440): the last rows of the last column, through the ring ----
@@ -404,8 +423,11 @@ __global__ void __launch_bounds__(32 * BAND_WARPS) band_fwd_kernel(WaveArgs A, i
             A.out.aln_score[oi] = score;
             A.out.aln_end_plane[oi] = (u8)(dq == score ? 0 : 1);
             state[idx] = K;
+            atomicAdd(&wi->band_cells, (unsigned long long)visited);
+            atomicAdd(&wi->band_rows, (unsigned long long)(X.Lq + X.Lr));
+            atomicAdd(&wi->band_cols, (unsigned long long)X.Lt);
         }
-    } else if (last_rung && lane == 0) state[idx] = BAND_DENSE;
+    } else if (lane == 0) { if (last_rung) state[idx] = BAND_DENSE; else hint[idx] = rung + 1; }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -675,12 +697,12 @@ struct PFBand {
 };
 
 // walk + credit of the alignments the band kernels solved: one alignment per warp (lane 0 walks)
-__global__ void band_walk_kernel(WaveArgs A, int n_items, const int *state, int only_k) {
+__global__ void band_walk_kernel(WaveArgs A, int n_items, int *state, int only_k) {
     const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (g >= n_items || (threadIdx.x & 31)) return;
     const int idx = n_items - 1 - g;
     const int K = state[idx];
-    if (K <= 0 || K != only_k) return;
+    if (K <= 0 || K != only_k) return;                       // not solved, another rung's, or walked already (BAND_DONE)
     const int item = A.items[idx];
     const int e = item >> 2, ai = item & 3;
     const int i = A.i0 + e;
@@ -705,22 +727,22 @@ __global__ void band_walk_kernel(WaveArgs A, int n_items, const int *state, int 
     const int end_plane = A.out.aln_end_plane[4 * (int64_t)sc + ai];
     walk_credit<GMem, 4, int>(mem, L, pfr, q, qm, t, rseq, p.lr, beg_plane, end_plane, A.in, A.out, sc, ai, status);
     A.out.status[4 * (int64_t)sc + ai] = status;
+    state[idx] = K | BAND_DONE;
 }
 
-template <int K> inline void band_launch(cudaStream_t st, const WaveArgs &A, int n_items, int *state, const int *lbound, bool fwd, int tau, int last) {
+template <int K> inline void band_launch(cudaStream_t st, const WaveArgs &A, int n_items, int *state, const int *lbound, int *hint, bool fwd, int rung, int exact, WaveItems *wi) {
     if (n_items <= 0) return;
     const int nb = (n_items + BAND_WARPS - 1) / BAND_WARPS, sm = BAND_WARPS * BandCfg<K>::SMEM;
-    if (fwd) VD_LAUNCH(band_fwd_kernel<K>, nb, 32 * BAND_WARPS, sm, st, A, n_items, state, lbound, tau, last);
+    if (fwd) VD_LAUNCH(band_fwd_kernel<K>, nb, 32 * BAND_WARPS, sm, st, A, n_items, state, lbound, hint, rung, exact, wi);
     else VD_LAUNCH(band_bwd_kernel<K>, nb, 32 * BAND_WARPS, sm, st, A, n_items, (const int *)state);
 }
-inline void band_launch_rung(cudaStream_t st, int rung, const WaveArgs &A, int n_items, int *state, const int *lbound, bool fwd) {
-    const int tau = band_rung_tau(rung), last = rung == N_RUNG - 1;
+inline void band_launch_rung(cudaStream_t st, int rung, const WaveArgs &A, int n_items, int *state, const int *lbound, int *hint, bool fwd, int exact, WaveItems *wi) {
     switch (band_rung_k(rung)) {
-        case 1: band_launch<1>(st, A, n_items, state, lbound, fwd, tau, last); break;
-        case 2: band_launch<2>(st, A, n_items, state, lbound, fwd, tau, last); break;
-        case 4: band_launch<4>(st, A, n_items, state, lbound, fwd, tau, last); break;
-        case 8: band_launch<8>(st, A, n_items, state, lbound, fwd, tau, last); break;
-        case 16: band_launch<16>(st, A, n_items, state, lbound, fwd, tau, last); break;
+        case 1: band_launch<1>(st, A, n_items, state, lbound, hint, fwd, rung, exact, wi); break;
+        case 2: band_launch<2>(st, A, n_items, state, lbound, hint, fwd, rung, exact, wi); break;
+        case 4: band_launch<4>(st, A, n_items, state, lbound, hint, fwd, rung, exact, wi); break;
+        case 8: band_launch<8>(st, A, n_items, state, lbound, hint, fwd, rung, exact, wi); break;
+        case 16: band_launch<16>(st, A, n_items, state, lbound, hint, fwd, rung, exact, wi); break;
     }
 }
 template <int K> inline void band_configure_one() {

@@ -97,7 +97,7 @@ __device__ __forceinline__ int small_need(int Lq, int Lr, int Lt) {
 
 // One thread per supercluster.  small_lo / small_hi: range of small classes in use (testing hooks
 // VD_SMALL_MIN / VD_SMALL_MAX; hi < lo disables the small kernels).
-__global__ void plan_kernel(BatchDev in, ScPlan *plan, int *list, u8 *ranks, int *iota, PlanCounters *cnt, int force_class,
+__global__ void plan_kernel(BatchDev in, OutDev out, ScPlan *plan, int *list, u8 *ranks, int *iota, PlanCounters *cnt, int force_class,
                             int big_class, int small_lo, int small_hi, int use_wsc, int use_hom) {
     const int sc0 = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = sc0 < in.n_sc;
@@ -169,6 +169,8 @@ __global__ void plan_kernel(BatchDev in, ScPlan *plan, int *list, u8 *ranks, int
     p.cls = cls | (sbin >= 0 ? (sbin << 8) : 0);
     p.hom = hom ? 1 : 0;
     if (live) { plan[sc] = p; ranks[sc] = (u8)(sbin >= 0 ? sbin : RANK_NONE); iota[sc] = sc; }
+    if (live && cls == CLS_BAD)                        // malformed supercluster: flagged per alignment, never computed
+        for (int k = 0; k < 4; k++) { out.status[4 * (int64_t)sc + k] = VD_ST_ERR_BADINPUT; out.aln_score[4 * (int64_t)sc + k] = -1; }
     // warp-aggregated counters: one atomic per warp and counter instead of one per thread
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -457,7 +459,7 @@ __global__ void slab_setup_kernel(BatchDev in, ScPlan *plan, const int *list, in
     if (i >= i1) return;
     const int sc = list[i];
     const ScPlan p = plan[sc];
-    if (p.hom && (h & 1) && p.cls == CLS_WAVE) { hap_ok[4 * (int64_t)(i - i0) + h] = 1; return; }   // same as haplotype h-1, never read
+    if (p.cls == CLS_WAVE) return;                       // long path: long_setup_kernel (vd_setup.cuh)
     const SlabLayout S = make_slab(p, p.cls == CLS_SCALAR);
     u8 *base = slab + (offs[i] - offs[i0]);
     SlabHap H(base + S.hap[h], p.len[h], p.lr);

@@ -324,6 +324,7 @@ struct WaveItems {
     int pad_;
     unsigned long long spill_cells;
     unsigned long long dense_bytes;
+    unsigned long long band_cells, band_rows, band_cols;   // banded kernels: candidate cells, rows and columns of the solved alignments
 };
 struct ClsBase { int b[N_WLIST]; };
 __global__ void wave_count_kernel(const ScPlan *plan, const int *list, int i0, int i1, const int *hap_ok,
@@ -341,7 +342,7 @@ __global__ void wave_count_kernel(const ScPlan *plan, const int *list, int i0, i
 __device__ inline int band_score_lb(const BatchDev &in, int sc, int ai, int Lr, int Lt);
 // state[]: 0 = pending for the banded kernels (band_on) or -1 = dense phase; lbound[]: lower bound of the score
 __global__ void wave_fill_kernel(BatchDev in, const ScPlan *plan, const int *list, int i0, int i1, const int *hap_ok,
-                                 WaveItems *wi, ClsBase cb, int *items, OutDev out, int *state, int *lbound, int band_on) {
+                                 WaveItems *wi, ClsBase cb, int *items, OutDev out, int *state, int *lbound, int *hint, int band_on) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = i0 + (g >> 2), ai = g & 3;
     if (i >= i1) return;
@@ -360,6 +361,7 @@ __global__ void wave_fill_kernel(BatchDev in, const ScPlan *plan, const int *lis
     items[pos] = ((i - i0) << 2) | ai;
     state[pos] = band_on ? 0 : -1;
     lbound[pos] = band_score_lb(in, sc, ai, p.lr, Lt);
+    hint[pos] = 0;
 }
 
 // dense phase: scratch bytes of every item the banded kernels did not solve (0 for the others)
@@ -413,7 +415,7 @@ typedef WaveCtxT<int> WaveCtx;
 __device__ inline WaveCtx wave_ctx(const WaveArgs &A, int idx) {
     WaveCtx x;
     const int item = A.items[idx];
-    x.skip = A.bstate && A.bstate[idx] > 0;
+    x.skip = A.bstate && A.bstate[idx] > 0;            // solved (and walked) by the banded kernels
     const int e = item >> 2;
     x.ai = item & 3;
     const int i = A.i0 + e;

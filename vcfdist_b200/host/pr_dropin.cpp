@@ -282,7 +282,7 @@ void precision_recall_threads_wrapper(
     if (rc != VD_OK) ERROR("vcfdist_b200: cannot initialise CUDA device %d (code %d); "
                            "there is no CPU fallback for the precision/recall path", device, rc);
     rc = vd_run(h, &in, &out);
-    if (rc != VD_OK && rc != VD_E_ALIGN)
+    if (rc != VD_OK && rc != VD_E_ALIGN && rc != VD_E_BADINPUT)     // the last two are reported per supercluster below
         ERROR("vcfdist_b200: vd_run failed (code %d): %s", rc, vd_last_error(h));
     if (g.verbosity >= 2) {
         vd_stats st; vd_get_stats(h, &st);
@@ -297,6 +297,11 @@ void precision_recall_threads_wrapper(
         if (!st) continue;
         const std::string &ctg = clusterdata_ptr->contigs[p.sc_loc[s].ctg];
         const int sc_idx = p.sc_loc[s].sc;
+        if (st & VD_ST_ERR_BADINPUT)
+            ERROR("vcfdist_b200: ctg %s supercluster %d cannot be processed on the GPU path (malformed variants, or more than "
+                  "8 swap sources for one row, e.g. 8 adjacent deletions)", ctg.data(), sc_idx);
+        if (st & VD_ST_ERR_MASK & ~(VD_ST_ERR_BADINPUT | VD_ST_ERR_UNFINISHED | VD_ST_ERR_NO_SWAP_PRED | VD_ST_ERR_NO_POINTER))
+            ERROR("vcfdist_b200: unknown error status 0x%x at ctg %s supercluster %d", st, ctg.data(), sc_idx);
         if (st & VD_ST_ERR_UNFINISHED) ERROR("Alignment not finished in 'prec_recall_aln()'.");   // :440
         if (st & VD_ST_ERR_NO_SWAP_PRED) ERROR("No swap predecessor, but PTR_SWP_MAT set.");      // :606
         if (st & VD_ST_ERR_NO_POINTER) ERROR("No valid pointer at ctg %s supercluster %d", ctg.data(), sc_idx); // :937
