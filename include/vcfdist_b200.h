@@ -205,6 +205,29 @@ const char *vd_last_error(const vd_handle *h);
  * e.g. torch.cuda.ExternalStream(vd_stream(h)).                                           */
 void *vd_stream(const vd_handle *h);
 
+/* ---- cluster-growing stage (the step before the path) --------------------------------
+ * Batches of the two affine-gap wavefront searches wf_swg_cluster (src/cluster.cpp:954-1263) is made of:
+ *   VD_WF_REACH  wf_swg_max_reach (src/dist.cpp:2150-2333; call sites src/cluster.cpp:1080-1090, :1139-1149): the
+ *                furthest truth index reachable with a score <= max_score[i]; reverse[i] = 1 for the leftward
+ *                search (the caller passes the reversed strings, as the reference does)
+ *   VD_WF_SCORE  the score of wf_swg_align (src/dist.cpp:1510-1652; call site src/cluster.cpp:1040-1046)
+ * Problem i: query = q_seq[q_off[i] .. q_off[i+1]), truth = t_seq[t_off[i] .. t_off[i+1]); penalties sub / open /
+ * extend as g.query_sub etc.; host buffers in, result[n] out; one warp per problem on the device.            */
+#define VD_WF_REACH 0
+#define VD_WF_SCORE 1
+int  vd_wf_batch(vd_handle *h, int mode, int n, const int64_t *q_off, const uint8_t *q_seq, const int64_t *t_off,
+                 const uint8_t *t_seq, const int32_t *main_diag, const int32_t *main_diag_start, const int32_t *max_score,
+                 const uint8_t *reverse, int sub, int open, int extend, int32_t *result);
+
+/* ---- `--distance` pass ------------------------------------------------------------------
+ * Batches of the affine-gap alignment edits_wrapper (src/dist.cpp:1908-2077) runs per supercluster and haplotype:
+ * wf_swg_align with its predecessor flags (src/dist.cpp:1510-1652) + wf_swg_backtrack (:2625-2757).
+ * score[i]: the alignment score, -1 where the reference's walk back would ERROR(); cigar: problem i at
+ * cigar[q_off[i] + t_off[i] ..], |query| + |truth| entries filled from the back exactly as the reference fills its
+ * vector (PTR_INS 1 / PTR_DEL 2 / PTR_MAT 4 / PTR_SUB 8; two entries per match or substitution), zeros in front. */
+int  vd_swg_align_batch(vd_handle *h, int n, const int64_t *q_off, const uint8_t *q_seq, const int64_t *t_off,
+                        const uint8_t *t_seq, int sub, int open, int extend, int32_t *score, int32_t *cigar);
+
 #ifdef __cplusplus
 }
 #endif

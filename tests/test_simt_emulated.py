@@ -59,3 +59,46 @@ def test_dense_block_kernels_alone():
     b = Batch.concat([synth.sv_case(310, 260, "ins", "het", 0.02), synth.sv_case(311, 200, "del", "hom", 0.0)])
     _, st = check(b, VD_BAND=0)
     assert st["n_dense"] > 0
+
+
+def test_cluster_wavefront_kernels_and_driver():
+    """the reach / score wavefront kernel (one warp per problem) and the batched cluster-growing
+    driver over it, against the recorded reference answers."""
+    import json
+    from vcfdist_b200 import cluster
+    from conftest import ROOT
+    z = np.load(os.path.join(ROOT, "tests", "golden", "reach_kat.npz"), allow_pickle=False)
+    e = EmuEngine()
+    idx = [i for i in range(300)]
+    groups = {}
+    for i in idx:
+        groups.setdefault(tuple(int(x) for x in z["params"][i][3:6]), []).append(i)
+    for (x, o, ex), ii in groups.items():
+        q = [z["query"][z["q_off"][i]: z["q_off"][i + 1]].tobytes() for i in ii]
+        t = [z["truth"][z["t_off"][i]: z["t_off"][i + 1]].tobytes() for i in ii]
+        p = z["params"][ii]
+        got = e.wf_batch(0, q, t, x, o, ex, p[:, 0], p[:, 1], p[:, 2], p[:, 6])
+        assert (got == z["answer"][ii]).all()
+    kat = json.load(open(os.path.join(ROOT, "tests", "golden", "cluster_kat.json")))
+    for c in kat[:40]:
+        var = [(v[0], v[1], v[2], v[3].encode()) for v in c["var"]]
+        got = cluster.wf_swg_cluster(e, c["fasta"].encode(), var, *c["penalties"])
+        assert [list(v) for v in got] == c["answer"]
+    e.close()
+
+
+def test_distance_alignment_kernel():
+    """affine-gap alignment with CIGAR (wf_swg_align + wf_swg_backtrack) against recorded reference answers."""
+    from conftest import ROOT
+    z = np.load(os.path.join(ROOT, "tests", "golden", "reach_kat.npz"), allow_pickle=False)
+    e = EmuEngine()
+    groups = {}
+    for i in range(200):
+        groups.setdefault(tuple(int(v) for v in z["swg_params"][i]), []).append(i)
+    for (x, o, ex), ii in groups.items():
+        q = [z["query"][z["q_off"][i]: z["q_off"][i + 1]].tobytes() for i in ii]
+        t = [z["truth"][z["t_off"][i]: z["t_off"][i + 1]].tobytes() for i in ii]
+        sc, cigs = e.swg_align_batch(q, t, x, o, ex)
+        for i, s, cg in zip(ii, sc, cigs):
+            assert s == int(z["cig_score"][i]) and (cg == z["cigar"][z["cig_off"][i]: z["cig_off"][i + 1]]).all()
+    e.close()

@@ -20,7 +20,7 @@ _ROOT = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_ROOT, "libvcfdist_b200.so")
 
 EXPORTS = ("vd_abi_version", "vd_create", "vd_destroy", "vd_run", "vd_run_device", "vd_run_device_slice",
-           "vd_finalize", "vd_get_stats", "vd_last_error", "vd_stream")
+           "vd_finalize", "vd_get_stats", "vd_last_error", "vd_stream", "vd_wf_batch", "vd_swg_align_batch")
 
 _lib = None
 
@@ -59,6 +59,10 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.vd_last_error.restype = C.c_char_p
     lib.vd_stream.argtypes = [C.c_void_p]
     lib.vd_stream.restype = C.c_void_p
+    lib.vd_wf_batch.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 8 + [C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.vd_wf_batch.restype = C.c_int
+    lib.vd_swg_align_batch.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.vd_swg_align_batch.restype = C.c_int
     if path is None:
         _lib = lib
     return lib
@@ -124,6 +128,38 @@ class Engine:
         """A slice of a resident batch (vd_run_device_slice): ref_off / var_off advanced to the slice."""
         self._check(self.lib.vd_run_device_slice(self.h, C.byref(din), C.byref(dout), first_var, n_var,
                                                  ref_bytes, alt_bytes))
+
+    def wf_batch(self, mode: int, queries, truths, sub: int, open_: int, extend: int, main_diag=None, main_diag_start=None,
+                 max_score=None, reverse=None) -> np.ndarray:
+        """Batch of affine-gap wavefront problems of the cluster-growing stage (vd_wf_batch): mode 0 =
+        wf_swg_max_reach (needs main_diag, main_diag_start, max_score, reverse per problem), mode 1 = score of
+        wf_swg_align.  queries / truths: sequences of bytes."""
+        n = len(queries)
+        q_off = np.zeros(n + 1, np.int64); q_off[1:] = np.cumsum([len(q) for q in queries])
+        t_off = np.zeros(n + 1, np.int64); t_off[1:] = np.cumsum([len(t) for t in truths])
+        q_seq = np.frombuffer(b"".join(queries) or b"\0", np.uint8)
+        t_seq = np.frombuffer(b"".join(truths) or b"\0", np.uint8)
+        res = np.zeros(max(n, 1), np.int32)
+        arr = lambda a, dt: None if a is None else np.ascontiguousarray(a, dt)
+        md, mds, ms, rv = arr(main_diag, np.int32), arr(main_diag_start, np.int32), arr(max_score, np.int32), arr(reverse, np.uint8)
+        p = lambda a: None if a is None else a.ctypes.data
+        self._check(self.lib.vd_wf_batch(self.h, mode, n, p(q_off), p(q_seq), p(t_off), p(t_seq), p(md), p(mds), p(ms), p(rv),
+                                         sub, open_, extend, p(res)), allow_align=False)
+        return res[:n]
+
+    def swg_align_batch(self, queries, truths, sub: int, open_: int, extend: int):
+        """`--distance` alignments (vd_swg_align_batch): -> (scores [n], list of CIGAR arrays as the reference fills them)."""
+        n = len(queries)
+        q_off = np.zeros(n + 1, np.int64); q_off[1:] = np.cumsum([len(q) for q in queries])
+        t_off = np.zeros(n + 1, np.int64); t_off[1:] = np.cumsum([len(t) for t in truths])
+        q_seq = np.frombuffer(b"".join(queries) or b"\0", np.uint8)
+        t_seq = np.frombuffer(b"".join(truths) or b"\0", np.uint8)
+        score = np.zeros(max(n, 1), np.int32)
+        cig = np.zeros(max(int(q_off[n] + t_off[n]), 1), np.int32)
+        self._check(self.lib.vd_swg_align_batch(self.h, n, q_off.ctypes.data, q_seq.ctypes.data, t_off.ctypes.data, t_seq.ctypes.data,
+                                                sub, open_, extend, score.ctypes.data, cig.ctypes.data), allow_align=False)
+        co = q_off + t_off
+        return score[:n], [cig[co[i]: co[i + 1]] for i in range(n)]
 
     def stats(self) -> dict:
         st = vd_stats()

@@ -22,6 +22,7 @@
 #include "vd_wave.cuh"
 #include "vd_band.cuh"
 #include "vd_setup.cuh"
+#include "vd_reach.cuh"
 
 using namespace vd;
 
@@ -95,6 +96,7 @@ struct vd_handle {
     int64_t chunk_sc = 1048576;      // superclusters per pipeline chunk (VD_CHUNK_SC)
     // work
     DevBuf need_dense, bytes, offs, cubtmp, slab, hap_ok, wave_desc, band_state, band_lb, dense_bytes, dense_off, dense;
+    DevBuf wf_in, wf_scratch;       // vd_wf_batch: staged problems, wavefront rings
     WaveItems *h_witems = nullptr;          // pinned + mapped (a small D2H memcpy would queue behind the bulk result copies of vd_run)
 };
 
@@ -192,7 +194,7 @@ extern "C" void vd_destroy(vd_handle *h) {
     if (h->s_in) cudaStreamDestroy(h->s_in);
     if (h->s_out) cudaStreamDestroy(h->s_out);
     DevBuf *bufs[] = {&h->need_dense, &h->bytes, &h->offs, &h->cubtmp, &h->slab, &h->hap_ok, &h->wave_desc, &h->band_state,
-                      &h->band_lb, &h->dense_bytes, &h->dense_off, &h->dense};
+                      &h->band_lb, &h->dense_bytes, &h->dense_off, &h->dense, &h->wf_in, &h->wf_scratch};
     for (DevBuf *b : bufs) b->release();
     for (auto &w : h->work) {
         DevBuf *wb[] = {&w.plan, &w.list, &w.order, &w.ranks, &w.ranks_out, &w.iota, &w.counters, &w.cubtmp};
@@ -747,5 +749,86 @@ extern "C" int vd_run(vd_handle *h, const vd_batch_in *in, vd_batch_out *out) {
                 return fail(h, (out->status[i] & VD_ST_ERR_BADINPUT) ? VD_E_BADINPUT : VD_E_ALIGN,
                             "alignment %lld of supercluster %lld: status 0x%x%s", (long long)(i & 3), (long long)(i >> 2), out->status[i],
                             (out->status[i] & VD_ST_ERR_BADINPUT) ? " (input the kernels cannot process, e.g. more than 8 swap sources for one row)" : "");
+    return VD_OK;
+}
+
+// ---- cluster-growing stage: batches of affine-gap wavefront problems ------------------
+extern "C" int vd_wf_batch(vd_handle *h, int mode, int n, const int64_t *q_off, const uint8_t *q_seq, const int64_t *t_off,
+                           const uint8_t *t_seq, const int32_t *main_diag, const int32_t *main_diag_start, const int32_t *max_score,
+                           const uint8_t *reverse, int sub, int open, int extend, int32_t *result) {
+    if (!h || n < 0 || !q_off || !t_off || !result || (mode != WF_MODE_REACH && mode != WF_MODE_SCORE)) return VD_E_BADINPUT;
+    if (mode == WF_MODE_REACH && (!main_diag || !main_diag_start || !max_score || !reverse)) return VD_E_BADINPUT;
+    if (sub < 0 || open < 0 || extend < 1) return fail(h, VD_E_BADINPUT, "penalties: sub %d open %d extend %d", sub, open, extend);
+    if (n == 0) return VD_OK;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    const int64_t qb = q_off[n], tb = t_off[n];
+    std::vector<int64_t> soff((size_t)n + 1);
+    soff[0] = 0;
+    for (int i = 0; i < n; i++) {
+        const int ql = (int)(q_off[i + 1] - q_off[i]), tl = (int)(t_off[i + 1] - t_off[i]);
+        if (ql < 1 || tl < 1) return fail(h, VD_E_BADINPUT, "problem %d: empty string", i);
+        soff[i + 1] = soff[i] + wf_scratch_ints(ql, tl, sub, open, extend);
+    }
+    if (4 * soff[n] > h->scratch_budget) return fail(h, VD_E_NOMEM, "wavefront rings need %lld bytes", (long long)(4 * soff[n]));
+    // one staging block: offsets, strings, per-problem parameters, results
+    size_t o_qoff = 0, o_toff = o_qoff + 8 * (size_t)(n + 1), o_soff = o_toff + 8 * (size_t)(n + 1), o_md = o_soff + 8 * (size_t)(n + 1);
+    size_t o_mds = o_md + 4 * (size_t)n, o_ms = o_mds + 4 * (size_t)n, o_res = o_ms + 4 * (size_t)n, o_rev = o_res + 4 * (size_t)n;
+    size_t o_q = (o_rev + n + 15) & ~(size_t)15, o_t = (o_q + qb + 15) & ~(size_t)15, total = o_t + tb + 16;
+    CK(h->wf_in.ensure(total));
+    CK(h->wf_scratch.ensure(4 * (size_t)soff[n] + 16));
+    u8 *d = (u8 *)h->wf_in.p;
+    CK(cudaMemcpyAsync(d + o_qoff, q_off, 8 * (size_t)(n + 1), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d + o_toff, t_off, 8 * (size_t)(n + 1), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d + o_soff, soff.data(), 8 * (size_t)(n + 1), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d + o_q, q_seq, (size_t)qb, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d + o_t, t_seq, (size_t)tb, cudaMemcpyHostToDevice, st));
+    if (mode == WF_MODE_REACH) {
+        CK(cudaMemcpyAsync(d + o_md, main_diag, 4 * (size_t)n, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d + o_mds, main_diag_start, 4 * (size_t)n, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d + o_ms, max_score, 4 * (size_t)n, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d + o_rev, reverse, (size_t)n, cudaMemcpyHostToDevice, st));
+    }
+    WfBatch B{n, (const int64_t *)(d + o_qoff), (const int64_t *)(d + o_toff), d + o_q, d + o_t, (const int32_t *)(d + o_md),
+              (const int32_t *)(d + o_mds), (const int32_t *)(d + o_ms), d + o_rev, (const int64_t *)(d + o_soff), (int32_t *)h->wf_scratch.p,
+              (int32_t *)(d + o_res), sub, open, extend, mode};
+    VD_LAUNCH(wf_kernel, (n + 3) / 4, 128, 0, st, B);
+    CK(cudaMemcpyAsync(result, d + o_res, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    return VD_OK;
+}
+
+// ---- `--distance` pass: batches of affine-gap alignments with their CIGARs -----------------
+extern "C" int vd_swg_align_batch(vd_handle *h, int n, const int64_t *q_off, const uint8_t *q_seq, const int64_t *t_off,
+                                  const uint8_t *t_seq, int sub, int open, int extend, int32_t *score, int32_t *cigar) {
+    if (!h || n < 0 || !q_off || !t_off || !score || !cigar) return VD_E_BADINPUT;
+    if (n == 0) return VD_OK;
+    // pass 1: scores (they size the wavefront storage of pass 2)
+    int rc = vd_wf_batch(h, WF_MODE_SCORE, n, q_off, q_seq, t_off, t_seq, nullptr, nullptr, nullptr, nullptr, sub, open, extend, score);
+    if (rc != VD_OK) return rc;
+    cudaStream_t st = h->stream;
+    const int64_t qb = q_off[n], tb = t_off[n];
+    std::vector<int64_t> boff((size_t)n + 1);
+    boff[0] = 0;
+    for (int i = 0; i < n; i++)
+        boff[i + 1] = boff[i] + wf_cigar_bytes((int)(q_off[i + 1] - q_off[i]), (int)(t_off[i + 1] - t_off[i]), score[i]);
+    if (boff[n] > h->scratch_budget) return fail(h, VD_E_NOMEM, "alignment wavefronts need %lld bytes", (long long)boff[n]);
+    // vd_wf_batch left offsets and strings staged in wf_in: lay the same block out again (same sizes)
+    size_t o_qoff = 0, o_toff = o_qoff + 8 * (size_t)(n + 1), o_soff = o_toff + 8 * (size_t)(n + 1), o_md = o_soff + 8 * (size_t)(n + 1);
+    size_t o_mds = o_md + 4 * (size_t)n, o_ms = o_mds + 4 * (size_t)n, o_res = o_ms + 4 * (size_t)n, o_rev = o_res + 4 * (size_t)n;
+    size_t o_q = (o_rev + n + 15) & ~(size_t)15, o_t = (o_q + qb + 15) & ~(size_t)15;
+    u8 *d = (u8 *)h->wf_in.p;
+    CK(h->wf_scratch.ensure((size_t)boff[n] + 4 * (size_t)(qb + tb) + 64));
+    CK(cudaMemcpyAsync(d + o_soff, boff.data(), 8 * (size_t)(n + 1), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d + o_ms, score, 4 * (size_t)n, cudaMemcpyHostToDevice, st));
+    int32_t *d_cigar = (int32_t *)((u8 *)h->wf_scratch.p + ((boff[n] + 15) / 16) * 16);
+    WfCigarBatch B{n, (const int64_t *)(d + o_qoff), (const int64_t *)(d + o_toff), d + o_q, d + o_t, (const int32_t *)(d + o_ms),
+                   (const int64_t *)(d + o_soff), (u8 *)h->wf_scratch.p, d_cigar, (int32_t *)(d + o_res), sub, open, extend};
+    VD_LAUNCH(wf_cigar_kernel, (n + 3) / 4, 128, 0, st, B);
+    CK(cudaMemcpyAsync(score, d + o_res, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(cigar, d_cigar, 4 * (size_t)(qb + tb), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
     return VD_OK;
 }

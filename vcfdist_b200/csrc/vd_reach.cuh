@@ -1,0 +1,298 @@
+// Affine-gap wavefront kernels of the cluster-growing stage: wf_swg_max_reach
+// (src/dist.cpp:2150-2333) and the score of wf_swg_align (:1510-1652), the two functions wf_swg_cluster
+// (src/cluster.cpp:954-1263) spends its time in - the reference runs them one (cluster, direction) after the
+// other on one thread, which made clustering the wall-clock bottleneck on SV input.
+//
+// One WARP per problem, diagonals across lanes.  Diagonal index d in [0, nd), nd = |query| + |truth| - 1, stands
+// for k = d + 1 - |query| (truth index minus query index); three wavefront kinds (M, I, D) hold per diagonal the
+// furthest QUERY index reached, NONE when the diagonal is not reached; only the last max(x, o+e) + 1 scores are
+// kept (a ring in HBM scratch, L2-resident for cluster-sized problems).  A score step reads other diagonals only
+// from EARLIER scores, so all diagonals of a step are independent; the free extension along matches is a per-lane
+// byte-compare loop; the exits of the reference (first diagonal, in ascending order, that reaches the end of a
+// string) are taken by warp vote in chunks of 32 diagonals.
+#pragma once
+#include "vd_common.cuh"
+
+namespace vd {
+
+constexpr int WF_NONE = -2;
+enum { WF_M = 0, WF_I = 1, WF_D = 2, WF_NW = 3 };
+enum { WF_MODE_REACH = 0, WF_MODE_SCORE = 1 };
+
+struct WfBatch {
+    int n;
+    const int64_t *q_off, *t_off;         // [n+1] byte offsets
+    const u8 *q_seq, *t_seq;
+    const int32_t *main_diag, *main_diag_start, *max_score;   // reach only
+    const u8 *reverse;                                        // reach only
+    const int64_t *scratch_off;           // [n+1] int offsets into scratch
+    int32_t *scratch;
+    int32_t *result;                      // reach: furthest truth index; score: the alignment score
+    int x, o, e, mode;
+};
+
+__host__ __device__ inline int wf_ring(int x, int o, int e) { return (x > o + e ? x : o + e) + 1; }
+__host__ __device__ inline int64_t wf_scratch_ints(int qlen, int tlen, int x, int o, int e) {
+    return (int64_t)WF_NW * wf_ring(x, o, e) * (qlen + tlen - 1);
+}
+
+__global__ void __launch_bounds__(128) wf_kernel(WfBatch B) {
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (p >= B.n) return;
+    const u8 *query = B.q_seq + B.q_off[p], *truth = B.t_seq + B.t_off[p];
+    const int qlen = (int)(B.q_off[p + 1] - B.q_off[p]), tlen = (int)(B.t_off[p + 1] - B.t_off[p]);
+    const int x = B.x, o = B.o, e = B.e;
+    const bool reach = B.mode == WF_MODE_REACH;
+    const bool reverse = reach && B.reverse[p];
+    const int nd = qlen + tlen - 1, ring = wf_ring(x, o, e);
+    int *v = B.scratch + B.scratch_off[p];
+    auto wf = [&](int kind, int slot, int d) -> int * { return v + ((int64_t)kind * ring + slot) * nd + d; };
+    auto slot_of = [&](int slot, int back) { const int s = slot - back; return s < 0 ? s + ring : s; };
+    for (int64_t i = lane; i < (int64_t)WF_NW * ring * nd; i += 32) v[i] = WF_NONE;
+    __syncwarp();
+    const int main_diag = reach ? B.main_diag[p] : 0;
+    const int stop_q = reach ? B.main_diag_start[p] - main_diag : 0;                // :2160
+    const int max_score = reach ? B.max_score[p] : 0x7fffffff;
+    int score = 0, slot = 0, result = -1;
+    if (lane == 0) *wf(WF_M, slot, qlen - 1) = -1;                                    // :2166 / :1528: diagonal k = 0, before the first base
+    __syncwarp();
+    bool done = false;
+    for (;;) {
+        // gaps are left for free at the score they were reached with (:2171-2184, :1533-1547); not in the reversed problem
+        if (!reverse)
+            for (int d = lane; d < nd; d += 32) {
+                const int k = d + 1 - qlen;
+                int m = *wf(WF_M, slot, d);
+#pragma unroll
+                for (int kind = WF_I; kind <= WF_D; kind++) {
+                    const int q = *wf(kind, slot, d);
+                    if (q >= 0 && q < qlen && k + q >= 0 && k + q < tlen && q >= m) m = q;
+                }
+                *wf(WF_M, slot, d) = m;
+            }
+        __syncwarp();
+        // free extension along matches, then the exits, diagonals in ascending order (:2187-2212, :1550-1568)
+        for (int d0 = 0; d0 < nd && !done; d0 += 32) {
+            const int d = d0 + lane;
+            bool hit = false;
+            int res = -1;
+            if (d < nd) {
+                int q = *wf(WF_M, slot, d);
+                const int k = d + 1 - qlen;
+                while ((!reach || k != main_diag || q + 1 < stop_q) && q != WF_NONE && k + q >= -1 &&
+                       q < qlen - 1 && k + q < tlen - 1 && query[q + 1] == truth[k + q + 1])
+                    q++;
+                *wf(WF_M, slot, d) = q;
+                if (reach) {
+                    if (q + k == tlen - 1) { hit = true; res = tlen - 1; }                                   // :2205-2207
+                    else if (q == qlen - 1 && q + k >= 0 && q + k < tlen - 1) { hit = true; res = q + k; }   // :2208-2210
+                } else if (q == qlen - 1 && q + k == tlen - 1) { hit = true; res = score; }
+            }
+            const unsigned m = __ballot_sync(FULL, hit);
+            if (m) { result = __shfl_sync(FULL, res, __ffs(m) - 1); done = true; }
+        }
+        if (done) break;
+        if (score == max_score) break;                                                // :2213
+        __syncwarp();                                                                 // the extended wavefront is read by other lanes below
+        // next score (:2225-2311, :1583-1650)
+        score++;
+        slot = slot + 1 == ring ? 0 : slot + 1;
+        for (int d = lane; d < nd; d += 32) {
+            const int k = d + 1 - qlen;
+            // :2228-2232 clears I and D only, the M wavefront of the slot is overwritten through >= tests; wf_swg_align
+            // starts every wavefront of a new score empty (:1583-1587)
+            int mc = reach ? *wf(WF_M, slot, d) : WF_NONE, ic = WF_NONE, dc = WF_NONE;
+            if (score - x >= 0) {                                                     // substitution (:2239-2250)
+                const int pv = x == 0 ? mc : *wf(WF_M, slot_of(slot, x), d);
+                if (pv != WF_NONE && pv + 1 < qlen && k + pv + 1 < tlen && pv + 1 >= mc) mc = pv + 1;
+            }
+            {                                                                         // gap opening (:2252-2275)
+                const int cost = reverse ? e : o + e;
+                if (score - cost >= 0) {
+                    const int ps = slot_of(slot, cost);
+                    if (d > 0) {
+                        const int pv = *wf(WF_M, ps, d - 1);
+                        if (pv != WF_NONE && k + pv < tlen && pv >= dc) dc = pv;
+                    }
+                    if (d < nd - 1) {
+                        const int pv = *wf(WF_M, ps, d + 1);
+                        if (pv != WF_NONE && pv + 1 < qlen && k + pv + 1 < tlen && k + pv + 1 >= 0 && pv + 1 >= ic) ic = pv + 1;
+                    }
+                }
+            }
+            if (reverse && score - o >= 0) {                                          // reversed problem: leaving a gap costs o (:2277-2294)
+                const int ps = slot_of(slot, o);
+                const int pi = o == 0 ? ic : *wf(WF_I, ps, d), pd = o == 0 ? dc : *wf(WF_D, ps, d);
+                if (pi >= 0 && pi < qlen && k + pi >= 0 && k + pi < tlen && pi > mc) mc = pi;
+                if (pd >= 0 && pd < qlen && k + pd >= 0 && k + pd < tlen && pd > mc) mc = pd;
+            }
+            if (score - e >= 0) {                                                     // gap extension (:2296-2311)
+                const int ps = slot_of(slot, e);
+                if (d > 0) {
+                    const int pv = *wf(WF_D, ps, d - 1);
+                    if (pv != WF_NONE && k + pv < tlen && pv >= dc) dc = pv;
+                }
+                if (d < nd - 1) {
+                    const int pv = *wf(WF_I, ps, d + 1);
+                    if (pv != WF_NONE && pv + 1 < qlen && k + pv + 1 < tlen && k + pv + 1 >= 0 && pv + 1 >= ic) ic = pv + 1;
+                }
+            }
+            *wf(WF_M, slot, d) = mc; *wf(WF_I, slot, d) = ic; *wf(WF_D, slot, d) = dc;
+        }
+        __syncwarp();
+    }
+    if (!done) {
+        // the score budget is spent: furthest truth index over everything still in the ring (:2316-2331)
+        int best = 0;
+        for (int64_t i = lane; i < (int64_t)WF_NW * ring * nd; i += 32) {
+            const int d = (int)(i % nd);
+            const int q = v[i], k = d + 1 - qlen;
+            if (q >= 0 && q < qlen && k + q >= 0 && k + q < tlen && k + q > best) best = k + q;
+        }
+        result = __reduce_max_sync(FULL, best);
+    }
+    if (lane == 0) B.result[p] = result;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// `--distance` pass: wf_swg_align WITH its predecessor flags (src/dist.cpp:1510-1652) and
+// wf_swg_backtrack (:2625-2757) - the affine-gap alignment edits_wrapper (:1908-2077) runs per supercluster and
+// haplotype.  Two passes: the score kernel above sizes the storage (every score keeps its three wavefronts and
+// one flag byte per diagonal), this kernel recomputes the wavefronts with their flags - diagonals across the
+// lanes of one warp per problem - and lane 0 walks back from the last cell: on the M wavefront leaving an
+// insertion is preferred over leaving a deletion over a substitution (:2662-2700), inside a gap extending over
+// opening (:2716-2745).  cigar[] has |query| + |truth| entries filled from the back as the reference does: two per
+// match / substitution, one per inserted / deleted base, zeros in front.
+// ------------------------------------------------------------------------------------------
+enum { WFC_INS = 1, WFC_DEL = 2, WFC_MAT = 4, WFC_SUB = 8 };
+
+struct WfCigarBatch {
+    int n;
+    const int64_t *q_off, *t_off;
+    const u8 *q_seq, *t_seq;
+    const int32_t *score;                 // from the score pass
+    const int64_t *store_off;             // [n+1] byte offsets into store
+    u8 *store;                            // per problem: int off[score+1][3][nd], then u8 flag[score+1][3][nd]
+    int32_t *cigar;                       // problem p at q_off[p] + t_off[p]
+    int32_t *result;                      // the score, -1 where the walk back fails (the reference would ERROR())
+    int x, o, e;
+};
+__host__ __device__ inline int64_t wf_cigar_bytes(int qlen, int tlen, int score) {
+    const int64_t cells = (int64_t)(score + 1) * WF_NW * (qlen + tlen - 1);
+    return (5 * cells + 15) / 16 * 16;
+}
+
+__global__ void __launch_bounds__(128) wf_cigar_kernel(WfCigarBatch B) {
+    const int lane = threadIdx.x & 31;
+    const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (p >= B.n) return;
+    const u8 *query = B.q_seq + B.q_off[p], *truth = B.t_seq + B.t_off[p];
+    const int qlen = (int)(B.q_off[p + 1] - B.q_off[p]), tlen = (int)(B.t_off[p + 1] - B.t_off[p]);
+    const int x = B.x, o = B.o, e = B.e, final_score = B.score[p];
+    const int nd = qlen + tlen - 1;
+    const int64_t cells = (int64_t)(final_score + 1) * WF_NW * nd;
+    int *off = (int *)(B.store + B.store_off[p]);
+    u8 *flag = (u8 *)(off + cells);
+    auto OFF = [&](int s, int kind, int d) -> int & { return off[((int64_t)s * WF_NW + kind) * nd + d]; };
+    auto FLG = [&](int s, int kind, int d) -> u8 & { return flag[((int64_t)s * WF_NW + kind) * nd + d]; };
+    for (int64_t i = lane; i < cells; i += 32) { off[i] = WF_NONE; flag[i] = 0; }
+    __syncwarp();
+    if (lane == 0) { OFF(0, WF_M, qlen - 1) = -1; FLG(0, WF_M, qlen - 1) = WFC_MAT; }                  // :1528-1529
+    __syncwarp();
+    for (int score = 0;; score++) {
+        for (int d = lane; d < nd; d += 32) {                                                             // :1533-1547
+            const int k = d + 1 - qlen;
+#pragma unroll
+            for (int kind = WF_I; kind <= WF_D; kind++) {
+                const int q = OFF(score, kind, d);
+                if (q >= 0 && q < qlen && k + q >= 0 && k + q < tlen && q >= OFF(score, WF_M, d)) {
+                    OFF(score, WF_M, d) = q;
+                    FLG(score, WF_M, d) |= (kind == WF_I) ? WFC_INS : WFC_DEL;
+                }
+            }
+            int q = OFF(score, WF_M, d);                                                                  // :1550-1568
+            while (q != WF_NONE && k + q >= -1 && q < qlen - 1 && k + q < tlen - 1 && query[q + 1] == truth[k + q + 1]) q++;
+            OFF(score, WF_M, d) = q;
+        }
+        __syncwarp();
+        if (score == final_score) break;                     // the score pass found the end at this score
+        const int s1 = score + 1;
+        for (int d = lane; d < nd; d += 32) {
+            const int k = d + 1 - qlen;
+            if (s1 - x >= 0) {                                                                            // :1592-1600
+                const int pv = OFF(s1 - x, WF_M, d);
+                if (pv != WF_NONE && pv + 1 < qlen && k + pv + 1 < tlen && pv + 1 >= OFF(s1, WF_M, d)) { OFF(s1, WF_M, d) = pv + 1; FLG(s1, WF_M, d) |= WFC_SUB; }
+            }
+            if (s1 - (o + e) >= 0) {                                                                      // :1602-1625
+                const int ps = s1 - (o + e);
+                if (d > 0) {
+                    const int pv = OFF(ps, WF_M, d - 1);
+                    if (pv != WF_NONE && k + pv < tlen && pv >= OFF(s1, WF_D, d)) { OFF(s1, WF_D, d) = pv; FLG(s1, WF_D, d) |= WFC_SUB; }
+                }
+                if (d < nd - 1) {
+                    const int pv = OFF(ps, WF_M, d + 1);
+                    if (pv != WF_NONE && pv + 1 < qlen && k + pv + 1 < tlen && k + pv + 1 >= 0 && pv + 1 >= OFF(s1, WF_I, d)) { OFF(s1, WF_I, d) = pv + 1; FLG(s1, WF_I, d) |= WFC_SUB; }
+                }
+            }
+            if (s1 - e >= 0) {                                                                            // :1627-1650
+                const int ps = s1 - e;
+                if (d > 0) {
+                    const int pv = OFF(ps, WF_D, d - 1);
+                    if (pv != WF_NONE && k + pv < tlen && pv >= OFF(s1, WF_D, d)) { OFF(s1, WF_D, d) = pv; FLG(s1, WF_D, d) |= WFC_DEL; }
+                }
+                if (d < nd - 1) {
+                    const int pv = OFF(ps, WF_I, d + 1);
+                    if (pv != WF_NONE && pv + 1 < qlen && k + pv + 1 < tlen && k + pv + 1 >= 0 && pv + 1 >= OFF(s1, WF_I, d)) { OFF(s1, WF_I, d) = pv + 1; FLG(s1, WF_I, d) |= WFC_INS; }
+                }
+            }
+        }
+        __syncwarp();
+    }
+    // ---- walk back (:2648-2755), one lane ----
+    int *cigar = B.cigar + B.q_off[p] + B.t_off[p];
+    for (int i = lane; i < qlen + tlen; i += 32) cigar[i] = 0;
+    __syncwarp();
+    if (lane) return;
+    int cp = qlen + tlen - 1, kind = WF_M, qi = qlen - 1, ti = tlen - 1, s = final_score;
+    bool failed = false;
+    while ((qi >= 0 || ti >= 0) && !failed) {
+        if (s < 0) { failed = true; break; }
+        const int d = qlen - 1 + (ti - qi);
+        if (kind == WF_M) {
+            const int f = FLG(s, WF_M, d);
+            if (f & (WFC_INS | WFC_DEL)) {                                    // a gap was left here for free
+                const int g = (f & WFC_INS) ? WF_I : WF_D;
+                const int stop = OFF(s, g, d);
+                while (qi > stop) { cigar[cp--] = WFC_MAT; cigar[cp--] = WFC_MAT; qi--; ti--; if (qi < 0 || ti < 0) { failed = true; break; } }
+                kind = g;
+            } else if (f & WFC_SUB) {
+                if (s - x < 0) { failed = true; break; }
+                const int stop = OFF(s - x, WF_M, d) + 1;
+                while (qi > stop) { cigar[cp--] = WFC_MAT; cigar[cp--] = WFC_MAT; qi--; ti--; if (qi < 0 || ti < 0) { failed = true; break; } }
+                if (failed) break;
+                cigar[cp--] = WFC_SUB; cigar[cp--] = WFC_SUB; qi--; ti--;
+                s -= x;
+            } else if (f & WFC_MAT) {
+                while (qi >= 0 && ti >= 0) { cigar[cp--] = WFC_MAT; cigar[cp--] = WFC_MAT; qi--; ti--; }
+                if (qi >= 0 || ti >= 0) failed = true;
+            } else failed = true;
+        } else if (kind == WF_I) {
+            const int f = FLG(s, WF_I, d);
+            if (f & WFC_INS) { cigar[cp--] = WFC_INS; qi--; s -= e; }
+            else if (f & WFC_SUB) { cigar[cp--] = WFC_INS; qi--; kind = WF_M; s -= o + e; }
+            else failed = true;
+        } else {
+            const int f = FLG(s, WF_D, d);
+            if (f & WFC_DEL) { cigar[cp--] = WFC_DEL; ti--; s -= e; }
+            else if (f & WFC_SUB) { cigar[cp--] = WFC_DEL; ti--; kind = WF_M; s -= o + e; }
+            else failed = true;
+        }
+        if (!(qi == -1 && ti == -1) && (qi < 0 || ti < 0)) failed = true;
+    }
+    B.result[p] = failed ? -1 : final_score;
+}
+
+}  // namespace vd
