@@ -37,7 +37,7 @@ sys.path.insert(0, ROOT)
 from vcfdist_b200 import capi, shard
 from workloads import synth  # noqa: E402
 from oracle import checkers  # noqa: E402  (CPU-baseline legs only: the reference arm and cpu_baseline)
-from vcfdist_b200.batch import Batch, Out, vd_batch_in, vd_batch_out  # noqa: E402
+from vcfdist_b200.batch import Batch, Out, PackedOut, vd_batch_in, vd_batch_out  # noqa: E402
 
 WORKLOADS = {
     "wgs": dict(n_sc=3_600_000, sv_frac=0.0, config="HG002 WGS SNP+INDEL vs GIAB v4.2.1, 1xB200 (BASELINE configs[2])"),
@@ -177,6 +177,53 @@ def tie_count(status, n_sc):
     return int((status[: 4 * n_sc].reshape(-1, 4) & 1).any(axis=1).sum())
 
 
+def cli_timer(stderr: str, idx: int) -> float:
+    """Seconds of timer [idx] in the reference CLI's own end-of-run report (src/timer.cpp:29-31)."""
+    import re
+    m = re.search(r"\[%d\] [a-z/ ]+:\s*([0-9.]+)s" % idx, stderr)
+    return float(m.group(1)) if m else float("nan")
+
+
+def run_seam(args, b):
+    """The product where a vcfdist user meets it: the reference's own timer around precision_recall_threads_wrapper
+    (g.timers[TIME_PR_ALN], src/main.cpp:218-221).  (1) function seam: the harness rebuilds the reference's
+    superclusterData for the bench batch and calls the wrapper, once resolved to the reference's own definition
+    (that is the reference arm / cpu_baseline) and once to the GPU drop-in (libvdseam.so): pack + vd_run_packed +
+    float step + scatter, host threads = -t.  (2) the reference CLI and the CLI with the drop-in linked in
+     on a seeded synthetic VCF pair, each reporting its own '[5] precision/recall' timer."""
+    cores = os.cpu_count() or 1
+    res = {}
+    if checkers.seam_available():
+        secs, bds = [], []
+        for _ in range(3):
+            _, sec = checkers.reference_run(b, threads=cores, seam=True)
+            secs.append(sec); bds.append(checkers.seam_breakdown())
+        best = int(np.argmin(secs[1:])) + 1
+        res["function_seam"] = {"api": "precision_recall_threads_wrapper (drop-in, vcfdist_b200/host/pr_dropin.cpp) on the reference's superclusterData",
+                                "n_superclusters": b.n_sc, "ms_first_call": secs[0] * 1e3, "ms_per_call": secs[best] * 1e3,
+                                "breakdown_ms": bds[best], "host_threads": cores}
+    ref, cli = (os.path.join(ROOT, "oracle", "_ref", n) for n in ("vcfdist_ref", "vcfdist_b200cli"))
+    if os.path.exists(ref) and os.path.exists(cli) and args.cli_contig_len > 0:
+        import tempfile
+        from workloads import vcfgen
+        with tempfile.TemporaryDirectory() as tmp:
+            q, t, fa = vcfgen.generate(os.path.join(tmp, "in"), seed=args.seed, contig_len=args.cli_contig_len, n_contigs=2)
+            out = {}
+            for name, exe in (("reference", ref), ("drop_in", cli)):
+                od = os.path.join(tmp, name)
+                os.makedirs(od, exist_ok=True)
+                t0 = time.perf_counter()
+                r = subprocess.run([exe, q, t, fa, "-p", od + "/", "-v", "1", "-t", str(cores), "-c", "gap", "50"],
+                                   capture_output=True, text=True, cwd=od)
+                out[name] = {"rc": r.returncode, "wall_s": time.perf_counter() - t0, "timer_5_precision_recall_s": cli_timer(r.stderr, 5),
+                             "timer_9_total_s": cli_timer(r.stderr, 9)}
+            same = all(open(os.path.join(tmp, "reference", f)).read() == open(os.path.join(tmp, "drop_in", f)).read()
+                       for f in ("precision-recall-summary.tsv", "superclusters.tsv", "phasing-summary.tsv"))
+            res["cli"] = {"input": f"workloads.vcfgen seed {args.seed}, 2 contigs x {args.cli_contig_len} bp, -c gap 50, -t {cores}",
+                          "reference": out["reference"], "drop_in": out["drop_in"], "summary_files_identical": bool(same)}
+    return res
+
+
 def run_secondary(eng, args, dev, torch):
     """BASELINE configs[3] (WGS + SV tail to 10 kb) at FULL scale through vd_run with host buffers: 3.6 M
     superclusters of the demo mixture of which 0.3 % carry one 50 bp..10 kb INS/DEL, with its own CPU baseline
@@ -248,6 +295,8 @@ def main():
     ap.add_argument("--secondary", action="store_true", default=True,
                     help="also time the SV-bearing workload (BASELINE configs[3]) at full scale through vd_run (default at N=1)")
     ap.add_argument("--no-secondary", dest="secondary", action="store_false")
+    ap.add_argument("--no-seam", action="store_true", help="skip the timing at the reference's own seam (function harness + CLI)")
+    ap.add_argument("--cli-contig-len", type=int, default=6_000_000, help="seam timing through the CLI: bases per synthetic contig (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         args.warmup = max(args.warmup, 1)
@@ -395,25 +444,34 @@ def main():
     for k in ("ref_off", "ref_seq", "var_off", "var_pos", "var_rlen", "var_type", "alt_off", "alt_seq", "var_qual"):
         t_, a_ = pin(getattr(b, k)); keep.append(t_); hb[k] = a_
     bp = Batch(**hb, max_qual=b.max_qual)
+    # results as 16-bit records (vd_run_packed): the copy out over PCIe bounds the end-to-end step, and the host
+    # float step (vd_finalize_packed) reads them as they are; the wide records (vd_run) are timed beside it
     ho = Out(b.n_sc, n_var)
     for f in Out.FIELDS:
         t_, a_ = pin(getattr(ho, f)); keep.append(t_); setattr(ho, f, a_)
-    for _ in range(3):
-        eng.run(bp, ho)
-    barrier()
+    hp = PackedOut(b.n_sc, n_var)
+    for f in PackedOut.FIELDS:
+        t_, a_ = pin(getattr(hp, f)); keep.append(t_); setattr(hp, f, a_)
     e2e_steps = max(3, min(args.steps, 7))
-    e2e_times = []
-    for _ in range(e2e_steps):                 # vd_run is synchronous: results are in host memory on return
-        t0 = time.perf_counter()
-        eng.run(bp, ho)
-        e2e_times.append((time.perf_counter() - t0) * 1e3)
-    torch.cuda.synchronize()
+
+    def time_e2e(call):
+        for _ in range(3):
+            call()
+        barrier()
+        ts = []
+        for _ in range(e2e_steps):             # synchronous calls: results are in host memory on return
+            t0 = time.perf_counter()
+            call()
+            ts.append((time.perf_counter() - t0) * 1e3)
+        torch.cuda.synchronize()
+        return ts, eng.stats()
+    wide_times, st_w = time_e2e(lambda: eng.run(bp, ho))
+    e2e_times, st_e = time_e2e(lambda: eng.run_packed(bp, hp))
     e2e_ms = float(np.mean(e2e_times))
-    st_e = eng.stats()
-    te = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    te = torch.tensor([e2e_ms, float(np.mean(wide_times))], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_ms = float(te.item())
+    e2e_ms, e2e_wide_ms = float(te[0].item()), float(te[1].item())
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -463,8 +521,10 @@ def main():
             "e2e": {"value": cells_total / (e2e_ms * 1e-3) / 1e9, "unit": "Gcells/s",
                     "superclusters_per_s": sc_total / (e2e_ms * 1e-3), "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(st_e["h2d_bytes"]), "d2h_bytes_per_step": int(st_e["d2h_bytes"]),
-                    "api": "vd_run (C-ABI, pinned host buffers)", "steps": e2e_steps,
-                    "ms_min": float(min(e2e_times)), "ms_max": float(max(e2e_times))},
+                    "api": "vd_run_packed (C-ABI, pinned host buffers, 16-bit result records)", "steps": e2e_steps,
+                    "ms_min": float(min(e2e_times)), "ms_max": float(max(e2e_times)),
+                    "wide_records": {"api": "vd_run (32-bit result records)", "ms_per_step": e2e_wide_ms,
+                                     "d2h_bytes_per_step": int(st_w["d2h_bytes"])}},
             "gpu_launches": int(launches),
             "tie_superclusters": {"count": tie_count(ho.status, b.n_sc) if world == 1 else None, "of": b.n_sc,
                                   "note": "superclusters with VD_ST_TIE on this rank: an ambiguous swap edge on an optimal path, where the "
@@ -493,6 +553,8 @@ def main():
                                                                   "active_lanes_per_instruction") if k_ in t_}
         if args.secondary and world == 1 and args.workload == "wgs":
             line["secondary"] = run_secondary(eng, args, dev, torch)
+        if not args.no_seam and world == 1 and args.workload == "wgs":
+            line["seam"] = run_seam(args, b)
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
             sb, scells, _ = make_workload(args.workload, args.cpu_sample, args.seed, 0, 1, args.sv_max)

@@ -54,6 +54,8 @@ extern "C" {
 #define VD_E_NOMEM      -5
 #define VD_E_ALIGN      -6   /* an alignment hit a fatal reference condition
                                 (src/dist.cpp:314, :440, :606, :644, :937)             */
+#define VD_E_RANGE      -7   /* vd_run_packed: a value does not fit the 16-bit records
+                                (call vd_run instead)                                  */
 
 /* per-alignment status bits, vd_batch_out.status[4*sc + i] */
 #define VD_ST_TIE            0x0001u  /* a swap edge on a reachable optimal cell had more than one
@@ -120,6 +122,20 @@ typedef struct vd_batch_out {
                                   VD_ASSIGN_REF_FP the variant's own quality (:1163)               */
 } vd_batch_out;
 
+/* The same results in 16-bit records: 20 bytes per supercluster and 20 per variant instead of 40 and 34, for
+ * callers that keep them as they are (vd_finalize_packed reads them directly) - the copy out over PCIe is what
+ * bounds an end-to-end step on a WGS batch.  Values that do not fit (a score, ref_ed or query_ed of 65535 or
+ * more, 16384 or more sync groups in one alignment) make vd_run_packed return VD_E_RANGE.                      */
+typedef struct vd_packed_out {
+    uint16_t *aln_score;       /* [4*n_sc] 0xffff: no score (malformed supercluster)                            */
+    uint8_t  *aln_planes;      /* [4*n_sc] bit 0 end plane, bit 1 origin plane                                  */
+    uint16_t *status;          /* [4*n_sc] VD_ST_* bits                                                         */
+    uint16_t *sync_group;      /* [2*n_var] assigned << 14 | sync_group                                         */
+    uint16_t *ref_ed;          /* [2*n_var]                                                                     */
+    uint16_t *query_ed;        /* [2*n_var]                                                                     */
+    float    *callq;           /* [2*n_var]                                                                     */
+} vd_packed_out;
+
 /* counters of the last vd_run*/
 typedef struct vd_stats {
     int64_t n_sc, n_var;
@@ -182,6 +198,15 @@ void vd_destroy(vd_handle *h);
 
 /* Synchronous.  Host buffers in, host buffers out: H2D copy, kernels, D2H copy.          */
 int  vd_run(vd_handle *h, const vd_batch_in *in, vd_batch_out *out);
+int  vd_run_packed(vd_handle *h, const vd_batch_in *in, vd_packed_out *out);
+int  vd_finalize_packed(const vd_batch_in *in, const vd_packed_out *out,
+                        double phase_threshold, double credit_threshold, vd_final *fin);
+
+/* Page-locked host memory for the buffers of vd_run / vd_run_packed (plain cudaHostAlloc / cudaFreeHost, so that a
+ * caller needs no CUDA headers): copies from and to pageable memory run at a fraction of the PCIe rate.
+ * NULL when the allocation fails.                                                                             */
+void *vd_host_alloc(int64_t bytes);
+void  vd_host_free(void *p);
 
 /* Same computation with every pointer of `in` and `out` already resident in this GPU's
  * HBM (n_var and the byte sizes are passed since the offsets live on the device).

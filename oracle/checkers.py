@@ -3,6 +3,8 @@
   liboracle.so          the plain-C restatement of the path (oracle/vd_oracle.c)
   libvdref.so / B       the reference's own object code behind a function-level harness
                         (oracle/ref_harness.cpp; B = with the canonical tie-break patch)
+  libvdseam.so          that harness with the hot-path call resolved to the GPU drop-in (seam timing and parity of
+                        vcfdist_b200/host/pr_dropin.cpp; here the harness is the test bench, the drop-in the product)
 
 Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may import this module;
 it is the checker, never the thing measured or shipped.  The product path
@@ -59,12 +61,29 @@ def reference_available(canonical: bool = False) -> bool:
 _ref_libs = {}
 
 
+def seam_available() -> bool:
+    return os.path.exists(os.path.join(ORACLE_DIR, "libvdseam.so"))
+
+
+def seam_breakdown() -> dict:
+    """Host-side times (ms) of the drop-in's last call through libvdseam.so (reference_run(..., seam=True))."""
+    lib = _ref_libs["libvdseam.so"]
+    a = (C.c_double * 10)()
+    lib.vd_dropin_last_times(a)
+    keys = ("wait_for_handle", "pack", "vd_run_wall", "vd_run_device", "status_scan", "float_step", "scatter")
+    d = {k: float(a[i]) for i, k in enumerate(keys)}
+    d.update(host_threads=int(a[7]), page_locked=bool(a[8]), tie_superclusters=int(a[9]))
+    return d
+
+
 def reference_run(batch: Batch, canonical: bool = False, threads: int = 1, max_ram: float = 64.0,
                   phase_threshold: float = 0.6, credit_threshold: float = 0.7,
-                  max_qual: int = 60) -> Tuple[dict, float]:
+                  max_qual: int = 60, seam: bool = False) -> Tuple[dict, float]:
     """Run the REFERENCE's own object code (oracle/_ref/libvdref[B].so) on the batch.
-    Returns (results dict like Final.trimmed(), seconds inside precision_recall_threads_wrapper)."""
-    name = "libvdrefB.so" if canonical else "libvdref.so"
+    Returns (results dict like Final.trimmed(), seconds inside precision_recall_threads_wrapper).
+    seam=True: the same harness and reference data structures with precision_recall_threads_wrapper resolved to the
+    GPU drop-in (libvdseam.so) - the product measured where the reference's own timer sits (needs a GPU)."""
+    name = "libvdseam.so" if seam else "libvdrefB.so" if canonical else "libvdref.so"
     if name not in _ref_libs:
         lib = C.CDLL(os.path.join(ORACLE_DIR, name))
         lib.vdref_run.argtypes = [C.POINTER(vd_batch_in), C.POINTER(vdref_out), C.c_int, C.c_double,

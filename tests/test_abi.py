@@ -26,13 +26,27 @@ def test_library_exports_every_declared_symbol():
     assert lib.vd_abi_version() == 2
 
 
-def test_struct_layouts_match_header():
-    # 11 pointers/ints + float, 9 pointers, 9 pointers: the ctypes mirrors must have the C sizes
-    from vcfdist_b200.batch import vd_batch_in, vd_batch_out, vd_final, vd_stats
-    assert C.sizeof(vd_batch_in) == 8 + 10 * 8 + 8
-    assert C.sizeof(vd_batch_out) == 9 * 8
-    assert C.sizeof(vd_final) == 9 * 8
-    assert C.sizeof(vd_stats) == 10 * 8 + 10 * 4 + 7 * 8
+def test_struct_layouts_match_header(tmp_path):
+    """The ctypes mirrors have the sizes and field offsets gcc gives the structs of include/vcfdist_b200.h."""
+    import subprocess
+    from vcfdist_b200 import batch
+    names = ["vd_batch_in", "vd_batch_out", "vd_packed_out", "vd_final", "vd_stats"]
+    prog = ['#include <stdio.h>', '#include <stddef.h>', '#include "vcfdist_b200.h"', 'int main(void) {']
+    for n in names:
+        prog.append(f'printf("{n} %zu\\n", sizeof({n}));')
+        for f, _ in getattr(batch, n)._fields_:
+            prog.append(f'printf("{n}.{f} %zu\\n", offsetof({n}, {f}));')
+    prog.append('return 0; }')
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(prog))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    want = dict(line.split() for line in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for n in names:
+        cls = getattr(batch, n)
+        assert C.sizeof(cls) == int(want[n]), n
+        for f, _ in cls._fields_:
+            assert getattr(cls, f).offset == int(want[f"{n}.{f}"]), (n, f)
 
 
 @pytest.mark.skipif(has_gpu(), reason="checks the no-GPU failure mode")
@@ -58,6 +72,31 @@ def test_finalize_host_step():
     assert list(fin["errtypes"]) == [0, 0, 1, 2]
     assert fin["credit"][3] == np.float32(1) - np.float32(1) / np.float32(3)
     assert fin["callq"][3] == 60.0 and fin["callq"][2] == 10.0
+
+
+def test_finalize_packed_equals_finalize():
+    """vd_finalize_packed over the 16-bit records = vd_finalize over the wide ones (random records, multi-threaded
+    split included: > 200 k superclusters)."""
+    from vcfdist_b200.batch import PackedOut
+    from workloads import synth
+    b = synth.wgs_like(5, 210_000)
+    rng = np.random.default_rng(7)
+    out, pk = Out(b.n_sc, b.n_var), PackedOut(b.n_sc, b.n_var)
+    a, v = 4 * b.n_sc, 2 * b.n_var
+    out.aln_score[:a] = rng.integers(-1, 40, a)
+    out.assigned[:v] = rng.integers(0, 3, v)
+    out.sync_group[:v] = rng.integers(0, 9, v)
+    out.ref_ed[:v] = rng.integers(1, 12, v)
+    out.query_ed[:v] = rng.integers(0, 12, v)
+    out.callq[:v] = rng.integers(0, 60, v).astype(np.float32)
+    pk.aln_score[:a] = np.where(out.aln_score[:a] < 0, 0xFFFF, out.aln_score[:a]).astype(np.uint16)
+    pk.sync_group[:v] = (out.assigned[:v].astype(np.uint16) << 14) | out.sync_group[:v].astype(np.uint16)
+    pk.ref_ed[:v] = out.ref_ed[:v]; pk.query_ed[:v] = out.query_ed[:v]; pk.callq[:v] = out.callq[:v]
+    f1, f2 = capi.finalize(b, out).trimmed(), capi.finalize(b, pk).trimmed()
+    for k in f1:
+        assert (f1[k].view(np.uint8) == f2[k].view(np.uint8)).all(), k
+    w = pk.widened()
+    assert (w["aln_score"] == out.aln_score[:a]).all() and (w["assigned"] == out.assigned[:v]).all()
 
 
 def test_product_package_never_touches_the_oracle():

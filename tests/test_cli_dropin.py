@@ -49,3 +49,19 @@ def test_cli_outputs_identical(tmp_path, seed, extra):
     for f in FILES:
         assert filecmp.cmp(os.path.join(c, f), os.path.join(b, f), shallow=False), f
     assert vcf_body(os.path.join(c, "summary.vcf")) == vcf_body(os.path.join(b, "summary.vcf"))
+
+
+@pytest.mark.parametrize("name", ["demo", "adv_11", "sv_21"])
+def test_dropin_at_the_function_seam(name):
+    """precision_recall_threads_wrapper of the drop-in (parallel packer, vd_run_packed, host float step, parallel
+    scatter) called on the reference's own superclusterData by the harness (libvdseam.so) against the recorded
+    results of the reference with the canonical tie-break, twice (the handle and its page-locked arena persist)."""
+    from conftest import FINAL_KEYS, load_golden, mismatches
+    from oracle import checkers
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libvdseam.so")):
+        pytest.skip("libvdseam.so not built")
+    b, _, refB = load_golden(name)
+    for threads in (1, 8):
+        got, sec = checkers.reference_run(b, threads=threads, seam=True)
+        assert mismatches(got, refB, FINAL_KEYS) == {}
+        assert sec > 0

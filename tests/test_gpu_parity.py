@@ -374,3 +374,38 @@ def test_chunked_pipeline_matches_single_pass():
     st = e.stats()
     assert st["cells"] == int(b.cells().sum()) and st["n_short"] + st["n_long"] == 4 * b.n_sc
     e.close()
+
+
+def test_packed_records_equal_wide_records(engine):
+    """vd_run_packed (16-bit records) against vd_run on the demo golden + SV pairs, and through the host step."""
+    from vcfdist_b200.batch import PackedOut
+    b0, _, refB = load_golden("demo")
+    for b in (b0, Batch.concat([synth.wgs_like(31, 3000), synth.sv_pairs(32, 2, 700, divergence=0.02)])):
+        wide = engine.run(b).trimmed()
+        pk = engine.run_packed(b)
+        w = pk.widened()
+        assert mismatches(w, wide, OUT_KEYS) == {}
+        fin_w, fin_p = capi.finalize(b, engine.run(b)).trimmed(), capi.finalize(b, pk).trimmed()
+        assert mismatches(fin_p, fin_w, FINAL_KEYS) == {}
+    assert mismatches(capi.finalize(b0, engine.run_packed(b0)).trimmed(), refB, FINAL_KEYS) == {}
+    assert pk.nbytes() < 0.6 * sum(getattr(engine.run(b), f).nbytes for f in OUT_KEYS)
+
+
+def test_packed_records_refuse_values_that_do_not_fit(engine):
+    """A supercluster with more than 16383 sync groups... is not constructible within the size limits, but a ref_ed
+    of 65535 or more is: a 70 kb deletion on the truth side only."""
+    rng = np.random.default_rng(3)
+    ref = rng.integers(0, 4, 70_100).astype(np.uint8)
+    ref = np.frombuffer(b"ACGT", np.uint8)[ref].tobytes()
+    bb = BatchBuilder(max_qual=60)
+    bb.add(ref, [[], [], [(20, TYPE_DEL, 70_000, b"", 30.0)], [(20, TYPE_DEL, 70_000, b"", 30.0)]])
+    b = bb.build()
+    try:
+        wide = engine.run(b)
+    except capi.VdError as e:          # shapes beyond the long path's limits are refused outright
+        assert e.code in (-4, -5)
+        return
+    assert int(wide.aln_score[:4].max()) >= 65535 or int(wide.ref_ed.max()) >= 65535
+    with pytest.raises(capi.VdError) as ei:
+        engine.run_packed(b)
+    assert ei.value.code == -7

@@ -39,6 +39,10 @@ class vd_batch_in(C.Structure):
     ]
 
 
+class vd_packed_out(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("aln_score", "aln_planes", "status", "sync_group", "ref_ed", "query_ed", "callq")]
+
+
 class vd_batch_out(C.Structure):
     _fields_ = [
         ("aln_score", C.c_void_p),
@@ -365,6 +369,45 @@ class Out:
         for f in self.FIELDS[4:]:
             d[f] = getattr(self, f)[:v]
         return d
+
+
+@dataclass
+class PackedOut:
+    """Host-side `vd_packed_out` buffers (16-bit records)."""
+    n_sc: int
+    n_var: int
+
+    FIELDS = ("aln_score", "aln_planes", "status", "sync_group", "ref_ed", "query_ed", "callq")
+
+    def __post_init__(self):
+        a, v = max(4 * self.n_sc, 1), max(2 * self.n_var, 1)
+        self.aln_score = np.full(a, 0xFFFF, np.uint16)
+        self.aln_planes = np.zeros(a, np.uint8)
+        self.status = np.zeros(a, np.uint16)
+        self.sync_group = np.zeros(v, np.uint16)
+        self.ref_ed = np.zeros(v, np.uint16)
+        self.query_ed = np.zeros(v, np.uint16)
+        self.callq = np.zeros(v, np.float32)
+
+    def as_c(self) -> vd_packed_out:
+        s = vd_packed_out()
+        for f in self.FIELDS:
+            setattr(s, f, _ptr(getattr(self, f)))
+        s._keep = self
+        return s
+
+    def widened(self) -> dict:
+        """The same results in the field layout of Out.trimmed()."""
+        a, v = 4 * self.n_sc, 2 * self.n_var
+        sc = self.aln_score[:a].astype(np.int32)
+        sc[self.aln_score[:a] == 0xFFFF] = -1
+        return {"aln_score": sc, "aln_end_plane": self.aln_planes[:a] & 1, "aln_beg_plane": (self.aln_planes[:a] >> 1) & 1,
+                "status": self.status[:a].astype(np.uint32), "assigned": (self.sync_group[:v] >> 14).astype(np.uint8),
+                "sync_group": (self.sync_group[:v] & 0x3FFF).astype(np.int32), "ref_ed": self.ref_ed[:v].astype(np.int32),
+                "query_ed": self.query_ed[:v].astype(np.int32), "callq": self.callq[:v]}
+
+    def nbytes(self) -> int:
+        return sum(getattr(self, f).nbytes for f in self.FIELDS)
 
 
 @dataclass

@@ -14,13 +14,14 @@ from typing import Optional, Tuple
 
 import numpy as np
 
-from .batch import Batch, Final, Out, vd_batch_in, vd_batch_out, vd_final, vd_stats
+from .batch import Batch, Final, Out, PackedOut, vd_batch_in, vd_batch_out, vd_final, vd_packed_out, vd_stats
 
 _ROOT = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_ROOT, "libvcfdist_b200.so")
 
 EXPORTS = ("vd_abi_version", "vd_create", "vd_destroy", "vd_run", "vd_run_device", "vd_run_device_slice",
-           "vd_finalize", "vd_get_stats", "vd_last_error", "vd_stream", "vd_wf_batch", "vd_swg_align_batch")
+           "vd_finalize", "vd_get_stats", "vd_last_error", "vd_stream", "vd_wf_batch", "vd_swg_align_batch",
+           "vd_run_packed", "vd_finalize_packed", "vd_host_alloc", "vd_host_free")
 
 _lib = None
 
@@ -44,6 +45,14 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.vd_destroy.restype = None
     lib.vd_run.argtypes = [C.c_void_p, C.POINTER(vd_batch_in), C.POINTER(vd_batch_out)]
     lib.vd_run.restype = C.c_int
+    lib.vd_run_packed.argtypes = [C.c_void_p, C.POINTER(vd_batch_in), C.POINTER(vd_packed_out)]
+    lib.vd_run_packed.restype = C.c_int
+    lib.vd_finalize_packed.argtypes = [C.POINTER(vd_batch_in), C.POINTER(vd_packed_out), C.c_double, C.c_double, C.POINTER(vd_final)]
+    lib.vd_finalize_packed.restype = C.c_int
+    lib.vd_host_alloc.argtypes = [C.c_int64]
+    lib.vd_host_alloc.restype = C.c_void_p
+    lib.vd_host_free.argtypes = [C.c_void_p]
+    lib.vd_host_free.restype = None
     lib.vd_run_device.argtypes = [C.c_void_p, C.POINTER(vd_batch_in), C.POINTER(vd_batch_out),
                                   C.c_int64, C.c_int64, C.c_int64]
     lib.vd_run_device.restype = C.c_int
@@ -74,12 +83,13 @@ class VdError(RuntimeError):
         self.code = code
 
 
-def finalize(batch: Batch, out: Out, phase_threshold: float = 0.6, credit_threshold: float = 0.7) -> Final:
-    """Host float step (store_phase + credit thresholds); needs no GPU."""
-    lib = load_library()
+def finalize(batch: Batch, out, phase_threshold: float = 0.6, credit_threshold: float = 0.7, lib=None) -> Final:
+    """Host float step (store_phase + credit thresholds) over wide (Out) or 16-bit (PackedOut) records; needs no GPU."""
+    lib = lib or load_library()
     fin = Final(batch.n_sc, batch.n_var)
     cin, cout, cfin = batch.as_c(), out.as_c(), fin.as_c()
-    rc = lib.vd_finalize(C.byref(cin), C.byref(cout), phase_threshold, credit_threshold, C.byref(cfin))
+    fn = lib.vd_finalize_packed if isinstance(out, PackedOut) else lib.vd_finalize
+    rc = fn(C.byref(cin), C.byref(cout), phase_threshold, credit_threshold, C.byref(cfin))
     if rc != 0:
         raise VdError(rc, "vd_finalize")
     return fin
@@ -117,6 +127,13 @@ class Engine:
         out = out or Out(batch.n_sc, batch.n_var)
         cin, cout = batch.as_c(), out.as_c()
         self._check(self.lib.vd_run(self.h, C.byref(cin), C.byref(cout)))
+        return out
+
+    def run_packed(self, batch: Batch, out: Optional[PackedOut] = None) -> PackedOut:
+        """vd_run_packed: the same results in 16-bit records (raises VdError -7 when a value does not fit)."""
+        out = out or PackedOut(batch.n_sc, batch.n_var)
+        cin, cout = batch.as_c(), out.as_c()
+        self._check(self.lib.vd_run_packed(self.h, C.byref(cin), C.byref(cout)))
         return out
 
     def run_device(self, din: vd_batch_in, dout: vd_batch_out, n_var: int, ref_bytes: int, alt_bytes: int):

@@ -88,6 +88,7 @@ struct vd_handle {
         DevBuf in_ref_off, in_ref_seq, in_rplane, in_var_off, in_var_pos, in_var_rlen, in_var_type,
                in_alt_off, in_alt_seq, in_var_qual;
         DevBuf o_score, o_endp, o_begp, o_status, o_assigned, o_sg, o_red, o_qed, o_callq;
+        DevBuf p_score, p_planes, p_status, p_sg, p_red, p_qed;       // 16-bit records (vd_run_packed)
         cudaEvent_t in_done = nullptr, out_done = nullptr;
         bool out_pending = false;
     } stage[NST];
@@ -97,6 +98,7 @@ struct vd_handle {
     // work
     DevBuf need_dense, bytes, offs, cubtmp, slab, hap_ok, wave_desc, band_state, band_lb, dense_bytes, dense_off, dense;
     DevBuf wf_in, wf_scratch;       // vd_wf_batch: staged problems, wavefront rings
+    unsigned *h_range = nullptr;            // pinned + mapped: set by pack_out_kernel when a value does not fit 16 bits
     WaveItems *h_witems = nullptr;          // pinned + mapped (a small D2H memcpy would queue behind the bulk result copies of vd_run)
 };
 
@@ -145,6 +147,7 @@ extern "C" int vd_create(int device, int64_t scratch_bytes, vd_handle **out) {
     cok &= cudaStreamCreateWithFlags(&h->s_plan, cudaStreamNonBlocking) == cudaSuccess;
     cok &= cudaStreamCreateWithFlags(&h->s_epi, cudaStreamNonBlocking) == cudaSuccess;
     cok &= cudaHostAlloc((void **)&h->h_witems, sizeof(WaveItems), cudaHostAllocMapped) == cudaSuccess;
+    cok &= cudaHostAlloc((void **)&h->h_range, 64, cudaHostAllocMapped) == cudaSuccess;
     if (scratch_bytes <= 0) {
         size_t fr = 0, tot = 0;
         cudaMemGetInfo(&fr, &tot);
@@ -186,7 +189,8 @@ extern "C" void vd_destroy(vd_handle *h) {
     for (auto &sg : h->stage) {
         DevBuf *sb[] = {&sg.in_ref_off, &sg.in_ref_seq, &sg.in_rplane, &sg.in_var_off, &sg.in_var_pos, &sg.in_var_rlen,
                         &sg.in_var_type, &sg.in_alt_off, &sg.in_alt_seq, &sg.in_var_qual, &sg.o_score, &sg.o_endp,
-                        &sg.o_begp, &sg.o_status, &sg.o_assigned, &sg.o_sg, &sg.o_red, &sg.o_qed, &sg.o_callq};
+                        &sg.o_begp, &sg.o_status, &sg.o_assigned, &sg.o_sg, &sg.o_red, &sg.o_qed, &sg.o_callq,
+                        &sg.p_score, &sg.p_planes, &sg.p_status, &sg.p_sg, &sg.p_red, &sg.p_qed};
         for (DevBuf *b : sb) b->release();
         if (sg.in_done) cudaEventDestroy(sg.in_done);
         if (sg.out_done) cudaEventDestroy(sg.out_done);
@@ -208,6 +212,7 @@ extern "C" void vd_destroy(vd_handle *h) {
     if (h->s_plan) cudaStreamDestroy(h->s_plan);
     if (h->s_epi) cudaStreamDestroy(h->s_epi);
     if (h->h_witems) cudaFreeHost(h->h_witems);
+    if (h->h_range) cudaFreeHost(h->h_range);
     for (auto &e : h->ev) if (e) cudaEventDestroy(e);
     for (int c = 0; c < N_WCLS; c++) {
         for (auto &e : h->sev[c]) if (e) cudaEventDestroy(e);
@@ -588,13 +593,30 @@ static int quiesce(vd_handle *h, int rc) {
     return rc;
 }
 
+static int run_host(vd_handle *h, const vd_batch_in *in, vd_batch_out *out, vd_packed_out *pout);
 extern "C" int vd_run(vd_handle *h, const vd_batch_in *in, vd_batch_out *out) {
     if (!h || !in || !out) return VD_E_BADINPUT;
+    return run_host(h, in, out, nullptr);
+}
+extern "C" int vd_run_packed(vd_handle *h, const vd_batch_in *in, vd_packed_out *pout) {
+    if (!h || !in || !pout) return VD_E_BADINPUT;
+    return run_host(h, in, nullptr, pout);
+}
+extern "C" void *vd_host_alloc(int64_t bytes) {
+    void *p = nullptr;
+    if (bytes <= 0 || cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+extern "C" void vd_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+// vd_run (out) / vd_run_packed (pout): exactly one of the two is given
+static int run_host(vd_handle *h, const vd_batch_in *in, vd_batch_out *out, vd_packed_out *pout) {
     CK(cudaSetDevice(h->device));
     const int64_t n_sc = in->n_sc;
     if (n_sc < 0) return fail(h, VD_E_BADINPUT, "negative n_sc");
     h->stats = vd_stats{};
     h->stats_status_or = 0;
+    *h->h_range = 0;
     if (n_sc == 0) return VD_OK;
     const int64_t n_var = in->var_off[4 * n_sc];
     const int64_t ref_bytes = in->ref_off[n_sc];
@@ -714,17 +736,39 @@ extern "C" int vd_run(vd_handle *h, const vd_batch_in *in, vd_batch_out *out) {
         CK(cudaStreamWaitEvent(h->s_out, W.ev[3], 0));      // copy-out behind the chunk's last kernel
 #define DOWN(dst, buf, off, bytes) do { if ((bytes) > 0) CK(cudaMemcpyAsync((dst), (const u8 *)sg.buf.p + (off), \
         (size_t)(bytes), cudaMemcpyDeviceToHost, h->s_out)); d2h += (bytes); } while (0)
-        DOWN(out->aln_score + 4 * r.s0, o_score, 0, 16 * ns);
-        DOWN(out->aln_end_plane + 4 * r.s0, o_endp, 0, 4 * ns);
-        DOWN(out->aln_beg_plane + 4 * r.s0, o_begp, 0, 4 * ns);
-        DOWN(out->status + 4 * r.s0, o_status, 0, 16 * ns);
-        for (int slot = 0; slot < 2; slot++) {
-            const int64_t ho = slot * n_var + r.v0, so = slot * nv;
-            DOWN(out->assigned + ho, o_assigned, so, nv);
-            DOWN(out->sync_group + ho, o_sg, 4 * so, 4 * nv);
-            DOWN(out->ref_ed + ho, o_red, 4 * so, 4 * nv);
-            DOWN(out->query_ed + ho, o_qed, 4 * so, 4 * nv);
-            DOWN(out->callq + ho, o_callq, 4 * so, 4 * nv);
+        if (out) {
+            DOWN(out->aln_score + 4 * r.s0, o_score, 0, 16 * ns);
+            DOWN(out->aln_end_plane + 4 * r.s0, o_endp, 0, 4 * ns);
+            DOWN(out->aln_beg_plane + 4 * r.s0, o_begp, 0, 4 * ns);
+            DOWN(out->status + 4 * r.s0, o_status, 0, 16 * ns);
+            for (int slot = 0; slot < 2; slot++) {
+                const int64_t ho = slot * n_var + r.v0, so = slot * nv;
+                DOWN(out->assigned + ho, o_assigned, so, nv);
+                DOWN(out->sync_group + ho, o_sg, 4 * so, 4 * nv);
+                DOWN(out->ref_ed + ho, o_red, 4 * so, 4 * nv);
+                DOWN(out->query_ed + ho, o_qed, 4 * so, 4 * nv);
+                DOWN(out->callq + ho, o_callq, 4 * so, 4 * nv);
+            }
+        } else {
+            // 16-bit records: narrowed on the device behind the chunk's last kernel, then copied out
+            CK(sg.p_score.ensure(8 * (size_t)ns + 16)); CK(sg.p_planes.ensure(4 * (size_t)ns + 16)); CK(sg.p_status.ensure(8 * (size_t)ns + 16));
+            CK(sg.p_sg.ensure(4 * (size_t)nv + 16)); CK(sg.p_red.ensure(4 * (size_t)nv + 16)); CK(sg.p_qed.ensure(4 * (size_t)nv + 16));
+            OutDev wide{(int32_t *)sg.o_score.p, (u8 *)sg.o_endp.p, (u8 *)sg.o_begp.p, (u32 *)sg.o_status.p, (u8 *)sg.o_assigned.p,
+                        (int32_t *)sg.o_sg.p, (int32_t *)sg.o_red.p, (int32_t *)sg.o_qed.p, (float *)sg.o_callq.p};
+            const int64_t nel = 4 * ns > 2 * nv ? 4 * ns : 2 * nv;
+            VD_LAUNCH(pack_out_kernel, (unsigned)((nel + 255) / 256), 256, 0, h->s_out, wide, 4 * ns, nv, (u16 *)sg.p_score.p, (u8 *)sg.p_planes.p,
+                      (u16 *)sg.p_status.p, (u16 *)sg.p_sg.p, (u16 *)sg.p_red.p, (u16 *)sg.p_qed.p, h->h_range);
+            h->stats.n_launches++;
+            DOWN(pout->aln_score + 4 * r.s0, p_score, 0, 8 * ns);
+            DOWN(pout->aln_planes + 4 * r.s0, p_planes, 0, 4 * ns);
+            DOWN(pout->status + 4 * r.s0, p_status, 0, 8 * ns);
+            for (int slot = 0; slot < 2; slot++) {
+                const int64_t ho = slot * n_var + r.v0, so = slot * nv;
+                DOWN(pout->sync_group + ho, p_sg, 2 * so, 2 * nv);
+                DOWN(pout->ref_ed + ho, p_red, 2 * so, 2 * nv);
+                DOWN(pout->query_ed + ho, p_qed, 2 * so, 2 * nv);
+                DOWN(pout->callq + ho, o_callq, 4 * so, 4 * nv);
+            }
         }
 #undef DOWN
         CK(cudaEventRecord(sg.out_done, h->s_out));
@@ -742,13 +786,16 @@ extern "C" int vd_run(vd_handle *h, const vd_batch_in *in, vd_batch_out *out) {
     h->stats.h2d_bytes = h2d;
     h->stats.d2h_bytes = d2h;
     if (rc_all != VD_OK) return rc_all;
+    if (pout && *h->h_range) return fail(h, VD_E_RANGE, "a result does not fit the 16-bit records: use vd_run");
     // fatal reference conditions are reported; results stay available for inspection
     if (h->stats_status_or & VD_ST_ERR_MASK)
-        for (int64_t i = 0; i < 4 * n_sc; i++)
-            if (out->status[i] & VD_ST_ERR_MASK)
-                return fail(h, (out->status[i] & VD_ST_ERR_BADINPUT) ? VD_E_BADINPUT : VD_E_ALIGN,
-                            "alignment %lld of supercluster %lld: status 0x%x%s", (long long)(i & 3), (long long)(i >> 2), out->status[i],
-                            (out->status[i] & VD_ST_ERR_BADINPUT) ? " (input the kernels cannot process, e.g. more than 8 swap sources for one row)" : "");
+        for (int64_t i = 0; i < 4 * n_sc; i++) {
+            const unsigned sti = out ? out->status[i] : pout->status[i];
+            if (sti & VD_ST_ERR_MASK)
+                return fail(h, (sti & VD_ST_ERR_BADINPUT) ? VD_E_BADINPUT : VD_E_ALIGN,
+                            "alignment %lld of supercluster %lld: status 0x%x%s", (long long)(i & 3), (long long)(i >> 2), sti,
+                            (sti & VD_ST_ERR_BADINPUT) ? " (input the kernels cannot process, e.g. more than 8 swap sources for one row)" : "");
+        }
     return VD_OK;
 }
 

@@ -83,6 +83,28 @@ __global__ void publish_kernel(const u32 *src, u32 *dst_host, int n_words) {
     __threadfence_system();
 }
 
+// 16-bit result records (vd_packed_out): narrowing of one chunk's result arrays before the copy out
+__global__ void pack_out_kernel(OutDev o, int64_t n_aln, int64_t n_var, u16 *score16, u8 *planes, u16 *status16,
+                                u16 *sg16, u16 *red16, u16 *qed16, unsigned *range_flag_host) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    bool over = false;
+    if (i < n_aln) {
+        const int sc = o.aln_score[i];
+        over |= sc >= 0xffff;
+        score16[i] = (u16)(sc < 0 ? 0xffff : sc);
+        planes[i] = (u8)((o.aln_end_plane[i] & 1) | ((o.aln_beg_plane[i] & 1) << 1));
+        over |= (o.status[i] >> 16) != 0;
+        status16[i] = (u16)o.status[i];
+    }
+    if (i < 2 * n_var) {
+        const int sg = o.sync_group[i], r = o.ref_ed[i], q = o.query_ed[i];
+        over |= sg < 0 || sg >= (1 << 14) || r < 0 || r >= 0xffff || q < 0 || q >= 0xffff;
+        sg16[i] = (u16)(((int)o.assigned[i] << 14) | (sg & 0x3fff));
+        red16[i] = (u16)r; qed16[i] = (u16)q;
+    }
+    if (over) { *range_flag_host = 1u; __threadfence_system(); }
+}
+
 // OR of all status words (so that the host only scans them when an error bit is set)
 __global__ void status_or_kernel(const u32 *status, int64_t n, unsigned *dst) {
     unsigned v = 0;

@@ -10,19 +10,27 @@
 // place of the original definition; everything else of vcfdist — VCF /
 // FASTA / BED parsing, clustering, phasing, output writers — is the reference's code.
 //
-// Host work here is O(input): pack the superclusters into the compact vd_batch_in
-// (include/vcfdist_b200.h), one vd_run() on the GPU, vd_finalize() for the float step,
-// scatter into ctgVariants / ctgSuperclusters (src/variant.h:49-60, src/cluster.h:36-42).
+// Host work here is O(input) and runs on the reference's own thread budget (-t, g.max_threads): pack the
+// superclusters into the compact vd_batch_in (include/vcfdist_b200.h) - two parallel passes over the
+// superclusters, sizes then bytes, straight into page-locked memory -, one vd_run_packed() on the GPU (16-bit
+// result records; vd_run() when a value does not fit), vd_finalize_packed() for the float step, parallel scatter
+// into ctgVariants / ctgSuperclusters (src/variant.h:49-60, src/cluster.h:36-42).  The GPU handle and the
+// page-locked arena are created once per process by a background thread started at load time, so that CUDA
+// start-up overlaps the reference's VCF parsing instead of sitting inside its precision/recall timer
+// (g.timers[TIME_PR_ALN], src/main.cpp:218-221).
 //
 // Build-time switch VD_DROPIN_WITH_REF (oracle/Makefile only, never the product build):
 // adds the fixture-dump mode that runs the REFERENCE's renamed wrapper instead of the GPU
 // and writes its results, used to generate tests/golden/.
 #include <array>
+#include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "globals.h"
@@ -40,109 +48,252 @@ void ref_precision_recall_threads_wrapper(
 
 namespace vdhost {
 
-struct VarLoc { int ctg, callset, hap, idx; };
 struct ScLoc { int ctg, sc; };
 
+// f(thread, first, last) over [0, n) on nt host threads
+template <class F>
+static void parallel_for(int64_t n, int nt, F f) {
+    if (nt > n / 2048) nt = (int)(n / 2048);
+    if (nt <= 1) { f(0, (int64_t)0, n); return; }
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; t++) th.emplace_back(f, t, n * t / nt, n * (t + 1) / nt);
+    f(0, (int64_t)0, n / nt);
+    for (auto &x : th) x.join();
+}
+
+// in-place exclusive-to-inclusive offsets: a[0] = 0, a[i+1] holds the size of item i on entry and the end offset
+// of item i on return
+static void offsets_from_sizes(int64_t *a, int64_t n, int nt) {
+    if (nt > n / 65536) nt = (int)(n / 65536);
+    if (nt <= 1) { for (int64_t i = 0; i < n; i++) a[i + 1] += a[i]; return; }
+    std::vector<int64_t> part(nt + 1, 0);
+    parallel_for(n, nt, [&](int t, int64_t i0, int64_t i1) {
+        int64_t sum = 0;
+        for (int64_t i = i0; i < i1; i++) sum += a[i + 1];
+        part[t + 1] = sum;
+    });
+    for (int t = 0; t < nt; t++) part[t + 1] += part[t];
+    const int64_t a0 = a[0];
+    parallel_for(n, nt, [&](int t, int64_t i0, int64_t i1) {
+        int64_t run = a0 + part[t];
+        for (int64_t i = i0; i < i1; i++) { run += a[i + 1]; a[i + 1] = run; }
+    });
+}
+
+#ifndef VD_DROPIN_WITH_REF
+// One GPU handle and one page-locked arena per process, set up by a background thread at load time.
+struct Runtime {
+    std::thread th;
+    vd_handle *h = nullptr;
+    int rc = VD_OK, device = 0;
+    uint8_t *arena = nullptr;
+    int64_t arena_cap = 0;
+    bool tried = false;
+    void init() {
+        tried = true;
+        if (const char *d = std::getenv("VD_DEVICE")) device = std::atoi(d);
+        rc = vd_create(device, 0, &h);
+        if (rc != VD_OK) return;
+        int64_t mb = 1024;
+        if (const char *m = std::getenv("VD_PIN_MB")) mb = std::atoll(m);
+        if (mb > 0) { arena = (uint8_t *)vd_host_alloc(mb << 20); arena_cap = arena ? (mb << 20) : 0; }
+    }
+    Runtime() { if (!std::getenv("VD_NO_WARM")) th = std::thread([this] { init(); }); }
+    vd_handle *get() {
+        if (th.joinable()) th.join();
+        if (!tried) init();
+        return h;
+    }
+    ~Runtime() {
+        if (th.joinable()) th.join();
+        if (arena) vd_host_free(arena);
+        if (h) vd_destroy(h);
+    }
+};
+static Runtime rt;
+#endif
+
+// host buffers of one call: carved from the page-locked arena while they fit, pageable otherwise
+struct HostMem {
+    uint8_t *arena = nullptr;
+    int64_t cap = 0, used = 0;
+    std::vector<void *> owned;
+    template <class T> T *take(int64_t n) {
+        const int64_t bytes = ((n > 0 ? n : 1) * (int64_t)sizeof(T) + 255) & ~(int64_t)255;
+        if (arena && used + bytes <= cap) { T *p = (T *)(arena + used); used += bytes; return p; }
+        void *p = std::malloc((size_t)bytes);
+        if (!p) ERROR("vcfdist_b200: out of host memory (%lld bytes)", (long long)bytes);
+        owned.push_back(p);
+        return (T *)p;
+    }
+    ~HostMem() { for (void *p : owned) std::free(p); }
+};
+
+struct CtgView {                       // per contig, resolved once (no map lookups per supercluster or variant)
+    const ctgSuperclusters *sc = nullptr;
+    ctgSuperclusters *sc_mut = nullptr;
+    ctgVariants *cv[CALLSETS * HAPS] = {};
+    const std::string *fa = nullptr;
+};
+
 struct Packed {
-    std::vector<int64_t> ref_off{0}, var_off{0}, alt_off{0};
-    std::vector<uint8_t> ref_seq, rplane_seq, alt_seq, var_type;
-    std::vector<int32_t> var_pos, var_rlen;
-    std::vector<float> var_qual;
-    bool need_rplane = false;
-    std::vector<VarLoc> var_loc;
-    std::vector<ScLoc> sc_loc;
+    int64_t n_sc = 0, n_var = 0;
+    int64_t *ref_off = nullptr, *var_off = nullptr, *alt_off = nullptr;
+    uint8_t *ref_seq = nullptr, *rplane_seq = nullptr, *alt_seq = nullptr, *var_type = nullptr;
+    int32_t *var_pos = nullptr, *var_rlen = nullptr;
+    float *var_qual = nullptr;
+    std::vector<ScLoc> sc_loc;                  // batch order -> (contig, supercluster)
+    std::vector<std::array<int, 4>> vb;         // first variant index of each haplotype of a supercluster in its ctgVariants
+    std::vector<CtgView> ctgs;
 
     vd_batch_in view(float max_qual) const {
         vd_batch_in in;
-        in.n_sc = (int32_t)sc_loc.size();
-        in.ref_off = ref_off.data();
-        in.ref_seq = ref_seq.data();
-        in.rplane_seq = need_rplane ? rplane_seq.data() : nullptr;
-        in.var_off = var_off.data();
-        in.var_pos = var_pos.data();
-        in.var_rlen = var_rlen.data();
-        in.var_type = var_type.data();
-        in.alt_off = alt_off.data();
-        in.alt_seq = alt_seq.data();
-        in.var_qual = var_qual.data();
+        in.n_sc = (int32_t)n_sc;
+        in.ref_off = ref_off; in.ref_seq = ref_seq; in.rplane_seq = rplane_seq;
+        in.var_off = var_off; in.var_pos = var_pos; in.var_rlen = var_rlen; in.var_type = var_type;
+        in.alt_off = alt_off; in.alt_seq = alt_seq; in.var_qual = var_qual;
         in.max_qual = max_qual;
         return in;
     }
 };
 
-// what precision_recall_wrapper reads per supercluster (src/dist.cpp:1786-1822)
-static void pack_one(const superclusterData *scd, int ctg_idx, int sc_idx, Packed &p) {
-    const std::string &ctg = scd->contigs[ctg_idx];
-    const std::shared_ptr<ctgSuperclusters> &sc = scd->superclusters.at(ctg);
-    const int beg = sc->begs[sc_idx], end = sc->ends[sc_idx];
-    const std::string &fa = scd->ref->fasta.at(ctg);
-    if (beg < 0 || end >= (int)fa.size() || end < beg)
-        ERROR("Contig '%s' not present in reference FASTA", ctg.data());   // src/dist.cpp:237-239
-    const size_t r0 = p.ref_seq.size();
-    p.ref_seq.insert(p.ref_seq.end(), fa.begin() + beg, fa.begin() + end + 1);
-    p.rplane_seq.insert(p.rplane_seq.end(), fa.begin() + beg, fa.begin() + end + 1);
-    p.ref_off.push_back((int64_t)p.ref_seq.size());
-    for (int k = 0; k < CALLSETS * HAPS; k++) {
-        const std::shared_ptr<ctgVariants> &cv = sc->ctg_variants[k >> 1][k & 1];
-        int vb = 0, ve = 0;
-        if (cv->clusters.size()) {                                          // src/dist.cpp:159-162
-            vb = cv->clusters[sc->superclusters[k >> 1][k & 1][sc_idx]];
-            ve = cv->clusters[sc->superclusters[k >> 1][k & 1][sc_idx + 1]];
+// What precision_recall_wrapper reads per supercluster (src/dist.cpp:1786-1822), for all superclusters, largest-RAM
+// bucket first as the reference schedules them (src/dist.cpp:1670-1672).  Pass 1 sizes, pass 2 bytes.
+static void pack(superclusterData *scd, const std::vector<std::vector<std::vector<int>>> &sc_groups, int nt,
+                 HostMem &mem, Packed &p) {
+    p.ctgs.resize(scd->contigs.size());
+    for (int step = (int)sc_groups.size() - 1; step >= 0; step--)
+        for (size_t k = 0; k < sc_groups[step][SC_IDX].size(); k++) {
+            const int ci = sc_groups[step][CTG_IDX][k];
+            CtgView &cvw = p.ctgs[ci];
+            if (!cvw.sc) {
+                const std::string &ctg = scd->contigs[ci];
+                cvw.sc_mut = scd->superclusters.at(ctg).get();
+                cvw.sc = cvw.sc_mut;
+                for (int j = 0; j < CALLSETS * HAPS; j++) cvw.cv[j] = cvw.sc->ctg_variants[j >> 1][j & 1].get();
+                auto it = scd->ref->fasta.find(ctg);
+                if (it == scd->ref->fasta.end())
+                    ERROR("Contig '%s' not present in reference FASTA", ctg.data());   // src/dist.cpp:237-239
+                cvw.fa = &it->second;
+            }
+            p.sc_loc.push_back({ci, sc_groups[step][SC_IDX][k]});
         }
-        for (int v = vb; v < ve; v++) {
-            p.var_pos.push_back(cv->poss[v] - beg);
-            p.var_rlen.push_back((int32_t)cv->refs[v].size());
-            p.var_type.push_back(cv->types[v]);
-            p.alt_seq.insert(p.alt_seq.end(), cv->alts[v].begin(), cv->alts[v].end());
-            p.alt_off.push_back((int64_t)p.alt_seq.size());
-            p.var_qual.push_back(cv->var_quals[v]);
-            p.var_loc.push_back({ctg_idx, k >> 1, k & 1, v});
-            // the REF-plane string is ref_q1: FASTA with query-hap-1 REF alleles written in
-            // (src/dist.cpp:187, :195, :1784-1792)
-            if (k == 0 && (cv->types[v] == TYPE_DEL || cv->types[v] == TYPE_SUB)) {
-                const int rel = cv->poss[v] - beg;
-                for (size_t j = 0; j < cv->refs[v].size(); j++) {
-                    const size_t at = r0 + rel + j;
-                    if (rel >= 0 && at < p.rplane_seq.size() && p.rplane_seq[at] != (uint8_t)cv->refs[v][j]) {
-                        p.rplane_seq[at] = (uint8_t)cv->refs[v][j];
-                        p.need_rplane = true;
+    const int64_t n_sc = p.n_sc = (int64_t)p.sc_loc.size();
+    p.vb.resize((size_t)n_sc);
+    p.ref_off = mem.take<int64_t>(n_sc + 1);
+    p.var_off = mem.take<int64_t>(4 * n_sc + 1);
+    std::vector<int64_t> alt_sc((size_t)n_sc + 1, 0);       // ALT bytes per supercluster -> first ALT byte of each
+    p.ref_off[0] = p.var_off[0] = 0;
+    std::atomic<int> bad_window{-1}, any_rplane{0};
+    parallel_for(n_sc, nt, [&](int, int64_t s0, int64_t s1) {
+        bool rpl = false;
+        for (int64_t s = s0; s < s1; s++) {
+            const CtgView &c = p.ctgs[p.sc_loc[s].ctg];
+            const int sc_idx = p.sc_loc[s].sc;
+            const int beg = c.sc->begs[sc_idx], end = c.sc->ends[sc_idx];
+            if (beg < 0 || end >= (int)c.fa->size() || end < beg) { bad_window = p.sc_loc[s].ctg; p.ref_off[s + 1] = 0; }
+            else p.ref_off[s + 1] = (int64_t)end - beg + 1;
+            int64_t ab = 0;
+            for (int k = 0; k < CALLSETS * HAPS; k++) {
+                const ctgVariants *cv = c.cv[k];
+                int vb = 0, ve = 0;
+                if (cv->clusters.size()) {                                          // src/dist.cpp:159-162
+                    vb = cv->clusters[c.sc->superclusters[k >> 1][k & 1][sc_idx]];
+                    ve = cv->clusters[c.sc->superclusters[k >> 1][k & 1][sc_idx + 1]];
+                }
+                p.vb[s][k] = vb;
+                p.var_off[4 * s + k + 1] = ve - vb;
+                for (int v = vb; v < ve; v++) {
+                    ab += (int64_t)cv->alts[v].size();
+                    // the REF-plane string is ref_q1: FASTA with query-hap-1 REF alleles written in
+                    // (src/dist.cpp:187, :195, :1784-1792); shipped only when some allele differs from the FASTA
+                    if (k == 0 && !rpl && (cv->types[v] == TYPE_DEL || cv->types[v] == TYPE_SUB) && p.ref_off[s + 1]) {
+                        const int64_t at = cv->poss[v];
+                        const std::string &r = cv->refs[v];
+                        if (at >= beg && at + (int64_t)r.size() <= (int64_t)end + 1) {
+                            if (std::memcmp(c.fa->data() + at, r.data(), r.size()) != 0) rpl = true;
+                        } else if (at >= beg) rpl = true;           // partly outside the window: byte-wise rule below
+                    }
+                }
+            }
+            alt_sc[s + 1] = ab;
+        }
+        if (rpl) any_rplane = 1;
+    });
+    if (bad_window >= 0) ERROR("Contig '%s' not present in reference FASTA", scd->contigs[bad_window].data());   // src/dist.cpp:237-239
+    offsets_from_sizes(p.ref_off, n_sc, nt);
+    offsets_from_sizes(p.var_off, 4 * n_sc, nt);
+    offsets_from_sizes(alt_sc.data(), n_sc, nt);
+    const int64_t n_var = p.n_var = p.var_off[4 * n_sc];
+    const int64_t ref_bytes = p.ref_off[n_sc], alt_bytes = alt_sc[(size_t)n_sc];
+    p.ref_seq = mem.take<uint8_t>(ref_bytes);
+    p.rplane_seq = any_rplane ? mem.take<uint8_t>(ref_bytes) : nullptr;
+    p.alt_seq = mem.take<uint8_t>(alt_bytes);
+    p.alt_off = mem.take<int64_t>(n_var + 1);
+    p.var_pos = mem.take<int32_t>(n_var);
+    p.var_rlen = mem.take<int32_t>(n_var);
+    p.var_type = mem.take<uint8_t>(n_var);
+    p.var_qual = mem.take<float>(n_var);
+    p.alt_off[0] = 0;
+    parallel_for(n_sc, nt, [&](int, int64_t s0, int64_t s1) {
+        for (int64_t s = s0; s < s1; s++) {
+            const CtgView &c = p.ctgs[p.sc_loc[s].ctg];
+            const int sc_idx = p.sc_loc[s].sc;
+            const int beg = c.sc->begs[sc_idx];
+            const int64_t r0 = p.ref_off[s], len = p.ref_off[s + 1] - r0;
+            std::memcpy(p.ref_seq + r0, c.fa->data() + beg, (size_t)len);
+            if (p.rplane_seq) std::memcpy(p.rplane_seq + r0, c.fa->data() + beg, (size_t)len);
+            int64_t a = alt_sc[s];
+            for (int k = 0; k < CALLSETS * HAPS; k++) {
+                const ctgVariants *cv = c.cv[k];
+                const int vb = p.vb[s][k];
+                const int64_t o0 = p.var_off[4 * s + k], o1 = p.var_off[4 * s + k + 1];
+                for (int64_t o = o0; o < o1; o++) {
+                    const int v = vb + (int)(o - o0);
+                    p.var_pos[o] = cv->poss[v] - beg;
+                    p.var_rlen[o] = (int32_t)cv->refs[v].size();
+                    p.var_type[o] = cv->types[v];
+                    p.var_qual[o] = cv->var_quals[v];
+                    const std::string &alt = cv->alts[v];
+                    std::memcpy(p.alt_seq + a, alt.data(), alt.size());
+                    a += (int64_t)alt.size();
+                    p.alt_off[o + 1] = a;
+                    if (p.rplane_seq && k == 0 && (cv->types[v] == TYPE_DEL || cv->types[v] == TYPE_SUB)) {
+                        const int rel = cv->poss[v] - beg;
+                        for (size_t j = 0; j < cv->refs[v].size(); j++) {
+                            const int64_t at = rel + (int64_t)j;
+                            if (rel >= 0 && at < len) p.rplane_seq[r0 + at] = (uint8_t)cv->refs[v][j];
+                        }
                     }
                 }
             }
         }
-        p.var_off.push_back((int64_t)p.var_pos.size());
-    }
-    p.sc_loc.push_back({ctg_idx, sc_idx});
+    });
 }
 
-static Packed pack(const superclusterData *scd,
-                   const std::vector<std::vector<std::vector<int>>> &sc_groups) {
-    Packed p;
-    // largest-RAM bucket first, as the reference schedules them (src/dist.cpp:1670-1672)
-    for (int step = (int)sc_groups.size() - 1; step >= 0; step--)
-        for (size_t k = 0; k < sc_groups[step][SC_IDX].size(); k++)
-            pack_one(scd, sc_groups[step][CTG_IDX][k], sc_groups[step][SC_IDX][k], p);
-    return p;
-}
-
-static void scatter(superclusterData *scd, const Packed &p, const vd_final &fin) {
-    const int64_t n_var = (int64_t)p.var_loc.size();
-    for (int64_t v = 0; v < n_var; v++) {
-        const VarLoc &l = p.var_loc[v];
-        ctgVariants &cv = *scd->superclusters.at(scd->contigs[l.ctg])->ctg_variants[l.callset][l.hap];
-        for (int slot = 0; slot < PHASES; slot++) {
-            const int64_t o = slot * n_var + v;
-            cv.errtypes[slot][l.idx] = fin.errtypes[o];
-            cv.sync_group[slot][l.idx] = fin.sync_group[o];
-            cv.credit[slot][l.idx] = fin.credit[o];
-            cv.ref_ed[slot][l.idx] = fin.ref_ed[o];
-            cv.query_ed[slot][l.idx] = fin.query_ed[o];
-            cv.callq[slot][l.idx] = fin.callq[o];
+static void scatter(const Packed &p, const vd_batch_in &in, const vd_final &fin, int nt) {
+    const int64_t n_var = p.n_var;
+    parallel_for(p.n_sc, nt, [&](int, int64_t s0, int64_t s1) {
+        for (int64_t s = s0; s < s1; s++) {
+            const CtgView &c = p.ctgs[p.sc_loc[s].ctg];
+            for (int k = 0; k < CALLSETS * HAPS; k++) {
+                ctgVariants &cv = *c.cv[k];
+                const int64_t o0 = in.var_off[4 * s + k], o1 = in.var_off[4 * s + k + 1];
+                for (int slot = 0; slot < PHASES; slot++) {
+                    uint8_t *et = cv.errtypes[slot].data(); int *sg = cv.sync_group[slot].data();
+                    float *cr = cv.credit[slot].data(), *cq = cv.callq[slot].data();
+                    int *re = cv.ref_ed[slot].data(), *qe = cv.query_ed[slot].data();
+                    for (int64_t v = o0; v < o1; v++) {
+                        const int64_t o = slot * n_var + v;
+                        const int idx = p.vb[s][k] + (int)(v - o0);
+                        et[idx] = fin.errtypes[o]; sg[idx] = fin.sync_group[o]; cr[idx] = fin.credit[o];
+                        re[idx] = fin.ref_ed[o]; qe[idx] = fin.query_ed[o]; cq[idx] = fin.callq[o];
+                    }
+                }
+            }
+            c.sc_mut->set_phase(p.sc_loc[s].sc, fin.sc_phase[s], fin.orig_dist[s], fin.swap_dist[s]);   // src/cluster.cpp:31-38
         }
-    }
-    for (size_t s = 0; s < p.sc_loc.size(); s++)
-        scd->superclusters.at(scd->contigs[p.sc_loc[s].ctg])->set_phase(     // src/cluster.cpp:31-38
-                p.sc_loc[s].sc, fin.sc_phase[s], fin.orig_dist[s], fin.swap_dist[s]);
+    });
 }
 
 // ---- tiny self-describing array container, read by vcfdist_b200/fixtures.py ----
@@ -158,42 +309,45 @@ static void put_arr(FILE *f, const char *name, char dtype, const void *data, int
 static void dump_batch(const Packed &p, float max_qual, const char *path) {
     FILE *f = std::fopen(path, "wb");
     if (!f) ERROR("cannot write '%s'", path);
+    const int64_t n_sc = p.n_sc, n_var = p.n_var, ref_bytes = p.ref_off[n_sc], alt_bytes = n_var ? p.alt_off[n_var] : 0;
     std::fwrite("VDARR001", 1, 8, f);
-    put_arr(f, "ref_off", 'q', p.ref_off.data(), (int64_t)p.ref_off.size(), 8);
-    put_arr(f, "ref_seq", 'B', p.ref_seq.data(), (int64_t)p.ref_seq.size(), 1);
-    if (p.need_rplane) put_arr(f, "rplane_seq", 'B', p.rplane_seq.data(), (int64_t)p.rplane_seq.size(), 1);
-    put_arr(f, "var_off", 'q', p.var_off.data(), (int64_t)p.var_off.size(), 8);
-    put_arr(f, "var_pos", 'i', p.var_pos.data(), (int64_t)p.var_pos.size(), 4);
-    put_arr(f, "var_rlen", 'i', p.var_rlen.data(), (int64_t)p.var_rlen.size(), 4);
-    put_arr(f, "var_type", 'B', p.var_type.data(), (int64_t)p.var_type.size(), 1);
-    put_arr(f, "alt_off", 'q', p.alt_off.data(), (int64_t)p.alt_off.size(), 8);
-    put_arr(f, "alt_seq", 'B', p.alt_seq.data(), (int64_t)p.alt_seq.size(), 1);
-    put_arr(f, "var_qual", 'f', p.var_qual.data(), (int64_t)p.var_qual.size(), 4);
+    put_arr(f, "ref_off", 'q', p.ref_off, n_sc + 1, 8);
+    put_arr(f, "ref_seq", 'B', p.ref_seq, ref_bytes, 1);
+    if (p.rplane_seq) put_arr(f, "rplane_seq", 'B', p.rplane_seq, ref_bytes, 1);
+    put_arr(f, "var_off", 'q', p.var_off, 4 * n_sc + 1, 8);
+    put_arr(f, "var_pos", 'i', p.var_pos, n_var, 4);
+    put_arr(f, "var_rlen", 'i', p.var_rlen, n_var, 4);
+    put_arr(f, "var_type", 'B', p.var_type, n_var, 1);
+    put_arr(f, "alt_off", 'q', p.alt_off, n_var + 1, 8);
+    put_arr(f, "alt_seq", 'B', p.alt_seq, alt_bytes, 1);
+    put_arr(f, "var_qual", 'f', p.var_qual, n_var, 4);
     put_arr(f, "max_qual", 'f', &max_qual, 1, 4);
     std::fclose(f);
 }
 
 // results as they stand in superclusterData, in batch order (whoever computed them)
-static void dump_final(const superclusterData *scd, const Packed &p, const char *path) {
-    const int64_t n_var = (int64_t)p.var_loc.size(), n_sc = (int64_t)p.sc_loc.size();
+static void dump_final(const Packed &p, const char *path) {
+    const int64_t n_var = p.n_var, n_sc = p.n_sc;
     std::vector<uint8_t> err(2 * n_var);
     std::vector<int32_t> sg(2 * n_var), red(2 * n_var), qed(2 * n_var), ph(n_sc), od(n_sc), sd(n_sc);
     std::vector<float> cq(2 * n_var), cr(2 * n_var);
-    for (int64_t v = 0; v < n_var; v++) {
-        const VarLoc &l = p.var_loc[v];
-        const ctgVariants &cv = *scd->superclusters.at(scd->contigs[l.ctg])->ctg_variants[l.callset][l.hap];
-        for (int slot = 0; slot < PHASES; slot++) {
-            const int64_t o = slot * n_var + v;
-            err[o] = cv.errtypes[slot][l.idx]; sg[o] = cv.sync_group[slot][l.idx];
-            red[o] = cv.ref_ed[slot][l.idx]; qed[o] = cv.query_ed[slot][l.idx];
-            cq[o] = cv.callq[slot][l.idx]; cr[o] = cv.credit[slot][l.idx];
-        }
-    }
     for (int64_t s = 0; s < n_sc; s++) {
-        const ctgSuperclusters &cs = *scd->superclusters.at(scd->contigs[p.sc_loc[s].ctg]);
-        ph[s] = cs.sc_phase[p.sc_loc[s].sc];
-        od[s] = cs.orig_phase_dist[p.sc_loc[s].sc];
-        sd[s] = cs.swap_phase_dist[p.sc_loc[s].sc];
+        const CtgView &c = p.ctgs[p.sc_loc[s].ctg];
+        for (int k = 0; k < CALLSETS * HAPS; k++) {
+            const ctgVariants &cv = *c.cv[k];
+            for (int64_t v = p.var_off[4 * s + k]; v < p.var_off[4 * s + k + 1]; v++) {
+                const int idx = p.vb[s][k] + (int)(v - p.var_off[4 * s + k]);
+                for (int slot = 0; slot < PHASES; slot++) {
+                    const int64_t o = slot * n_var + v;
+                    err[o] = cv.errtypes[slot][idx]; sg[o] = cv.sync_group[slot][idx];
+                    red[o] = cv.ref_ed[slot][idx]; qed[o] = cv.query_ed[slot][idx];
+                    cq[o] = cv.callq[slot][idx]; cr[o] = cv.credit[slot][idx];
+                }
+            }
+        }
+        ph[s] = c.sc->sc_phase[p.sc_loc[s].sc];
+        od[s] = c.sc->orig_phase_dist[p.sc_loc[s].sc];
+        sd[s] = c.sc->swap_phase_dist[p.sc_loc[s].sc];
     }
     FILE *f = std::fopen(path, "wb");
     if (!f) ERROR("cannot write '%s'", path);
@@ -234,7 +388,13 @@ static void print_supercluster(const superclusterData *scd, int ctg_idx, int sc_
     }
 }
 
+static std::array<double, 10> last_times{};
+
 }  // namespace vdhost
+
+// host-side times of the last call in ms: wait for the handle, pack, vd_run (wall), vd_run (device), status scan, float step,
+// scatter; then host threads used, 1 if every GPU-facing buffer was page-locked, superclusters with a tie
+extern "C" void vd_dropin_last_times(double *out10) { for (int i = 0; i < 10; i++) out10[i] = vdhost::last_times[i]; }
 
 void precision_recall_threads_wrapper(
         std::shared_ptr<superclusterData> clusterdata_ptr,
@@ -250,51 +410,81 @@ void precision_recall_threads_wrapper(
                 int(sc_groups[i][CTG_IDX].size()));
     }
 
-    vdhost::Packed p = vdhost::pack(clusterdata_ptr.get(), sc_groups);
+    using clk = std::chrono::steady_clock;
+    auto ms_since = [](clk::time_point t) { return std::chrono::duration<double, std::milli>(clk::now() - t).count(); };
+    int nt = g.max_threads;                                          // the reference's -t
+    const int hw = (int)std::thread::hardware_concurrency();
+    if (hw > 0 && nt > hw) nt = hw;
+    if (nt < 1) nt = 1;
     const float max_qual = float(g.max_qual);                       // src/dist.cpp:1284
-    if (const char *path = std::getenv("VD_DUMP_BATCH")) vdhost::dump_batch(p, max_qual, path);
 
 #ifdef VD_DROPIN_WITH_REF
     {   // fixture tool (oracle/_ref/vcfdist_dump): the REFERENCE computes, we only record
+        vdhost::HostMem mem;
+        vdhost::Packed p;
+        vdhost::pack(clusterdata_ptr.get(), sc_groups, nt, mem, p);
+        if (const char *path = std::getenv("VD_DUMP_BATCH")) vdhost::dump_batch(p, max_qual, path);
         ref_precision_recall_threads_wrapper(clusterdata_ptr, sc_groups);
-        if (const char *path = std::getenv("VD_DUMP_FINAL"))
-            vdhost::dump_final(clusterdata_ptr.get(), p, path);
+        if (const char *path = std::getenv("VD_DUMP_FINAL")) vdhost::dump_final(p, path);
         return;
     }
 #else
+    auto t0 = clk::now();
+    vd_handle *h = vdhost::rt.get();                                // normally ready long before this point
+    if (!h) ERROR("vcfdist_b200: cannot initialise CUDA device %d (code %d); "
+                  "there is no CPU fallback for the precision/recall path", vdhost::rt.device, vdhost::rt.rc);
+    const double ms_wait = ms_since(t0);
+    t0 = clk::now();
+    vdhost::HostMem mem;
+    mem.arena = vdhost::rt.arena; mem.cap = vdhost::rt.arena_cap;
+    vdhost::Packed p;
+    vdhost::pack(clusterdata_ptr.get(), sc_groups, nt, mem, p);
+    const double ms_pack = ms_since(t0);
+    if (const char *path = std::getenv("VD_DUMP_BATCH")) vdhost::dump_batch(p, max_qual, path);
 
-    const int64_t n_sc = (int64_t)p.sc_loc.size(), n_var = (int64_t)p.var_loc.size();
+    const int64_t n_sc = p.n_sc, n_var = p.n_var;
     if (n_sc == 0) return;
     vd_batch_in in = p.view(max_qual);
 
-    std::vector<int32_t> aln_score(4 * n_sc), sync_group(2 * n_var + 1), ref_ed(2 * n_var + 1),
-            query_ed(2 * n_var + 1);
-    std::vector<uint8_t> end_plane(4 * n_sc), beg_plane(4 * n_sc), assigned(2 * n_var + 1);
-    std::vector<uint32_t> status(4 * n_sc);
-    std::vector<float> callq(2 * n_var + 1);
-    vd_batch_out out{aln_score.data(), end_plane.data(), beg_plane.data(), status.data(),
-                     assigned.data(), sync_group.data(), ref_ed.data(), query_ed.data(), callq.data()};
-
-    int device = 0;
-    if (const char *d = std::getenv("VD_DEVICE")) device = std::atoi(d);
-    vd_handle *h = nullptr;
-    int rc = vd_create(device, 0, &h);
-    if (rc != VD_OK) ERROR("vcfdist_b200: cannot initialise CUDA device %d (code %d); "
-                           "there is no CPU fallback for the precision/recall path", device, rc);
-    rc = vd_run(h, &in, &out);
+    // 16-bit result records first; 32-bit ones only when a value does not fit (VD_E_RANGE)
+    t0 = clk::now();
+    vd_packed_out pk{mem.take<uint16_t>(4 * n_sc), mem.take<uint8_t>(4 * n_sc), mem.take<uint16_t>(4 * n_sc),
+                     mem.take<uint16_t>(2 * n_var), mem.take<uint16_t>(2 * n_var), mem.take<uint16_t>(2 * n_var),
+                     mem.take<float>(2 * n_var)};
+    vd_batch_out out{};
+    int rc = vd_run_packed(h, &in, &pk);
+    const bool wide = rc == VD_E_RANGE;
+    if (wide) {
+        out = vd_batch_out{mem.take<int32_t>(4 * n_sc), mem.take<uint8_t>(4 * n_sc), mem.take<uint8_t>(4 * n_sc),
+                           mem.take<uint32_t>(4 * n_sc), mem.take<uint8_t>(2 * n_var), mem.take<int32_t>(2 * n_var),
+                           mem.take<int32_t>(2 * n_var), mem.take<int32_t>(2 * n_var), mem.take<float>(2 * n_var)};
+        rc = vd_run(h, &in, &out);
+    }
     if (rc != VD_OK && rc != VD_E_ALIGN && rc != VD_E_BADINPUT)     // the last two are reported per supercluster below
         ERROR("vcfdist_b200: vd_run failed (code %d): %s", rc, vd_last_error(h));
-    if (g.verbosity >= 2) {
-        vd_stats st; vd_get_stats(h, &st);
-        INFO("  GPU precision/recall: %lld superclusters, %lld cells, %.3f ms on device, %lld launches",
-             (long long)st.n_sc, (long long)st.cells, st.ms_total, (long long)st.n_launches);
-    }
-    vd_destroy(h);
+    const double ms_run = ms_since(t0);
+    vd_stats st; vd_get_stats(h, &st);
 
-    // fatal conditions and data warnings of the reference, in batch order
-    for (int64_t s = 0; s < n_sc; s++) {
-        uint32_t st = status[4 * s] | status[4 * s + 1] | status[4 * s + 2] | status[4 * s + 3];
-        if (!st) continue;
+    // fatal conditions and data warnings of the reference, in batch order; superclusters whose status is zero or
+    // only says "tie" are the rule, so the scan for the others runs on all threads
+    t0 = clk::now();
+    auto status_of = [&](int64_t s) -> uint32_t {
+        return wide ? (out.status[4 * s] | out.status[4 * s + 1] | out.status[4 * s + 2] | out.status[4 * s + 3])
+                    : (uint32_t)(pk.status[4 * s] | pk.status[4 * s + 1] | pk.status[4 * s + 2] | pk.status[4 * s + 3]);
+    };
+    std::vector<std::vector<int64_t>> flagged((size_t)nt);
+    std::vector<int64_t> ties((size_t)nt, 0);
+    vdhost::parallel_for(n_sc, nt, [&](int t, int64_t s0, int64_t s1) {
+        for (int64_t s = s0; s < s1; s++) {
+            const uint32_t stw = status_of(s);
+            if (stw & VD_ST_TIE) ties[t]++;
+            if (stw & ~(uint32_t)VD_ST_TIE) flagged[t].push_back(s);
+        }
+    });
+    int64_t n_tie = 0;
+    for (int64_t x : ties) n_tie += x;
+    for (const auto &fl : flagged) for (int64_t s : fl) {
+        const uint32_t st = status_of(s);
         const std::string &ctg = clusterdata_ptr->contigs[p.sc_loc[s].ctg];
         const int sc_idx = p.sc_loc[s].sc;
         if (st & VD_ST_ERR_BADINPUT)
@@ -317,13 +507,28 @@ void precision_recall_threads_wrapper(
         if (warn) vdhost::print_supercluster(clusterdata_ptr.get(), p.sc_loc[s].ctg, sc_idx);
     }
 
-    std::vector<uint8_t> errtypes(2 * n_var + 1);
-    std::vector<float> credit(2 * n_var + 1), fcallq(2 * n_var + 1);
-    std::vector<int32_t> fsg(2 * n_var + 1), fred(2 * n_var + 1), fqed(2 * n_var + 1),
-            phase(n_sc), od(n_sc), sd(n_sc);
-    vd_final fin{errtypes.data(), credit.data(), fcallq.data(), fsg.data(), fred.data(), fqed.data(),
-                 phase.data(), od.data(), sd.data()};
-    vd_finalize(&in, &out, g.phase_threshold, g.credit_threshold, &fin);
-    vdhost::scatter(clusterdata_ptr.get(), p, fin);
+    const double ms_status = ms_since(t0);
+
+    t0 = clk::now();
+    vdhost::HostMem heap;                                           // never copied to or from the GPU: pageable
+    vd_final fin{heap.take<uint8_t>(2 * n_var), heap.take<float>(2 * n_var), heap.take<float>(2 * n_var),
+                 heap.take<int32_t>(2 * n_var), heap.take<int32_t>(2 * n_var), heap.take<int32_t>(2 * n_var),
+                 heap.take<int32_t>(n_sc), heap.take<int32_t>(n_sc), heap.take<int32_t>(n_sc)};
+    if (wide) vd_finalize(&in, &out, g.phase_threshold, g.credit_threshold, &fin);
+    else vd_finalize_packed(&in, &pk, g.phase_threshold, g.credit_threshold, &fin);
+    const double ms_fin = ms_since(t0);
+    t0 = clk::now();
+    vdhost::scatter(p, in, fin, nt);
+    const double ms_scatter = ms_since(t0);
+    vdhost::last_times = {ms_wait, ms_pack, ms_run, (double)st.ms_total, ms_status, ms_fin, ms_scatter, (double)nt,
+                          mem.owned.empty() ? 1.0 : 0.0, (double)n_tie};
+    if (g.verbosity >= 1 && n_tie)
+        INFO("  %lld of %lld superclusters had an ambiguous swap predecessor on an optimal path (equal-score tie): "
+             "resolved canonically here, by hash-set order upstream", (long long)n_tie, (long long)n_sc);
+    if (g.verbosity >= 2 || std::getenv("VD_DROPIN_TIMES"))
+        INFO("  GPU precision/recall: %lld superclusters, %lld variants, %lld cells, %lld launches; wait %.1f ms, pack %.1f ms, "
+             "vd_run%s %.1f ms (%.1f on device), status %.1f ms, finalize %.1f ms, scatter %.1f ms, %d host threads, %s buffers",
+             (long long)st.n_sc, (long long)n_var, (long long)st.cells, (long long)st.n_launches, ms_wait, ms_pack,
+             wide ? "" : "_packed", ms_run, st.ms_total, ms_status, ms_fin, ms_scatter, nt, mem.owned.empty() ? "page-locked" : "pageable");
 #endif  // VD_DROPIN_WITH_REF
 }
