@@ -214,13 +214,20 @@ def run_seam(args, b):
                 os.makedirs(od, exist_ok=True)
                 t0 = time.perf_counter()
                 r = subprocess.run([exe, q, t, fa, "-p", od + "/", "-v", "1", "-t", str(cores), "-c", "gap", "50"],
-                                   capture_output=True, text=True, cwd=od)
+                                   capture_output=True, text=True, cwd=od, env=dict(os.environ, VD_DROPIN_TIMES="1"))
                 out[name] = {"rc": r.returncode, "wall_s": time.perf_counter() - t0, "timer_5_precision_recall_s": cli_timer(r.stderr, 5),
                              "timer_9_total_s": cli_timer(r.stderr, 9)}
-            same = all(open(os.path.join(tmp, "reference", f)).read() == open(os.path.join(tmp, "drop_in", f)).read()
-                       for f in ("precision-recall-summary.tsv", "superclusters.tsv", "phasing-summary.tsv"))
+                bd = [ln.split("GPU precision/recall:")[1].strip() for ln in r.stderr.splitlines() if "GPU precision/recall:" in ln]
+                if bd:
+                    out[name]["breakdown"] = bd[-1]
+            def same(files):
+                return bool(all(open(os.path.join(tmp, "reference", f)).read() == open(os.path.join(tmp, "drop_in", f)).read() for f in files))
             res["cli"] = {"input": f"workloads.vcfgen seed {args.seed}, 2 contigs x {args.cli_contig_len} bp, -c gap 50, -t {cores}",
-                          "reference": out["reference"], "drop_in": out["drop_in"], "summary_files_identical": bool(same)}
+                          "reference": out["reference"], "drop_in": out["drop_in"],
+                          # the tie rule can move single variants between TP and FP against the UNMODIFIED reference;
+                          # tests/test_cli_dropin.py holds the byte-for-byte comparison against the canonical-tie-break build
+                          "order_independent_files_identical": same(("superclusters.tsv", "phase-blocks.tsv", "phasing-summary.tsv", "switchflips.tsv")),
+                          "precision_recall_summary_identical": same(("precision-recall-summary.tsv",))}
     return res
 
 
@@ -287,9 +294,9 @@ def main():
                     help="--impl reference: superclusters per step (0 = the workload's full batch, i.e. the GPU arm's config)")
     ap.add_argument("--cpu-sample", type=int, default=600_000, help="superclusters in the cpu_baseline sample of the GPU arm's line")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--gather-slices", type=int, default=0,
-                    help="N > 1: slices of a rank's shard whose result all-gather overlaps the next slice's kernels "
-                         "(0 = by world size: 1 up to 2 GPUs, 2 up to 4, 3 beyond - the exchange grows with the number of ranks)")
+    ap.add_argument("--exchange", default="overlap", choices=["overlap", "sync"],
+                    help="N > 1: the all-gather of a step's records runs beside the next step's kernels (two records alternate), "
+                         "or every step waits for its own exchange")
     ap.add_argument("--sv-n-sc", type=int, default=3_600_000, help="superclusters of the secondary (configs[3]) workload")
     ap.add_argument("--sv-cpu-sample", type=int, default=40_000, help="superclusters in the secondary workload's cpu_baseline sample")
     ap.add_argument("--secondary", action="store_true", default=True,
@@ -335,71 +342,72 @@ def main():
         setattr(din, k, t.data_ptr())
     din.rplane_seq = None
     din.max_qual = b.max_qual
-    # Results live in contiguous record buffers (shard.ResultRecord): the kernels write straight into
-    # them and the end-of-step exchange is an all-gather with no packing.  With several GPUs the shard
-    # is run in `--gather-slices` slices (vd_run_device_slice), each with its own record, so that the
-    # all-gather of slice k (on a side stream) overlaps the kernels of slice k+1; one GPU: one slice.
-    K = (args.gather_slices or (1 if world <= 2 else 2 if world <= 4 else 3)) if world > 1 else 1
-    s_cut = [b.n_sc * k // K for k in range(K + 1)]
-    v_cut = [int(b.var_off[4 * c]) for c in s_cut]
-    counts = torch.tensor([[s_cut[k + 1] - s_cut[k], v_cut[k + 1] - v_cut[k]] for k in range(K)], dtype=torch.int64, device=dev)
-    off_sc = off_var = 0
+    # The kernels write wide (32-bit) result arrays in HBM.  With several GPUs each rank then narrows its results into
+    # a 16-bit exchange record (vd_pack_device, shard.PackedRecord) and ONE all-gather per step moves the records of
+    # all ranks (north_star: "a single NCCL all-gather over NVLink of the per-cluster score/credit arrays at the end").
+    # The batch-global indices of a shard never change and are exchanged once, before the timed region.  Two records
+    # alternate, so that the all-gather of step k (comm stream) runs beside the kernels of step k+1; every step's
+    # exchange completes inside the timed region (--exchange sync: each step waits for its own all-gather).
+    wide = {"aln_score": torch.zeros(4 * b.n_sc, dtype=torch.int32, device=dev), "status": torch.zeros(4 * b.n_sc, dtype=torch.int32, device=dev),
+            "aln_end_plane": torch.zeros(4 * b.n_sc, dtype=torch.uint8, device=dev), "aln_beg_plane": torch.zeros(4 * b.n_sc, dtype=torch.uint8, device=dev),
+            "assigned": torch.zeros(max(2 * n_var, 1), dtype=torch.uint8, device=dev), "callq": torch.zeros(max(2 * n_var, 1), dtype=torch.float32, device=dev)}
+    for k in ("sync_group", "ref_ed", "query_ed"):
+        wide[k] = torch.zeros(max(2 * n_var, 1), dtype=torch.int32, device=dev)
+    dout = vd_batch_out()
+    for name, t in wide.items():
+        setattr(dout, name, t.data_ptr())
+    K = 1
+    precs, dpacked, gathered, comm_done = [], [], [], []
+    comm = None
     if world > 1:
+        counts = torch.tensor([b.n_sc, n_var], dtype=torch.int64, device=dev)
         allc = [torch.zeros_like(counts) for _ in range(world)]
         dist.all_gather(allc, counts)
-        allc = torch.stack(allc).cpu().numpy()                      # [world, K, 2]
-        off_sc, off_var = int(allc[:rank, :, 0].sum()), int(allc[:rank, :, 1].sum())
-        caps = allc.max(axis=0)                                     # [K, 2]
-    else:
-        caps = counts.cpu().numpy()
-    recs, slices, gathered = [], [], []
-    for k in range(K):
-        s0, s1, v0, v1 = s_cut[k], s_cut[k + 1], v_cut[k], v_cut[k + 1]
-        rec = shard.ResultRecord(int(caps[k, 0]), max(int(caps[k, 1]), 1), dev)
-        # batch-global indices of this slice's records (ranks own disjoint ranges of the global arrays)
-        rec.set_shard(np.arange(off_sc + s0, off_sc + s1), np.arange(off_var + v0, off_var + v1))
-        din_k = vd_batch_in()
-        din_k.n_sc = s1 - s0
-        for name, t in d_in.items():
-            setattr(din_k, name, t.data_ptr())
-        din_k.ref_off = d_in["ref_off"].data_ptr() + 8 * s0
-        din_k.var_off = d_in["var_off"].data_ptr() + 8 * 4 * s0
-        din_k.rplane_seq = None
-        din_k.max_qual = b.max_qual
-        dout_k = vd_batch_out()
-        for name in ("aln_score", "aln_end_plane", "aln_beg_plane", "status", "assigned", "sync_group", "ref_ed", "query_ed", "callq"):
-            setattr(dout_k, name, rec.views[name].data_ptr())
-        recs.append(rec)
-        slices.append((din_k, dout_k, v0, v1 - v0))
-        gathered.append(torch.empty(world * rec.nbytes, dtype=torch.uint8, device=dev) if world > 1 else None)
-    rec, dout = recs[0], slices[0][1]          # one GPU: the whole shard is slice 0
-    comm = torch.cuda.Stream(device=dev) if world > 1 else None
+        allc = torch.stack(allc).cpu().numpy()
+        cap_sc, cap_var = int(allc[:, 0].max()), max(int(allc[:, 1].max()), 1)
+        off_sc, off_var = int(allc[:rank, 0].sum()), int(allc[:rank, 1].sum())
+        # ranks own disjoint ranges of the global arrays; exchanged once
+        all_sc, all_var = shard.gather_index(np.arange(off_sc, off_sc + b.n_sc), np.arange(off_var, off_var + n_var), cap_sc, cap_var, dist, dev)
+        assert sum(len(x) for x in all_sc) == sc_total
+        for _ in range(2):
+            pr = shard.PackedRecord(cap_sc, cap_var, dev)
+            pr.set_counts(b.n_sc, n_var)
+            dp = vd_packed_out()
+            for name in ("aln_score", "aln_planes", "status", "sync_group", "ref_ed", "query_ed", "callq"):
+                setattr(dp, name, pr.views[name].data_ptr())
+            precs.append(pr); dpacked.append(dp)
+            gathered.append(torch.empty(world * pr.nbytes, dtype=torch.uint8, device=dev))
+            comm_done.append(torch.cuda.Event())
+        comm = torch.cuda.Stream(device=dev)
     torch.cuda.synchronize()
     step_stats = {}
+    step_no = [0]
 
     def run_pass(engine, acc, exchange):
-        """One pass of the hot path over this rank's shard, slice by slice (+ the exchange)."""
+        """One pass of the hot path over this rank's shard (+ the exchange of its results)."""
         acc.clear()
-        for k in range(K):
-            din_k, dout_k, v0, nv = slices[k]
-            if K == 1:
-                engine.run_device(din, dout, n_var, b.ref_bytes, b.alt_bytes)
-            else:
-                engine.run_device_slice(din_k, dout_k, v0, nv, b.ref_bytes // K, b.alt_bytes // K)
-            st_ = engine.stats()               # returns with the slice's kernels finished
-            for key, val in st_.items():
-                if isinstance(val, list):
-                    acc[key] = [x + y for x, y in zip(acc.get(key, [0] * len(val)), val)]
-                else:
-                    acc[key] = acc.get(key, 0) + val
-            if exchange and world > 1:
-                with torch.cuda.stream(comm):
-                    recs[k].all_gather(dist, gathered[k])
+        engine.run_device(din, dout, n_var, b.ref_bytes, b.alt_bytes)      # returns with the kernels finished
+        acc.update(engine.stats())
         if exchange and world > 1:
-            stream.wait_stream(comm)           # the step ends when the last slice has been exchanged
+            i = step_no[0] % 2
+            step_no[0] += 1
+            stream.wait_event(comm_done[i])        # the all-gather that last read this record (two steps ago) is done
+            engine.pack_device(dout, b.n_sc, n_var, dpacked[i])
+            ready = torch.cuda.Event()
+            ready.record(stream)
+            with torch.cuda.stream(comm):
+                comm.wait_event(ready)
+                precs[i].all_gather(dist, gathered[i])
+                comm_done[i].record(comm)
+            if args.exchange == "sync":
+                stream.wait_event(comm_done[i])
 
     def step_resident():
         run_pass(eng, step_stats, True)
+
+    def finish_exchange():
+        if world > 1:
+            stream.wait_stream(comm)               # the timed region ends when the last step's records have arrived
 
     def barrier():
         if world > 1:
@@ -409,6 +417,7 @@ def main():
     # ---- warm-up, then EXACTLY K timed steps; device time, max over ranks ----
     for _ in range(args.warmup):
         step_resident()
+    finish_exchange()
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -421,10 +430,11 @@ def main():
     for _ in range(args.steps):
         step_resident()
         st = dict(step_stats)
-        launches += st["n_launches"]
+        launches += st["n_launches"] + (1 if world > 1 else 0)
         ms_short += st["ms_short"]; ms_fwd += st["ms_long_fwd"]; ms_bwd += st["ms_long_bwd"]
         ms_walk += st["ms_long_walk"]; ms_plan += st["ms_plan"]; ms_kernels += st["ms_total"]
         ms_small = [a + b_ for a, b_ in zip(ms_small, st["ms_small"])]
+    finish_exchange()
     ev1.record(stream)
     barrier()
     ms = ev0.elapsed_time(ev1)
@@ -434,6 +444,17 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
     st = dict(step_stats)
+    per_rank = None
+    if world > 1:        # cell load and kernel time of every rank (LPT by cells, shard.lpt_partition) and the straggler's long path
+        mine = torch.tensor([float(b.cells().sum()), float(b.n_sc), ms / args.steps, ms_kernels / args.steps,
+                             float(st["ms_long_wall"]), float(st["n_long"])], dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        allr = torch.stack(allr).cpu().numpy()
+        per_rank = {"cells": [int(x) for x in allr[:, 0]], "superclusters": [int(x) for x in allr[:, 1]],
+                    "ms_per_step": [round(float(x), 3) for x in allr[:, 2]], "kernel_ms_per_step": [round(float(x), 3) for x in allr[:, 3]],
+                    "long_path_wall_ms": [round(float(x), 3) for x in allr[:, 4]], "long_alignments": [int(x) for x in allr[:, 5]],
+                    "cell_imbalance_max_over_mean": float(allr[:, 0].max() / allr[:, 0].mean())}
 
     # ---- e2e: vd_run() with pinned host buffers, H2D + D2H inside the timed region ----
     def pin(a):
@@ -515,7 +536,7 @@ def main():
                        "source": "superclusters resampled (seeded) from the real HG002 chr1:1-5Mb demo batch"
                                  + (" + synthetic SV tail" if WORKLOADS[args.workload]["sv_frac"] else ""),
                        "n_superclusters_per_step": sc_total, "cells_per_step": cells_total,
-                       "per_gpu_superclusters": b.n_sc, "parallelism": f"shard{world}+allgather({K} overlapped slices)" if world > 1 else "single",
+                       "per_gpu_superclusters": b.n_sc, "parallelism": f"shard{world} (LPT by cells) + one all-gather of 16-bit records per step ({args.exchange})" if world > 1 else "single",
                        "l2": "inputs+outputs exceed L2 (no flush needed)" if b.io_bytes() > 200e6 else "small batch: L2-resident"},
             "clocks": clocks,
             "e2e": {"value": cells_total / (e2e_ms * 1e-3) / 1e9, "unit": "Gcells/s",
@@ -526,6 +547,10 @@ def main():
                     "wide_records": {"api": "vd_run (32-bit result records)", "ms_per_step": e2e_wide_ms,
                                      "d2h_bytes_per_step": int(st_w["d2h_bytes"])}},
             "gpu_launches": int(launches),
+            "per_rank": per_rank,
+            "exchange": ({"collective": "all_gather_into_tensor (NCCL) of shard.PackedRecord", "bytes_per_rank": precs[0].nbytes,
+                          "received_bytes_per_rank_per_step": (world - 1) * precs[0].nbytes, "mode": args.exchange,
+                          "static_index_exchanged_once_bytes_per_rank": 8 * (2 + cap_sc + cap_var)} if world > 1 else None),
             "tie_superclusters": {"count": tie_count(ho.status, b.n_sc) if world == 1 else None, "of": b.n_sc,
                                   "note": "superclusters with VD_ST_TIE on this rank: an ambiguous swap edge on an optimal path, where the "
                                           "reference's pick depends on unordered_set iteration order (SURVEY.md 8a); parity there is against oracle-B"},

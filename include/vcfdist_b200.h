@@ -223,6 +223,13 @@ int  vd_run_device(vd_handle *h, const vd_batch_in *in_dev, vd_batch_out *out_de
 int  vd_run_device_slice(vd_handle *h, const vd_batch_in *in_dev, vd_batch_out *out_dev,
                          int64_t first_var, int64_t n_var, int64_t ref_bytes, int64_t alt_bytes);
 
+/* 16-bit records from wide ones, both resident in this GPU's HBM: enqueued on the handle's stream behind the kernels
+ * of vd_run_device / vd_run_device_slice (the exchange step of a multi-GPU run moves the narrow records).  packed->callq
+ * may alias wide->callq or be null (nothing to narrow there).  vd_packed_overflow: nonzero once a value did not fit,
+ * valid after the stream has been synchronised; reset by the next vd_run_device*.                                   */
+int  vd_pack_device(vd_handle *h, const vd_batch_out *wide_dev, int64_t n_sc, int64_t n_var, const vd_packed_out *packed_dev);
+int  vd_packed_overflow(const vd_handle *h);
+
 int  vd_get_stats(const vd_handle *h, vd_stats *out);
 const char *vd_last_error(const vd_handle *h);
 

@@ -103,6 +103,34 @@ def _worker(rank, world, port, q):
                     bad["slice_" + name] = 1
     if not (np.concatenate(seen_sc) == mine).all():
         bad["slice_cover"] = 1
+    # the 16-bit exchange record (what vd_pack_device fills on the GPU): indices exchanged once, then one all-gather
+    cap_sc, cap_var = max(len(p) for p in parts), b.n_var
+    all_sc, all_var = shard.gather_index(mine, vidx, cap_sc, cap_var, dist, "cpu")
+    prec = shard.PackedRecord(cap_sc, cap_var, "cpu")
+    prec.set_counts(len(mine), len(vidx))
+    a, v = 4 * len(mine), 2 * len(vidx)
+    sc16 = np.where(out["aln_score"] < 0, 0xFFFF, out["aln_score"]).astype(np.uint16)
+    prec.views["aln_score"][:a] = torch.from_numpy(sc16.view(np.int16))
+    prec.views["status"][:a] = torch.from_numpy(out["status"].astype(np.uint16).view(np.int16))
+    prec.views["aln_planes"][:a] = torch.from_numpy((out["aln_end_plane"] | (out["aln_beg_plane"] << 1)).astype(np.uint8))
+    prec.views["sync_group"][:v] = torch.from_numpy(((out["assigned"].astype(np.uint16) << 14) | out["sync_group"].astype(np.uint16)).view(np.int16))
+    prec.views["ref_ed"][:v] = torch.from_numpy(out["ref_ed"].astype(np.uint16).view(np.int16))
+    prec.views["query_ed"][:v] = torch.from_numpy(out["query_ed"].astype(np.uint16).view(np.int16))
+    prec.views["callq"][:v] = torch.from_numpy(out["callq"])
+    gp = prec.all_gather(dist)
+    for r in range(world):
+        if not (all_sc[r] == parts[r]).all():
+            bad["packed_index"] = 1
+        pr = prec.parse(gp, r)
+        aidx = (all_sc[r][:, None] * 4 + np.arange(4)[None, :]).reshape(-1)
+        for name in ("aln_score", "aln_end_plane", "aln_beg_plane"):
+            if not (pr[name].numpy() == want[name][aidx]).all():
+                bad["packed_" + name] = 1
+        if not (pr["status"].numpy().astype(np.uint32) == want["status"][aidx]).all():
+            bad["packed_status"] = 1
+        for name in ("assigned", "sync_group", "ref_ed", "query_ed", "callq"):
+            if not (pr[name].numpy() == want[name].reshape(2, -1)[:, all_var[r]]).all():
+                bad["packed_" + name] = 1
     q.put((rank, bad))
     dist.barrier()
     dist.destroy_process_group()

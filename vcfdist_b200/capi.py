@@ -21,7 +21,7 @@ LIB_PATH = os.path.join(_ROOT, "libvcfdist_b200.so")
 
 EXPORTS = ("vd_abi_version", "vd_create", "vd_destroy", "vd_run", "vd_run_device", "vd_run_device_slice",
            "vd_finalize", "vd_get_stats", "vd_last_error", "vd_stream", "vd_wf_batch", "vd_swg_align_batch",
-           "vd_run_packed", "vd_finalize_packed", "vd_host_alloc", "vd_host_free")
+           "vd_run_packed", "vd_finalize_packed", "vd_host_alloc", "vd_host_free", "vd_pack_device", "vd_packed_overflow")
 
 _lib = None
 
@@ -53,6 +53,10 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.vd_host_alloc.restype = C.c_void_p
     lib.vd_host_free.argtypes = [C.c_void_p]
     lib.vd_host_free.restype = None
+    lib.vd_pack_device.argtypes = [C.c_void_p, C.POINTER(vd_batch_out), C.c_int64, C.c_int64, C.POINTER(vd_packed_out)]
+    lib.vd_pack_device.restype = C.c_int
+    lib.vd_packed_overflow.argtypes = [C.c_void_p]
+    lib.vd_packed_overflow.restype = C.c_int
     lib.vd_run_device.argtypes = [C.c_void_p, C.POINTER(vd_batch_in), C.POINTER(vd_batch_out),
                                   C.c_int64, C.c_int64, C.c_int64]
     lib.vd_run_device.restype = C.c_int
@@ -135,6 +139,13 @@ class Engine:
         cin, cout = batch.as_c(), out.as_c()
         self._check(self.lib.vd_run_packed(self.h, C.byref(cin), C.byref(cout)))
         return out
+
+    def pack_device(self, dwide: vd_batch_out, n_sc: int, n_var: int, dpacked: vd_packed_out):
+        """Narrow device-resident wide records into 16-bit ones on the handle's stream (asynchronous)."""
+        self._check(self.lib.vd_pack_device(self.h, C.byref(dwide), n_sc, n_var, C.byref(dpacked)))
+
+    def packed_overflow(self) -> bool:
+        return bool(self.lib.vd_packed_overflow(self.h))
 
     def run_device(self, din: vd_batch_in, dout: vd_batch_out, n_var: int, ref_bytes: int, alt_bytes: int):
         """All pointers already resident in this GPU's HBM."""

@@ -572,6 +572,7 @@ extern "C" int vd_run_device_slice(vd_handle *h, const vd_batch_in *in, vd_batch
     h->stats_status_or = 0;
     h->stats.n_sc = in->n_sc; h->stats.n_var = n_var;
     h->stats.io_bytes = io_bytes_of(in->n_sc, n_var, ref_bytes, alt_bytes);
+    *h->h_range = 0;
     Work &W = h->work[0];
     const OutDev base = o;                 // per-variant arrays are indexed [slot*n_var + (v - first_var)]
     o.assigned -= first_var; o.sync_group -= first_var; o.ref_ed -= first_var; o.query_ed -= first_var; o.callq -= first_var;
@@ -580,6 +581,23 @@ extern "C" int vd_run_device_slice(vd_handle *h, const vd_batch_in *in, vd_batch
     const int rc2 = chunk_harvest(h, W);
     return rc != VD_OK ? rc : rc2;
 }
+
+// 16-bit records from device-resident wide ones, on the handle's stream (the exchange of a multi-GPU step moves these)
+extern "C" int vd_pack_device(vd_handle *h, const vd_batch_out *wide, int64_t n_sc, int64_t n_var, const vd_packed_out *packed) {
+    if (!h || !wide || !packed || n_sc < 0 || n_var < 0) return VD_E_BADINPUT;
+    CK(cudaSetDevice(h->device));
+    if (n_sc == 0) return VD_OK;
+    OutDev o{wide->aln_score, wide->aln_end_plane, wide->aln_beg_plane, wide->status, wide->assigned,
+             wide->sync_group, wide->ref_ed, wide->query_ed, wide->callq};
+    const int64_t nel = 4 * n_sc > 2 * n_var ? 4 * n_sc : 2 * n_var;
+    VD_LAUNCH(pack_out_kernel, (unsigned)((nel + 255) / 256), 256, 0, h->stream, o, 4 * n_sc, n_var, packed->aln_score, packed->aln_planes,
+              packed->status, packed->sync_group, packed->ref_ed, packed->query_ed, h->h_range);
+    if (packed->callq && packed->callq != wide->callq)
+        CK(cudaMemcpyAsync(packed->callq, wide->callq, 8 * (size_t)n_var, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaGetLastError());
+    return VD_OK;
+}
+extern "C" int vd_packed_overflow(const vd_handle *h) { return h && h->h_range ? (int)*h->h_range : 0; }
 
 // error path of vd_run: nothing of this call may still be in flight when the caller gets its buffers back, and
 // the handle must be reusable (no stale chunk state, no stale malformed-input count)

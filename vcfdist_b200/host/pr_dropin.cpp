@@ -89,14 +89,61 @@ struct Runtime {
     uint8_t *arena = nullptr;
     int64_t arena_cap = 0;
     bool tried = false;
+    double init_ms[3] = {0, 0, 0};              // vd_create, page-locking the arena, warm-up batch
     void init() {
+        using clk = std::chrono::steady_clock;
+        auto ms_since = [](clk::time_point t) { return std::chrono::duration<double, std::milli>(clk::now() - t).count(); };
+        auto t0 = clk::now();
         tried = true;
         if (const char *d = std::getenv("VD_DEVICE")) device = std::atoi(d);
         rc = vd_create(device, 0, &h);
         if (rc != VD_OK) return;
+        init_ms[0] = ms_since(t0); t0 = clk::now();
         int64_t mb = 1024;
         if (const char *m = std::getenv("VD_PIN_MB")) mb = std::atoll(m);
         if (mb > 0) { arena = (uint8_t *)vd_host_alloc(mb << 20); arena_cap = arena ? (mb << 20) : 0; }
+        init_ms[1] = ms_since(t0); t0 = clk::now();
+        if (!std::getenv("VD_NO_WARMUP_BATCH")) warm_up();
+        init_ms[2] = ms_since(t0);
+    }
+    // A few synthetic superclusters of every size class through the whole path, so that the kernels' code is on the
+    // GPU and the handle's work buffers exist before the real batch arrives (CUDA loads a kernel at its first launch).
+    void warm_up() {
+        const int lens[] = {5, 5, 5, 5, 14, 14, 40, 40, 100, 700, 3000};
+        std::vector<int64_t> ref_off{0}, var_off{0}, alt_off{0};
+        std::vector<uint8_t> ref, alt, type;
+        std::vector<int32_t> pos, rlen;
+        std::vector<float> qual;
+        unsigned x = 12345u;
+        auto rnd = [&x]() { x = x * 1664525u + 1013904223u; return x >> 16; };
+        for (int rep = 0; rep < 8; rep++)
+            for (int L : lens) {
+                const size_t r0 = ref.size();
+                for (int k = 0; k < L; k++) ref.push_back("ACGT"[rnd() & 3]);
+                ref_off.push_back((int64_t)ref.size());
+                for (int hap = 0; hap < 4; hap++) {
+                    // haplotype `hap` carries a SNP at 1 + hap (+ a second one further on in long windows): heterozygous,
+                    // so that every alignment of the supercluster is computed
+                    for (int at : {1 + hap, L > 30 ? L / 2 + hap : -1}) {
+                        if (at < 0 || at >= L - 1) continue;
+                        pos.push_back(at); rlen.push_back(1); type.push_back(VD_TYPE_SUB);
+                        alt.push_back(ref[r0 + at] == 'A' ? 'C' : 'A');
+                        alt_off.push_back((int64_t)alt.size());
+                        qual.push_back(30.f);
+                    }
+                    var_off.push_back((int64_t)pos.size());
+                }
+            }
+        const int64_t n_sc = (int64_t)ref_off.size() - 1, n_var = (int64_t)pos.size();
+        vd_batch_in in{};
+        in.n_sc = (int32_t)n_sc; in.ref_off = ref_off.data(); in.ref_seq = ref.data(); in.rplane_seq = nullptr;
+        in.var_off = var_off.data(); in.var_pos = pos.data(); in.var_rlen = rlen.data(); in.var_type = type.data();
+        in.alt_off = alt_off.data(); in.alt_seq = alt.data(); in.var_qual = qual.data(); in.max_qual = 60.f;
+        std::vector<uint16_t> a16(3 * 4 * n_sc), v16(3 * 2 * n_var);
+        std::vector<uint8_t> pl(4 * n_sc);
+        std::vector<float> cq(2 * n_var);
+        vd_packed_out pk{a16.data(), pl.data(), a16.data() + 4 * n_sc, v16.data(), v16.data() + 2 * n_var, v16.data() + 4 * n_var, cq.data()};
+        vd_run_packed(h, &in, &pk);          // result and return code are of no interest
     }
     Runtime() { if (!std::getenv("VD_NO_WARM")) th = std::thread([this] { init(); }); }
     vd_handle *get() {
@@ -114,19 +161,39 @@ static Runtime rt;
 #endif
 
 // host buffers of one call: carved from the page-locked arena while they fit, pageable otherwise
+// Pageable blocks that outlive a call: the k-th request of a call gets the k-th block, grown when too small.  A second
+// call of the same size then touches no fresh page (first-touch faults cost more than the packing itself).
+struct HeapSlots {
+    std::vector<std::pair<void *, int64_t>> slot;
+    size_t next = 0;
+    void *take(int64_t bytes) {
+        if (next == slot.size()) slot.push_back({nullptr, 0});
+        auto &sl = slot[next++];
+        if (sl.second < bytes) {
+            std::free(sl.first);
+            sl.first = std::malloc((size_t)(bytes + bytes / 8));
+            sl.second = sl.first ? bytes + bytes / 8 : 0;
+        }
+        return sl.first;
+    }
+    ~HeapSlots() { for (auto &sl : slot) std::free(sl.first); }
+};
+static HeapSlots heap_slots[2];              // [0] pageable stand-ins for arena overflow, [1] host-only scratch
+
 struct HostMem {
     uint8_t *arena = nullptr;
     int64_t cap = 0, used = 0;
-    std::vector<void *> owned;
+    HeapSlots *heap = nullptr;
+    bool spilled = false;
+    explicit HostMem(HeapSlots *hs) : heap(hs) { heap->next = 0; }
     template <class T> T *take(int64_t n) {
         const int64_t bytes = ((n > 0 ? n : 1) * (int64_t)sizeof(T) + 255) & ~(int64_t)255;
         if (arena && used + bytes <= cap) { T *p = (T *)(arena + used); used += bytes; return p; }
-        void *p = std::malloc((size_t)bytes);
+        if (arena) spilled = true;
+        void *p = heap->take(bytes);
         if (!p) ERROR("vcfdist_b200: out of host memory (%lld bytes)", (long long)bytes);
-        owned.push_back(p);
         return (T *)p;
     }
-    ~HostMem() { for (void *p : owned) std::free(p); }
 };
 
 struct CtgView {                       // per contig, resolved once (no map lookups per supercluster or variant)
@@ -142,8 +209,8 @@ struct Packed {
     uint8_t *ref_seq = nullptr, *rplane_seq = nullptr, *alt_seq = nullptr, *var_type = nullptr;
     int32_t *var_pos = nullptr, *var_rlen = nullptr;
     float *var_qual = nullptr;
-    std::vector<ScLoc> sc_loc;                  // batch order -> (contig, supercluster)
-    std::vector<std::array<int, 4>> vb;         // first variant index of each haplotype of a supercluster in its ctgVariants
+    ScLoc *sc_loc = nullptr;                    // batch order -> (contig, supercluster)
+    std::array<int, 4> *vb = nullptr;           // first variant index of each haplotype of a supercluster in its ctgVariants
     std::vector<CtgView> ctgs;
 
     vd_batch_in view(float max_qual) const {
@@ -159,31 +226,45 @@ struct Packed {
 
 // What precision_recall_wrapper reads per supercluster (src/dist.cpp:1786-1822), for all superclusters, largest-RAM
 // bucket first as the reference schedules them (src/dist.cpp:1670-1672).  Pass 1 sizes, pass 2 bytes.
+static double pack_ms[3];                    // sizes pass + offsets, allocation, bytes pass (VD_DROPIN_TIMES)
 static void pack(superclusterData *scd, const std::vector<std::vector<std::vector<int>>> &sc_groups, int nt,
-                 HostMem &mem, Packed &p) {
+                 HostMem &mem, HostMem &heap, Packed &p) {
+    using clk = std::chrono::steady_clock;
+    auto ms_since = [](clk::time_point t) { return std::chrono::duration<double, std::milli>(clk::now() - t).count(); };
+    auto tp0 = clk::now();
     p.ctgs.resize(scd->contigs.size());
-    for (int step = (int)sc_groups.size() - 1; step >= 0; step--)
-        for (size_t k = 0; k < sc_groups[step][SC_IDX].size(); k++) {
-            const int ci = sc_groups[step][CTG_IDX][k];
-            CtgView &cvw = p.ctgs[ci];
-            if (!cvw.sc) {
-                const std::string &ctg = scd->contigs[ci];
-                cvw.sc_mut = scd->superclusters.at(ctg).get();
-                cvw.sc = cvw.sc_mut;
-                for (int j = 0; j < CALLSETS * HAPS; j++) cvw.cv[j] = cvw.sc->ctg_variants[j >> 1][j & 1].get();
-                auto it = scd->ref->fasta.find(ctg);
-                if (it == scd->ref->fasta.end())
-                    ERROR("Contig '%s' not present in reference FASTA", ctg.data());   // src/dist.cpp:237-239
-                cvw.fa = &it->second;
-            }
-            p.sc_loc.push_back({ci, sc_groups[step][SC_IDX][k]});
+    for (size_t ci = 0; ci < scd->contigs.size(); ci++) {               // every map lookup of the call happens here
+        const std::string &ctg = scd->contigs[ci];
+        auto sit = scd->superclusters.find(ctg);
+        if (sit == scd->superclusters.end()) continue;
+        CtgView &cvw = p.ctgs[ci];
+        cvw.sc_mut = sit->second.get();
+        cvw.sc = cvw.sc_mut;
+        for (int j = 0; j < CALLSETS * HAPS; j++) cvw.cv[j] = cvw.sc->ctg_variants[j >> 1][j & 1].get();
+        auto it = scd->ref->fasta.find(ctg);
+        cvw.fa = it == scd->ref->fasta.end() ? nullptr : &it->second;   // reported below if a supercluster needs it
+    }
+    {
+        int64_t total = 0;
+        for (const auto &grp : sc_groups) total += (int64_t)grp[SC_IDX].size();
+        p.sc_loc = heap.take<ScLoc>(total);
+        p.n_sc = total;
+        int64_t at = 0;
+        for (int step = (int)sc_groups.size() - 1; step >= 0; step--) {
+            const std::vector<int> &ci = sc_groups[step][CTG_IDX], &si = sc_groups[step][SC_IDX];
+            ScLoc *dst = p.sc_loc + at;
+            parallel_for((int64_t)si.size(), nt, [&](int, int64_t k0, int64_t k1) {
+                for (int64_t k = k0; k < k1; k++) dst[k] = ScLoc{ci[k], si[k]};
+            });
+            at += (int64_t)si.size();
         }
-    const int64_t n_sc = p.n_sc = (int64_t)p.sc_loc.size();
-    p.vb.resize((size_t)n_sc);
+    }
+    const int64_t n_sc = p.n_sc;
+    p.vb = heap.take<std::array<int, 4>>(n_sc);
     p.ref_off = mem.take<int64_t>(n_sc + 1);
     p.var_off = mem.take<int64_t>(4 * n_sc + 1);
-    std::vector<int64_t> alt_sc((size_t)n_sc + 1, 0);       // ALT bytes per supercluster -> first ALT byte of each
-    p.ref_off[0] = p.var_off[0] = 0;
+    int64_t *alt_sc = heap.take<int64_t>(n_sc + 1);                         // ALT bytes per supercluster -> first ALT byte of each
+    p.ref_off[0] = p.var_off[0] = alt_sc[0] = 0;
     std::atomic<int> bad_window{-1}, any_rplane{0};
     parallel_for(n_sc, nt, [&](int, int64_t s0, int64_t s1) {
         bool rpl = false;
@@ -191,7 +272,7 @@ static void pack(superclusterData *scd, const std::vector<std::vector<std::vecto
             const CtgView &c = p.ctgs[p.sc_loc[s].ctg];
             const int sc_idx = p.sc_loc[s].sc;
             const int beg = c.sc->begs[sc_idx], end = c.sc->ends[sc_idx];
-            if (beg < 0 || end >= (int)c.fa->size() || end < beg) { bad_window = p.sc_loc[s].ctg; p.ref_off[s + 1] = 0; }
+            if (!c.fa || beg < 0 || end >= (int)c.fa->size() || end < beg) { bad_window = p.sc_loc[s].ctg; p.ref_off[s + 1] = 0; }
             else p.ref_off[s + 1] = (int64_t)end - beg + 1;
             int64_t ab = 0;
             for (int k = 0; k < CALLSETS * HAPS; k++) {
@@ -223,9 +304,10 @@ static void pack(superclusterData *scd, const std::vector<std::vector<std::vecto
     if (bad_window >= 0) ERROR("Contig '%s' not present in reference FASTA", scd->contigs[bad_window].data());   // src/dist.cpp:237-239
     offsets_from_sizes(p.ref_off, n_sc, nt);
     offsets_from_sizes(p.var_off, 4 * n_sc, nt);
-    offsets_from_sizes(alt_sc.data(), n_sc, nt);
+    offsets_from_sizes(alt_sc, n_sc, nt);
     const int64_t n_var = p.n_var = p.var_off[4 * n_sc];
     const int64_t ref_bytes = p.ref_off[n_sc], alt_bytes = alt_sc[(size_t)n_sc];
+    pack_ms[0] = ms_since(tp0); tp0 = clk::now();
     p.ref_seq = mem.take<uint8_t>(ref_bytes);
     p.rplane_seq = any_rplane ? mem.take<uint8_t>(ref_bytes) : nullptr;
     p.alt_seq = mem.take<uint8_t>(alt_bytes);
@@ -235,6 +317,7 @@ static void pack(superclusterData *scd, const std::vector<std::vector<std::vecto
     p.var_type = mem.take<uint8_t>(n_var);
     p.var_qual = mem.take<float>(n_var);
     p.alt_off[0] = 0;
+    pack_ms[1] = ms_since(tp0); tp0 = clk::now();
     parallel_for(n_sc, nt, [&](int, int64_t s0, int64_t s1) {
         for (int64_t s = s0; s < s1; s++) {
             const CtgView &c = p.ctgs[p.sc_loc[s].ctg];
@@ -269,6 +352,7 @@ static void pack(superclusterData *scd, const std::vector<std::vector<std::vecto
             }
         }
     });
+    pack_ms[2] = ms_since(tp0);
 }
 
 static void scatter(const Packed &p, const vd_batch_in &in, const vd_final &fin, int nt) {
@@ -420,9 +504,9 @@ void precision_recall_threads_wrapper(
 
 #ifdef VD_DROPIN_WITH_REF
     {   // fixture tool (oracle/_ref/vcfdist_dump): the REFERENCE computes, we only record
-        vdhost::HostMem mem;
+        vdhost::HostMem mem(&vdhost::heap_slots[0]), heap(&vdhost::heap_slots[1]);
         vdhost::Packed p;
-        vdhost::pack(clusterdata_ptr.get(), sc_groups, nt, mem, p);
+        vdhost::pack(clusterdata_ptr.get(), sc_groups, nt, mem, heap, p);
         if (const char *path = std::getenv("VD_DUMP_BATCH")) vdhost::dump_batch(p, max_qual, path);
         ref_precision_recall_threads_wrapper(clusterdata_ptr, sc_groups);
         if (const char *path = std::getenv("VD_DUMP_FINAL")) vdhost::dump_final(p, path);
@@ -435,10 +519,10 @@ void precision_recall_threads_wrapper(
                   "there is no CPU fallback for the precision/recall path", vdhost::rt.device, vdhost::rt.rc);
     const double ms_wait = ms_since(t0);
     t0 = clk::now();
-    vdhost::HostMem mem;
+    vdhost::HostMem mem(&vdhost::heap_slots[0]), heap(&vdhost::heap_slots[1]);   // GPU-facing buffers / host-only scratch
     mem.arena = vdhost::rt.arena; mem.cap = vdhost::rt.arena_cap;
     vdhost::Packed p;
-    vdhost::pack(clusterdata_ptr.get(), sc_groups, nt, mem, p);
+    vdhost::pack(clusterdata_ptr.get(), sc_groups, nt, mem, heap, p);
     const double ms_pack = ms_since(t0);
     if (const char *path = std::getenv("VD_DUMP_BATCH")) vdhost::dump_batch(p, max_qual, path);
 
@@ -510,7 +594,6 @@ void precision_recall_threads_wrapper(
     const double ms_status = ms_since(t0);
 
     t0 = clk::now();
-    vdhost::HostMem heap;                                           // never copied to or from the GPU: pageable
     vd_final fin{heap.take<uint8_t>(2 * n_var), heap.take<float>(2 * n_var), heap.take<float>(2 * n_var),
                  heap.take<int32_t>(2 * n_var), heap.take<int32_t>(2 * n_var), heap.take<int32_t>(2 * n_var),
                  heap.take<int32_t>(n_sc), heap.take<int32_t>(n_sc), heap.take<int32_t>(n_sc)};
@@ -521,14 +604,15 @@ void precision_recall_threads_wrapper(
     vdhost::scatter(p, in, fin, nt);
     const double ms_scatter = ms_since(t0);
     vdhost::last_times = {ms_wait, ms_pack, ms_run, (double)st.ms_total, ms_status, ms_fin, ms_scatter, (double)nt,
-                          mem.owned.empty() ? 1.0 : 0.0, (double)n_tie};
+                          mem.spilled ? 0.0 : 1.0, (double)n_tie};
     if (g.verbosity >= 1 && n_tie)
         INFO("  %lld of %lld superclusters had an ambiguous swap predecessor on an optimal path (equal-score tie): "
              "resolved canonically here, by hash-set order upstream", (long long)n_tie, (long long)n_sc);
     if (g.verbosity >= 2 || std::getenv("VD_DROPIN_TIMES"))
-        INFO("  GPU precision/recall: %lld superclusters, %lld variants, %lld cells, %lld launches; wait %.1f ms, pack %.1f ms, "
-             "vd_run%s %.1f ms (%.1f on device), status %.1f ms, finalize %.1f ms, scatter %.1f ms, %d host threads, %s buffers",
-             (long long)st.n_sc, (long long)n_var, (long long)st.cells, (long long)st.n_launches, ms_wait, ms_pack,
-             wide ? "" : "_packed", ms_run, st.ms_total, ms_status, ms_fin, ms_scatter, nt, mem.owned.empty() ? "page-locked" : "pageable");
+        INFO("  GPU precision/recall: %lld superclusters, %lld variants, %lld cells, %lld launches; wait %.1f ms (start-up: create %.0f, page-lock %.0f, warm-up %.0f), pack %.1f ms "
+             "[sizes %.1f, alloc %.1f, bytes %.1f], vd_run%s %.1f ms (%.1f on device), status %.1f ms, finalize %.1f ms, scatter %.1f ms, %d host threads, %s buffers",
+             (long long)st.n_sc, (long long)n_var, (long long)st.cells, (long long)st.n_launches, ms_wait,
+             vdhost::rt.init_ms[0], vdhost::rt.init_ms[1], vdhost::rt.init_ms[2], ms_pack, vdhost::pack_ms[0], vdhost::pack_ms[1], vdhost::pack_ms[2],
+             wide ? "" : "_packed", ms_run, st.ms_total, ms_status, ms_fin, ms_scatter, nt, mem.spilled ? "partly pageable" : "page-locked");
 #endif  // VD_DROPIN_WITH_REF
 }

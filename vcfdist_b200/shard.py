@@ -197,3 +197,78 @@ class ResultRecord:
         for k in ("sync_group", "ref_ed", "query_ed", "callq", "assigned"):
             out[k] = v[k][: 2 * n_var].view(2, n_var)
         return out
+
+
+class PackedRecord:
+    """The exchange record in 16-bit form (include/vcfdist_b200.h: vd_packed_out): what vd_pack_device writes behind a
+    rank's kernels and ONE all-gather moves - half the bytes of ResultRecord.  The batch-global indices of the shard's
+    superclusters and variants do not change from step to step and are exchanged once (`gather_index`), not with
+    every record.
+
+        [ n_sc, n_var (int64) | aln_score u16 | status u16 | sync_group u16 x2 (assigned << 14 | group) | ref_ed u16 x2 |
+          query_ed u16 x2 | callq f32 x2 | aln_planes u8 ]"""
+
+    FIELDS = (("aln_score", 2, "sc"), ("status", 2, "sc"), ("sync_group", 2, "var"), ("ref_ed", 2, "var"), ("query_ed", 2, "var"),
+              ("callq", 4, "var"), ("aln_planes", 1, "sc"))
+
+    def __init__(self, cap_sc: int, cap_var: int, device):
+        import torch
+        self.cap_sc, self.cap_var = cap_sc, cap_var
+        off, self.layout = 16, {}
+        for k, w, per in self.FIELDS:
+            n = 4 * cap_sc if per == "sc" else 2 * cap_var
+            self.layout[k] = (off, n, w); off = (off + w * n + 15) & ~15
+        self.nbytes = off
+        self.buf = torch.zeros(self.nbytes, dtype=torch.uint8, device=device)
+        self.views = self._views(self.buf)
+
+    def _views(self, buf):
+        import torch
+        v = {"counts": buf[:16].view(torch.int64)}
+        for k, (o, n, w) in self.layout.items():
+            t = buf[o: o + n * w]
+            v[k] = t.view(torch.float32) if k == "callq" else (t.view(torch.int16) if w == 2 else t)
+        return v
+
+    def set_counts(self, n_sc: int, n_var: int):
+        self.views["counts"][0] = n_sc
+        self.views["counts"][1] = n_var
+
+    def all_gather(self, dist, out=None):
+        import torch
+        world = dist.get_world_size()
+        if out is None:
+            out = torch.empty(world * self.nbytes, dtype=torch.uint8, device=self.buf.device)
+        dist.all_gather_into_tensor(out, self.buf)
+        return out.view(world, self.nbytes)
+
+    def parse(self, gathered, rank: int) -> dict:
+        """Rank `rank`'s arrays inside the gathered tensor, widened to the field meaning of vd_batch_out
+        (per-variant arrays as [2, n_var_of_rank])."""
+        import torch
+        v = self._views(gathered[rank])
+        n_sc, n_var = int(v["counts"][0]), int(v["counts"][1])
+        u16 = lambda t: t.to(torch.int32) & 0xFFFF
+        sc = u16(v["aln_score"][: 4 * n_sc])
+        sg = u16(v["sync_group"][: 2 * n_var]).view(2, n_var)
+        pl = v["aln_planes"][: 4 * n_sc]
+        return {"aln_score": torch.where(sc == 0xFFFF, torch.full_like(sc, -1), sc), "status": u16(v["status"][: 4 * n_sc]),
+                "aln_end_plane": pl & 1, "aln_beg_plane": (pl >> 1) & 1, "assigned": (sg >> 14).to(torch.uint8),
+                "sync_group": sg & 0x3FFF, "ref_ed": u16(v["ref_ed"][: 2 * n_var]).view(2, n_var),
+                "query_ed": u16(v["query_ed"][: 2 * n_var]).view(2, n_var), "callq": v["callq"][: 2 * n_var].view(2, n_var)}
+
+
+def gather_index(sc_idx: np.ndarray, var_idx: np.ndarray, cap_sc: int, cap_var: int, dist, device):
+    """One-off exchange of every rank's batch-global supercluster / variant indices -> ([world][n_sc_r], [world][n_var_r])
+    as int64 numpy arrays.  The partition is static, so this is not part of a step."""
+    import torch
+    world = dist.get_world_size()
+    mine = torch.full((2 + cap_sc + cap_var,), -1, dtype=torch.int64, device=device)
+    mine[0], mine[1] = len(sc_idx), len(var_idx)
+    mine[2: 2 + len(sc_idx)] = torch.from_numpy(np.asarray(sc_idx, np.int64)).to(device)
+    mine[2 + cap_sc: 2 + cap_sc + len(var_idx)] = torch.from_numpy(np.asarray(var_idx, np.int64)).to(device)
+    allv = torch.empty(world * mine.numel(), dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(allv, mine)
+    allv = allv.view(world, -1).cpu().numpy()
+    return ([allv[r, 2: 2 + allv[r, 0]] for r in range(world)],
+            [allv[r, 2 + cap_sc: 2 + cap_sc + allv[r, 1]] for r in range(world)])
