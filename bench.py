@@ -37,7 +37,7 @@ sys.path.insert(0, ROOT)
 from vcfdist_b200 import capi, shard
 from workloads import synth  # noqa: E402
 from oracle import checkers  # noqa: E402  (CPU-baseline legs only: the reference arm and cpu_baseline)
-from vcfdist_b200.batch import Batch, Out, PackedOut, vd_batch_in, vd_batch_out  # noqa: E402
+from vcfdist_b200.batch import Batch, Out, PackedOut, vd_batch_in, vd_batch_out, vd_packed_out  # noqa: E402
 
 WORKLOADS = {
     "wgs": dict(n_sc=3_600_000, sv_frac=0.0, config="HG002 WGS SNP+INDEL vs GIAB v4.2.1, 1xB200 (BASELINE configs[2])"),

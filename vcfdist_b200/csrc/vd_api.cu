@@ -45,11 +45,14 @@ struct DevBuf {
 // so that the plan pass of chunk i+1 runs while the kernels of chunk i are still executing.
 struct Work {
     DevBuf plan, list, order, ranks, ranks_out, iota, counters, cubtmp;
+    DevBuf wsc_slab, wsc_hdr;               // split warp path: one slot per supercluster of the wsc groups, and its header
     PlanCounters *h_counters = nullptr;     // pinned + mapped: written by publish_kernel, never by a copy engine
     cudaEvent_t ev[4] = {};                 // plan start, plan end, short kernels issued, chunk end
     cudaEvent_t ev5 = nullptr;              // fork point of the short-kernel launch groups
     cudaEvent_t evL = nullptr;              // everything issued on the main stream for this chunk
     cudaEvent_t gev[vd::N_GROUP][2] = {};   // start / end of each short-kernel launch group
+    cudaEvent_t wev[4] = {};                // split warp path: expansion start / end, walk start / end
+    bool wsc_used = false;
     bool grp_used[vd::N_GROUP] = {};
     bool busy = false;                      // launched, not yet harvested
     BatchDev in; OutDev out;
@@ -83,6 +86,7 @@ struct vd_handle {
     int use_hom = 1;                // VD_HOM=0: homozygous superclusters run all four alignments (testing)
     int use_band = 1;               // VD_BAND=0: no banded warp kernels, every long alignment goes to the dense block kernels (testing)
     int use_wsc = 1;                // VD_WSC=0: mid-size superclusters go to the HBM-slab path instead of the warp kernel
+    int wsc_split = 1;              // VD_WSC_SPLIT=0: the fused warp kernels instead of expansion / sweeps / walk as separate launches
     // staged input / output (vd_run)
     struct Stage {                  // one of the staging sets of the host-buffer pipeline
         DevBuf in_ref_off, in_ref_seq, in_rplane, in_var_off, in_var_pos, in_var_rlen, in_var_type,
@@ -142,6 +146,7 @@ extern "C" int vd_create(int device, int64_t scratch_bytes, vd_handle **out) {
         cok &= cudaEventCreate(&w.ev5) == cudaSuccess;
         cok &= cudaEventCreate(&w.evL) == cudaSuccess;
         for (auto &g : w.gev) for (auto &e : g) cok &= cudaEventCreate(&e) == cudaSuccess;
+        for (auto &e : w.wev) cok &= cudaEventCreate(&e) == cudaSuccess;
         cok &= cudaHostAlloc((void **)&w.h_counters, sizeof(PlanCounters), cudaHostAllocMapped) == cudaSuccess;
     }
     cok &= cudaStreamCreateWithFlags(&h->s_plan, cudaStreamNonBlocking) == cudaSuccess;
@@ -159,6 +164,7 @@ extern "C" int vd_create(int device, int64_t scratch_bytes, vd_handle **out) {
     if (const char *v = getenv("VD_SMALL_MAX")) h->small_hi = atoi(v);
     if (const char *v = getenv("VD_WSC")) h->use_wsc = atoi(v);
     if (const char *v = getenv("VD_BAND")) h->use_band = atoi(v);
+    if (const char *v = getenv("VD_WSC_SPLIT")) h->wsc_split = atoi(v);
     if (const char *v = getenv("VD_SERIAL")) h->serial = atoi(v);
     if (const char *v = getenv("VD_HOM")) h->use_hom = atoi(v);
     if (const char *v = getenv("VD_RAMP")) h->ramp = atoi(v);
@@ -176,6 +182,7 @@ extern "C" int vd_create(int device, int64_t scratch_bytes, vd_handle **out) {
     if (!cok) { vd_destroy(h); return VD_E_CUDA; }          // a stream, event or pinned block could not be created
     small_configure();
     wsc_configure();
+    wsc_split_configure();
     wave_configure();
     band_configure();
     *out = h;
@@ -201,13 +208,14 @@ extern "C" void vd_destroy(vd_handle *h) {
                       &h->band_lb, &h->dense_bytes, &h->dense_off, &h->dense, &h->wf_in, &h->wf_scratch};
     for (DevBuf *b : bufs) b->release();
     for (auto &w : h->work) {
-        DevBuf *wb[] = {&w.plan, &w.list, &w.order, &w.ranks, &w.ranks_out, &w.iota, &w.counters, &w.cubtmp};
+        DevBuf *wb[] = {&w.plan, &w.list, &w.order, &w.ranks, &w.ranks_out, &w.iota, &w.counters, &w.cubtmp, &w.wsc_slab, &w.wsc_hdr};
         for (DevBuf *b : wb) b->release();
         if (w.h_counters) cudaFreeHost(w.h_counters);
         for (auto &e : w.ev) if (e) cudaEventDestroy(e);
         if (w.ev5) cudaEventDestroy(w.ev5);
         if (w.evL) cudaEventDestroy(w.evL);
         for (auto &g : w.gev) for (auto &e : g) if (e) cudaEventDestroy(e);
+        for (auto &e : w.wev) if (e) cudaEventDestroy(e);
     }
     if (h->s_plan) cudaStreamDestroy(h->s_plan);
     if (h->s_epi) cudaStreamDestroy(h->s_epi);
@@ -298,6 +306,33 @@ static int chunk_exec(vd_handle *h, Work &W) {
     //      overlap with each other and with everything else), the thread-per-alignment classes on the
     //      main stream ----
     int n_small = 0;
+    // split warp path: slab slots (one per supercluster of a wsc group, of the group's bin size) and headers; the
+    // expansion of all groups is one launch, ahead of everything else on the main stream
+    int64_t slab_off[N_GROUP] = {}, hdr_off[N_GROUP] = {};
+    WscGroups WG{};
+    W.wsc_used = false;
+    if (h->wsc_split) {
+        int64_t so = 0, ho = 0;
+        for (int g = 2 * N_SMALL; g < N_GROUP; g++) {
+            const int w = (g >> 1) - N_SMALL, cap = wsc_bin_cap(N_WBIN - 1 - w % N_WBIN);
+            slab_off[g] = so; hdr_off[g] = ho;
+            if (pc.grp_count[g] > 0) {
+                const int k = WG.n++;
+                WG.first[k] = (int)ho; WG.order_first[k] = pc.grp_first[g]; WG.stride[k] = cap; WG.hom[k] = g & 1; WG.base[k] = so;
+            }
+            so += (int64_t)pc.grp_count[g] * cap;
+            ho += pc.grp_count[g];
+        }
+        WG.first[WG.n] = (int)ho;
+        if (ho > 0) {
+            CK(W.wsc_slab.ensure((size_t)so + 256)); CK(W.wsc_hdr.ensure(sizeof(WscHdr) * (size_t)ho + 16));
+            W.wsc_used = true;
+            CK(cudaEventRecord(W.wev[0], st));
+            wsc_expand_launch(st, in, plan, order, WG, (u8 *)W.wsc_slab.p, (WscHdr *)W.wsc_hdr.p);
+            CK(cudaEventRecord(W.wev[1], st));
+            S.n_launches++;
+        }
+    }
     CK(cudaEventRecord(W.ev5, st));
     for (int g = N_GROUP - 1; g >= 0; g--) {
         const int cnt = pc.grp_count[g];
@@ -310,7 +345,12 @@ static int chunk_exec(vd_handle *h, Work &W) {
         if (g0 < N_SMALL) small_launch(gs, g0, hom, in, out, plan, order + pc.grp_first[g], cnt);
         else {
             const int w = g0 - N_SMALL;                      // (slots - 1) * N_WBIN + (N_WBIN - 1 - bin)
-            wsc_launch(gs, w / N_WBIN + 1, N_WBIN - 1 - w % N_WBIN, hom, in, out, plan, order + pc.grp_first[g], cnt);
+            if (h->wsc_split) {
+                wsc_split_launch(gs, w / N_WBIN + 1, N_WBIN - 1 - w % N_WBIN, hom, in, out, plan, order + pc.grp_first[g], cnt,
+                                 (u8 *)W.wsc_slab.p + slab_off[g], (WscHdr *)W.wsc_hdr.p + hdr_off[g]);
+            } else {
+                wsc_launch(gs, w / N_WBIN + 1, N_WBIN - 1 - w % N_WBIN, hom, in, out, plan, order + pc.grp_first[g], cnt);
+            }
         }
         CK(cudaEventRecord(W.gev[g][1], gs));
         W.grp_used[g] = true;
@@ -517,6 +557,12 @@ static int chunk_exec(vd_handle *h, Work &W) {
         CK(cudaStreamWaitEvent(se, W.evL, 0));
         for (int g = 2 * N_SMALL; g < N_GROUP; g++) if (W.grp_used[g]) CK(cudaStreamWaitEvent(se, W.gev[g][1], 0));
     }
+    if (W.wsc_used) {                          // walk + credit of all warp-path groups, behind their sweeps
+        CK(cudaEventRecord(W.wev[2], se));
+        wsc_walk_launch(se, in, out, plan, order, WG, (u8 *)W.wsc_slab.p, (const WscHdr *)W.wsc_hdr.p);
+        CK(cudaEventRecord(W.wev[3], se));
+        S.n_launches++;
+    }
     VD_LAUNCH(status_or_kernel, 296, 256, 0, se, out.status, 4 * (int64_t)n_sc, &((PlanCounters *)W.counters.p)->status_or);
     S.n_launches++;
     VD_LAUNCH(publish_kernel, 1, 64, 0, se, (const u32 *)W.counters.p, (u32 *)W.h_counters, (int)(sizeof(PlanCounters) / 4));
@@ -541,6 +587,11 @@ static int chunk_harvest(vd_handle *h, Work &W) {
         if (!W.grp_used[g]) continue;
         cudaEventElapsedTime(&e_, W.gev[g][0], W.gev[g][1]);
         S.ms_small[(g >> 1) < N_SMALL ? (g >> 1) : N_SMALL] += e_;
+    }
+    if (W.wsc_used) {
+        cudaEventElapsedTime(&e_, W.wev[0], W.wev[1]); S.ms_small[N_SMALL] += e_;
+        cudaEventElapsedTime(&e_, W.wev[2], W.wev[3]); S.ms_small[N_SMALL] += e_;
+        W.wsc_used = false;
     }
     if (W.n_bad > 0) return fail(h, VD_E_BADINPUT, "%d malformed superclusters", W.n_bad);
     return VD_OK;
@@ -597,6 +648,14 @@ extern "C" int vd_pack_device(vd_handle *h, const vd_batch_out *wide, int64_t n_
     CK(cudaGetLastError());
     return VD_OK;
 }
+#ifdef VD_PHASE_PROF
+extern "C" void vd_debug_phases(unsigned long long *out48, int reset) {       // out48: 56 words
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out48, vd::g_wsc_phase, sizeof(unsigned long long) * 48);
+    cudaMemcpyFromSymbol(out48 + 48, vd::g_walk_phase, sizeof(unsigned long long) * 8);
+    if (reset) { unsigned long long z[48] = {}; cudaMemcpyToSymbol(vd::g_wsc_phase, z, sizeof(z)); cudaMemcpyToSymbol(vd::g_walk_phase, z, 64); }
+}
+#endif
 extern "C" int vd_packed_overflow(const vd_handle *h) { return h && h->h_range ? (int)*h->h_range : 0; }
 
 // error path of vd_run: nothing of this call may still be in flight when the caller gets its buffers back, and

@@ -38,6 +38,16 @@ struct SMemIL {                    // shared memory: one contiguous slice per th
     __device__ __forceinline__ void st16(int o, int v) const { *(short *)(base + o) = (short)v; }
 };
 
+struct GMemIL {                    // the same byte/halfword interface over a region of HBM (path scratch of wsc_walk_kernel)
+    typedef int off_t;
+    u8 *base;
+    __device__ __forceinline__ u8 *at(int o) const { return base + o; }
+    __device__ __forceinline__ int ld8(int o) const { return base[o]; }
+    __device__ __forceinline__ void st8(int o, int v) const { base[o] = (u8)v; }
+    __device__ __forceinline__ int ld16(int o) const { return *(const short *)(base + o); }
+    __device__ __forceinline__ void st16(int o, int v) const { *(short *)(base + o) = (short)v; }
+};
+
 // value accessors: W = element width of the D / T / path / lev arrays (4 in HBM, 2 in smem)
 template <class Mem, int W> struct Val;
 template <> struct Val<GMem, 4> {
@@ -47,6 +57,10 @@ template <> struct Val<GMem, 4> {
 template <> struct Val<SMemIL, 2> {
     static __device__ __forceinline__ int ld(const SMemIL &m, int base, int i) { return m.ld16(base + 2 * i); }
     static __device__ __forceinline__ void st(const SMemIL &m, int base, int i, int v) { m.st16(base + 2 * i, v); }
+};
+template <> struct Val<GMemIL, 2> {
+    static __device__ __forceinline__ int ld(const GMemIL &m, int base, int i) { return m.ld16(base + 2 * i); }
+    static __device__ __forceinline__ void st(const GMemIL &m, int base, int i, int v) { m.st16(base + 2 * i, v); }
 };
 
 // expanded haplotype (generate_ptrs_strs output), PT = pointer element type
@@ -99,28 +113,64 @@ __host__ __device__ inline AlnLayout<OffT> make_layout(int N, int Lt, int Lr) {
 // generate_ptrs_strs, :145-242.  Writes str/flg/ptr (hap side) and, when rptr != nullptr,
 // the ref side.  Returns the hap length, or -1 on input the reference cannot process.
 // ---------------------------------------------------------------------------------------
-template <class PT>
-__device__ int expand_hap(const BatchDev &in, int sc, int h, u8 *str, u8 *flg, PT *ptr,
-                          PT *rptr, u8 *rflg, u8 *ins, int cap) {
-    const int64_t r0 = in.ref_off[sc];
-    const int win = (int)(in.ref_off[sc + 1] - r0);
-    const u8 *fa = in.ref_seq + r0;
-    int64_t v = in.var_off[4 * (int64_t)sc + h];
-    const int64_t ve = in.var_off[4 * (int64_t)sc + h + 1];
+// Where the expansion reads a supercluster's compact input from: straight from the batch in HBM, or from a copy the
+// warp staged in shared memory with coalesced loads (wsc_block_kernel) - the expansion is one lane following offsets,
+// i.e. a chain of dependent loads, and each link costs an HBM/L2 round trip or a shared-memory one.
+struct HapSrcGlobal {
+    const BatchDev &in; int sc, h;
+    int64_t r0, v0, ve;
+    __device__ HapSrcGlobal(const BatchDev &in_, int sc_, int h_) : in(in_), sc(sc_), h(h_) {
+        r0 = in.ref_off[sc];
+        v0 = in.var_off[4 * (int64_t)sc + h];
+        ve = in.var_off[4 * (int64_t)sc + h + 1];
+    }
+    __device__ int win() const { return (int)(in.ref_off[sc + 1] - r0); }
+    __device__ int nvar() const { return (int)(ve - v0); }
+    __device__ int fa(int k) const { return in.ref_seq[r0 + k]; }
+    __device__ int pos(int v) const { return in.var_pos[v0 + v]; }
+    __device__ int rlen(int v) const { return in.var_rlen[v0 + v]; }
+    __device__ int type(int v) const { return in.var_type[v0 + v]; }
+    __device__ const u8 *alt(int v, int &alen) const {
+        const int64_t a0 = in.alt_off[v0 + v];
+        alen = (int)(in.alt_off[v0 + v + 1] - a0);
+        return in.alt_seq + a0;
+    }
+};
+struct HapSrcStaged {        // variant v of the haplotype is entry vb + v of the supercluster's staged arrays
+    const u8 *fa_; int win_; int vb, n;
+    const int *pos_, *rlen_, *aoff_;        // aoff_: low words of alt_off, nv + 1 of them
+    const u8 *type_, *alt_;                 // alt_: ALT bytes from the supercluster's first variant on
+    __device__ int win() const { return win_; }
+    __device__ int nvar() const { return n; }
+    __device__ int fa(int k) const { return fa_[k]; }
+    __device__ int pos(int v) const { return pos_[vb + v]; }
+    __device__ int rlen(int v) const { return rlen_[vb + v]; }
+    __device__ int type(int v) const { return type_[vb + v]; }
+    __device__ const u8 *alt(int v, int &alen) const {
+        alen = aoff_[vb + v + 1] - aoff_[vb + v];
+        return alt_ + (aoff_[vb + v] - aoff_[0]);
+    }
+};
+
+template <class PT, class SRC>
+__device__ int expand_hap_src(const SRC &src, u8 *str, u8 *flg, PT *ptr, PT *rptr, u8 *rflg, u8 *ins, int cap) {
+    const int win = src.win();
+    int v = 0;
+    const int ve = src.nvar();
     int Q = 0, R = 0, ref_pos = 0;
     if (ins) for (int k = 0; k < win; k++) ins[k] = 0;
     while (ref_pos < win) {                                      // :163
-        if (v < ve && ref_pos == in.var_pos[v]) {                // :165-166
-            const int64_t a0 = in.alt_off[v];
-            const int alen = (int)(in.alt_off[v + 1] - a0);
-            const int rl = in.var_rlen[v];
-            const int ty = in.var_type[v];
+        if (v < ve && ref_pos == src.pos(v)) {                   // :165-166
+            int alen;
+            const u8 *alt = src.alt(v, alen);
+            const int rl = src.rlen(v);
+            const int ty = src.type(v);
             if (ty == VD_TYPE_INS) {                             // :169-178
                 if (alen < 1 || Q + alen > cap) return -1;
                 for (int k = 0; k < alen; k++) {
                     ptr[Q + k] = (PT)(R - 1);
                     flg[Q + k] = P_VARIANT;
-                    str[Q + k] = in.alt_seq[a0 + k];
+                    str[Q + k] = alt[k];
                 }
                 flg[Q + alen - 1] |= P_VAR_END;
                 flg[Q] |= P_VAR_BEG | P_INS_LOC;
@@ -138,25 +188,31 @@ __device__ int expand_hap(const BatchDev &in, int sc, int h, u8 *str, u8 *flg, P
                 if (alen != 1 || rl != 1 || Q + 1 > cap) return -1;
                 if (rptr) { rptr[R] = (PT)Q; rflg[R] = P_VARIANT | P_VAR_BEG | P_VAR_END; }
                 ptr[Q] = (PT)R; flg[Q] = P_VARIANT | P_VAR_BEG | P_VAR_END;
-                str[Q] = in.alt_seq[a0];
+                str[Q] = alt[0];
                 R++; Q++; ref_pos++;
             } else {
                 return -1;                                       // :199-201
             }
             v++;                                                 // :204
         } else {                                                 // :206-235
-            const int ref_end = (v < ve) ? in.var_pos[v] : win;
+            const int ref_end = (v < ve) ? src.pos(v) : win;
             if (ref_end < ref_pos || ref_end > win || Q + (ref_end - ref_pos) > cap) return -1;
             const int n = ref_end - ref_pos;
             for (int k = 0; k < n; k++) {
                 ptr[Q + k] = (PT)(R + k); flg[Q + k] = 0;
                 if (rptr) { rptr[R + k] = (PT)(Q + k); rflg[R + k] = 0; }
-                str[Q + k] = fa[ref_pos + k];
+                str[Q + k] = (u8)src.fa(ref_pos + k);
             }
             Q += n; R += n; ref_pos = ref_end;
         }
     }
     return Q;
+}
+
+template <class PT>
+__device__ int expand_hap(const BatchDev &in, int sc, int h, u8 *str, u8 *flg, PT *ptr,
+                          PT *rptr, u8 *rflg, u8 *ins, int cap) {
+    return expand_hap_src<PT>(HapSrcGlobal(in, sc, h), str, flg, ptr, rptr, rflg, ins, cap);
 }
 
 // swap-source table of one destination plane, CSR: tab[0..ndst] = offsets, then the source
@@ -384,6 +440,11 @@ template <class Mem> struct PFScalar {          // [column][row], rows = Lq + Lr
 // ---------------------------------------------------------------------------------------
 // walk (get_prec_recall_path_sync :842-999) + integer credit (calc_prec_recall :1005-1401).
 // ---------------------------------------------------------------------------------------
+#ifdef VD_PHASE_PROF
+template <class A, class B> struct vd_same { static constexpr int v = 0; };
+template <class A> struct vd_same<A, A> { static constexpr int v = 1; };
+__device__ unsigned long long g_walk_phase[8];      // walk loop, credit loop, walk steps, sync sections (thread 0 of a block only)
+#endif
 template <class Mem, int W, class PT, class PFR>
 __device__ void walk_credit(const Mem &mem, const AlnLayout<typename Mem::off_t> &L, const PFR &pfr,
                             const Hap<PT> &q, const QMaps<PT> &qm, const Hap<PT> &t,
@@ -392,6 +453,11 @@ __device__ void walk_credit(const Mem &mem, const AlnLayout<typename Mem::off_t>
     typedef Val<Mem, W> V;
     constexpr int HB = (W == 2) ? 14 : 30;      // bit holding the plane in a packed path entry
     const int Lq = q.len, Lt = t.len;
+#ifdef VD_PHASE_PROF
+    long long ph_w0 = clock64();
+    int ph_nsync = 0;
+    constexpr int ph_o = vd_same<PFR, PFScalar<Mem>>::v ? 0 : 4;     // thread-per-alignment kernels / everything else
+#endif
     const int maxpath = Lq + Lr + Lt + 3;
     int np = 0, ns = 0;
     int last_edit = 0;          // edits[] entry of the move that hit the :941 break, if any
@@ -400,19 +466,27 @@ __device__ void walk_credit(const Mem &mem, const AlnLayout<typename Mem::off_t>
         V::st(mem, L.oPQ, 0, qri | (hi << HB)); V::st(mem, L.oPT, 0, ti);
         mem.st8(L.oPS, 1);                                                                    // :897-899
         np = 1; ns = 1;
-        while ((hi == 1 && qri < Lr - 1) || (hi == 0 && qri < Lq - 1) || ti < Lt - 1) {        // :905
+        // The move is picked with selects and the loop is left through `go` only: the lanes of a warp walk different
+        // alignments, and a chain of branches with early exits would keep them apart for the rest of each iteration.
+        bool go = true, err = false;
+        while (go && ((hi == 1 && qri < Lr - 1) || (hi == 0 && qri < Lq - 1) || ti < Lt - 1)) {  // :905
             const int pf = pfr.get(hi, qri, ti);
-            int ty, ed;
-            if (hi == 1 && (pf & PTR_SWP)) { ty = PTR_SWP; hi = 0; qri = (int)qm.rptr[qri] + 1; ti++; ed = 0; }  // :907-912
-            else if (pf & PTR_MAT) { ty = PTR_MAT; qri++; ti++; ed = 0; }                       // :914-916
-            else if (pf & PTR_SUB) { ty = PTR_SUB; qri++; ti++; ed = 1; }                       // :918-920
-            else if (pf & PTR_INS) { ty = PTR_INS; qri++; ed = 1; }                             // :922-924
-            else if (pf & PTR_DEL) { ty = PTR_DEL; ti++; ed = 1; }                              // :926-928
-            else if (hi == 0 && (pf & PTR_SWP)) { ty = PTR_SWP; hi = 1; qri = (int)q.ptr[qri] + 1; ti++; ed = 0; }  // :930-934
-            else { status |= VD_ST_ERR_NO_POINTER; return; }                                    // :936-939
-            if ((hi == 0 && qri >= Lq) || (hi == 1 && qri >= Lr) || ti >= Lt) { last_edit = ed; ns++; break; }  // :941
+            const bool sw_r = hi == 1 && (pf & PTR_SWP);                                        // :907-912
+            const int ty = sw_r ? PTR_SWP : (pf & PTR_MAT) ? PTR_MAT : (pf & PTR_SUB) ? PTR_SUB      // :914-920
+                         : (pf & PTR_INS) ? PTR_INS : (pf & PTR_DEL) ? PTR_DEL                  // :922-928
+                         : (hi == 0 && (pf & PTR_SWP)) ? PTR_SWP : 0;                           // :930-934, else :936-939
+            const bool sw_q = !sw_r && ty == PTR_SWP;
+            const int ed = (ty & (PTR_SUB | PTR_INS | PTR_DEL)) ? 1 : 0;
+            int jump = 0;
+            if (sw_r) jump = (int)qm.rptr[qri] + 1;
+            if (sw_q) jump = (int)q.ptr[qri] + 1;
+            qri = (ty == PTR_SWP) ? jump : qri + ((ty & (PTR_MAT | PTR_SUB | PTR_INS)) ? 1 : 0);
+            ti += (ty & (PTR_MAT | PTR_SUB | PTR_DEL | PTR_SWP)) ? 1 : 0;
+            hi = sw_r ? 0 : (sw_q ? 1 : hi);
+            const bool past = (hi == 0 && qri >= Lq) || (hi == 1 && qri >= Lr) || ti >= Lt;       // :941
+            if (!ty || (!past && np >= maxpath)) { err = true; go = false; continue; }
+            if (past) { last_edit = ed; ns++; go = false; continue; }
             pfr.prefetch(hi, qri, ti);                  // flag bytes a few steps ahead (HBM-resident matrices only)
-            if (np >= maxpath) { status |= VD_ST_ERR_NO_POINTER; return; }
             const int tf = t.flg[ti];
             bool in_truth_var = tf & P_VARIANT;                                                 // :949-951
             if (ty & (PTR_MAT | PTR_SWP | PTR_SUB | PTR_DEL)) in_truth_var = in_truth_var && !(tf & P_VAR_BEG);
@@ -433,10 +507,14 @@ __device__ void walk_credit(const Mem &mem, const AlnLayout<typename Mem::off_t>
             mem.st8(L.oPS + np, (is_sync ? 1 : 0) | (ed ? 2 : 0));
             np++; ns++;
         }
+        if (err) { status |= VD_ST_ERR_NO_POINTER; return; }
     }
     // sync[] has np+1 entries (the last forced true, :995), edits[] index k <= np:
     //   k < np  -> bit 1 of path flag k;  k == np -> the :941 break move's edit, else false
     const bool broke = (ns == np + 1);
+#ifdef VD_PHASE_PROF
+    if (threadIdx.x == 0) { const long long n_ = clock64(); atomicAdd(&g_walk_phase[ph_o + 0], (unsigned long long)(n_ - ph_w0)); ph_w0 = n_; atomicAdd(&g_walk_phase[ph_o + 2], (unsigned long long)np); }
+#endif
 
     const int swap = (ai == 1 || ai == 2);                                                     // :1037
     const int qh = ai >> 1, th = 2 + (ai & 1);
@@ -459,31 +537,65 @@ __device__ void walk_credit(const Mem &mem, const AlnLayout<typename Mem::off_t>
     int t_pos = (tvp >= tb) ? in.var_pos[tvp] : 0;
     int sync_idx = np;                                                                         // :1082
 
-    while (sync_idx >= 0) {                                                                    // :1136
-        const int query_ref_pos = (prev_hi == 1) ? prev_qri : (int)q.ptr[prev_qri];            // :1139-1144
-        while (query_ref_pos < q_pos && qvp >= qb) {                                           // :1147
-            if (hi == 1) {                                                                     // :1157-1168
-                asg[qvp] = VD_ASSIGN_REF_FP;
-                sg[qvp] = sync_group++;
-                red[qvp] = 0; qed[qvp] = 0;
-                cq[qvp] = in.var_qual[qvp];
+    // The reference's loop (:1136-1399) visits every path entry from the end; at a sync point it closes the section since
+    // the previous one (:1190-1380).  Most sections are a run of matched bases between variants: nothing is assigned and
+    // the section's edit distance is 0.  Those are closed inline; a section that needs the full treatment (variants to
+    // credit, or strings that differ) stops the inner loop instead, so that the lanes of a warp - each on its own
+    // alignment - reach the expensive part together rather than one after the other at their own path positions.
+    bool more = true;
+    while (more) {
+        int sync_ref_idx = 0, sync_truth_idx = 0, rn = 0, tn = 0;
+        bool full = false;
+        while (sync_idx >= 0) {                                                                // :1136
+            const int query_ref_pos = (prev_hi == 1) ? prev_qri : (int)q.ptr[prev_qri];        // :1139-1144
+            while (query_ref_pos < q_pos && qvp >= qb) {                                       // :1147
+                if (hi == 1) {                                                                 // :1157-1168
+                    asg[qvp] = VD_ASSIGN_REF_FP;
+                    sg[qvp] = sync_group++;
+                    red[qvp] = 0; qed[qvp] = 0;
+                    cq[qvp] = in.var_qual[qvp];
+                }
+                qvp--;
+                q_pos = (qvp < qb) ? -1 : in.var_pos[qvp];                                     // :1175-1176
             }
-            qvp--;
-            q_pos = (qvp < qb) ? -1 : in.var_pos[qvp];                                         // :1175-1176
+            const int truth_ref_pos = (int)t.ptr[prev_ti];                                     // :1180
+            while (truth_ref_pos < t_pos && tvp >= tb) {                                       // :1181-1187
+                tvp--;
+                t_pos = (tvp < tb) ? -1 : in.var_pos[tvp];
+            }
+            const bool is_sync = (sync_idx == np) ? true : (mem.ld8(L.oPS + sync_idx) & 1);
+            if (is_sync) {                                                                     // :1190
+                sync_ref_idx = query_ref_pos + 1;                                              // :1194
+                sync_truth_idx = prev_ti + 1;                                                  // :1195
+                rn = prev_sync_ref_idx - sync_ref_idx;                                         // substr clipping
+                if (rn < 0 || sync_ref_idx + rn > Lr) rn = Lr - sync_ref_idx;
+                tn = prev_sync_truth_idx - sync_truth_idx;
+                if (tn < 0 || sync_truth_idx + tn > Lt) tn = Lt - sync_truth_idx;
+                bool plain = prev_qvp == qvp && prev_tvp == tvp && rn == tn && rn <= 8;        // no variant passed, equal lengths
+                for (int k = 0; k < rn && plain; k++) plain = rseq[sync_ref_idx + k] == t.str[sync_truth_idx + k];
+                if (!plain) { full = true; break; }
+                // ref_ed = 0 here (:1197-1199 on identical strings), so of :1203-1380 only these remain
+                if (query_ed != 0) status |= VD_ST_WARN_QED_NOQUERY | VD_ST_WARN_QED_GT_REFED;  // :1207, :1211
+                prev_sync_ref_idx = sync_ref_idx;
+                prev_sync_truth_idx = sync_truth_idx;
+                query_ed = 0;
+            }
+            if (sync_idx == np) query_ed += broke ? last_edit : 0;                             // :1382
+            else query_ed += (mem.ld8(L.oPS + sync_idx) >> 1) & 1;
+            sync_idx--;
+            if (sync_idx < 0) break;
+            hi = prev_hi;                                                                      // :1387-1392
+            const int pq = V::ld(mem, L.oPQ, sync_idx);
+            prev_qri = pq & ((1 << HB) - 1); prev_hi = (pq >> HB) & 1;
+            prev_ti = V::ld(mem, L.oPT, sync_idx);
+            // :1395-1398 reload q_pos / t_pos here; they already hold var_pos[qvp] / var_pos[tvp] (set where qvp and tvp
+            // move), and are not looked at once qvp < qb / tvp < tb: no load from HBM on the per-entry path
         }
-        const int truth_ref_pos = (int)t.ptr[prev_ti];                                         // :1180
-        while (truth_ref_pos < t_pos && tvp >= tb) {                                           // :1181-1187
-            tvp--;
-            t_pos = (tvp < tb) ? -1 : in.var_pos[tvp];
-        }
-        const bool is_sync = (sync_idx == np) ? true : (mem.ld8(L.oPS + sync_idx) & 1);
-        if (is_sync) {                                                                         // :1190
-            const int sync_ref_idx = query_ref_pos + 1;                                        // :1194
-            const int sync_truth_idx = prev_ti + 1;                                            // :1195
-            int rn = prev_sync_ref_idx - sync_ref_idx;                                         // substr clipping
-            if (rn < 0 || sync_ref_idx + rn > Lr) rn = Lr - sync_ref_idx;
-            int tn = prev_sync_truth_idx - sync_truth_idx;
-            if (tn < 0 || sync_truth_idx + tn > Lt) tn = Lt - sync_truth_idx;
+        more = full;
+        if (full) {
+#ifdef VD_PHASE_PROF
+            ph_nsync++;
+#endif
             int ref_ed = lev_scalar<Mem, W>(mem, L.oLev, rseq + sync_ref_idx, rn,               // :1197-1199
                                             t.str + sync_truth_idx, tn);
             if (prev_tvp == tvp && ref_ed != 0) status |= VD_ST_WARN_REFED_NOTRUTH;            // :1203
@@ -507,18 +619,22 @@ __device__ void walk_credit(const Mem &mem, const AlnLayout<typename Mem::off_t>
             prev_sync_ref_idx = sync_ref_idx;
             prev_sync_truth_idx = sync_truth_idx;
             query_ed = 0;
+            // the rest of this path entry (:1382-1398), then on with the next one
+            if (sync_idx == np) query_ed += broke ? last_edit : 0;                             // :1382
+            else query_ed += (mem.ld8(L.oPS + sync_idx) >> 1) & 1;
+            sync_idx--;
+            if (sync_idx < 0) more = false;
+            else {
+                hi = prev_hi;                                                                  // :1387-1392
+                const int pq = V::ld(mem, L.oPQ, sync_idx);
+                prev_qri = pq & ((1 << HB) - 1); prev_hi = (pq >> HB) & 1;
+                prev_ti = V::ld(mem, L.oPT, sync_idx);
+            }
         }
-        if (sync_idx == np) query_ed += broke ? last_edit : 0;                                 // :1382
-        else query_ed += (mem.ld8(L.oPS + sync_idx) >> 1) & 1;
-        sync_idx--;
-        if (sync_idx < 0) break;
-        hi = prev_hi;                                                                          // :1387-1392
-        const int pq = V::ld(mem, L.oPQ, sync_idx);
-        prev_qri = pq & ((1 << HB) - 1); prev_hi = (pq >> HB) & 1;
-        prev_ti = V::ld(mem, L.oPT, sync_idx);
-        q_pos = (qvp < qb) ? -1 : in.var_pos[qvp];                                             // :1395-1398
-        t_pos = (tvp < tb) ? -1 : in.var_pos[tvp];
     }
+#ifdef VD_PHASE_PROF
+    if (threadIdx.x == 0) { atomicAdd(&g_walk_phase[ph_o + 1], (unsigned long long)(clock64() - ph_w0)); atomicAdd(&g_walk_phase[ph_o + 3], (unsigned long long)ph_nsync); }
+#endif
 }
 
 // ---------------------------------------------------------------------------------------

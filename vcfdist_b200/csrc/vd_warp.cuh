@@ -501,12 +501,38 @@ wsc_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, const int *
 // warp 0, one lane per haplotype / alignment: 16 busy lanes in one warp instead of 4 busy lanes in
 // each of four warps, i.e. a quarter of the issue slots for the part that cannot use more lanes.
 // ------------------------------------------------------------------------------------------
+#ifndef VD_WSC_P3_PER_WARP
+#define VD_WSC_P3_PER_WARP 0
+#endif
+#ifdef VD_PHASE_PROF
+// build-time profiling hook (never in the product build): cycles of the block's phases, summed per kernel flavour
+__device__ unsigned long long g_wsc_phase[8][6];
+#define VD_PH_DECL long long ph_t = clock64(); const int ph_k = (S - 1) * 2 + (HOM ? 1 : 0)
+#define VD_PH_MARK(i) do { if (threadIdx.x == 0) { const long long n_ = clock64(); atomicAdd(&g_wsc_phase[ph_k][i], (unsigned long long)(n_ - ph_t)); ph_t = n_; } } while (0)
+#else
+#define VD_PH_DECL
+#define VD_PH_MARK(i)
+#endif
+
 struct WscDesc {
     ScPlan p; WscLayout M;
     int sc;            // -1: no supercluster for this warp (tail of the launch)
     int ok;            // expansion succeeded
     unsigned trivial;  // alignments without variants on either side
+    int staged;        // the variant records and ALT bytes were staged in shared memory (else: read from the batch)
+    int vb[5];         // first staged variant of each haplotype (and the end)
     int res[4][4];     // per alignment: score, end plane, origin plane, status
+};
+
+// staged copy of a supercluster's variant records, in the (not yet used) flag-matrix area: pos | rlen | alt_off low words
+// (nv + 1) | type | ALT bytes
+struct WscStage {
+    int *pos, *rlen, *aoff; u8 *type, *alt;
+    __device__ WscStage(u8 *base, const WscLayout &M, int nv) {
+        pos = (int *)(base + ((M.F[0] + 3) & ~3)); rlen = pos + nv; aoff = rlen + nv;
+        type = (u8 *)(aoff + nv + 1); alt = type + nv;
+    }
+    static __device__ int bytes(int nv, int alt_bytes) { return 13 * nv + 8 + alt_bytes; }
 };
 
 template <int S, bool HOM, int NW>
@@ -514,26 +540,64 @@ __global__ void __launch_bounds__(32 * NW, wsc_minb(S))
 wsc_block_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, const int *__restrict__ order, int count, int warp_bytes) {
     VD_DYN_SHARED(smem);
     __shared__ WscDesc desc[NW];
+    VD_PH_DECL;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int slot = blockIdx.x * (NW) + warp;
     const bool live = slot < count;
+    constexpr unsigned FULLM = 0xffffffffu;
+    // ---- phase 0: every warp describes its own supercluster and stages its input: the variant records, the ALT bytes
+    //      and the window, read with all lanes at once (four rounds of loads instead of one per field and variant) ----
     if (lane == 0) {
         WscDesc &d = desc[warp];
         d.sc = live ? order[slot] : -1;
         d.ok = 1;
         d.trivial = 0;
+        d.staged = 0;
         if (live) {
             d.p = plan[d.sc];
             d.M = wsc_layout(d.p, HOM);
-            if (in.rplane_seq == in.ref_seq) {       // see wsc_kernel
-                const int64_t *vo = in.var_off + 4 * (int64_t)d.sc;
-                const int64_t o0 = vo[0], o1 = vo[1], o2 = vo[2], o3 = vo[3], o4 = vo[4];
-                const bool eq0 = o1 == o0, eq1 = o2 == o1, et0 = o3 == o2, et1 = o4 == o3;
-                d.trivial = (eq0 && et0 ? 1u : 0u) | (eq0 && et1 ? 2u : 0u) | (eq1 && et0 ? 4u : 0u) | (eq1 && et1 ? 8u : 0u);
-            }
         }
     }
+    __syncwarp();
+    if (live) {
+        WscDesc &d = desc[warp];
+        const int sc = d.sc;
+        u8 *base = smem + warp * warp_bytes;
+        const int64_t myvo = lane < 5 ? in.var_off[4 * (int64_t)sc + lane] : 0;
+        const int64_t r0 = in.ref_off[sc];
+        const int64_t v0 = __shfl_sync(FULLM, myvo, 0);
+        const int nv = (int)(__shfl_sync(FULLM, myvo, 4) - v0);
+        if (lane < 5) d.vb[lane] = (int)(myvo - v0);
+        const int64_t nxvo = __shfl_down_sync(FULLM, myvo, 1);
+        const unsigned e = __ballot_sync(FULLM, lane < 4 && nxvo == myvo);       // bit h: haplotype h carries no variant
+        if (lane == 0 && in.rplane_seq == in.ref_seq)                            // see wsc_kernel
+            d.trivial = ((e & 5u) == 5u ? 1u : 0u) | ((e & 9u) == 9u ? 2u : 0u) | ((e & 6u) == 6u ? 4u : 0u) | ((e & 10u) == 10u ? 8u : 0u);
+        const int room = warp_bytes - ((d.M.F[0] + 3) & ~3);
+        bool staged = in.rplane_seq == in.ref_seq && WscStage::bytes(nv, 0) <= room;
+        WscStage st(base, d.M, nv);
+        int64_t a0 = 0;
+        if (staged) {
+            for (int v = lane; v <= nv; v += 32) {
+                const int64_t ao = in.alt_off[v0 + v];
+                if (v == 0) a0 = ao;
+                st.aoff[v] = (int)ao;
+                if (v < nv) { st.pos[v] = in.var_pos[v0 + v]; st.rlen[v] = in.var_rlen[v0 + v]; st.type[v] = in.var_type[v0 + v]; }
+            }
+        }
+        const u8 *rs = in.rplane_seq + r0;
+        u8 *rseq = base + d.M.rseq;
+        for (int k = lane; k < d.p.lr; k += 32) rseq[k] = rs[k];
+        __syncwarp();
+        if (staged) {
+            a0 = __shfl_sync(FULLM, a0, 0);
+            const int ab = st.aoff[nv] - st.aoff[0];
+            staged = ab >= 0 && WscStage::bytes(nv, ab) <= room;
+            if (staged) for (int k = lane; k < ab; k += 32) st.alt[k] = in.alt_seq[a0 + k];
+        }
+        if (lane == 0) d.staged = staged ? 1 : 0;
+    }
     __syncthreads();
+    VD_PH_MARK(0);
     // shared-memory views of supercluster w
     auto hbase = [&](int w, int h) { return smem + w * warp_bytes + desc[w].M.hap[h]; };
     auto qbase = [&](int w, int k) { return smem + w * warp_bytes + desc[w].M.qm[k]; };
@@ -549,7 +613,14 @@ wsc_block_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, const
             const bool isq = h < 2;
             int8_t *rptr = isq ? (int8_t *)qbase(w, h) : nullptr;
             u8 *rflg = isq ? qbase(w, h) + Lr : nullptr;
-            const int len = expand_hap<int8_t>(in, d.sc, h, str, flg, ptr, rptr, rflg, ins, L);
+            int len;
+            if (d.staged) {
+                const WscStage st(smem + w * warp_bytes, d.M, d.vb[4]);
+                const HapSrcStaged src{smem + w * warp_bytes + d.M.rseq, Lr, d.vb[h], d.vb[h + 1] - d.vb[h], st.pos, st.rlen, st.aoff, st.type, st.alt};
+                len = expand_hap_src<int8_t>(src, str, flg, ptr, rptr, rflg, ins, L);
+            } else {
+                len = expand_hap<int8_t>(in, d.sc, h, str, flg, ptr, rptr, rflg, ins, L);
+            }
             bool ok = len == L;
             if (ok && isq) {
                 int8_t *toQ = (int8_t *)(qbase(w, h) + 2 * Lr), *toR = toQ + (L + 1 + Lr);
@@ -558,13 +629,8 @@ wsc_block_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, const
             if (!ok) desc[w].ok = 0;
         }
     }
-    if (live) {                                      // every warp stages its own REF-plane string meanwhile
-        const WscDesc &d = desc[warp];
-        const u8 *rs = in.rplane_seq + in.ref_off[d.sc];
-        u8 *rseq = smem + warp * warp_bytes + d.M.rseq;
-        for (int k = lane; k < d.p.lr; k += 32) rseq[k] = rs[k];
-    }
     __syncthreads();
+    VD_PH_MARK(1);
 
     // ---- phase 2: every warp sweeps the alignments of its own supercluster ----
     if (live && desc[warp].ok) {
@@ -598,11 +664,23 @@ wsc_block_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, const
             __syncwarp();
         }
     }
+#if VD_WSC_P3_PER_WARP
+    __syncwarp();
+#else
     __syncthreads();
+#endif
+    VD_PH_MARK(2);
 
-    // ---- phase 3: warp 0, lane 4w+ai walks alignment ai of supercluster w ----
-    if (warp == 0 && lane < 4 * (NW)) {
-        const int w = lane >> 2, ai = lane & 3;
+    // ---- phase 3: warp 0, lane 4w+ai walks alignment ai of supercluster w (VD_WSC_P3_PER_WARP: every warp its own
+    //      supercluster on lanes 0-3 - four times the issue slots for a quarter of the latency) ----
+#ifdef VD_PHASE_PROF
+    if (VD_WSC_P3_PER_WARP || warp == 0) {
+        __syncwarp();
+        if (lane < (VD_WSC_P3_PER_WARP ? 4 : 4 * (NW))) [&]() {
+#else
+    if (VD_WSC_P3_PER_WARP ? lane < 4 : (warp == 0 && lane < 4 * (NW))) {
+#endif
+        const int w = VD_WSC_P3_PER_WARP ? warp : lane >> 2, ai = lane & 3;
         const WscDesc &d = desc[w];
         if (d.sc < 0 || (HOM && ai)) return;
         const int sc = d.sc;
@@ -635,7 +713,262 @@ wsc_block_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, const
             out.status[oi + k] = status;
         }
         if constexpr (HOM) replicate_hom(in, out, sc);
+#ifdef VD_PHASE_PROF
+        }();
+        __syncwarp();
+        VD_PH_MARK(3);
+        if (threadIdx.x == 0) atomicAdd(&g_wsc_phase[ph_k][4], 1ull);
     }
+#else
+    }
+#endif
+}
+
+// ------------------------------------------------------------------------------------------
+// Split form of the same computation (the default): three launches per group instead of one fused kernel.
+// In the fused kernels the single-lane phases (expansion + swap tables before the sweeps, walk + credit after) run as ONE
+// warp per block while the block's other warps wait at a barrier and its registers and shared memory stay allocated:
+// measured, they are 50 % of a block's lifetime for 10 % of its instructions (profiles/, r2_b9).  Here they are kernels
+// of their own with one THREAD per haplotype / alignment over the whole group - hundreds of thousands of independent
+// threads instead of one warp per block - and the warp sweeps keep the SMs to themselves.  The hand-off goes through a
+// slab in HBM (one slot of the group's shared-memory bin size per supercluster, laid out like the shared memory of the
+// fused kernels: WscLayout): about 3 KB per supercluster written once and read once, against 20 us of a block's time.
+//
+//   wsc_expand_kernel   thread per (supercluster, haplotype): expand_hap + swap tables + truth-column info -> slab
+//   wsc_sweep_kernel<S> block per supercluster, warp per alignment: the expanded part of the slot comes in by one TMA
+//                       bulk copy (cp.async.bulk + mbarrier), forward and backward sweep in shared memory as before,
+//                       path flags back to the slot
+//   wsc_walk_kernel     thread per alignment: walk + credit over the slot
+// ------------------------------------------------------------------------------------------
+struct WscHdr { int ok; unsigned trivial; };
+
+// the wsc launch groups of one chunk in slot order (kernel parameter of the two thread-per-item kernels, which run once
+// over all groups: a launch of a few thousand threads would be all latency)
+constexpr int WSC_MAXG = 2 * WSC_MAXSLOT * N_WBIN;
+struct WscGroups {
+    int n;
+    int first[WSC_MAXG + 1];         // first slot of group k, first[n] = number of slots
+    int order_first[WSC_MAXG];       // where the group's superclusters start in order[]
+    int stride[WSC_MAXG];            // slab bytes per slot
+    int hom[WSC_MAXG];
+    long long base[WSC_MAXG];        // slab offset of the group's first slot
+};
+struct WscSlot { int sc, hom, stride; u8 *base; };
+__device__ __forceinline__ WscSlot wsc_slot(const WscGroups &G, int slot, const int *__restrict__ order, u8 *slab) {
+    int k = 0;
+    while (k + 1 < G.n && slot >= G.first[k + 1]) k++;
+    const int j = slot - G.first[k];
+    return WscSlot{order[G.order_first[k] + j], G.hom[k], G.stride[k], slab + G.base[k] + (int64_t)j * G.stride[k]};
+}
+
+__global__ void __launch_bounds__(128)
+wsc_expand_kernel(BatchDev in, const ScPlan *__restrict__ plan, const int *__restrict__ order, const __grid_constant__ WscGroups G, u8 *slab, WscHdr *hdr) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int slot = g >> 2, h = g & 3, lane = threadIdx.x & 31;
+    const bool live = slot < G.first[G.n];
+    bool ok = true;
+    unsigned trivial = 0;
+    if (live) {
+        const WscSlot ws = wsc_slot(G, slot, order, slab);
+        const int sc = ws.sc;
+        const bool HOM = ws.hom;
+        const ScPlan p = plan[sc];
+        const WscLayout M = wsc_layout(p, HOM);
+        u8 *base = ws.base;
+        const int L = p.len[h], Lr = p.lr;
+        if (!(HOM && (h & 1))) {
+            // built in thread-local memory (L1-cached: the swap tables re-read what the expansion wrote), then copied to
+            // the slot region by region, which have the same internal layout
+            __align__(4) u8 lh[(4 * WSC_MAXLEN + 3) & ~3], lq[(2 * WSC_MAXLEN + 2 * (2 * WSC_MAXLEN + 1) + 3) & ~3];
+            u8 *str = lh, *flg = str + L, *ins = str + 3 * L;
+            int8_t *ptr = (int8_t *)(str + 2 * L);
+            const bool isq = h < 2;
+            int8_t *rptr = isq ? (int8_t *)lq : nullptr;
+            u8 *rflg = isq ? lq + Lr : nullptr;
+            const int len = expand_hap<int8_t>(in, sc, h, str, flg, ptr, rptr, rflg, ins, L);
+            ok = len == L;
+            if (ok && isq) {
+                int8_t *toQ = (int8_t *)(lq + 2 * Lr), *toR = toQ + (L + 1 + Lr);
+                ok = build_swsrc<int8_t>(ptr, flg, len, toR, Lr) && build_swsrc<int8_t>(rptr, rflg, Lr, toQ, len);
+            }
+            if (ok) {
+                u32 *dst = (u32 *)(base + M.hap[h]);
+                const u32 *src = (const u32 *)lh;
+                for (int k = 0; k < (3 * L + Lr + 3) / 4; k++) dst[k] = src[k];
+                if (isq) {
+                    dst = (u32 *)(base + M.qm[h]); src = (const u32 *)lq;
+                    for (int k = 0; k < (2 * Lr + 2 * (L + Lr + 1) + 3) / 4; k++) dst[k] = src[k];
+                }
+            }
+            if (ok && !isq) {                        // truth columns: base | tok << 8   (:338-339, :367-368)
+                u16 *ti = (u16 *)(base + M.tinf[h - 2]);
+                for (int c = 0; c < L; c++) {
+                    const bool tok = c > 0 && (!(flg[c - 1] & P_VARIANT) || (flg[c - 1] & P_VAR_END));
+                    ti[c] = (u16)(str[c] | (tok ? 0x100 : 0));
+                }
+            }
+        }
+        if (h == 1) {                                // the REF-plane string
+            const u8 *rs = in.rplane_seq + in.ref_off[sc];
+            u8 *rseq = base + M.rseq;
+            for (int k = 0; k < Lr; k++) rseq[k] = rs[k];
+        }
+        if (h == 3 && in.rplane_seq == in.ref_seq) { // see wsc_kernel
+            const int64_t *vo = in.var_off + 4 * (int64_t)sc;
+            const int64_t o0 = vo[0], o1 = vo[1], o2 = vo[2], o3 = vo[3], o4 = vo[4];
+            const bool eq0 = o1 == o0, eq1 = o2 == o1, et0 = o3 == o2, et1 = o4 == o3;
+            trivial = (eq0 && et0 ? 1u : 0u) | (eq0 && et1 ? 2u : 0u) | (eq1 && et0 ? 4u : 0u) | (eq1 && et1 ? 8u : 0u);
+        }
+    }
+    // the four threads of a supercluster are neighbouring lanes
+    const unsigned okm = __ballot_sync(0xffffffffu, ok);
+    trivial = __shfl_sync(0xffffffffu, trivial, lane | 3);
+    if (live && h == 0) hdr[slot] = WscHdr{((okm >> (lane & ~3)) & 15u) == 15u ? 1 : 0, trivial};
+}
+
+template <int S, bool HOM>
+__global__ void __launch_bounds__(HOM ? 32 : 128, HOM ? 16 : wsc_minb(S))
+wsc_sweep_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, const int *__restrict__ order, int count, u8 *slab, int stride,
+                 const WscHdr *__restrict__ hdr) {
+    VD_DYN_SHARED(smem);
+    __shared__ __align__(8) unsigned long long s_bar;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slot = blockIdx.x;
+    const int sc = order[slot];
+    const ScPlan p = plan[sc];
+    const WscLayout M = wsc_layout(p, HOM);
+    const WscHdr hd = hdr[slot];
+    u8 *gbase = slab + (int64_t)slot * stride;
+    const int64_t oi = 4 * (int64_t)sc + (HOM ? 0 : warp);
+    if (!hd.ok) {
+        if (lane == 0) for (int k = 0; k < (HOM ? 4 : 1); k++) { out.status[oi + k] = ST_BAD; out.aln_score[oi + k] = -1; }
+        return;
+    }
+    // the expanded haplotypes, maps and tables of the slot: one TMA bulk copy, every thread waits on its barrier
+    if (threadIdx.x == 0) { VD_MBAR_INIT(&s_bar, 1); VD_MBAR_INIT_FENCE(); }
+    __syncthreads();
+    if (threadIdx.x == 0) VD_BULK_G2S(smem, gbase, (unsigned)((M.F[0] + 15) & ~15), &s_bar);
+    VD_MBAR_WAIT(&s_bar, 0u);
+    __syncthreads();
+    const int ai = HOM ? 0 : warp;
+    int score = 0, end_plane = 0, beg_plane = 0;
+    u32 status = 0;
+    if (!((hd.trivial >> ai) & 1)) {
+        const int qh = ai >> 1, th = 2 + (ai & 1);
+        const int Lr = p.lr, Lq = p.len[qh], Lt = p.len[th], N = Lq + Lr;
+        const u8 *qs = smem + M.hap[qh], *qb = smem + M.qm[qh];
+        WscAln X{qs, qs + Lq, smem + M.rseq, qb + Lr, (const int8_t *)(qs + 2 * Lq), (const int8_t *)qb,
+                 (const int8_t *)(qb + 2 * Lr), (const int8_t *)(qb + 2 * Lr + (Lq + 1 + Lr)),
+                 (const u16 *)(smem + M.tinf[ai & 1]), smem + M.F[ai], Lq, Lr, Lt};
+        wsc_sweep<S>(lane, X, score, end_plane, beg_plane, status);
+        __syncwarp();
+        // path flags to the slot (the regions are 4-byte aligned in both places)
+        const u32 *src = (const u32 *)(smem + M.F[ai]);
+        u32 *dst = (u32 *)(gbase + M.F[ai]);
+        for (int k = lane; k < (N * Lt + 3) / 4; k += 32) dst[k] = src[k];
+    }
+    if (lane == 0)
+        for (int k = 0; k < (HOM ? 4 : 1); k++) {
+            out.aln_score[oi + k] = score;
+            out.aln_end_plane[oi + k] = (u8)end_plane;
+            out.aln_beg_plane[oi + k] = (u8)beg_plane;
+            out.status[oi + k] = status;
+        }
+}
+
+// Small bins: one WARP per supercluster (its alignments one after the other, as in the fused kernel), four independent
+// warps per block - no block-wide barrier; each warp pulls its slot's expanded part in with its own TMA bulk copy.
+template <int S, bool HOM>
+__global__ void __launch_bounds__(WSC_TPB, wsc_minb(S))
+wsc_sweep_warp_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, const int *__restrict__ order, int count, u8 *slab, int stride,
+                      const WscHdr *__restrict__ hdr) {
+    VD_DYN_SHARED(smem);
+    __shared__ __align__(8) unsigned long long s_bar[WSC_TPB / 32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slot = blockIdx.x * (WSC_TPB / 32) + warp;
+    if (slot >= count) return;
+    const int sc = order[slot];
+    const ScPlan p = plan[sc];
+    const WscLayout M = wsc_layout(p, HOM);
+    const WscHdr hd = hdr[slot];
+    u8 *gbase = slab + (int64_t)slot * stride;
+    u8 *base = smem + warp * stride;
+    const int64_t oi = 4 * (int64_t)sc;
+    if (!hd.ok) {
+        if (lane < 4) { out.status[oi + lane] = ST_BAD; out.aln_score[oi + lane] = -1; }
+        return;
+    }
+    if (lane == 0) { VD_MBAR_INIT(&s_bar[warp], 1); VD_MBAR_INIT_FENCE(); }
+    __syncwarp();
+    if (lane == 0) VD_BULK_G2S(base, gbase, (unsigned)((M.F[0] + 15) & ~15), &s_bar[warp]);
+    VD_MBAR_WAIT(&s_bar[warp], 0u);
+    __syncwarp();
+    const int Lr = p.lr;
+    for (int ai = 0; ai < (HOM ? 1 : 4); ai++) {
+        int score = 0, end_plane = 0, beg_plane = 0;
+        u32 status = 0;
+        if (!((hd.trivial >> ai) & 1)) {
+            const int qh = ai >> 1, th = 2 + (ai & 1);
+            const int Lq = p.len[qh], Lt = p.len[th], N = Lq + Lr;
+            const u8 *qs = base + M.hap[qh], *qb = base + M.qm[qh];
+            u8 *F = base + M.F[0];                   // one flag matrix at a time: it leaves for the slot right after its sweeps
+            WscAln X{qs, qs + Lq, base + M.rseq, qb + Lr, (const int8_t *)(qs + 2 * Lq), (const int8_t *)qb,
+                     (const int8_t *)(qb + 2 * Lr), (const int8_t *)(qb + 2 * Lr + (Lq + 1 + Lr)),
+                     (const u16 *)(base + M.tinf[ai & 1]), F, Lq, Lr, Lt};
+            wsc_sweep<S>(lane, X, score, end_plane, beg_plane, status);
+            __syncwarp();
+            const u32 *src = (const u32 *)F;
+            u32 *dst = (u32 *)(gbase + M.F[ai]);
+            for (int k = lane; k < (N * Lt + 3) / 4; k += 32) dst[k] = src[k];
+            __syncwarp();
+        }
+        if (lane == 0)
+            for (int k = ai; k < (HOM ? 4 : ai + 1); k++) {
+                out.aln_score[oi + k] = score;
+                out.aln_end_plane[oi + k] = (u8)end_plane;
+                out.aln_beg_plane[oi + k] = (u8)beg_plane;
+                out.status[oi + k] = status;
+            }
+    }
+}
+
+__global__ void __launch_bounds__(128)
+wsc_walk_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, const int *__restrict__ order, const __grid_constant__ WscGroups G, u8 *slab,
+                const WscHdr *__restrict__ hdr) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int slot = g >> 2, ai = g & 3;
+    if (slot >= G.first[G.n]) return;
+    const WscHdr hd = hdr[slot];
+    if (!hd.ok || ((hd.trivial >> ai) & 1)) return;             // the sweep kernels have written those records
+    const WscSlot ws = wsc_slot(G, slot, order, slab);
+    const bool HOM = ws.hom;
+    if (HOM && ai) return;
+    const int sc = ws.sc;
+    const ScPlan p = plan[sc];
+    const WscLayout M = wsc_layout(p, HOM);
+    u8 *base = ws.base;
+    const int64_t oi = 4 * (int64_t)sc + ai;
+    const int qh = ai >> 1, th = 2 + (ai & 1);
+    const int Lr = p.lr, Lq = p.len[qh], Lt = p.len[th], N = Lq + Lr;
+    const u8 *qs = base + M.hap[qh], *ts = base + M.hap[th], *qb = base + M.qm[qh];
+    Hap<int8_t> q{Lq, qs, qs + Lq, (const int8_t *)(qs + 2 * Lq), qs + 3 * Lq};
+    Hap<int8_t> t{Lt, ts, ts + Lt, (const int8_t *)(ts + 2 * Lt), ts + 3 * Lt};
+    QMaps<int8_t> qm{(const int8_t *)qb, qb + Lr, (const int8_t *)(qb + 2 * Lr), (const int8_t *)(qb + 2 * Lr + (Lq + 1 + Lr))};
+    // path and Levenshtein scratch in thread-local memory (L1-cached, written and read back by this thread only): in the
+    // slot they would cost an L2 round trip per entry of the credit loop
+    constexpr int NPMAX = 32 * WSC_MAXSLOT + WSC_MAXLEN + 4, MNMAX = WSC_MAXLEN + 1;
+    __align__(4) u8 scratch[2 * ((2 * NPMAX + 3) & ~3) + ((NPMAX + 3) & ~3) + ((2 * MNMAX + 3) & ~3)];
+    GMemIL mem{scratch};
+    AlnLayout<int> L;
+    const int np = N + Lt + 4;
+    L.oPF = L.oF = L.oD0 = L.oD1 = L.oT0 = L.oT1 = 0;
+    L.oPQ = 0; L.oPT = wa4(2 * np); L.oPS = 2 * wa4(2 * np); L.oLev = L.oPS + wa4(np); L.total = 0;
+    PFWarp pfr{base + M.F[ai], N, Lq};
+    u32 status = out.status[oi];
+    const int end_plane = out.aln_end_plane[oi], beg_plane = out.aln_beg_plane[oi];
+    walk_credit<GMemIL, 2, int8_t>(mem, L, pfr, q, qm, t, base + M.rseq, Lr, beg_plane, end_plane, in, out, sc, ai, status);
+    for (int k = 0; k < (HOM ? 4 : 1); k++) out.status[oi + k] = status;
+    if (HOM) replicate_hom(in, out, sc);
 }
 
 #ifndef VD_WSC_PAR_MINBIN
@@ -680,6 +1013,58 @@ template <int S> inline void wsc_launch_one(cudaStream_t st, int bin, bool hom, 
         auto kw = wsc_kernel<S, false, false>;
         VD_LAUNCH(kw, (count + wpb - 1) / wpb, WSC_TPB, wpb * wb, st, in, out, plan, order, count, wb);
     }
+}
+template <int S> inline void wsc_split_configure_one() {
+    cudaFuncSetAttribute(wsc_sweep_kernel<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wsc_bin_cap(N_WBIN - 1));
+    cudaFuncSetAttribute(wsc_sweep_kernel<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wsc_bin_cap(N_WBIN - 1));
+    const int shmax = (WSC_TPB / 32) * wsc_bin_cap(N_WBIN - 1) < WSC_SMEM_MAX ? (WSC_TPB / 32) * wsc_bin_cap(N_WBIN - 1) : WSC_SMEM_MAX;
+    cudaFuncSetAttribute(wsc_sweep_warp_kernel<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, shmax);
+    cudaFuncSetAttribute(wsc_sweep_warp_kernel<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, shmax);
+}
+inline void wsc_split_configure() { wsc_split_configure_one<1>(); wsc_split_configure_one<2>(); wsc_split_configure_one<3>(); wsc_split_configure_one<4>(); }
+// split form, sweeps of one group over its slab (count slots of wsc_bin_cap(bin) bytes); the expansion before and the
+// walk after run once over all groups (wsc_expand_launch / wsc_walk_launch)
+template <int S> inline void wsc_split_launch_one(cudaStream_t st, int bin, bool hom, const BatchDev &in, const OutDev &out, const ScPlan *plan,
+                                                  const int *order, int count, u8 *slab, WscHdr *hdr) {
+    const int wb = wsc_bin_cap(bin), wpb = WSC_TPB / 32;
+    const bool par = !hom && bin >= (S >= 2 ? WSC_PAR_MINBIN_S2 : WSC_PAR_MINBIN);       // big bins: a block per supercluster
+    const bool fits = wpb * wb <= WSC_SMEM_MAX;
+    if (hom) {
+        if (fits) {
+            auto kw = wsc_sweep_warp_kernel<S, true>;
+            VD_LAUNCH(kw, (count + wpb - 1) / wpb, WSC_TPB, wpb * wb, st, in, out, plan, order, count, slab, wb, (const WscHdr *)hdr);
+        } else {
+            auto ks = wsc_sweep_kernel<S, true>;
+            VD_LAUNCH(ks, count, 32, wb, st, in, out, plan, order, count, slab, wb, (const WscHdr *)hdr);
+        }
+    } else {
+        if (!par && fits) {
+            auto kw = wsc_sweep_warp_kernel<S, false>;
+            VD_LAUNCH(kw, (count + wpb - 1) / wpb, WSC_TPB, wpb * wb, st, in, out, plan, order, count, slab, wb, (const WscHdr *)hdr);
+        } else {
+            auto ks = wsc_sweep_kernel<S, false>;
+            VD_LAUNCH(ks, count, 128, wb, st, in, out, plan, order, count, slab, wb, (const WscHdr *)hdr);
+        }
+    }
+}
+inline void wsc_split_launch(cudaStream_t st, int slots, int bin, bool hom, const BatchDev &in, const OutDev &out, const ScPlan *plan,
+                             const int *order, int count, u8 *slab, WscHdr *hdr) {
+    if (count <= 0) return;
+    switch (slots) {
+        case 1: wsc_split_launch_one<1>(st, bin, hom, in, out, plan, order, count, slab, hdr); break;
+        case 2: wsc_split_launch_one<2>(st, bin, hom, in, out, plan, order, count, slab, hdr); break;
+        case 3: wsc_split_launch_one<3>(st, bin, hom, in, out, plan, order, count, slab, hdr); break;
+        case 4: wsc_split_launch_one<4>(st, bin, hom, in, out, plan, order, count, slab, hdr); break;
+    }
+}
+inline void wsc_expand_launch(cudaStream_t st, const BatchDev &in, const ScPlan *plan, const int *order, const WscGroups &G, u8 *slab, WscHdr *hdr) {
+    const int n = G.first[G.n];
+    if (n > 0) VD_LAUNCH(wsc_expand_kernel, (4 * n + 127) / 128, 128, 0, st, in, plan, order, G, slab, hdr);
+}
+inline void wsc_walk_launch(cudaStream_t st, const BatchDev &in, const OutDev &out, const ScPlan *plan, const int *order, const WscGroups &G, u8 *slab,
+                            const WscHdr *hdr) {
+    const int n = G.first[G.n];
+    if (n > 0) VD_LAUNCH(wsc_walk_kernel, (4 * n + 127) / 128, 128, 0, st, in, out, plan, order, G, slab, hdr);
 }
 inline void wsc_launch(cudaStream_t st, int slots, int bin, bool hom, const BatchDev &in, const OutDev &out, const ScPlan *plan,
                        const int *order, int count) {
