@@ -136,6 +136,31 @@ typedef struct vd_packed_out {
     float    *callq;           /* [2*n_var]                                                                     */
 } vd_packed_out;
 
+/* The batch in compact form, for the copy in over PCIe (which bounds an end-to-end step once the results are 16-bit
+ * records): lengths instead of 64-bit offsets, 16-bit positions and lengths - 47 instead of 111 bytes per supercluster
+ * on a WGS batch.  The offsets are rebuilt on the GPU (prefix sums).  vd_compact_pack fills it from a vd_batch_in and
+ * returns VD_E_RANGE when a value does not fit (a window or REF/ALT allele of 65536 bases or more, more than 255
+ * variants on one haplotype of a supercluster): use vd_run / vd_run_packed for such a batch.                       */
+#define VD_COMPACT_BLOCK 65536   /* superclusters per entry of the blk_* index (where the host pipeline may cut)     */
+typedef struct vd_compact_in {
+    int32_t n_sc;
+    float   max_qual;
+    int64_t n_var, ref_bytes, alt_bytes;
+    const uint16_t *ref_len;     /* [n_sc] window length (ends - begs + 1)                                          */
+    const uint8_t  *ref_seq;     /* [ref_bytes]                                                                      */
+    const uint8_t  *rplane_seq;  /* [ref_bytes] or NULL, as in vd_batch_in                                           */
+    const uint8_t  *hap_nvar;    /* [4*n_sc] variants per haplotype q1,q2,t1,t2                                      */
+    const uint16_t *var_pos;     /* [n_var]                                                                          */
+    const uint16_t *var_rlen;    /* [n_var]                                                                          */
+    const uint16_t *alt_len;     /* [n_var]                                                                          */
+    const uint8_t  *var_type;    /* [n_var]                                                                          */
+    const uint8_t  *alt_seq;     /* [alt_bytes]                                                                      */
+    const float    *var_qual;    /* [n_var]                                                                          */
+    const int64_t  *blk_var;     /* [n_blk+1], n_blk = ceil(n_sc / VD_COMPACT_BLOCK): first variant of block b ...   */
+    const int64_t  *blk_ref;     /* ... its first window byte ...                                                    */
+    const int64_t  *blk_alt;     /* ... its first ALT byte; entry n_blk = the totals                                 */
+} vd_compact_in;
+
 /* counters of the last vd_run*/
 typedef struct vd_stats {
     int64_t n_sc, n_var;
@@ -201,6 +226,11 @@ int  vd_run(vd_handle *h, const vd_batch_in *in, vd_batch_out *out);
 int  vd_run_packed(vd_handle *h, const vd_batch_in *in, vd_packed_out *out);
 int  vd_finalize_packed(const vd_batch_in *in, const vd_packed_out *out,
                         double phase_threshold, double credit_threshold, vd_final *fin);
+
+/* Host only: fills *out (whose array pointers the caller has allocated: sizes as commented in vd_compact_in) from *in. */
+int  vd_compact_pack(const vd_batch_in *in, vd_compact_in *out);
+/* vd_run_packed with the batch in compact form.                                                                    */
+int  vd_run_compact(vd_handle *h, const vd_compact_in *in, vd_packed_out *out);
 
 /* Page-locked host memory for the buffers of vd_run / vd_run_packed (plain cudaHostAlloc / cudaFreeHost, so that a
  * caller needs no CUDA headers): copies from and to pageable memory run at a fraction of the PCIe rate.

@@ -36,5 +36,6 @@ for tool in memcheck racecheck; do
   BATCH=short run $tool force_wave VD_FORCE_CLASS=1
   BATCH=short run $tool force_slab VD_FORCE_CLASS=2
   BATCH=short run $tool wsc_only VD_SMALL_MAX=-1
+  BATCH=short run $tool wsc_fused VD_SMALL_MAX=-1 VD_WSC_SPLIT=0
   BATCH=short run $tool small1 VD_SMALL_MIN=1 VD_SMALL_MAX=1
 done

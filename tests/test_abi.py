@@ -30,7 +30,7 @@ def test_struct_layouts_match_header(tmp_path):
     """The ctypes mirrors have the sizes and field offsets gcc gives the structs of include/vcfdist_b200.h."""
     import subprocess
     from vcfdist_b200 import batch
-    names = ["vd_batch_in", "vd_batch_out", "vd_packed_out", "vd_final", "vd_stats"]
+    names = ["vd_batch_in", "vd_batch_out", "vd_packed_out", "vd_compact_in", "vd_final", "vd_stats"]
     prog = ['#include <stdio.h>', '#include <stddef.h>', '#include "vcfdist_b200.h"', 'int main(void) {']
     for n in names:
         prog.append(f'printf("{n} %zu\\n", sizeof({n}));')
@@ -97,6 +97,29 @@ def test_finalize_packed_equals_finalize():
         assert (f1[k].view(np.uint8) == f2[k].view(np.uint8)).all(), k
     w = pk.widened()
     assert (w["aln_score"] == out.aln_score[:a]).all() and (w["assigned"] == out.assigned[:v]).all()
+
+
+def test_compact_form_of_a_batch():
+    """vd_compact_pack (host only): lengths whose prefix sums are the batch's offsets, 16-bit positions, the block index the
+    host pipeline cuts at; VD_E_RANGE when a window does not fit 16 bits."""
+    from workloads import synth
+    from vcfdist_b200.batch import COMPACT_BLOCK
+    b = synth.wgs_like(9, 150_000, sv_frac=0.001, sv_max=3000)      # (the packer does not validate: plan_kernel does)
+    ci = capi.compact(b)
+    assert (np.concatenate([[0], np.cumsum(ci.ref_len[: b.n_sc].astype(np.int64))]) == b.ref_off).all()
+    assert (np.concatenate([[0], np.cumsum(ci.hap_nvar[: 4 * b.n_sc].astype(np.int64))]) == b.var_off).all()
+    assert (np.concatenate([[0], np.cumsum(ci.alt_len[: b.n_var].astype(np.int64))]) == b.alt_off).all()
+    assert (ci.var_pos[: b.n_var] == b.var_pos[: b.n_var]).all() and (ci.var_rlen[: b.n_var] == b.var_rlen[: b.n_var]).all()
+    blk = np.arange(0, b.n_sc, COMPACT_BLOCK)
+    assert (ci.blk_ref[: len(blk)] == b.ref_off[blk]).all() and ci.blk_ref[len(blk)] == b.ref_bytes
+    assert (ci.blk_var[: len(blk)] == b.var_off[4 * blk]).all() and ci.blk_var[len(blk)] == b.n_var
+    assert (ci.blk_alt[: len(blk)] == b.alt_off[b.var_off[4 * blk]]).all() and ci.blk_alt[len(blk)] == b.alt_bytes
+    assert ci.c.n_sc == b.n_sc and ci.c.n_var == b.n_var and ci.nbytes() < 0.55 * b.io_bytes()
+    bb = BatchBuilder(max_qual=60)
+    bb.add(b"ACGT" * 20000, [[(5, TYPE_SUB, 1, b"T", 10.0)], [], [], []])
+    with pytest.raises(capi.VdError) as ei:
+        capi.compact(bb.build())
+    assert ei.value.code == -7
 
 
 def test_product_package_never_touches_the_oracle():

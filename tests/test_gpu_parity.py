@@ -409,3 +409,26 @@ def test_packed_records_refuse_values_that_do_not_fit(engine):
     with pytest.raises(capi.VdError) as ei:
         engine.run_packed(b)
     assert ei.value.code == -7
+
+
+def test_compact_input_gives_the_same_records(engine):
+    """vd_run_compact (offsets rebuilt on the GPU from lengths, chunk cuts at the block index) against vd_run_packed, on
+    the demo golden, on a batch with long superclusters, on one that needs the REF-plane string, and on a batch big enough
+    for several pipeline chunks."""
+    b0, _, _ = load_golden("demo")
+    big = b0.take(np.resize(np.arange(b0.n_sc), 300_000))
+    a = synth.adversarial(41, 1500, max_len=40)
+    rp = a.ref_seq.copy()
+    rp[::13] = ord("A")
+    a_rp = Batch(ref_off=a.ref_off, ref_seq=a.ref_seq, var_off=a.var_off, var_pos=a.var_pos, var_rlen=a.var_rlen, var_type=a.var_type,
+                 alt_off=a.alt_off, alt_seq=a.alt_seq, var_qual=a.var_qual, max_qual=a.max_qual, rplane_seq=rp)
+    for b, env in ((b0, {}), (Batch.concat([synth.wgs_like(31, 3000), synth.sv_pairs(32, 2, 700, divergence=0.02)]), {}),
+                   (a_rp, {}), (big, {"VD_CHUNK_SC": 65536})):
+        e = engine_with(**env) if env else engine
+        want = e.run_packed(b)
+        got = e.run_compact(capi.compact(b))
+        for f in want.FIELDS:
+            x, y = getattr(got, f), getattr(want, f)
+            assert (x.view(np.uint8) == y.view(np.uint8)).all(), f
+        if env:
+            e.close()

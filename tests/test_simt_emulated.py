@@ -102,3 +102,17 @@ def test_distance_alignment_kernel():
         for i, s, cg in zip(ii, sc, cigs):
             assert s == int(z["cig_score"][i]) and (cg == z["cigar"][z["cig_off"][i]: z["cig_off"][i + 1]]).all()
     e.close()
+
+
+def test_compact_input_and_packed_records():
+    """vd_run_compact (offsets rebuilt on the device) and vd_run_packed against vd_run, several pipeline chunks."""
+    from vcfdist_b200 import capi
+    b0, _, _ = load_golden("demo")
+    b = b0.take(np.resize(np.arange(b0.n_sc), 70_000))
+    e = EmuEngine(VD_CHUNK_SC=65536)
+    wide = e.run(b).trimmed()
+    pk = e.run_packed(b).widened()
+    ck = e.run_compact(capi.compact(b)).widened()
+    e.close()
+    assert mismatches(pk, wide, OUT_KEYS) == {}
+    assert mismatches(ck, wide, OUT_KEYS) == {}

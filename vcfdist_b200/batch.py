@@ -43,6 +43,15 @@ class vd_packed_out(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("aln_score", "aln_planes", "status", "sync_group", "ref_ed", "query_ed", "callq")]
 
 
+class vd_compact_in(C.Structure):
+    _fields_ = [("n_sc", C.c_int32), ("max_qual", C.c_float), ("n_var", C.c_int64), ("ref_bytes", C.c_int64), ("alt_bytes", C.c_int64)] + \
+               [(n, C.c_void_p) for n in ("ref_len", "ref_seq", "rplane_seq", "hap_nvar", "var_pos", "var_rlen", "alt_len", "var_type",
+                                          "alt_seq", "var_qual", "blk_var", "blk_ref", "blk_alt")]
+
+
+COMPACT_BLOCK = 65536
+
+
 class vd_batch_out(C.Structure):
     _fields_ = [
         ("aln_score", C.c_void_p),
@@ -369,6 +378,36 @@ class Out:
         for f in self.FIELDS[4:]:
             d[f] = getattr(self, f)[:v]
         return d
+
+
+class CompactIn:
+    """Host-side `vd_compact_in`: the batch with lengths instead of 64-bit offsets and 16-bit positions (filled by
+    vd_compact_pack, capi.compact).  ref_seq / rplane_seq / var_type / alt_seq / var_qual are the batch's own arrays."""
+    OWN = (("ref_len", np.uint16, "sc"), ("hap_nvar", np.uint8, "sc4"), ("var_pos", np.uint16, "var"), ("var_rlen", np.uint16, "var"),
+           ("alt_len", np.uint16, "var"), ("blk_var", np.int64, "blk"), ("blk_ref", np.int64, "blk"), ("blk_alt", np.int64, "blk"))
+    SHARED = ("ref_seq", "rplane_seq", "var_type", "alt_seq", "var_qual")
+
+    def __init__(self, batch: "Batch"):
+        self.batch = batch
+        n_blk = (batch.n_sc + COMPACT_BLOCK - 1) // COMPACT_BLOCK
+        size = {"sc": batch.n_sc, "sc4": 4 * batch.n_sc, "var": batch.n_var, "blk": n_blk + 1}
+        for name, dt, per in self.OWN:
+            setattr(self, name, np.zeros(max(size[per], 1), dt))
+        for name in self.SHARED:
+            setattr(self, name, getattr(batch, name))
+        self.c = vd_compact_in()
+
+    def refresh_pointers(self):
+        """After replacing arrays (e.g. by page-locked copies): point the C struct at them."""
+        for name, _, _ in self.OWN:
+            setattr(self.c, name, _ptr(getattr(self, name)))
+        for name in self.SHARED:
+            setattr(self.c, name, _ptr(getattr(self, name)))
+
+    def nbytes(self) -> int:
+        b = self.batch
+        return (sum(getattr(self, n).nbytes for n, _, _ in self.OWN[:5]) + b.ref_bytes * (2 if b.rplane_seq is not None else 1)
+                + b.n_var + b.alt_bytes + 4 * b.n_var)
 
 
 @dataclass

@@ -14,14 +14,15 @@ from typing import Optional, Tuple
 
 import numpy as np
 
-from .batch import Batch, Final, Out, PackedOut, vd_batch_in, vd_batch_out, vd_final, vd_packed_out, vd_stats
+from .batch import Batch, CompactIn, Final, Out, PackedOut, vd_batch_in, vd_batch_out, vd_compact_in, vd_final, vd_packed_out, vd_stats
 
 _ROOT = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_ROOT, "libvcfdist_b200.so")
 
 EXPORTS = ("vd_abi_version", "vd_create", "vd_destroy", "vd_run", "vd_run_device", "vd_run_device_slice",
            "vd_finalize", "vd_get_stats", "vd_last_error", "vd_stream", "vd_wf_batch", "vd_swg_align_batch",
-           "vd_run_packed", "vd_finalize_packed", "vd_host_alloc", "vd_host_free", "vd_pack_device", "vd_packed_overflow")
+           "vd_run_packed", "vd_finalize_packed", "vd_host_alloc", "vd_host_free", "vd_pack_device", "vd_packed_overflow",
+           "vd_compact_pack", "vd_run_compact")
 
 _lib = None
 
@@ -53,6 +54,10 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.vd_host_alloc.restype = C.c_void_p
     lib.vd_host_free.argtypes = [C.c_void_p]
     lib.vd_host_free.restype = None
+    lib.vd_compact_pack.argtypes = [C.POINTER(vd_batch_in), C.POINTER(vd_compact_in)]
+    lib.vd_compact_pack.restype = C.c_int
+    lib.vd_run_compact.argtypes = [C.c_void_p, C.POINTER(vd_compact_in), C.POINTER(vd_packed_out)]
+    lib.vd_run_compact.restype = C.c_int
     lib.vd_pack_device.argtypes = [C.c_void_p, C.POINTER(vd_batch_out), C.c_int64, C.c_int64, C.POINTER(vd_packed_out)]
     lib.vd_pack_device.restype = C.c_int
     lib.vd_packed_overflow.argtypes = [C.c_void_p]
@@ -99,6 +104,18 @@ def finalize(batch: Batch, out, phase_threshold: float = 0.6, credit_threshold: 
     return fin
 
 
+def compact(batch: Batch, lib=None) -> CompactIn:
+    """vd_compact_pack: the batch in compact form (host only; raises VdError -7 when a value does not fit 16 / 8 bits)."""
+    lib = lib or load_library()
+    ci = CompactIn(batch)
+    ci.refresh_pointers()
+    cin = batch.as_c()
+    rc = lib.vd_compact_pack(C.byref(cin), C.byref(ci.c))
+    if rc != 0:
+        raise VdError(rc, "vd_compact_pack: a value does not fit the compact form")
+    return ci
+
+
 class Engine:
     """One handle per GPU (vd_create / vd_run / vd_destroy)."""
 
@@ -138,6 +155,13 @@ class Engine:
         out = out or PackedOut(batch.n_sc, batch.n_var)
         cin, cout = batch.as_c(), out.as_c()
         self._check(self.lib.vd_run_packed(self.h, C.byref(cin), C.byref(cout)))
+        return out
+
+    def run_compact(self, ci: CompactIn, out: Optional[PackedOut] = None) -> PackedOut:
+        """vd_run_compact: compact batch in (less than half the bytes over PCIe), 16-bit records out."""
+        out = out or PackedOut(ci.batch.n_sc, ci.batch.n_var)
+        cout = out.as_c()
+        self._check(self.lib.vd_run_compact(self.h, C.byref(ci.c), C.byref(cout)))
         return out
 
     def pack_device(self, dwide: vd_batch_out, n_sc: int, n_var: int, dpacked: vd_packed_out):

@@ -93,12 +93,13 @@ struct vd_handle {
                in_alt_off, in_alt_seq, in_var_qual;
         DevBuf o_score, o_endp, o_begp, o_status, o_assigned, o_sg, o_red, o_qed, o_callq;
         DevBuf p_score, p_planes, p_status, p_sg, p_red, p_qed;       // 16-bit records (vd_run_packed)
+        DevBuf c_ref_len, c_hap_nvar, c_pos16, c_rlen16, c_alen16, c_tmp;   // compact input (vd_run_compact)
         cudaEvent_t in_done = nullptr, out_done = nullptr;
         bool out_pending = false;
     } stage[NST];
     cudaStream_t s_in = nullptr, s_out = nullptr;
     int ramp = 1;                   // VD_RAMP=0: uniform chunks
-    int64_t chunk_sc = 1048576;      // superclusters per pipeline chunk (VD_CHUNK_SC)
+    int64_t chunk_sc = 786432;       // superclusters per pipeline chunk (VD_CHUNK_SC; a multiple of VD_COMPACT_BLOCK)
     // work
     DevBuf need_dense, bytes, offs, cubtmp, slab, hap_ok, wave_desc, band_state, band_lb, dense_bytes, dense_off, dense;
     DevBuf wf_in, wf_scratch;       // vd_wf_batch: staged problems, wavefront rings
@@ -197,7 +198,8 @@ extern "C" void vd_destroy(vd_handle *h) {
         DevBuf *sb[] = {&sg.in_ref_off, &sg.in_ref_seq, &sg.in_rplane, &sg.in_var_off, &sg.in_var_pos, &sg.in_var_rlen,
                         &sg.in_var_type, &sg.in_alt_off, &sg.in_alt_seq, &sg.in_var_qual, &sg.o_score, &sg.o_endp,
                         &sg.o_begp, &sg.o_status, &sg.o_assigned, &sg.o_sg, &sg.o_red, &sg.o_qed, &sg.o_callq,
-                        &sg.p_score, &sg.p_planes, &sg.p_status, &sg.p_sg, &sg.p_red, &sg.p_qed};
+                        &sg.p_score, &sg.p_planes, &sg.p_status, &sg.p_sg, &sg.p_red, &sg.p_qed,
+                        &sg.c_ref_len, &sg.c_hap_nvar, &sg.c_pos16, &sg.c_rlen16, &sg.c_alen16, &sg.c_tmp};
         for (DevBuf *b : sb) b->release();
         if (sg.in_done) cudaEventDestroy(sg.in_done);
         if (sg.out_done) cudaEventDestroy(sg.out_done);
@@ -670,14 +672,18 @@ static int quiesce(vd_handle *h, int rc) {
     return rc;
 }
 
-static int run_host(vd_handle *h, const vd_batch_in *in, vd_batch_out *out, vd_packed_out *pout);
+static int run_host(vd_handle *h, const vd_batch_in *in, const vd_compact_in *cin, vd_batch_out *out, vd_packed_out *pout);
 extern "C" int vd_run(vd_handle *h, const vd_batch_in *in, vd_batch_out *out) {
     if (!h || !in || !out) return VD_E_BADINPUT;
-    return run_host(h, in, out, nullptr);
+    return run_host(h, in, nullptr, out, nullptr);
 }
 extern "C" int vd_run_packed(vd_handle *h, const vd_batch_in *in, vd_packed_out *pout) {
     if (!h || !in || !pout) return VD_E_BADINPUT;
-    return run_host(h, in, nullptr, pout);
+    return run_host(h, in, nullptr, nullptr, pout);
+}
+extern "C" int vd_run_compact(vd_handle *h, const vd_compact_in *cin, vd_packed_out *pout) {
+    if (!h || !cin || !pout) return VD_E_BADINPUT;
+    return run_host(h, nullptr, cin, nullptr, pout);
 }
 extern "C" void *vd_host_alloc(int64_t bytes) {
     void *p = nullptr;
@@ -686,18 +692,21 @@ extern "C" void *vd_host_alloc(int64_t bytes) {
 }
 extern "C" void vd_host_free(void *p) { if (p) cudaFreeHost(p); }
 
-// vd_run (out) / vd_run_packed (pout): exactly one of the two is given
-static int run_host(vd_handle *h, const vd_batch_in *in, vd_batch_out *out, vd_packed_out *pout) {
+// vd_run (out) / vd_run_packed (pout): exactly one of the two is given; the batch as vd_batch_in (in) or in compact form
+// (cin, vd_run_compact): then the offsets are rebuilt per chunk on the device, 0-based
+static int run_host(vd_handle *h, const vd_batch_in *in, const vd_compact_in *cin, vd_batch_out *out, vd_packed_out *pout) {
     CK(cudaSetDevice(h->device));
-    const int64_t n_sc = in->n_sc;
+    const int64_t n_sc = in ? in->n_sc : cin->n_sc;
     if (n_sc < 0) return fail(h, VD_E_BADINPUT, "negative n_sc");
     h->stats = vd_stats{};
     h->stats_status_or = 0;
     *h->h_range = 0;
     if (n_sc == 0) return VD_OK;
-    const int64_t n_var = in->var_off[4 * n_sc];
-    const int64_t ref_bytes = in->ref_off[n_sc];
-    const int64_t alt_bytes = n_var ? in->alt_off[n_var] : 0;
+    const int64_t n_var = in ? in->var_off[4 * n_sc] : cin->n_var;
+    const int64_t ref_bytes = in ? in->ref_off[n_sc] : cin->ref_bytes;
+    const int64_t alt_bytes = in ? (n_var ? in->alt_off[n_var] : 0) : cin->alt_bytes;
+    const float max_qual = in ? in->max_qual : cin->max_qual;
+    const bool has_rplane = in ? in->rplane_seq != nullptr : cin->rplane_seq != nullptr;
     if (n_var < 0 || ref_bytes < 0 || alt_bytes < 0) return fail(h, VD_E_BADINPUT, "negative sizes");
     h->stats.n_sc = n_sc; h->stats.n_var = n_var;
     h->stats.io_bytes = io_bytes_of(n_sc, n_var, ref_bytes, alt_bytes);
@@ -717,6 +726,15 @@ static int run_host(vd_handle *h, const vd_batch_in *in, vd_batch_out *out, vd_p
         while (n_sc - s0 > CH + CH / 2) { s0 += CH; cut.push_back(s0); }
         if (h->ramp && n_sc - s0 > CH / 2 && CH / 4 > 0) { s0 = n_sc - CH / 4; cut.push_back(s0); }
         cut.push_back(n_sc);
+        if (cin) {                  // the compact form can only be cut where its block index has an entry
+            std::vector<int64_t> c2{0};
+            for (size_t k = 1; k + 1 < cut.size(); k++) {
+                const int64_t a = cut[k] / VD_COMPACT_BLOCK * VD_COMPACT_BLOCK;
+                if (a > c2.back()) c2.push_back(a);
+            }
+            c2.push_back(n_sc);
+            cut.swap(c2);
+        }
     }
     const int n_chunks = (int)cut.size() - 1;
     int64_t h2d = 0, d2h = 0;
@@ -725,6 +743,13 @@ static int run_host(vd_handle *h, const vd_batch_in *in, vd_batch_out *out, vd_p
     auto range_of = [&](int i) {
         Range r;
         r.s0 = cut[i]; r.s1 = cut[i + 1];
+        if (cin) {
+            auto at = [&](const int64_t *blk, int64_t s, int64_t total) { return s >= n_sc ? total : blk[s / VD_COMPACT_BLOCK]; };
+            r.v0 = at(cin->blk_var, r.s0, n_var); r.v1 = at(cin->blk_var, r.s1, n_var);
+            r.r0 = at(cin->blk_ref, r.s0, ref_bytes); r.r1 = at(cin->blk_ref, r.s1, ref_bytes);
+            r.a0 = at(cin->blk_alt, r.s0, alt_bytes); r.a1 = at(cin->blk_alt, r.s1, alt_bytes);
+            return r;
+        }
         r.v0 = in->var_off[4 * r.s0]; r.v1 = in->var_off[4 * r.s1];
         r.r0 = in->ref_off[r.s0]; r.r1 = in->ref_off[r.s1];
         r.a0 = n_var ? in->alt_off[r.v0] : 0; r.a1 = n_var ? in->alt_off[r.v1] : 0;
@@ -739,6 +764,37 @@ static int run_host(vd_handle *h, const vd_batch_in *in, vd_batch_out *out, vd_p
 #define UP(buf, src, bytes) do { CK(sg.buf.ensure((size_t)(bytes) + 16)); \
         if ((bytes) > 0) CK(cudaMemcpyAsync(sg.buf.p, (src), (size_t)(bytes), cudaMemcpyHostToDevice, h->s_in)); \
         h2d += (bytes); } while (0)
+        if (cin) {
+            // compact arrays in; sizes widened and prefix-summed on the copy stream behind them (0-based offsets)
+            UP(c_ref_len, cin->ref_len + r.s0, 2 * ns);
+            UP(in_ref_seq, cin->ref_seq + r.r0, r.r1 - r.r0);
+            if (cin->rplane_seq) UP(in_rplane, cin->rplane_seq + r.r0, r.r1 - r.r0);
+            UP(c_hap_nvar, cin->hap_nvar + 4 * r.s0, 4 * ns);
+            UP(c_pos16, cin->var_pos + r.v0, 2 * nv);
+            UP(c_rlen16, cin->var_rlen + r.v0, 2 * nv);
+            UP(c_alen16, cin->alt_len + r.v0, 2 * nv);
+            UP(in_var_type, cin->var_type + r.v0, nv);
+            UP(in_alt_seq, cin->alt_seq + r.a0, r.a1 - r.a0);
+            UP(in_var_qual, cin->var_qual + r.v0, 4 * nv);
+            CK(sg.in_ref_off.ensure(8 * (size_t)(ns + 1) + 16)); CK(sg.in_var_off.ensure(8 * (size_t)(4 * ns + 1) + 16));
+            CK(sg.in_alt_off.ensure(8 * (size_t)(nv + 1) + 16));
+            CK(sg.in_var_pos.ensure(4 * (size_t)nv + 16)); CK(sg.in_var_rlen.ensure(4 * (size_t)nv + 16));
+            const int64_t nel = (4 * ns > nv ? 4 * ns : nv) + 1;
+            VD_LAUNCH(unpack_sizes_kernel, (unsigned)((nel + 255) / 256), 256, 0, h->s_in, (const u16 *)sg.c_ref_len.p, ns, (const u8 *)sg.c_hap_nvar.p,
+                      (const u16 *)sg.c_alen16.p, nv, (int64_t *)sg.in_ref_off.p, (int64_t *)sg.in_var_off.p, (int64_t *)sg.in_alt_off.p,
+                      (const u16 *)sg.c_pos16.p, (const u16 *)sg.c_rlen16.p, (int32_t *)sg.in_var_pos.p, (int32_t *)sg.in_var_rlen.p);
+            int64_t *offs3[3] = {(int64_t *)sg.in_ref_off.p, (int64_t *)sg.in_var_off.p, (int64_t *)sg.in_alt_off.p};
+            const int64_t cnt3[3] = {ns + 1, 4 * ns + 1, nv + 1};
+            for (int k = 0; k < 3; k++) {
+                size_t tmp = 0;
+                cub::DeviceScan::ExclusiveSum(nullptr, tmp, offs3[k], offs3[k], (int)cnt3[k], h->s_in);
+                CK(sg.c_tmp.ensure(tmp));
+                cub::DeviceScan::ExclusiveSum(sg.c_tmp.p, tmp, offs3[k], offs3[k], (int)cnt3[k], h->s_in);
+            }
+            h->stats.n_launches += 4;
+            CK(cudaEventRecord(sg.in_done, h->s_in));
+            return VD_OK;
+        }
         UP(in_ref_off, in->ref_off + r.s0, 8 * (ns + 1));
         UP(in_ref_seq, in->ref_seq + r.r0, r.r1 - r.r0);
         if (in->rplane_seq) UP(in_rplane, in->rplane_seq + r.r0, r.r1 - r.r0);
@@ -776,17 +832,20 @@ static int run_host(vd_handle *h, const vd_batch_in *in, vd_batch_out *out, vd_p
         CK(sg.o_sg.ensure(8 * (size_t)nv + 16)); CK(sg.o_red.ensure(8 * (size_t)nv + 16));
         CK(sg.o_qed.ensure(8 * (size_t)nv + 16)); CK(sg.o_callq.ensure(8 * (size_t)nv + 16));
         CK(cudaStreamWaitEvent(h->s_plan, sg.in_done, 0));
-        const u8 *d_ref = (const u8 *)sg.in_ref_seq.p - r.r0;
-        const u8 *d_rpl = in->rplane_seq ? (const u8 *)sg.in_rplane.p - r.r0 : d_ref;
+        // offsets of a vd_batch_in chunk are the batch's own (absolute): the data pointers are shifted back instead;
+        // a compact chunk's offsets were rebuilt from 0
+        const int64_t sr = cin ? 0 : r.r0, sv = cin ? 0 : r.v0, sa = cin ? 0 : r.a0;
+        const u8 *d_ref = (const u8 *)sg.in_ref_seq.p - sr;
+        const u8 *d_rpl = has_rplane ? (const u8 *)sg.in_rplane.p - sr : d_ref;
         BatchDev b{(int)ns, (const int64_t *)sg.in_ref_off.p, d_ref, d_rpl, (const int64_t *)sg.in_var_off.p,
-                   (const int32_t *)sg.in_var_pos.p - r.v0, (const int32_t *)sg.in_var_rlen.p - r.v0,
-                   (const u8 *)sg.in_var_type.p - r.v0, (const int64_t *)sg.in_alt_off.p - r.v0,
-                   (const u8 *)sg.in_alt_seq.p - r.a0, (const float *)sg.in_var_qual.p - r.v0, in->max_qual, nv};
+                   (const int32_t *)sg.in_var_pos.p - sv, (const int32_t *)sg.in_var_rlen.p - sv,
+                   (const u8 *)sg.in_var_type.p - sv, (const int64_t *)sg.in_alt_off.p - sv,
+                   (const u8 *)sg.in_alt_seq.p - sa, (const float *)sg.in_var_qual.p - sv, max_qual, nv};
         OutDev base{(int32_t *)sg.o_score.p, (u8 *)sg.o_endp.p, (u8 *)sg.o_begp.p, (u32 *)sg.o_status.p,
                     (u8 *)sg.o_assigned.p, (int32_t *)sg.o_sg.p, (int32_t *)sg.o_red.p, (int32_t *)sg.o_qed.p,
                     (float *)sg.o_callq.p};
         OutDev o = base;                       // per-variant arrays are indexed [slot*nv + (v - v0)]
-        o.assigned -= r.v0; o.sync_group -= r.v0; o.ref_ed -= r.v0; o.query_ed -= r.v0; o.callq -= r.v0;
+        o.assigned -= sv; o.sync_group -= sv; o.ref_ed -= sv; o.query_ed -= sv; o.callq -= sv;
         return chunk_plan(h, W, h->s_plan, b, o, base);
     };
 

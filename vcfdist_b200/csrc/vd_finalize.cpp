@@ -133,3 +133,41 @@ extern "C" int vd_finalize_packed(const vd_batch_in *in, const vd_packed_out *ou
     if (!in || !out || !fin) return VD_E_BADINPUT;
     return finalize_all(in, PackedOut{out}, phase_threshold, credit_threshold, fin);
 }
+
+// compact form of a batch (host only; include/vcfdist_b200.h: vd_compact_in)
+extern "C" int vd_compact_pack(const vd_batch_in *in, vd_compact_in *out) {
+    if (!in || !out) return VD_E_BADINPUT;
+    const int64_t n_sc = in->n_sc;
+    const int64_t n_var = in->var_off[4 * n_sc];
+    uint16_t *ref_len = const_cast<uint16_t *>(out->ref_len), *pos = const_cast<uint16_t *>(out->var_pos),
+             *rlen = const_cast<uint16_t *>(out->var_rlen), *alen = const_cast<uint16_t *>(out->alt_len);
+    uint8_t *nvar = const_cast<uint8_t *>(out->hap_nvar);
+    int64_t *bv = const_cast<int64_t *>(out->blk_var), *br = const_cast<int64_t *>(out->blk_ref), *ba = const_cast<int64_t *>(out->blk_alt);
+    out->n_sc = in->n_sc; out->max_qual = in->max_qual;
+    out->n_var = n_var; out->ref_bytes = in->ref_off[n_sc]; out->alt_bytes = n_var ? in->alt_off[n_var] : 0;
+    out->ref_seq = in->ref_seq; out->rplane_seq = in->rplane_seq; out->var_type = in->var_type;
+    out->alt_seq = in->alt_seq; out->var_qual = in->var_qual;
+    bool fits = true;
+    for (int64_t s = 0; s < n_sc; s++) {
+        const int64_t len = in->ref_off[s + 1] - in->ref_off[s];
+        fits &= len >= 0 && len < 65536;
+        ref_len[s] = (uint16_t)len;
+        for (int k = 0; k < 4; k++) {
+            const int64_t n = in->var_off[4 * s + k + 1] - in->var_off[4 * s + k];
+            fits &= n >= 0 && n < 256;
+            nvar[4 * s + k] = (uint8_t)n;
+        }
+        if (s % VD_COMPACT_BLOCK == 0) {
+            const int64_t b = s / VD_COMPACT_BLOCK, v0 = in->var_off[4 * s];
+            bv[b] = v0; br[b] = in->ref_off[s]; ba[b] = n_var ? in->alt_off[v0] : 0;
+        }
+    }
+    const int64_t n_blk = (n_sc + VD_COMPACT_BLOCK - 1) / VD_COMPACT_BLOCK;
+    bv[n_blk] = n_var; br[n_blk] = out->ref_bytes; ba[n_blk] = out->alt_bytes;
+    for (int64_t v = 0; v < n_var; v++) {
+        const int64_t al = in->alt_off[v + 1] - in->alt_off[v];
+        fits &= al >= 0 && al < 65536 && in->var_pos[v] >= 0 && in->var_pos[v] < 65536 && in->var_rlen[v] >= 0 && in->var_rlen[v] < 65536;
+        pos[v] = (uint16_t)in->var_pos[v]; rlen[v] = (uint16_t)in->var_rlen[v]; alen[v] = (uint16_t)al;
+    }
+    return fits ? VD_OK : VD_E_RANGE;
+}

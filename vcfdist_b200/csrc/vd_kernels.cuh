@@ -105,6 +105,18 @@ __global__ void pack_out_kernel(OutDev o, int64_t n_aln, int64_t n_var, u16 *sco
     if (over) { *range_flag_host = 1u; __threadfence_system(); }
 }
 
+// compact input (vd_compact_in): sizes widened to 64 bits where the prefix sums will stand (entry n = 0), positions
+// and REF lengths to 32 bits
+__global__ void unpack_sizes_kernel(const u16 *ref_len, int64_t ns, const u8 *hap_nvar, const u16 *alt_len, int64_t nv,
+                                    int64_t *ref_off, int64_t *var_off, int64_t *alt_off,
+                                    const u16 *pos16, const u16 *rlen16, int32_t *var_pos, int32_t *var_rlen) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i <= ns) ref_off[i] = i < ns ? ref_len[i] : 0;
+    if (i <= 4 * ns) var_off[i] = i < 4 * ns ? hap_nvar[i] : 0;
+    if (i <= nv) alt_off[i] = i < nv ? alt_len[i] : 0;
+    if (i < nv) { var_pos[i] = pos16[i]; var_rlen[i] = rlen16[i]; }
+}
+
 // OR of all status words (so that the host only scans them when an error bit is set)
 __global__ void status_or_kernel(const u32 *status, int64_t n, unsigned *dst) {
     unsigned v = 0;
