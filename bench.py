@@ -203,31 +203,41 @@ def run_seam(args, b):
                                 "n_superclusters": b.n_sc, "ms_first_call": secs[0] * 1e3, "ms_per_call": secs[best] * 1e3,
                                 "breakdown_ms": bds[best], "host_threads": cores}
     ref, cli = (os.path.join(ROOT, "oracle", "_ref", n) for n in ("vcfdist_ref", "vcfdist_b200cli"))
-    if os.path.exists(ref) and os.path.exists(cli) and args.cli_contig_len > 0:
+    if os.path.exists(ref) and os.path.exists(cli) and (args.cli_contig_len > 0 or args.cli_cluster_contig_len > 0):
         import tempfile
         from workloads import vcfgen
         with tempfile.TemporaryDirectory() as tmp:
-            q, t, fa = vcfgen.generate(os.path.join(tmp, "in"), seed=args.seed, contig_len=args.cli_contig_len, n_contigs=2)
-            out = {}
-            for name, exe in (("reference", ref), ("drop_in", cli)):
-                od = os.path.join(tmp, name)
+            def run_cli(exe, od, q_, t_, fa_, extra):
                 os.makedirs(od, exist_ok=True)
                 t0 = time.perf_counter()
-                r = subprocess.run([exe, q, t, fa, "-p", od + "/", "-v", "1", "-t", str(cores), "-c", "gap", "50"],
+                r = subprocess.run([exe, q_, t_, fa_, "-p", od + "/", "-v", "1", "-t", str(cores), *extra],
                                    capture_output=True, text=True, cwd=od, env=dict(os.environ, VD_DROPIN_TIMES="1"))
-                out[name] = {"rc": r.returncode, "wall_s": time.perf_counter() - t0, "timer_5_precision_recall_s": cli_timer(r.stderr, 5),
-                             "timer_9_total_s": cli_timer(r.stderr, 9)}
+                res_ = {"rc": r.returncode, "wall_s": time.perf_counter() - t0, "timer_3_reclustering_s": cli_timer(r.stderr, 3),
+                        "timer_5_precision_recall_s": cli_timer(r.stderr, 5), "timer_9_total_s": cli_timer(r.stderr, 9)}
                 bd = [ln.split("GPU precision/recall:")[1].strip() for ln in r.stderr.splitlines() if "GPU precision/recall:" in ln]
                 if bd:
-                    out[name]["breakdown"] = bd[-1]
-            def same(files):
-                return bool(all(open(os.path.join(tmp, "reference", f)).read() == open(os.path.join(tmp, "drop_in", f)).read() for f in files))
-            res["cli"] = {"input": f"workloads.vcfgen seed {args.seed}, 2 contigs x {args.cli_contig_len} bp, -c gap 50, -t {cores}",
-                          "reference": out["reference"], "drop_in": out["drop_in"],
-                          # the tie rule can move single variants between TP and FP against the UNMODIFIED reference;
-                          # tests/test_cli_dropin.py holds the byte-for-byte comparison against the canonical-tie-break build
-                          "order_independent_files_identical": same(("superclusters.tsv", "phase-blocks.tsv", "phasing-summary.tsv", "switchflips.tsv")),
-                          "precision_recall_summary_identical": same(("precision-recall-summary.tsv",))}
+                    res_["breakdown"] = bd[-1]
+                return res_
+            if args.cli_contig_len > 0:
+                q, t, fa = vcfgen.generate(os.path.join(tmp, "in"), seed=args.seed, contig_len=args.cli_contig_len, n_contigs=2)
+                out = {name: run_cli(exe, os.path.join(tmp, name), q, t, fa, ["-c", "gap", "50"]) for name, exe in (("reference", ref), ("drop_in", cli))}
+                def same(files):
+                    return bool(all(open(os.path.join(tmp, "reference", f)).read() == open(os.path.join(tmp, "drop_in", f)).read() for f in files))
+                res["cli"] = {"input": f"workloads.vcfgen seed {args.seed}, 2 contigs x {args.cli_contig_len} bp, -c gap 50, -t {cores}",
+                              "reference": out["reference"], "drop_in": out["drop_in"],
+                              # the tie rule can move single variants between TP and FP against the UNMODIFIED reference;
+                              # tests/test_cli_dropin.py holds the byte-for-byte comparison against the canonical-tie-break build
+                              "order_independent_files_identical": same(("superclusters.tsv", "phase-blocks.tsv", "phasing-summary.tsv", "switchflips.tsv")),
+                              "precision_recall_summary_identical": same(("precision-recall-summary.tsv",))}
+            # the default clustering (biwfa, wf_swg_cluster): the stage the cluster drop-in replaces ([3] reclustering)
+            if args.cli_cluster_contig_len > 0:
+                q2, t2, fa2 = vcfgen.generate(os.path.join(tmp, "in2"), seed=args.seed + 1, contig_len=args.cli_cluster_contig_len, n_contigs=2)
+                out2 = {name: run_cli(exe, os.path.join(tmp, name + "_biwfa"), q2, t2, fa2, []) for name, exe in (("reference", ref), ("drop_in", cli))}
+                res["cli_biwfa_clustering"] = {
+                    "input": f"workloads.vcfgen seed {args.seed + 1}, 2 contigs x {args.cli_cluster_contig_len} bp, default clustering (biwfa), -t {cores}",
+                    "reference": out2["reference"], "drop_in": out2["drop_in"],
+                    "superclusters_identical": bool(open(os.path.join(tmp, "reference_biwfa", "superclusters.tsv")).read()
+                                                    == open(os.path.join(tmp, "drop_in_biwfa", "superclusters.tsv")).read())}
     return res
 
 
@@ -304,6 +314,8 @@ def main():
     ap.add_argument("--no-secondary", dest="secondary", action="store_false")
     ap.add_argument("--no-seam", action="store_true", help="skip the timing at the reference's own seam (function harness + CLI)")
     ap.add_argument("--cli-contig-len", type=int, default=6_000_000, help="seam timing through the CLI: bases per synthetic contig (0 = skip)")
+    ap.add_argument("--cli-cluster-contig-len", type=int, default=2_000_000,
+                    help="seam timing through the CLI with the default (biwfa) clustering: bases per synthetic contig (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         args.warmup = max(args.warmup, 1)
@@ -570,7 +582,8 @@ def main():
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": dom_ms,
                          "timing": "CUDA events around the kernel in a serial pass of the same step (VD_SERIAL=1); "
-                                   "wsc_kernel<S> = all launches of the warp-per-supercluster kernel (one per slots x smem bin)",
+                                   "wsc_kernel<S> = the warp path of the mid-size superclusters: wsc_expand_kernel + all wsc_sweep_* launches "
+                                   "(one per register slots x shared-memory bin x homozygous) + wsc_walk_kernel",
                          "serial_pass_ms": {k_: v_[0] for k_, v_ in ser.items()}, "serial_step_ms": ser_total,
                          "superclusters_per_class": [int(x) for x in st["n_small"]] + [int(st["n_long"]) // 4]},
         }

@@ -1,6 +1,8 @@
 """End to end through the reference's own CLI: oracle/_ref/vcfdist_ref (unmodified reference) and
-oracle/_ref/vcfdist_b200cli (same object code, hot-path call replaced by the drop-in of
-vcfdist_b200/host/pr_dropin.cpp -> vd_run on the GPU) must write byte-identical output files.
+oracle/_ref/vcfdist_b200cli (same object code; the hot-path call replaced by the drop-in of
+vcfdist_b200/host/pr_dropin.cpp -> vd_run_packed on the GPU, and the cluster-growing stage wf_swg_cluster by
+vcfdist_b200/host/cluster_dropin.cpp -> vd_wf_batch) must write byte-identical output files.  The default clustering
+method is biwfa, so the cases without -c go through the GPU clustering; superclusters.tsv then pins its result.
 Both binaries are prebuilt by oracle/Makefile and travel to the GPU box."""
 import filecmp
 import os
@@ -35,7 +37,7 @@ def vcf_body(path):
 
 
 @pytest.mark.parametrize("seed,extra", [(1, ["-c", "gap", "50"]), (2, ["-c", "size", "50", "-l", "400", "-s", "2000"]),
-                                        (3, [])])
+                                        (3, []), (4, ["-t", "3"]), (5, ["-i", "2"])])
 def test_cli_outputs_identical(tmp_path, seed, extra):
     q, t, fa = vcfgen.generate(str(tmp_path / "in"), seed=seed, contig_len=80_000 if not extra else 150_000)
     a = str(tmp_path / "ref"); b = str(tmp_path / "gpu"); c = str(tmp_path / "refB")

@@ -1,0 +1,100 @@
+// One GPU handle and one page-locked arena per process, shared by the drop-ins (pr_dropin.cpp, cluster_dropin.cpp): a
+// background thread started when the first of them is loaded creates the handle, page-locks the staging arena and runs a
+// small warm-up batch, so that CUDA start-up overlaps the reference's VCF parsing.
+#pragma once
+#include <chrono>
+#include <cstdint>
+#include <cstdlib>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "vcfdist_b200.h"
+
+namespace vdhost {
+
+// One GPU handle and one page-locked arena per process, set up by a background thread at load time.
+struct Runtime {
+    std::thread th;
+    vd_handle *h = nullptr;
+    int rc = VD_OK, device = 0;
+    uint8_t *arena = nullptr;
+    int64_t arena_cap = 0;
+    bool tried = false;
+    double init_ms[3] = {0, 0, 0};              // vd_create, page-locking the arena, warm-up batch
+    void init() {
+        using clk = std::chrono::steady_clock;
+        auto ms_since = [](clk::time_point t) { return std::chrono::duration<double, std::milli>(clk::now() - t).count(); };
+        auto t0 = clk::now();
+        tried = true;
+        if (const char *d = std::getenv("VD_DEVICE")) device = std::atoi(d);
+        rc = vd_create(device, 0, &h);
+        if (rc != VD_OK) return;
+        init_ms[0] = ms_since(t0); t0 = clk::now();
+        int64_t mb = 1024;
+        if (const char *m = std::getenv("VD_PIN_MB")) mb = std::atoll(m);
+        if (mb > 0) { arena = (uint8_t *)vd_host_alloc(mb << 20); arena_cap = arena ? (mb << 20) : 0; }
+        init_ms[1] = ms_since(t0); t0 = clk::now();
+        if (!std::getenv("VD_NO_WARMUP_BATCH")) warm_up();
+        init_ms[2] = ms_since(t0);
+    }
+    // A few synthetic superclusters of every size class through the whole path, so that the kernels' code is on the
+    // GPU and the handle's work buffers exist before the real batch arrives (CUDA loads a kernel at its first launch).
+    void warm_up() {
+        const int lens[] = {5, 5, 5, 5, 14, 14, 40, 40, 100, 700, 3000};
+        std::vector<int64_t> ref_off{0}, var_off{0}, alt_off{0};
+        std::vector<uint8_t> ref, alt, type;
+        std::vector<int32_t> pos, rlen;
+        std::vector<float> qual;
+        unsigned x = 12345u;
+        auto rnd = [&x]() { x = x * 1664525u + 1013904223u; return x >> 16; };
+        for (int rep = 0; rep < 8; rep++)
+            for (int L : lens) {
+                const size_t r0 = ref.size();
+                for (int k = 0; k < L; k++) ref.push_back("ACGT"[rnd() & 3]);
+                ref_off.push_back((int64_t)ref.size());
+                for (int hap = 0; hap < 4; hap++) {
+                    // haplotype `hap` carries a SNP at 1 + hap (+ a second one further on in long windows): heterozygous,
+                    // so that every alignment of the supercluster is computed
+                    for (int at : {1 + hap, L > 30 ? L / 2 + hap : -1}) {
+                        if (at < 0 || at >= L - 1) continue;
+                        pos.push_back(at); rlen.push_back(1); type.push_back(VD_TYPE_SUB);
+                        alt.push_back(ref[r0 + at] == 'A' ? 'C' : 'A');
+                        alt_off.push_back((int64_t)alt.size());
+                        qual.push_back(30.f);
+                    }
+                    var_off.push_back((int64_t)pos.size());
+                }
+            }
+        const int64_t n_sc = (int64_t)ref_off.size() - 1, n_var = (int64_t)pos.size();
+        vd_batch_in in{};
+        in.n_sc = (int32_t)n_sc; in.ref_off = ref_off.data(); in.ref_seq = ref.data(); in.rplane_seq = nullptr;
+        in.var_off = var_off.data(); in.var_pos = pos.data(); in.var_rlen = rlen.data(); in.var_type = type.data();
+        in.alt_off = alt_off.data(); in.alt_seq = alt.data(); in.var_qual = qual.data(); in.max_qual = 60.f;
+        std::vector<uint16_t> a16(3 * 4 * n_sc), v16(3 * 2 * n_var);
+        std::vector<uint8_t> pl(4 * n_sc);
+        std::vector<float> cq(2 * n_var);
+        vd_packed_out pk{a16.data(), pl.data(), a16.data() + 4 * n_sc, v16.data(), v16.data() + 2 * n_var, v16.data() + 4 * n_var, cq.data()};
+        vd_run_packed(h, &in, &pk);          // result and return code are of no interest
+    }
+    Runtime() { if (!std::getenv("VD_NO_WARM")) th = std::thread([this] { init(); }); }
+    std::mutex mu;                              // get() may be called from several host threads (the clustering stage)
+    std::mutex gpu;                             // a handle serves one host thread at a time: callers hold this around GPU calls
+    vd_handle *get() {
+        std::lock_guard<std::mutex> lk(mu);
+        if (th.joinable()) th.join();
+        if (!tried) init();
+        return h;
+    }
+    ~Runtime() {
+        if (th.joinable()) th.join();
+        if (arena) vd_host_free(arena);
+        if (h) vd_destroy(h);
+    }
+};
+
+inline Runtime &runtime() { static Runtime rt; return rt; }
+// one per translation unit that includes this header: the runtime starts at load time, not at the first call
+static const int runtime_started_at_load = (runtime(), 0);
+
+}  // namespace vdhost

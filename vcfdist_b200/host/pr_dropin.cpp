@@ -39,6 +39,9 @@
 #include "dist.h"
 
 #include "vcfdist_b200.h"
+#ifndef VD_DROPIN_WITH_REF
+#include "dropin_runtime.h"
+#endif
 
 #ifdef VD_DROPIN_WITH_REF
 void ref_precision_recall_threads_wrapper(
@@ -80,85 +83,6 @@ static void offsets_from_sizes(int64_t *a, int64_t n, int nt) {
     });
 }
 
-#ifndef VD_DROPIN_WITH_REF
-// One GPU handle and one page-locked arena per process, set up by a background thread at load time.
-struct Runtime {
-    std::thread th;
-    vd_handle *h = nullptr;
-    int rc = VD_OK, device = 0;
-    uint8_t *arena = nullptr;
-    int64_t arena_cap = 0;
-    bool tried = false;
-    double init_ms[3] = {0, 0, 0};              // vd_create, page-locking the arena, warm-up batch
-    void init() {
-        using clk = std::chrono::steady_clock;
-        auto ms_since = [](clk::time_point t) { return std::chrono::duration<double, std::milli>(clk::now() - t).count(); };
-        auto t0 = clk::now();
-        tried = true;
-        if (const char *d = std::getenv("VD_DEVICE")) device = std::atoi(d);
-        rc = vd_create(device, 0, &h);
-        if (rc != VD_OK) return;
-        init_ms[0] = ms_since(t0); t0 = clk::now();
-        int64_t mb = 1024;
-        if (const char *m = std::getenv("VD_PIN_MB")) mb = std::atoll(m);
-        if (mb > 0) { arena = (uint8_t *)vd_host_alloc(mb << 20); arena_cap = arena ? (mb << 20) : 0; }
-        init_ms[1] = ms_since(t0); t0 = clk::now();
-        if (!std::getenv("VD_NO_WARMUP_BATCH")) warm_up();
-        init_ms[2] = ms_since(t0);
-    }
-    // A few synthetic superclusters of every size class through the whole path, so that the kernels' code is on the
-    // GPU and the handle's work buffers exist before the real batch arrives (CUDA loads a kernel at its first launch).
-    void warm_up() {
-        const int lens[] = {5, 5, 5, 5, 14, 14, 40, 40, 100, 700, 3000};
-        std::vector<int64_t> ref_off{0}, var_off{0}, alt_off{0};
-        std::vector<uint8_t> ref, alt, type;
-        std::vector<int32_t> pos, rlen;
-        std::vector<float> qual;
-        unsigned x = 12345u;
-        auto rnd = [&x]() { x = x * 1664525u + 1013904223u; return x >> 16; };
-        for (int rep = 0; rep < 8; rep++)
-            for (int L : lens) {
-                const size_t r0 = ref.size();
-                for (int k = 0; k < L; k++) ref.push_back("ACGT"[rnd() & 3]);
-                ref_off.push_back((int64_t)ref.size());
-                for (int hap = 0; hap < 4; hap++) {
-                    // haplotype `hap` carries a SNP at 1 + hap (+ a second one further on in long windows): heterozygous,
-                    // so that every alignment of the supercluster is computed
-                    for (int at : {1 + hap, L > 30 ? L / 2 + hap : -1}) {
-                        if (at < 0 || at >= L - 1) continue;
-                        pos.push_back(at); rlen.push_back(1); type.push_back(VD_TYPE_SUB);
-                        alt.push_back(ref[r0 + at] == 'A' ? 'C' : 'A');
-                        alt_off.push_back((int64_t)alt.size());
-                        qual.push_back(30.f);
-                    }
-                    var_off.push_back((int64_t)pos.size());
-                }
-            }
-        const int64_t n_sc = (int64_t)ref_off.size() - 1, n_var = (int64_t)pos.size();
-        vd_batch_in in{};
-        in.n_sc = (int32_t)n_sc; in.ref_off = ref_off.data(); in.ref_seq = ref.data(); in.rplane_seq = nullptr;
-        in.var_off = var_off.data(); in.var_pos = pos.data(); in.var_rlen = rlen.data(); in.var_type = type.data();
-        in.alt_off = alt_off.data(); in.alt_seq = alt.data(); in.var_qual = qual.data(); in.max_qual = 60.f;
-        std::vector<uint16_t> a16(3 * 4 * n_sc), v16(3 * 2 * n_var);
-        std::vector<uint8_t> pl(4 * n_sc);
-        std::vector<float> cq(2 * n_var);
-        vd_packed_out pk{a16.data(), pl.data(), a16.data() + 4 * n_sc, v16.data(), v16.data() + 2 * n_var, v16.data() + 4 * n_var, cq.data()};
-        vd_run_packed(h, &in, &pk);          // result and return code are of no interest
-    }
-    Runtime() { if (!std::getenv("VD_NO_WARM")) th = std::thread([this] { init(); }); }
-    vd_handle *get() {
-        if (th.joinable()) th.join();
-        if (!tried) init();
-        return h;
-    }
-    ~Runtime() {
-        if (th.joinable()) th.join();
-        if (arena) vd_host_free(arena);
-        if (h) vd_destroy(h);
-    }
-};
-static Runtime rt;
-#endif
 
 // host buffers of one call: carved from the page-locked arena while they fit, pageable otherwise
 // Pageable blocks that outlive a call: the k-th request of a call gets the k-th block, grown when too small.  A second
@@ -514,13 +438,13 @@ void precision_recall_threads_wrapper(
     }
 #else
     auto t0 = clk::now();
-    vd_handle *h = vdhost::rt.get();                                // normally ready long before this point
+    vd_handle *h = vdhost::runtime().get();                                // normally ready long before this point
     if (!h) ERROR("vcfdist_b200: cannot initialise CUDA device %d (code %d); "
-                  "there is no CPU fallback for the precision/recall path", vdhost::rt.device, vdhost::rt.rc);
+                  "there is no CPU fallback for the precision/recall path", vdhost::runtime().device, vdhost::runtime().rc);
     const double ms_wait = ms_since(t0);
     t0 = clk::now();
     vdhost::HostMem mem(&vdhost::heap_slots[0]), heap(&vdhost::heap_slots[1]);   // GPU-facing buffers / host-only scratch
-    mem.arena = vdhost::rt.arena; mem.cap = vdhost::rt.arena_cap;
+    mem.arena = vdhost::runtime().arena; mem.cap = vdhost::runtime().arena_cap;
     vdhost::Packed p;
     vdhost::pack(clusterdata_ptr.get(), sc_groups, nt, mem, heap, p);
     const double ms_pack = ms_since(t0);
@@ -536,6 +460,7 @@ void precision_recall_threads_wrapper(
                      mem.take<uint16_t>(2 * n_var), mem.take<uint16_t>(2 * n_var), mem.take<uint16_t>(2 * n_var),
                      mem.take<float>(2 * n_var)};
     vd_batch_out out{};
+    std::lock_guard<std::mutex> gpu_lock(vdhost::runtime().gpu);
     int rc = vd_run_packed(h, &in, &pk);
     const bool wide = rc == VD_E_RANGE;
     if (wide) {
@@ -612,7 +537,7 @@ void precision_recall_threads_wrapper(
         INFO("  GPU precision/recall: %lld superclusters, %lld variants, %lld cells, %lld launches; wait %.1f ms (start-up: create %.0f, page-lock %.0f, warm-up %.0f), pack %.1f ms "
              "[sizes %.1f, alloc %.1f, bytes %.1f], vd_run%s %.1f ms (%.1f on device), status %.1f ms, finalize %.1f ms, scatter %.1f ms, %d host threads, %s buffers",
              (long long)st.n_sc, (long long)n_var, (long long)st.cells, (long long)st.n_launches, ms_wait,
-             vdhost::rt.init_ms[0], vdhost::rt.init_ms[1], vdhost::rt.init_ms[2], ms_pack, vdhost::pack_ms[0], vdhost::pack_ms[1], vdhost::pack_ms[2],
+             vdhost::runtime().init_ms[0], vdhost::runtime().init_ms[1], vdhost::runtime().init_ms[2], ms_pack, vdhost::pack_ms[0], vdhost::pack_ms[1], vdhost::pack_ms[2],
              wide ? "" : "_packed", ms_run, st.ms_total, ms_status, ms_fin, ms_scatter, nt, mem.spilled ? "partly pageable" : "page-locked");
 #endif  // VD_DROPIN_WITH_REF
 }
