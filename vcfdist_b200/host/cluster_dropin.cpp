@@ -15,6 +15,7 @@
 // The reference calls this function from up to -t host threads at once (src/main.cpp:82, :119, :146, :193), one per
 // (contig, haplotype): the strings of a batch are built concurrently, the GPU calls take turns on the process's handle.
 #include <algorithm>
+#include <chrono>
 #include <climits>
 #include <cstdint>
 #include <cstdlib>
@@ -56,6 +57,8 @@ void apply_variants(const std::string &fa, const ctgVariants &V, int beg_idx, in
     }
 }
 
+struct Times { double gpu_ms = 0, wait_ms = 0; long batches = 0, problems = 0, bytes = 0; };
+
 struct Batch {                       // problems of one vd_wf_batch call
     std::vector<int64_t> q_off{0}, t_off{0};
     std::string q, t;
@@ -63,19 +66,25 @@ struct Batch {                       // problems of one vd_wf_batch call
     std::vector<uint8_t> reverse;
     int n() const { return (int)q_off.size() - 1; }
     void close() { q_off.push_back((int64_t)q.size()); t_off.push_back((int64_t)t.size()); }
-    void run(int mode, int sub, int open, int extend) {
+    void run(int mode, int sub, int open, int extend, Times &tm) {
+        using clk = std::chrono::steady_clock;
         result.assign((size_t)std::max(n(), 1), 0);
         if (!n()) return;
+        const auto t0 = clk::now();
         vdhost::Runtime &rt = vdhost::runtime();
-        vd_handle *h = rt.get();
+        vdhost::Runtime::Lease lease(rt);                  // this thread's handle for the call
+        vd_handle *h = lease.h;
         if (!h) ERROR("vcfdist_b200: cannot initialise CUDA device %d (code %d); there is no CPU fallback for the clustering path",
                       rt.device, rt.rc);
-        std::lock_guard<std::mutex> lk(rt.gpu);
+        const auto t1 = clk::now();
         const bool reach = mode == 0;
         const int rc = vd_wf_batch(h, mode, n(), q_off.data(), (const uint8_t *)q.data(), t_off.data(), (const uint8_t *)t.data(),
                                    reach ? main_diag.data() : nullptr, reach ? main_diag_start.data() : nullptr,
                                    reach ? max_score.data() : nullptr, reach ? reverse.data() : nullptr, sub, open, extend, result.data());
         if (rc != VD_OK) ERROR("vcfdist_b200: vd_wf_batch failed (code %d): %s", rc, vd_last_error(h));
+        tm.wait_ms += std::chrono::duration<double, std::milli>(t1 - t0).count();
+        tm.gpu_ms += std::chrono::duration<double, std::milli>(clk::now() - t1).count();
+        tm.batches++; tm.problems += n(); tm.bytes += (long)(q.size() + t.size());
     }
 };
 
@@ -95,6 +104,8 @@ void wf_swg_cluster(variantData *vcf, int ctg_idx, int hap, int sub, int open, i
     const int L = vcf->lengths[ctg_idx];
     const int n = V.n;
 
+    Times tm;
+    const auto t_begin = std::chrono::steady_clock::now();
     std::vector<int> prev_clusters(n + 1);
     for (int i = 0; i <= n; i++) prev_clusters[i] = i;
     std::vector<char> prev_active(n + 1, 1);
@@ -117,7 +128,7 @@ void wf_swg_cluster(variantData *vcf, int ctg_idx, int hap, int sub, int open, i
             sb.t.append(fa, (size_t)beg, (size_t)(end - beg));
             sb.close();
         }
-        sb.run(/*score*/1, sub, open, extend);
+        sb.run(/*score*/1, sub, open, extend, tm);
         // ---- reaches: every (cluster, direction) search, one batch per doubling round (:1049-1158) ----
         std::vector<Search> searches;
         searches.reserve(2 * act.size());
@@ -162,7 +173,7 @@ void wf_swg_cluster(variantData *vcf, int ctg_idx, int hap, int sub, int open, i
                 rb.main_diag.push_back(s.main_diag); rb.main_diag_start.push_back(s.main_diag_start);
                 rb.max_score.push_back(s.score); rb.reverse.push_back(s.left ? 1 : 0);
             }
-            rb.run(/*reach*/0, sub, open, extend);
+            rb.run(/*reach*/0, sub, open, extend, tm);
             std::vector<int> next;
             for (size_t k = 0; k < pending.size(); k++) {
                 Search &s = searches[pending[k]];
@@ -214,6 +225,11 @@ void wf_swg_cluster(variantData *vcf, int ctg_idx, int hap, int sub, int open, i
         prev_clusters.swap(next_clusters);
         prev_active.swap(next_active);
     }
+    if (g.verbosity >= 2 || std::getenv("VD_DROPIN_TIMES"))
+        INFO("  GPU clustering %s hap %d: %d variants -> %d clusters, %d iterations, %ld batches, %ld problems, %.1f MB of strings; "
+             "%.0f ms in all, %.0f ms in vd_wf_batch, %.0f ms waiting for the handle", ctg.data(), hap + 1, n, (int)prev_clusters.size() - 1,
+             iter, tm.batches, tm.problems, tm.bytes / 1e6,
+             std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(), tm.gpu_ms, tm.wait_ms);
     vars->clusters = prev_clusters;                                                          // :1259-1262
     vars->left_reaches = left_reach;
     vars->right_reaches = right_reach;

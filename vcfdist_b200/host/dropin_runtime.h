@@ -3,6 +3,7 @@
 // small warm-up batch, so that CUDA start-up overlaps the reference's VCF parsing.
 #pragma once
 #include <chrono>
+#include <condition_variable>
 #include <cstdint>
 #include <cstdlib>
 #include <mutex>
@@ -79,16 +80,55 @@ struct Runtime {
     }
     Runtime() { if (!std::getenv("VD_NO_WARM")) th = std::thread([this] { init(); }); }
     std::mutex mu;                              // get() may be called from several host threads (the clustering stage)
-    std::mutex gpu;                             // a handle serves one host thread at a time: callers hold this around GPU calls
     vd_handle *get() {
         std::lock_guard<std::mutex> lk(mu);
         if (th.joinable()) th.join();
         if (!tried) init();
         return h;
     }
+    // A handle serves one host thread at a time.  The reference calls its clustering stage from several threads at once
+    // (one per contig and haplotype): each takes a handle of its own from a small pool (the first one plus up to
+    // VD_HANDLES - 1 more, created on demand), so that their batches run side by side on the GPU.
+    std::mutex pool_mu;
+    std::condition_variable pool_cv;
+    std::vector<vd_handle *> idle_extra;
+    bool main_busy = false;
+    int n_extra = 0, max_extra = 7;
+    vd_handle *acquire() {
+        vd_handle *first = get();
+        if (!first) return nullptr;
+        if (const char *m = std::getenv("VD_HANDLES")) max_extra = std::atoi(m) - 1;
+        std::unique_lock<std::mutex> lk(pool_mu);
+        for (;;) {
+            if (!main_busy) { main_busy = true; return first; }
+            if (!idle_extra.empty()) { vd_handle *x = idle_extra.back(); idle_extra.pop_back(); return x; }
+            if (n_extra < max_extra) {
+                n_extra++;
+                lk.unlock();
+                vd_handle *x = nullptr;
+                if (vd_create(device, 0, &x) == VD_OK) return x;
+                lk.lock();
+                n_extra--; max_extra = n_extra;         // no more handles to be had: share the ones there are
+                continue;
+            }
+            pool_cv.wait(lk);
+        }
+    }
+    void release(vd_handle *x) {
+        { std::lock_guard<std::mutex> lk(pool_mu); if (x == h) main_busy = false; else idle_extra.push_back(x); }
+        pool_cv.notify_one();
+    }
+    struct Lease {
+        Runtime &rt; vd_handle *h;
+        explicit Lease(Runtime &r) : rt(r), h(r.acquire()) {}
+        ~Lease() { if (h) rt.release(h); }
+        Lease(const Lease &) = delete;
+        Lease &operator=(const Lease &) = delete;
+    };
     ~Runtime() {
         if (th.joinable()) th.join();
         if (arena) vd_host_free(arena);
+        for (vd_handle *x : idle_extra) vd_destroy(x);
         if (h) vd_destroy(h);
     }
 };

@@ -438,7 +438,8 @@ void precision_recall_threads_wrapper(
     }
 #else
     auto t0 = clk::now();
-    vd_handle *h = vdhost::runtime().get();                                // normally ready long before this point
+    vdhost::Runtime::Lease lease(vdhost::runtime());                // normally ready long before this point
+    vd_handle *h = lease.h;
     if (!h) ERROR("vcfdist_b200: cannot initialise CUDA device %d (code %d); "
                   "there is no CPU fallback for the precision/recall path", vdhost::runtime().device, vdhost::runtime().rc);
     const double ms_wait = ms_since(t0);
@@ -460,7 +461,6 @@ void precision_recall_threads_wrapper(
                      mem.take<uint16_t>(2 * n_var), mem.take<uint16_t>(2 * n_var), mem.take<uint16_t>(2 * n_var),
                      mem.take<float>(2 * n_var)};
     vd_batch_out out{};
-    std::lock_guard<std::mutex> gpu_lock(vdhost::runtime().gpu);
     int rc = vd_run_packed(h, &in, &pk);
     const bool wide = rc == VD_E_RANGE;
     if (wide) {
