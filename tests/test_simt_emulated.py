@@ -116,3 +116,43 @@ def test_compact_input_and_packed_records():
     e.close()
     assert mismatches(pk, wide, OUT_KEYS) == {}
     assert mismatches(ck, wide, OUT_KEYS) == {}
+
+
+def test_bit_parallel_levenshtein_against_the_row_dp():
+    """lev_myers64 (csrc/vd_scalar.cuh: what wf_ed's `s`, src/dist.cpp:1406-1506, is computed with when the shorter string
+    has at most 64 symbols) against the textbook DP: random pairs over ACGT, with N / IUPAC symbols (the per-symbol
+    fallback of the match mask), pattern lengths 1..64, one-sided long texts, identical and disjoint strings."""
+    import ctypes as C
+    from emu import EMU_LIB, build
+    build()
+    lib = C.CDLL(EMU_LIB)
+    lib.vd_emu_lev_myers64.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int]
+    lib.vd_emu_lev_myers64.restype = C.c_int
+
+    def dp(a, b):
+        prev = list(range(len(b) + 1))
+        for i, x in enumerate(a, 1):
+            cur = [i]
+            for j, y in enumerate(b, 1):
+                cur.append(min(prev[j - 1] + (x != y), prev[j] + 1, cur[j - 1] + 1))
+            prev = cur
+        return prev[-1]
+
+    rng = np.random.default_rng(11)
+    alph = [b"ACGT", b"ACGTN", b"ACGTNRYKM", b"AC"]
+    cases = [(b"A", b"A"), (b"A", b"C"), (b"ACGT" * 16, b"ACGT" * 16), (b"C" * 300, b"A" * 64), (b"N" * 10, b"ACGTN" * 7)]
+    for _ in range(1500):
+        al = alph[int(rng.integers(0, len(alph)))]
+        n = int(rng.integers(1, 65))
+        m = int(rng.integers(1, 400 if rng.random() < 0.2 else 90))
+        b = bytes(al[i] for i in rng.integers(0, len(al), n))
+        if rng.random() < 0.5:                                   # a mutated copy: small distances
+            a = bytearray(b * (m // n + 1))[:m]
+            for k in rng.integers(0, max(len(a), 1), int(rng.integers(0, 6))):
+                a[int(k)] = al[int(rng.integers(0, len(al)))]
+            a = bytes(a)
+        else:
+            a = bytes(al[i] for i in rng.integers(0, len(al), m))
+        cases.append((a, b))
+    for a, b in cases:
+        assert lib.vd_emu_lev_myers64(a, len(a), b, len(b)) == dp(a, b), (a, b)

@@ -669,6 +669,10 @@ extern "C" void vd_debug_phases(unsigned long long *out48, int reset) {       //
     if (reset) { unsigned long long z[48] = {}; cudaMemcpyToSymbol(vd::g_wsc_phase, z, sizeof(z)); cudaMemcpyToSymbol(vd::g_walk_phase, z, 64); }
 }
 #endif
+#ifdef VD_EMU
+// CPU build under the SIMT emulator only (tests/simt): the bit-parallel section edit distance on its own
+extern "C" int vd_emu_lev_myers64(const uint8_t *a, int m, const uint8_t *b, int n) { return vd::lev_myers64(a, m, b, n); }
+#endif
 extern "C" int vd_packed_overflow(const vd_handle *h) { return h && h->h_range ? (int)*h->h_range : 0; }
 
 // error path of vd_run: nothing of this call may still be in flight when the caller gets its buffers back, and
