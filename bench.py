@@ -204,13 +204,14 @@ def run_seam(args, b):
         import tempfile
         from workloads import vcfgen
         with tempfile.TemporaryDirectory() as tmp:
-            def run_cli(exe, od, q_, t_, fa_, extra):
+            def run_cli(exe, od, q_, t_, fa_, extra, **env):
                 os.makedirs(od, exist_ok=True)
                 t0 = time.perf_counter()
                 r = subprocess.run([exe, q_, t_, fa_, "-p", od + "/", "-v", "1", "-t", str(cores), *extra],
-                                   capture_output=True, text=True, cwd=od, env=dict(os.environ, VD_DROPIN_TIMES="1"))
+                                   capture_output=True, text=True, cwd=od, env=dict(os.environ, VD_DROPIN_TIMES="1", **env))
                 res_ = {"rc": r.returncode, "wall_s": time.perf_counter() - t0, "timer_3_reclustering_s": cli_timer(r.stderr, 3),
-                        "timer_5_precision_recall_s": cli_timer(r.stderr, 5), "timer_9_total_s": cli_timer(r.stderr, 9)}
+                        "timer_5_precision_recall_s": cli_timer(r.stderr, 5), "timer_6_edit_distance_s": cli_timer(r.stderr, 6),
+                        "timer_9_total_s": cli_timer(r.stderr, 9)}
                 bd = [ln.split("GPU precision/recall:")[1].strip() for ln in r.stderr.splitlines() if "GPU precision/recall:" in ln]
                 if bd:
                     res_["breakdown"] = bd[-1]
@@ -229,12 +230,17 @@ def run_seam(args, b):
             # the default clustering (biwfa, wf_swg_cluster): the stage the cluster drop-in replaces ([3] reclustering)
             if args.cli_cluster_contig_len > 0:
                 q2, t2, fa2 = vcfgen.generate(os.path.join(tmp, "in2"), seed=args.seed + 1, contig_len=args.cli_cluster_contig_len, n_contigs=2)
-                out2 = {name: run_cli(exe, os.path.join(tmp, name + "_biwfa"), q2, t2, fa2, []) for name, exe in (("reference", ref), ("drop_in", cli))}
-                res["cli_biwfa_clustering"] = {
-                    "input": f"workloads.vcfgen seed {args.seed + 1}, 2 contigs x {args.cli_cluster_contig_len} bp, default clustering (biwfa), -t {cores}",
-                    "reference": out2["reference"], "drop_in": out2["drop_in"],
-                    "superclusters_identical": bool(open(os.path.join(tmp, "reference_biwfa", "superclusters.tsv")).read()
-                                                    == open(os.path.join(tmp, "drop_in_biwfa", "superclusters.tsv")).read())}
+                out2 = {name: run_cli(exe, os.path.join(tmp, name + "_biwfa"), q2, t2, fa2, ["--distance"]) for name, exe in (("reference", ref), ("drop_in", cli))}
+                out2["drop_in_every_clustering_call_on_the_gpu"] = run_cli(cli, os.path.join(tmp, "drop_in_biwfa_wait"), q2, t2, fa2, ["--distance"],
+                                                                            VD_GPU_CLUSTER_WAIT="1")
+                def same2(f):
+                    return bool(open(os.path.join(tmp, "reference_biwfa", f)).read() == open(os.path.join(tmp, "drop_in_biwfa", f)).read())
+                res["cli_biwfa_clustering_and_distance"] = {
+                    "input": f"workloads.vcfgen seed {args.seed + 1}, 2 contigs x {args.cli_cluster_contig_len} bp, default clustering (biwfa), --distance, -t {cores}",
+                    "note": "[3] reclustering = wf_swg_cluster (drop-in: on the GPU once CUDA is up, the reference's own code for the calls that "
+                            "arrive earlier), [5] precision/recall, [6] edit distance = edits_wrapper (drop-in: vd_swg_align_batch)",
+                    **out2, "superclusters_identical": same2("superclusters.tsv"), "distance_identical": same2("distance.tsv"),
+                    "edits_identical": same2("edits.tsv")}
     return res
 
 

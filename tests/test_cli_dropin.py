@@ -1,7 +1,8 @@
 """End to end through the reference's own CLI: oracle/_ref/vcfdist_ref (unmodified reference) and
 oracle/_ref/vcfdist_b200cli (same object code; the hot-path call replaced by the drop-in of
 vcfdist_b200/host/pr_dropin.cpp -> vd_run_packed on the GPU, and the cluster-growing stage wf_swg_cluster by
-vcfdist_b200/host/cluster_dropin.cpp -> vd_wf_batch) must write byte-identical output files.  The default clustering
+vcfdist_b200/host/cluster_dropin.cpp -> vd_wf_batch, the --distance pass edits_wrapper by
+vcfdist_b200/host/edits_dropin.cpp -> vd_swg_align_batch) must write byte-identical output files.  The default clustering
 method is biwfa, so the cases without -c go through the GPU clustering; superclusters.tsv then pins its result.
 Both binaries are prebuilt by oracle/Makefile and travel to the GPU box."""
 import filecmp
@@ -26,8 +27,10 @@ FILES = ["precision-recall.tsv", "precision-recall-summary.tsv", "query.tsv", "t
 
 def run(binary, q, t, fa, out, extra):
     os.makedirs(out, exist_ok=True)
+    # VD_GPU_CLUSTER_WAIT: every clustering call goes to the GPU (by default the calls that arrive before CUDA is up run the
+    # reference's own code)
     r = subprocess.run([binary, q, t, fa, "-p", out + "/", "-v", "0", *extra],
-                       capture_output=True, text=True, cwd=out, timeout=900)
+                       capture_output=True, text=True, cwd=out, timeout=900, env=dict(os.environ, VD_GPU_CLUSTER_WAIT="1"))
     assert r.returncode == 0, r.stderr[-2000:]
     return r
 
@@ -37,7 +40,8 @@ def vcf_body(path):
 
 
 @pytest.mark.parametrize("seed,extra", [(1, ["-c", "gap", "50"]), (2, ["-c", "size", "50", "-l", "400", "-s", "2000"]),
-                                        (3, []), (4, ["-t", "3"]), (5, ["-i", "2"])])
+                                        (3, []), (4, ["-t", "3"]), (5, ["-i", "2"]), (6, ["--distance"]),
+                                        (7, ["--distance", "-c", "gap", "30"])])
 def test_cli_outputs_identical(tmp_path, seed, extra):
     q, t, fa = vcfgen.generate(str(tmp_path / "in"), seed=seed, contig_len=80_000 if not extra else 150_000)
     a = str(tmp_path / "ref"); b = str(tmp_path / "gpu"); c = str(tmp_path / "refB")
@@ -51,6 +55,9 @@ def test_cli_outputs_identical(tmp_path, seed, extra):
     for f in FILES:
         assert filecmp.cmp(os.path.join(c, f), os.path.join(b, f), shallow=False), f
     assert vcf_body(os.path.join(c, "summary.vcf")) == vcf_body(os.path.join(b, "summary.vcf"))
+    if "--distance" in extra:            # the --distance pass (edits_wrapper -> vd_swg_align_batch): its two files
+        for f in ("distance.tsv", "distance-summary.tsv", "edits.tsv"):
+            assert filecmp.cmp(os.path.join(c, f), os.path.join(b, f), shallow=False), f
 
 
 @pytest.mark.parametrize("name", ["demo", "adv_11", "sv_21"])

@@ -13,7 +13,13 @@
 // Python (tests/test_gpu_cluster.py pins it against the reference's recorded answers).
 //
 // The reference calls this function from up to -t host threads at once (src/main.cpp:82, :119, :146, :193), one per
-// (contig, haplotype): the strings of a batch are built concurrently, the GPU calls take turns on the process's handle.
+// (contig, haplotype): every caller takes a handle of its own from the runtime's pool.
+//
+// Clustering is the first stage after the VCFs are read, so on a small input it starts before CUDA is up (0.5-4 s on these
+// boxes).  A call that arrives while the runtime is still starting runs the reference's own definition (linked in under
+// the name ref_wf_swg_cluster) instead of waiting: same results - that is what the parity tests check - and the GPU takes
+// over as soon as it is there.  VD_GPU_CLUSTER=0 keeps the stage on the CPU altogether, VD_GPU_CLUSTER_WAIT=1 makes every
+// call wait for the GPU (tests).  This is not a fallback of the precision/recall path, which has none.
 #include <algorithm>
 #include <chrono>
 #include <climits>
@@ -95,7 +101,14 @@ struct Search {                      // one reach search of one cluster (left or
 
 }  // namespace
 
+void ref_wf_swg_cluster(variantData *vcf, int ctg_idx, int hap, int sub, int open, int extend);   // the reference's, renamed at build time
+
 void wf_swg_cluster(variantData *vcf, int ctg_idx, int hap, int sub, int open, int extend) {
+    {
+        const char *on = std::getenv("VD_GPU_CLUSTER"), *wait = std::getenv("VD_GPU_CLUSTER_WAIT");
+        if ((on && !std::atoi(on)) || (!vdhost::runtime().ready && !(wait && std::atoi(wait))))
+            return ref_wf_swg_cluster(vcf, ctg_idx, hap, sub, open, extend);
+    }
     const std::string ctg = vcf->contigs[ctg_idx];
     std::shared_ptr<ctgVariants> vars = vcf->variants[hap][ctg];
     if (!vars->n) return;                                                                  // :964

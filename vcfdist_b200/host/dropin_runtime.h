@@ -2,6 +2,7 @@
 // background thread started when the first of them is loaded creates the handle, page-locks the staging arena and runs a
 // small warm-up batch, so that CUDA start-up overlaps the reference's VCF parsing.
 #pragma once
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <cstdint>
@@ -22,6 +23,7 @@ struct Runtime {
     uint8_t *arena = nullptr;
     int64_t arena_cap = 0;
     bool tried = false;
+    std::atomic<bool> ready{false};             // init() has finished (successfully or not)
     double init_ms[3] = {0, 0, 0};              // vd_create, page-locking the arena, warm-up batch
     void init() {
         using clk = std::chrono::steady_clock;
@@ -30,7 +32,7 @@ struct Runtime {
         tried = true;
         if (const char *d = std::getenv("VD_DEVICE")) device = std::atoi(d);
         rc = vd_create(device, 0, &h);
-        if (rc != VD_OK) return;
+        if (rc != VD_OK) { ready = true; return; }
         init_ms[0] = ms_since(t0); t0 = clk::now();
         int64_t mb = 1024;
         if (const char *m = std::getenv("VD_PIN_MB")) mb = std::atoll(m);
@@ -38,6 +40,7 @@ struct Runtime {
         init_ms[1] = ms_since(t0); t0 = clk::now();
         if (!std::getenv("VD_NO_WARMUP_BATCH")) warm_up();
         init_ms[2] = ms_since(t0);
+        ready = true;
     }
     // A few synthetic superclusters of every size class through the whole path, so that the kernels' code is on the
     // GPU and the handle's work buffers exist before the real batch arrives (CUDA loads a kernel at its first launch).
