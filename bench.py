@@ -244,6 +244,43 @@ def run_seam(args, b):
     return res
 
 
+def run_seeds(eng, args, dev, torch, first_seed_ms):
+    """The resident step on four more draws of the workload (seeds 2..5 beside the line's own seed): per-seed ms per step,
+    median and spread (SURVEY.md 8d asks for five seeds)."""
+    out = {str(args.seed): first_seed_ms}
+    for seed in range(args.seed + 1, args.seed + 5):
+        b, cells, _ = make_workload(args.workload, args.n_sc or WORKLOADS[args.workload]["n_sc"], seed, 0, 1, args.sv_max)
+        t_in = {k: torch.from_numpy(getattr(b, k)).to(dev) for k in ("ref_off", "ref_seq", "var_off", "var_pos", "var_rlen", "var_type",
+                                                                     "alt_off", "alt_seq", "var_qual")}
+        din = vd_batch_in()
+        din.n_sc = b.n_sc
+        for k, t in t_in.items():
+            setattr(din, k, t.data_ptr())
+        din.rplane_seq = None
+        din.max_qual = b.max_qual
+        nv = max(2 * b.n_var, 1)
+        t_out = {"aln_score": torch.zeros(4 * b.n_sc, dtype=torch.int32, device=dev), "status": torch.zeros(4 * b.n_sc, dtype=torch.int32, device=dev),
+                 "aln_end_plane": torch.zeros(4 * b.n_sc, dtype=torch.uint8, device=dev), "aln_beg_plane": torch.zeros(4 * b.n_sc, dtype=torch.uint8, device=dev),
+                 "assigned": torch.zeros(nv, dtype=torch.uint8, device=dev), "callq": torch.zeros(nv, dtype=torch.float32, device=dev),
+                 "sync_group": torch.zeros(nv, dtype=torch.int32, device=dev), "ref_ed": torch.zeros(nv, dtype=torch.int32, device=dev),
+                 "query_ed": torch.zeros(nv, dtype=torch.int32, device=dev)}
+        dout = vd_batch_out()
+        for k, t in t_out.items():
+            setattr(dout, k, t.data_ptr())
+        torch.cuda.synchronize()
+        for _ in range(3):
+            eng.run_device(din, dout, b.n_var, b.ref_bytes, b.alt_bytes)
+        ms = []
+        for _ in range(5):
+            eng.run_device(din, dout, b.n_var, b.ref_bytes, b.alt_bytes)
+            ms.append(float(eng.stats()["ms_total"]))
+        out[str(seed)] = {"ms_per_step": float(np.mean(ms)), "gcells_per_s": cells / (float(np.mean(ms)) * 1e-3) / 1e9, "cells": cells}
+        del t_in, t_out
+    vals = [v["ms_per_step"] for v in out.values()]
+    return {"per_seed": out, "median_ms_per_step": float(np.median(vals)), "min_ms_per_step": float(min(vals)), "max_ms_per_step": float(max(vals)),
+            "timing": "vd_stats.ms_total (CUDA events inside vd_run_device), 3 warm-up + 5 timed passes per seed"}
+
+
 def run_secondary(eng, args, dev, torch):
     """BASELINE configs[3] (WGS + SV tail to 10 kb) at FULL scale through vd_run with host buffers: 3.6 M
     superclusters of the demo mixture of which 0.3 % carry one 50 bp..10 kb INS/DEL, with its own CPU baseline
@@ -315,6 +352,7 @@ def main():
     ap.add_argument("--secondary", action="store_true", default=True,
                     help="also time the SV-bearing workload (BASELINE configs[3]) at full scale through vd_run (default at N=1)")
     ap.add_argument("--no-secondary", dest="secondary", action="store_false")
+    ap.add_argument("--no-seeds", action="store_true", help="skip the four extra draws of the workload (seeds 2..5)")
     ap.add_argument("--no-seam", action="store_true", help="skip the timing at the reference's own seam (function harness + CLI)")
     ap.add_argument("--cli-contig-len", type=int, default=6_000_000, help="seam timing through the CLI: bases per synthetic contig (0 = skip)")
     ap.add_argument("--cli-cluster-contig-len", type=int, default=2_000_000,
@@ -600,6 +638,9 @@ def main():
                 # the kernel is issue-bound, not HBM-bound: what the same capture says about the issue slots
                 line["roofline"]["ncu"] = {k_: t_[k_] for k_ in ("issue_slots_busy_pct", "warps_active_pct",
                                                                   "active_lanes_per_instruction") if k_ in t_}
+        if not args.no_seeds and world == 1:
+            line["seeds"] = run_seeds(eng, args, dev, torch, {"ms_per_step": ms_kernels / args.steps, "gcells_per_s": cells_total / (ms_kernels / args.steps * 1e-3) / 1e9,
+                                                               "cells": cells_total})
         if args.secondary and world == 1 and args.workload == "wgs":
             line["secondary"] = run_secondary(eng, args, dev, torch)
         if not args.no_seam and world == 1 and args.workload == "wgs":

@@ -7,7 +7,7 @@ out=gpurun_out/$tag
 mkdir -p "$out"
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > "$out/gpu.txt" 2>&1
 nproc >> "$out/gpu.txt"
-Q="--no-cpu-baseline --no-secondary --no-seam"
+Q="--no-cpu-baseline --no-secondary --no-seam --no-seeds"
 for w in $what; do
   case $w in
     tests)     timeout 1500 python -m pytest tests -m gpu -x -q > "$out/pytest_gpu.log" 2>&1; echo "tests rc=$?"; tail -2 "$out/pytest_gpu.log" ;;
