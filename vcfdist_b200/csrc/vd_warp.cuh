@@ -932,7 +932,10 @@ wsc_sweep_warp_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, 
     }
 }
 
-__global__ void __launch_bounds__(128)
+#ifndef VD_WSC_WALK_MINB
+#define VD_WSC_WALK_MINB 1
+#endif
+__global__ void __launch_bounds__(128, VD_WSC_WALK_MINB)
 wsc_walk_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, const int *__restrict__ order, const __grid_constant__ WscGroups G, u8 *slab,
                 const WscHdr *__restrict__ hdr) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
