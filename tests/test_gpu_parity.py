@@ -432,3 +432,50 @@ def test_compact_input_gives_the_same_records(engine):
             assert (x.view(np.uint8) == y.view(np.uint8)).all(), f
         if env:
             e.close()
+
+
+def test_device_records_narrowed_on_the_gpu(engine):
+    """The exchange record of the multi-GPU path: vd_run_device into wide device arrays, vd_pack_device into a
+    shard.PackedRecord, parsed back - against the oracle; and the overflow flag on a value that does not fit."""
+    import torch
+    from vcfdist_b200 import shard
+    from vcfdist_b200.batch import vd_batch_in, vd_batch_out, vd_packed_out
+    b = Batch.concat([synth.wgs_like(23, 5000, sv_frac=0.002, sv_max=400), synth.adversarial(24, 300, max_len=40)])
+    want = checkers.oracle_run(b).trimmed()
+    dev = torch.device("cuda", 0)
+    d_in = {k: torch.from_numpy(getattr(b, k)).to(dev) for k in ("ref_off", "ref_seq", "var_off", "var_pos", "var_rlen", "var_type",
+                                                                 "alt_off", "alt_seq", "var_qual")}
+    din = vd_batch_in()
+    din.n_sc = b.n_sc
+    for name, t in d_in.items():
+        setattr(din, name, t.data_ptr())
+    din.rplane_seq = None
+    din.max_qual = b.max_qual
+    nv = 2 * b.n_var
+    wide = {"aln_score": torch.zeros(4 * b.n_sc, dtype=torch.int32, device=dev), "status": torch.zeros(4 * b.n_sc, dtype=torch.int32, device=dev),
+            "aln_end_plane": torch.zeros(4 * b.n_sc, dtype=torch.uint8, device=dev), "aln_beg_plane": torch.zeros(4 * b.n_sc, dtype=torch.uint8, device=dev),
+            "assigned": torch.zeros(nv, dtype=torch.uint8, device=dev), "callq": torch.zeros(nv, dtype=torch.float32, device=dev),
+            "sync_group": torch.zeros(nv, dtype=torch.int32, device=dev), "ref_ed": torch.zeros(nv, dtype=torch.int32, device=dev),
+            "query_ed": torch.zeros(nv, dtype=torch.int32, device=dev)}
+    dout = vd_batch_out()
+    for name, t in wide.items():
+        setattr(dout, name, t.data_ptr())
+    rec = shard.PackedRecord(b.n_sc + 7, b.n_var + 5, dev)          # sized for a larger shard, as on a rank that is not the biggest
+    rec.set_counts(b.n_sc, b.n_var)
+    dp = vd_packed_out()
+    for name in ("aln_score", "aln_planes", "status", "sync_group", "ref_ed", "query_ed", "callq"):
+        setattr(dp, name, rec.views[name].data_ptr())
+    engine.run_device(din, dout, b.n_var, b.ref_bytes, b.alt_bytes)
+    engine.pack_device(dout, b.n_sc, b.n_var, dp)
+    torch.cuda.synchronize()
+    assert not engine.packed_overflow()
+    got = rec.parse(rec.buf.view(1, -1), 0)
+    for name in ("aln_score", "aln_end_plane", "aln_beg_plane", "status"):
+        assert (got[name].cpu().numpy().astype(np.int64) == want[name].astype(np.int64)).all(), name
+    for name in ("assigned", "sync_group", "ref_ed", "query_ed"):
+        assert (got[name].cpu().numpy().reshape(-1).astype(np.int64) == want[name].astype(np.int64)).all(), name
+    assert (got["callq"].cpu().numpy().reshape(-1).view(np.uint32) == want["callq"].view(np.uint32)).all()
+    wide["ref_ed"][3] = 70000                                         # does not fit 16 bits
+    engine.pack_device(dout, b.n_sc, b.n_var, dp)
+    torch.cuda.synchronize()
+    assert engine.packed_overflow()
