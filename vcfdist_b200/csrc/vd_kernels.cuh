@@ -205,7 +205,15 @@ __global__ void plan_kernel(BatchDev in, OutDev out, ScPlan *plan, int *list, u8
     if (live) { plan[sc] = p; ranks[sc] = (u8)(sbin >= 0 ? sbin : RANK_NONE); iota[sc] = sc; }
     if (live && cls == CLS_BAD)                        // malformed supercluster: flagged per alignment, never computed
         for (int k = 0; k < 4; k++) { out.status[4 * (int64_t)sc + k] = VD_ST_ERR_BADINPUT; out.aln_score[4 * (int64_t)sc + k] = -1; }
-    // warp-aggregated counters: one atomic per warp and counter instead of one per thread
+    // Counters: aggregated per warp (shuffles, match), then per block in shared memory, then ONE global atomic per block and
+    // counter - the batch's 14 k blocks would otherwise send half a million atomics to the same few addresses, which the L2
+    // serialises (that, not the loads, was most of this kernel's time).
+    __shared__ unsigned long long s_cells, s_io[N_GROUP];
+    __shared__ unsigned s_key[N_KEY];
+    for (int i = threadIdx.x; i < N_KEY; i += blockDim.x) s_key[i] = 0;
+    for (int i = threadIdx.x; i < N_GROUP; i += blockDim.x) s_io[i] = 0;
+    if (threadIdx.x == 0) s_cells = 0;
+    __syncthreads();
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const bool is_bad = live && cls == CLS_BAD, is_list = live && (cls == CLS_WAVE || cls == CLS_SCALAR);
@@ -218,18 +226,17 @@ __global__ void plan_kernel(BatchDev in, OutDev out, ScPlan *plan, int *list, u8
     const unsigned m_list = __ballot_sync(full, is_list), m_bad = __ballot_sync(full, is_bad);
     int base = 0;
     if (lane == 0) {
-        if (c_all) atomicAdd(&cnt->cells, c_all);
-        if (m_list) { base = atomicAdd(&cnt->n_list, __popc(m_list)); atomicAdd(&cnt->cells_list, c_list); }
+        if (c_all) atomicAdd(&s_cells, c_all);
+        if (m_list) { base = atomicAdd(&cnt->n_list, __popc(m_list)); atomicAdd(&cnt->cells_list, c_list); }     // long superclusters: rare
         if (m_bad) atomicAdd(&cnt->n_bad, __popc(m_bad));
     }
     base = __shfl_sync(full, base, 0);
     if (is_list) list[base + __popc(m_list & ((1u << lane) - 1))] = sc;
-    // per-bin counts of the small classes: one atomic per distinct bin in the warp
+    // per-bin counts of the small classes: one shared-memory atomic per distinct bin in the warp
     const int key = (live && sbin >= 0) ? sbin : -1;
     const unsigned peers = __match_any_sync(full, key);
-    if (key >= 0 && lane == __ffs(peers) - 1) atomicAdd(&cnt->n_key[key], __popc(peers));
-    {   // algorithmic bytes of each launch group's superclusters (io_bytes_of in vd_api.cu): one atomic per
-        // distinct group in the warp
+    if (key >= 0 && lane == __ffs(peers) - 1) atomicAdd(&s_key[key], (unsigned)__popc(peers));
+    {   // algorithmic bytes of each launch group's superclusters (io_bytes_of in vd_api.cu)
         const int grp = key >= 0 ? group_of_key(key) : -1;
         unsigned long long io = 0;
         if (grp >= 0) {
@@ -242,8 +249,12 @@ __global__ void plan_kernel(BatchDev in, OutDev out, ScPlan *plan, int *list, u8
         const int gl = __ffs(gp) - 1;
         unsigned long long tot = 0;
         for (unsigned m = gp; m; m &= m - 1) tot += __shfl_sync(gp, io, __ffs(m) - 1);
-        if (grp >= 0 && lane == gl) atomicAdd(&cnt->io_grp[grp], tot);
+        if (grp >= 0 && lane == gl) atomicAdd(&s_io[grp], tot);
     }
+    __syncthreads();
+    for (int i = threadIdx.x; i < N_KEY; i += blockDim.x) if (s_key[i]) atomicAdd(&cnt->n_key[i], (int)s_key[i]);
+    for (int i = threadIdx.x; i < N_GROUP; i += blockDim.x) if (s_io[i]) atomicAdd(&cnt->io_grp[i], s_io[i]);
+    if (threadIdx.x == 0 && s_cells) atomicAdd(&cnt->cells, s_cells);
 }
 
 // group ranges in the rank-sorted order array
