@@ -45,7 +45,7 @@ struct DevBuf {
 // so that the plan pass of chunk i+1 runs while the kernels of chunk i are still executing.
 struct Work {
     DevBuf plan, list, order, ranks, ranks_out, iota, counters, cubtmp;
-    DevBuf wsc_slab, wsc_hdr;               // split warp path: one slot per supercluster of the wsc groups, and its header
+    DevBuf wsc_slab, wsc_hdr, wsc_work;     // split warp path: one slot per supercluster of the wsc groups, its header, the walk kernel's work list
     PlanCounters *h_counters = nullptr;     // pinned + mapped: written by publish_kernel, never by a copy engine
     cudaEvent_t ev[4] = {};                 // plan start, plan end, short kernels issued, chunk end
     cudaEvent_t ev5 = nullptr;              // fork point of the short-kernel launch groups
@@ -218,7 +218,7 @@ extern "C" void vd_destroy(vd_handle *h) {
                       &h->band_lb, &h->dense_bytes, &h->dense_off, &h->dense, &h->wf_in, &h->wf_scratch};
     for (DevBuf *b : bufs) b->release();
     for (auto &w : h->work) {
-        DevBuf *wb[] = {&w.plan, &w.list, &w.order, &w.ranks, &w.ranks_out, &w.iota, &w.counters, &w.cubtmp, &w.wsc_slab, &w.wsc_hdr};
+        DevBuf *wb[] = {&w.plan, &w.list, &w.order, &w.ranks, &w.ranks_out, &w.iota, &w.counters, &w.cubtmp, &w.wsc_slab, &w.wsc_hdr, &w.wsc_work};
         for (DevBuf *b : wb) b->release();
         if (w.h_counters) cudaFreeHost(w.h_counters);
         for (auto &e : w.ev) if (e) cudaEventDestroy(e);
@@ -337,9 +337,11 @@ static int chunk_exec(vd_handle *h, Work &W) {
         WG.first[WG.n] = (int)ho;
         if (ho > 0) {
             CK(W.wsc_slab.ensure((size_t)so + 256)); CK(W.wsc_hdr.ensure(sizeof(WscHdr) * (size_t)ho + 16));
+            CK(W.wsc_work.ensure(4 * (size_t)(4 * ho + 4)));       // [0]: count, [4..]: items
             W.wsc_used = true;
             cudaStream_t sx = h->serial ? st : h->s_wsc;           // nothing on the main stream depends on the expansion
             if (sx != st) CK(cudaStreamWaitEvent(sx, W.ev[1], 0));
+            CK(cudaMemsetAsync(W.wsc_work.p, 0, 16, sx));
             CK(cudaEventRecord(W.wev[0], sx));
             wsc_expand_launch(sx, in, plan, order, WG, (u8 *)W.wsc_slab.p, (WscHdr *)W.wsc_hdr.p);
             CK(cudaEventRecord(W.wev[1], sx));
@@ -360,7 +362,8 @@ static int chunk_exec(vd_handle *h, Work &W) {
             const int w = g0 - N_SMALL;                      // (slots - 1) * N_WBIN + (N_WBIN - 1 - bin)
             if (h->wsc_split) {
                 wsc_split_launch(gs, w / N_WBIN + 1, N_WBIN - 1 - w % N_WBIN, hom, in, out, plan, order + pc.grp_first[g], cnt,
-                                 (u8 *)W.wsc_slab.p + slab_off[g], (WscHdr *)W.wsc_hdr.p + hdr_off[g]);
+                                 (u8 *)W.wsc_slab.p + slab_off[g], (WscHdr *)W.wsc_hdr.p + hdr_off[g],
+                                 WscWork{(int *)W.wsc_work.p, (int *)W.wsc_work.p + 4, (int)hdr_off[g]});
             } else {
                 wsc_launch(gs, w / N_WBIN + 1, N_WBIN - 1 - w % N_WBIN, hom, in, out, plan, order + pc.grp_first[g], cnt);
             }
@@ -572,7 +575,8 @@ static int chunk_exec(vd_handle *h, Work &W) {
     }
     if (W.wsc_used) {                          // walk + credit of all warp-path groups, behind their sweeps
         CK(cudaEventRecord(W.wev[2], se));
-        wsc_walk_launch(se, in, out, plan, order, WG, (u8 *)W.wsc_slab.p, (const WscHdr *)W.wsc_hdr.p);
+        wsc_walk_launch(se, in, out, plan, order, WG, (u8 *)W.wsc_slab.p, (const WscHdr *)W.wsc_hdr.p, (const int *)W.wsc_work.p,
+                        (const int *)W.wsc_work.p + 4);
         CK(cudaEventRecord(W.wev[3], se));
         S.n_launches++;
     }

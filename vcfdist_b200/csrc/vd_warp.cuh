@@ -741,6 +741,9 @@ wsc_block_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, const
 //   wsc_walk_kernel     thread per alignment: walk + credit over the slot
 // ------------------------------------------------------------------------------------------
 struct WscHdr { int ok; unsigned trivial; };
+// alignments the sweeps have finished and the walk kernel has to do, (global slot << 2 | alignment), in completion order:
+// the walk kernel then runs on dense warps instead of one thread per (slot, alignment) of which two thirds have nothing to do
+struct WscWork { int *count; int *item; int slot_base; };
 
 // the wsc launch groups of one chunk in slot order (kernel parameter of the two thread-per-item kernels, which run once
 // over all groups: a launch of a few thousand threads would be all latency)
@@ -829,7 +832,7 @@ wsc_expand_kernel(BatchDev in, const ScPlan *__restrict__ plan, const int *__res
 template <int S, bool HOM>
 __global__ void __launch_bounds__(HOM ? 32 : 128, HOM ? 16 : wsc_minb(S))
 wsc_sweep_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, const int *__restrict__ order, int count, u8 *slab, int stride,
-                 const WscHdr *__restrict__ hdr) {
+                 const WscHdr *__restrict__ hdr, WscWork work) {
     VD_DYN_SHARED(smem);
     __shared__ __align__(8) unsigned long long s_bar;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -867,13 +870,18 @@ wsc_sweep_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, const
         u32 *dst = (u32 *)(gbase + M.F[ai]);
         for (int k = lane; k < (N * Lt + 3) / 4; k += 32) dst[k] = src[k];
     }
-    if (lane == 0)
+    if (lane == 0) {
         for (int k = 0; k < (HOM ? 4 : 1); k++) {
             out.aln_score[oi + k] = score;
             out.aln_end_plane[oi + k] = (u8)end_plane;
             out.aln_beg_plane[oi + k] = (u8)beg_plane;
             out.status[oi + k] = status;
         }
+        if (!((hd.trivial >> ai) & 1)) {
+            __threadfence();                                   // records and path flags before the work item
+            work.item[atomicAdd(work.count, 1)] = ((work.slot_base + slot) << 2) | ai;
+        }
+    }
 }
 
 // Small bins: one WARP per supercluster (its alignments one after the other, as in the fused kernel), four independent
@@ -881,7 +889,7 @@ wsc_sweep_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, const
 template <int S, bool HOM>
 __global__ void __launch_bounds__(WSC_TPB, wsc_minb(S))
 wsc_sweep_warp_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, const int *__restrict__ order, int count, u8 *slab, int stride,
-                      const WscHdr *__restrict__ hdr) {
+                      const WscHdr *__restrict__ hdr, WscWork work) {
     VD_DYN_SHARED(smem);
     __shared__ __align__(8) unsigned long long s_bar[WSC_TPB / 32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -930,6 +938,15 @@ wsc_sweep_warp_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, 
                 out.status[oi + k] = status;
             }
     }
+    if (lane == 0) {                                           // this supercluster's alignments for the walk kernel
+        const unsigned todo = (HOM ? 1u : 15u) & ~hd.trivial;
+        const int n = __popc(todo);
+        if (n) {
+            __threadfence();
+            int at = atomicAdd(work.count, n);
+            for (int ai = 0; ai < 4; ai++) if ((todo >> ai) & 1) work.item[at++] = ((work.slot_base + slot) << 2) | ai;
+        }
+    }
 }
 
 #ifndef VD_WSC_WALK_MINB
@@ -937,15 +954,12 @@ wsc_sweep_warp_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, 
 #endif
 __global__ void __launch_bounds__(128, VD_WSC_WALK_MINB)
 wsc_walk_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, const int *__restrict__ order, const __grid_constant__ WscGroups G, u8 *slab,
-                const WscHdr *__restrict__ hdr) {
+                const WscHdr *__restrict__ hdr, const int *__restrict__ work_count, const int *__restrict__ work_item) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    const int slot = g >> 2, ai = g & 3;
-    if (slot >= G.first[G.n]) return;
-    const WscHdr hd = hdr[slot];
-    if (!hd.ok || ((hd.trivial >> ai) & 1)) return;             // the sweep kernels have written those records
+    if (g >= *work_count) return;                               // everything else the sweep kernels have written already
+    const int slot = work_item[g] >> 2, ai = work_item[g] & 3;
     const WscSlot ws = wsc_slot(G, slot, order, slab);
     const bool HOM = ws.hom;
-    if (HOM && ai) return;
     const int sc = ws.sc;
     const ScPlan p = plan[sc];
     const WscLayout M = wsc_layout(p, HOM);
@@ -1028,36 +1042,36 @@ inline void wsc_split_configure() { wsc_split_configure_one<1>(); wsc_split_conf
 // split form, sweeps of one group over its slab (count slots of wsc_bin_cap(bin) bytes); the expansion before and the
 // walk after run once over all groups (wsc_expand_launch / wsc_walk_launch)
 template <int S> inline void wsc_split_launch_one(cudaStream_t st, int bin, bool hom, const BatchDev &in, const OutDev &out, const ScPlan *plan,
-                                                  const int *order, int count, u8 *slab, WscHdr *hdr) {
+                                                  const int *order, int count, u8 *slab, WscHdr *hdr, WscWork work) {
     const int wb = wsc_bin_cap(bin), wpb = WSC_TPB / 32;
     const bool par = !hom && bin >= (S >= 2 ? WSC_PAR_MINBIN_S2 : WSC_PAR_MINBIN);       // big bins: a block per supercluster
     const bool fits = wpb * wb <= WSC_SMEM_MAX;
     if (hom) {
         if (fits) {
             auto kw = wsc_sweep_warp_kernel<S, true>;
-            VD_LAUNCH(kw, (count + wpb - 1) / wpb, WSC_TPB, wpb * wb, st, in, out, plan, order, count, slab, wb, (const WscHdr *)hdr);
+            VD_LAUNCH(kw, (count + wpb - 1) / wpb, WSC_TPB, wpb * wb, st, in, out, plan, order, count, slab, wb, (const WscHdr *)hdr, work);
         } else {
             auto ks = wsc_sweep_kernel<S, true>;
-            VD_LAUNCH(ks, count, 32, wb, st, in, out, plan, order, count, slab, wb, (const WscHdr *)hdr);
+            VD_LAUNCH(ks, count, 32, wb, st, in, out, plan, order, count, slab, wb, (const WscHdr *)hdr, work);
         }
     } else {
         if (!par && fits) {
             auto kw = wsc_sweep_warp_kernel<S, false>;
-            VD_LAUNCH(kw, (count + wpb - 1) / wpb, WSC_TPB, wpb * wb, st, in, out, plan, order, count, slab, wb, (const WscHdr *)hdr);
+            VD_LAUNCH(kw, (count + wpb - 1) / wpb, WSC_TPB, wpb * wb, st, in, out, plan, order, count, slab, wb, (const WscHdr *)hdr, work);
         } else {
             auto ks = wsc_sweep_kernel<S, false>;
-            VD_LAUNCH(ks, count, 128, wb, st, in, out, plan, order, count, slab, wb, (const WscHdr *)hdr);
+            VD_LAUNCH(ks, count, 128, wb, st, in, out, plan, order, count, slab, wb, (const WscHdr *)hdr, work);
         }
     }
 }
 inline void wsc_split_launch(cudaStream_t st, int slots, int bin, bool hom, const BatchDev &in, const OutDev &out, const ScPlan *plan,
-                             const int *order, int count, u8 *slab, WscHdr *hdr) {
+                             const int *order, int count, u8 *slab, WscHdr *hdr, WscWork work) {
     if (count <= 0) return;
     switch (slots) {
-        case 1: wsc_split_launch_one<1>(st, bin, hom, in, out, plan, order, count, slab, hdr); break;
-        case 2: wsc_split_launch_one<2>(st, bin, hom, in, out, plan, order, count, slab, hdr); break;
-        case 3: wsc_split_launch_one<3>(st, bin, hom, in, out, plan, order, count, slab, hdr); break;
-        case 4: wsc_split_launch_one<4>(st, bin, hom, in, out, plan, order, count, slab, hdr); break;
+        case 1: wsc_split_launch_one<1>(st, bin, hom, in, out, plan, order, count, slab, hdr, work); break;
+        case 2: wsc_split_launch_one<2>(st, bin, hom, in, out, plan, order, count, slab, hdr, work); break;
+        case 3: wsc_split_launch_one<3>(st, bin, hom, in, out, plan, order, count, slab, hdr, work); break;
+        case 4: wsc_split_launch_one<4>(st, bin, hom, in, out, plan, order, count, slab, hdr, work); break;
     }
 }
 inline void wsc_expand_launch(cudaStream_t st, const BatchDev &in, const ScPlan *plan, const int *order, const WscGroups &G, u8 *slab, WscHdr *hdr) {
@@ -1065,9 +1079,9 @@ inline void wsc_expand_launch(cudaStream_t st, const BatchDev &in, const ScPlan 
     if (n > 0) VD_LAUNCH(wsc_expand_kernel, (4 * n + 127) / 128, 128, 0, st, in, plan, order, G, slab, hdr);
 }
 inline void wsc_walk_launch(cudaStream_t st, const BatchDev &in, const OutDev &out, const ScPlan *plan, const int *order, const WscGroups &G, u8 *slab,
-                            const WscHdr *hdr) {
-    const int n = G.first[G.n];
-    if (n > 0) VD_LAUNCH(wsc_walk_kernel, (4 * n + 127) / 128, 128, 0, st, in, out, plan, order, G, slab, hdr);
+                            const WscHdr *hdr, const int *work_count, const int *work_item) {
+    const int n = G.first[G.n];          // the grid covers the worst case (every alignment to be walked); the count is on the device
+    if (n > 0) VD_LAUNCH(wsc_walk_kernel, (4 * n + 127) / 128, 128, 0, st, in, out, plan, order, G, slab, hdr, work_count, work_item);
 }
 inline void wsc_launch(cudaStream_t st, int slots, int bin, bool hom, const BatchDev &in, const OutDev &out, const ScPlan *plan,
                        const int *order, int count) {
