@@ -310,6 +310,7 @@ small_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, const int
     SMemIL mem{smem + SPB * D::SC_BYTES + tid * SmallMem<K>::STRIDE};
 
     int lr = 0;
+    bool novar = false;                                  // my haplotype carries no variant
     if (active) {
         lr = plan[sc].lr;
         // thread h expands haplotype h (generate_ptrs_strs); query haps also keep the ref side
@@ -323,37 +324,69 @@ small_kernel(BatchDev in, OutDev out, const ScPlan *__restrict__ plan, const int
                  build_swsrc<int8_t>(A.rptr(h), A.rflg(h), lr, A.toQ(h), len);
         }
         A.hlen()[h] = (short)(ok ? len : -1);
+        novar = in.var_off[4 * (int64_t)sc + h + 1] == in.var_off[4 * (int64_t)sc + h];
         if (h == 2) {
             const u8 *rs = in.rplane_seq + in.ref_off[sc];
             for (int k = 0; k < lr; k++) A.rseq()[k] = rs[k];
         }
     }
     __syncwarp();
-    if (!active) return;
-    const int ai = h;
+    // Which of the block's alignments there is something to compute for.  An alignment whose query and truth haplotypes
+    // both carry no variant compares the window with itself (score 0, both path ends on the QUERY plane, nothing to
+    // credit: the Q2T2 of every heterozygous site; see wsc_kernel) and a supercluster with a malformed haplotype is
+    // flagged: both are written here.  The rest is compacted over the block, so that the sweeps run on full warps.
+    const unsigned fullm = 0xffffffffu;
+    const int lane = tid & 31, qbase = lane & ~3;
+    const unsigned nv4 = (__ballot_sync(fullm, novar) >> qbase) & 15u;                        // bit h: haplotype h has no variant
+    const short *hl = A.hlen();
+    const bool hap_bad = active && (hl[0] < 0 || hl[1] < 0 || hl[2] < 0 || hl[3] < 0);
+    bool todo = active && !hap_bad;
+    if (active) {
+        const int ai = h;
+        if (hap_bad) {
+            out.status[4 * (int64_t)sc + ai] = ST_BAD;
+            out.aln_score[4 * (int64_t)sc + ai] = -1;
+        } else if (in.rplane_seq == in.ref_seq && ((nv4 >> (ai >> 1)) & 1) && ((nv4 >> (2 + (ai & 1))) & 1)) {
+            out.aln_score[4 * (int64_t)sc + ai] = 0;
+            out.aln_end_plane[4 * (int64_t)sc + ai] = 0;
+            out.aln_beg_plane[4 * (int64_t)sc + ai] = 0;
+            out.status[4 * (int64_t)sc + ai] = 0;
+            todo = false;
+        }
+    }
+    __shared__ int s_wcnt[C::TPB / 32];
+    __shared__ unsigned char s_task[C::TPB];
+    const unsigned tm = __ballot_sync(fullm, todo);
+    if (lane == 0) s_wcnt[tid >> 5] = __popc(tm);
+    __syncthreads();
+    int before = 0, ntask = 0;
+    for (int w = 0; w < C::TPB / 32; w++) { if (w < (tid >> 5)) before += s_wcnt[w]; ntask += s_wcnt[w]; }
+    if (todo) s_task[before + __popc(tm & ((1u << lane) - 1))] = (unsigned char)tid;
+    __syncthreads();
+    if (tid >= ntask) return;
+    // ---- my task: alignment ai of the block's supercluster tq ----
+    const int tq = s_task[tid] >> 2, ai = s_task[tid] & 3;
+    const int tsc = order[blockIdx.x * SPB + tq];
+    SmallArea<C::TL, C::TR> B{smem + tq * D::SC_BYTES};
+    const int tlr = plan[tsc].lr;
     const int qh = ai >> 1, th = 2 + (ai & 1);
     u32 status = 0;
-    const short *hl = A.hlen();
-    if (hl[0] < 0 || hl[1] < 0 || hl[2] < 0 || hl[3] < 0) {
-        out.status[4 * (int64_t)sc + ai] = ST_BAD;
-        out.aln_score[4 * (int64_t)sc + ai] = -1;
-        return;
-    }
-    Hap<int8_t> q{hl[qh], A.str(qh), A.flg(qh), A.ptr(qh), A.ins(qh)};
-    Hap<int8_t> t{hl[th], A.str(th), A.flg(th), A.ptr(th), A.ins(th)};
-    QMaps<int8_t> qm{A.rptr(qh), A.rflg(qh), A.toQ(qh), A.toR(qh)};
-    const AlnLayout<int> L = make_layout<int, 2, true>(q.len + lr, t.len, lr);
+    const short *thl = B.hlen();
+    Hap<int8_t> q{thl[qh], B.str(qh), B.flg(qh), B.ptr(qh), B.ins(qh)};
+    Hap<int8_t> t{thl[th], B.str(th), B.flg(th), B.ptr(th), B.ins(th)};
+    QMaps<int8_t> qm{B.rptr(qh), B.rflg(qh), B.toQ(qh), B.toR(qh)};
+    const AlnLayout<int> L = make_layout<int, 2, true>(q.len + tlr, t.len, tlr);
 
     int score, end_plane;
-    forward_scalar<SMemIL, 2, int8_t>(mem, L, q, qm, t, A.rseq(), lr, score, end_plane);
-    const int beg_plane = backward_scalar<SMemIL, 2, int8_t>(mem, L, q, qm, t, A.rseq(), lr, end_plane, status);
-    PFScalar<SMemIL> pfr{&mem, L.oPF, q.len + lr, q.len};
-    walk_credit<SMemIL, 2, int8_t>(mem, L, pfr, q, qm, t, A.rseq(), lr, beg_plane, end_plane,
-                                   in, out, sc, ai, status);
-    out.aln_score[4 * (int64_t)sc + ai] = score;
-    out.aln_end_plane[4 * (int64_t)sc + ai] = (u8)end_plane;
-    out.aln_beg_plane[4 * (int64_t)sc + ai] = (u8)beg_plane;
-    out.status[4 * (int64_t)sc + ai] = status;
+    forward_scalar<SMemIL, 2, int8_t>(mem, L, q, qm, t, B.rseq(), tlr, score, end_plane);
+    const int beg_plane = backward_scalar<SMemIL, 2, int8_t>(mem, L, q, qm, t, B.rseq(), tlr, end_plane, status);
+    PFScalar<SMemIL> pfr{&mem, L.oPF, q.len + tlr, q.len};
+    walk_credit<SMemIL, 2, int8_t>(mem, L, pfr, q, qm, t, B.rseq(), tlr, beg_plane, end_plane,
+                                   in, out, tsc, ai, status);
+    out.aln_score[4 * (int64_t)tsc + ai] = score;
+    out.aln_end_plane[4 * (int64_t)tsc + ai] = (u8)end_plane;
+    out.aln_beg_plane[4 * (int64_t)tsc + ai] = (u8)beg_plane;
+    out.status[4 * (int64_t)tsc + ai] = status;
 }
 
 
