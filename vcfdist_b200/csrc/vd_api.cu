@@ -87,6 +87,7 @@ struct vd_handle {
     int use_hom = 1;                // VD_HOM=0: homozygous superclusters run all four alignments (testing)
     int use_band = 1;               // VD_BAND=0: no banded warp kernels, every long alignment goes to the dense block kernels (testing)
     int use_wsc = 1;                // VD_WSC=0: mid-size superclusters go to the HBM-slab path instead of the warp kernel
+    int walk_wpw = 0;               // VD_WALK_WPW: alignments per warp in the long path's walk kernels (0 = by their number)
     int wsc_split = 1;              // VD_WSC_SPLIT=0: the fused warp kernels instead of expansion / sweeps / walk as separate launches
     // staged input / output (vd_run)
     struct Stage {                  // one of the staging sets of the host-buffer pipeline
@@ -143,10 +144,12 @@ extern "C" int vd_create(int device, int64_t scratch_bytes, vd_handle **out) {
     // so it is off by default.
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-    if (!(getenv("VD_PRIO") && atoi(getenv("VD_PRIO")))) prio_hi = prio_lo;
+    const int prio_mode = getenv("VD_PRIO") ? atoi(getenv("VD_PRIO")) : 0;      // 2: only the side streams of the wide rungs (few, long alignments)
+    const int prio_top = prio_hi;
+    if (prio_mode != 1) prio_hi = prio_lo;
     for (auto &e : h->ev) cok &= cudaEventCreate(&e) == cudaSuccess;
     for (int c = 0; c < N_WCLS; c++) {
-        cok &= cudaStreamCreateWithPriority(&h->side[c], cudaStreamNonBlocking, prio_hi) == cudaSuccess;
+        cok &= cudaStreamCreateWithPriority(&h->side[c], cudaStreamNonBlocking, (prio_mode == 2 && c >= 2 && c < N_RUNG) ? prio_top : prio_hi) == cudaSuccess;
         for (auto &e : h->sev[c]) cok &= cudaEventCreate(&e) == cudaSuccess;
     }
     for (auto &w : h->work) {
@@ -174,6 +177,7 @@ extern "C" int vd_create(int device, int64_t scratch_bytes, vd_handle **out) {
     if (const char *v = getenv("VD_WSC")) h->use_wsc = atoi(v);
     if (const char *v = getenv("VD_BAND")) h->use_band = atoi(v);
     if (const char *v = getenv("VD_WSC_SPLIT")) h->wsc_split = atoi(v);
+    if (const char *v = getenv("VD_WALK_WPW")) { const int w = atoi(v); h->walk_wpw = (w == 1 || w == 2 || w == 4 || w == 8 || w == 16 || w == 32) ? w : 0; }
     if (const char *v = getenv("VD_SERIAL")) h->serial = atoi(v);
     if (const char *v = getenv("VD_HOM")) h->use_hom = atoi(v);
     if (const char *v = getenv("VD_RAMP")) h->ramp = atoi(v);
@@ -446,6 +450,9 @@ static int chunk_exec(vd_handle *h, Work &W) {
                 CK(h->dense_bytes.ensure(8 * (size_t)(total_items + 1)));
                 CK(h->dense_off.ensure(8 * (size_t)(total_items + 1)));
                 WaveArgs WA{in, out, plan, list, i0, offs, (u8 *)h->slab.p, items, bstate, nullptr, nullptr};
+                // alignments per warp in the walk kernels (VD_WALK_WPW): one - measured on the SV workload, 41 k long alignments
+                // per step, 2 .. 32 per warp change nothing: the walks' time is the longest walk, not their number
+                const int wpw = h->walk_wpw > 0 ? h->walk_wpw : 1;
                 CK(cudaEventRecord(h->ev[4], st));
                 // ---- banded warp kernels (vd_band.cuh): rung K = 4, 8, 16; the backward sweep and the walk of a rung
                 //      run beside the forward sweep of the next one ----
@@ -462,7 +469,7 @@ static int chunk_exec(vd_handle *h, Work &W) {
                         CK(cudaEventRecord(h->sev[r][1], bs));
                         band_launch_rung(bs, r, WA, total_items, bstate, blb, bhint, false, 0, wi);
                         CK(cudaEventRecord(h->sev[r][2], bs));
-                        VD_LAUNCH(band_walk_kernel, (total_items + 3) / 4, 128, 0, bs, WA, total_items, bstate, band_rung_k(r));
+                        VD_LAUNCH(band_walk_kernel, (total_items + 4 * wpw - 1) / (4 * wpw), 128, 0, bs, WA, total_items, bstate, band_rung_k(r), wpw);
                         CK(cudaEventRecord(h->sev[r][3], bs));
                         S.n_launches += 3;
                     }
@@ -470,7 +477,7 @@ static int chunk_exec(vd_handle *h, Work &W) {
                     for (int r = 2; r < N_RUNG; r++) {
                         band_launch_rung(st, r, WA, total_items, bstate, blb, bhint, true, 0, wi);
                         band_launch_rung(st, r, WA, total_items, bstate, blb, bhint, false, 0, wi);
-                        VD_LAUNCH(band_walk_kernel, (total_items + 3) / 4, 128, 0, st, WA, total_items, bstate, band_rung_k(r));
+                        VD_LAUNCH(band_walk_kernel, (total_items + 4 * wpw - 1) / (4 * wpw), 128, 0, st, WA, total_items, bstate, band_rung_k(r), wpw);
                         S.n_launches += 3;
                     }
                 }
@@ -534,7 +541,7 @@ static int chunk_exec(vd_handle *h, Work &W) {
                                     h->banded_fwd ? (int *)h->need_dense.p : nullptr, h->banded_bwd);
                         CK(cudaEventRecord(h->sev[c][2], ss));
                         // walk + credit of this class right behind its backward sweep, on the same stream
-                        VD_LAUNCH(wave_walk_kernel, (hwi.count[c] + 3) / 4, 128, 0, ss, WA, cb.b[c], hwi.count[c]);
+                        VD_LAUNCH(wave_walk_kernel, (hwi.count[c] + 4 * wpw - 1) / (4 * wpw), 128, 0, ss, WA, cb.b[c], hwi.count[c], wpw);
                         CK(cudaEventRecord(h->sev[c][3], ss));
                         if (ss != st) CK(cudaStreamWaitEvent(st, h->sev[c][3], 0));
                         S.n_launches += 3;

@@ -696,10 +696,13 @@ struct PFBand {
     }
 };
 
-// walk + credit of the alignments the band kernels solved: one alignment per warp (lane 0 walks)
-__global__ void band_walk_kernel(WaveArgs A, int n_items, int *state, int only_k) {
-    const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (g >= n_items || (threadIdx.x & 31)) return;
+// walk + credit of the alignments the band kernels solved: wpw alignments per warp, on lanes 32/wpw apart (one per warp keeps
+// walks of very different lengths from holding each other up but leaves 31 lanes idle: with tens of thousands of
+// alignments the kernel is then bound by the number of resident warps)
+__global__ void band_walk_kernel(WaveArgs A, int n_items, int *state, int only_k, int wpw) {
+    const int lane = threadIdx.x & 31, lpi = 32 / wpw;
+    const int g = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * wpw + lane / lpi;
+    if (g >= n_items || (lane % lpi)) return;
     const int idx = n_items - 1 - g;
     const int K = state[idx];
     if (K <= 0 || K != only_k) return;                       // not solved, another rung's, or walked already (BAND_DONE)

@@ -1629,9 +1629,10 @@ struct PFWave {
 // one thread per alignment: walk + credit
 // One alignment per WARP (lane 0 walks): walks of very different lengths and move mixes in one warp
 // serialise each other's branches, and there are only a few thousand long alignments in a batch.
-__global__ void wave_walk_kernel(WaveArgs A, int item0, int n_items) {
-    const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (g >= n_items || (threadIdx.x & 31)) return;
+__global__ void wave_walk_kernel(WaveArgs A, int item0, int n_items, int wpw) {
+    const int lane = threadIdx.x & 31, lpi = 32 / wpw;                 // wpw alignments per warp (see band_walk_kernel)
+    const int g = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * wpw + lane / lpi;
+    if (g >= n_items || (lane % lpi)) return;
     if (A.bstate && A.bstate[item0 + g] > 0) return;         // walked by band_walk_kernel
     const int item = A.items[item0 + g];
     const int e = item >> 2, ai = item & 3;
