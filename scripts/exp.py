@@ -19,6 +19,8 @@ for i in range(reps):
     if i == reps - 1 and os.environ.get("TRACE"): os.environ["VD_TRACE"] = "1"
     t = time.time(); e.run(b); dt = time.time() - t
     st = e.stats()
+    if os.environ.get("ALLREPS") and i > 0:
+        print(f"  rep {i}: wall {dt*1e3:.1f} dev {st['ms_total']:.1f} longwall {st['ms_long_wall']:.1f}", flush=True)
     if i == reps - 1:
         print(f"[{wl} {n} {tag}] wall {dt*1e3:.1f} ms dev {st['ms_total']:.2f} plan {st['ms_plan']:.2f} small {st['ms_short']:.2f} "
               f"[{' '.join('%.2f' % x for x in st['ms_small'])}] n_small {st['n_small']} fwd {st['ms_long_fwd']:.2f} bwd {st['ms_long_bwd']:.2f} walk {st['ms_long_walk']:.2f} "

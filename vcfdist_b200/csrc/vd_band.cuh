@@ -172,6 +172,13 @@ template <int K> struct BandCfg {
     static constexpr int SMEM = 16 * W + 32 * R + 1024 + 16 * NS;
 };
 
+// resident blocks per SM the register allocation must allow, by rung: the narrow rungs take tens of thousands of alignments
+// (bound by the number of resident warps), the wide ones a few hundred long ones (bound by one warp's column step)
+#ifndef VD_BAND_MINB_NARROW
+#define VD_BAND_MINB_NARROW 1
+#endif
+constexpr int band_minb(int K) { return K <= 2 ? VD_BAND_MINB_NARROW : 1; }
+
 // ------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------
@@ -181,7 +188,7 @@ template <int K> struct BandCfg {
 // exact_hint: take only the items whose hint IS this rung (first round, all rungs side by side); otherwise
 // every pending item whose hint is not above it (second round, rung after rung).
 template <int K>
-__global__ void __launch_bounds__(32 * BAND_WARPS) band_fwd_kernel(WaveArgs A, int n_items, int *state, const int *lbound, int *hint,
+__global__ void __launch_bounds__(32 * BAND_WARPS, band_minb(K)) band_fwd_kernel(WaveArgs A, int n_items, int *state, const int *lbound, int *hint,
                                                                    int rung, int exact_hint, WaveItems *wi) {
     VD_DYN_SHARED(smem_raw);
     typedef BandCfg<K> C;
@@ -434,7 +441,7 @@ __global__ void __launch_bounds__(32 * BAND_WARPS) band_fwd_kernel(WaveArgs A, i
 // backward
 // ------------------------------------------------------------------------------------------
 template <int K>
-__global__ void __launch_bounds__(32 * BAND_WARPS) band_bwd_kernel(WaveArgs A, int n_items, const int *state) {
+__global__ void __launch_bounds__(32 * BAND_WARPS, band_minb(K)) band_bwd_kernel(WaveArgs A, int n_items, const int *state) {
     VD_DYN_SHARED(smem_raw);
     typedef BandCfg<K> C;
     constexpr unsigned FULL = 0xffffffffu;
