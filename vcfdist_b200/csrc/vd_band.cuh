@@ -34,7 +34,12 @@
 
 namespace vd {
 
-constexpr int BAND_WARPS = 4;                                  // alignments per block (one warp each)
+#ifndef VD_BAND_WARPS
+#define VD_BAND_WARPS 1
+#endif
+constexpr int BAND_WARPS = VD_BAND_WARPS;                      // alignments per block (one warp each).  One: a block's shared memory
+// (43 KB per warp at K = 16) is held as long as its slowest warp runs, and with four warps a block of the wide rungs - typically
+// one live alignment and three that are not this rung's - kept a whole SM's shared memory from the other rungs' blocks
 constexpr int N_RUNG = 5;
 inline int band_rung_k(int r) { const int v[N_RUNG] = {1, 2, 4, 8, 16}; return v[r]; }
 __host__ __device__ inline int band_rung_tau(int r) { const int v[N_RUNG] = {14, 30, 60, 120, 240}; return v[r]; }
