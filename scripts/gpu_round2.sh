@@ -20,7 +20,7 @@ for w in $what; do
                  --log-file "$out/launches_wgs_sv.csv" python scripts/exp.py wgs_sv 400000 3 > "$out/launches_wgs_sv.log" 2>&1
                python scripts/launch_summary.py "$out/launches_wgs.csv" "$out/launches_wgs_sv.csv" > "$out/launch_summary.txt" 2>&1
                echo "launches rc=$?" ;;
-    full_wsc)  VD_SERIAL=1 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'wsc_' -s 27 -c 9 \
+    full_wsc)  VD_SERIAL=1 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'wsc_' -s 36 -c 12 \
                  -f -o "$out/prof_wsc" python bench.py --steps 1 --warmup 3 $Q > "$out/prof_wsc.log" 2>&1; echo "full_wsc rc=$?"
                ncu -i "$out/prof_wsc.ncu-rep" --page raw --csv > "$out/prof_wsc_raw.csv" 2>/dev/null
                python scripts/ncu_summary.py "$out/prof_wsc_raw.csv" > "$out/prof_wsc_summary.txt" 2>&1
