@@ -27,10 +27,8 @@ FILES = ["precision-recall.tsv", "precision-recall-summary.tsv", "query.tsv", "t
 
 def run(binary, q, t, fa, out, extra):
     os.makedirs(out, exist_ok=True)
-    # VD_GPU_CLUSTER_WAIT: every clustering call goes to the GPU (by default the calls that arrive before CUDA is up run the
-    # reference's own code)
     r = subprocess.run([binary, q, t, fa, "-p", out + "/", "-v", "0", *extra],
-                       capture_output=True, text=True, cwd=out, timeout=900, env=dict(os.environ, VD_GPU_CLUSTER_WAIT="1"))
+                       capture_output=True, text=True, cwd=out, timeout=900)
     assert r.returncode == 0, r.stderr[-2000:]
     return r
 

@@ -58,11 +58,16 @@ __global__ void __launch_bounds__(128) wf_kernel(WfBatch B) {
     int score = 0, slot = 0, result = -1;
     if (lane == 0) *wf(WF_M, slot, qlen - 1) = -1;                                    // :2166 / :1528: diagonal k = 0, before the first base
     __syncwarp();
+    // Diagonals any wavefront has reached so far: [dlo, dhi].  A score step reaches at most one more on either side (its
+    // sources are the same diagonal and its two neighbours at earlier scores), everything outside still holds NONE from the
+    // fill above - so the passes below run over this range and not over all |query| + |truth| - 1 diagonals: a structural
+    // variant's cluster has thousands of diagonals and hundreds of score steps, of which a step touches a few dozen.
+    int dlo = qlen - 1, dhi = qlen - 1;
     bool done = false;
     for (;;) {
         // gaps are left for free at the score they were reached with (:2171-2184, :1533-1547); not in the reversed problem
         if (!reverse)
-            for (int d = lane; d < nd; d += 32) {
+            for (int d = dlo + lane; d <= dhi; d += 32) {
                 const int k = d + 1 - qlen;
                 int m = *wf(WF_M, slot, d);
 #pragma unroll
@@ -74,11 +79,11 @@ __global__ void __launch_bounds__(128) wf_kernel(WfBatch B) {
             }
         __syncwarp();
         // free extension along matches, then the exits, diagonals in ascending order (:2187-2212, :1550-1568)
-        for (int d0 = 0; d0 < nd && !done; d0 += 32) {
+        for (int d0 = dlo; d0 <= dhi && !done; d0 += 32) {
             const int d = d0 + lane;
             bool hit = false;
             int res = -1;
-            if (d < nd) {
+            if (d <= dhi) {
                 int q = *wf(WF_M, slot, d);
                 const int k = d + 1 - qlen;
                 while ((!reach || k != main_diag || q + 1 < stop_q) && q != WF_NONE && k + q >= -1 &&
@@ -99,7 +104,8 @@ __global__ void __launch_bounds__(128) wf_kernel(WfBatch B) {
         // next score (:2225-2311, :1583-1650)
         score++;
         slot = slot + 1 == ring ? 0 : slot + 1;
-        for (int d = lane; d < nd; d += 32) {
+        dlo = max(dlo - 1, 0); dhi = min(dhi + 1, nd - 1);
+        for (int d = dlo + lane; d <= dhi; d += 32) {
             const int k = d + 1 - qlen;
             // :2228-2232 clears I and D only, the M wavefront of the slot is overwritten through >= tests; wf_swg_align
             // starts every wavefront of a new score empty (:1583-1587)
@@ -202,8 +208,9 @@ __global__ void __launch_bounds__(128) wf_cigar_kernel(WfCigarBatch B) {
     __syncwarp();
     if (lane == 0) { OFF(0, WF_M, qlen - 1) = -1; FLG(0, WF_M, qlen - 1) = WFC_MAT; }                  // :1528-1529
     __syncwarp();
+    int dlo = qlen - 1, dhi = qlen - 1;                      // diagonals reached so far (see wf_kernel): the passes run over these only
     for (int score = 0;; score++) {
-        for (int d = lane; d < nd; d += 32) {                                                             // :1533-1547
+        for (int d = dlo + lane; d <= dhi; d += 32) {                                                     // :1533-1547
             const int k = d + 1 - qlen;
 #pragma unroll
             for (int kind = WF_I; kind <= WF_D; kind++) {
@@ -220,7 +227,8 @@ __global__ void __launch_bounds__(128) wf_cigar_kernel(WfCigarBatch B) {
         __syncwarp();
         if (score == final_score) break;                     // the score pass found the end at this score
         const int s1 = score + 1;
-        for (int d = lane; d < nd; d += 32) {
+        dlo = max(dlo - 1, 0); dhi = min(dhi + 1, nd - 1);
+        for (int d = dlo + lane; d <= dhi; d += 32) {
             const int k = d + 1 - qlen;
             if (s1 - x >= 0) {                                                                            // :1592-1600
                 const int pv = OFF(s1 - x, WF_M, d);

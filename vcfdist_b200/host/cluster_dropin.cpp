@@ -16,10 +16,10 @@
 // (contig, haplotype): every caller takes a handle of its own from the runtime's pool.
 //
 // Clustering is the first stage after the VCFs are read, so on a small input it starts before CUDA is up (0.5-4 s on these
-// boxes).  A call that arrives while the runtime is still starting runs the reference's own definition (linked in under
-// the name ref_wf_swg_cluster) instead of waiting: same results - that is what the parity tests check - and the GPU takes
-// over as soon as it is there.  VD_GPU_CLUSTER=0 keeps the stage on the CPU altogether, VD_GPU_CLUSTER_WAIT=1 makes every
-// call wait for the GPU (tests).  This is not a fallback of the precision/recall path, which has none.
+// boxes) and the first calls wait for it.  VD_GPU_CLUSTER_NOWAIT=1: a call that arrives while the runtime is still starting
+// runs the reference's own definition (linked in under the name ref_wf_swg_cluster) instead of waiting - same results, that
+// is what the parity tests check; VD_GPU_CLUSTER=0 keeps the stage on the CPU altogether.  Neither is a fallback of the
+// precision/recall path, which has none.
 #include <algorithm>
 #include <chrono>
 #include <climits>
@@ -105,8 +105,8 @@ void ref_wf_swg_cluster(variantData *vcf, int ctg_idx, int hap, int sub, int ope
 
 void wf_swg_cluster(variantData *vcf, int ctg_idx, int hap, int sub, int open, int extend) {
     {
-        const char *on = std::getenv("VD_GPU_CLUSTER"), *wait = std::getenv("VD_GPU_CLUSTER_WAIT");
-        if ((on && !std::atoi(on)) || (!vdhost::runtime().ready && !(wait && std::atoi(wait))))
+        const char *on = std::getenv("VD_GPU_CLUSTER"), *nowait = std::getenv("VD_GPU_CLUSTER_NOWAIT");
+        if ((on && !std::atoi(on)) || (!vdhost::runtime().ready && nowait && std::atoi(nowait)))
             return ref_wf_swg_cluster(vcf, ctg_idx, hap, sub, open, extend);
     }
     const std::string ctg = vcf->contigs[ctg_idx];
