@@ -106,7 +106,7 @@ void ref_wf_swg_cluster(variantData *vcf, int ctg_idx, int hap, int sub, int ope
 void wf_swg_cluster(variantData *vcf, int ctg_idx, int hap, int sub, int open, int extend) {
     {
         const char *on = std::getenv("VD_GPU_CLUSTER"), *nowait = std::getenv("VD_GPU_CLUSTER_NOWAIT");
-        if ((on && !std::atoi(on)) || (!vdhost::runtime().ready && nowait && std::atoi(nowait)))
+        if ((on && !std::atoi(on)) || (nowait && std::atoi(nowait) && !vdhost::runtime().reached(1)))
             return ref_wf_swg_cluster(vcf, ctg_idx, hap, sub, open, extend);
     }
     const std::string ctg = vcf->contigs[ctg_idx];

@@ -22,25 +22,35 @@ struct Runtime {
     int rc = VD_OK, device = 0;
     uint8_t *arena = nullptr;
     int64_t arena_cap = 0;
-    bool tried = false;
-    std::atomic<bool> ready{false};             // init() has finished (successfully or not)
     double init_ms[3] = {0, 0, 0};              // vd_create, page-locking the arena, warm-up batch
+    // start-up stages: 1 = the handle exists (or could not be created), 2 = arena page-locked and warm-up batch done.
+    // The clustering stage only needs the first; the precision/recall stage, which uses the arena, waits for the second.
+    std::mutex st_mu;
+    std::condition_variable st_cv;
+    int stage = 0;
+    bool started = false;
+    void set_stage(int s) { { std::lock_guard<std::mutex> lk(st_mu); stage = s; } st_cv.notify_all(); }
+    void wait_stage(int s) { std::unique_lock<std::mutex> lk(st_mu); st_cv.wait(lk, [&] { return stage >= s; }); }
+    bool reached(int s) { std::lock_guard<std::mutex> lk(st_mu); return stage >= s; }
     void init() {
         using clk = std::chrono::steady_clock;
         auto ms_since = [](clk::time_point t) { return std::chrono::duration<double, std::milli>(clk::now() - t).count(); };
         auto t0 = clk::now();
-        tried = true;
         if (const char *d = std::getenv("VD_DEVICE")) device = std::atoi(d);
         rc = vd_create(device, 0, &h);
-        if (rc != VD_OK) { ready = true; return; }
+        if (rc != VD_OK) { set_stage(2); return; }
         init_ms[0] = ms_since(t0); t0 = clk::now();
+        { std::lock_guard<std::mutex> lk(pool_mu); main_busy = true; }      // the warm-up batch below runs on the first handle
+        set_stage(1);
         int64_t mb = 1024;
         if (const char *m = std::getenv("VD_PIN_MB")) mb = std::atoll(m);
         if (mb > 0) { arena = (uint8_t *)vd_host_alloc(mb << 20); arena_cap = arena ? (mb << 20) : 0; }
         init_ms[1] = ms_since(t0); t0 = clk::now();
         if (!std::getenv("VD_NO_WARMUP_BATCH")) warm_up();
         init_ms[2] = ms_since(t0);
-        ready = true;
+        { std::lock_guard<std::mutex> lk(pool_mu); main_busy = false; }
+        pool_cv.notify_all();
+        set_stage(2);
     }
     // A few synthetic superclusters of every size class through the whole path, so that the kernels' code is on the
     // GPU and the handle's work buffers exist before the real batch arrives (CUDA loads a kernel at its first launch).
@@ -81,14 +91,11 @@ struct Runtime {
         vd_packed_out pk{a16.data(), pl.data(), a16.data() + 4 * n_sc, v16.data(), v16.data() + 2 * n_var, v16.data() + 4 * n_var, cq.data()};
         vd_run_packed(h, &in, &pk);          // result and return code are of no interest
     }
-    Runtime() { if (!std::getenv("VD_NO_WARM")) th = std::thread([this] { init(); }); }
-    std::mutex mu;                              // get() may be called from several host threads (the clustering stage)
-    vd_handle *get() {
-        std::lock_guard<std::mutex> lk(mu);
-        if (th.joinable()) th.join();
-        if (!tried) init();
-        return h;
+    void start() {
+        std::lock_guard<std::mutex> lk(st_mu);
+        if (!started) { started = true; th = std::thread([this] { init(); }); }
     }
+    Runtime() { if (!std::getenv("VD_NO_WARM")) start(); }
     // A handle serves one host thread at a time.  The reference calls its clustering stage from several threads at once
     // (one per contig and haplotype): each takes a handle of its own from a small pool (the first one plus up to
     // VD_HANDLES - 1 more, created on demand), so that their batches run side by side on the GPU.
@@ -98,7 +105,9 @@ struct Runtime {
     bool main_busy = false;
     int n_extra = 0, max_extra = 7;
     vd_handle *acquire() {
-        vd_handle *first = get();
+        start();
+        wait_stage(1);
+        vd_handle *first = h;
         if (!first) return nullptr;
         if (const char *m = std::getenv("VD_HANDLES")) max_extra = std::atoi(m) - 1;
         std::unique_lock<std::mutex> lk(pool_mu);

@@ -438,7 +438,9 @@ void precision_recall_threads_wrapper(
     }
 #else
     auto t0 = clk::now();
-    vdhost::Runtime::Lease lease(vdhost::runtime());                // normally ready long before this point
+    vdhost::runtime().start();
+    vdhost::runtime().wait_stage(2);                                // handle, page-locked arena, warm-up: normally done long before
+    vdhost::Runtime::Lease lease(vdhost::runtime());
     vd_handle *h = lease.h;
     if (!h) ERROR("vcfdist_b200: cannot initialise CUDA device %d (code %d); "
                   "there is no CPU fallback for the precision/recall path", vdhost::runtime().device, vdhost::runtime().rc);
