@@ -1,0 +1,15 @@
+# CLI with the default (biwfa) clustering on an SV-bearing synthetic pair: reference vs drop-ins.  usage: cli_sv_cluster.sh [contig_len] [sv_max]
+L=${1:-500000}; SV=${2:-1500}
+mkdir -p /tmp/vs; python - <<P
+import sys; sys.path.insert(0,'.')
+from workloads import vcfgen
+print(vcfgen.generate('/tmp/vs/in', seed=5, contig_len=$L, n_contigs=2, sv_rate=0.03, sv_max=$SV))
+P
+for b in vcfdist_b200cli vcfdist_ref; do
+  mkdir -p /tmp/vs/$b; cd /tmp/vs/$b
+  echo "== $b"; SECONDS=0
+  VD_DROPIN_TIMES=1 timeout 900 $GRAFT_REPO_ROOT/oracle/_ref/$b /tmp/vs/in/query.vcf /tmp/vs/in/truth.vcf /tmp/vs/in/ref.fa -p /tmp/vs/$b/ -v 1 -t 16 2>&1 | grep -E "\[[0-9]\] |ERROR|GPU clustering"
+  echo "wall ${SECONDS} s"
+  cd $GRAFT_REPO_ROOT
+done
+for f in superclusters.tsv precision-recall-summary.tsv query.tsv; do cmp /tmp/vs/vcfdist_ref/$f /tmp/vs/vcfdist_b200cli/$f && echo "$f identical"; done

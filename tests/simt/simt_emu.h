@@ -87,6 +87,7 @@ struct Ctx {
     size_t dyn_cap = 256 * 1024;
     // block barrier
     int bar_arrived = 0, bar_gen = 0, alive = 0;
+    int bar_or[3] = {0, 0, 0};
     unsigned long progress = 0;
     unsigned long launches = 0;
 };
@@ -291,6 +292,18 @@ inline void __syncthreads() {
     c.bar_arrived++;
     if (c.bar_arrived >= c.alive) { c.bar_arrived = 0; c.bar_gen++; }
     else while (c.bar_gen == g) simt::yield();
+}
+inline int __syncthreads_or(int pred) {
+    // a block-wide flag between two barriers.  Every thread enters with the same barrier generation; the flag of generation
+    // g mod 3 cannot be set again before everybody has cleared it (that takes three more barriers).
+    simt::Ctx &c = simt::ctx();
+    const int idx = c.bar_gen % 3;
+    if (pred) c.bar_or[idx] = 1;
+    __syncthreads();
+    const int r = c.bar_or[idx];
+    __syncthreads();
+    c.bar_or[idx] = 0;
+    return r;
 }
 inline void __threadfence() {}
 inline void __threadfence_block() {}

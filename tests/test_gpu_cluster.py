@@ -1,5 +1,5 @@
 """SURVEY 8f-1 on the GPU: the affine-gap wavefront kernels of the cluster-growing stage (vd_wf_batch:
-wf_swg_max_reach and the score of wf_swg_align, one warp per problem) and the batched cluster-growing driver
+wf_swg_max_reach and the score of wf_swg_align, a warp or a block per problem) and the batched cluster-growing driver
 over them (vcfdist_b200.cluster.wf_swg_cluster), through the C-ABI, against the known answers recorded from the
 reference's own object code (tests/golden/reach_kat.npz, cluster_kat.json), the C restatement and - where the
 reference objects travelled to the box - the reference itself on fresh random cases."""
@@ -75,6 +75,54 @@ def test_reach_and_score_random_cases(engine):
         cs = [pairs[i] for i in idx]
         got = engine.wf_batch(1, [c[0] for c in cs], [c[1] for c in cs], x, o, e)
         assert (got == np.array([checkers.swg_score_oracle(*c) for c in cs])).all(), (x, o, e)
+
+
+def sv_like_cases(rng, n):
+    """Wide problems: a window of one to three thousand bases whose query carries one long insertion or deletion
+    (and a few small edits), forwards and reversed - the reached range grows to hundreds of diagonals."""
+    out = []
+    for _ in range(n):
+        tlen = int(rng.integers(900, 2600))
+        truth = bytes(rng.choice(list(b"ACGT"), tlen).tolist())
+        at = int(rng.integers(50, tlen - 400))
+        size = int(rng.integers(150, 700))
+        if rng.random() < 0.5:
+            q = truth[:at] + bytes(rng.choice(list(b"ACGT"), size).tolist()) + truth[at:]; main_diag = -size
+        else:
+            q = truth[:at] + truth[at + size:]; main_diag = size
+        q = bytearray(q)
+        for _ in range(int(rng.integers(0, 4))):
+            j = int(rng.integers(0, len(q))); q[j] = b"ACGT"[(b"ACGT".index(q[j]) + 1) % 4]
+        q = bytes(q)
+        x, o, e = [(3, 2, 1), (2, 3, 1), (1, 1, 1), (4, 6, 2)][int(rng.integers(0, 4))]
+        rev = int(rng.random() < 0.5)
+        if rev:
+            q, truth = q[::-1], truth[::-1]
+        budget = int(rng.integers(20, o + e * size + 40))
+        out.append((q, truth, main_diag, int(rng.integers(0, len(q))), budget, x, o, e, rev))
+    return out
+
+
+@pytest.mark.parametrize("block_min", [1, 40, 100000])
+def test_block_and_warp_forms_agree(monkeypatch, block_min):
+    """vd_wf_batch gives a problem a warp or a whole block by the width its wavefront can reach (VD_WF_BLOCK_MIN):
+    all through the block form, mixed, all through the warp form - same answers as the C restatement, on cluster-sized
+    and on structural-variant-sized problems, reach and score."""
+    monkeypatch.setenv("VD_WF_BLOCK_MIN", str(block_min))
+    e = capi.Engine(0)
+    rng = np.random.default_rng(23)
+    cases = [TR.random_case(rng) for _ in range(600)] + sv_like_cases(rng, 60)
+    for (x, o, ex), idx in by_penalties(cases, lambda c: c[5:8]).items():
+        cs = [cases[i] for i in idx]
+        got = e.wf_batch(0, [c[0] for c in cs], [c[1] for c in cs], x, o, ex, [c[2] for c in cs], [c[3] for c in cs],
+                         [c[4] for c in cs], [int(c[8]) for c in cs])
+        assert (got == np.array([checkers.reach_oracle(*c) for c in cs])).all(), (x, o, ex)
+    pairs = [TR.random_pair(rng) for _ in range(600)] + [(c[0], c[1], c[5], c[6], c[7]) for c in sv_like_cases(rng, 12)]
+    for (x, o, ex), idx in by_penalties(pairs, lambda c: c[2:5]).items():
+        cs = [pairs[i] for i in idx]
+        got = e.wf_batch(1, [c[0] for c in cs], [c[1] for c in cs], x, o, ex)
+        assert (got == np.array([checkers.swg_score_oracle(*c) for c in cs])).all(), (x, o, ex)
+    e.close()
 
 
 def test_cluster_growth_known_answers(engine):

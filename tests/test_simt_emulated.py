@@ -61,10 +61,13 @@ def test_dense_block_kernels_alone():
     assert st["n_dense"] > 0
 
 
-def test_cluster_wavefront_kernels_and_driver():
-    """the reach / score wavefront kernel (one warp per problem) and the batched cluster-growing
-    driver over it, against the recorded reference answers."""
+@pytest.mark.parametrize("block_min", [None, "1"])
+def test_cluster_wavefront_kernels_and_driver(monkeypatch, block_min):
+    """the reach / score wavefront kernel (a warp per problem; with VD_WF_BLOCK_MIN=1 a block per problem)
+    and the batched cluster-growing driver over it, against the recorded reference answers."""
     import json
+    if block_min:
+        monkeypatch.setenv("VD_WF_BLOCK_MIN", block_min)
     from vcfdist_b200 import cluster
     from conftest import ROOT
     z = np.load(os.path.join(ROOT, "tests", "golden", "reach_kat.npz"), allow_pickle=False)

@@ -87,6 +87,8 @@ struct vd_handle {
     int use_hom = 1;                // VD_HOM=0: homozygous superclusters run all four alignments (testing)
     int use_band = 1;               // VD_BAND=0: no banded warp kernels, every long alignment goes to the dense block kernels (testing)
     int use_wsc = 1;                // VD_WSC=0: mid-size superclusters go to the HBM-slab path instead of the warp kernel
+    int wf_block_min = 384;         // VD_WF_BLOCK_MIN: wavefront width from which a clustering / --distance problem gets a block, not a warp
+    cudaEvent_t wf_ev[2] = {};
     int walk_wpw = 0;               // VD_WALK_WPW: alignments per warp in the long path's walk kernels (0 = by their number)
     int wsc_split = 1;              // VD_WSC_SPLIT=0: the fused warp kernels instead of expansion / sweeps / walk as separate launches
     // staged input / output (vd_run)
@@ -148,6 +150,7 @@ extern "C" int vd_create(int device, int64_t scratch_bytes, vd_handle **out) {
     const int prio_top = prio_hi;
     if (prio_mode != 1) prio_hi = prio_lo;
     for (auto &e : h->ev) cok &= cudaEventCreate(&e) == cudaSuccess;
+    for (auto &e : h->wf_ev) cok &= cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
     for (int c = 0; c < N_WCLS; c++) {
         cok &= cudaStreamCreateWithPriority(&h->side[c], cudaStreamNonBlocking, (prio_mode == 2 && c >= 2 && c < N_RUNG) ? prio_top : prio_hi) == cudaSuccess;
         for (auto &e : h->sev[c]) cok &= cudaEventCreate(&e) == cudaSuccess;
@@ -177,6 +180,7 @@ extern "C" int vd_create(int device, int64_t scratch_bytes, vd_handle **out) {
     if (const char *v = getenv("VD_WSC")) h->use_wsc = atoi(v);
     if (const char *v = getenv("VD_BAND")) h->use_band = atoi(v);
     if (const char *v = getenv("VD_WSC_SPLIT")) h->wsc_split = atoi(v);
+    if (const char *v = getenv("VD_WF_BLOCK_MIN")) h->wf_block_min = std::max(1, atoi(v));
     if (const char *v = getenv("VD_WALK_WPW")) { const int w = atoi(v); h->walk_wpw = (w == 1 || w == 2 || w == 4 || w == 8 || w == 16 || w == 32) ? w : 0; }
     if (const char *v = getenv("VD_SERIAL")) h->serial = atoi(v);
     if (const char *v = getenv("VD_HOM")) h->use_hom = atoi(v);
@@ -237,6 +241,7 @@ extern "C" void vd_destroy(vd_handle *h) {
     if (h->h_witems) cudaFreeHost(h->h_witems);
     if (h->h_range) cudaFreeHost(h->h_range);
     for (auto &e : h->ev) if (e) cudaEventDestroy(e);
+    for (auto &e : h->wf_ev) if (e) cudaEventDestroy(e);
     for (int c = 0; c < N_WCLS; c++) {
         for (auto &e : h->sev[c]) if (e) cudaEventDestroy(e);
         if (h->side[c]) cudaStreamDestroy(h->side[c]);
@@ -983,7 +988,17 @@ extern "C" int vd_wf_batch(vd_handle *h, int mode, int n, const int64_t *q_off, 
     // one staging block: offsets, strings, per-problem parameters, results
     size_t o_qoff = 0, o_toff = o_qoff + 8 * (size_t)(n + 1), o_soff = o_toff + 8 * (size_t)(n + 1), o_md = o_soff + 8 * (size_t)(n + 1);
     size_t o_mds = o_md + 4 * (size_t)n, o_ms = o_mds + 4 * (size_t)n, o_res = o_ms + 4 * (size_t)n, o_rev = o_res + 4 * (size_t)n;
-    size_t o_q = (o_rev + n + 15) & ~(size_t)15, o_t = (o_q + qb + 15) & ~(size_t)15, total = o_t + tb + 16;
+    size_t o_q = (o_rev + n + 15) & ~(size_t)15, o_t = (o_q + qb + 15) & ~(size_t)15, o_sel = (o_t + tb + 15) & ~(size_t)15;
+    size_t total = o_sel + 4 * (size_t)n + 16;
+    // Problems whose wavefront can grow to wf_block_min diagonals or more get a whole block, the others a warp: sel holds the
+    // warp problems from the front and the block problems from the back.
+    std::vector<int> sel((size_t)n);
+    int n_warp = 0, n_block = 0;
+    for (int i = 0; i < n; i++) {
+        int64_t width = (q_off[i + 1] - q_off[i]) + (t_off[i + 1] - t_off[i]) - 1;
+        if (mode == WF_MODE_REACH) width = std::min<int64_t>(width, 2 * (int64_t)std::max(max_score[i], 0) + 1);
+        if (width >= h->wf_block_min) sel[(size_t)n - 1 - n_block++] = i; else sel[(size_t)n_warp++] = i;
+    }
     CK(h->wf_in.ensure(total));
     CK(h->wf_scratch.ensure(4 * (size_t)soff[n] + 16));
     u8 *d = (u8 *)h->wf_in.p;
@@ -1001,7 +1016,19 @@ extern "C" int vd_wf_batch(vd_handle *h, int mode, int n, const int64_t *q_off, 
     WfBatch B{n, (const int64_t *)(d + o_qoff), (const int64_t *)(d + o_toff), d + o_q, d + o_t, (const int32_t *)(d + o_md),
               (const int32_t *)(d + o_mds), (const int32_t *)(d + o_ms), d + o_rev, (const int64_t *)(d + o_soff), (int32_t *)h->wf_scratch.p,
               (int32_t *)(d + o_res), sub, open, extend, mode};
-    VD_LAUNCH(wf_kernel, (n + 3) / 4, 128, 0, st, B);
+    CK(cudaMemcpyAsync(d + o_sel, sel.data(), 4 * (size_t)n, cudaMemcpyHostToDevice, st));
+    const int *d_sel = (const int *)(d + o_sel);
+    if (n_block > 0 && n_warp > 0 && !h->serial) {                                    // the few wide problems beside the many narrow ones
+        CK(cudaEventRecord(h->wf_ev[0], st));
+        CK(cudaStreamWaitEvent(h->side[0], h->wf_ev[0], 0));
+        VD_LAUNCH(wf_kernel<WF_BLOCK>, n_block, WF_BLOCK, 0, h->side[0], B, d_sel + n_warp, n_block);
+        CK(cudaEventRecord(h->wf_ev[1], h->side[0]));
+        VD_LAUNCH(wf_kernel<32>, (n_warp + 3) / 4, 128, 0, st, B, d_sel, n_warp);
+        CK(cudaStreamWaitEvent(st, h->wf_ev[1], 0));
+    } else {
+        if (n_block > 0) VD_LAUNCH(wf_kernel<WF_BLOCK>, n_block, WF_BLOCK, 0, st, B, d_sel + n_warp, n_block);
+        if (n_warp > 0) VD_LAUNCH(wf_kernel<32>, (n_warp + 3) / 4, 128, 0, st, B, d_sel, n_warp);
+    }
     CK(cudaMemcpyAsync(result, d + o_res, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());

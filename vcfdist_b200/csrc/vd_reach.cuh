@@ -36,11 +36,22 @@ __host__ __device__ inline int64_t wf_scratch_ints(int qlen, int tlen, int x, in
     return (int64_t)WF_NW * wf_ring(x, o, e) * (qlen + tlen - 1);
 }
 
-__global__ void __launch_bounds__(128) wf_kernel(WfBatch B) {
+// NT threads per problem: 32 (a warp; four problems per block) for the many cluster-sized problems, WF_BLOCK (a whole
+// block) for the few whose wavefront grows to hundreds of diagonals - a structural variant's cluster, where one warp would
+// walk the reached range in dozens of chunks per score.  sel lists the problems of this launch.  One barrier per score:
+// a thread computes the new wavefronts of ITS diagonals from earlier scores, leaves the gaps, extends along matches and
+// tests the exits without anybody else's values of the current score.
+constexpr int WF_BLOCK = 256;
+
+template <int NT>
+__global__ void __launch_bounds__(NT == 32 ? 128 : NT) wf_kernel(WfBatch B, const int *sel, int nsel) {
     constexpr unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (p >= B.n) return;
+    constexpr int NO_HIT = 0x7fffffff;
+    __shared__ int s_first, s_best;                                                   // block form only
+    const int t = NT == 32 ? (threadIdx.x & 31) : threadIdx.x;
+    const int w = NT == 32 ? blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5) : blockIdx.x;
+    if (w >= nsel) return;
+    const int p = sel ? sel[w] : w;
     const u8 *query = B.q_seq + B.q_off[p], *truth = B.t_seq + B.t_off[p];
     const int qlen = (int)(B.q_off[p + 1] - B.q_off[p]), tlen = (int)(B.t_off[p + 1] - B.t_off[p]);
     const int x = B.x, o = B.o, e = B.e;
@@ -50,116 +61,119 @@ __global__ void __launch_bounds__(128) wf_kernel(WfBatch B) {
     int *v = B.scratch + B.scratch_off[p];
     auto wf = [&](int kind, int slot, int d) -> int * { return v + ((int64_t)kind * ring + slot) * nd + d; };
     auto slot_of = [&](int slot, int back) { const int s = slot - back; return s < 0 ? s + ring : s; };
-    for (int64_t i = lane; i < (int64_t)WF_NW * ring * nd; i += 32) v[i] = WF_NONE;
-    __syncwarp();
+    auto inside = [&](int q, int k) { return q >= 0 && q < qlen && k + q >= 0 && k + q < tlen; };
+    // true if any thread of the problem says so; also the barrier after which the wavefronts of this score are everybody's
+    auto any_of = [&](bool f) -> bool {
+        if (NT == 32) { const bool r = __any_sync(FULL, f); __syncwarp(); return r; }
+        return __syncthreads_or(f) != 0;
+    };
+    for (int64_t i = t; i < (int64_t)WF_NW * ring * nd; i += NT) v[i] = WF_NONE;
+    if (NT != 32 && t == 0) { s_first = NO_HIT; s_best = 0; }
     const int main_diag = reach ? B.main_diag[p] : 0;
     const int stop_q = reach ? B.main_diag_start[p] - main_diag : 0;                // :2160
     const int max_score = reach ? B.max_score[p] : 0x7fffffff;
-    int score = 0, slot = 0, result = -1;
-    if (lane == 0) *wf(WF_M, slot, qlen - 1) = -1;                                    // :2166 / :1528: diagonal k = 0, before the first base
-    __syncwarp();
+    int score = 0, slot = 0;
+    if (NT == 32) __syncwarp(); else __syncthreads();
+    if (t == 0) *wf(WF_M, slot, qlen - 1) = -1;                                       // :2166 / :1528: diagonal k = 0, before the first base
+    if (NT == 32) __syncwarp(); else __syncthreads();
     // Diagonals any wavefront has reached so far: [dlo, dhi].  A score step reaches at most one more on either side (its
     // sources are the same diagonal and its two neighbours at earlier scores), everything outside still holds NONE from the
-    // fill above - so the passes below run over this range and not over all |query| + |truth| - 1 diagonals: a structural
+    // fill above - so a step runs over this range and not over all |query| + |truth| - 1 diagonals: a structural
     // variant's cluster has thousands of diagonals and hundreds of score steps, of which a step touches a few dozen.
     int dlo = qlen - 1, dhi = qlen - 1;
-    bool done = false;
     for (;;) {
-        // gaps are left for free at the score they were reached with (:2171-2184, :1533-1547); not in the reversed problem
-        if (!reverse)
-            for (int d = dlo + lane; d <= dhi; d += 32) {
-                const int k = d + 1 - qlen;
-                int m = *wf(WF_M, slot, d);
-#pragma unroll
-                for (int kind = WF_I; kind <= WF_D; kind++) {
-                    const int q = *wf(kind, slot, d);
-                    if (q >= 0 && q < qlen && k + q >= 0 && k + q < tlen && q >= m) m = q;
-                }
-                *wf(WF_M, slot, d) = m;
-            }
-        __syncwarp();
-        // free extension along matches, then the exits, diagonals in ascending order (:2187-2212, :1550-1568)
-        for (int d0 = dlo; d0 <= dhi && !done; d0 += 32) {
-            const int d = d0 + lane;
-            bool hit = false;
-            int res = -1;
-            if (d <= dhi) {
-                int q = *wf(WF_M, slot, d);
-                const int k = d + 1 - qlen;
-                while ((!reach || k != main_diag || q + 1 < stop_q) && q != WF_NONE && k + q >= -1 &&
-                       q < qlen - 1 && k + q < tlen - 1 && query[q + 1] == truth[k + q + 1])
-                    q++;
-                *wf(WF_M, slot, d) = q;
-                if (reach) {
-                    if (q + k == tlen - 1) { hit = true; res = tlen - 1; }                                   // :2205-2207
-                    else if (q == qlen - 1 && q + k >= 0 && q + k < tlen - 1) { hit = true; res = q + k; }   // :2208-2210
-                } else if (q == qlen - 1 && q + k == tlen - 1) { hit = true; res = score; }
-            }
-            const unsigned m = __ballot_sync(FULL, hit);
-            if (m) { result = __shfl_sync(FULL, res, __ffs(m) - 1); done = true; }
-        }
-        if (done) break;
-        if (score == max_score) break;                                                // :2213
-        __syncwarp();                                                                 // the extended wavefront is read by other lanes below
-        // next score (:2225-2311, :1583-1650)
-        score++;
-        slot = slot + 1 == ring ? 0 : slot + 1;
-        dlo = max(dlo - 1, 0); dhi = min(dhi + 1, nd - 1);
-        for (int d = dlo + lane; d <= dhi; d += 32) {
+        int hit_d = NO_HIT, hit_res = -1;
+        for (int d = dlo + t; d <= dhi; d += NT) {
             const int k = d + 1 - qlen;
-            // :2228-2232 clears I and D only, the M wavefront of the slot is overwritten through >= tests; wf_swg_align
-            // starts every wavefront of a new score empty (:1583-1587)
-            int mc = reach ? *wf(WF_M, slot, d) : WF_NONE, ic = WF_NONE, dc = WF_NONE;
-            if (score - x >= 0) {                                                     // substitution (:2239-2250)
-                const int pv = x == 0 ? mc : *wf(WF_M, slot_of(slot, x), d);
-                if (pv != WF_NONE && pv + 1 < qlen && k + pv + 1 < tlen && pv + 1 >= mc) mc = pv + 1;
-            }
-            {                                                                         // gap opening (:2252-2275)
-                const int cost = reverse ? e : o + e;
-                if (score - cost >= 0) {
-                    const int ps = slot_of(slot, cost);
+            // the wavefronts of this score from those of earlier scores (:2225-2311, :1583-1650).  :2228-2232 clears I and D
+            // only, the M wavefront of the slot is overwritten through >= tests; wf_swg_align starts every wavefront of a
+            // new score empty (:1583-1587)
+            int mc = (reach || score == 0) ? *wf(WF_M, slot, d) : WF_NONE, ic = WF_NONE, dc = WF_NONE;
+            if (score > 0) {
+                if (score - x >= 0) {                                                 // substitution (:2239-2250)
+                    const int pv = x == 0 ? mc : *wf(WF_M, slot_of(slot, x), d);
+                    if (pv != WF_NONE && pv + 1 < qlen && k + pv + 1 < tlen && pv + 1 >= mc) mc = pv + 1;
+                }
+                {                                                                     // gap opening (:2252-2275)
+                    const int cost = reverse ? e : o + e;
+                    if (score - cost >= 0) {
+                        const int ps = slot_of(slot, cost);
+                        if (d > 0) {
+                            const int pv = *wf(WF_M, ps, d - 1);
+                            if (pv != WF_NONE && k + pv < tlen && pv >= dc) dc = pv;
+                        }
+                        if (d < nd - 1) {
+                            const int pv = *wf(WF_M, ps, d + 1);
+                            if (pv != WF_NONE && pv + 1 < qlen && k + pv + 1 < tlen && k + pv + 1 >= 0 && pv + 1 >= ic) ic = pv + 1;
+                        }
+                    }
+                }
+                if (reverse && score - o >= 0) {                                      // reversed problem: leaving a gap costs o (:2277-2294)
+                    const int ps = slot_of(slot, o);
+                    const int pi = o == 0 ? ic : *wf(WF_I, ps, d), pd = o == 0 ? dc : *wf(WF_D, ps, d);
+                    if (inside(pi, k) && pi > mc) mc = pi;
+                    if (inside(pd, k) && pd > mc) mc = pd;
+                }
+                if (score - e >= 0) {                                                 // gap extension (:2296-2311)
+                    const int ps = slot_of(slot, e);
                     if (d > 0) {
-                        const int pv = *wf(WF_M, ps, d - 1);
+                        const int pv = *wf(WF_D, ps, d - 1);
                         if (pv != WF_NONE && k + pv < tlen && pv >= dc) dc = pv;
                     }
                     if (d < nd - 1) {
-                        const int pv = *wf(WF_M, ps, d + 1);
+                        const int pv = *wf(WF_I, ps, d + 1);
                         if (pv != WF_NONE && pv + 1 < qlen && k + pv + 1 < tlen && k + pv + 1 >= 0 && pv + 1 >= ic) ic = pv + 1;
                     }
                 }
+                *wf(WF_I, slot, d) = ic; *wf(WF_D, slot, d) = dc;
             }
-            if (reverse && score - o >= 0) {                                          // reversed problem: leaving a gap costs o (:2277-2294)
-                const int ps = slot_of(slot, o);
-                const int pi = o == 0 ? ic : *wf(WF_I, ps, d), pd = o == 0 ? dc : *wf(WF_D, ps, d);
-                if (pi >= 0 && pi < qlen && k + pi >= 0 && k + pi < tlen && pi > mc) mc = pi;
-                if (pd >= 0 && pd < qlen && k + pd >= 0 && k + pd < tlen && pd > mc) mc = pd;
+            // gaps are left for free at the score they were reached with (:2171-2184, :1533-1547); not in the reversed problem
+            int q = mc;
+            if (!reverse) {
+                if (inside(ic, k) && ic >= q) q = ic;
+                if (inside(dc, k) && dc >= q) q = dc;
             }
-            if (score - e >= 0) {                                                     // gap extension (:2296-2311)
-                const int ps = slot_of(slot, e);
-                if (d > 0) {
-                    const int pv = *wf(WF_D, ps, d - 1);
-                    if (pv != WF_NONE && k + pv < tlen && pv >= dc) dc = pv;
-                }
-                if (d < nd - 1) {
-                    const int pv = *wf(WF_I, ps, d + 1);
-                    if (pv != WF_NONE && pv + 1 < qlen && k + pv + 1 < tlen && k + pv + 1 >= 0 && pv + 1 >= ic) ic = pv + 1;
-                }
-            }
-            *wf(WF_M, slot, d) = mc; *wf(WF_I, slot, d) = ic; *wf(WF_D, slot, d) = dc;
+            // free extension along matches, then the exits, diagonals in ascending order (:2187-2212, :1550-1568)
+            while ((!reach || k != main_diag || q + 1 < stop_q) && q != WF_NONE && k + q >= -1 &&
+                   q < qlen - 1 && k + q < tlen - 1 && query[q + 1] == truth[k + q + 1])
+                q++;
+            *wf(WF_M, slot, d) = q;
+            if (reach) {
+                if (q + k == tlen - 1) { hit_d = d; hit_res = tlen - 1; break; }                                   // :2205-2207
+                if (q == qlen - 1 && q + k >= 0 && q + k < tlen - 1) { hit_d = d; hit_res = q + k; break; }        // :2208-2210
+            } else if (q == qlen - 1 && q + k == tlen - 1) { hit_d = d; hit_res = score; break; }
         }
-        __syncwarp();
-    }
-    if (!done) {
-        // the score budget is spent: furthest truth index over everything still in the ring (:2316-2331)
-        int best = 0;
-        for (int64_t i = lane; i < (int64_t)WF_NW * ring * nd; i += 32) {
-            const int d = (int)(i % nd);
-            const int q = v[i], k = d + 1 - qlen;
-            if (q >= 0 && q < qlen && k + q >= 0 && k + q < tlen && k + q > best) best = k + q;
+        if (any_of(hit_d != NO_HIT)) {
+            // the reference leaves at the FIRST diagonal in ascending order that reached an end
+            int first;
+            if (NT == 32) first = __reduce_min_sync(FULL, hit_d);
+            else {
+                if (hit_d != NO_HIT) atomicMin(&s_first, hit_d);
+                __syncthreads();
+                first = s_first;
+            }
+            if (hit_d == first) B.result[p] = hit_res;
+            return;
         }
-        result = __reduce_max_sync(FULL, best);
+        if (score == max_score) break;                                                // :2213
+        score++;
+        slot = slot + 1 == ring ? 0 : slot + 1;
+        dlo = max(dlo - 1, 0); dhi = min(dhi + 1, nd - 1);
     }
-    if (lane == 0) B.result[p] = result;
+    // the score budget is spent: furthest truth index over everything still in the ring (:2316-2331)
+    int best = 0;
+    for (int64_t i = t; i < (int64_t)WF_NW * ring * nd; i += NT) {
+        const int d = (int)(i % nd);
+        const int q = v[i], k = d + 1 - qlen;
+        if (inside(q, k) && k + q > best) best = k + q;
+    }
+    if (NT == 32) best = __reduce_max_sync(FULL, best);
+    else {
+        atomicMax(&s_best, best);
+        __syncthreads();
+        best = s_best;
+    }
+    if (t == 0) B.result[p] = best;
 }
 
 
