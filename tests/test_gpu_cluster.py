@@ -122,6 +122,16 @@ def test_block_and_warp_forms_agree(monkeypatch, block_min):
         cs = [pairs[i] for i in idx]
         got = e.wf_batch(1, [c[0] for c in cs], [c[1] for c in cs], x, o, ex)
         assert (got == np.array([checkers.swg_score_oracle(*c) for c in cs])).all(), (x, o, ex)
+    # the --distance alignment (scores, CIGARs): this engine's mix of forms against an all-warp engine
+    monkeypatch.setenv("VD_WF_BLOCK_MIN", "100000")
+    w = capi.Engine(0)
+    for (x, o, ex), idx in by_penalties(pairs, lambda c: c[2:5]).items():
+        cs = [pairs[i] for i in idx]
+        sa, ca = e.swg_align_batch([c[0] for c in cs], [c[1] for c in cs], x, o, ex)
+        sb, cb = w.swg_align_batch([c[0] for c in cs], [c[1] for c in cs], x, o, ex)
+        assert (np.asarray(sa) == np.asarray(sb)).all() and all((a == b).all() for a, b in zip(ca, cb)), (x, o, ex)
+        assert (np.asarray(sa) == np.array([checkers.swg_score_oracle(*c) for c in cs])).all()
+    w.close()
     e.close()
 
 

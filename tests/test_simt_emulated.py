@@ -90,9 +90,13 @@ def test_cluster_wavefront_kernels_and_driver(monkeypatch, block_min):
     e.close()
 
 
-def test_distance_alignment_kernel():
-    """affine-gap alignment with CIGAR (wf_swg_align + wf_swg_backtrack) against recorded reference answers."""
+@pytest.mark.parametrize("block_min", [None, "1"])
+def test_distance_alignment_kernel(monkeypatch, block_min):
+    """affine-gap alignment with CIGAR (wf_swg_align + wf_swg_backtrack) against recorded reference answers,
+    a warp per problem and (VD_WF_BLOCK_MIN=1) a block per problem."""
     from conftest import ROOT
+    if block_min:
+        monkeypatch.setenv("VD_WF_BLOCK_MIN", block_min)
     z = np.load(os.path.join(ROOT, "tests", "golden", "reach_kat.npz"), allow_pickle=False)
     e = EmuEngine()
     groups = {}

@@ -1061,7 +1061,18 @@ extern "C" int vd_swg_align_batch(vd_handle *h, int n, const int64_t *q_off, con
     int32_t *d_cigar = (int32_t *)((u8 *)h->wf_scratch.p + ((boff[n] + 15) / 16) * 16);
     WfCigarBatch B{n, (const int64_t *)(d + o_qoff), (const int64_t *)(d + o_toff), d + o_q, d + o_t, (const int32_t *)(d + o_ms),
                    (const int64_t *)(d + o_soff), (u8 *)h->wf_scratch.p, d_cigar, (int32_t *)(d + o_res), sub, open, extend};
-    VD_LAUNCH(wf_cigar_kernel, (n + 3) / 4, 128, 0, st, B);
+    // warp or block per problem by the width its wavefront reached (as vd_wf_batch; the score is known here)
+    size_t o_sel = (o_t + tb + 15) & ~(size_t)15;
+    std::vector<int> sel((size_t)n);
+    int n_warp = 0, n_block = 0;
+    for (int i = 0; i < n; i++) {
+        const int64_t width = std::min<int64_t>((q_off[i + 1] - q_off[i]) + (t_off[i + 1] - t_off[i]) - 1, 2 * (int64_t)std::max(score[i], 0) + 1);
+        if (width >= h->wf_block_min) sel[(size_t)n - 1 - n_block++] = i; else sel[(size_t)n_warp++] = i;
+    }
+    CK(cudaMemcpyAsync(d + o_sel, sel.data(), 4 * (size_t)n, cudaMemcpyHostToDevice, st));
+    const int *d_sel = (const int *)(d + o_sel);
+    if (n_block > 0) VD_LAUNCH(wf_cigar_kernel<WF_BLOCK>, n_block, WF_BLOCK, 0, st, B, d_sel + n_warp, n_block);
+    if (n_warp > 0) VD_LAUNCH(wf_cigar_kernel<32>, (n_warp + 3) / 4, 128, 0, st, B, d_sel, n_warp);
     CK(cudaMemcpyAsync(score, d + o_res, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(cigar, d_cigar, 4 * (size_t)(qb + tb), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));

@@ -205,10 +205,13 @@ __host__ __device__ inline int64_t wf_cigar_bytes(int qlen, int tlen, int score)
     return (5 * cells + 15) / 16 * 16;
 }
 
-__global__ void __launch_bounds__(128) wf_cigar_kernel(WfCigarBatch B) {
-    const int lane = threadIdx.x & 31;
-    const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (p >= B.n) return;
+template <int NT>                                             // threads per problem, as wf_kernel
+__global__ void __launch_bounds__(NT == 32 ? 128 : NT) wf_cigar_kernel(WfCigarBatch B, const int *sel, int nsel) {
+    const int lane = NT == 32 ? (threadIdx.x & 31) : threadIdx.x;
+    const int w = NT == 32 ? blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5) : blockIdx.x;
+    if (w >= nsel) return;
+    const int p = sel ? sel[w] : w;
+    auto barrier = [&]() { if (NT == 32) __syncwarp(); else __syncthreads(); };
     const u8 *query = B.q_seq + B.q_off[p], *truth = B.t_seq + B.t_off[p];
     const int qlen = (int)(B.q_off[p + 1] - B.q_off[p]), tlen = (int)(B.t_off[p + 1] - B.t_off[p]);
     const int x = B.x, o = B.o, e = B.e, final_score = B.score[p];
@@ -218,13 +221,13 @@ __global__ void __launch_bounds__(128) wf_cigar_kernel(WfCigarBatch B) {
     u8 *flag = (u8 *)(off + cells);
     auto OFF = [&](int s, int kind, int d) -> int & { return off[((int64_t)s * WF_NW + kind) * nd + d]; };
     auto FLG = [&](int s, int kind, int d) -> u8 & { return flag[((int64_t)s * WF_NW + kind) * nd + d]; };
-    for (int64_t i = lane; i < cells; i += 32) { off[i] = WF_NONE; flag[i] = 0; }
-    __syncwarp();
+    for (int64_t i = lane; i < cells; i += NT) { off[i] = WF_NONE; flag[i] = 0; }
+    barrier();
     if (lane == 0) { OFF(0, WF_M, qlen - 1) = -1; FLG(0, WF_M, qlen - 1) = WFC_MAT; }                  // :1528-1529
-    __syncwarp();
+    barrier();
     int dlo = qlen - 1, dhi = qlen - 1;                      // diagonals reached so far (see wf_kernel): the passes run over these only
     for (int score = 0;; score++) {
-        for (int d = dlo + lane; d <= dhi; d += 32) {                                                     // :1533-1547
+        for (int d = dlo + lane; d <= dhi; d += NT) {                                                     // :1533-1547
             const int k = d + 1 - qlen;
 #pragma unroll
             for (int kind = WF_I; kind <= WF_D; kind++) {
@@ -238,11 +241,11 @@ __global__ void __launch_bounds__(128) wf_cigar_kernel(WfCigarBatch B) {
             while (q != WF_NONE && k + q >= -1 && q < qlen - 1 && k + q < tlen - 1 && query[q + 1] == truth[k + q + 1]) q++;
             OFF(score, WF_M, d) = q;
         }
-        __syncwarp();
+        barrier();
         if (score == final_score) break;                     // the score pass found the end at this score
         const int s1 = score + 1;
         dlo = max(dlo - 1, 0); dhi = min(dhi + 1, nd - 1);
-        for (int d = dlo + lane; d <= dhi; d += 32) {
+        for (int d = dlo + lane; d <= dhi; d += NT) {
             const int k = d + 1 - qlen;
             if (s1 - x >= 0) {                                                                            // :1592-1600
                 const int pv = OFF(s1 - x, WF_M, d);
@@ -271,12 +274,12 @@ __global__ void __launch_bounds__(128) wf_cigar_kernel(WfCigarBatch B) {
                 }
             }
         }
-        __syncwarp();
+        barrier();
     }
     // ---- walk back (:2648-2755), one lane ----
     int *cigar = B.cigar + B.q_off[p] + B.t_off[p];
-    for (int i = lane; i < qlen + tlen; i += 32) cigar[i] = 0;
-    __syncwarp();
+    for (int i = lane; i < qlen + tlen; i += NT) cigar[i] = 0;
+    barrier();
     if (lane) return;
     int cp = qlen + tlen - 1, kind = WF_M, qi = qlen - 1, ti = tlen - 1, s = final_score;
     bool failed = false;
