@@ -5,10 +5,11 @@ import sys; sys.path.insert(0,'.')
 from workloads import vcfgen
 print(vcfgen.generate('/tmp/vs/in', seed=5, contig_len=$L, n_contigs=2, sv_rate=0.03, sv_max=$SV))
 P
-for b in vcfdist_b200cli vcfdist_ref; do
+for b in vcfdist_b200cli ${SKIP_REF:+-} vcfdist_ref; do
+  [ "$b" = "-" ] && break
   mkdir -p /tmp/vs/$b; cd /tmp/vs/$b
   echo "== $b"; SECONDS=0
-  VD_DROPIN_TIMES=1 timeout 900 $GRAFT_REPO_ROOT/oracle/_ref/$b /tmp/vs/in/query.vcf /tmp/vs/in/truth.vcf /tmp/vs/in/ref.fa -p /tmp/vs/$b/ -v 1 -t 16 $EXTRA 2>&1 | grep -E "\[[0-9]\] |ERROR|GPU clustering"
+  VD_DROPIN_TIMES=1 timeout 900 $GRAFT_REPO_ROOT/oracle/_ref/$b /tmp/vs/in/query.vcf /tmp/vs/in/truth.vcf /tmp/vs/in/ref.fa -p /tmp/vs/$b/ -v 1 -t 16 $EXTRA 2>&1 | grep -E "\[[0-9]\] |ERROR|GPU clustering|vd_wf_batch"
   echo "wall ${SECONDS} s"
   cd $GRAFT_REPO_ROOT
 done

@@ -103,12 +103,14 @@ def sv_like_cases(rng, n):
     return out
 
 
-@pytest.mark.parametrize("block_min", [1, 40, 100000])
-def test_block_and_warp_forms_agree(monkeypatch, block_min):
-    """vd_wf_batch gives a problem a warp or a whole block by the width its wavefront can reach (VD_WF_BLOCK_MIN):
-    all through the block form, mixed, all through the warp form - same answers as the C restatement, on cluster-sized
-    and on structural-variant-sized problems, reach and score."""
+@pytest.mark.parametrize("block_min,cluster_min", [(1, 10 ** 9), (40, 600), (100000, 10 ** 9), (16, 64), (100000, 1)])
+def test_block_and_warp_forms_agree(monkeypatch, block_min, cluster_min):
+    """vd_wf_batch gives a problem a warp, a 256- or 1024-thread block or a cluster of eight blocks by the width its
+    wavefront can reach (VD_WF_BLOCK_MIN, VD_WF_CLUSTER_MIN): all through the block forms, mixed, all through the warp
+    form, everything on clusters - same answers as the C restatement, on cluster-sized and on structural-variant-sized
+    problems, reach and score."""
     monkeypatch.setenv("VD_WF_BLOCK_MIN", str(block_min))
+    monkeypatch.setenv("VD_WF_CLUSTER_MIN", str(cluster_min))
     e = capi.Engine(0)
     rng = np.random.default_rng(23)
     cases = [TR.random_case(rng) for _ in range(600)] + sv_like_cases(rng, 60)

@@ -61,9 +61,9 @@ def test_dense_block_kernels_alone():
     assert st["n_dense"] > 0
 
 
-@pytest.mark.parametrize("block_min", [None, "1"])
+@pytest.mark.parametrize("block_min", [None, "1", "8"])
 def test_cluster_wavefront_kernels_and_driver(monkeypatch, block_min):
-    """the reach / score wavefront kernel (a warp per problem; with VD_WF_BLOCK_MIN=1 a block per problem)
+    """the reach / score wavefront kernel (a warp per problem; with VD_WF_BLOCK_MIN a 256- or 1024-thread block per problem from that width on)
     and the batched cluster-growing driver over it, against the recorded reference answers."""
     import json
     if block_min:
@@ -90,7 +90,7 @@ def test_cluster_wavefront_kernels_and_driver(monkeypatch, block_min):
     e.close()
 
 
-@pytest.mark.parametrize("block_min", [None, "1"])
+@pytest.mark.parametrize("block_min", [None, "8"])
 def test_distance_alignment_kernel(monkeypatch, block_min):
     """affine-gap alignment with CIGAR (wf_swg_align + wf_swg_backtrack) against recorded reference answers,
     a warp per problem and (VD_WF_BLOCK_MIN=1) a block per problem."""

@@ -11,6 +11,7 @@
 #include <cstring>
 #include <ctime>
 #include <string>
+#include <chrono>
 #include <vector>
 
 #ifndef VD_EMU
@@ -88,7 +89,8 @@ struct vd_handle {
     int use_band = 1;               // VD_BAND=0: no banded warp kernels, every long alignment goes to the dense block kernels (testing)
     int use_wsc = 1;                // VD_WSC=0: mid-size superclusters go to the HBM-slab path instead of the warp kernel
     int wf_block_min = 384;         // VD_WF_BLOCK_MIN: wavefront width from which a clustering / --distance problem gets a block, not a warp
-    cudaEvent_t wf_ev[2] = {};
+    cudaEvent_t wf_ev[4] = {};
+    int64_t wf_cluster_min = 6144;  // VD_WF_CLUSTER_MIN: ... and from which it gets a cluster of blocks
     int walk_wpw = 0;               // VD_WALK_WPW: alignments per warp in the long path's walk kernels (0 = by their number)
     int wsc_split = 1;              // VD_WSC_SPLIT=0: the fused warp kernels instead of expansion / sweeps / walk as separate launches
     // staged input / output (vd_run)
@@ -131,11 +133,16 @@ extern "C" int vd_create(int device, int64_t scratch_bytes, vd_handle **out) {
     if (!out) return VD_E_BADINPUT;
     *out = nullptr;
     int n = 0;
+    const bool times = getenv("VD_CREATE_TIMES") != nullptr;                 // where start-up goes: context, streams and events, kernel attributes
+    const auto t_0 = std::chrono::steady_clock::now();
+    auto since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count(); };
     if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return VD_E_NODEVICE;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return VD_E_NODEVICE;
     if (prop.major != 10) return VD_E_NODEVICE;          // built for sm_100a only
     if (cudaSetDevice(device) != cudaSuccess) return VD_E_NODEVICE;
+    cudaFree(nullptr);                                                       // the context comes up here
+    const double ms_ctx = since(t_0);
     vd_handle *h = new vd_handle();
     h->device = device;
     h->num_sms = prop.multiProcessorCount;
@@ -181,6 +188,10 @@ extern "C" int vd_create(int device, int64_t scratch_bytes, vd_handle **out) {
     if (const char *v = getenv("VD_BAND")) h->use_band = atoi(v);
     if (const char *v = getenv("VD_WSC_SPLIT")) h->wsc_split = atoi(v);
     if (const char *v = getenv("VD_WF_BLOCK_MIN")) h->wf_block_min = std::max(1, atoi(v));
+    if (const char *v = getenv("VD_WF_CLUSTER_MIN")) h->wf_cluster_min = std::max(1, atoi(v));
+#ifdef VD_EMU
+    h->wf_cluster_min = INT64_MAX;                                            // no thread-block clusters under the emulator
+#endif
     if (const char *v = getenv("VD_WALK_WPW")) { const int w = atoi(v); h->walk_wpw = (w == 1 || w == 2 || w == 4 || w == 8 || w == 16 || w == 32) ? w : 0; }
     if (const char *v = getenv("VD_SERIAL")) h->serial = atoi(v);
     if (const char *v = getenv("VD_HOM")) h->use_hom = atoi(v);
@@ -197,11 +208,14 @@ extern "C" int vd_create(int device, int64_t scratch_bytes, vd_handle **out) {
         cok &= cudaEventCreateWithFlags(&sg.out_done, cudaEventDisableTiming) == cudaSuccess;
     }
     if (!cok) { vd_destroy(h); return VD_E_CUDA; }          // a stream, event or pinned block could not be created
+    const double ms_obj = since(t_0) - ms_ctx;
     small_configure();
     wsc_configure();
     wsc_split_configure();
     wave_configure();
     band_configure();
+    if (times) fprintf(stderr, "vd_create: context %.1f ms, streams / events / pinned blocks %.1f ms, kernel attributes %.1f ms\n",
+                       ms_ctx, ms_obj, since(t_0) - ms_ctx - ms_obj);
     *out = h;
     return VD_OK;
 }
@@ -990,15 +1004,23 @@ extern "C" int vd_wf_batch(vd_handle *h, int mode, int n, const int64_t *q_off, 
     size_t o_mds = o_md + 4 * (size_t)n, o_ms = o_mds + 4 * (size_t)n, o_res = o_ms + 4 * (size_t)n, o_rev = o_res + 4 * (size_t)n;
     size_t o_q = (o_rev + n + 15) & ~(size_t)15, o_t = (o_q + qb + 15) & ~(size_t)15, o_sel = (o_t + tb + 15) & ~(size_t)15;
     size_t total = o_sel + 4 * (size_t)n + 16;
-    // Problems whose wavefront can grow to wf_block_min diagonals or more get a whole block, the others a warp: sel holds the
-    // warp problems from the front and the block problems from the back.
+    // Problems whose wavefront can grow to wf_block_min diagonals or more get a whole block (WF_BLOCK threads, WF_WIDE for
+    // the wider ones, a cluster of WF_CLUSTER such blocks from wf_cluster_min diagonals on), the others a warp: sel holds
+    // the warp problems, then the block problems, the wide ones, the cluster ones.
     std::vector<int> sel((size_t)n);
-    int n_warp = 0, n_block = 0;
-    for (int i = 0; i < n; i++) {
-        int64_t width = (q_off[i + 1] - q_off[i]) + (t_off[i + 1] - t_off[i]) - 1;
-        if (mode == WF_MODE_REACH) width = std::min<int64_t>(width, 2 * (int64_t)std::max(max_score[i], 0) + 1);
-        if (width >= h->wf_block_min) sel[(size_t)n - 1 - n_block++] = i; else sel[(size_t)n_warp++] = i;
+    int n_form[4] = {0, 0, 0, 0};
+    {
+        std::vector<u8> form((size_t)n);
+        for (int i = 0; i < n; i++) {
+            int64_t width = (q_off[i + 1] - q_off[i]) + (t_off[i + 1] - t_off[i]) - 1;
+            if (mode == WF_MODE_REACH) width = std::min<int64_t>(width, 2 * (int64_t)std::max(max_score[i], 0) + 1);
+            form[i] = width >= h->wf_cluster_min ? 3 : width >= 4 * (int64_t)h->wf_block_min ? 2 : width >= h->wf_block_min ? 1 : 0;
+            n_form[form[i]]++;
+        }
+        int at[4] = {0, n_form[0], n_form[0] + n_form[1], n_form[0] + n_form[1] + n_form[2]};
+        for (int i = 0; i < n; i++) sel[(size_t)at[form[i]]++] = i;
     }
+    const int n_warp = n_form[0], n_block = n_form[1], n_wide = n_form[2], n_cluster = n_form[3];
     CK(h->wf_in.ensure(total));
     CK(h->wf_scratch.ensure(4 * (size_t)soff[n] + 16));
     u8 *d = (u8 *)h->wf_in.p;
@@ -1018,20 +1040,51 @@ extern "C" int vd_wf_batch(vd_handle *h, int mode, int n, const int64_t *q_off, 
               (int32_t *)(d + o_res), sub, open, extend, mode};
     CK(cudaMemcpyAsync(d + o_sel, sel.data(), 4 * (size_t)n, cudaMemcpyHostToDevice, st));
     const int *d_sel = (const int *)(d + o_sel);
-    if (n_block > 0 && n_warp > 0 && !h->serial) {                                    // the few wide problems beside the many narrow ones
+    // the few wide problems beside the many narrow ones: every form on its own stream
+    const bool beside = !h->serial && (n_cluster > 0) + (n_wide > 0) + (n_block > 0) + (n_warp > 0) > 1;
+    cudaStream_t s_cluster = beside ? h->side[2] : st, s_wide = beside ? h->side[0] : st, s_block = beside ? h->side[1] : st;
+    if (beside) {
         CK(cudaEventRecord(h->wf_ev[0], st));
-        CK(cudaStreamWaitEvent(h->side[0], h->wf_ev[0], 0));
-        VD_LAUNCH(wf_kernel<WF_BLOCK>, n_block, WF_BLOCK, 0, h->side[0], B, d_sel + n_warp, n_block);
-        CK(cudaEventRecord(h->wf_ev[1], h->side[0]));
-        VD_LAUNCH(wf_kernel<32>, (n_warp + 3) / 4, 128, 0, st, B, d_sel, n_warp);
-        CK(cudaStreamWaitEvent(st, h->wf_ev[1], 0));
-    } else {
-        if (n_block > 0) VD_LAUNCH(wf_kernel<WF_BLOCK>, n_block, WF_BLOCK, 0, st, B, d_sel + n_warp, n_block);
-        if (n_warp > 0) VD_LAUNCH(wf_kernel<32>, (n_warp + 3) / 4, 128, 0, st, B, d_sel, n_warp);
+        CK(cudaStreamWaitEvent(s_cluster, h->wf_ev[0], 0));
+        CK(cudaStreamWaitEvent(s_wide, h->wf_ev[0], 0));
+        CK(cudaStreamWaitEvent(s_block, h->wf_ev[0], 0));
     }
+#ifndef VD_EMU
+    if (n_cluster > 0) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)n_cluster * WF_CLUSTER); cfg.blockDim = dim3(WF_WIDE); cfg.dynamicSmemBytes = 0; cfg.stream = s_cluster;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = WF_CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        CK(cudaLaunchKernelEx(&cfg, wf_kernel<WF_WIDE, WF_CLUSTER>, B, d_sel + n_warp + n_block + n_wide, n_cluster));
+    }
+#endif
+    if (n_wide > 0) VD_LAUNCH(wf_kernel<WF_WIDE>, n_wide, WF_WIDE, 0, s_wide, B, d_sel + n_warp + n_block, n_wide);
+    if (n_block > 0) VD_LAUNCH(wf_kernel<WF_BLOCK>, n_block, WF_BLOCK, 0, s_block, B, d_sel + n_warp, n_block);
+    if (n_warp > 0) VD_LAUNCH(wf_kernel<32>, (n_warp + 3) / 4, 128, 0, st, B, d_sel, n_warp);
+    if (beside) {
+        CK(cudaEventRecord(h->wf_ev[1], s_wide));
+        CK(cudaEventRecord(h->wf_ev[2], s_block));
+        CK(cudaEventRecord(h->wf_ev[3], s_cluster));
+        CK(cudaStreamWaitEvent(st, h->wf_ev[1], 0));
+        CK(cudaStreamWaitEvent(st, h->wf_ev[2], 0));
+        CK(cudaStreamWaitEvent(st, h->wf_ev[3], 0));
+    }
+    const auto t_sync = std::chrono::steady_clock::now();
     CK(cudaMemcpyAsync(result, d + o_res, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
+    if (getenv("VD_WF_STATS")) {                                                      // one line per batch: what it held, how long it ran
+        int64_t wmax = 0, lmax = 0, smax = 0;
+        for (int i = 0; i < n; i++) {
+            const int64_t nd = (q_off[i + 1] - q_off[i]) + (t_off[i + 1] - t_off[i]) - 1;
+            lmax = std::max(lmax, nd);
+            if (mode == WF_MODE_REACH) { smax = std::max<int64_t>(smax, max_score[i]); wmax = std::max(wmax, std::min<int64_t>(nd, 2 * (int64_t)max_score[i] + 1)); }
+        }
+        fprintf(stderr, "vd_wf_batch mode %d: %d problems (%d on a block, %d on a wide block, %d on a cluster), longest %lld diagonals, largest budget %lld (width %lld), %.1f ms\n", mode, n, n_block, n_wide, n_cluster,
+                (long long)lmax, (long long)smax, (long long)wmax, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_sync).count());
+    }
     return VD_OK;
 }
 
@@ -1064,13 +1117,20 @@ extern "C" int vd_swg_align_batch(vd_handle *h, int n, const int64_t *q_off, con
     // warp or block per problem by the width its wavefront reached (as vd_wf_batch; the score is known here)
     size_t o_sel = (o_t + tb + 15) & ~(size_t)15;
     std::vector<int> sel((size_t)n);
-    int n_warp = 0, n_block = 0;
-    for (int i = 0; i < n; i++) {
-        const int64_t width = std::min<int64_t>((q_off[i + 1] - q_off[i]) + (t_off[i + 1] - t_off[i]) - 1, 2 * (int64_t)std::max(score[i], 0) + 1);
-        if (width >= h->wf_block_min) sel[(size_t)n - 1 - n_block++] = i; else sel[(size_t)n_warp++] = i;
+    int n_warp = 0, n_block = 0, n_wide = 0;
+    {
+        std::vector<u8> form((size_t)n);
+        for (int i = 0; i < n; i++) {
+            const int64_t width = std::min<int64_t>((q_off[i + 1] - q_off[i]) + (t_off[i + 1] - t_off[i]) - 1, 2 * (int64_t)std::max(score[i], 0) + 1);
+            form[i] = width >= 4 * (int64_t)h->wf_block_min ? 2 : width >= h->wf_block_min ? 1 : 0;
+            (form[i] == 2 ? n_wide : form[i] == 1 ? n_block : n_warp)++;
+        }
+        int at[3] = {0, n_warp, n_warp + n_block};
+        for (int i = 0; i < n; i++) sel[(size_t)at[form[i]]++] = i;
     }
     CK(cudaMemcpyAsync(d + o_sel, sel.data(), 4 * (size_t)n, cudaMemcpyHostToDevice, st));
     const int *d_sel = (const int *)(d + o_sel);
+    if (n_wide > 0) VD_LAUNCH(wf_cigar_kernel<WF_WIDE>, n_wide, WF_WIDE, 0, st, B, d_sel + n_warp + n_block, n_wide);
     if (n_block > 0) VD_LAUNCH(wf_cigar_kernel<WF_BLOCK>, n_block, WF_BLOCK, 0, st, B, d_sel + n_warp, n_block);
     if (n_warp > 0) VD_LAUNCH(wf_cigar_kernel<32>, (n_warp + 3) / 4, 128, 0, st, B, d_sel, n_warp);
     CK(cudaMemcpyAsync(score, d + o_res, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));

@@ -32,8 +32,12 @@ struct WfBatch {
 };
 
 __host__ __device__ inline int wf_ring(int x, int o, int e) { return (x > o + e ? x : o + e) + 1; }
-__host__ __device__ inline int64_t wf_scratch_ints(int qlen, int tlen, int x, int o, int e) {
+__host__ __device__ inline int64_t wf_ring_ints(int qlen, int tlen, int x, int o, int e) {
     return (int64_t)WF_NW * wf_ring(x, o, e) * (qlen + tlen - 1);
+}
+// the ring, then (8-byte aligned) four words the blocks of a cluster meet in: the first exit as a 64-bit key, the best of the last scan
+__host__ __device__ inline int64_t wf_scratch_ints(int qlen, int tlen, int x, int o, int e) {
+    return ((wf_ring_ints(qlen, tlen, x, o, e) + 1) & ~(int64_t)1) + 4;
 }
 
 // NT threads per problem: 32 (a warp; four problems per block) for the many cluster-sized problems, WF_BLOCK (a whole
@@ -41,15 +45,35 @@ __host__ __device__ inline int64_t wf_scratch_ints(int qlen, int tlen, int x, in
 // walk the reached range in dozens of chunks per score.  sel lists the problems of this launch.  One barrier per score:
 // a thread computes the new wavefronts of ITS diagonals from earlier scores, leaves the gaps, extends along matches and
 // tests the exits without anybody else's values of the current score.
-constexpr int WF_BLOCK = 256;
+constexpr int WF_BLOCK = 256, WF_WIDE = 1024;
 
-template <int NT>
+// The widest problems (a several-kb variant: ten thousand scores over twenty thousand diagonals) outgrow one SM's path to L2 -
+// the ring is megabytes, every step streams it: CL blocks of one thread-block cluster share the diagonals of such a problem.
+// They meet at the hardware cluster barrier once per score (release / acquire at cluster scope); ring values cross SMs, so
+// they are read past L1 (ld.global.cg), and the exit is agreed on through a 64-bit atomicMin (diagonal, result) in scratch.
+constexpr int WF_CLUSTER = 8;
+#ifdef VD_EMU
+__device__ inline void wf_cluster_sync() {}
+__device__ inline unsigned wf_cluster_rank() { return 0; }
+__device__ inline int wf_ld_l2(const int *p) { return *p; }
+__device__ inline unsigned long long wf_ld_l2(const unsigned long long *p) { return *p; }
+#else
+__device__ __forceinline__ void wf_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned wf_cluster_rank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ int wf_ld_l2(const int *p) { return __ldcg(p); }
+__device__ __forceinline__ unsigned long long wf_ld_l2(const unsigned long long *p) { return __ldcg(p); }
+#endif
+
+template <int NT, int CL = 1>
 __global__ void __launch_bounds__(NT == 32 ? 128 : NT) wf_kernel(WfBatch B, const int *sel, int nsel) {
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int NO_HIT = 0x7fffffff;
     __shared__ int s_first, s_best;                                                   // block form only
-    const int t = NT == 32 ? (threadIdx.x & 31) : threadIdx.x;
-    const int w = NT == 32 ? blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5) : blockIdx.x;
+    constexpr int NTT = NT * CL;                                                      // threads on one problem
+    const int t = NT == 32 ? (threadIdx.x & 31) : CL > 1 ? (int)(wf_cluster_rank() * NT + threadIdx.x) : threadIdx.x;
+    const int w = NT == 32 ? blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5) : blockIdx.x / CL;
     if (w >= nsel) return;
     const int p = sel ? sel[w] : w;
     const u8 *query = B.q_seq + B.q_off[p], *truth = B.t_seq + B.t_off[p];
@@ -59,6 +83,10 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT) wf_kernel(WfBatch B, cons
     const bool reverse = reach && B.reverse[p];
     const int nd = qlen + tlen - 1, ring = wf_ring(x, o, e);
     int *v = B.scratch + B.scratch_off[p];
+    const int64_t ring_ints = (int64_t)WF_NW * ring * nd;
+    unsigned long long *x_first = (unsigned long long *)(v + ((ring_ints + 1) & ~(int64_t)1));   // cluster form: (diagonal << 32) | result of the first exit
+    int *x_best = (int *)(x_first + 1);
+    auto ld = [&](const int *q) -> int { return CL > 1 ? wf_ld_l2(q) : *q; };
     auto wf = [&](int kind, int slot, int d) -> int * { return v + ((int64_t)kind * ring + slot) * nd + d; };
     auto slot_of = [&](int slot, int back) { const int s = slot - back; return s < 0 ? s + ring : s; };
     auto inside = [&](int q, int k) { return q >= 0 && q < qlen && k + q >= 0 && k + q < tlen; };
@@ -67,15 +95,17 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT) wf_kernel(WfBatch B, cons
         if (NT == 32) { const bool r = __any_sync(FULL, f); __syncwarp(); return r; }
         return __syncthreads_or(f) != 0;
     };
-    for (int64_t i = t; i < (int64_t)WF_NW * ring * nd; i += NT) v[i] = WF_NONE;
-    if (NT != 32 && t == 0) { s_first = NO_HIT; s_best = 0; }
+    auto barrier = [&]() { if (NT == 32) __syncwarp(); else if (CL > 1) wf_cluster_sync(); else __syncthreads(); };
+    for (int64_t i = t; i < ring_ints; i += NTT) v[i] = WF_NONE;
+    if (NT != 32 && threadIdx.x == 0) { s_first = NO_HIT; s_best = 0; }
+    if (CL > 1 && t == 0) { *x_first = ~0ull; *x_best = 0; }
     const int main_diag = reach ? B.main_diag[p] : 0;
     const int stop_q = reach ? B.main_diag_start[p] - main_diag : 0;                // :2160
     const int max_score = reach ? B.max_score[p] : 0x7fffffff;
     int score = 0, slot = 0;
-    if (NT == 32) __syncwarp(); else __syncthreads();
+    barrier();
     if (t == 0) *wf(WF_M, slot, qlen - 1) = -1;                                       // :2166 / :1528: diagonal k = 0, before the first base
-    if (NT == 32) __syncwarp(); else __syncthreads();
+    barrier();
     // Diagonals any wavefront has reached so far: [dlo, dhi].  A score step reaches at most one more on either side (its
     // sources are the same diagonal and its two neighbours at earlier scores), everything outside still holds NONE from the
     // fill above - so a step runs over this range and not over all |query| + |truth| - 1 diagonals: a structural
@@ -83,15 +113,15 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT) wf_kernel(WfBatch B, cons
     int dlo = qlen - 1, dhi = qlen - 1;
     for (;;) {
         int hit_d = NO_HIT, hit_res = -1;
-        for (int d = dlo + t; d <= dhi; d += NT) {
+        for (int d = dlo + t; d <= dhi; d += NTT) {
             const int k = d + 1 - qlen;
             // the wavefronts of this score from those of earlier scores (:2225-2311, :1583-1650).  :2228-2232 clears I and D
             // only, the M wavefront of the slot is overwritten through >= tests; wf_swg_align starts every wavefront of a
             // new score empty (:1583-1587)
-            int mc = (reach || score == 0) ? *wf(WF_M, slot, d) : WF_NONE, ic = WF_NONE, dc = WF_NONE;
+            int mc = (reach || score == 0) ? ld(wf(WF_M, slot, d)) : WF_NONE, ic = WF_NONE, dc = WF_NONE;
             if (score > 0) {
                 if (score - x >= 0) {                                                 // substitution (:2239-2250)
-                    const int pv = x == 0 ? mc : *wf(WF_M, slot_of(slot, x), d);
+                    const int pv = x == 0 ? mc : ld(wf(WF_M, slot_of(slot, x), d));
                     if (pv != WF_NONE && pv + 1 < qlen && k + pv + 1 < tlen && pv + 1 >= mc) mc = pv + 1;
                 }
                 {                                                                     // gap opening (:2252-2275)
@@ -99,29 +129,29 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT) wf_kernel(WfBatch B, cons
                     if (score - cost >= 0) {
                         const int ps = slot_of(slot, cost);
                         if (d > 0) {
-                            const int pv = *wf(WF_M, ps, d - 1);
+                            const int pv = ld(wf(WF_M, ps, d - 1));
                             if (pv != WF_NONE && k + pv < tlen && pv >= dc) dc = pv;
                         }
                         if (d < nd - 1) {
-                            const int pv = *wf(WF_M, ps, d + 1);
+                            const int pv = ld(wf(WF_M, ps, d + 1));
                             if (pv != WF_NONE && pv + 1 < qlen && k + pv + 1 < tlen && k + pv + 1 >= 0 && pv + 1 >= ic) ic = pv + 1;
                         }
                     }
                 }
                 if (reverse && score - o >= 0) {                                      // reversed problem: leaving a gap costs o (:2277-2294)
                     const int ps = slot_of(slot, o);
-                    const int pi = o == 0 ? ic : *wf(WF_I, ps, d), pd = o == 0 ? dc : *wf(WF_D, ps, d);
+                    const int pi = o == 0 ? ic : ld(wf(WF_I, ps, d)), pd = o == 0 ? dc : ld(wf(WF_D, ps, d));
                     if (inside(pi, k) && pi > mc) mc = pi;
                     if (inside(pd, k) && pd > mc) mc = pd;
                 }
                 if (score - e >= 0) {                                                 // gap extension (:2296-2311)
                     const int ps = slot_of(slot, e);
                     if (d > 0) {
-                        const int pv = *wf(WF_D, ps, d - 1);
+                        const int pv = ld(wf(WF_D, ps, d - 1));
                         if (pv != WF_NONE && k + pv < tlen && pv >= dc) dc = pv;
                     }
                     if (d < nd - 1) {
-                        const int pv = *wf(WF_I, ps, d + 1);
+                        const int pv = ld(wf(WF_I, ps, d + 1));
                         if (pv != WF_NONE && pv + 1 < qlen && k + pv + 1 < tlen && k + pv + 1 >= 0 && pv + 1 >= ic) ic = pv + 1;
                     }
                 }
@@ -143,7 +173,16 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT) wf_kernel(WfBatch B, cons
                 if (q == qlen - 1 && q + k >= 0 && q + k < tlen - 1) { hit_d = d; hit_res = q + k; break; }        // :2208-2210
             } else if (q == qlen - 1 && q + k == tlen - 1) { hit_d = d; hit_res = score; break; }
         }
-        if (any_of(hit_d != NO_HIT)) {
+        if (CL > 1) {
+            // blocks of a cluster: the exits meet in scratch, everybody reads the outcome after the cluster barrier
+            if (hit_d != NO_HIT) atomicMin(x_first, ((unsigned long long)(unsigned)hit_d << 32) | (unsigned)hit_res);
+            wf_cluster_sync();
+            const unsigned long long key = wf_ld_l2(x_first);
+            if (key != ~0ull) {
+                if (t == 0) B.result[p] = (int)(unsigned)(key & 0xffffffffu);
+                return;
+            }
+        } else if (any_of(hit_d != NO_HIT)) {
             // the reference leaves at the FIRST diagonal in ascending order that reached an end
             int first;
             if (NT == 32) first = __reduce_min_sync(FULL, hit_d);
@@ -162,13 +201,17 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT) wf_kernel(WfBatch B, cons
     }
     // the score budget is spent: furthest truth index over everything still in the ring (:2316-2331)
     int best = 0;
-    for (int64_t i = t; i < (int64_t)WF_NW * ring * nd; i += NT) {
+    for (int64_t i = t; i < ring_ints; i += NTT) {
         const int d = (int)(i % nd);
-        const int q = v[i], k = d + 1 - qlen;
+        const int q = ld(v + i), k = d + 1 - qlen;
         if (inside(q, k) && k + q > best) best = k + q;
     }
     if (NT == 32) best = __reduce_max_sync(FULL, best);
-    else {
+    else if (CL > 1) {
+        if (best > 0) atomicMax(x_best, best);
+        wf_cluster_sync();
+        best = wf_ld_l2(x_best);
+    } else {
         atomicMax(&s_best, best);
         __syncthreads();
         best = s_best;
