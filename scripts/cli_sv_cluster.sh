@@ -9,7 +9,7 @@ for b in vcfdist_b200cli ${SKIP_REF:+-} vcfdist_ref; do
   [ "$b" = "-" ] && break
   mkdir -p /tmp/vs/$b; cd /tmp/vs/$b
   echo "== $b"; SECONDS=0
-  VD_DROPIN_TIMES=1 timeout 900 $GRAFT_REPO_ROOT/oracle/_ref/$b /tmp/vs/in/query.vcf /tmp/vs/in/truth.vcf /tmp/vs/in/ref.fa -p /tmp/vs/$b/ -v 1 -t 16 $EXTRA 2>&1 | grep -E "\[[0-9]\] |ERROR|GPU clustering|vd_wf_batch"
+  VD_DROPIN_TIMES=1 timeout 900 $GRAFT_REPO_ROOT/oracle/_ref/$b /tmp/vs/in/query.vcf /tmp/vs/in/truth.vcf /tmp/vs/in/ref.fa -p /tmp/vs/$b/ -v 1 -t 16 $EXTRA 2>&1 | grep -E "\[[0-9]\] |ERROR|GPU clustering|GPU precision|vd_wf_batch"
   echo "wall ${SECONDS} s"
   cd $GRAFT_REPO_ROOT
 done
