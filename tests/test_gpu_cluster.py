@@ -188,3 +188,23 @@ def test_distance_alignment_known_answers(engine):
         for c, s, cg in zip(cs, sc, cigs):
             so, co = checkers.swg_cigar_oracle(*c)
             assert so == s and (co[: len(cg)] == cg).all(), c
+
+
+def test_distance_alignment_in_rounds(engine):
+    """vd_swg_align_batch with a storage budget far below what the batch needs: the alignments run in rounds over the same
+    storage; scores and CIGARs equal to those of an engine with room for everything, scores equal to the C restatement.  An
+    alignment that alone exceeds the budget is refused (VD_E_NOMEM), nothing is computed on the CPU instead."""
+    small = capi.Engine(0, scratch_bytes=3_000_000)
+    rng = np.random.default_rng(17)
+    pairs = [TR.random_pair(rng)[:2] for _ in range(400)]
+    q, t = [c[0] for c in pairs], [c[1] for c in pairs]
+    sa, ca = small.swg_align_batch(q, t, 2, 3, 1)
+    sb, cb = engine.swg_align_batch(q, t, 2, 3, 1)
+    assert (np.asarray(sa) == np.asarray(sb)).all() and all((a == b).all() for a, b in zip(ca, cb))
+    assert (np.asarray(sa) == np.array([checkers.swg_score_oracle(a, b, 2, 3, 1) for a, b in pairs])).all()
+    need = sum(5 * (int(s) + 1) * 3 * (len(a) + len(b) - 1) for s, (a, b) in zip(sa, pairs))
+    assert need > 2 * 3_000_000                                   # so there were at least three rounds
+    big = b"ACGT" * 200
+    with pytest.raises(capi.VdError):
+        small.swg_align_batch([big], [big[1:400] + b"T" * 300], 2, 3, 1)
+    small.close()

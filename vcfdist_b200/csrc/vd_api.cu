@@ -1098,41 +1098,61 @@ extern "C" int vd_swg_align_batch(vd_handle *h, int n, const int64_t *q_off, con
     if (rc != VD_OK) return rc;
     cudaStream_t st = h->stream;
     const int64_t qb = q_off[n], tb = t_off[n];
-    std::vector<int64_t> boff((size_t)n + 1);
-    boff[0] = 0;
-    for (int i = 0; i < n; i++)
-        boff[i + 1] = boff[i] + wf_cigar_bytes((int)(q_off[i + 1] - q_off[i]), (int)(t_off[i + 1] - t_off[i]), score[i]);
-    if (boff[n] > h->scratch_budget) return fail(h, VD_E_NOMEM, "alignment wavefronts need %lld bytes", (long long)boff[n]);
+    // Every score of an alignment keeps its wavefronts and flags: a structural variant's alignment takes gigabytes.  The batch
+    // runs in rounds of consecutive problems whose storage fits the budget together; rounds follow each other on the stream
+    // and reuse the same storage.  boff[i] = offset of problem i inside its round.
+    const int64_t cigar_bytes = ((4 * (qb + tb) + 15) / 16) * 16;
+    const int64_t budget = h->scratch_budget - cigar_bytes;
+    std::vector<int64_t> boff((size_t)n + 1, 0);
+    std::vector<int> round_begin{0};
+    int64_t at_byte = 0, round_max = 0;
+    for (int i = 0; i < n; i++) {
+        const int64_t need = wf_cigar_bytes((int)(q_off[i + 1] - q_off[i]), (int)(t_off[i + 1] - t_off[i]), score[i]);
+        if (need > budget) return fail(h, VD_E_NOMEM, "alignment %d: its wavefronts need %lld bytes", i, (long long)need);
+        if (at_byte + need > budget) { round_begin.push_back(i); at_byte = 0; }
+        boff[i] = at_byte;
+        at_byte += need;
+        round_max = std::max(round_max, at_byte);
+    }
+    round_begin.push_back(n);
     // vd_wf_batch left offsets and strings staged in wf_in: lay the same block out again (same sizes)
     size_t o_qoff = 0, o_toff = o_qoff + 8 * (size_t)(n + 1), o_soff = o_toff + 8 * (size_t)(n + 1), o_md = o_soff + 8 * (size_t)(n + 1);
     size_t o_mds = o_md + 4 * (size_t)n, o_ms = o_mds + 4 * (size_t)n, o_res = o_ms + 4 * (size_t)n, o_rev = o_res + 4 * (size_t)n;
     size_t o_q = (o_rev + n + 15) & ~(size_t)15, o_t = (o_q + qb + 15) & ~(size_t)15;
     u8 *d = (u8 *)h->wf_in.p;
-    CK(h->wf_scratch.ensure((size_t)boff[n] + 4 * (size_t)(qb + tb) + 64));
+    CK(h->wf_scratch.ensure((size_t)(cigar_bytes + round_max) + 64));
     CK(cudaMemcpyAsync(d + o_soff, boff.data(), 8 * (size_t)(n + 1), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d + o_ms, score, 4 * (size_t)n, cudaMemcpyHostToDevice, st));
-    int32_t *d_cigar = (int32_t *)((u8 *)h->wf_scratch.p + ((boff[n] + 15) / 16) * 16);
+    int32_t *d_cigar = (int32_t *)h->wf_scratch.p;
     WfCigarBatch B{n, (const int64_t *)(d + o_qoff), (const int64_t *)(d + o_toff), d + o_q, d + o_t, (const int32_t *)(d + o_ms),
-                   (const int64_t *)(d + o_soff), (u8 *)h->wf_scratch.p, d_cigar, (int32_t *)(d + o_res), sub, open, extend};
-    // warp or block per problem by the width its wavefront reached (as vd_wf_batch; the score is known here)
+                   (const int64_t *)(d + o_soff), (u8 *)h->wf_scratch.p + cigar_bytes, d_cigar, (int32_t *)(d + o_res), sub, open, extend};
+    // warp or block per problem by the width its wavefront reached (as vd_wf_batch; the score is known here); sel holds, round
+    // after round, the warp problems, the block problems, the wide ones
     size_t o_sel = (o_t + tb + 15) & ~(size_t)15;
     std::vector<int> sel((size_t)n);
-    int n_warp = 0, n_block = 0, n_wide = 0;
-    {
-        std::vector<u8> form((size_t)n);
-        for (int i = 0; i < n; i++) {
-            const int64_t width = std::min<int64_t>((q_off[i + 1] - q_off[i]) + (t_off[i + 1] - t_off[i]) - 1, 2 * (int64_t)std::max(score[i], 0) + 1);
-            form[i] = width >= 4 * (int64_t)h->wf_block_min ? 2 : width >= h->wf_block_min ? 1 : 0;
-            (form[i] == 2 ? n_wide : form[i] == 1 ? n_block : n_warp)++;
-        }
-        int at[3] = {0, n_warp, n_warp + n_block};
-        for (int i = 0; i < n; i++) sel[(size_t)at[form[i]]++] = i;
+    std::vector<u8> form((size_t)n);
+    for (int i = 0; i < n; i++) {
+        const int64_t width = std::min<int64_t>((q_off[i + 1] - q_off[i]) + (t_off[i + 1] - t_off[i]) - 1, 2 * (int64_t)std::max(score[i], 0) + 1);
+        form[i] = width >= 4 * (int64_t)h->wf_block_min ? 2 : width >= h->wf_block_min ? 1 : 0;
+    }
+    std::vector<int> cnt(3 * (round_begin.size() - 1), 0);
+    for (size_t r = 0; r + 1 < round_begin.size(); r++) {
+        int *c = &cnt[3 * r];
+        for (int i = round_begin[r]; i < round_begin[r + 1]; i++) c[form[i]]++;
+        int at[3] = {round_begin[r], round_begin[r] + c[0], round_begin[r] + c[0] + c[1]};
+        for (int i = round_begin[r]; i < round_begin[r + 1]; i++) sel[(size_t)at[form[i]]++] = i;
     }
     CK(cudaMemcpyAsync(d + o_sel, sel.data(), 4 * (size_t)n, cudaMemcpyHostToDevice, st));
     const int *d_sel = (const int *)(d + o_sel);
-    if (n_wide > 0) VD_LAUNCH(wf_cigar_kernel<WF_WIDE>, n_wide, WF_WIDE, 0, st, B, d_sel + n_warp + n_block, n_wide);
-    if (n_block > 0) VD_LAUNCH(wf_cigar_kernel<WF_BLOCK>, n_block, WF_BLOCK, 0, st, B, d_sel + n_warp, n_block);
-    if (n_warp > 0) VD_LAUNCH(wf_cigar_kernel<32>, (n_warp + 3) / 4, 128, 0, st, B, d_sel, n_warp);
+    for (size_t r = 0; r + 1 < round_begin.size(); r++) {
+        const int n_warp = cnt[3 * r], n_block = cnt[3 * r + 1], n_wide = cnt[3 * r + 2];
+        const int *rs = d_sel + round_begin[r];
+        if (n_wide > 0) VD_LAUNCH(wf_cigar_kernel<WF_WIDE>, n_wide, WF_WIDE, 0, st, B, rs + n_warp + n_block, n_wide);
+        if (n_block > 0) VD_LAUNCH(wf_cigar_kernel<WF_BLOCK>, n_block, WF_BLOCK, 0, st, B, rs + n_warp, n_block);
+        if (n_warp > 0) VD_LAUNCH(wf_cigar_kernel<32>, (n_warp + 3) / 4, 128, 0, st, B, rs, n_warp);
+    }
+    if (getenv("VD_WF_STATS"))
+        fprintf(stderr, "vd_swg_align_batch: %d alignments in %d round(s), %.1f MB of wavefronts per round at most\n", n, (int)round_begin.size() - 1, round_max / 1e6);
     CK(cudaMemcpyAsync(score, d + o_res, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(cigar, d_cigar, 4 * (size_t)(qb + tb), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
