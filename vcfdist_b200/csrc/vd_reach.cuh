@@ -113,50 +113,50 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT) wf_kernel(WfBatch B, cons
     int dlo = qlen - 1, dhi = qlen - 1;
     for (;;) {
         int hit_d = NO_HIT, hit_res = -1;
+        // rows of the ring this score reads and writes (index arithmetic once per score, not per diagonal)
+        const int cost_open = reverse ? e : o + e;
+        int *const Mc = wf(WF_M, slot, 0), *const Ic = wf(WF_I, slot, 0), *const Dc = wf(WF_D, slot, 0);
+        const int *const Mx = wf(WF_M, slot_of(slot, x), 0), *const Mg = wf(WF_M, slot_of(slot, cost_open), 0);
+        const int *const Io = wf(WF_I, slot_of(slot, o), 0), *const Do = wf(WF_D, slot_of(slot, o), 0);
+        const int *const Ie = wf(WF_I, slot_of(slot, e), 0), *const De = wf(WF_D, slot_of(slot, e), 0);
+        const bool has_x = score > 0 && score - x >= 0, has_g = score > 0 && score - cost_open >= 0;
+        const bool has_o = score > 0 && reverse && score - o >= 0, has_e = score > 0 && score - e >= 0;
         for (int d = dlo + t; d <= dhi; d += NTT) {
             const int k = d + 1 - qlen;
             // the wavefronts of this score from those of earlier scores (:2225-2311, :1583-1650).  :2228-2232 clears I and D
             // only, the M wavefront of the slot is overwritten through >= tests; wf_swg_align starts every wavefront of a
             // new score empty (:1583-1587)
-            int mc = (reach || score == 0) ? ld(wf(WF_M, slot, d)) : WF_NONE, ic = WF_NONE, dc = WF_NONE;
-            if (score > 0) {
-                if (score - x >= 0) {                                                 // substitution (:2239-2250)
-                    const int pv = x == 0 ? mc : ld(wf(WF_M, slot_of(slot, x), d));
-                    if (pv != WF_NONE && pv + 1 < qlen && k + pv + 1 < tlen && pv + 1 >= mc) mc = pv + 1;
-                }
-                {                                                                     // gap opening (:2252-2275)
-                    const int cost = reverse ? e : o + e;
-                    if (score - cost >= 0) {
-                        const int ps = slot_of(slot, cost);
-                        if (d > 0) {
-                            const int pv = ld(wf(WF_M, ps, d - 1));
-                            if (pv != WF_NONE && k + pv < tlen && pv >= dc) dc = pv;
-                        }
-                        if (d < nd - 1) {
-                            const int pv = ld(wf(WF_M, ps, d + 1));
-                            if (pv != WF_NONE && pv + 1 < qlen && k + pv + 1 < tlen && k + pv + 1 >= 0 && pv + 1 >= ic) ic = pv + 1;
-                        }
-                    }
-                }
-                if (reverse && score - o >= 0) {                                      // reversed problem: leaving a gap costs o (:2277-2294)
-                    const int ps = slot_of(slot, o);
-                    const int pi = o == 0 ? ic : ld(wf(WF_I, ps, d)), pd = o == 0 ? dc : ld(wf(WF_D, ps, d));
-                    if (inside(pi, k) && pi > mc) mc = pi;
-                    if (inside(pd, k) && pd > mc) mc = pd;
-                }
-                if (score - e >= 0) {                                                 // gap extension (:2296-2311)
-                    const int ps = slot_of(slot, e);
-                    if (d > 0) {
-                        const int pv = ld(wf(WF_D, ps, d - 1));
-                        if (pv != WF_NONE && k + pv < tlen && pv >= dc) dc = pv;
-                    }
-                    if (d < nd - 1) {
-                        const int pv = ld(wf(WF_I, ps, d + 1));
-                        if (pv != WF_NONE && pv + 1 < qlen && k + pv + 1 < tlen && k + pv + 1 >= 0 && pv + 1 >= ic) ic = pv + 1;
-                    }
-                }
-                *wf(WF_I, slot, d) = ic; *wf(WF_D, slot, d) = dc;
+            int mc = (reach || score == 0) ? ld(Mc + d) : WF_NONE, ic = WF_NONE, dc = WF_NONE;
+            if (has_x) {                                                              // substitution (:2239-2250)
+                const int pv = x == 0 ? mc : ld(Mx + d);
+                if (pv != WF_NONE && pv + 1 < qlen && k + pv + 1 < tlen && pv + 1 >= mc) mc = pv + 1;
             }
+            if (has_g) {                                                              // gap opening (:2252-2275)
+                if (d > 0) {
+                    const int pv = ld(Mg + d - 1);
+                    if (pv != WF_NONE && k + pv < tlen && pv >= dc) dc = pv;
+                }
+                if (d < nd - 1) {
+                    const int pv = ld(Mg + d + 1);
+                    if (pv != WF_NONE && pv + 1 < qlen && k + pv + 1 < tlen && k + pv + 1 >= 0 && pv + 1 >= ic) ic = pv + 1;
+                }
+            }
+            if (has_o) {                                                              // reversed problem: leaving a gap costs o (:2277-2294)
+                const int pi = o == 0 ? ic : ld(Io + d), pd = o == 0 ? dc : ld(Do + d);
+                if (inside(pi, k) && pi > mc) mc = pi;
+                if (inside(pd, k) && pd > mc) mc = pd;
+            }
+            if (has_e) {                                                              // gap extension (:2296-2311)
+                if (d > 0) {
+                    const int pv = ld(De + d - 1);
+                    if (pv != WF_NONE && k + pv < tlen && pv >= dc) dc = pv;
+                }
+                if (d < nd - 1) {
+                    const int pv = ld(Ie + d + 1);
+                    if (pv != WF_NONE && pv + 1 < qlen && k + pv + 1 < tlen && k + pv + 1 >= 0 && pv + 1 >= ic) ic = pv + 1;
+                }
+            }
+            if (score > 0) { Ic[d] = ic; Dc[d] = dc; }
             // gaps are left for free at the score they were reached with (:2171-2184, :1533-1547); not in the reversed problem
             int q = mc;
             if (!reverse) {
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(NT == 32 ? 128 : NT) wf_kernel(WfBatch B, cons
             while ((!reach || k != main_diag || q + 1 < stop_q) && q != WF_NONE && k + q >= -1 &&
                    q < qlen - 1 && k + q < tlen - 1 && query[q + 1] == truth[k + q + 1])
                 q++;
-            *wf(WF_M, slot, d) = q;
+            Mc[d] = q;
             if (reach) {
                 if (q + k == tlen - 1) { hit_d = d; hit_res = tlen - 1; break; }                                   // :2205-2207
                 if (q == qlen - 1 && q + k >= 0 && q + k < tlen - 1) { hit_d = d; hit_res = q + k; break; }        // :2208-2210
