@@ -58,6 +58,22 @@ def test_cli_outputs_identical(tmp_path, seed, extra):
             assert filecmp.cmp(os.path.join(c, f), os.path.join(b, f), shallow=False), f
 
 
+def test_cli_sv_bearing_input_default_clustering(tmp_path, monkeypatch):
+    """Structural variants to 600 bp with the default (biwfa) clustering and --distance: the cluster-growing stage and the
+    alignment pass meet problems hundreds to thousands of diagonals wide - with the form thresholds lowered here every form
+    of the wavefront kernels (warp, 256 threads, 1024 threads, cluster of eight blocks) runs inside the CLI - and the
+    precision/recall stage its long path.  Same files as the reference, byte for byte."""
+    q, t, fa = vcfgen.generate(str(tmp_path / "in"), seed=9, contig_len=40_000, n_contigs=2, sv_rate=0.03, sv_max=600)
+    c = str(tmp_path / "refB"); b = str(tmp_path / "gpu")
+    run(REFB, q, t, fa, c, ["--distance"])
+    monkeypatch.setenv("VD_WF_BLOCK_MIN", "64")
+    monkeypatch.setenv("VD_WF_CLUSTER_MIN", "700")
+    run(CLI, q, t, fa, b, ["--distance"])
+    for f in FILES + ["distance.tsv", "distance-summary.tsv", "edits.tsv"]:
+        assert filecmp.cmp(os.path.join(c, f), os.path.join(b, f), shallow=False), f
+    assert vcf_body(os.path.join(c, "summary.vcf")) == vcf_body(os.path.join(b, "summary.vcf"))
+
+
 @pytest.mark.parametrize("name", ["demo", "adv_11", "sv_21"])
 def test_dropin_at_the_function_seam(name):
     """precision_recall_threads_wrapper of the drop-in (parallel packer, vd_run_packed, host float step, parallel
