@@ -3,13 +3,14 @@
 // (src/cluster.cpp:954-1263) spends its time in - the reference runs them one (cluster, direction) after the
 // other on one thread, which made clustering the wall-clock bottleneck on SV input.
 //
-// One WARP per problem, diagonals across lanes.  Diagonal index d in [0, nd), nd = |query| + |truth| - 1, stands
-// for k = d + 1 - |query| (truth index minus query index); three wavefront kinds (M, I, D) hold per diagonal the
-// furthest QUERY index reached, NONE when the diagonal is not reached; only the last max(x, o+e) + 1 scores are
-// kept (a ring in HBM scratch, L2-resident for cluster-sized problems).  A score step reads other diagonals only
-// from EARLIER scores, so all diagonals of a step are independent; the free extension along matches is a per-lane
-// byte-compare loop; the exits of the reference (first diagonal, in ascending order, that reaches the end of a
-// string) are taken by warp vote in chunks of 32 diagonals.
+// Diagonals across the threads of a problem: a warp for the many cluster-sized problems, a 256- or 1024-thread block or a
+// thread-block cluster of eight blocks for the few whose wavefront grows wide (see wf_kernel).  Diagonal index d in [0, nd),
+// nd = |query| + |truth| - 1, stands for k = d + 1 - |query| (truth index minus query index); three wavefront kinds (M, I, D)
+// hold per diagonal the furthest QUERY index reached, NONE when the diagonal is not reached; only the last max(x, o+e) + 1
+// scores are kept (a ring in HBM scratch, L1/L2-resident).  A score step reads other diagonals only from EARLIER scores, so
+// all diagonals of a step are independent and a step needs one barrier; the free extension along matches is a per-thread
+// byte-compare loop; the exit of the reference (the first diagonal, in ascending order, that reaches the end of a string) is
+// the minimum over the threads that saw one.
 #pragma once
 #include "vd_common.cuh"
 
